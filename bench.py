@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""Benchmark of the robustness-evaluation hot path (BASELINE.json metric: trace-samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl b200|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic traces: the fused
+formula kernel over ``signal[B, T, D]`` (plus the gradient kernel for the forward+backward
+workloads).  ``value`` is whole-job trace-samples/sec with the inputs resident in HBM;
+``e2e`` is the same metric through the public API with pinned HOST buffers (H2D copy of
+the batch and D2H read of the mean robustness inside the timed region).
+
+Under torchrun (N > 1) every rank evaluates its own shard of the batch (weak scaling: the
+per-GPU batch is fixed) and the mean robustness is finished by one 16-byte NCCL
+all-reduce; the time is the max over ranks of the device-timed region.
+
+``--impl reference`` times the CPU implementation of the same path: the oracle port of the
+reference's per-(trace, t) recursion (oracle/scalar.py; the Python reference itself cannot
+travel to the GPU box), on all host cores, on a bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from pystl_b200.formula import BASELINE_SHAPES, BASELINE_SPECS, from_spec  # noqa: E402
+
+METRIC = "trace-samples/sec"
+UNIT = "trace-samples/s"
+
+# semantics, kwargs, does the workload include the backward pass
+WORKLOADS = {
+    "cfg1": ("classical", {}, False),
+    "cfg2": ("smooth", {"temperature": 1.0}, True),
+    "cfg3": ("agm", {}, True),
+    "cfg3d": ("dgmsr", {"eps": 1e-8, "p": 1}, True),
+    "cfg4": ("cumulative", {}, False),
+    "cfg5": ("classical", {}, False),
+}
+DESCR = {
+    "cfg1": "Classic G[0,10](x>0) & F[0,5](y<1), 1024x1000x2, forward",
+    "cfg2": "Smooth tau=1 G[0,50](x>0) | F[0,20](y<0.5), 65536x4096x2, forward+backward",
+    "cfg3": "AGM G[0,100](F[0,10](x>0) & !(y>2)), 32768x8192x2, forward+backward",
+    "cfg3d": "D-GMSR G[0,100](F[0,10](x>0) & !(y>2)), 32768x8192x2, forward+backward",
+    "cfg4": "Cumulative G[0,200]((x>0) U[0,64] (y>1)), 16384x16384x4, forward",
+    "cfg5": "Classic 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
+}
+
+
+def algorithmic_bytes_per_sample(cfg: str, backward: bool) -> float:
+    """forward 4*D_ref + 4*C_out; backward 4*C_out(grad_out, 0 when the
+    constant cotangent is fused) + 4*D_ref (re-read) + 4*D (grad write)."""
+    _, _, D = BASELINE_SHAPES[cfg]
+    d_ref = {"cfg1": 2, "cfg2": 2, "cfg3": 2, "cfg3d": 2, "cfg4": 2, "cfg5": 8}[cfg]
+    c_out = 2 if cfg == "cfg4" else 1
+    fwd = 4 * d_ref + 4 * c_out
+    if not backward:
+        return fwd
+    return fwd + 4 * d_ref + 4 * D  # constant cotangent fused: no grad_out read
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    QUERY = (
+        "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+        "clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                    capture_output=True, text=True, timeout=5,
+                ).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self) -> dict:
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "reasons": reasons,
+            "samples": len(self.rows),
+        }
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    cfg, lo, hi, T_eval, n_t, seed = args
+    from oracle import scalar
+
+    sem_name, kw, _ = WORKLOADS[cfg]
+    _, T, D = BASELINE_SHAPES[cfg]
+    phi = from_spec(BASELINE_SPECS[cfg])
+    sem = scalar.make(sem_name, **kw)
+    rng = np.random.default_rng(seed)
+    done = 0
+    t0 = time.perf_counter()
+    for b in range(lo, hi):
+        sig = rng.standard_normal((T_eval, D)).astype(np.float32).astype(np.float64)
+        ts = rng.integers(0, T_eval, size=n_t)
+        for t in ts:
+            scalar.evaluate_sliced(phi, sig, sem, int(t))
+            done += 1
+    return done, time.perf_counter() - t0
+
+
+def cpu_port_throughput(cfg: str, budget_s: float, cores: int) -> dict:
+    """Oracle port of the reference recursion on a bounded sample: (trace, t) pairs per second.
+    One evaluation = one trace-sample of the forward pass (the reference has no batched path)."""
+    import multiprocessing as mp
+
+    _, T, _ = BASELINE_SHAPES[cfg]
+    T_eval = min(T, 1024)
+    # calibrate on one core
+    n, dt = _cpu_worker((cfg, 0, 1, T_eval, 4, 0))
+    per = dt / max(n, 1)
+    total = max(int(budget_s / per), 8) * cores
+    n_t = 8
+    traces = max(total // n_t, cores)
+    chunks = [(cfg, i * traces // cores, (i + 1) * traces // cores, T_eval, n_t, 100 + i) for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, chunks)
+    else:
+        res = [_cpu_worker(chunks[0])]
+    wall = time.perf_counter() - t0
+    done = sum(r[0] for r in res)
+    return {
+        "value": done / wall,
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{done} (trace,t) pairs: {traces} traces x {n_t} random t, horizon {T_eval} of {T}, "
+        f"slice identity (SURVEY A1), forward only, float64",
+    }
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = args.workload
+    cores = os.cpu_count() or 1
+    steps = max(args.steps, 1)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_port_throughput(cfg, 0.5, cores)
+    t0 = time.perf_counter()
+    base = None
+    for _ in range(steps):
+        base = cpu_port_throughput(cfg, max(20.0 / steps, 1.0), cores)
+        vals.append(base["value"])
+    wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    base["value"] = value
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{cfg}: {DESCR[cfg]}", "note": "CPU oracle port of the reference recursion, bounded sample"},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200(args) -> None:
+    import torch.distributed as dist
+
+    import pystl_b200
+    from pystl_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = args.workload
+    sem_name, kw, with_bwd = WORKLOADS[cfg]
+    if args.forward_only:
+        with_bwd = False
+    B, T, D = BASELINE_SHAPES[cfg]
+    if args.batch:
+        B = args.batch
+    if cfg == "cfg5" and not args.batch:
+        # 2^20 traces are sharded over 8 GPUs in the BASELINE config: 2^17 per GPU
+        B = (1 << 20) // 8
+    phi = from_spec(BASELINE_SPECS[cfg])
+    sem = pystl_b200.create_semantics(sem_name, backend="b200", **kw)
+    capi.lib()  # fail loudly if the CUDA library is missing
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    signal = torch.randn((B, T, D), generator=gen, device=dev, dtype=torch.float32)
+    cf = sem.compile(phi, D)
+    C_out = sem.out_channels
+    out = torch.empty((B, T, C_out), dtype=torch.float32, device=dev)
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+    grad = torch.empty_like(signal) if with_bwd else None
+    stream = torch.cuda.current_stream(dev)
+    lib = capi.lib()
+    plan = sem.plan(phi, T, D)
+    n_valid = B * max(T - plan["start_slack"], 0)
+    launches = 0
+
+    def step() -> int:
+        n = 0
+        acc.zero_()
+        rc = lib.pystl_b200_eval_forward(cf.ptr(), signal.data_ptr(), B, T, D, out.data_ptr(), acc.data_ptr(), stream.cuda_stream)
+        capi.raise_for(rc, lib.pystl_b200_last_error())
+        n += 1
+        if with_bwd:
+            # loss = mean robustness over the whole (sharded) batch: constant cotangent 1 / (world * n_valid)
+            rc = lib.pystl_b200_eval_backward(
+                cf.ptr(), signal.data_ptr(), B, T, D, None, 1.0 / (world * n_valid), grad.data_ptr(), stream.cuda_stream
+            )
+            capi.raise_for(rc, lib.pystl_b200_last_error())
+            n += 1
+        if world > 1:
+            dist.all_reduce(acc)
+        return n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # kernel-only time of the forward kernel (the dominant one) for the roofline
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for i in range(args.steps):
+        launches += step()
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = t_start.elapsed_time(t_end)
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    samples_per_step = world * B * T
+    value = samples_per_step * args.steps / (ms * 1e-3)
+
+    # dominant kernel alone (forward), CUDA events on the launching stream
+    fwd_ms = []
+    for a, b_ in ev:
+        a.record(stream)
+        rc = lib.pystl_b200_eval_forward(cf.ptr(), signal.data_ptr(), B, T, D, out.data_ptr(), None, stream.cuda_stream)
+        b_.record(stream)
+    torch.cuda.synchronize(dev)
+    fwd_ms = [a.elapsed_time(b_) for a, b_ in ev]
+    k_ms = float(np.mean(fwd_ms))
+    peak, peak_src = measured_peak_gbs()
+    bytes_per_launch = algorithmic_bytes_per_sample(cfg, False) * B * T
+    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm",
+        "kernel": f"fwd_kernel<{sem_name}>",
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_sample": algorithmic_bytes_per_sample(cfg, False),
+        "kernel_ms": k_ms,
+    }
+
+    # end to end through the public API with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        Bh = min(B, max(1, (1 << 28) // (T * D)))  # <= 1 GiB of pinned input per step
+        host = torch.empty((Bh, T, D), dtype=torch.float32).pin_memory()
+        host.copy_(signal[:Bh].cpu())
+        e_steps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            x = host.to(dev, non_blocking=True)
+            if with_bwd:
+                x.requires_grad_(True)
+                rho = sem.robustness_trace(phi, x)
+                loss = rho.mean() if C_out == 1 else (rho.pos + rho.neg).mean()
+                loss.backward()
+                return float(loss.detach().cpu()), x.grad
+            return float(sem.mean_robustness(phi, x).cpu()), None
+
+        try:
+            e2e_step()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                e2e_step()
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            e2e = {
+                "value": world * Bh * T * e_steps / dt,
+                "unit": UNIT,
+                "h2d_bytes_per_step": Bh * T * D * 4,
+                "d2h_bytes_per_step": 8,
+                "traces_per_step": Bh,
+            }
+        except NotImplementedError as exc:
+            e2e = {"value": None, "unit": UNIT, "error": str(exc)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_port_throughput(cfg, args.cpu_seconds, 1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": f"{cfg}: {DESCR[cfg]}",
+                "traces_per_gpu": B,
+                "horizon": T,
+                "channels": D,
+                "pass": "forward+backward" if with_bwd else "forward",
+                "l2": "inputs larger than L2 (no flush needed)" if B * T * D * 4 > (1 << 28) else "input fits L2 (CPU-comparison config)",
+                "plan": plan,
+            },
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override traces per GPU")
+    ap.add_argument("--forward-only", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,158 @@
+/*
+ * pystl_b200 -- C ABI of the B200-native robustness evaluator.
+ *
+ * This is the drop-in boundary for PySTL's robustness hot path.  The reference
+ * (ericpalto/PySTL 1.0.0) is pure Python and has no native interface, so every
+ * entry point below names the Python interface it stands in for:
+ *
+ *   reference interface                                   | entry point here
+ *   ------------------------------------------------------+----------------------------------
+ *   Formula.evaluate(signal, semantics, t)                | pystl_b200_eval_forward
+ *     pystl/api.py:142-302 (recursive driver) with the    |   (all t of all traces in one call)
+ *     operator interface pystl/semantics/base.py:18-75    |
+ *   backward of the torch backend (autograd through       | pystl_b200_eval_backward
+ *     pystl/torch/semantics.py:87-587), and               |
+ *     DgmsrSemantics.evaluate_with_grad,                  |
+ *     pystl/semantics/dgmsr.py:120-274                    |
+ *   Interval / _window_indices clipping, api.py:29-54;    | pystl_b200_plan (validity, tiling)
+ *     "window is empty" ValueError, api.py:218-221        |
+ *   create_semantics(**kwargs): temperature / eps / p,    | pystl_formula_t.{temperature,eps,p}
+ *     pystl/semantics/__init__.py:108-125                 |
+ *
+ * Conventions: plain pointers and sizes only; the CALLER owns every buffer
+ * (kernels never allocate); device pointers unless the name says host; all
+ * launches are asynchronous on `stream` (a cudaStream_t passed as void*);
+ * functions return 0 on success or a negative pystl_status; the message for
+ * the last failure on the calling thread is pystl_b200_last_error().
+ *
+ * The binding a maintainer adds on the reference side (ctypes) is shown in
+ * INTEGRATION.md; pystl_b200/capi.py is that binding.
+ */
+#ifndef PYSTL_B200_H
+#define PYSTL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYSTL_B200_ABI_VERSION 1
+#define PYSTL_MAX_TERMS 8 /* affine terms per predicate */
+
+typedef enum pystl_status {
+  PYSTL_OK = 0,
+  PYSTL_E_INVALID = -1,     /* malformed formula / arguments (Python: ValueError)            */
+  PYSTL_E_UNSUPPORTED = -2, /* valid but outside this build's limits (NotImplementedError)  */
+  PYSTL_E_CUDA = -3         /* a CUDA call failed                                            */
+} pystl_status;
+
+/* registry syntaxes, pystl/semantics/__init__.py:47-52 */
+typedef enum pystl_semantics {
+  PYSTL_SEM_CLASSIC = 0,    /* semantics/classic.py    */
+  PYSTL_SEM_SMOOTH = 1,     /* semantics/smooth.py     */
+  PYSTL_SEM_CUMULATIVE = 2, /* semantics/cumulative.py */
+  PYSTL_SEM_AGM = 3,        /* semantics/agm.py        */
+  PYSTL_SEM_DGMSR = 4       /* semantics/dgmsr.py, _dgmsr.py */
+} pystl_semantics;
+
+/* node classes of pystl/api.py:129-302 */
+typedef enum pystl_node_kind {
+  PYSTL_NODE_PRED = 0,
+  PYSTL_NODE_NOT = 1,
+  PYSTL_NODE_AND = 2,
+  PYSTL_NODE_OR = 3,
+  PYSTL_NODE_ALWAYS = 4,
+  PYSTL_NODE_EVENTUALLY = 5,
+  PYSTL_NODE_UNTIL = 6
+} pystl_node_kind;
+
+/* One formula node.  Nodes are listed in post-order (children before parents);
+ * the root is the last node. */
+typedef struct pystl_node {
+  int32_t kind;       /* pystl_node_kind */
+  int32_t n_children; /* PRED 0, NOT 1, AND/OR n, ALWAYS/EVENTUALLY 1, UNTIL 2 (left, right) */
+  int32_t child_off;  /* first entry of this node's children in pystl_formula_t.children */
+  int32_t a;          /* Interval.start (api.py:33) */
+  int32_t b;          /* Interval.end, -1 = None = up to the horizon (api.py:34,51) */
+  int32_t pred;       /* PRED: index into pystl_formula_t.preds */
+  int32_t w_off;      /* weights: AND/OR per child; ALWAYS/EVENTUALLY per window position;
+                         UNTIL weights_left.  -1 = None (uniform) */
+  int32_t w_len;
+  int32_t w2_off;     /* UNTIL weights_right, -1 = None */
+  int32_t w2_len;
+  float wp0, wp1;     /* UNTIL weights_pair (api.py:265), default (1, 1) */
+} pystl_node_t;
+
+/* Affine predicate rho(t) = bias + sum_k coeff[k] * signal[t, channel[k]]
+ * (the structured form of Predicate.fn, api.py:133-143). */
+typedef struct pystl_pred {
+  int32_t n_terms;
+  int32_t channel[PYSTL_MAX_TERMS];
+  float coeff[PYSTL_MAX_TERMS];
+  float bias;
+} pystl_pred_t;
+
+typedef struct pystl_formula {
+  int32_t semantics;  /* pystl_semantics */
+  float temperature;  /* smooth: SmoothRobustSemantics(temperature=), smooth.py:28 */
+  float eps;          /* dgmsr: DgmsrSemantics(eps=), dgmsr.py:31 */
+  int32_t p;          /* dgmsr: DgmsrSemantics(p=),   dgmsr.py:31 */
+  int32_t n_nodes;
+  const pystl_node_t* nodes;
+  int32_t n_children;
+  const int32_t* children; /* node indices */
+  int32_t n_preds;
+  const pystl_pred_t* preds;
+  int32_t n_weights;
+  const float* weights;
+} pystl_formula_t;
+
+/* What pystl_b200_plan reports (host only, no GPU needed). */
+typedef struct pystl_plan {
+  int32_t out_channels;  /* 1; 2 for cumulative (pos, neg), cumulative.py:13-18 */
+  int32_t lookahead;     /* samples after t the value at t depends on; -1 = unbounded */
+  int32_t start_slack;   /* outputs at t > T-1-start_slack have an empty window: the
+                            reference raises ValueError (api.py:218-221); written as NaN */
+  int32_t raises_always; /* 1: an UNTIL child has start_slack > 0, the reference raises for
+                            every t (api.py:288-293) */
+  int32_t threads;       /* CTA size chosen for this (formula, T, D) */
+  int32_t tile_ext;      /* samples staged per CTA (= 8 * threads) */
+  int32_t tile_out;      /* outputs produced per CTA */
+  int32_t n_tiles;       /* tiles per trace */
+  int32_t smem_bytes;    /* dynamic shared memory per CTA */
+  int32_t n_instr;       /* lowered tile instructions */
+  int32_t n_planes;      /* shared-memory value planes */
+} pystl_plan_t;
+
+int pystl_b200_abi_version(void);
+const char* pystl_b200_last_error(void);
+
+/* Validate + lower the formula for traces of length T with D channels.
+ * backward != 0 plans the gradient kernel instead of the forward one. */
+int pystl_b200_plan(const pystl_formula_t* formula, int64_t T, int32_t D, int32_t backward,
+                    pystl_plan_t* plan);
+
+/* Robustness of every (trace, t):  out[b, t, c] for signal[b, t, d] (fp32, contiguous).
+ *   out      [B, T, out_channels]  written for all t; NaN where the reference raises
+ *   mean_acc optional double[2]: += (sum of the valid outputs' channels, count); the
+ *            fused mean-robustness reduction (one NCCL all-reduce of these 16 bytes
+ *            finishes a batch-sharded mean).  May be NULL.
+ * Replaces the per-(trace, t) recursion of pystl/api.py:142-302. */
+int pystl_b200_eval_forward(const pystl_formula_t* formula, const float* signal, int64_t B,
+                            int64_t T, int32_t D, float* out, double* mean_acc, void* stream);
+
+/* Gradient of sum_{b,t,c} grad_out[b,t,c] * out[b,t,c] with respect to signal.
+ *   grad_out    [B, T, out_channels] or NULL for the constant cotangent grad_scale
+ *               (d mean / d out); entries at t the reference raises on are ignored
+ *   grad_signal [B, T, D], fully overwritten (zeros for unreferenced channels)
+ * Replaces autograd through pystl/torch/semantics.py and
+ * DgmsrSemantics.evaluate_with_grad (pystl/semantics/dgmsr.py:120-274). */
+int pystl_b200_eval_backward(const pystl_formula_t* formula, const float* signal, int64_t B,
+                             int64_t T, int32_t D, const float* grad_out, float grad_scale,
+                             float* grad_signal, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYSTL_B200_H */

@@ -1,0 +1,224 @@
+"""Formula tree -> flat post-order node list (the ``pystl_formula_t`` of the C ABI).
+
+Accepts ``pystl_b200.formula`` nodes and the reference's ``pystl.api`` nodes alike
+(duck-typed on the class name; field names per api.py:129-302).
+
+Predicates: the fused kernels evaluate affine predicates
+``bias + sum_d coeff[d] * signal[t, d]``.  ``metadata["affine"]`` is used when
+present; otherwise ``Predicate.fn`` -- an opaque callable in the reference
+(api.py:24,133-143) -- is probed with float64 rows and accepted if it is an
+affine function of ``signal[t]`` alone.  Anything else raises
+``NotImplementedError`` (no silent host evaluation).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import capi
+
+_SEM_IDS = {
+    "classical": capi.SEM_CLASSIC,
+    "smooth": capi.SEM_SMOOTH,
+    "cumulative": capi.SEM_CUMULATIVE,
+    "agm": capi.SEM_AGM,
+    "dgmsr": capi.SEM_DGMSR,
+}
+
+
+def affine_of(pred: Any, n_channels: int) -> Tuple[Tuple[Tuple[int, float], ...], float]:
+    """``((channel, coeff), ...), bias`` of a predicate, or NotImplementedError."""
+    meta = getattr(pred, "metadata", None) or {}
+    if "affine" in meta:
+        terms, bias = meta["affine"]
+        if isinstance(terms, dict):
+            terms = tuple(sorted(terms.items()))
+        return tuple((int(d), float(c)) for d, c in terms), float(bias)
+    fn = getattr(pred, "fn", None)
+    if fn is None:  # classic.py:16-19
+        raise ValueError(f"Predicate '{pred.name}' does not define `fn(signal, t)`.")
+    D = int(n_channels)
+
+    def call(sig: np.ndarray, t: int) -> float:
+        return float(fn(sig, t))
+
+    try:
+        zero = np.zeros((3, D))
+        bias = call(zero, 1)
+        coeffs = np.zeros(D)
+        for d in range(D):
+            probe = np.zeros((3, D))
+            probe[1, d] = 1.0
+            coeffs[d] = call(probe, 1) - bias
+        rng = np.random.default_rng(12345)
+        ok = True
+        for _ in range(4):
+            sig = rng.normal(size=(3, D)) * 3.0
+            for t in (0, 1, 2):
+                want = bias + float(coeffs @ sig[t])
+                got = call(sig, t)
+                if not np.isfinite(got) or abs(got - want) > 1e-9 * (1.0 + abs(want)):
+                    ok = False
+    except Exception as exc:  # the callable needs something the probe cannot give it
+        raise NotImplementedError(
+            f"Predicate '{pred.name}': fn(signal, t) could not be probed ({exc!r}); "
+            "give it metadata={'affine': ({channel: coeff}, bias)}"
+        ) from exc
+    if not ok:
+        raise NotImplementedError(
+            f"Predicate '{pred.name}' is not an affine function of signal[t]; the b200 backend "
+            "evaluates affine predicates only (metadata={'affine': ({channel: coeff}, bias)})."
+        )
+    terms = tuple((d, float(c)) for d, c in enumerate(coeffs) if c != 0.0)
+    return terms, float(bias)
+
+
+@dataclass
+class CompiledFormula:
+    """Owns the ctypes arrays a ``pystl_formula_t`` points into."""
+
+    struct: capi.Formula
+    nodes: Any
+    children: Any
+    preds: Any
+    weights: Any
+    n_channels_min: int  # highest channel referenced + 1
+    channels_used: Tuple[int, ...]
+    pred_terms: List[Tuple[Tuple[Tuple[int, float], ...], float]]
+
+    def ptr(self):
+        return C.byref(self.struct)
+
+
+def compile_formula(
+    formula: Any,
+    semantics: str,
+    n_channels: int,
+    *,
+    temperature: float = 1.0,
+    eps: float = 1e-8,
+    p: int = 1,
+) -> CompiledFormula:
+    sem_id = _SEM_IDS[semantics]
+    nodes: List[capi.Node] = []
+    children: List[int] = []
+    weights: List[float] = []
+    preds: List[Tuple[Tuple[Tuple[int, float], ...], float]] = []
+    pred_index: Dict[Any, int] = {}
+    memo: Dict[int, int] = {}
+
+    def add_weights(w) -> Tuple[int, int]:
+        if w is None:
+            return -1, 0
+        w = [float(x) for x in w]
+        off = len(weights)
+        weights.extend(w)
+        return off, len(w)
+
+    def interval_of(node) -> Tuple[int, int]:
+        iv = node.interval
+        a = int(iv.start)
+        b = -1 if iv.end is None else int(iv.end)
+        if a < 0:
+            raise ValueError("Interval start must be >= 0.")
+        if b != -1 and b < a:
+            raise ValueError("Interval end must be >= start.")
+        return a, b
+
+    def visit(node: Any) -> int:
+        key = id(node)
+        if key in memo:
+            return memo[key]
+        kind = type(node).__name__
+        n = capi.Node()
+        n.w_off, n.w_len, n.w2_off, n.w2_len = -1, 0, -1, 0
+        n.wp0 = n.wp1 = 1.0
+        n.pred = -1
+        kids: List[int] = []
+        if kind == "Predicate":
+            n.kind = capi.NODE_PRED
+            terms, bias = affine_of(node, n_channels)
+            if len(terms) > capi.MAX_TERMS:
+                raise NotImplementedError(f"Predicate '{node.name}' has more than {capi.MAX_TERMS} terms")
+            for d, _ in terms:
+                if d < 0 or d >= n_channels:
+                    raise ValueError(f"Predicate '{node.name}' reads channel {d} of a {n_channels}-channel signal")
+            pkey = (terms, bias)
+            if pkey not in pred_index:
+                pred_index[pkey] = len(preds)
+                preds.append(pkey)
+            n.pred = pred_index[pkey]
+        elif kind == "Not":
+            n.kind = capi.NODE_NOT
+            kids = [visit(node.child)]
+        elif kind in ("And", "Or"):
+            n.kind = capi.NODE_AND if kind == "And" else capi.NODE_OR
+            if len(node.children) == 0:
+                raise ValueError(f"{kind} requires at least one child.")
+            kids = [visit(c) for c in node.children]
+            n.w_off, n.w_len = add_weights(node.weights)
+        elif kind in ("Always", "Eventually"):
+            n.kind = capi.NODE_ALWAYS if kind == "Always" else capi.NODE_EVENTUALLY
+            kids = [visit(node.child)]
+            n.a, n.b = interval_of(node)
+            n.w_off, n.w_len = add_weights(node.weights)
+        elif kind == "Until":
+            n.kind = capi.NODE_UNTIL
+            kids = [visit(node.left), visit(node.right)]
+            n.a, n.b = interval_of(node)
+            n.w_off, n.w_len = add_weights(node.weights_left)
+            n.w2_off, n.w2_len = add_weights(node.weights_right)
+            wp = tuple(float(x) for x in node.weights_pair)
+            if len(wp) < 2:
+                raise ValueError("weights_pair requires at least 2 entries.")
+            n.wp0, n.wp1 = wp[0], wp[1]
+        else:
+            raise TypeError(f"Unsupported formula node type: {type(node)!r}")
+        n.n_children = len(kids)
+        n.child_off = len(children)
+        children.extend(kids)
+        nodes.append(n)
+        memo[key] = len(nodes) - 1
+        return memo[key]
+
+    visit(formula)
+
+    node_arr = (capi.Node * len(nodes))(*nodes)
+    child_arr = (C.c_int32 * max(len(children), 1))(*children)
+    weight_arr = (C.c_float * max(len(weights), 1))(*weights)
+    pred_arr = (capi.Pred * max(len(preds), 1))()
+    used = set()
+    for i, (terms, bias) in enumerate(preds):
+        pred_arr[i].n_terms = len(terms)
+        for k, (d, c) in enumerate(terms):
+            pred_arr[i].channel[k] = d
+            pred_arr[i].coeff[k] = c
+            used.add(d)
+        pred_arr[i].bias = bias
+    st = capi.Formula()
+    st.semantics = sem_id
+    st.temperature = float(temperature)
+    st.eps = float(eps)
+    st.p = int(p)
+    st.n_nodes = len(nodes)
+    st.nodes = C.cast(node_arr, C.POINTER(capi.Node))
+    st.n_children = len(children)
+    st.children = C.cast(child_arr, C.POINTER(C.c_int32))
+    st.n_preds = len(preds)
+    st.preds = C.cast(pred_arr, C.POINTER(capi.Pred))
+    st.n_weights = len(weights)
+    st.weights = C.cast(weight_arr, C.POINTER(C.c_float))
+    return CompiledFormula(
+        struct=st,
+        nodes=node_arr,
+        children=child_arr,
+        preds=pred_arr,
+        weights=weight_arr,
+        n_channels_min=(max(used) + 1) if used else 1,
+        channels_used=tuple(sorted(used)),
+        pred_terms=preds,
+    )

@@ -1,0 +1,105 @@
+// Tile program: what a formula is lowered to before it reaches the kernel.
+//
+// A CTA evaluates the whole formula over one tile of one trace.  Every node
+// value lives in a shared-memory "plane" (one float per sample of the tile,
+// two for cumulative's (pos, neg)); a thread owns 8 consecutive samples of
+// every plane.  The program is a flat list of instructions over plane slots,
+// passed to the kernel by value (__grid_constant__), so decoding is a uniform
+// constant-bank read.
+#pragma once
+#include <stdint.h>
+
+namespace pystl {
+
+constexpr int kChunk = 8;       // samples per thread (two float4)
+constexpr int kMaxSrc = 8;      // operands of one n-ary instruction
+constexpr int kMaxTerms = 8;    // == PYSTL_MAX_TERMS
+constexpr int kMaxPreds = 16;   // distinct affine predicates per formula
+constexpr int kMaxInstr = 40;   // lowered instructions per formula
+constexpr int kMaxThreads = 1024;
+
+enum Sem : int32_t { SEM_CLASSIC = 0, SEM_SMOOTH = 1, SEM_CUMULATIVE = 2, SEM_AGM = 3, SEM_DGMSR = 4 };
+
+// which reduction an instruction performs
+enum Mode : int32_t {
+  MODE_AND = 0,  // conjunction / ALWAYS
+  MODE_OR = 1,   // disjunction / EVENTUALLY
+  MODE_SUM = 2   // cumulative EVENTUALLY (cumulative.py:61-72)
+};
+
+enum TOp : int32_t {
+  T_NARY = 0,        // dst[t] = reduce_i src_i[t]                       (And / Or)
+  T_WIN_DIRECT = 1,  // dst[t] = reduce_{k in [a,b]} src[t+k], b-a+1 <= 8
+  T_WIN_VH = 2,      // same, van Herk / Gil-Werman over 8-sample chunks, b-a+1 >= 9
+  T_WIN_SUFFIX = 3,  // dst[t] = reduce_{k >= a} src[t+k] up to the horizon (tile must reach T)
+  T_UNTIL = 4,       // dst[t] = OR_{i in [a,b]} AND(AND_{k<=i} l[t+k], r[t+i])   O(b) per sample
+  T_CLAMP_SCAN = 5   // classic unbounded until: W(t) = min(l_t, max(r_t, W(t+1)))
+};
+
+struct TPred {
+  int16_t dst;  // plane slot
+  int16_t n_terms;
+  int32_t f64;  // classic only: evaluate in float64 and round once (bit-exact against the float64 reference)
+  int16_t ch[kMaxTerms];
+  float coeff[kMaxTerms];
+  float bias;
+};
+
+struct TInstr {
+  int16_t op;    // TOp
+  int16_t mode;  // Mode
+  int16_t dst;   // plane slot of the result
+  int16_t nsrc;
+  int16_t src[kMaxSrc];  // plane slots
+  uint16_t negmask;      // bit i: operand i is negated (Not folded into the consumer)
+  int16_t unbounded;     // T_UNTIL: b is the horizon
+  int32_t a, b;          // window offsets relative to t (signed: the backward pass looks back)
+  float w[kMaxSrc];      // n-ary weights; T_UNTIL: w[0], w[1] = weights_pair
+  float sw;              // sum of the n-ary weights
+};
+
+struct TileProgram {
+  int32_t sem;      // Sem
+  int32_t p;        // dgmsr exponent
+  float tau;        // smooth temperature
+  float eps;        // dgmsr eps
+  int32_t n_preds;
+  int32_t n_instr;
+  int32_t n_slots;  // plane slots in use
+  int16_t root;     // plane slot holding the formula value
+  int16_t root_neg; // formula is Not(...) at the top
+  int32_t start_slack;  // outputs at t > T-1-start_slack are NaN
+  int32_t raises_always;
+  TPred preds[kMaxPreds];
+  TInstr ins[kMaxInstr];
+};
+
+// Geometry of one launch.
+struct TileGeom {
+  int64_t B, T;
+  int32_t D;
+  int32_t nt;        // threads per CTA
+  int32_t lext;      // samples staged per tile = 8 * nt
+  int32_t lout;      // outputs per tile (multiple of 8)
+  int32_t n_tiles;   // tiles per trace
+  int32_t vw;        // words per value (2 for cumulative)
+  int32_t scr_planes;  // scratch planes
+  // shared-memory carve-up, in floats
+  int32_t off_planes, off_scratch, off_chunk, off_red, smem_floats;
+};
+
+// Lowering result (host only).
+struct Lowered {
+  TileProgram prog;
+  int32_t lookahead;  // -1: unbounded
+  int32_t out_channels;
+};
+
+}  // namespace pystl
+
+struct pystl_formula;
+namespace pystl {
+int lower_formula(const ::pystl_formula* f, Lowered* out, char* msg, int msg_len);
+// force_nt > 0 pins the CTA size (tests); 0 = choose
+int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_nt, TileGeom* g, char* msg, int msg_len);
+}  // namespace pystl

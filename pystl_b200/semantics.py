@@ -1,0 +1,353 @@
+"""The five semantics of the ``b200`` backend.
+
+Each class implements the reference's seven-method operator interface
+(``pystl/semantics/base.py:18-75``: ``predicate, boolean_not, boolean_and,
+boolean_or, temporal_always, temporal_eventually, temporal_until``) so that it
+can be handed to ``Formula.evaluate(signal, semantics, t)`` like any other
+backend, and mirrors the constructor kwargs of ``pystl/torch/semantics.py``
+(``temperature`` for smooth, ``eps`` / ``p`` for dgmsr; the others take none and
+raise ``TypeError`` on unknown kwargs, like the reference classes).
+
+The real work happens one level up, where the reference already lets a
+semantics object take the whole formula (``Formula.evaluate_with_grad`` ->
+``semantics.evaluate_with_grad``, api.py:64-78):
+
+* ``robustness_trace(formula, signal[B, T, D])`` -- every ``t`` of every trace in
+  one fused kernel launch; differentiable (``torch.autograd.Function``);
+* ``evaluate_formula(formula, signal, t)`` -- value at one ``t`` (what
+  ``phi.evaluate(signal, sem, t)`` returns), raising where the reference raises;
+* ``evaluate_with_grad(formula, signal, t=...)`` -- ``(value, d value / d signal)``.
+
+Tensors go to the CUDA library through the C ABI (``capi``) as raw pointers on
+the current stream.  There is no CPU path: a CPU tensor is copied to the
+device, evaluated there and copied back; without the CUDA library or a GPU
+every call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import capi
+from .compiler import CompiledFormula, compile_formula
+from .formula import Predicate, affine_predicate
+
+
+@dataclass(frozen=True)
+class B200CumulativeRobustness:
+    """``(pos, neg)`` pair, like ``TorchCumulativeRobustness`` (torch/semantics.py:218-223)."""
+
+    pos: Any
+    neg: Any
+
+
+def _device_of(signal: torch.Tensor) -> torch.device:
+    if signal.is_cuda:
+        return signal.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("the b200 backend needs a CUDA device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class _B200Semantics:
+    syntax = ""
+    out_channels = 1
+
+    def __init__(self) -> None:
+        self._cache: Dict[Tuple[int, int], Tuple[Any, CompiledFormula]] = {}
+
+    # ---- kwargs forwarded to the C ABI -------------------------------------------------
+    def _params(self) -> dict:
+        return {}
+
+    # ---- formula cache (the only mutable state; keyed by object identity + D) ----------
+    def compile(self, formula: Any, n_channels: int) -> CompiledFormula:
+        key = (id(formula), int(n_channels))
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] is formula:
+            return hit[1]
+        cf = compile_formula(formula, self.syntax, n_channels, **self._params())
+        if len(self._cache) > 256:
+            self._cache.clear()
+        self._cache[key] = (formula, cf)
+        return cf
+
+    def plan(self, formula: Any, horizon: int, n_channels: int) -> dict:
+        """Tiling / validity report for ``formula`` on traces of ``horizon`` samples (host only)."""
+        cf = self.compile(formula, n_channels)
+        p = capi.Plan()
+        rc = capi.lib().pystl_b200_plan(cf.ptr(), int(horizon), int(n_channels), 0, C.byref(p))
+        capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+        return p.as_dict()
+
+    # ---- whole-formula evaluation --------------------------------------------------------
+    def _forward_raw(self, cf: CompiledFormula, sig: torch.Tensor, mean_acc: Optional[torch.Tensor]) -> torch.Tensor:
+        B, T, D = sig.shape
+        out = torch.empty((B, T, self.out_channels), dtype=torch.float32, device=sig.device)
+        stream = torch.cuda.current_stream(sig.device).cuda_stream
+        with torch.cuda.device(sig.device):
+            rc = capi.lib().pystl_b200_eval_forward(
+                cf.ptr(), sig.data_ptr(), B, T, D, out.data_ptr(),
+                None if mean_acc is None else mean_acc.data_ptr(), stream,
+            )
+        capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+        return out
+
+    def _prepare(self, signal: Any) -> Tuple[torch.Tensor, bool, torch.device]:
+        sig = torch.as_tensor(signal)
+        squeeze = sig.dim() == 2
+        if squeeze:
+            sig = sig.unsqueeze(0)
+        if sig.dim() != 3:
+            raise ValueError("signal must have shape (time, state_dim) or (batch, time, state_dim).")
+        home = sig.device
+        dev = _device_of(sig)
+        sig = sig.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        return sig, squeeze, home
+
+    def robustness_trace(self, formula: Any, signal: Any) -> Any:
+        """Robustness at every ``t``: ``[B, T]`` for ``signal[B, T, D]`` (``[T]`` for ``[T, D]``).
+
+        Cumulative returns ``B200CumulativeRobustness(pos, neg)`` of such tensors.  Entries the
+        reference would raise ``ValueError`` on (empty window, api.py:218-221) are NaN.
+        """
+        sig, squeeze, home = self._prepare(signal)
+        cf = self.compile(formula, sig.shape[-1])
+        if torch.is_grad_enabled() and isinstance(signal, torch.Tensor) and signal.requires_grad:
+            from .autograd import RobustnessFn
+
+            out = RobustnessFn.apply(signal if not squeeze else signal.unsqueeze(0), self, cf)
+        else:
+            out = self._forward_raw(cf, sig, None)
+        if home != out.device:
+            out = out.to(home)
+        if squeeze:
+            out = out[0]
+        if self.out_channels == 2:
+            return B200CumulativeRobustness(pos=out[..., 0], neg=out[..., 1])
+        return out[..., 0]
+
+    def mean_robustness(self, formula: Any, signal: Any, *, group=None) -> torch.Tensor:
+        """Mean of the valid outputs (cumulative: of ``pos + neg``), reduced inside the kernel.
+
+        With ``torch.distributed`` initialised the ``(sum, count)`` pair is all-reduced (one
+        16-byte NCCL all-reduce) so that every rank gets the mean over the whole sharded batch."""
+        from .distributed import all_reduce_mean
+
+        sig, _, _ = self._prepare(signal)
+        cf = self.compile(formula, sig.shape[-1])
+        acc = torch.zeros(2, dtype=torch.float64, device=sig.device)
+        plan = self.plan(formula, sig.shape[1], sig.shape[2])
+        self._forward_raw(cf, sig, acc)
+        valid = 0 if plan["raises_always"] else max(sig.shape[1] - plan["start_slack"], 0)
+        acc[1] = float(sig.shape[0] * valid)
+        return all_reduce_mean(acc, group=group)
+
+    def evaluate_formula(self, formula: Any, signal: Any, t: int = 0) -> Any:
+        """``phi.evaluate(signal, sem, t)`` of the reference, for ``signal[T, D]`` or ``[B, T, D]``."""
+        sig = torch.as_tensor(signal)
+        T = sig.shape[-2]
+        if t < 0 or t >= T:
+            raise IndexError(f"t={t} is out of bounds for horizon={T}.")
+        plan = self.plan(formula, T, sig.shape[-1])
+        if plan["raises_always"] or t > T - 1 - plan["start_slack"]:
+            raise ValueError(f"temporal window is empty at t={t} for a horizon of {T} samples.")
+        out = self.robustness_trace(formula, signal)
+        if self.out_channels == 2:
+            return B200CumulativeRobustness(pos=out.pos[..., t], neg=out.neg[..., t])
+        return out[..., t]
+
+    def evaluate_with_grad(self, formula: Any, signal: Any, *, t: int = 0, **_unused: Any):
+        """``(rho_t, d rho_t / d signal)`` like ``DgmsrSemantics.evaluate_with_grad`` (dgmsr.py:120-274)."""
+        import numpy as np
+
+        x = torch.as_tensor(signal, dtype=torch.float32)
+        if x.dim() != 2:
+            raise ValueError("signal must be a 2D array with shape (time, state_dim).")
+        if t < 0 or t >= x.shape[0]:
+            raise IndexError(f"t={t} is out of bounds for signal with horizon={x.shape[0]}.")
+        x = x.to(_device_of(x)).requires_grad_(True)
+        val = self.evaluate_formula(formula, x, t)
+        scalar = (val.pos + val.neg) if self.out_channels == 2 else val
+        (grad,) = torch.autograd.grad(scalar, x)
+        if self.out_channels == 2:
+            value = B200CumulativeRobustness(pos=float(val.pos), neg=float(val.neg))
+        else:
+            value = float(val)
+        return value, np.asarray(grad.detach().cpu().numpy(), dtype=float)
+
+    # ---- the reference's operator interface (base.py:21-75) -------------------------------
+    # Values are torch tensors of any (broadcastable) shape on a CUDA device; a list of n
+    # values is stacked into an n-channel signal and reduced by the same fused kernel.
+    def predicate(self, predicate: Any, signal: Any, t: int) -> Any:
+        if predicate.fn is None:
+            raise ValueError(f"Predicate '{predicate.name}' does not define `fn(signal, t)`.")
+        sig = torch.as_tensor(signal)
+        value = torch.as_tensor(predicate.fn(sig, t), dtype=torch.float32, device=_device_of(sig))
+        return self._leaf(value)
+
+    def _leaf(self, value: torch.Tensor) -> Any:
+        return value
+
+    def boolean_not(self, value: Any) -> Any:
+        return -torch.as_tensor(value)
+
+    def _stack(self, values: Sequence[Any], where: str) -> torch.Tensor:
+        if len(values) == 0:
+            raise ValueError(f"{where} requires at least one value.")
+        vals = [torch.as_tensor(v, dtype=torch.float32) for v in values]
+        dev = next((v.device for v in vals if v.is_cuda), None)
+        if dev is None:
+            dev = _device_of(vals[0])
+        vals = torch.broadcast_tensors(*[v.to(dev) for v in vals])
+        return torch.stack(vals, dim=-1)  # [..., n]
+
+    def _reduce(self, values: Sequence[Any], kind: str, weights, where: str) -> torch.Tensor:
+        from .formula import And, Or
+
+        x = self._stack(values, where)
+        n = x.shape[-1]
+        leaves = [affine_predicate(f"v{i}", {i: 1.0}, 0.0) for i in range(n)]
+        phi = (And if kind == "and" else Or)(*leaves, weights=weights)
+        flat = x.reshape(1, -1, n)
+        out = self.robustness_trace(phi, flat)
+        return out.reshape(x.shape[:-1])
+
+    def boolean_and(self, values: Sequence[Any], *, weights: Optional[Sequence[float]] = None) -> Any:
+        return self._reduce(values, "and", weights, "boolean_and")
+
+    def boolean_or(self, values: Sequence[Any], *, weights: Optional[Sequence[float]] = None) -> Any:
+        return self._reduce(values, "or", weights, "boolean_or")
+
+    def temporal_always(self, values: Sequence[Any], *, weights: Optional[Sequence[float]] = None) -> Any:
+        return self.boolean_and(values, weights=weights)
+
+    def temporal_eventually(self, values: Sequence[Any], *, weights: Optional[Sequence[float]] = None) -> Any:
+        return self.boolean_or(values, weights=weights)
+
+    def temporal_until(
+        self,
+        *,
+        left_trace: Sequence[Any],
+        right_trace: Sequence[Any],
+        start: int,
+        end: Optional[int],
+        weights_left: Optional[Sequence[float]] = None,
+        weights_right: Optional[Sequence[float]] = None,
+        weights_pair: Sequence[float] = (1.0, 1.0),
+    ) -> Any:
+        from .formula import Until
+
+        if len(left_trace) == 0 or len(right_trace) == 0:
+            raise ValueError("UNTIL traces must be non-empty.")
+        if len(left_trace) != len(right_trace):
+            raise ValueError("UNTIL traces must have the same length.")
+        if start < 0:
+            raise ValueError("UNTIL start must be >= 0.")
+        n = len(left_trace)
+        last = n - 1 if end is None else min(end, n - 1)
+        if start > last:
+            raise ValueError("UNTIL temporal window is empty.")
+        l = self._stack(left_trace, "temporal_until")  # [..., n]
+        r = self._stack(right_trace, "temporal_until")
+        l, r = torch.broadcast_tensors(l, r)
+        sig = torch.stack((l, r), dim=-1).reshape(-1, n, 2)  # [batch, time, (l, r)]
+        phi = Until(
+            affine_predicate("l", {0: 1.0}), affine_predicate("r", {1: 1.0}), (start, end),
+            weights_left=weights_left, weights_right=weights_right, weights_pair=weights_pair,
+        )
+        out = self.robustness_trace(phi, sig)[:, 0]
+        return out.reshape(l.shape[:-1])
+
+
+class B200ClassicRobustSemantics(_B200Semantics):
+    """Hard min / max (``TorchClassicRobustSemantics``, torch/semantics.py:87-146)."""
+
+    syntax = "classical"
+
+
+class B200SmoothRobustSemantics(_B200Semantics):
+    """Log-sum-exp soft min / max (``TorchSmoothRobustSemantics``, torch/semantics.py:149-215)."""
+
+    syntax = "smooth"
+
+    def __init__(self, *, temperature: float = 1.0) -> None:
+        super().__init__()
+        if temperature <= 0.0:  # torch/semantics.py:13-16
+            raise ValueError("temperature must be > 0.")
+        self.temperature = float(temperature)
+
+    def _params(self) -> dict:
+        return {"temperature": self.temperature}
+
+
+class B200CumulativeSemantics(_B200Semantics):
+    """``(pos, neg)`` cumulative robustness (``TorchCumulativeSemantics``, torch/semantics.py:226-345)."""
+
+    syntax = "cumulative"
+    out_channels = 2
+
+    def _leaf(self, value: torch.Tensor) -> Any:
+        zero = torch.zeros_like(value)
+        return B200CumulativeRobustness(pos=torch.maximum(zero, value), neg=torch.minimum(zero, value))
+
+    def boolean_not(self, value: Any) -> Any:
+        return B200CumulativeRobustness(pos=-value.neg, neg=-value.pos)
+
+    # (pos, neg) lists: each channel is reduced independently by the same kernel, fed with
+    # predicates that are already clipped (pos >= 0, neg <= 0 pass through the leaf unchanged)
+    def _pair_reduce(self, values, op: str):
+        if len(values) == 0:
+            raise ValueError(f"{op} requires at least one value.")
+        pos = [v.pos for v in values]
+        neg = [v.neg for v in values]
+        helper = B200ClassicRobustSemantics()
+        if op == "sum":
+            return B200CumulativeRobustness(
+                pos=torch.stack(list(torch.broadcast_tensors(*pos)), 0).sum(0),
+                neg=torch.stack(list(torch.broadcast_tensors(*neg)), 0).sum(0),
+            )
+        red = helper.boolean_and if op == "min" else helper.boolean_or
+        return B200CumulativeRobustness(pos=red(pos), neg=red(neg))
+
+    def boolean_and(self, values, *, weights=None):
+        return self._pair_reduce(values, "min")
+
+    def boolean_or(self, values, *, weights=None):
+        return self._pair_reduce(values, "max")
+
+    def temporal_always(self, values, *, weights=None):
+        return self._pair_reduce(values, "min")
+
+    def temporal_eventually(self, values, *, weights=None):
+        return self._pair_reduce(values, "sum")
+
+    def temporal_until(self, *, left_trace, right_trace, start, end, weights_left=None, weights_right=None,
+                       weights_pair=(1.0, 1.0)):
+        raise NotImplementedError(
+            "cumulative temporal_until on (pos, neg) lists: use robustness_trace / evaluate_formula on the formula"
+        )
+
+
+class B200AgmRobustSemantics(_B200Semantics):
+    """Arithmetic-geometric mean robustness (``TorchAgmRobustSemantics``, torch/semantics.py:348-463)."""
+
+    syntax = "agm"
+
+
+class B200DgmsrSemantics(_B200Semantics):
+    """D-GMSR (``TorchDgmsrSemantics``, torch/semantics.py:509-587)."""
+
+    syntax = "dgmsr"
+
+    def __init__(self, *, eps: float = 1e-8, p: int = 1) -> None:
+        super().__init__()
+        self.eps = float(eps)
+        self.p = int(p)
+
+    def _params(self) -> dict:
+        return {"eps": self.eps, "p": self.p}

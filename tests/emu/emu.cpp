@@ -1,0 +1,93 @@
+// TEST INFRASTRUCTURE -- host emulation of the CUDA tile kernel.
+//
+// Compiles pystl_b200/csrc/tile_eval.h (the single-source CTA body) and
+// pystl_b200/csrc/lower.cpp with g++ and runs every "CTA" as a sequential loop
+// over its threads (HostExec).  It exists so that the CPU-only test tier can
+// check the kernel's lowering, tiling, halo and index arithmetic against the
+// oracle without a GPU.  It is built into tests/_emu/ by tests/emu/build.py and
+// is never loaded by the pystl_b200 package: the product path is CUDA only.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/pystl_b200.h"
+#include "../../pystl_b200/csrc/program.h"
+#include "../../pystl_b200/csrc/tile_eval.h"
+
+using namespace pystl;
+
+static thread_local char g_err[512];
+
+template <int SEM>
+static void run_all(const Lowered& lw, const TileGeom& g, const float* signal, float* out, double* mean_acc) {
+  std::vector<float> smem((size_t)g.smem_floats + 64, 0.f);
+  // 16-byte align the base like the device's dynamic shared memory
+  float* base = smem.data();
+  while (reinterpret_cast<uintptr_t>(base) & 15) ++base;
+  constexpr int VW = Tr<SEM>::VW;
+  for (int64_t b = 0; b < g.B; ++b) {
+    for (int j = 0; j < g.n_tiles; ++j) {
+      // poison shared memory so that reads of never-written samples show up
+      for (int i = 0; i < g.smem_floats; ++i) base[i] = NAN;
+      Ctx c;
+      c.smem = base;
+      c.g = g;
+      c.P = &lw.prog;
+      c.e0 = (int64_t)j * g.lout;
+      c.T = g.T;
+      c.rp = make_rp(lw.prog);
+      float* raw = c.scr(0);
+      const int nlive = c.n_live();
+      const float* src = signal + (b * g.T + c.e0) * g.D;
+      for (int i = 0; i < nlive * g.D; ++i) raw[i] = src[i];
+      HostExec ex(g.nt);
+      run_program<SEM>(ex, c, raw);
+      store_root<SEM>(ex, c, out + b * g.T * VW, g.lout, mean_acc);
+    }
+  }
+}
+
+extern "C" const char* pystl_emu_last_error(void) { return g_err; }
+
+extern "C" int pystl_emu_plan(const pystl_formula_t* f, int64_t T, int32_t D, int32_t backward, pystl_plan_t* plan) {
+  (void)backward;
+  Lowered lw;
+  int rc = lower_formula(reinterpret_cast<const ::pystl_formula*>(f), &lw, g_err, sizeof(g_err));
+  if (rc) return rc;
+  TileGeom g;
+  rc = plan_geometry(lw, 1, T, D, 0, &g, g_err, sizeof(g_err));
+  if (rc) return rc;
+  plan->out_channels = lw.out_channels;
+  plan->lookahead = lw.lookahead;
+  plan->start_slack = lw.prog.start_slack;
+  plan->raises_always = lw.prog.raises_always;
+  plan->threads = g.nt;
+  plan->tile_ext = g.lext;
+  plan->tile_out = g.lout;
+  plan->n_tiles = g.n_tiles;
+  plan->smem_bytes = g.smem_floats * 4;
+  plan->n_instr = lw.prog.n_instr;
+  plan->n_planes = lw.prog.n_slots;
+  return 0;
+}
+
+// force_threads > 0 overrides the CTA size (to exercise multi-tile paths on short traces)
+extern "C" int pystl_emu_eval_forward(const pystl_formula_t* f, const float* signal, int64_t B, int64_t T, int32_t D,
+                                      float* out, double* mean_acc, int32_t force_threads) {
+  Lowered lw;
+  int rc = lower_formula(reinterpret_cast<const ::pystl_formula*>(f), &lw, g_err, sizeof(g_err));
+  if (rc) return rc;
+  if (B == 0 || T == 0) return 0;
+  TileGeom g;
+  rc = plan_geometry(lw, B, T, D, force_threads, &g, g_err, sizeof(g_err));
+  if (rc) return rc;
+  switch (lw.prog.sem) {
+    case SEM_CLASSIC: run_all<SEM_CLASSIC>(lw, g, signal, out, mean_acc); break;
+    case SEM_SMOOTH: run_all<SEM_SMOOTH>(lw, g, signal, out, mean_acc); break;
+    case SEM_CUMULATIVE: run_all<SEM_CUMULATIVE>(lw, g, signal, out, mean_acc); break;
+    case SEM_AGM: run_all<SEM_AGM>(lw, g, signal, out, mean_acc); break;
+    case SEM_DGMSR: run_all<SEM_DGMSR>(lw, g, signal, out, mean_acc); break;
+    default: return PYSTL_E_INVALID;
+  }
+  return 0;
+}

@@ -1,0 +1,90 @@
+"""Shared helpers of the parity tests: tolerances, random formulas, comparisons."""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import dense
+from pystl_b200.formula import from_spec
+
+# Tolerance of the fp32 kernels against the float64 reference:
+# bit-exact for classic; |got - want| <= ATOL + RTOL * |want| for the smooth semantics.
+RTOL = 1e-5
+ATOL = 5e-6
+
+
+def oracle_trace(spec, sem: str, kw: dict, sig64: np.ndarray) -> np.ndarray:
+    out = dense.robustness_trace(from_spec(spec), torch.tensor(sig64), dense.make(sem, **kw)).numpy()
+    return np.moveaxis(out, 0, -1) if sem == "cumulative" else out
+
+
+def assert_parity(got: np.ndarray, want64: np.ndarray, sem: str, what: str = "", scale: float = 1.0) -> None:
+    assert got.shape == want64.shape, (what, got.shape, want64.shape)
+    assert np.array_equal(np.isnan(got), np.isnan(want64)), f"{what}: NaN pattern differs"
+    if sem == "classical":
+        w32 = want64.astype(np.float32)
+        bad = ~((got == w32) | (np.isnan(got) & np.isnan(w32)))
+        assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.size} classic values are not bit-exact"
+        return
+    err = np.abs(got.astype(np.float64) - want64)
+    tol = scale * (ATOL + RTOL * np.abs(want64))
+    bad = err > tol
+    bad &= ~np.isnan(want64)
+    assert not bad.any(), (
+        f"{what}: {int(bad.sum())} of {bad.size} values off; worst abs err {np.nanmax(err):.3e} "
+        f"at want={want64.flat[np.nanargmax(err)]:.6g}"
+    )
+
+
+def mixed_signal(rng: np.random.Generator, B: int, T: int, D: int) -> np.ndarray:
+    """mu_b + 0.5 N(0,1), mu ~ U(-1, 3): both AGM / D-GMSR branches occur."""
+    mu = rng.uniform(-1.0, 3.0, size=(B, 1, D))
+    x = mu + 0.5 * rng.standard_normal((B, T, D))
+    x[0] = rng.standard_normal((T, D))
+    return x.astype(np.float32).astype(np.float64)
+
+
+def random_spec(rng: np.random.Generator, D: int, depth: int, max_b: int, allow_open: bool = False):
+    """Random formula spec over D channels with fp32-representable constants."""
+    def pred():
+        d = int(rng.integers(D))
+        c = float(rng.choice([-0.5, 0.0, 0.25, 0.5, 1.0, 1.5, 2.0]))
+        sign = float(rng.choice([-1.0, 1.0]))
+        if D > 1 and rng.random() < 0.25:
+            d2 = int((d + 1 + rng.integers(D - 1)) % D)
+            return ("pred", {d: 1.0, d2: -1.0}, 0.0)
+        return ("pred", {d: sign}, -sign * c)
+
+    def interval():
+        a = int(rng.choice([0, 0, 0, 1, 3]))
+        if allow_open and rng.random() < 0.2:
+            return (a, None)
+        return (a, a + int(rng.integers(0, max_b + 1)))
+
+    def node(d):
+        if d == 0 or rng.random() < 0.15:
+            return pred()
+        r = rng.random()
+        if r < 0.15:
+            return ("not", node(d - 1))
+        if r < 0.40:
+            k = int(rng.integers(2, 4))
+            return (str(rng.choice(["and", "or"])), [node(d - 1) for _ in range(k)])
+        if r < 0.85:
+            return (str(rng.choice(["always", "eventually"])), interval(), node(d - 1))
+        a = int(rng.choice([0, 0, 1]))
+        b = None if (allow_open and rng.random() < 0.2) else a + int(rng.integers(0, min(max_b, 24) + 1))
+        return ("until", (a, b), node(d - 1), node(d - 1))
+
+    return node(depth)
+
+
+SEM_KW = [
+    ("classical", {}),
+    ("smooth", {"temperature": 0.5}),
+    ("cumulative", {}),
+    ("agm", {}),
+    ("dgmsr", {"eps": 1e-8, "p": 1}),
+    ("dgmsr", {"eps": 1e-8, "p": 2}),
+]
