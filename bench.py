@@ -61,7 +61,7 @@ DESCR = {
 def algorithmic_bytes_per_sample(cfg: str, backward: bool) -> float:
     """forward 4*D_ref + 4*C_out; backward 4*C_out(grad_out, 0 when the
     constant cotangent is fused) + 4*D_ref (re-read) + 4*D (grad write)."""
-    _, _, D = BASELINE_SHAPES[cfg]
+    _, _, D = BASELINE_SHAPES[cfg[:4]]
     d_ref = {"cfg1": 2, "cfg2": 2, "cfg3": 2, "cfg3d": 2, "cfg4": 2, "cfg5": 8}[cfg]
     c_out = 2 if cfg == "cfg4" else 1
     fwd = 4 * d_ref + 4 * c_out
@@ -83,10 +83,10 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(
                     ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
@@ -96,10 +96,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
@@ -127,8 +127,8 @@ def _cpu_worker(args):
     from oracle import scalar
 
     sem_name, kw, _ = WORKLOADS[cfg]
-    _, T, D = BASELINE_SHAPES[cfg]
-    phi = from_spec(BASELINE_SPECS[cfg])
+    _, T, D = BASELINE_SHAPES[cfg[:4]]
+    phi = from_spec(BASELINE_SPECS[cfg[:4]])
     sem = scalar.make(sem_name, **kw)
     rng = np.random.default_rng(seed)
     done = 0
@@ -147,7 +147,7 @@ def cpu_port_throughput(cfg: str, budget_s: float, cores: int) -> dict:
     One evaluation = one trace-sample of the forward pass (the reference has no batched path)."""
     import multiprocessing as mp
 
-    _, T, _ = BASELINE_SHAPES[cfg]
+    _, T, _ = BASELINE_SHAPES[cfg[:4]]
     T_eval = min(T, 1024)
     # calibrate on one core
     n, dt = _cpu_worker((cfg, 0, 1, T_eval, 4, 0))
@@ -233,13 +233,13 @@ def run_b200(args) -> None:
     sem_name, kw, with_bwd = WORKLOADS[cfg]
     if args.forward_only:
         with_bwd = False
-    B, T, D = BASELINE_SHAPES[cfg]
+    B, T, D = BASELINE_SHAPES[cfg[:4]]
     if args.batch:
         B = args.batch
     if cfg == "cfg5" and not args.batch:
         # 2^20 traces are sharded over 8 GPUs in the BASELINE config: 2^17 per GPU
         B = (1 << 20) // 8
-    phi = from_spec(BASELINE_SPECS[cfg])
+    phi = from_spec(BASELINE_SPECS[cfg[:4]])
     sem = pystl_b200.create_semantics(sem_name, backend="b200", **kw)
     capi.lib()  # fail loudly if the CUDA library is missing
 

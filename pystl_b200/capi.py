@@ -91,7 +91,10 @@ EXPORTS = (
     "pystl_b200_eval_backward",
 )
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libpystl_b200.so")
+# PYSTL_B200_LIB points at an alternative build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("PYSTL_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "csrc", "libpystl_b200.so"
+)
 _lib: Optional[C.CDLL] = None
 
 

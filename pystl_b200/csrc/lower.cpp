@@ -194,6 +194,21 @@ struct Lowerer {
     P().tau = f->temperature;
     P().eps = f->eps;
     P().p = f->p;
+    {
+      RP& r = P().rp;
+      const double tau = f->temperature > 0.f ? f->temperature : 1.0;
+      const int pp = f->p < 1 ? 1 : f->p;
+      const double eps = f->eps > 0.f ? f->eps : 1e-8;
+      r.k = (float)(1.4426950408889634 / tau);
+      r.invk = (float)(tau * 0.6931471805599453);
+      r.shift = 0.f;
+      r.eps = (float)eps;
+      r.sqrt_eps = (float)std::sqrt(eps);
+      r.ln_eps = (float)std::log(eps);
+      r.eps_p = (float)std::pow(eps, (double)pp);
+      r.inv2p = (float)(0.5 / pp);
+      r.p = pp;
+    }
     if (sem == SEM_SMOOTH && !(f->temperature > 0.f)) fail(PYSTL_E_INVALID, "temperature must be > 0.");  // smooth.py:12-15
     if (sem == SEM_DGMSR && (!(f->eps > 0.f) || f->p < 1)) fail(PYSTL_E_INVALID, "dgmsr needs eps > 0 and p >= 1");
     const bool uses_weights = (sem == SEM_AGM || sem == SEM_DGMSR);
@@ -450,6 +465,15 @@ int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_
   const int aw = (P.sem == SEM_CLASSIC || P.sem == SEM_SMOOTH) ? 1 : 2;
   const int scr_planes = 2 * std::max(aw, vw);
   const bool full = needs_full_trace(P) || lw.lookahead < 0;
+  // furthest offsets any window instruction reads at (guards of the scratch planes)
+  int max_b = 0, min_a = 0;
+  for (int i = 0; i < P.n_instr; ++i) {
+    const TInstr& in = P.ins[i];
+    if (in.op == T_WIN_DIRECT || in.op == T_WIN_VH || in.op == T_WIN_SUFFIX) {
+      max_b = std::max(max_b, std::max(in.a, in.b));
+      min_a = std::min(min_a, std::min(in.a, in.b));
+    }
+  }
   const int64_t Tn = std::max<int64_t>(T, 1);
   const int smem_cap = 227 * 1024;
   // geometry for one CTA size; false if it does not fit
@@ -471,12 +495,14 @@ int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_
       if (t.lout < 8) return false;
       t.n_tiles = (int)((Tn + t.lout - 1) / t.lout);
     }
+    t.gr = ((std::min(max_b, t.lext) + 4 + 7) / 8) * 8;
+    t.gl = ((std::min(-min_a, t.lext) + 7) / 8) * 8;
     t.off_planes = 0;
     t.off_scratch = P.n_slots * vw * t.lext;
     // the raw [sample][channel] rows share their storage with the scratch planes
     const int raw_floats = ((t.lext * D + 3) / 4) * 4;
-    t.off_chunk = t.off_scratch + std::max(raw_floats, scr_planes * t.lext);
-    t.off_red = t.off_chunk + 4 * nt;
+    t.off_chunk = t.off_scratch + std::max(raw_floats, scr_planes * (t.gl + t.lext + t.gr));
+    t.off_red = t.off_chunk + 4 * (t.gl / 8 + nt + t.gr / 8);
     t.smem_floats = t.off_red + 128;
     if (t.smem_floats * 4 > smem_cap) return false;
     *out = t;
@@ -487,24 +513,30 @@ int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_
     if (!build(force_nt, g)) return fail(PYSTL_E_UNSUPPORTED, "forced CTA size %d does not fit this formula", force_nt);
     return PYSTL_OK;
   }
-  const int cand[4] = {256, 512, 128, 1024};
+  // CTA sizes: every multiple of 32 up to 512 threads (tiles of 256 .. 4096 samples), then 768 / 1024
+  int cand[32], n_cand = 0;
+  for (int nt = 512; nt >= 64; nt -= 32) cand[n_cand++] = nt;  // ties go to the larger tile
+  cand[n_cand++] = 768;
+  cand[n_cand++] = 1024;
   double best_cost = 0;
   int best = -1;
   TileGeom bg{};
-  for (int ci = 0; ci < 4; ++ci) {
+  for (int ci = 0; ci < n_cand; ++ci) {
     TileGeom t{};
     if (!build(cand[ci], &t)) continue;
     if (t.n_tiles > 1 && t.lout < t.lext / 4) continue;  // more than 3/4 of every tile would be halo
-    // staged samples per trace, weighted by what the CTA shape costs in occupancy:
-    // 512 / 1024-thread CTAs are compiled for 64 registers per thread (spills), and a
-    // CTA that owns most of the SM's shared memory has nothing to overlap its loads with
+    // Cost = samples staged per trace (halo + tail waste), scaled by how well the CTA shape
+    // fills an SM.  All kernels are built for 64 registers per thread (2048 threads / SM), so
+    // residency is limited by shared memory; measured on B200, throughput keeps improving up
+    // to ~32 resident warps and larger tiles amortise the per-tile fixed costs.
     double cost = (double)t.n_tiles * t.lext;
-    if (t.nt == 512) cost *= 1.10;
-    if (t.nt == 1024) cost *= 1.30;
-    const int smem_bytes = t.smem_floats * 4;
-    if (smem_bytes > 113 * 1024) cost *= 1.5;
-    else if (smem_bytes > 75 * 1024) cost *= 1.15;
-    if (best < 0 || cost < best_cost * 0.97) {
+    const int smem_bytes = t.smem_floats * 4 + 1024;
+    int ctas = std::min((int)(227 * 1024 / smem_bytes), 2048 / t.nt);
+    if (ctas < 1) ctas = 1;
+    const int warps = ctas * t.nt / 32;
+    if (warps < 32) cost *= 1.0 + 0.6 * (32 - warps) / 32.0;
+    if (t.nt < 256) cost *= 1.0 + 0.15 * (256 - t.nt) / 256.0;  // per-tile fixed costs
+    if (best < 0 || cost < best_cost * 0.98) {
       best = ci;
       best_cost = cost;
       bg = t;

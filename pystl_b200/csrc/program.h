@@ -58,6 +58,19 @@ struct TInstr {
   float sw;              // sum of the n-ary weights
 };
 
+// Scalars derived from the semantics' kwargs, computed once on the host (lower.cpp).
+struct RP {
+  float k;         // smooth: log2(e) / tau
+  float invk;      // smooth: tau * ln 2
+  float shift;     // smooth: block-wide max of the exponent, set per instruction
+  float eps;       // dgmsr
+  float sqrt_eps;  // dgmsr
+  float ln_eps;    // dgmsr
+  float eps_p;     // dgmsr eps^p
+  float inv2p;     // dgmsr 1 / (2p)
+  int32_t p;
+};
+
 struct TileProgram {
   int32_t sem;      // Sem
   int32_t p;        // dgmsr exponent
@@ -70,6 +83,7 @@ struct TileProgram {
   int16_t root_neg; // formula is Not(...) at the top
   int32_t start_slack;  // outputs at t > T-1-start_slack are NaN
   int32_t raises_always;
+  RP rp;
   TPred preds[kMaxPreds];
   TInstr ins[kMaxInstr];
 };
@@ -84,6 +98,8 @@ struct TileGeom {
   int32_t n_tiles;   // tiles per trace
   int32_t vw;        // words per value (2 for cumulative)
   int32_t scr_planes;  // scratch planes
+  int32_t gl, gr;      // scratch guard bands (floats, multiples of 8) left / right of the tile:
+                       // hold the identity so that window reads need no bounds checks
   // shared-memory carve-up, in floats
   int32_t off_planes, off_scratch, off_chunk, off_red, smem_floats;
 };

@@ -69,34 +69,6 @@ PYSTL_HD float fast_lg2(float x) {
 #endif
 }
 
-// ------------------------------------------------------------------ run-time parameters
-struct RP {
-  float k;         // smooth: log2(e) / tau
-  float invk;      // smooth: tau * ln 2
-  float shift;     // smooth: block-wide max of the exponent, set per instruction
-  float eps;       // dgmsr
-  float sqrt_eps;  // dgmsr
-  float ln_eps;    // dgmsr
-  float eps_p;     // dgmsr eps^p
-  float inv2p;     // dgmsr 1 / (2p)
-  int p;
-};
-
-PYSTL_HD RP make_rp(const TileProgram& P) {
-  RP r;
-  const float tau = P.tau > 0.f ? P.tau : 1.f;
-  r.k = 1.4426950408889634f / tau;
-  r.invk = tau * 0.6931471805599453f;
-  r.shift = 0.f;
-  r.eps = P.eps;
-  r.sqrt_eps = sqrtf(P.eps);
-  r.ln_eps = logf(P.eps);
-  r.p = P.p < 1 ? 1 : P.p;
-  r.eps_p = powf(P.eps, (float)r.p);
-  r.inv2p = 0.5f / (float)r.p;
-  return r;
-}
-
 // ------------------------------------------------------------------ values and accumulators
 template <int SEM>
 struct Tr {
@@ -225,24 +197,45 @@ struct Red<SEM_DGMSR, MODE> {
 // ------------------------------------------------------------------ tile context
 struct Ctx {
   float* smem;
-  TileGeom g;
-  const TileProgram* P;
-  int64_t e0;  // trace time of tile sample 0
-  int64_t T;
+  int nt, lext, D;
+  int off_planes, off_scratch, off_chunk, off_red;
+  int gl, gr;   // scratch guard bands (floats), see TileGeom
+  int nlive;    // tile samples that exist in the trace: min(T - e0, lext)
+  int first;    // tile position of trace sample 0 (= -e0, clamped): positions below it do not exist
+  int last_ok;  // last tile position whose output does not raise (T-1-start_slack-e0, clamped), < 0: none
   RP rp;
-  PYSTL_HD float* plane(int slot, int w, int vw) const { return smem + g.off_planes + (slot * vw + w) * g.lext; }
-  PYSTL_HD float* scr(int i) const { return smem + g.off_scratch + i * g.lext; }
-  PYSTL_HD float* chunk(int i) const { return smem + g.off_chunk + i * g.nt; }
-  PYSTL_HD float* red() const { return smem + g.off_red; }
-  // number of tile samples that exist in the trace
-  PYSTL_HD int n_live() const {
-    const int64_t r = T - e0;
-    return r < (int64_t)g.lext ? (int)r : g.lext;
-  }
+  PYSTL_HD float* plane(int slot, int w, int vw) const { return smem + off_planes + (slot * vw + w) * lext; }
+  // scratch plane i / chunk-aggregate array i, addressed by LOGICAL position: valid for
+  // positions [-gl, lext + gr) and chunks [-gl/8, nt + gr/8)
+  PYSTL_HD float* scr(int i) const { return smem + off_scratch + i * (gl + lext + gr) + gl; }
+  PYSTL_HD float* chunk(int i) const { return smem + off_chunk + i * (gl / 8 + nt + gr / 8) + gl / 8; }
+  PYSTL_HD float* raw() const { return smem + off_scratch; }
+  PYSTL_HD float* red() const { return smem + off_red; }
 };
 
+PYSTL_HD Ctx make_ctx(float* smem, const TileGeom& g, const TileProgram& P, int64_t e0) {
+  Ctx c;
+  c.smem = smem;
+  c.nt = g.nt;
+  c.lext = g.lext;
+  c.D = g.D;
+  c.off_planes = g.off_planes;
+  c.off_scratch = g.off_scratch;
+  c.off_chunk = g.off_chunk;
+  c.off_red = g.off_red;
+  c.gl = g.gl;
+  c.gr = g.gr;
+  const int64_t live = g.T - e0;
+  c.nlive = live < (int64_t)g.lext ? (int)live : g.lext;
+  c.first = e0 > (int64_t)(1 << 30) ? -(1 << 30) : -(int)e0;
+  const int64_t ok = P.raises_always ? -1 : g.T - 1 - P.start_slack - e0;
+  c.last_ok = ok > (int64_t)(1 << 30) ? (1 << 30) : (ok < -1 ? -1 : (int)ok);
+  c.rp = P.rp;
+  return c;
+}
+
 // own chunk of a plane <-> registers
-PYSTL_HD void load8(const float* plane, int tid, float (&v)[8]) {
+PYSTL_HD void load8(const float* plane, int tid, float (&v)[8]) {  // tid = chunk index, may be negative
   const F4* P4 = reinterpret_cast<const F4*>(plane);
   const int s = (tid >> 2) & 1;
   const F4 lo = P4[2 * tid + s], hi = P4[2 * tid + (s ^ 1)];
@@ -290,25 +283,18 @@ PYSTL_HD void store_val8(const Ctx& c, int slot, int tid, const Vec<Tr<SEM>::VW>
   }
 }
 
-// run of 8 consecutive logical samples starting at `start` (any alignment, any sign)
-// from a scratch plane; positions outside [0, lext) read as `fill`.
-PYSTL_HD void load_run8(const float* plane, int lext, int start, float fill, float (&v)[8]) {
+// run of 8 consecutive logical samples starting at `start` (any alignment, any sign) from a
+// scratch plane.  No bounds checks: the guard bands of the scratch planes hold the identity.
+PYSTL_HD void load_run8(const float* plane, int start, float (&v)[8]) {
   const F4* P4 = reinterpret_cast<const F4*>(plane);
   const int f0 = start >> 2;  // arithmetic shift: floor
   const int r = start & 3;
-  const int nf = lext >> 2;
   float t[12];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    const int f = f0 + j;
-    if (f >= 0 && f < nf) {
-      const F4 q = P4[pf4(f)];
+    const F4 q = P4[pf4(f0 + j)];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) t[4 * j + k] = q.v[k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) t[4 * j + k] = fill;
-    }
+    for (int k = 0; k < 4; ++k) t[4 * j + k] = q.v[k];
   }
   // r is uniform across the CTA: a 4-way switch keeps every register index static
   switch (r) {
@@ -332,41 +318,106 @@ PYSTL_HD void load_run8(const float* plane, int lext, int start, float fill, flo
 }
 
 // ------------------------------------------------------------------ predicates
-// Strided ownership (sample p = tid + nt*i) so that the raw [sample][channel]
-// rows are read without bank conflicts; results go to the predicate planes.
-template <int SEM, class EX>
-PYSTL_HD void eval_predicates(EX& ex, const Ctx& c, const float* raw) {
+// Strided ownership (sample p = tid + nt*i): consecutive lanes read consecutive rows of the
+// raw [sample][channel] tile (one vector load per row for D = 1, 2, 4, 8) and write
+// consecutive words of the predicate plane.  Branch-free: rows past the horizon are
+// evaluated on whatever the staging area holds and never consumed.
+template <int DV>
+PYSTL_HD void load_row(const float* raw, int p, int D, float (&row)[8]) {
+  if constexpr (DV == 1) {
+    row[0] = raw[p];
+  } else if constexpr (DV == 2) {
+    struct alignas(8) F2 { float v[2]; };
+    const F2 q = reinterpret_cast<const F2*>(raw)[p];
+    row[0] = q.v[0];
+    row[1] = q.v[1];
+  } else if constexpr (DV == 4) {
+    const F4 q = reinterpret_cast<const F4*>(raw)[p];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) row[k] = q.v[k];
+  } else if constexpr (DV == 8) {
+    const F4 q0 = reinterpret_cast<const F4*>(raw)[2 * p], q1 = reinterpret_cast<const F4*>(raw)[2 * p + 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      row[k] = q0.v[k];
+      row[4 + k] = q1.v[k];
+    }
+  }
+  (void)D;
+}
+// row[ch] with ch uniform: a select chain keeps the row in registers
+template <int DV>
+PYSTL_HD float pick(const float (&row)[8], int ch) {
+  float x = row[0];
+#pragma unroll
+  for (int d = 1; d < DV; ++d) x = (ch == d) ? row[d] : x;
+  return x;
+}
+
+template <int DV>
+PYSTL_HD float chan(const float (&row)[8], const float* raw, int p, int D, int ch) {
+  if constexpr (DV > 0) return pick<DV>(row, ch);
+  else return raw[p * D + ch];
+}
+
+template <int SEM, int DV, class EX>
+PYSTL_HD void eval_predicates_d(EX& ex, const Ctx& c, const TileProgram& P, const float* raw) {
   constexpr int VW = Tr<SEM>::VW;
-  const TileProgram& P = *c.P;
-  const int D = c.g.D, nlive = c.n_live();
+  const int D = c.D, nt = c.nt;
+  const int np = P.n_preds;
   PYSTL_FOR_THREADS(ex, tid) {
+#pragma unroll 1
     for (int i = 0; i < kChunk; ++i) {
-      const int p = tid + c.g.nt * i;
-      if (p >= nlive) continue;
-      const float* row = raw + (int64_t)p * D;
-      for (int q = 0; q < P.n_preds; ++q) {
-        const TPred& pr = P.preds[q];
+      const int p = tid + nt * i;
+      const int pp = pidx(p);
+      float row[8];
+      if constexpr (DV > 0) load_row<DV>(raw, p, D, row);
+#pragma unroll 1
+      for (int q = 0; q < np; ++q) {
+        const int nterms = P.preds[q].n_terms;
+        const float bias = P.preds[q].bias;
         float acc;
-        if (SEM == SEM_CLASSIC && pr.f64) {
+        if ((SEM == SEM_CLASSIC) && P.preds[q].f64) {
           // the reference evaluates predicates in float64 (classic.py:20); same operations, same
           // order as formula.affine_predicate, one final rounding: bit-exact after the cast
           double a = 0.0;
-          for (int k = 0; k < pr.n_terms; ++k) a = fma((double)pr.coeff[k], (double)row[pr.ch[k]], a);
-          acc = (float)(a + (double)pr.bias);
+#pragma unroll 1
+          for (int k = 0; k < nterms; ++k)
+            a = fma((double)P.preds[q].coeff[k], (double)chan<DV>(row, raw, p, D, P.preds[q].ch[k]), a);
+          acc = (float)(a + (double)bias);
+        } else if (nterms == 1) {
+          // 0 + (+-x) is exact: a single-term predicate rounds once
+          acc = fmaf(P.preds[q].coeff[0], chan<DV>(row, raw, p, D, P.preds[q].ch[0]), 0.f) + bias;
+        } else if (nterms == 2) {
+          acc = fmaf(P.preds[q].coeff[0], chan<DV>(row, raw, p, D, P.preds[q].ch[0]), 0.f);
+          acc = fmaf(P.preds[q].coeff[1], chan<DV>(row, raw, p, D, P.preds[q].ch[1]), acc) + bias;
         } else {
-          acc = 0.f;  // 0 + (+-x) is exact, so single-term predicates round once
-          for (int k = 0; k < pr.n_terms; ++k) acc = fmaf(pr.coeff[k], row[pr.ch[k]], acc);
-          acc += pr.bias;
+          acc = 0.f;
+#pragma unroll 1
+          for (int k = 0; k < nterms; ++k)
+            acc = fmaf(P.preds[q].coeff[k], chan<DV>(row, raw, p, D, P.preds[q].ch[k]), acc);
+          acc += bias;
         }
-        const int pp = pidx(p);
+        const int dst = P.preds[q].dst;
         if constexpr (SEM == SEM_CUMULATIVE) {  // cumulative.py:29-30
-          c.plane(pr.dst, 0, VW)[pp] = fmaxf(0.f, acc);
-          c.plane(pr.dst, 1, VW)[pp] = fminf(0.f, acc);
+          c.plane(dst, 0, VW)[pp] = fmaxf(0.f, acc);
+          c.plane(dst, 1, VW)[pp] = fminf(0.f, acc);
         } else {
-          c.plane(pr.dst, 0, VW)[pp] = acc;
+          c.plane(dst, 0, VW)[pp] = acc;
         }
       }
     }
+  }
+}
+
+template <int SEM, class EX>
+PYSTL_HD void eval_predicates(EX& ex, const Ctx& c, const TileProgram& P, const float* raw) {
+  switch (c.D) {
+    case 1: eval_predicates_d<SEM, 1>(ex, c, P, raw); break;
+    case 2: eval_predicates_d<SEM, 2>(ex, c, P, raw); break;
+    case 4: eval_predicates_d<SEM, 4>(ex, c, P, raw); break;
+    case 8: eval_predicates_d<SEM, 8>(ex, c, P, raw); break;
+    default: eval_predicates_d<SEM, 0>(ex, c, P, raw); break;
   }
 }
 
@@ -376,6 +427,9 @@ PYSTL_HD void op_nary(EX& ex, const Ctx& c, const TInstr& in) {
   using R = Red<SEM, MODE>;
   using V = typename R::V;
   using A = typename R::A;
+  const int nsrc = in.nsrc, dst = in.dst;
+  const unsigned negmask = in.negmask;
+  const float sw = in.sw;
   PYSTL_FOR_THREADS(ex, tid) {
     RP rp = c.rp;
     A acc[8];
@@ -384,17 +438,19 @@ PYSTL_HD void op_nary(EX& ex, const Ctx& c, const TInstr& in) {
       float m[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) m[i] = -f_inf();
-      for (int j = 0; j < in.nsrc; ++j) {
+#pragma unroll 1
+      for (int j = 0; j < nsrc; ++j) {
         V v[8];
-        load_val8<SEM>(c, in.src[j], (in.negmask >> j) & 1, tid, v);
+        load_val8<SEM>(c, in.src[j], (negmask >> j) & 1, tid, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], R::expo(v[i], rp));
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = R::ident();
-      for (int j = 0; j < in.nsrc; ++j) {
+#pragma unroll 1
+      for (int j = 0; j < nsrc; ++j) {
         V v[8];
-        load_val8<SEM>(c, in.src[j], (in.negmask >> j) & 1, tid, v);
+        load_val8<SEM>(c, in.src[j], (negmask >> j) & 1, tid, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i].x[0] += fast_ex2(R::expo(v[i], rp) - m[i]);
       }
@@ -402,31 +458,43 @@ PYSTL_HD void op_nary(EX& ex, const Ctx& c, const TInstr& in) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         rp.shift = m[i];
-        o[i] = R::fin(acc[i], in.sw, rp);
+        o[i] = R::fin(acc[i], sw, rp);
       }
-      store_val8<SEM>(c, in.dst, tid, o);
+      store_val8<SEM>(c, dst, tid, o);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = R::ident();
-      for (int j = 0; j < in.nsrc; ++j) {
+#pragma unroll 1
+      for (int j = 0; j < nsrc; ++j) {
         V v[8];
-        load_val8<SEM>(c, in.src[j], (in.negmask >> j) & 1, tid, v);
+        load_val8<SEM>(c, in.src[j], (negmask >> j) & 1, tid, v);
+        const float wj = in.w[j];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = R::comb(acc[i], R::lift(v[i], rp, in.w[j]));
+        for (int i = 0; i < 8; ++i) acc[i] = R::comb(acc[i], R::lift(v[i], rp, wj));
       }
       V o[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = R::fin(acc[i], in.sw, rp);
-      store_val8<SEM>(c, in.dst, tid, o);
+      for (int i = 0; i < 8; ++i) o[i] = R::fin(acc[i], sw, rp);
+      store_val8<SEM>(c, dst, tid, o);
     }
   }
 }
 
-// number of samples of the clipped window [t+a, min(t+b, T-1)] (api.py:49-54)
-PYSTL_HD int window_count(int64_t t, int a, int b, int64_t T) {
-  const int64_t lo = t + a, hi = (t + b < T - 1) ? t + b : T - 1;
-  const int64_t lo2 = lo < 0 ? 0 : lo;
-  return hi >= lo2 ? (int)(hi - lo2 + 1) : 0;
+// A window instruction, decoded once per thread into registers.
+struct Win {
+  int a, b;    // offsets relative to t
+  int src;     // operand plane slot
+  bool neg;    // operand negated
+  int dst;
+};
+PYSTL_HD Win decode_win(const TInstr& in) { return Win{in.a, in.b, in.src[0], (in.negmask & 1) != 0, in.dst}; }
+
+// number of samples of the clipped window [t+a, min(t+b, T-1)] (api.py:49-54), in tile positions
+PYSTL_HD int window_count(const Ctx& c, int p, int a, int b) {
+  int lo = p + a, hi = p + b;
+  if (lo < c.first) lo = c.first;
+  if (hi > c.nlive - 1) hi = c.nlive - 1;
+  return hi - lo + 1;
 }
 
 // smooth only: block-wide max exponent of the operand over the live samples
@@ -434,7 +502,7 @@ template <int SEM, int MODE, class EX>
 PYSTL_HD float smooth_block_shift(EX& ex, const Ctx& c, int slot, bool neg) {
   using R = Red<SEM, MODE>;
   using V = typename R::V;
-  const int nlive = c.n_live();
+  const int nlive = c.nlive;
   PYSTL_FOR_THREADS(ex, tid) {
     V v[8];
     load_val8<SEM>(c, slot, neg, tid, v);
@@ -450,21 +518,20 @@ PYSTL_HD float smooth_block_shift(EX& ex, const Ctx& c, int slot, bool neg) {
 // smooth only: exact logsumexp of one window straight from the operand plane (rare path,
 // taken when the block-shifted sum lost its precision to underflow)
 template <int SEM, int MODE>
-PYSTL_HD Vec<1> smooth_exact_window(const Ctx& c, int slot, bool neg, int p, int a, int b) {
+PYSTL_HD Vec<1> smooth_exact_window(const Ctx& c, const Win& w, int p) {
   using R = Red<SEM, MODE>;
-  const float* pl = c.plane(slot, 0, 1);
-  const int nlive = c.n_live();
-  int lo = p + a, hi = p + b;
+  const float* pl = c.plane(w.src, 0, 1);
+  int lo = p + w.a, hi = p + w.b;
   if (lo < 0) lo = 0;
-  if (hi > nlive - 1) hi = nlive - 1;
+  if (hi > c.nlive - 1) hi = c.nlive - 1;
   float m = -f_inf();
   for (int q = lo; q <= hi; ++q) {
-    Vec<1> v{{neg ? -pl[pidx(q)] : pl[pidx(q)]}};
+    Vec<1> v{{w.neg ? -pl[pidx(q)] : pl[pidx(q)]}};
     m = fmaxf(m, R::expo(v, c.rp));
   }
   float s = 0.f;
   for (int q = lo; q <= hi; ++q) {
-    Vec<1> v{{neg ? -pl[pidx(q)] : pl[pidx(q)]}};
+    Vec<1> v{{w.neg ? -pl[pidx(q)] : pl[pidx(q)]}};
     s += fast_ex2(R::expo(v, c.rp) - m);
   }
   RP rp = c.rp;
@@ -474,33 +541,94 @@ PYSTL_HD Vec<1> smooth_exact_window(const Ctx& c, int slot, bool neg, int p, int
 
 constexpr float kSmoothTiny = 7.8886090522101181e-31f;  // 2^-100
 
+// Per-thread view of the window sizes of its 8 outputs: away from the ends of the trace every
+// window has b-a+1 samples (`interior`), so the clipped count is only computed near the horizon.
+struct WinCount {
+  bool interior;
+  float full;
+};
+PYSTL_HD WinCount win_count8(const Ctx& c, const Win& w, int p0) {
+  WinCount k;
+  k.interior = (p0 + 7 + w.b <= c.nlive - 1) && (p0 + w.a >= c.first);
+  k.full = (float)(w.b - w.a + 1);
+  return k;
+}
+
+// accumulators of the thread's 8 outputs -> values.  Thread-level fast path for windows that
+// are not clipped; the clipped count, the NaN of an empty window (the reference raises,
+// api.py:218-221) and smooth's exact recomputation are handled off the hot path.
 template <int SEM, int MODE>
-PYSTL_HD typename Red<SEM, MODE>::V finish_window(const Ctx& c, const TInstr& in, const RP& rp,
-                                                  typename Red<SEM, MODE>::A acc, int p) {
+PYSTL_HD void finish8(const Ctx& c, const Win& w, const RP& rp, const typename Red<SEM, MODE>::A (&acc)[8], int p0,
+                      const WinCount& k, typename Red<SEM, MODE>::V (&o)[8]) {
   using R = Red<SEM, MODE>;
-  const int n = window_count(c.e0 + p, in.a, in.b, c.T);
-  typename R::V o;
-  if (n <= 0) {
+  if (k.interior) {
 #pragma unroll
-    for (int w = 0; w < Tr<SEM>::VW; ++w) o.x[w] = f_nan();
-    return o;
+    for (int i = 0; i < 8; ++i) o[i] = R::fin(acc[i], k.full, rp);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = window_count(c, p0 + i, w.a, w.b);
+      o[i] = R::fin(acc[i], (float)(n > 0 ? n : 1), rp);
+      if (n <= 0) {
+#pragma unroll
+        for (int q = 0; q < Tr<SEM>::VW; ++q) o[i].x[q] = f_nan();
+      }
+    }
   }
   if constexpr (SEM == SEM_SMOOTH) {
-    if (!(acc.x[0] >= kSmoothTiny)) return smooth_exact_window<SEM, MODE>(c, in.src[0], in.negmask & 1, p, in.a, in.b);
+    bool lost = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) lost = lost || !(acc[i].x[0] >= kSmoothTiny);
+    if (lost) {  // rare: the block-shifted sum underflowed (or the window is empty)
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        float a_i = 0.f;  // acc[i] with a static register index
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j == i) a_i = acc[j].x[0];
+        if (!(a_i >= kSmoothTiny)) {
+          const float v = window_count(c, p0 + i, w.a, w.b) <= 0 ? f_nan() : smooth_exact_window<SEM, MODE>(c, w, p0 + i).x[0];
+          // (static indexing keeps o[] in registers)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j == i) o[j].x[0] = v;
+        }
+      }
+    }
   }
-  return R::fin(acc, (float)n, rp);
 }
 
 // lift the own chunk of the operand, treating samples past the horizon as the identity
 template <int SEM, int MODE>
-PYSTL_HD void lift_own8(const Ctx& c, const TInstr& in, const RP& rp, int tid, typename Red<SEM, MODE>::A (&x)[8]) {
+PYSTL_HD void lift_own8(const Ctx& c, const Win& w, const RP& rp, int tid, typename Red<SEM, MODE>::A (&x)[8]) {
   using R = Red<SEM, MODE>;
   typename R::V v[8];
-  load_val8<SEM>(c, in.src[0], in.negmask & 1, tid, v);
-  const int nlive = c.n_live();
+  load_val8<SEM>(c, w.src, w.neg, tid, v);
+  const int nlive = c.nlive;
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = (8 * tid + i < nlive) ? R::lift(v[i], rp, 1.f) : R::ident();
 }
+
+// Write the identity into the guard bands of `nplanes` scratch planes (and, if `chunks`, of the
+// chunk-aggregate arrays).  A few threads do it; it is part of the instruction's first phase.
+template <int AW>
+PYSTL_HD void fill_guards(const Ctx& c, int tid, Vec<AW> id, int nplanes_per_word, bool chunks) {
+  const int ncl = c.gl >> 3, ncr = c.gr >> 3;
+  for (int g = tid; g < ncl + ncr; g += c.nt) {
+    const int ch = g < ncr ? c.nt + g : -(g - ncr) - 1;
+#pragma unroll
+    for (int w = 0; w < AW; ++w) {
+      float t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = id.x[w];
+      for (int k = 0; k < nplanes_per_word; ++k) store8(c.scr(k * AW + w), ch, t);
+      if (chunks) c.chunk(w)[ch] = id.x[w];
+    }
+  }
+}
+
+// clamp a window offset to the tile: beyond +-lext every position is past the horizon anyway
+PYSTL_HD int clamp_off(int x, int lext) { return x > lext ? lext : (x < -lext ? -lext : x); }
 
 // ------------------------------------------------------------------ window, direct (W <= 8)
 template <int SEM, int MODE, class EX>
@@ -510,10 +638,12 @@ PYSTL_HD void op_win_direct(EX& ex, const Ctx& c, const TInstr& in) {
   using V = typename R::V;
   constexpr int AW = Tr<SEM>::AW;
   RP rp = c.rp;
-  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, in.src[0], in.negmask & 1);
+  const Win wn = decode_win(in);
+  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, wn.src, wn.neg);
+  const int wa = clamp_off(wn.a, c.lext), wb = clamp_off(wn.b, c.lext);
   PYSTL_FOR_THREADS(ex, tid) {
     A x[8];
-    lift_own8<SEM, MODE>(c, in, rp, tid, x);
+    lift_own8<SEM, MODE>(c, wn, rp, tid, x);
 #pragma unroll
     for (int w = 0; w < AW; ++w) {
       float t[8];
@@ -521,18 +651,18 @@ PYSTL_HD void op_win_direct(EX& ex, const Ctx& c, const TInstr& in) {
       for (int i = 0; i < 8; ++i) t[i] = x[i].x[w];
       store8(c.scr(w), tid, t);
     }
+    fill_guards<AW>(c, tid, R::ident(), 1, false);
   }
   ex.sync();
   PYSTL_FOR_THREADS(ex, tid) {
-    const int p0 = 8 * tid, W = in.b - in.a + 1;
+    const int p0 = 8 * tid, W = wb - wa + 1;
     const A id = R::ident();
     A acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = id;
-    const int nf = c.g.lext >> 2;
-    const int f_lo = (p0 + in.a) >> 2, f_hi = (p0 + 7 + in.b) >> 2;
+    const int f_lo = (p0 + wa) >> 2, f_hi = (p0 + 7 + wb) >> 2;
+#pragma unroll 1
     for (int f = f_lo; f <= f_hi; ++f) {
-      if (f < 0 || f >= nf) continue;  // outside the tile: identity
       F4 q[AW];
 #pragma unroll
       for (int w = 0; w < AW; ++w) q[w] = reinterpret_cast<const F4*>(c.scr(w))[pf4(f)];
@@ -541,28 +671,25 @@ PYSTL_HD void op_win_direct(EX& ex, const Ctx& c, const TInstr& in) {
         A e;
 #pragma unroll
         for (int w = 0; w < AW; ++w) e.x[w] = q[w].v[k];
-        const int d = 4 * f + k - p0 - in.a;  // window slot of output 0 this element fills
+        const int d = 4 * f + k - p0 - wa;  // window slot of output 0 this element fills
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (d - i >= 0 && d - i < W) acc[i] = R::comb(acc[i], e);
       }
     }
     V o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = finish_window<SEM, MODE>(c, in, rp, acc[i], p0 + i);
-    store_val8<SEM>(c, in.dst, tid, o);
+    finish8<SEM, MODE>(c, wn, rp, acc, p0, win_count8(c, wn, p0), o);
+    store_val8<SEM>(c, wn.dst, tid, o);
   }
   ex.sync();
 }
 
-// aggregate of chunk `ch`, identity outside the tile
+// aggregate of chunk `ch` (the guard entries hold the identity)
 template <int AW>
-PYSTL_HD Vec<AW> load_agg(const Ctx& c, int ch, int nt, Vec<AW> id) {
-  Vec<AW> r = id;
-  if (ch >= 0 && ch < nt) {
+PYSTL_HD Vec<AW> load_agg(const Ctx& c, int ch) {
+  Vec<AW> r;
 #pragma unroll
-    for (int w = 0; w < AW; ++w) r.x[w] = c.chunk(w)[ch];
-  }
+  for (int w = 0; w < AW; ++w) r.x[w] = c.chunk(w)[ch];
   return r;
 }
 
@@ -578,10 +705,11 @@ PYSTL_HD void op_win_vh(EX& ex, const Ctx& c, const TInstr& in) {
   using V = typename R::V;
   constexpr int AW = Tr<SEM>::AW;
   RP rp = c.rp;
-  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, in.src[0], in.negmask & 1);
+  const Win wn = decode_win(in);
+  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, wn.src, wn.neg);
   PYSTL_FOR_THREADS(ex, tid) {
     A x[8], suf[8], pre[8];
-    lift_own8<SEM, MODE>(c, in, rp, tid, x);
+    lift_own8<SEM, MODE>(c, wn, rp, tid, x);
     pre[0] = x[0];
 #pragma unroll
     for (int i = 1; i < 8; ++i) pre[i] = R::comb(pre[i - 1], x[i]);
@@ -599,23 +727,27 @@ PYSTL_HD void op_win_vh(EX& ex, const Ctx& c, const TInstr& in) {
       store8(c.scr(AW + w), tid, t);
       c.chunk(w)[tid] = pre[7].x[w];
     }
+    fill_guards<AW>(c, tid, R::ident(), 2, true);
   }
   ex.sync();
   PYSTL_FOR_THREADS(ex, tid) {
-    const int nt = c.g.nt, lext = c.g.lext;
     const A id = R::ident();
-    const int qa = in.a >> 3, ra = in.a & 7, qb = in.b >> 3, rb = in.b & 7;
+    const int wa = clamp_off(wn.a, c.lext), wb = clamp_off(wn.b, c.lext);
+    const int qa = wa >> 3, ra = wa & 7, qb = wb >> 3, rb = wb & 7;
     float sufv[AW][8], prev[AW][8];
 #pragma unroll
     for (int w = 0; w < AW; ++w) {
-      load_run8(c.scr(w), lext, 8 * tid + in.a, id.x[w], sufv[w]);
-      load_run8(c.scr(AW + w), lext, 8 * tid + in.b, id.x[w], prev[w]);
+      load_run8(c.scr(w), 8 * tid + wa, sufv[w]);
+      load_run8(c.scr(AW + w), 8 * tid + wb, prev[w]);
     }
-    const A al = load_agg<AW>(c, tid + qa + 1, nt, id), ar = load_agg<AW>(c, tid + qb, nt, id);
+    const A al = load_agg<AW>(c, tid + qa + 1), ar = load_agg<AW>(c, tid + qb);
     A core = id;
-    for (int ch = tid + qa + 2; ch <= tid + qb - 1; ++ch) core = R::comb(core, load_agg<AW>(c, ch, nt, id));
+#pragma unroll 2
+    for (int ch = tid + qa + 2; ch <= tid + qb - 1; ++ch) core = R::comb(core, load_agg<AW>(c, ch));
     const bool two = qb >= qa + 2;
-    V o[8];
+    // the four possible sets of whole chunks between the two partial ones, in time order
+    const A m_l = R::comb(al, core), m_r = R::comb(core, ar), m_lr = R::comb(m_l, ar);
+    A acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       A s, e;
@@ -627,14 +759,15 @@ PYSTL_HD void op_win_vh(EX& ex, const Ctx& c, const TInstr& in) {
       const int cs = (ra + i) >> 3, ce = (rb + i) >> 3;  // 0 or 1: did start / end spill into the next chunk
       const bool inc_l = (cs == 0) && (qb + ce - 1 >= qa + 1);
       const bool inc_r = (ce == 1) && two;
-      A acc = s;
-      if (inc_l) acc = R::comb(acc, al);
-      acc = R::comb(acc, core);
-      if (inc_r) acc = R::comb(acc, ar);
-      acc = R::comb(acc, e);
-      o[i] = finish_window<SEM, MODE>(c, in, rp, acc, 8 * tid + i);
+      A mid;
+#pragma unroll
+      for (int w = 0; w < AW; ++w)
+        mid.x[w] = inc_l ? (inc_r ? m_lr.x[w] : m_l.x[w]) : (inc_r ? m_r.x[w] : core.x[w]);
+      acc[i] = R::comb(R::comb(s, mid), e);
     }
-    store_val8<SEM>(c, in.dst, tid, o);
+    V o[8];
+    finish8<SEM, MODE>(c, wn, rp, acc, 8 * tid, win_count8(c, wn, 8 * tid), o);
+    store_val8<SEM>(c, wn.dst, tid, o);
   }
   ex.sync();
 }
@@ -658,10 +791,12 @@ PYSTL_HD void op_win_suffix(EX& ex, const Ctx& c, const TInstr& in) {
   using V = typename R::V;
   constexpr int AW = Tr<SEM>::AW;
   RP rp = c.rp;
-  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, in.src[0], in.negmask & 1);
+  Win wn = decode_win(in);
+  wn.b = 0x3fffffff;  // open end: clipped at the horizon by window_count
+  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, wn.src, wn.neg);
   PYSTL_FOR_THREADS(ex, tid) {
     A x[8];
-    lift_own8<SEM, MODE>(c, in, rp, tid, x);
+    lift_own8<SEM, MODE>(c, wn, rp, tid, x);
     A agg = x[7];
 #pragma unroll
     for (int i = 6; i >= 0; --i) agg = R::comb(x[i], agg);
@@ -669,10 +804,10 @@ PYSTL_HD void op_win_suffix(EX& ex, const Ctx& c, const TInstr& in) {
     for (int w = 0; w < AW; ++w) c.chunk(w)[tid] = agg.x[w];
   }
   ex.sync();
-  ex.template excl_suffix_scan<AW, RedOp<SEM, MODE>>(c.chunk(0), c.g.nt, c.red());
+  ex.template excl_suffix_scan<AW, RedOp<SEM, MODE>>(c.chunk(0), c.nt, (int)(c.chunk(1) - c.chunk(0)), c.red());
   PYSTL_FOR_THREADS(ex, tid) {
     A x[8], suf[8];
-    lift_own8<SEM, MODE>(c, in, rp, tid, x);
+    lift_own8<SEM, MODE>(c, wn, rp, tid, x);
     A tail;
 #pragma unroll
     for (int w = 0; w < AW; ++w) tail.x[w] = c.chunk(w)[tid];
@@ -686,24 +821,22 @@ PYSTL_HD void op_win_suffix(EX& ex, const Ctx& c, const TInstr& in) {
       for (int i = 0; i < 8; ++i) t[i] = suf[i].x[w];
       store8(c.scr(w), tid, t);
     }
+    fill_guards<AW>(c, tid, R::ident(), 1, false);
   }
   ex.sync();
   PYSTL_FOR_THREADS(ex, tid) {
-    const A id = R::ident();
     float sv[AW][8];
 #pragma unroll
-    for (int w = 0; w < AW; ++w) load_run8(c.scr(w), c.g.lext, 8 * tid + in.a, id.x[w], sv[w]);
+    for (int w = 0; w < AW; ++w) load_run8(c.scr(w), 8 * tid + clamp_off(wn.a, c.lext), sv[w]);
     V o[8];
-    TInstr open = in;
-    open.b = 0x3fffffff;
+    A acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      A acc;
 #pragma unroll
-      for (int w = 0; w < AW; ++w) acc.x[w] = sv[w][i];
-      o[i] = finish_window<SEM, MODE>(c, open, rp, acc, 8 * tid + i);
+      for (int w = 0; w < AW; ++w) acc[i].x[w] = sv[w][i];
     }
-    store_val8<SEM>(c, in.dst, tid, o);
+    finish8<SEM, MODE>(c, wn, rp, acc, 8 * tid, WinCount{false, 0.f}, o);
+    store_val8<SEM>(c, wn.dst, tid, o);
   }
   ex.sync();
 }
@@ -721,18 +854,27 @@ struct ClampOp {
   }
 };
 
-PYSTL_HD void clamp_load_lr(const Ctx& c, const TInstr& in, int tid, int nlive, ClampOp::A (&x)[8]) {
+struct Pair {  // a two-operand instruction, decoded once per thread
+  int sl, sr, dst;
+  bool nl, nr;
+};
+PYSTL_HD Pair decode_pair(const TInstr& in) {
+  return Pair{in.src[0], in.src[1], in.dst, (in.negmask & 1) != 0, (in.negmask & 2) != 0};
+}
+
+PYSTL_HD void clamp_load_lr(const Ctx& c, const Pair& in, int tid, int nlive, ClampOp::A (&x)[8]) {
   Vec<1> l[8], r[8];
-  load_val8<SEM_CLASSIC>(c, in.src[0], in.negmask & 1, tid, l);
-  load_val8<SEM_CLASSIC>(c, in.src[1], (in.negmask >> 1) & 1, tid, r);
+  load_val8<SEM_CLASSIC>(c, in.sl, in.nl, tid, l);
+  load_val8<SEM_CLASSIC>(c, in.sr, in.nr, tid, r);
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = (8 * tid + i < nlive) ? ClampOp::A{{l[i].x[0], r[i].x[0]}} : ClampOp::ident();
 }
 
 template <class EX>
-PYSTL_HD void op_clamp_scan(EX& ex, const Ctx& c, const TInstr& in) {
+PYSTL_HD void op_clamp_scan(EX& ex, const Ctx& c, const TInstr& ins) {
   using A = ClampOp::A;
-  const int nlive = c.n_live();
+  const int nlive = c.nlive;
+  const Pair in = decode_pair(ins);
   PYSTL_FOR_THREADS(ex, tid) {
     A x[8];
     clamp_load_lr(c, in, tid, nlive, x);
@@ -743,7 +885,7 @@ PYSTL_HD void op_clamp_scan(EX& ex, const Ctx& c, const TInstr& in) {
     c.chunk(1)[tid] = agg.x[1];
   }
   ex.sync();
-  ex.template excl_suffix_scan<2, ClampOp>(c.chunk(0), c.g.nt, c.red());
+  ex.template excl_suffix_scan<2, ClampOp>(c.chunk(0), c.nt, (int)(c.chunk(1) - c.chunk(0)), c.red());
   PYSTL_FOR_THREADS(ex, tid) {
     A x[8];
     clamp_load_lr(c, in, tid, nlive, x);
@@ -769,7 +911,7 @@ template <>
 struct UntilState<SEM_CLASSIC> {  // classic.py:63-67
   float pm, best;
   PYSTL_HD void init() { pm = f_inf(); best = -f_inf(); }
-  PYSTL_HD void step(Vec<1> l, Vec<1> r, bool cand, const RP&, const TInstr&) {
+  PYSTL_HD void step(Vec<1> l, Vec<1> r, bool cand, const RP&, float, float) {
     pm = fminf(pm, l.x[0]);
     if (cand) best = fmaxf(best, fminf(pm, r.x[0]));
   }
@@ -780,7 +922,7 @@ template <>
 struct UntilState<SEM_CUMULATIVE> {  // cumulative.py:96-102
   float pm0, pm1, s0, s1;
   PYSTL_HD void init() { pm0 = pm1 = f_inf(); s0 = s1 = 0.f; }
-  PYSTL_HD void step(Vec<2> l, Vec<2> r, bool cand, const RP&, const TInstr&) {
+  PYSTL_HD void step(Vec<2> l, Vec<2> r, bool cand, const RP&, float, float) {
     pm0 = fminf(pm0, l.x[0]);
     pm1 = fminf(pm1, l.x[1]);
     if (cand) {
@@ -799,7 +941,7 @@ template <>
 struct UntilState<SEM_SMOOTH> {
   float S, acc;
   PYSTL_HD void init() { S = 0.f; acc = 0.f; }
-  PYSTL_HD void step(Vec<1> l, Vec<1> r, bool cand, const RP& rp, const TInstr&) {
+  PYSTL_HD void step(Vec<1> l, Vec<1> r, bool cand, const RP& rp, float, float) {
     S += fast_ex2(-l.x[0] * rp.k - rp.shift);
     if (cand) acc += 1.f / (S + fast_ex2(-r.x[0] * rp.k - rp.shift));
   }
@@ -811,15 +953,15 @@ struct UntilState<SEM_AGM> {  // agm.py:112-130 (uniform weights_left / weights_
   Vec<2> pre, orr;
   int k;
   PYSTL_HD void init() { pre = Red<SEM_AGM, MODE_AND>::ident(); orr = Red<SEM_AGM, MODE_OR>::ident(); k = 0; }
-  PYSTL_HD void step(Vec<1> l, Vec<1> r, bool cand, const RP& rp, const TInstr& in) {
+  PYSTL_HD void step(Vec<1> l, Vec<1> r, bool cand, const RP& rp, float w0, float w1) {
     using RA = Red<SEM_AGM, MODE_AND>;
     using RO = Red<SEM_AGM, MODE_OR>;
     pre = RA::comb(pre, RA::lift(l, rp, 1.f));
     ++k;
     if (cand) {
       const Vec<1> y = RA::fin(pre, (float)k, rp);
-      const Vec<2> pr = RA::comb(RA::lift(y, rp, in.w[0]), RA::lift(r, rp, in.w[1]));
-      orr = RO::comb(orr, RO::lift(RA::fin(pr, in.w[0] + in.w[1], rp), rp, 1.f));
+      const Vec<2> pr = RA::comb(RA::lift(y, rp, w0), RA::lift(r, rp, w1));
+      orr = RO::comb(orr, RO::lift(RA::fin(pr, w0 + w1, rp), rp, 1.f));
     }
   }
   PYSTL_HD Vec<1> done(int ncand, const RP& rp) { return Red<SEM_AGM, MODE_OR>::fin(orr, (float)ncand, rp); }
@@ -830,37 +972,41 @@ struct UntilState<SEM_DGMSR> {  // dgmsr.py:88-118 (uniform weights_left / weigh
   Vec<2> pre, orr;
   int k;
   PYSTL_HD void init() { pre = Red<SEM_DGMSR, MODE_AND>::ident(); orr = Red<SEM_DGMSR, MODE_OR>::ident(); k = 0; }
-  PYSTL_HD void step(Vec<1> l, Vec<1> r, bool cand, const RP& rp, const TInstr& in) {
+  PYSTL_HD void step(Vec<1> l, Vec<1> r, bool cand, const RP& rp, float w0, float w1) {
     using RA = Red<SEM_DGMSR, MODE_AND>;
     using RO = Red<SEM_DGMSR, MODE_OR>;
     pre = RA::comb(pre, RA::lift(l, rp, 1.f));
     ++k;
     if (cand) {
       const Vec<1> y = RA::fin(pre, (float)k, rp);
-      const Vec<2> pr = RA::comb(RA::lift(y, rp, in.w[0]), RA::lift(r, rp, in.w[1]));
-      orr = RO::comb(orr, RO::lift(RA::fin(pr, in.w[0] + in.w[1], rp), rp, 1.f));
+      const Vec<2> pr = RA::comb(RA::lift(y, rp, w0), RA::lift(r, rp, w1));
+      orr = RO::comb(orr, RO::lift(RA::fin(pr, w0 + w1, rp), rp, 1.f));
     }
   }
   PYSTL_HD Vec<1> done(int ncand, const RP& rp) { return Red<SEM_DGMSR, MODE_OR>::fin(orr, (float)ncand, rp); }
 };
 
 template <int SEM, class EX>
-PYSTL_HD void op_until(EX& ex, const Ctx& c, const TInstr& in) {
+PYSTL_HD void op_until(EX& ex, const Ctx& c, const TInstr& ins) {
   constexpr int VW = Tr<SEM>::VW;
   using V = Vec<VW>;
-  const int nlive = c.n_live();
+  const int nlive = c.nlive;
+  const Pair in = decode_pair(ins);
+  const int ua = ins.a, ub = ins.b;
+  const bool open = ins.unbounded != 0;
+  const float w0 = ins.w[0], w1 = ins.w[1];
   RP rp = c.rp;
   if constexpr (SEM == SEM_SMOOTH) {
     // shift = max over both operands of the exponent -v/tau
-    const float ml = smooth_block_shift<SEM, MODE_AND>(ex, c, in.src[0], in.negmask & 1);
-    const float mr = smooth_block_shift<SEM, MODE_AND>(ex, c, in.src[1], (in.negmask >> 1) & 1);
+    const float ml = smooth_block_shift<SEM, MODE_AND>(ex, c, in.sl, in.nl);
+    const float mr = smooth_block_shift<SEM, MODE_AND>(ex, c, in.sr, in.nr);
     rp.shift = fmaxf(ml, mr);
   }
   // stage l and r (negations applied) in scratch planes so that phase 2 reads plain runs
   PYSTL_FOR_THREADS(ex, tid) {
     V l[8], r[8];
-    load_val8<SEM>(c, in.src[0], in.negmask & 1, tid, l);
-    load_val8<SEM>(c, in.src[1], (in.negmask >> 1) & 1, tid, r);
+    load_val8<SEM>(c, in.sl, in.nl, tid, l);
+    load_val8<SEM>(c, in.sr, in.nr, tid, r);
 #pragma unroll
     for (int w = 0; w < VW; ++w) {
       float t[8];
@@ -875,12 +1021,13 @@ PYSTL_HD void op_until(EX& ex, const Ctx& c, const TInstr& in) {
   ex.sync();
   PYSTL_FOR_THREADS(ex, tid) {
     const int p0 = 8 * tid;
-    const int b = in.unbounded ? c.g.lext : in.b;
+    const int b = open ? c.lext : ub;
     UntilState<SEM> st[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) st[i].init();
     int q_hi = p0 + 7 + b;
     if (q_hi > nlive - 1) q_hi = nlive - 1;
+#pragma unroll 1
     for (int f = p0 >> 2; f <= (q_hi >> 2); ++f) {
       F4 ql[VW], qr[VW];
 #pragma unroll
@@ -902,17 +1049,16 @@ PYSTL_HD void op_until(EX& ex, const Ctx& c, const TInstr& in) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int kk = d - i;  // offset inside output i's window
-          if (kk >= 0 && kk <= b) st[i].step(l, r, kk >= in.a, rp, in);
+          if (kk >= 0 && kk <= b) st[i].step(l, r, kk >= ua, rp, w0, w1);
         }
       }
     }
     V o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int64_t t = c.e0 + p0 + i;
-      int64_t last = c.T - 1 - t;  // min(b, T-1-t): api.py:284-293 + classic.py:59
-      if (!in.unbounded && last > in.b) last = in.b;
-      const int ncand = (int)(last - in.a + 1);
+      int last = nlive - 1 - (p0 + i);  // min(b, T-1-t): api.py:284-293 + classic.py:59
+      if (!open && last > ub) last = ub;
+      const int ncand = last - ua + 1;
       if (ncand <= 0 || p0 + i >= nlive) {
 #pragma unroll
         for (int w = 0; w < VW; ++w) o[i].x[w] = f_nan();
@@ -935,7 +1081,7 @@ PYSTL_HD void op_until(EX& ex, const Ctx& c, const TInstr& in) {
               } else {
                 S += fast_ex2(zl - mS);
               }
-              if (kk >= in.a) {
+              if (kk >= ua) {
                 const float zr = -pr[pidx(p + kk)] * rp.k;
                 const float mc = fmaxf(mS, zr);
                 const float cl = -(mc + fast_lg2(S * fast_ex2(mS - mc) + fast_ex2(zr - mc)));  // log2 of the term
@@ -994,38 +1140,70 @@ PYSTL_HD void run_instr(EX& ex, const Ctx& c, const TInstr& in) {
 
 // Evaluate the whole program on a tile whose raw samples are already in shared memory.
 template <int SEM, class EX>
-PYSTL_HD void run_program(EX& ex, const Ctx& c, const float* raw) {
-  eval_predicates<SEM>(ex, c, raw);
+PYSTL_HD void run_program(EX& ex, const Ctx& c, const TileProgram& P, const float* raw) {
+  eval_predicates<SEM>(ex, c, P, raw);
   ex.sync();
-  const TileProgram& P = *c.P;
+#pragma unroll 1
   for (int i = 0; i < P.n_instr; ++i) run_instr<SEM>(ex, c, P.ins[i]);
 }
 
 // ------------------------------------------------------------------ result
-// Write the formula value of this tile's outputs [0, n_out) to out_trace[(e0 + p) * C + w].
-// Outputs the reference raises on (api.py:218-221) are NaN.  Optionally accumulates the
-// sum of the valid outputs (all channels) for the fused mean-robustness reduction.
+// Write the formula value of this tile's outputs [0, n_out) to out_tile[p * C + w]
+// (out_tile = &out[b, e0, 0]).  Outputs the reference raises on (api.py:218-221) are NaN.
+// The root plane is re-read with lane-consecutive float4 ownership (float4 index
+// tid + nt*j) so that the global stores are fully coalesced 128-bit stores.
+// Optionally accumulates the sum of the valid outputs (all channels) for the fused
+// mean-robustness reduction.
 template <int SEM, class EX>
-PYSTL_HD void store_root(EX& ex, const Ctx& c, float* out_trace, int n_out, double* mean_acc) {
+PYSTL_HD void store_root(EX& ex, const Ctx& c, const TileProgram& P, float* out_tile, int n_out, double* mean_acc) {
   constexpr int VW = Tr<SEM>::VW;
-  const TileProgram& P = *c.P;
-  const int64_t last_valid = P.raises_always ? -1 : c.T - 1 - P.start_slack;
+  const int root = P.root;
+  const bool neg = P.root_neg != 0;
+  int n_store = n_out < c.nlive ? n_out : c.nlive;
+  const bool vec = (reinterpret_cast<uintptr_t>(out_tile) & 15) == 0;
+  ex.sync();  // the root plane was written with blocked ownership
   PYSTL_FOR_THREADS(ex, tid) {
-    Vec<VW> v[8];
-    load_val8<SEM>(c, P.root, P.root_neg != 0, tid, v);
     float part = 0.f;
-    const int p0 = 8 * tid;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int64_t t = c.e0 + p0 + i;
-      if (p0 + i < n_out && t < c.T) {
-        const bool ok = t <= last_valid;
+    for (int j = 0; j < 2; ++j) {
+      const int f = tid + c.nt * j;  // logical float4 index
+      const int p = 4 * f;
+      if (p >= n_store) continue;
+      Vec<VW> v[4];
+      {
+        F4 q[VW];
 #pragma unroll
-        for (int w = 0; w < VW; ++w) {
-          const float x = ok ? v[i].x[w] : f_nan();
-          out_trace[t * VW + w] = x;
-          if (ok) part += x;
+        for (int w = 0; w < VW; ++w) q[w] = reinterpret_cast<const F4*>(c.plane(root, w, VW))[pf4(f)];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int w = 0; w < VW; ++w) v[k].x[w] = q[w].v[k];
+          if (neg) v[k] = negate<SEM>(v[k]);
+          if (p + k > c.last_ok) {
+#pragma unroll
+            for (int w = 0; w < VW; ++w) v[k].x[w] = f_nan();
+          } else if (p + k < n_store) {
+#pragma unroll
+            for (int w = 0; w < VW; ++w) part += v[k].x[w];
+          }
         }
+      }
+      float* dst = out_tile + (int64_t)p * VW;
+      if (vec && p + 4 <= n_store) {
+        F4* d4 = reinterpret_cast<F4*>(dst);
+        if constexpr (VW == 1) {
+          d4[0] = F4{{v[0].x[0], v[1].x[0], v[2].x[0], v[3].x[0]}};
+        } else {
+          d4[0] = F4{{v[0].x[0], v[0].x[1], v[1].x[0], v[1].x[1]}};
+          d4[1] = F4{{v[2].x[0], v[2].x[1], v[3].x[0], v[3].x[1]}};
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (p + k < n_store) {
+#pragma unroll
+            for (int w = 0; w < VW; ++w) dst[k * VW + w] = v[k].x[w];
+          }
       }
     }
     ex.put(tid, part);
@@ -1053,14 +1231,14 @@ struct HostExec {
     for (int i = 0; i < nt_; ++i) s += stash[i];
     *acc += s;
   }
-  // a[w*n + c] <- comb(a[c+1], ..., a[n-1]) (identity for the last chunk), in time order
+  // a[w*stride + c] <- comb(a[c+1], ..., a[n-1]) (identity for the last chunk), in time order
   template <int AW, class OP>
-  void excl_suffix_scan(float* a, int n, float*) {
+  void excl_suffix_scan(float* a, int n, int stride, float*) {
     typename OP::A run = OP::ident();
     for (int ch = n - 1; ch >= 0; --ch) {
       typename OP::A cur;
-      for (int w = 0; w < AW; ++w) cur.x[w] = a[w * n + ch];
-      for (int w = 0; w < AW; ++w) a[w * n + ch] = run.x[w];
+      for (int w = 0; w < AW; ++w) cur.x[w] = a[w * stride + ch];
+      for (int w = 0; w < AW; ++w) a[w * stride + ch] = run.x[w];
       run = OP::comb(cur, run);
     }
   }

@@ -29,20 +29,14 @@ static void run_all(const Lowered& lw, const TileGeom& g, const float* signal, f
     for (int j = 0; j < g.n_tiles; ++j) {
       // poison shared memory so that reads of never-written samples show up
       for (int i = 0; i < g.smem_floats; ++i) base[i] = NAN;
-      Ctx c;
-      c.smem = base;
-      c.g = g;
-      c.P = &lw.prog;
-      c.e0 = (int64_t)j * g.lout;
-      c.T = g.T;
-      c.rp = make_rp(lw.prog);
-      float* raw = c.scr(0);
-      const int nlive = c.n_live();
-      const float* src = signal + (b * g.T + c.e0) * g.D;
-      for (int i = 0; i < nlive * g.D; ++i) raw[i] = src[i];
+      const int64_t e0 = (int64_t)j * g.lout;
+      const Ctx c = make_ctx(base, g, lw.prog, e0);
+      float* raw = c.raw();
+      const float* src = signal + (b * g.T + e0) * g.D;
+      for (int i = 0; i < c.nlive * g.D; ++i) raw[i] = src[i];
       HostExec ex(g.nt);
-      run_program<SEM>(ex, c, raw);
-      store_root<SEM>(ex, c, out + b * g.T * VW, g.lout, mean_acc);
+      run_program<SEM>(ex, c, lw.prog, raw);
+      store_root<SEM>(ex, c, lw.prog, out + (b * g.T + e0) * VW, g.lout, mean_acc);
     }
   }
 }
