@@ -10,6 +10,7 @@
 #include "../../include/pystl_b200.h"
 #include "program.h"
 #include "tile_eval.h"
+#include "tile_bwd.h"
 
 namespace pystl {
 
@@ -22,6 +23,8 @@ struct DevExec {
   __device__ __forceinline__ int t1() const { return tid_ + 1; }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ void put(int, float v) { stash_ = v; }
+  __device__ __forceinline__ float get(int) const { return stash_; }
+  __device__ __forceinline__ void atomic_add(float* p, float v) { atomicAdd(p, v); }
 
   // max over a warp with one REDUX: floats are mapped to integers of the same order
   static __device__ __forceinline__ float warp_max(float v) {
@@ -166,6 +169,34 @@ __global__ void __launch_bounds__(MAXT, MINB) fwd_kernel(const __grid_constant__
   run_program<SEM>(ex, c, P, raw);
   constexpr int VW = Tr<SEM>::VW;
   store_root<SEM>(ex, c, P, out + (b * g.T + e0) * VW, g.lout, mean_acc);
+}
+
+// ------------------------------------------------------------------ backward kernel
+// grad_out == nullptr: constant cotangent `scale` (the mean-robustness loss)
+template <int SEM, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) bwd_kernel(const __grid_constant__ TileProgram P, const __grid_constant__ TileGeom g,
+                                                        const float* __restrict__ signal, const float* __restrict__ grad_out,
+                                                        float scale, float* __restrict__ grad_signal) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bar;
+  DevExec ex;
+  if (ex.tid_ == 0) mbar_init(&bar, 1);
+  __syncthreads();
+
+  const int64_t tile = blockIdx.x;
+  const int64_t b = tile / g.n_tiles;
+  const int j = (int)(tile - b * g.n_tiles);
+  const int64_t t0 = (int64_t)j * g.lout;
+  const int64_t e0 = t0 > g.hh ? t0 - g.hh : 0;
+  const Ctx c = make_ctx(smem, g, P, e0);
+  const int p_lo = (int)(t0 - e0);
+  int p_hi = p_lo + g.lout;
+  if (p_hi > c.nlive) p_hi = c.nlive;
+
+  float* raw = c.raw();
+  stage_raw(raw, signal + (b * g.T + e0) * g.D, c.nlive * g.D, &bar, ex.tid_, ex.nt_);
+  run_backward<SEM>(ex, c, P, raw, grad_out ? grad_out + (b * g.T + e0) : nullptr, scale,
+                    grad_signal + (b * g.T + e0) * g.D, p_lo, p_hi);
 }
 
 }  // namespace pystl

@@ -35,6 +35,7 @@ struct Fail {
 
 struct Lowerer {
   const pystl_formula_t* f = nullptr;
+  bool backward = false;
   Lowered* out = nullptr;
   char* msg = nullptr;
   int msg_len = 0;
@@ -70,7 +71,7 @@ struct Lowerer {
     return s;
   }
   void release(int slot) {
-    if (--slot_refs[slot] == 0) free_slots.push_back(slot);
+    if (--slot_refs[slot] == 0 && !backward) free_slots.push_back(slot);  // backward: no reuse
   }
 
   TileProgram& P() { return out->prog; }
@@ -209,6 +210,8 @@ struct Lowerer {
       r.inv2p = (float)(0.5 / pp);
       r.p = pp;
     }
+    if (backward && sem == SEM_CUMULATIVE)
+      fail(PYSTL_E_UNSUPPORTED, "the gradient of the cumulative semantics is not implemented yet");
     if (sem == SEM_SMOOTH && !(f->temperature > 0.f)) fail(PYSTL_E_INVALID, "temperature must be > 0.");  // smooth.py:12-15
     if (sem == SEM_DGMSR && (!(f->eps > 0.f) || f->p < 1)) fail(PYSTL_E_INVALID, "dgmsr needs eps > 0 and p >= 1");
     const bool uses_weights = (sem == SEM_AGM || sem == SEM_DGMSR);
@@ -339,6 +342,8 @@ struct Lowerer {
           break;
         }
         case PYSTL_NODE_UNTIL: {
+          if (backward && sem != SEM_CLASSIC)
+            fail(PYSTL_E_UNSUPPORTED, "the gradient of Until is only implemented for the classical semantics so far");
           if (uses_weights && (nd.w_off >= 0 || nd.w2_off >= 0))
             fail(PYSTL_E_UNSUPPORTED, "weights_left / weights_right on Until are not implemented for agm / dgmsr yet");
           float wp0 = 1.f, wp1 = 1.f;
@@ -425,7 +430,7 @@ struct Lowerer {
 
 }  // namespace
 
-int lower_formula(const ::pystl_formula* f, Lowered* out, char* msg, int msg_len) {
+int lower_formula(const ::pystl_formula* f, bool backward, Lowered* out, char* msg, int msg_len) {
   if (msg && msg_len > 0) msg[0] = 0;
   if (!f || !out) {
     if (msg) snprintf(msg, msg_len, "null formula");
@@ -433,6 +438,7 @@ int lower_formula(const ::pystl_formula* f, Lowered* out, char* msg, int msg_len
   }
   Lowerer L;
   L.f = reinterpret_cast<const pystl_formula_t*>(f);
+  L.backward = backward;
   L.out = out;
   L.msg = msg;
   L.msg_len = msg_len;
@@ -450,7 +456,8 @@ static bool needs_full_trace(const TileProgram& P) {
   return false;
 }
 
-int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_nt, TileGeom* g, char* msg, int msg_len) {
+int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_nt, bool backward, TileGeom* g, char* msg,
+                  int msg_len) {
   const TileProgram& P = lw.prog;
   auto fail = [&](int code, const char* fmt, auto... a) {
     if (msg && msg_len > 0) snprintf(msg, msg_len, fmt, a...);
@@ -461,9 +468,11 @@ int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_
     for (int k = 0; k < P.preds[q].n_terms; ++k)
       if (P.preds[q].ch[k] < 0 || P.preds[q].ch[k] >= D)
         return fail(PYSTL_E_INVALID, "predicate reads channel %d of a %d-channel signal", (int)P.preds[q].ch[k], D);
-  const int vw = P.sem == SEM_CUMULATIVE ? 2 : 1;
+  // the classic backward kernel evaluates SEM_CLASSIC_SRC: two words per value
+  const int vw = (P.sem == SEM_CUMULATIVE || (backward && P.sem == SEM_CLASSIC)) ? 2 : 1;
   const int aw = (P.sem == SEM_CLASSIC || P.sem == SEM_SMOOTH) ? 1 : 2;
-  const int scr_planes = 2 * std::max(aw, vw);
+  const int scr_planes = backward ? 4 : 2 * std::max(aw, vw);
+  const int hh = backward && lw.lookahead > 0 ? ((lw.lookahead + 7) / 8) * 8 : 0;
   const bool full = needs_full_trace(P) || lw.lookahead < 0;
   // furthest offsets any window instruction reads at (guards of the scratch planes)
   int max_b = 0, min_a = 0;
@@ -486,19 +495,26 @@ int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_
     t.lext = kChunk * nt;
     t.vw = vw;
     t.scr_planes = scr_planes;
+    t.bwd = backward ? 1 : 0;
+    t.hh = hh;
+    t.n_slots = P.n_slots;
     if (Tn <= t.lext) {
       t.lout = t.lext;
       t.n_tiles = 1;
     } else {
       if (full) return false;
-      t.lout = ((t.lext - lw.lookahead) / 8) * 8;
+      t.lout = backward ? t.lext - 2 * hh : ((t.lext - lw.lookahead) / 8) * 8;
       if (t.lout < 8) return false;
       t.n_tiles = (int)((Tn + t.lout - 1) / t.lout);
     }
     t.gr = ((std::min(max_b, t.lext) + 4 + 7) / 8) * 8;
     t.gl = ((std::min(-min_a, t.lext) + 7) / 8) * 8;
+    if (backward) {  // the adjoint windows look back as far as the forward ones look ahead
+      const int reach = needs_full_trace(P) ? t.lext : std::min(std::max(max_b, -min_a), t.lext);
+      t.gl = t.gr = ((reach + 8 + 7) / 8) * 8;
+    }
     t.off_planes = 0;
-    t.off_scratch = P.n_slots * vw * t.lext;
+    t.off_scratch = P.n_slots * (vw + (backward ? 1 : 0)) * t.lext;
     // the raw [sample][channel] rows share their storage with the scratch planes
     const int raw_floats = ((t.lext * D + 3) / 4) * 4;
     t.off_chunk = t.off_scratch + std::max(raw_floats, scr_planes * (t.gl + t.lext + t.gr));

@@ -18,7 +18,16 @@ constexpr int kMaxPreds = 16;   // distinct affine predicates per formula
 constexpr int kMaxInstr = 40;   // lowered instructions per formula
 constexpr int kMaxThreads = 1024;
 
-enum Sem : int32_t { SEM_CLASSIC = 0, SEM_SMOOTH = 1, SEM_CUMULATIVE = 2, SEM_AGM = 3, SEM_DGMSR = 4 };
+enum Sem : int32_t {
+  SEM_CLASSIC = 0,
+  SEM_SMOOTH = 1,
+  SEM_CUMULATIVE = 2,
+  SEM_AGM = 3,
+  SEM_DGMSR = 4,
+  // kernel-internal: classic values that carry the leaf they came from (predicate, position,
+  // sign) through every min / max; the classic backward pass is one scatter through them
+  SEM_CLASSIC_SRC = 5
+};
 
 // which reduction an instruction performs
 enum Mode : int32_t {
@@ -98,6 +107,9 @@ struct TileGeom {
   int32_t n_tiles;   // tiles per trace
   int32_t vw;        // words per value (2 for cumulative)
   int32_t scr_planes;  // scratch planes
+  int32_t bwd;         // geometry of the backward kernel: halo of `hh` samples on both sides
+  int32_t hh;          // look-ahead rounded up to 8 (backward only)
+  int32_t n_slots;     // value slots; the backward kernel adds one adjoint plane per slot
   int32_t gl, gr;      // scratch guard bands (floats, multiples of 8) left / right of the tile:
                        // hold the identity so that window reads need no bounds checks
   // shared-memory carve-up, in floats
@@ -115,7 +127,10 @@ struct Lowered {
 
 struct pystl_formula;
 namespace pystl {
-int lower_formula(const ::pystl_formula* f, Lowered* out, char* msg, int msg_len);
+// backward: every node keeps its own plane (values are re-read by the adjoint pass) and
+// constructs without a backward kernel are rejected
+int lower_formula(const ::pystl_formula* f, bool backward, Lowered* out, char* msg, int msg_len);
 // force_nt > 0 pins the CTA size (tests); 0 = choose
-int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_nt, TileGeom* g, char* msg, int msg_len);
+int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_nt, bool backward, TileGeom* g, char* msg,
+                  int msg_len);
 }  // namespace pystl

@@ -21,6 +21,9 @@ namespace pystl {
 template <int SEM>
 int launch_fwd_sem(const Lowered& lw, const TileGeom& g, const float* signal, float* out, double* mean_acc,
                    cudaStream_t stream, char* err, int err_len);
+template <int SEM>
+int launch_bwd_sem(const Lowered& lw, const TileGeom& g, const float* signal, const float* grad_out, float scale,
+                   float* grad_signal, cudaStream_t stream, char* err, int err_len);
 }  // namespace pystl
 
 // ====================================================================== C ABI
@@ -41,10 +44,10 @@ static int forced_threads() {
   return e ? atoi(e) : 0;
 }
 
-static int prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t D, Lowered* lw, TileGeom* g) {
-  int rc = lower_formula(reinterpret_cast<const ::pystl_formula*>(f), lw, g_err, sizeof(g_err));
+static int prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t D, bool backward, Lowered* lw, TileGeom* g) {
+  int rc = lower_formula(reinterpret_cast<const ::pystl_formula*>(f), backward, lw, g_err, sizeof(g_err));
   if (rc) return rc;
-  return plan_geometry(*lw, B, T, D, forced_threads(), g, g_err, sizeof(g_err));
+  return plan_geometry(*lw, B, T, D, forced_threads(), backward, g, g_err, sizeof(g_err));
 }
 
 extern "C" int pystl_b200_abi_version(void) { return PYSTL_B200_ABI_VERSION; }
@@ -52,10 +55,9 @@ extern "C" const char* pystl_b200_last_error(void) { return g_err; }
 
 extern "C" int pystl_b200_plan(const pystl_formula_t* f, int64_t T, int32_t D, int32_t backward, pystl_plan_t* plan) {
   if (!plan) return set_err(PYSTL_E_INVALID, "plan is NULL");
-  if (backward) return set_err(PYSTL_E_UNSUPPORTED, "backward planning is not implemented yet");
   Lowered lw;
   TileGeom g;
-  int rc = prepare(f, 1, T, D, &lw, &g);
+  int rc = prepare(f, 1, T, D, backward != 0, &lw, &g);
   if (rc) return rc;
   plan->out_channels = lw.out_channels;
   plan->lookahead = lw.lookahead;
@@ -75,7 +77,7 @@ extern "C" int pystl_b200_eval_forward(const pystl_formula_t* f, const float* si
                                        float* out, double* mean_acc, void* stream) {
   Lowered lw;
   TileGeom g;
-  int rc = prepare(f, B, T, D, &lw, &g);
+  int rc = prepare(f, B, T, D, false, &lw, &g);
   if (rc) return rc;
   if (B == 0 || T == 0) return PYSTL_OK;
   if (!signal || !out) return set_err(PYSTL_E_INVALID, "signal / out is NULL");
@@ -91,7 +93,22 @@ extern "C" int pystl_b200_eval_forward(const pystl_formula_t* f, const float* si
   }
 }
 
-extern "C" int pystl_b200_eval_backward(const pystl_formula_t*, const float*, int64_t, int64_t, int32_t, const float*,
-                                        float, float*, void*) {
-  return set_err(PYSTL_E_UNSUPPORTED, "backward kernels are not built yet");
+extern "C" int pystl_b200_eval_backward(const pystl_formula_t* f, const float* signal, int64_t B, int64_t T, int32_t D,
+                                        const float* grad_out, float grad_scale, float* grad_signal, void* stream) {
+  Lowered lw;
+  TileGeom g;
+  int rc = prepare(f, B, T, D, true, &lw, &g);
+  if (rc) return rc;
+  if (B == 0 || T == 0) return PYSTL_OK;
+  if (!signal || !grad_signal) return set_err(PYSTL_E_INVALID, "signal / grad_signal is NULL");
+  if (g.nt % 32 != 0) return set_err(PYSTL_E_INVALID, "CTA size %d is not a multiple of 32", g.nt);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int el = (int)sizeof(g_err);
+  switch (lw.prog.sem) {
+    case SEM_CLASSIC: return launch_bwd_sem<SEM_CLASSIC>(lw, g, signal, grad_out, grad_scale, grad_signal, s, g_err, el);
+    case SEM_SMOOTH: return launch_bwd_sem<SEM_SMOOTH>(lw, g, signal, grad_out, grad_scale, grad_signal, s, g_err, el);
+    case SEM_AGM: return launch_bwd_sem<SEM_AGM>(lw, g, signal, grad_out, grad_scale, grad_signal, s, g_err, el);
+    case SEM_DGMSR: return launch_bwd_sem<SEM_DGMSR>(lw, g, signal, grad_out, grad_scale, grad_signal, s, g_err, el);
+    default: return set_err(PYSTL_E_UNSUPPORTED, "no backward kernel for this semantics");
+  }
 }

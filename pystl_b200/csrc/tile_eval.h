@@ -27,6 +27,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "program.h"
 
@@ -50,6 +51,26 @@ PYSTL_HD int pidx(int p) { return p ^ (((p >> 5) & 1) << 2); }  // physical scal
 PYSTL_HD float f_inf() { return INFINITY; }
 PYSTL_HD float f_nan() { return NAN; }
 
+// bit casts (values of SEM_CLASSIC_SRC carry an integer in a float register)
+PYSTL_HD int f2i(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  int i;
+  memcpy(&i, &f, 4);
+  return i;
+#endif
+}
+PYSTL_HD float i2f(int i) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(i);
+#else
+  float f;
+  memcpy(&f, &i, 4);
+  return f;
+#endif
+}
+
 PYSTL_HD float fast_ex2(float x) {
 #if defined(__CUDA_ARCH__)
   float y;
@@ -72,8 +93,8 @@ PYSTL_HD float fast_lg2(float x) {
 // ------------------------------------------------------------------ values and accumulators
 template <int SEM>
 struct Tr {
-  static constexpr int VW = (SEM == SEM_CUMULATIVE) ? 2 : 1;                       // words per node value
-  static constexpr int AW = (SEM == SEM_CLASSIC || SEM == SEM_SMOOTH) ? 1 : 2;     // words per accumulator
+  static constexpr int VW = (SEM == SEM_CUMULATIVE || SEM == SEM_CLASSIC_SRC) ? 2 : 1;  // words per node value
+  static constexpr int AW = (SEM == SEM_CLASSIC || SEM == SEM_SMOOTH) ? 1 : 2;          // words per accumulator
 };
 
 template <int N>
@@ -87,6 +108,9 @@ PYSTL_HD Vec<Tr<SEM>::VW> negate(Vec<Tr<SEM>::VW> v) {
   if constexpr (SEM == SEM_CUMULATIVE) {  // cumulative.py:32-33
     r.x[0] = -v.x[1];
     r.x[1] = -v.x[0];
+  } else if constexpr (SEM == SEM_CLASSIC_SRC) {
+    r.x[0] = -v.x[0];
+    r.x[1] = i2f(f2i(v.x[1]) ^ (int)0x80000000);  // the source's sign bit
   } else {
     r.x[0] = -v.x[0];
   }
@@ -105,6 +129,21 @@ struct Red<SEM_CLASSIC, MODE> {
   static PYSTL_HD A lift(V v, const RP&, float) { return A{{v.x[0]}}; }
   static PYSTL_HD A comb(A a, A b) { return A{{MODE == MODE_AND ? fminf(a.x[0], b.x[0]) : fmaxf(a.x[0], b.x[0])}}; }
   static PYSTL_HD V fin(A a, float, const RP&) { return V{{a.x[0]}}; }
+};
+
+// Classic with provenance: x[0] = value, x[1] = bits of (sign << 31 | predicate << 24 | tile
+// position).  Ties go to the earlier operand, like torch.min / max(dim) (torch/semantics.py:106,113).
+template <int MODE>
+struct Red<SEM_CLASSIC_SRC, MODE> {
+  using V = Vec<2>;
+  using A = Vec<2>;
+  static PYSTL_HD A ident() { return A{{MODE == MODE_AND ? f_inf() : -f_inf(), 0.f}}; }
+  static PYSTL_HD A lift(V v, const RP&, float) { return v; }
+  static PYSTL_HD A comb(A a, A b) {
+    const bool take_b = MODE == MODE_AND ? (b.x[0] < a.x[0]) : (b.x[0] > a.x[0]);
+    return A{{take_b ? b.x[0] : a.x[0], take_b ? b.x[1] : a.x[1]}};
+  }
+  static PYSTL_HD V fin(A a, float, const RP&) { return a; }
 };
 
 template <int MODE>
@@ -200,6 +239,7 @@ struct Ctx {
   int nt, lext, D;
   int off_planes, off_scratch, off_chunk, off_red;
   int gl, gr;   // scratch guard bands (floats), see TileGeom
+  int n_slots;  // value slots (adjoint planes of the backward kernel follow them)
   int nlive;    // tile samples that exist in the trace: min(T - e0, lext)
   int first;    // tile position of trace sample 0 (= -e0, clamped): positions below it do not exist
   int last_ok;  // last tile position whose output does not raise (T-1-start_slack-e0, clamped), < 0: none
@@ -225,6 +265,7 @@ PYSTL_HD Ctx make_ctx(float* smem, const TileGeom& g, const TileProgram& P, int6
   c.off_red = g.off_red;
   c.gl = g.gl;
   c.gr = g.gr;
+  c.n_slots = g.n_slots;
   const int64_t live = g.T - e0;
   c.nlive = live < (int64_t)g.lext ? (int)live : g.lext;
   c.first = e0 > (int64_t)(1 << 30) ? -(1 << 30) : -(int)e0;
@@ -377,7 +418,7 @@ PYSTL_HD void eval_predicates_d(EX& ex, const Ctx& c, const TileProgram& P, cons
         const int nterms = P.preds[q].n_terms;
         const float bias = P.preds[q].bias;
         float acc;
-        if ((SEM == SEM_CLASSIC) && P.preds[q].f64) {
+        if ((SEM == SEM_CLASSIC || SEM == SEM_CLASSIC_SRC) && P.preds[q].f64) {
           // the reference evaluates predicates in float64 (classic.py:20); same operations, same
           // order as formula.affine_predicate, one final rounding: bit-exact after the cast
           double a = 0.0;
@@ -402,6 +443,9 @@ PYSTL_HD void eval_predicates_d(EX& ex, const Ctx& c, const TileProgram& P, cons
         if constexpr (SEM == SEM_CUMULATIVE) {  // cumulative.py:29-30
           c.plane(dst, 0, VW)[pp] = fmaxf(0.f, acc);
           c.plane(dst, 1, VW)[pp] = fminf(0.f, acc);
+        } else if constexpr (SEM == SEM_CLASSIC_SRC) {
+          c.plane(dst, 0, VW)[pp] = acc;
+          c.plane(dst, 1, VW)[pp] = i2f((q << 24) | p);
         } else {
           c.plane(dst, 0, VW)[pp] = acc;
         }
@@ -630,20 +674,29 @@ PYSTL_HD void fill_guards(const Ctx& c, int tid, Vec<AW> id, int nplanes_per_wor
 // clamp a window offset to the tile: beyond +-lext every position is past the horizon anyway
 PYSTL_HD int clamp_off(int x, int lext) { return x > lext ? lext : (x < -lext ? -lext : x); }
 
-// ------------------------------------------------------------------ window, direct (W <= 8)
-template <int SEM, int MODE, class EX>
-PYSTL_HD void op_win_direct(EX& ex, const Ctx& c, const TInstr& in) {
-  using R = Red<SEM, MODE>;
-  using A = typename R::A;
-  using V = typename R::V;
-  constexpr int AW = Tr<SEM>::AW;
-  RP rp = c.rp;
-  const Win wn = decode_win(in);
-  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, wn.src, wn.neg);
-  const int wa = clamp_off(wn.a, c.lext), wb = clamp_off(wn.b, c.lext);
-  PYSTL_FOR_THREADS(ex, tid) {
-    A x[8];
-    lift_own8<SEM, MODE>(c, wn, rp, tid, x);
+// ------------------------------------------------------------------ sliding windows
+// aggregate of chunk `ch` (the guard entries hold the identity)
+template <int AW>
+PYSTL_HD Vec<AW> load_agg(const Ctx& c, int ch) {
+  Vec<AW> r;
+#pragma unroll
+  for (int w = 0; w < AW; ++w) r.x[w] = c.chunk(w)[ch];
+  return r;
+}
+
+// The two phases of a sliding-window reduction out[p] = (+)_{k in [wa, wb]} x[p + k] over the
+// tile, for any associative (+) (R::comb, identity R::ident; operands are always combined in
+// time order).  A __syncthreads separates them.
+//
+//   direct   (wb - wa + 1 <= 8)  phase 1 stages x; phase 2 walks the 8 + W - 1 samples the
+//            thread's outputs need as float4s and feeds every output it belongs to
+//   van Herk / Gil-Werman (>= 9) chunk = the 8 samples of one thread.  Phase 1: in-register
+//            suffix and prefix scans of the own chunk -> scratch planes SUF, PRE and the chunk
+//            aggregate AGG.  Phase 2: out[p] = SUF[p+wa] (+) AGG[whole chunks strictly inside]
+//            (+) PRE[p+wb]; the pieces are disjoint, so (+) need not be idempotent.
+template <class R, int AW>
+PYSTL_HD void win_phase1(const Ctx& c, int tid, bool vh, const Vec<AW> (&x)[8]) {
+  if (!vh) {
 #pragma unroll
     for (int w = 0; w < AW; ++w) {
       float t[8];
@@ -652,12 +705,36 @@ PYSTL_HD void op_win_direct(EX& ex, const Ctx& c, const TInstr& in) {
       store8(c.scr(w), tid, t);
     }
     fill_guards<AW>(c, tid, R::ident(), 1, false);
+    return;
   }
-  ex.sync();
-  PYSTL_FOR_THREADS(ex, tid) {
-    const int p0 = 8 * tid, W = wb - wa + 1;
-    const A id = R::ident();
-    A acc[8];
+  Vec<AW> suf[8], pre[8];
+  pre[0] = x[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) pre[i] = R::comb(pre[i - 1], x[i]);
+  suf[7] = x[7];
+#pragma unroll
+  for (int i = 6; i >= 0; --i) suf[i] = R::comb(x[i], suf[i + 1]);
+#pragma unroll
+  for (int w = 0; w < AW; ++w) {
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = suf[i].x[w];
+    store8(c.scr(w), tid, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = pre[i].x[w];
+    store8(c.scr(AW + w), tid, t);
+    c.chunk(w)[tid] = pre[7].x[w];
+  }
+  fill_guards<AW>(c, tid, R::ident(), 2, true);
+}
+
+template <class R, int AW>
+PYSTL_HD void win_phase2(const Ctx& c, int tid, bool vh, int wa, int wb, Vec<AW> (&acc)[8]) {
+  using A = Vec<AW>;
+  const A id = R::ident();
+  const int p0 = 8 * tid;
+  if (!vh) {
+    const int W = wb - wa + 1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = id;
     const int f_lo = (p0 + wa) >> 2, f_hi = (p0 + 7 + wb) >> 2;
@@ -677,29 +754,43 @@ PYSTL_HD void op_win_direct(EX& ex, const Ctx& c, const TInstr& in) {
           if (d - i >= 0 && d - i < W) acc[i] = R::comb(acc[i], e);
       }
     }
-    V o[8];
-    finish8<SEM, MODE>(c, wn, rp, acc, p0, win_count8(c, wn, p0), o);
-    store_val8<SEM>(c, wn.dst, tid, o);
+    return;
   }
-  ex.sync();
-}
-
-// aggregate of chunk `ch` (the guard entries hold the identity)
-template <int AW>
-PYSTL_HD Vec<AW> load_agg(const Ctx& c, int ch) {
-  Vec<AW> r;
+  const int qa = wa >> 3, ra = wa & 7, qb = wb >> 3, rb = wb & 7;
+  float sufv[AW][8], prev[AW][8];
 #pragma unroll
-  for (int w = 0; w < AW; ++w) r.x[w] = c.chunk(w)[ch];
-  return r;
+  for (int w = 0; w < AW; ++w) {
+    load_run8(c.scr(w), p0 + wa, sufv[w]);
+    load_run8(c.scr(AW + w), p0 + wb, prev[w]);
+  }
+  const A al = load_agg<AW>(c, tid + qa + 1), ar = load_agg<AW>(c, tid + qb);
+  A core = id;
+#pragma unroll 2
+  for (int ch = tid + qa + 2; ch <= tid + qb - 1; ++ch) core = R::comb(core, load_agg<AW>(c, ch));
+  const bool two = qb >= qa + 2;
+  // the four possible sets of whole chunks between the two partial ones, in time order
+  const A m_l = R::comb(al, core), m_r = R::comb(core, ar), m_lr = R::comb(m_l, ar);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    A s, e;
+#pragma unroll
+    for (int w = 0; w < AW; ++w) {
+      s.x[w] = sufv[w][i];
+      e.x[w] = prev[w][i];
+    }
+    const int cs = (ra + i) >> 3, ce = (rb + i) >> 3;  // 0 or 1: did start / end spill into the next chunk
+    const bool inc_l = (cs == 0) && (qb + ce - 1 >= qa + 1);
+    const bool inc_r = (ce == 1) && two;
+    A mid;
+#pragma unroll
+    for (int w = 0; w < AW; ++w) mid.x[w] = inc_l ? (inc_r ? m_lr.x[w] : m_l.x[w]) : (inc_r ? m_r.x[w] : core.x[w]);
+    acc[i] = R::comb(R::comb(s, mid), e);
+  }
 }
 
-// ------------------------------------------------------------------ window, van Herk / Gil-Werman (W >= 9)
-// Chunk = the 8 samples of one thread.  Phase 1: in-register suffix and prefix
-// scans of the own chunk -> scratch planes SUF, PRE and the chunk aggregate AGG.
-// Phase 2: out[t] = SUF[t+a] (+) AGG[whole chunks strictly inside] (+) PRE[t+b].
-// The pieces are disjoint, so (+) only has to be associative (min, max, +).
+// Always / Eventually over a bounded interval (T_WIN_DIRECT, T_WIN_VH)
 template <int SEM, int MODE, class EX>
-PYSTL_HD void op_win_vh(EX& ex, const Ctx& c, const TInstr& in) {
+PYSTL_HD void op_win(EX& ex, const Ctx& c, const TInstr& in, bool vh) {
   using R = Red<SEM, MODE>;
   using A = typename R::A;
   using V = typename R::V;
@@ -707,64 +798,16 @@ PYSTL_HD void op_win_vh(EX& ex, const Ctx& c, const TInstr& in) {
   RP rp = c.rp;
   const Win wn = decode_win(in);
   if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, wn.src, wn.neg);
+  const int wa = clamp_off(wn.a, c.lext), wb = clamp_off(wn.b, c.lext);
   PYSTL_FOR_THREADS(ex, tid) {
-    A x[8], suf[8], pre[8];
+    A x[8];
     lift_own8<SEM, MODE>(c, wn, rp, tid, x);
-    pre[0] = x[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) pre[i] = R::comb(pre[i - 1], x[i]);
-    suf[7] = x[7];
-#pragma unroll
-    for (int i = 6; i >= 0; --i) suf[i] = R::comb(x[i], suf[i + 1]);
-#pragma unroll
-    for (int w = 0; w < AW; ++w) {
-      float t[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) t[i] = suf[i].x[w];
-      store8(c.scr(w), tid, t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) t[i] = pre[i].x[w];
-      store8(c.scr(AW + w), tid, t);
-      c.chunk(w)[tid] = pre[7].x[w];
-    }
-    fill_guards<AW>(c, tid, R::ident(), 2, true);
+    win_phase1<R, AW>(c, tid, vh, x);
   }
   ex.sync();
   PYSTL_FOR_THREADS(ex, tid) {
-    const A id = R::ident();
-    const int wa = clamp_off(wn.a, c.lext), wb = clamp_off(wn.b, c.lext);
-    const int qa = wa >> 3, ra = wa & 7, qb = wb >> 3, rb = wb & 7;
-    float sufv[AW][8], prev[AW][8];
-#pragma unroll
-    for (int w = 0; w < AW; ++w) {
-      load_run8(c.scr(w), 8 * tid + wa, sufv[w]);
-      load_run8(c.scr(AW + w), 8 * tid + wb, prev[w]);
-    }
-    const A al = load_agg<AW>(c, tid + qa + 1), ar = load_agg<AW>(c, tid + qb);
-    A core = id;
-#pragma unroll 2
-    for (int ch = tid + qa + 2; ch <= tid + qb - 1; ++ch) core = R::comb(core, load_agg<AW>(c, ch));
-    const bool two = qb >= qa + 2;
-    // the four possible sets of whole chunks between the two partial ones, in time order
-    const A m_l = R::comb(al, core), m_r = R::comb(core, ar), m_lr = R::comb(m_l, ar);
     A acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      A s, e;
-#pragma unroll
-      for (int w = 0; w < AW; ++w) {
-        s.x[w] = sufv[w][i];
-        e.x[w] = prev[w][i];
-      }
-      const int cs = (ra + i) >> 3, ce = (rb + i) >> 3;  // 0 or 1: did start / end spill into the next chunk
-      const bool inc_l = (cs == 0) && (qb + ce - 1 >= qa + 1);
-      const bool inc_r = (ce == 1) && two;
-      A mid;
-#pragma unroll
-      for (int w = 0; w < AW; ++w)
-        mid.x[w] = inc_l ? (inc_r ? m_lr.x[w] : m_l.x[w]) : (inc_r ? m_r.x[w] : core.x[w]);
-      acc[i] = R::comb(R::comb(s, mid), e);
-    }
+    win_phase2<R, AW>(c, tid, vh, wa, wb, acc);
     V o[8];
     finish8<SEM, MODE>(c, wn, rp, acc, 8 * tid, win_count8(c, wn, 8 * tid), o);
     store_val8<SEM>(c, wn.dst, tid, o);
@@ -846,11 +889,37 @@ PYSTL_HD void op_win_suffix(EX& ex, const Ctx& c, const TInstr& in) {
 // which is closed under composition, so the whole tile is one
 // suffix scan.  Starting the recurrence at the tile's last sample is exact for every
 // output whose bounded window lies inside the tile ("Classic until").
-struct ClampOp {
-  using A = Vec<2>;
+template <int SEM>
+struct ClampOp;
+
+template <>
+struct ClampOp<SEM_CLASSIC> {
+  using A = Vec<2>;  // (A, B)
+  static constexpr int W = 2;
   static PYSTL_HD A ident() { return A{{f_inf(), -f_inf()}}; }
   static PYSTL_HD A comb(A f, A g) {  // f after g:  x -> f(g(x)), f is the EARLIER sample
     return A{{fminf(f.x[0], fmaxf(f.x[1], g.x[0])), fmaxf(f.x[1], g.x[1])}};
+  }
+  static PYSTL_HD A make(Vec<1> l, Vec<1> r) { return A{{l.x[0], r.x[0]}}; }
+  static PYSTL_HD Vec<1> value(A f) { return Vec<1>{{fminf(f.x[0], f.x[1])}}; }  // f(-inf) = min(A, B)
+};
+
+template <>
+struct ClampOp<SEM_CLASSIC_SRC> {
+  using A = Vec<4>;  // (A, src A, B, src B); ties go to the earlier sample
+  static constexpr int W = 4;
+  static PYSTL_HD A ident() { return A{{f_inf(), 0.f, -f_inf(), 0.f}}; }
+  static PYSTL_HD A comb(A f, A g) {
+    const bool up = g.x[0] > f.x[2];  // max(B_f, A_g)
+    const float mv = up ? g.x[0] : f.x[2], ms = up ? g.x[1] : f.x[3];
+    const bool dn = mv < f.x[0];  // min(A_f, .)
+    const bool bb = g.x[2] > f.x[2];
+    return A{{dn ? mv : f.x[0], dn ? ms : f.x[1], bb ? g.x[2] : f.x[2], bb ? g.x[3] : f.x[3]}};
+  }
+  static PYSTL_HD A make(Vec<2> l, Vec<2> r) { return A{{l.x[0], l.x[1], r.x[0], r.x[1]}}; }
+  static PYSTL_HD Vec<2> value(A f) {
+    const bool b = f.x[2] < f.x[0];
+    return Vec<2>{{b ? f.x[2] : f.x[0], b ? f.x[3] : f.x[1]}};
   }
 };
 
@@ -862,42 +931,46 @@ PYSTL_HD Pair decode_pair(const TInstr& in) {
   return Pair{in.src[0], in.src[1], in.dst, (in.negmask & 1) != 0, (in.negmask & 2) != 0};
 }
 
-PYSTL_HD void clamp_load_lr(const Ctx& c, const Pair& in, int tid, int nlive, ClampOp::A (&x)[8]) {
-  Vec<1> l[8], r[8];
-  load_val8<SEM_CLASSIC>(c, in.sl, in.nl, tid, l);
-  load_val8<SEM_CLASSIC>(c, in.sr, in.nr, tid, r);
+template <int SEM>
+PYSTL_HD void clamp_load_lr(const Ctx& c, const Pair& in, int tid, int nlive, typename ClampOp<SEM>::A (&x)[8]) {
+  Vec<Tr<SEM>::VW> l[8], r[8];
+  load_val8<SEM>(c, in.sl, in.nl, tid, l);
+  load_val8<SEM>(c, in.sr, in.nr, tid, r);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = (8 * tid + i < nlive) ? ClampOp::A{{l[i].x[0], r[i].x[0]}} : ClampOp::ident();
+  for (int i = 0; i < 8; ++i) x[i] = (8 * tid + i < nlive) ? ClampOp<SEM>::make(l[i], r[i]) : ClampOp<SEM>::ident();
 }
 
-template <class EX>
+template <int SEM, class EX>
 PYSTL_HD void op_clamp_scan(EX& ex, const Ctx& c, const TInstr& ins) {
-  using A = ClampOp::A;
+  using OP = ClampOp<SEM>;
+  using A = typename OP::A;
+  constexpr int W = OP::W;
   const int nlive = c.nlive;
   const Pair in = decode_pair(ins);
   PYSTL_FOR_THREADS(ex, tid) {
     A x[8];
-    clamp_load_lr(c, in, tid, nlive, x);
+    clamp_load_lr<SEM>(c, in, tid, nlive, x);
     A agg = x[7];
 #pragma unroll
-    for (int i = 6; i >= 0; --i) agg = ClampOp::comb(x[i], agg);
-    c.chunk(0)[tid] = agg.x[0];
-    c.chunk(1)[tid] = agg.x[1];
+    for (int i = 6; i >= 0; --i) agg = OP::comb(x[i], agg);
+#pragma unroll
+    for (int w = 0; w < W; ++w) c.chunk(w)[tid] = agg.x[w];
   }
   ex.sync();
-  ex.template excl_suffix_scan<2, ClampOp>(c.chunk(0), c.nt, (int)(c.chunk(1) - c.chunk(0)), c.red());
+  ex.template excl_suffix_scan<W, OP>(c.chunk(0), c.nt, (int)(c.chunk(1) - c.chunk(0)), c.red());
   PYSTL_FOR_THREADS(ex, tid) {
     A x[8];
-    clamp_load_lr(c, in, tid, nlive, x);
-    A tail{{c.chunk(0)[tid], c.chunk(1)[tid]}};
-    Vec<1> o[8];
-    A run = tail;
+    clamp_load_lr<SEM>(c, in, tid, nlive, x);
+    A run;
+#pragma unroll
+    for (int w = 0; w < W; ++w) run.x[w] = c.chunk(w)[tid];
+    Vec<Tr<SEM>::VW> o[8];
 #pragma unroll
     for (int i = 7; i >= 0; --i) {
-      run = ClampOp::comb(x[i], run);
-      o[i].x[0] = fminf(run.x[0], run.x[1]);  // f(-inf) = min(A, B)
+      run = OP::comb(x[i], run);
+      o[i] = OP::value(run);
     }
-    store_val8<SEM_CLASSIC>(c, in.dst, tid, o);
+    store_val8<SEM>(c, in.dst, tid, o);
   }
   ex.sync();
 }
@@ -916,6 +989,17 @@ struct UntilState<SEM_CLASSIC> {  // classic.py:63-67
     if (cand) best = fmaxf(best, fminf(pm, r.x[0]));
   }
   PYSTL_HD Vec<1> done(int, const RP&) { return Vec<1>{{best}}; }
+};
+
+template <>
+struct UntilState<SEM_CLASSIC_SRC> {  // classic.py:63-67 with provenance (earlier operand wins ties)
+  Vec<2> pm, best;
+  PYSTL_HD void init() { pm = Vec<2>{{f_inf(), 0.f}}; best = Vec<2>{{-f_inf(), 0.f}}; }
+  PYSTL_HD void step(Vec<2> l, Vec<2> r, bool cand, const RP&, float, float) {
+    pm = Red<SEM_CLASSIC_SRC, MODE_AND>::comb(pm, l);
+    if (cand) best = Red<SEM_CLASSIC_SRC, MODE_OR>::comb(best, Red<SEM_CLASSIC_SRC, MODE_AND>::comb(pm, r));
+  }
+  PYSTL_HD Vec<2> done(int, const RP&) { return best; }
 };
 
 template <>
@@ -1113,14 +1197,10 @@ PYSTL_HD void run_instr(EX& ex, const Ctx& c, const TInstr& in) {
       else op_nary<SEM, MODE_OR>(ex, c, in);
       break;
     case T_WIN_DIRECT:
-      if (in.mode == MODE_AND) op_win_direct<SEM, MODE_AND>(ex, c, in);
-      else if (in.mode == MODE_OR) op_win_direct<SEM, MODE_OR>(ex, c, in);
-      else if constexpr (has_sum) op_win_direct<SEM, MODE_SUM>(ex, c, in);
-      break;
     case T_WIN_VH:
-      if (in.mode == MODE_AND) op_win_vh<SEM, MODE_AND>(ex, c, in);
-      else if (in.mode == MODE_OR) op_win_vh<SEM, MODE_OR>(ex, c, in);
-      else if constexpr (has_sum) op_win_vh<SEM, MODE_SUM>(ex, c, in);
+      if (in.mode == MODE_AND) op_win<SEM, MODE_AND>(ex, c, in, in.op == T_WIN_VH);
+      else if (in.mode == MODE_OR) op_win<SEM, MODE_OR>(ex, c, in, in.op == T_WIN_VH);
+      else if constexpr (has_sum) op_win<SEM, MODE_SUM>(ex, c, in, in.op == T_WIN_VH);
       break;
     case T_WIN_SUFFIX:
       if (in.mode == MODE_AND) op_win_suffix<SEM, MODE_AND>(ex, c, in);
@@ -1131,7 +1211,7 @@ PYSTL_HD void run_instr(EX& ex, const Ctx& c, const TInstr& in) {
       op_until<SEM>(ex, c, in);
       break;
     case T_CLAMP_SCAN:
-      if constexpr (SEM == SEM_CLASSIC) op_clamp_scan(ex, c, in);
+      if constexpr (SEM == SEM_CLASSIC || SEM == SEM_CLASSIC_SRC) op_clamp_scan<SEM>(ex, c, in);
       break;
     default:
       break;
@@ -1221,6 +1301,8 @@ struct HostExec {
   int t1() const { return nt_; }
   void sync() {}
   void put(int tid, float v) { stash[tid] = v; }
+  float get(int tid) const { return stash[tid]; }
+  void atomic_add(float* p, float v) { *p += v; }
   float all_max(float*) {
     float m = -INFINITY;
     for (int i = 0; i < nt_; ++i) m = fmaxf(m, stash[i]);

@@ -13,6 +13,7 @@
 #include "../../include/pystl_b200.h"
 #include "../../pystl_b200/csrc/program.h"
 #include "../../pystl_b200/csrc/tile_eval.h"
+#include "../../pystl_b200/csrc/tile_bwd.h"
 
 using namespace pystl;
 
@@ -44,12 +45,11 @@ static void run_all(const Lowered& lw, const TileGeom& g, const float* signal, f
 extern "C" const char* pystl_emu_last_error(void) { return g_err; }
 
 extern "C" int pystl_emu_plan(const pystl_formula_t* f, int64_t T, int32_t D, int32_t backward, pystl_plan_t* plan) {
-  (void)backward;
   Lowered lw;
-  int rc = lower_formula(reinterpret_cast<const ::pystl_formula*>(f), &lw, g_err, sizeof(g_err));
+  int rc = lower_formula(reinterpret_cast<const ::pystl_formula*>(f), backward != 0, &lw, g_err, sizeof(g_err));
   if (rc) return rc;
   TileGeom g;
-  rc = plan_geometry(lw, 1, T, D, 0, &g, g_err, sizeof(g_err));
+  rc = plan_geometry(lw, 1, T, D, 0, backward != 0, &g, g_err, sizeof(g_err));
   if (rc) return rc;
   plan->out_channels = lw.out_channels;
   plan->lookahead = lw.lookahead;
@@ -69,11 +69,11 @@ extern "C" int pystl_emu_plan(const pystl_formula_t* f, int64_t T, int32_t D, in
 extern "C" int pystl_emu_eval_forward(const pystl_formula_t* f, const float* signal, int64_t B, int64_t T, int32_t D,
                                       float* out, double* mean_acc, int32_t force_threads) {
   Lowered lw;
-  int rc = lower_formula(reinterpret_cast<const ::pystl_formula*>(f), &lw, g_err, sizeof(g_err));
+  int rc = lower_formula(reinterpret_cast<const ::pystl_formula*>(f), false, &lw, g_err, sizeof(g_err));
   if (rc) return rc;
   if (B == 0 || T == 0) return 0;
   TileGeom g;
-  rc = plan_geometry(lw, B, T, D, force_threads, &g, g_err, sizeof(g_err));
+  rc = plan_geometry(lw, B, T, D, force_threads, false, &g, g_err, sizeof(g_err));
   if (rc) return rc;
   switch (lw.prog.sem) {
     case SEM_CLASSIC: run_all<SEM_CLASSIC>(lw, g, signal, out, mean_acc); break;
@@ -82,6 +82,51 @@ extern "C" int pystl_emu_eval_forward(const pystl_formula_t* f, const float* sig
     case SEM_AGM: run_all<SEM_AGM>(lw, g, signal, out, mean_acc); break;
     case SEM_DGMSR: run_all<SEM_DGMSR>(lw, g, signal, out, mean_acc); break;
     default: return PYSTL_E_INVALID;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- backward
+template <int SEM>
+static void run_all_bwd(const Lowered& lw, const TileGeom& g, const float* signal, const float* grad_out, float scale,
+                        float* grad_signal) {
+  std::vector<float> smem((size_t)g.smem_floats + 64, 0.f);
+  float* base = smem.data();
+  while (reinterpret_cast<uintptr_t>(base) & 15) ++base;
+  for (int64_t b = 0; b < g.B; ++b) {
+    for (int j = 0; j < g.n_tiles; ++j) {
+      for (int i = 0; i < g.smem_floats; ++i) base[i] = NAN;
+      const int64_t t0 = (int64_t)j * g.lout;
+      const int64_t e0 = t0 > g.hh ? t0 - g.hh : 0;
+      const Ctx c = make_ctx(base, g, lw.prog, e0);
+      const int p_lo = (int)(t0 - e0);
+      int p_hi = p_lo + g.lout;
+      if (p_hi > c.nlive) p_hi = c.nlive;
+      float* raw = c.raw();
+      const float* src = signal + (b * g.T + e0) * g.D;
+      for (int i = 0; i < c.nlive * g.D; ++i) raw[i] = src[i];
+      HostExec ex(g.nt);
+      run_backward<SEM>(ex, c, lw.prog, raw, grad_out ? grad_out + (b * g.T + e0) : nullptr, scale,
+                        grad_signal + (b * g.T + e0) * g.D, p_lo, p_hi);
+    }
+  }
+}
+
+extern "C" int pystl_emu_eval_backward(const pystl_formula_t* f, const float* signal, int64_t B, int64_t T, int32_t D,
+                                       const float* grad_out, float scale, float* grad_signal, int32_t force_threads) {
+  Lowered lw;
+  int rc = lower_formula(reinterpret_cast<const ::pystl_formula*>(f), true, &lw, g_err, sizeof(g_err));
+  if (rc) return rc;
+  if (B == 0 || T == 0) return 0;
+  TileGeom g;
+  rc = plan_geometry(lw, B, T, D, force_threads, true, &g, g_err, sizeof(g_err));
+  if (rc) return rc;
+  switch (lw.prog.sem) {
+    case SEM_CLASSIC: run_all_bwd<SEM_CLASSIC>(lw, g, signal, grad_out, scale, grad_signal); break;
+    case SEM_SMOOTH: run_all_bwd<SEM_SMOOTH>(lw, g, signal, grad_out, scale, grad_signal); break;
+    case SEM_AGM: run_all_bwd<SEM_AGM>(lw, g, signal, grad_out, scale, grad_signal); break;
+    case SEM_DGMSR: run_all_bwd<SEM_DGMSR>(lw, g, signal, grad_out, scale, grad_signal); break;
+    default: snprintf(g_err, sizeof(g_err), "no backward for this semantics"); return PYSTL_E_UNSUPPORTED;
   }
   return 0;
 }

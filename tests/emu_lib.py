@@ -21,6 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = [os.path.join(ROOT, "tests", "emu", "emu.cpp"), os.path.join(ROOT, "pystl_b200", "csrc", "lower.cpp")]
 DEPS = SRC + [
     os.path.join(ROOT, "pystl_b200", "csrc", "tile_eval.h"),
+    os.path.join(ROOT, "pystl_b200", "csrc", "tile_bwd.h"),
     os.path.join(ROOT, "pystl_b200", "csrc", "program.h"),
     os.path.join(ROOT, "include", "pystl_b200.h"),
 ]
@@ -45,6 +46,11 @@ def lib() -> C.CDLL:
         handle.pystl_emu_eval_forward.restype = C.c_int
         handle.pystl_emu_eval_forward.argtypes = [
             C.POINTER(capi.Formula), C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+        ]
+        handle.pystl_emu_eval_backward.restype = C.c_int
+        handle.pystl_emu_eval_backward.argtypes = [
+            C.POINTER(capi.Formula), C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_float, C.c_void_p,
+            C.c_int32,
         ]
         _lib = handle
     return _lib
@@ -72,3 +78,18 @@ def eval_forward(formula, semantics: str, signal: np.ndarray, *, force_threads: 
     capi.raise_for(rc, lib().pystl_emu_last_error())
     res = out if ch == 2 else out[..., 0]
     return (res, acc) if mean else res
+
+
+def eval_backward(formula, semantics: str, signal: np.ndarray, grad_out=None, *, scale: float = 1.0,
+                  force_threads: int = 0, **kw) -> np.ndarray:
+    """d sum(grad_out * out) / d signal, [B, T, D] float32 (grad_out None: constant cotangent `scale`)."""
+    sig = np.ascontiguousarray(signal, dtype=np.float32)
+    B, T, D = sig.shape
+    cf = compile_formula(formula, semantics, D, **kw)
+    go = None if grad_out is None else np.ascontiguousarray(grad_out, dtype=np.float32)
+    gs = np.full((B, T, D), np.float32(-12345.0), dtype=np.float32)
+    rc = lib().pystl_emu_eval_backward(
+        cf.ptr(), sig.ctypes.data, B, T, D, None if go is None else go.ctypes.data, scale, gs.ctypes.data, force_threads
+    )
+    capi.raise_for(rc, lib().pystl_emu_last_error())
+    return gs
