@@ -175,9 +175,9 @@ class _B200Semantics:
         scalar = (val.pos + val.neg) if self.out_channels == 2 else val
         (grad,) = torch.autograd.grad(scalar, x)
         if self.out_channels == 2:
-            value = B200CumulativeRobustness(pos=float(val.pos), neg=float(val.neg))
+            value = B200CumulativeRobustness(pos=float(val.pos.detach()), neg=float(val.neg.detach()))
         else:
-            value = float(val)
+            value = float(val.detach())
         return value, np.asarray(grad.detach().cpu().numpy(), dtype=float)
 
     # ---- the reference's operator interface (base.py:21-75) -------------------------------

@@ -13,7 +13,7 @@ from golden_cases import case_cotangent, case_signal
 from parity_util import SEM_KW, mixed_signal, random_spec
 from pystl_b200 import create_semantics
 from pystl_b200.formula import BASELINE_SPECS, from_spec
-from test_emu_backward import BWD_SEMS, GOLD, GRAD_CASES, check, has_until, oracle_grad
+from test_emu_backward import BWD_SEMS, GOLD, GRAD_CASES, check, grad_tol, has_until, oracle_grad
 
 pytestmark = pytest.mark.gpu
 
@@ -39,7 +39,7 @@ def test_golden_gradients(case):
     sig = case_signal(case)
     vals = GOLD[f"{case['name']}/values"]
     got = gpu_grad(case["spec"], case["sem"], case["kw"], sig, case_cotangent(case, vals.shape))
-    check(got, GOLD[f"{case['name']}/grad"], case["sem"], case["name"])
+    check(got, GOLD[f"{case['name']}/grad"], case["sem"], case["name"], *grad_tol(case["sem"], case["kw"]))
 
 
 @pytest.mark.parametrize("sem,kw", BWD_SEMS, ids=["classical", "smooth", "agm", "dgmsr", "dgmsr_p2"])

@@ -1,0 +1,164 @@
+"""CPU tier: host-side logic -- the create_semantics dispatch, the formula compiler, the C ABI
+surface of the CUDA library (load + symbols + planning, no compute calls), error behaviour."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pystl_b200
+from pystl_b200 import capi, create_semantics
+from pystl_b200.compiler import affine_of, compile_formula
+from pystl_b200.formula import (
+    BASELINE_SHAPES, BASELINE_SPECS, Always, And, Eventually, Interval, Not, Or, Predicate, Until, affine_predicate,
+    from_spec, gt, lt,
+)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------- dispatch
+def test_create_semantics_mirrors_the_reference_dispatch():
+    # same syntaxes / aliases / kwargs as pystl/semantics/__init__.py:76-125
+    for syntax, cls in [
+        ("classical", "B200ClassicRobustSemantics"),
+        ("smooth", "B200SmoothRobustSemantics"),
+        ("cumulative", "B200CumulativeSemantics"),
+        ("dgmsr", "B200DgmsrSemantics"),
+        ("agm", "B200AgmRobustSemantics"),
+        ("arithmetic-geometric-mean", "B200AgmRobustSemantics"),
+        (" Smooth ", "B200SmoothRobustSemantics"),
+    ]:
+        assert type(create_semantics(syntax, backend="b200")).__name__ == cls
+    assert create_semantics("smooth", backend="cuda", temperature=0.25).temperature == 0.25
+    sem = create_semantics("dgmsr", backend="B200", eps=1e-6, p=2)
+    assert (sem.eps, sem.p) == (1e-6, 2)
+    for bad in ("not_a_syntax", "classic", "traditional", "ctstl"):  # reference tests/test_api.py:197-205,255-257
+        with pytest.raises(KeyError):
+            create_semantics(bad, backend="b200")
+    with pytest.raises(ValueError):  # torch/semantics.py:13-16
+        create_semantics("smooth", backend="b200", temperature=0.0)
+    with pytest.raises(TypeError):  # classes without kwargs reject them, like the reference's
+        create_semantics("classical", backend="b200", temperature=1.0)
+
+
+def test_registration_in_the_reference_registry_when_present():
+    pystl = pytest.importorskip("pystl", reason="reference package not importable here")
+    assert pystl_b200.install()
+    import pystl.semantics as ref
+
+    assert "b200" in ref.registry.backends()
+    for syntax in ("classical", "smooth", "cumulative", "dgmsr", "agm"):
+        assert f"{syntax}/b200" in ref.registry.names()
+    # the alias gate of semantics/__init__.py:101-105 now lets the backend through
+    sem = pystl.create_semantics("smooth", backend="b200", temperature=0.5)
+    assert type(sem).__name__ == "B200SmoothRobustSemantics"
+    # and the reference's own backends are untouched
+    assert type(pystl.create_semantics("classical")).__name__ == "ClassicRobustSemantics"
+
+
+# ---------------------------------------------------------------------------- formula / compiler
+def test_formula_builders_and_interval_validation():
+    with pytest.raises(ValueError):
+        Interval(3, 2)
+    with pytest.raises(ValueError):
+        Interval(-1, 2)
+    with pytest.raises(ValueError):
+        And()
+    p, q = gt(0, 0.0), lt(1, 1.0)
+    phi = (p & ~q).always((0, 3)).until(q.eventually(Interval(1, None)), (0, 5), weights_pair=(1.0, 2.0))
+    assert isinstance(phi, Until) and isinstance(phi.left, Always) and isinstance(phi.right, Eventually)
+    assert phi.right.interval.end is None and phi.weights_pair == (1.0, 2.0)
+    assert isinstance((p | q), Or) and isinstance(~p, Not)
+
+
+def test_compile_is_post_order_and_dedups_predicates():
+    p = gt(0, 0.5)
+    phi = And(p.always((0, 4)), Not(p), Or(p, lt(1, 2.0)))
+    cf = compile_formula(phi, "classical", 2)
+    kinds = [cf.nodes[i].kind for i in range(cf.struct.n_nodes)]
+    assert kinds[-1] == capi.NODE_AND
+    for i in range(cf.struct.n_nodes):  # children precede parents
+        n = cf.nodes[i]
+        assert all(cf.children[n.child_off + k] < i for k in range(n.n_children))
+    assert cf.struct.n_preds == 2  # x>0.5 used three times, y<2 once
+    assert cf.channels_used == (0, 1)
+
+
+def test_affine_probe_recognises_reference_style_lambdas():
+    # the reference's own fixtures (tests/test_api.py:71-75)
+    p1 = Predicate("speed_ok", fn=lambda s, t: 0.6 - s[t, 0])
+    p2 = Predicate("alt_ok", fn=lambda s, t: s[t, 1] - 0.2)
+    assert affine_of(p1, 2) == (((0, -1.0),), 0.6)
+    terms, bias = affine_of(p2, 2)
+    assert terms == ((1, 1.0),) and bias == pytest.approx(-0.2)
+    assert affine_of(affine_predicate("p", {3: 2.0, 1: -1.0}, 0.5), 4) == (((1, -1.0), (3, 2.0)), 0.5)
+    with pytest.raises(NotImplementedError):
+        affine_of(Predicate("sq", fn=lambda s, t: s[t, 0] ** 2), 2)
+    with pytest.raises(NotImplementedError):  # looks at another time step
+        affine_of(Predicate("lag", fn=lambda s, t: s[t, 0] - s[max(t - 1, 0), 0]), 2)
+    with pytest.raises(ValueError):  # classic.py:16-19
+        affine_of(Predicate("nofn"), 2)
+
+
+# ---------------------------------------------------------------------------- C ABI surface
+def test_header_and_library_agree():
+    """Every function declared in include/pystl_b200.h is exported by the built library."""
+    header = open(os.path.join(ROOT, "include", "pystl_b200.h")).read()
+    declared = set(re.findall(r"\b(pystl_b200_\w+)\s*\(", header))
+    assert declared == set(capi.EXPORTS)
+    lib = capi.lib()  # loads without a GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pystl_b200_abi_version() == capi.ABI_VERSION
+    assert C.sizeof(capi.Node) == 48 and C.sizeof(capi.Pred) == 72
+
+
+@pytest.mark.parametrize("cfg", sorted(BASELINE_SPECS))
+def test_plan_reports_tiling_and_validity(cfg):
+    B, T, D = BASELINE_SHAPES[cfg]
+    phi = from_spec(BASELINE_SPECS[cfg])
+    for sem_name in ("classical", "smooth", "cumulative", "agm", "dgmsr"):
+        plan = create_semantics(sem_name, backend="b200").plan(phi, T, D)
+        assert plan["out_channels"] == (2 if sem_name == "cumulative" else 1)
+        assert plan["lookahead"] == {"cfg1": 10, "cfg2": 50, "cfg3": 110, "cfg4": 264, "cfg5": 32}[cfg]
+        assert plan["start_slack"] == 0 and plan["raises_always"] == 0
+        assert plan["tile_ext"] == 8 * plan["threads"] and plan["threads"] % 32 == 0
+        assert plan["n_tiles"] * plan["tile_out"] >= T
+        assert plan["smem_bytes"] <= 227 * 1024
+
+
+def test_plan_validity_rules_follow_the_reference():
+    sem = create_semantics("classical", backend="b200")
+    x = gt(0, 0.0)
+    # api.py:218-221: t + a must not pass the horizon
+    assert sem.plan(x.eventually((2, 7)), 30, 1)["start_slack"] == 2
+    # a child that raises near the horizon makes every clipped parent window raise: slack = a_child + b
+    assert sem.plan(x.eventually((3, 11)).always((1, 33)), 200, 1)["start_slack"] == 36
+    # api.py:288-293: Until evaluates its children up to the horizon
+    assert sem.plan(x.eventually((1, 2)).until(x, (0, 3)), 80, 1)["raises_always"] == 1
+    assert sem.plan(x.eventually((0, 2)).until(x, (0, 3)), 80, 1)["raises_always"] == 0
+    with pytest.raises(NotImplementedError):  # open interval on a trace longer than any tile
+        sem.plan(x.always((0, None)), 100000, 1)
+    assert sem.plan(x.always((0, None)), 4000, 1)["n_tiles"] == 1
+
+
+def test_loud_failure_without_the_library(monkeypatch, tmp_path):
+    monkeypatch.setattr(capi, "_lib", None)
+    monkeypatch.setattr(capi, "LIB_PATH", str(tmp_path / "missing.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        capi.lib()
+
+
+def test_no_cuda_device_is_an_error_not_a_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    sem = create_semantics("classical", backend="b200")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sem.robustness_trace(gt(0, 0.0).always((0, 3)), np.zeros((2, 10, 1), np.float32))
