@@ -17,8 +17,8 @@ namespace pystl {
 // ------------------------------------------------------------------ device executor
 struct DevExec {
   int tid_, nt_;
-  float stash_;
-  __device__ __forceinline__ DevExec() : tid_(threadIdx.x), nt_(blockDim.x), stash_(0.f) {}
+  float stash_, stash2_;
+  __device__ __forceinline__ DevExec() : tid_(threadIdx.x), nt_(blockDim.x), stash_(0.f), stash2_(0.f) {}
   __device__ __forceinline__ int t0() const { return tid_; }
   __device__ __forceinline__ int t1() const { return tid_ + 1; }
   __device__ __forceinline__ void sync() { __syncthreads(); }
@@ -33,6 +33,23 @@ struct DevExec {
     k = __reduce_max_sync(0xffffffffu, k);
     k = k >= 0 ? k : k ^ 0x7fffffff;
     return __int_as_float(k);
+  }
+  __device__ __forceinline__ void put2(int, float a, float b) {
+    stash_ = a;
+    stash2_ = b;
+  }
+  // two block-wide maxima at once
+  __device__ __forceinline__ void all_max2(float* red, float& a, float& b) {
+    float va = warp_max(stash_), vb = warp_max(stash2_);
+    const int lane = tid_ & 31, warp = tid_ >> 5, nw = nt_ >> 5;
+    if (lane == 0) {
+      red[64 + warp] = va;
+      red[96 + warp] = vb;
+    }
+    __syncthreads();
+    a = warp_max(lane < nw ? red[64 + lane] : -INFINITY);
+    b = warp_max(lane < nw ? red[96 + lane] : -INFINITY);
+    __syncthreads();
   }
   __device__ __forceinline__ float all_max(float* red) {
     float v = warp_max(stash_);
@@ -157,9 +174,10 @@ __global__ void __launch_bounds__(MAXT, MINB) fwd_kernel(const __grid_constant__
   if (ex.tid_ == 0) mbar_init(&bar, 1);
   __syncthreads();
 
-  const int64_t tile = blockIdx.x;
-  const int64_t b = tile / g.n_tiles;
-  const int j = (int)(tile - b * g.n_tiles);
+  const unsigned tile = blockIdx.x;
+  const unsigned bu = tile / (unsigned)g.n_tiles;
+  const int j = (int)(tile - bu * (unsigned)g.n_tiles);
+  const int64_t b = bu;
   const int64_t e0 = (int64_t)j * g.lout;
   const Ctx c = make_ctx(smem, g, P, e0);
 
@@ -183,9 +201,10 @@ __global__ void __launch_bounds__(MAXT, MINB) bwd_kernel(const __grid_constant__
   if (ex.tid_ == 0) mbar_init(&bar, 1);
   __syncthreads();
 
-  const int64_t tile = blockIdx.x;
-  const int64_t b = tile / g.n_tiles;
-  const int j = (int)(tile - b * g.n_tiles);
+  const unsigned tile = blockIdx.x;
+  const unsigned bu = tile / (unsigned)g.n_tiles;
+  const int j = (int)(tile - bu * (unsigned)g.n_tiles);
+  const int64_t b = bu;
   const int64_t t0 = (int64_t)j * g.lout;
   const int64_t e0 = t0 > g.hh ? t0 - g.hh : 0;
   const Ctx c = make_ctx(smem, g, P, e0);

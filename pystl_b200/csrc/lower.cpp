@@ -418,6 +418,7 @@ struct Lowerer {
       }
     }
     const Ref rr = operand(n - 1);
+    if (n_slots > kMaxSlots) fail(PYSTL_E_UNSUPPORTED, "formula needs more than %d value planes", kMaxSlots);
     P().root = (int16_t)rr.slot;
     P().root_neg = (int16_t)(rr.neg ? 1 : 0);
     P().n_slots = n_slots;
@@ -425,6 +426,60 @@ struct Lowerer {
     P().raises_always = slack[n - 1] >= kNever ? 1 : 0;
     out->lookahead = look[n - 1];
     out->out_channels = sem == SEM_CUMULATIVE ? 2 : 1;
+    if (backward) plan_adjoint_planes();
+  }
+
+  // Backward pass: assign a plane to every adjoint, reusing planes whose contents are dead.
+  // Instructions run in reverse; after instruction i its result's value and adjoint are dead
+  // (every consumer has a higher index and has already run), and an operand's value dies
+  // with its lowest-index consumer.  Classic only needs the predicates' adjoints (the
+  // gradient is one scatter through the recorded provenance).
+  void plan_adjoint_planes() {
+    TileProgram& p = P();
+    const int vw = p.sem == SEM_CLASSIC ? 2 : 1;  // SEM_CLASSIC_SRC values are two words
+    for (int s = 0; s < kMaxSlots; ++s) p.adj_of[s] = -1;
+    int n_planes = p.n_slots * vw;
+    if (p.sem == SEM_CLASSIC) {
+      for (int q = 0; q < p.n_preds; ++q) p.adj_of[p.preds[q].dst] = (int16_t)n_planes++;
+      p.n_planes_bwd = n_planes;
+      return;
+    }
+    std::vector<int> free_planes;
+    auto take = [&]() {
+      if (!free_planes.empty()) {
+        const int x = free_planes.back();
+        free_planes.pop_back();
+        return x;
+      }
+      return n_planes++;
+    };
+    std::vector<int> first_use(p.n_slots, p.n_instr);  // lowest-index instruction reading the value
+    std::vector<char> is_pred(p.n_slots, 0);
+    for (int q = 0; q < p.n_preds; ++q) is_pred[p.preds[q].dst] = 1;
+    for (int i = 0; i < p.n_instr; ++i)
+      for (int j = 0; j < p.ins[i].nsrc; ++j) first_use[p.ins[i].src[j]] = std::min(first_use[p.ins[i].src[j]], i);
+    p.adj_of[p.root] = (int16_t)take();  // the cotangent lands here
+    for (int i = p.n_instr - 1; i >= 0; --i) {
+      TInstr& in = p.ins[i];
+      in.adj_first = 0;
+      if (p.adj_of[in.dst] < 0) continue;  // result never reaches the root (cannot happen: dead code is not lowered)
+      for (int j = 0; j < in.nsrc; ++j) {
+        if (p.adj_of[in.src[j]] < 0) {
+          p.adj_of[in.src[j]] = (int16_t)take();
+          in.adj_first |= (uint8_t)(1u << j);
+        }
+      }
+      // the result's adjoint and value are dead now; so is any operand value this was the last reader of
+      free_planes.push_back(p.adj_of[in.dst]);
+      free_planes.push_back(in.dst);
+      for (int j = 0; j < in.nsrc; ++j) {
+        const int sj = in.src[j];
+        bool again = false;
+        for (int k = 0; k < j; ++k) again = again || in.src[k] == sj;
+        if (!again && first_use[sj] == i && is_pred[sj]) free_planes.push_back(sj);
+      }
+    }
+    p.n_planes_bwd = n_planes;
   }
 };
 
@@ -514,12 +569,12 @@ int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_
       t.gl = t.gr = ((reach + 8 + 7) / 8) * 8;
     }
     t.off_planes = 0;
-    t.off_scratch = P.n_slots * (vw + (backward ? 1 : 0)) * t.lext;
+    t.off_scratch = (backward ? P.n_planes_bwd : P.n_slots * vw) * t.lext;
     // the raw [sample][channel] rows share their storage with the scratch planes
     const int raw_floats = ((t.lext * D + 3) / 4) * 4;
     t.off_chunk = t.off_scratch + std::max(raw_floats, scr_planes * (t.gl + t.lext + t.gr));
     t.off_red = t.off_chunk + 4 * (t.gl / 8 + nt + t.gr / 8);
-    t.smem_floats = t.off_red + 128;
+    t.smem_floats = t.off_red + 128 + 2 * (P.n_slots + 1) + kMaxSlots;  // reduction scratch, value ranges, adjoint map
     if (t.smem_floats * 4 > smem_cap) return false;
     *out = t;
     return true;

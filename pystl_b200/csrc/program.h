@@ -17,6 +17,7 @@ constexpr int kMaxTerms = 8;    // == PYSTL_MAX_TERMS
 constexpr int kMaxPreds = 16;   // distinct affine predicates per formula
 constexpr int kMaxInstr = 40;   // lowered instructions per formula
 constexpr int kMaxThreads = 1024;
+constexpr int kMaxSlots = kMaxPreds + kMaxInstr + 8;  // value slots of one formula
 
 enum Sem : int32_t {
   SEM_CLASSIC = 0,
@@ -61,7 +62,8 @@ struct TInstr {
   int16_t nsrc;
   int16_t src[kMaxSrc];  // plane slots
   uint16_t negmask;      // bit i: operand i is negated (Not folded into the consumer)
-  int16_t unbounded;     // T_UNTIL: b is the horizon
+  int8_t unbounded;      // T_UNTIL: b is the horizon
+  uint8_t adj_first;     // backward: bit i: this instruction is the first to write operand i's adjoint
   int32_t a, b;          // window offsets relative to t (signed: the backward pass looks back)
   float w[kMaxSrc];      // n-ary weights; T_UNTIL: w[0], w[1] = weights_pair
   float sw;              // sum of the n-ary weights
@@ -93,6 +95,10 @@ struct TileProgram {
   int32_t start_slack;  // outputs at t > T-1-start_slack are NaN
   int32_t raises_always;
   RP rp;
+  // backward only: plane holding the adjoint of value slot s (-1: none), and how many planes
+  // (values + adjoints, after reuse of dead ones) the tile needs
+  int16_t adj_of[kMaxSlots];
+  int32_t n_planes_bwd;
   TPred preds[kMaxPreds];
   TInstr ins[kMaxInstr];
 };

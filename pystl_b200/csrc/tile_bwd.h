@@ -43,18 +43,24 @@ struct SumOp {
   }
 };
 
-// adjoint plane of value slot `slot` (one word per slot; they follow the value planes)
+// adjoint plane of value slot `slot` (one word per slot; the host assigned it, reusing planes
+// whose contents are dead by the time the adjoint is first written: lower.cpp)
 template <int SEM>
 PYSTL_HD float* adj_plane(const Ctx& c, int slot) {
-  return c.smem + c.off_planes + (c.n_slots * Tr<SEM>::VW + slot) * c.lext;
+  return c.smem + c.off_planes + c.adj_tab()[slot] * c.lext;
 }
 
-// g_plane[own chunk] += sign * g
+// g_plane[own chunk] (+)= sign * g; `first`: this is the first write, the plane holds garbage
 template <int SEM>
-PYSTL_HD void adj_accum8(const Ctx& c, int slot, bool neg, int tid, const float (&g)[8]) {
+PYSTL_HD void adj_accum8(const Ctx& c, int slot, bool neg, bool first, int tid, const float (&g)[8]) {
   float* pl = adj_plane<SEM>(c, slot);
   float cur[8];
-  load8(pl, tid, cur);
+  if (first) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur[i] = 0.f;
+  } else {
+    load8(pl, tid, cur);
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) cur[i] += neg ? -g[i] : g[i];
   store8(pl, tid, cur);
@@ -139,7 +145,7 @@ template <int SEM, int MODE, class EX>
 PYSTL_HD void op_nary_bwd(EX& ex, const Ctx& c, const TInstr& in) {
   using AD = Adj<SEM, MODE>;
   const int nsrc = in.nsrc, dst = in.dst;
-  const unsigned negmask = in.negmask;
+  const unsigned negmask = in.negmask, firstmask = in.adj_first;
   const float sw = in.sw;
   PYSTL_FOR_THREADS(ex, tid) {
     RP rp = c.rp;
@@ -159,7 +165,7 @@ PYSTL_HD void op_nary_bwd(EX& ex, const Ctx& c, const TInstr& in) {
           const float wgt = AD::pair_weight(o[i].x[0], v[i].x[0], rp);
           gj[i] = (g[i] != 0.f) ? g[i] * wgt : 0.f;
         }
-        adj_accum8<SEM>(c, in.src[j], neg, tid, gj);
+        adj_accum8<SEM>(c, in.src[j], neg, (firstmask >> j) & 1, tid, gj);
       }
     } else {
       Vec<AD::KW> k[8];
@@ -178,7 +184,7 @@ PYSTL_HD void op_nary_bwd(EX& ex, const Ctx& c, const TInstr& in) {
         float gj[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) gj[i] = (g[i] != 0.f) ? AD::in_factor(k[i], v[i].x[0], wj, rp) : 0.f;
-        adj_accum8<SEM>(c, in.src[j], neg, tid, gj);
+        adj_accum8<SEM>(c, in.src[j], neg, (firstmask >> j) & 1, tid, gj);
       }
     }
   }
@@ -195,7 +201,7 @@ PYSTL_HD void op_win_bwd(EX& ex, const Ctx& c, const TInstr& in) {
   Win wn = decode_win(in);
   const bool open = in.op == T_WIN_SUFFIX;
   if (open) wn.b = 0x3fffffff;
-  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, wn.src, wn.neg);
+  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_shift<MODE>(c, wn.src, wn.neg);
   // backward-looking window: t in [q - b, q - a]
   const int fa = clamp_off(wn.a, c.lext), fb = clamp_off(wn.b, c.lext);
   const int wa = -fb, wb = -fa;
@@ -232,7 +238,7 @@ PYSTL_HD void op_win_bwd(EX& ex, const Ctx& c, const TInstr& in) {
     float gx[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) gx[i] = (8 * tid + i < c.nlive) ? AD::in_factor(w[i], x[i].x[0], 1.f, rp) : 0.f;
-    adj_accum8<SEM>(c, wn.src, wn.neg, tid, gx);
+    adj_accum8<SEM>(c, wn.src, wn.neg, (in.adj_first & 1) != 0, tid, gx);
   }
   ex.sync();
   if constexpr (SEM == SEM_SMOOTH) {
@@ -301,11 +307,6 @@ PYSTL_HD void init_adjoints(EX& ex, const Ctx& c, const TileProgram& P, const fl
   const bool neg = P.root_neg != 0;
   if (p_hi > c.last_ok + 1) p_hi = c.last_ok + 1;
   PYSTL_FOR_THREADS(ex, tid) {
-    float z[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) z[i] = 0.f;
-    for (int s = 0; s < c.n_slots; ++s)
-      if (s != root) store8(adj_plane<SEM>(c, s), tid, z);
     float g[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -316,6 +317,15 @@ PYSTL_HD void init_adjoints(EX& ex, const Ctx& c, const TileProgram& P, const fl
     }
     store8(adj_plane<SEM>(c, root), tid, g);
   }
+}
+
+// copy the adjoint-plane map of the program next to the planes (uniform reads afterwards)
+template <class EX>
+PYSTL_HD void load_adj_table(EX& ex, const Ctx& c, const TileProgram& P) {
+  PYSTL_FOR_THREADS(ex, tid) {
+    for (int s = tid; s < kMaxSlots; s += c.nt) c.adj_tab()[s] = P.adj_of[s];
+  }
+  ex.sync();
 }
 
 // grad_signal[p, d] = sum over predicates of coeff[d] * adjoint(predicate)[p] for tile positions
@@ -336,7 +346,7 @@ PYSTL_HD void store_signal_grad(EX& ex, const Ctx& c, const TileProgram& P, floa
         for (int d = 0; d < 8; ++d) row[d] = 0.f;
 #pragma unroll 1
         for (int q = 0; q < np; ++q) {
-          const float g = adj_plane<SEM>(c, P.preds[q].dst)[pp];
+          const float g = c.adj_tab()[P.preds[q].dst] >= 0 ? adj_plane<SEM>(c, P.preds[q].dst)[pp] : 0.f;
           const int nterms = P.preds[q].n_terms;
 #pragma unroll 1
           for (int k = 0; k < nterms; ++k) {
@@ -353,7 +363,7 @@ PYSTL_HD void store_signal_grad(EX& ex, const Ctx& c, const TileProgram& P, floa
         for (int d = 0; d < D; ++d) {
           float acc = 0.f;
           for (int q = 0; q < np; ++q) {
-            const float g = adj_plane<SEM>(c, P.preds[q].dst)[pp];
+            const float g = c.adj_tab()[P.preds[q].dst] >= 0 ? adj_plane<SEM>(c, P.preds[q].dst)[pp] : 0.f;
             for (int k = 0; k < P.preds[q].n_terms; ++k)
               if (P.preds[q].ch[k] == d) acc += P.preds[q].coeff[k] * g;
           }
@@ -369,6 +379,7 @@ PYSTL_HD void store_signal_grad(EX& ex, const Ctx& c, const TileProgram& P, floa
 template <int SEM, class EX>
 PYSTL_HD void run_backward(EX& ex, const Ctx& c, const TileProgram& P, const float* raw, const float* go_tile,
                            float scale, float* gs_tile, int p_lo, int p_hi) {
+  load_adj_table(ex, c, P);
   if constexpr (SEM == SEM_CLASSIC) {
     constexpr int S = SEM_CLASSIC_SRC;
     run_program<S>(ex, c, P, raw);

@@ -250,6 +250,11 @@ struct Ctx {
   PYSTL_HD float* scr(int i) const { return smem + off_scratch + i * (gl + lext + gr) + gl; }
   PYSTL_HD float* chunk(int i) const { return smem + off_chunk + i * (gl / 8 + nt + gr / 8) + gl / 8; }
   PYSTL_HD float* raw() const { return smem + off_scratch; }
+  // [lo, hi] of every value plane (smooth only): every thread writes the same numbers, so a
+  // thread always reads back what it wrote itself and no barrier is needed
+  PYSTL_HD float* bounds() const { return smem + off_red + 128; }
+  // backward: adj_tab()[s] = plane index of the adjoint of value slot s (copied from the program)
+  PYSTL_HD int* adj_tab() const { return reinterpret_cast<int*>(smem + off_red + 128 + 2 * (n_slots + 1)); }
   PYSTL_HD float* red() const { return smem + off_red; }
 };
 
@@ -273,6 +278,23 @@ PYSTL_HD Ctx make_ctx(float* smem, const TileGeom& g, const TileProgram& P, int6
   c.last_ok = ok > (int64_t)(1 << 30) ? (1 << 30) : (ok < -1 ? -1 : (int)ok);
   c.rp = P.rp;
   return c;
+}
+
+// smooth only: an upper bound of the operand's exponent over the tile, from the value range
+// tracked per plane (exact for predicates, within log2(#terms) per operator above them)
+template <int MODE>
+PYSTL_HD float smooth_shift(const Ctx& c, int slot, bool neg) {
+  const float lo = c.bounds()[2 * slot], hi = c.bounds()[2 * slot + 1];
+  const float vlo = neg ? -hi : lo, vhi = neg ? -lo : hi;  // range of the (possibly negated) operand
+  return (MODE == MODE_AND ? -vlo : vhi) * c.rp.k;
+}
+// range of softmin / softmax over n terms of operands within [lo, hi]:
+//   min - tau ln n <= softmin <= min,   max <= softmax <= max + tau ln n
+template <int MODE>
+PYSTL_HD void smooth_set_bounds(const Ctx& c, int dst, float lo, float hi, float n) {
+  const float pad = c.rp.invk * fast_lg2(n > 1.f ? n : 1.f) + 1e-6f * (fabsf(lo) + fabsf(hi));
+  c.bounds()[2 * dst] = MODE == MODE_AND ? lo - pad : lo;
+  c.bounds()[2 * dst + 1] = MODE == MODE_AND ? hi : hi + pad;
 }
 
 // own chunk of a plane <-> registers
@@ -404,21 +426,33 @@ PYSTL_HD float chan(const float (&row)[8], const float* raw, int p, int D, int c
 template <int SEM, int DV, class EX>
 PYSTL_HD void eval_predicates_d(EX& ex, const Ctx& c, const TileProgram& P, const float* raw) {
   constexpr int VW = Tr<SEM>::VW;
-  const int D = c.D, nt = c.nt;
+  const int D = c.D, nt = c.nt, nlive = c.nlive;
   const int np = P.n_preds;
-  PYSTL_FOR_THREADS(ex, tid) {
 #pragma unroll 1
-    for (int i = 0; i < kChunk; ++i) {
-      const int p = tid + nt * i;
-      const int pp = pidx(p);
-      float row[8];
-      if constexpr (DV > 0) load_row<DV>(raw, p, D, row);
-#pragma unroll 1
-      for (int q = 0; q < np; ++q) {
-        const int nterms = P.preds[q].n_terms;
-        const float bias = P.preds[q].bias;
+  for (int q = 0; q < np; ++q) {
+    // everything about the predicate is fetched once, then 8 samples are streamed through it
+    const int nterms = P.preds[q].n_terms;
+    const float bias = P.preds[q].bias;
+    const bool f64 = (SEM == SEM_CLASSIC || SEM == SEM_CLASSIC_SRC) && P.preds[q].f64;
+    const int ch0 = P.preds[q].ch[0], ch1 = P.preds[q].ch[1];
+    const float c0 = P.preds[q].coeff[0], c1 = nterms > 1 ? P.preds[q].coeff[1] : 0.f;
+    float* pl0 = c.plane(P.preds[q].dst, 0, VW);
+    float* pl1 = c.plane(P.preds[q].dst, VW - 1, VW);
+    PYSTL_FOR_THREADS(ex, tid) {
+      float lo = f_inf(), hi = -f_inf();
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i) {
+        const int p = tid + nt * i;
+        float row[8];
+        if constexpr (DV > 0) load_row<DV>(raw, p, D, row);
         float acc;
-        if ((SEM == SEM_CLASSIC || SEM == SEM_CLASSIC_SRC) && P.preds[q].f64) {
+        if (!f64 && nterms <= 2) {
+          // 0 + (+-x) is exact: a single-term predicate rounds once
+          acc = fmaf(c0, chan<DV>(row, raw, p, D, ch0), 0.f);
+          if (nterms == 2) acc = fmaf(c1, chan<DV>(row, raw, p, D, ch1), acc);
+          if (nterms == 0) acc = 0.f;
+          acc += bias;
+        } else if (f64) {
           // the reference evaluates predicates in float64 (classic.py:20); same operations, same
           // order as formula.affine_predicate, one final rounding: bit-exact after the cast
           double a = 0.0;
@@ -426,12 +460,6 @@ PYSTL_HD void eval_predicates_d(EX& ex, const Ctx& c, const TileProgram& P, cons
           for (int k = 0; k < nterms; ++k)
             a = fma((double)P.preds[q].coeff[k], (double)chan<DV>(row, raw, p, D, P.preds[q].ch[k]), a);
           acc = (float)(a + (double)bias);
-        } else if (nterms == 1) {
-          // 0 + (+-x) is exact: a single-term predicate rounds once
-          acc = fmaf(P.preds[q].coeff[0], chan<DV>(row, raw, p, D, P.preds[q].ch[0]), 0.f) + bias;
-        } else if (nterms == 2) {
-          acc = fmaf(P.preds[q].coeff[0], chan<DV>(row, raw, p, D, P.preds[q].ch[0]), 0.f);
-          acc = fmaf(P.preds[q].coeff[1], chan<DV>(row, raw, p, D, P.preds[q].ch[1]), acc) + bias;
         } else {
           acc = 0.f;
 #pragma unroll 1
@@ -439,17 +467,31 @@ PYSTL_HD void eval_predicates_d(EX& ex, const Ctx& c, const TileProgram& P, cons
             acc = fmaf(P.preds[q].coeff[k], chan<DV>(row, raw, p, D, P.preds[q].ch[k]), acc);
           acc += bias;
         }
-        const int dst = P.preds[q].dst;
+        const int pp = pidx(p);
         if constexpr (SEM == SEM_CUMULATIVE) {  // cumulative.py:29-30
-          c.plane(dst, 0, VW)[pp] = fmaxf(0.f, acc);
-          c.plane(dst, 1, VW)[pp] = fminf(0.f, acc);
+          pl0[pp] = fmaxf(0.f, acc);
+          pl1[pp] = fminf(0.f, acc);
         } else if constexpr (SEM == SEM_CLASSIC_SRC) {
-          c.plane(dst, 0, VW)[pp] = acc;
-          c.plane(dst, 1, VW)[pp] = i2f((q << 24) | p);
+          pl0[pp] = acc;
+          pl1[pp] = i2f((q << 24) | p);
         } else {
-          c.plane(dst, 0, VW)[pp] = acc;
+          pl0[pp] = acc;
+        }
+        if constexpr (SEM == SEM_SMOOTH) {
+          if (p < nlive) {
+            lo = fminf(lo, acc);
+            hi = fmaxf(hi, acc);
+          }
         }
       }
+      if constexpr (SEM == SEM_SMOOTH) ex.put2(tid, -lo, hi);
+    }
+    if constexpr (SEM == SEM_SMOOTH) {
+      // value range of the plane: smooth windows shift their exponentials by a bound of the max
+      float mlo, mhi;
+      ex.all_max2(c.red(), mlo, mhi);
+      c.bounds()[2 * P.preds[q].dst] = -mlo;
+      c.bounds()[2 * P.preds[q].dst + 1] = mhi;
     }
   }
 }
@@ -474,6 +516,17 @@ PYSTL_HD void op_nary(EX& ex, const Ctx& c, const TInstr& in) {
   const int nsrc = in.nsrc, dst = in.dst;
   const unsigned negmask = in.negmask;
   const float sw = in.sw;
+  if constexpr (SEM == SEM_SMOOTH) {
+    float lo = MODE == MODE_AND ? f_inf() : -f_inf(), hi = lo;  // min / max over the operands' ranges
+    for (int j = 0; j < nsrc; ++j) {
+      const bool ng = (negmask >> j) & 1;
+      const float l = ng ? -c.bounds()[2 * in.src[j] + 1] : c.bounds()[2 * in.src[j]];
+      const float h = ng ? -c.bounds()[2 * in.src[j]] : c.bounds()[2 * in.src[j] + 1];
+      lo = MODE == MODE_AND ? fminf(lo, l) : fmaxf(lo, l);
+      hi = MODE == MODE_AND ? fminf(hi, h) : fmaxf(hi, h);
+    }
+    smooth_set_bounds<MODE>(c, dst, lo, hi, (float)nsrc);
+  }
   PYSTL_FOR_THREADS(ex, tid) {
     RP rp = c.rp;
     A acc[8];
@@ -539,24 +592,6 @@ PYSTL_HD int window_count(const Ctx& c, int p, int a, int b) {
   if (lo < c.first) lo = c.first;
   if (hi > c.nlive - 1) hi = c.nlive - 1;
   return hi - lo + 1;
-}
-
-// smooth only: block-wide max exponent of the operand over the live samples
-template <int SEM, int MODE, class EX>
-PYSTL_HD float smooth_block_shift(EX& ex, const Ctx& c, int slot, bool neg) {
-  using R = Red<SEM, MODE>;
-  using V = typename R::V;
-  const int nlive = c.nlive;
-  PYSTL_FOR_THREADS(ex, tid) {
-    V v[8];
-    load_val8<SEM>(c, slot, neg, tid, v);
-    float m = -f_inf();
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (8 * tid + i < nlive) m = fmaxf(m, R::expo(v[i], c.rp));
-    ex.put(tid, m);
-  }
-  return ex.all_max(c.red());
 }
 
 // smooth only: exact logsumexp of one window straight from the operand plane (rare path,
@@ -797,8 +832,12 @@ PYSTL_HD void op_win(EX& ex, const Ctx& c, const TInstr& in, bool vh) {
   constexpr int AW = Tr<SEM>::AW;
   RP rp = c.rp;
   const Win wn = decode_win(in);
-  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, wn.src, wn.neg);
   const int wa = clamp_off(wn.a, c.lext), wb = clamp_off(wn.b, c.lext);
+  if constexpr (SEM == SEM_SMOOTH) {
+    rp.shift = smooth_shift<MODE>(c, wn.src, wn.neg);
+    const float lo = c.bounds()[2 * wn.src], hi = c.bounds()[2 * wn.src + 1];
+    smooth_set_bounds<MODE>(c, wn.dst, wn.neg ? -hi : lo, wn.neg ? -lo : hi, (float)(wb - wa + 1));
+  }
   PYSTL_FOR_THREADS(ex, tid) {
     A x[8];
     lift_own8<SEM, MODE>(c, wn, rp, tid, x);
@@ -836,7 +875,11 @@ PYSTL_HD void op_win_suffix(EX& ex, const Ctx& c, const TInstr& in) {
   RP rp = c.rp;
   Win wn = decode_win(in);
   wn.b = 0x3fffffff;  // open end: clipped at the horizon by window_count
-  if constexpr (SEM == SEM_SMOOTH) rp.shift = smooth_block_shift<SEM, MODE>(ex, c, wn.src, wn.neg);
+  if constexpr (SEM == SEM_SMOOTH) {
+    rp.shift = smooth_shift<MODE>(c, wn.src, wn.neg);
+    const float lo = c.bounds()[2 * wn.src], hi = c.bounds()[2 * wn.src + 1];
+    smooth_set_bounds<MODE>(c, wn.dst, wn.neg ? -hi : lo, wn.neg ? -lo : hi, (float)c.lext);
+  }
   PYSTL_FOR_THREADS(ex, tid) {
     A x[8];
     lift_own8<SEM, MODE>(c, wn, rp, tid, x);
@@ -1082,9 +1125,16 @@ PYSTL_HD void op_until(EX& ex, const Ctx& c, const TInstr& ins) {
   RP rp = c.rp;
   if constexpr (SEM == SEM_SMOOTH) {
     // shift = max over both operands of the exponent -v/tau
-    const float ml = smooth_block_shift<SEM, MODE_AND>(ex, c, in.sl, in.nl);
-    const float mr = smooth_block_shift<SEM, MODE_AND>(ex, c, in.sr, in.nr);
-    rp.shift = fmaxf(ml, mr);
+    rp.shift = fmaxf(smooth_shift<MODE_AND>(c, in.sl, in.nl), smooth_shift<MODE_AND>(c, in.sr, in.nr));
+    // softmin over <= b+2 terms inside a softmax over <= b+1 candidates
+    const float llo = in.nl ? -c.bounds()[2 * in.sl + 1] : c.bounds()[2 * in.sl];
+    const float lhi = in.nl ? -c.bounds()[2 * in.sl] : c.bounds()[2 * in.sl + 1];
+    const float rlo = in.nr ? -c.bounds()[2 * in.sr + 1] : c.bounds()[2 * in.sr];
+    const float rhi = in.nr ? -c.bounds()[2 * in.sr] : c.bounds()[2 * in.sr + 1];
+    const float nn = (float)((open ? c.lext : ub) + 2);
+    const float pad = 2.f * c.rp.invk * fast_lg2(nn) + 1e-6f * (fabsf(llo) + fabsf(rhi));
+    c.bounds()[2 * in.dst] = fminf(llo, rlo) - pad;
+    c.bounds()[2 * in.dst + 1] = fmaxf(lhi, rhi) + pad;
   }
   // stage l and r (negations applied) in scratch planes so that phase 2 reads plain runs
   PYSTL_FOR_THREADS(ex, tid) {
@@ -1302,6 +1352,18 @@ struct HostExec {
   void sync() {}
   void put(int tid, float v) { stash[tid] = v; }
   float get(int tid) const { return stash[tid]; }
+  float stash2[kMaxThreads];
+  void put2(int tid, float a, float b) {
+    stash[tid] = a;
+    stash2[tid] = b;
+  }
+  void all_max2(float*, float& a, float& b) {
+    a = b = -INFINITY;
+    for (int i = 0; i < nt_; ++i) {
+      a = fmaxf(a, stash[i]);
+      b = fmaxf(b, stash2[i]);
+    }
+  }
   void atomic_add(float* p, float v) { *p += v; }
   float all_max(float*) {
     float m = -INFINITY;
