@@ -526,7 +526,10 @@ int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_
   // the classic backward kernel evaluates SEM_CLASSIC_SRC: two words per value
   const int vw = (P.sem == SEM_CUMULATIVE || (backward && P.sem == SEM_CLASSIC)) ? 2 : 1;
   const int aw = (P.sem == SEM_CLASSIC || P.sem == SEM_SMOOTH) ? 1 : 2;
-  const int scr_planes = backward ? 4 : 2 * std::max(aw, vw);
+  // scratch planes: SUF + PRE of the widest accumulator (forward: aw words; the adjoint window
+  // sums of the backward pass: 1 word for smooth, 2 for agm / dgmsr), or the staged until operands
+  const int kw = P.sem == SEM_SMOOTH ? 1 : 2;
+  const int scr_planes = backward ? 2 * std::max(aw, P.sem == SEM_CLASSIC ? 2 : kw) : 2 * std::max(aw, vw);
   const int hh = backward && lw.lookahead > 0 ? ((lw.lookahead + 7) / 8) * 8 : 0;
   const bool full = needs_full_trace(P) || lw.lookahead < 0;
   // furthest offsets any window instruction reads at (guards of the scratch planes)
