@@ -89,6 +89,8 @@ EXPORTS = (
     "pystl_b200_plan",
     "pystl_b200_eval_forward",
     "pystl_b200_eval_backward",
+    "pystl_b200_fused_precompile",
+    "pystl_b200_fused_source",
 )
 
 # PYSTL_B200_LIB points at an alternative build of the same library (A/B timing of kernel variants)
@@ -121,6 +123,12 @@ def declare(lib: C.CDLL, prefix: str = "pystl_b200") -> None:
             C.POINTER(Formula), C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
             C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
         ]
+        f = lib.pystl_b200_fused_precompile
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(Formula), C.c_int64, C.c_int32, C.c_int32]
+        f = lib.pystl_b200_fused_source
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(Formula), C.c_int64, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
 
 
 def lib() -> C.CDLL:

@@ -1,0 +1,427 @@
+// Code generator of the FUSED tier: lowered formula (SSA TileProgram) -> CUDA kernel source.
+//
+// The generated kernel is glue: a straight-line sequence of calls into the hand-written
+// templates of fused_rt.cuh with every structural constant (window offsets, operand signs,
+// channel indices, shared-memory offsets, CTA size) baked in as a template argument, and every
+// numeric parameter (predicate coefficients, weights, temperature, eps) read from the
+// TileProgram the kernel receives by value -- retuning a threshold or the temperature does not
+// trigger a recompile.  Values live in registers (`v<slot>[8]`, the 8 samples a thread owns);
+// windows of the same nesting depth share one barrier.
+//
+// Host-only C++ (also compiled into the test-only emulator library).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pystl_b200.h"
+#include "fused_host.h"
+#include "program.h"
+
+namespace pystl {
+namespace {
+
+struct Src {
+  std::string s;
+  int indent = 1;
+  void line(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    for (int i = 0; i < indent; ++i) s += "  ";
+    s += buf;
+    s += "\n";
+  }
+};
+
+int roundup(int x, int m) { return ((x + m - 1) / m) * m; }
+int clamp_off(int x, int lext) { return x > lext ? lext : (x < -lext ? -lext : x); }
+
+// mirror of fused::WinOp<R, WA, WB, NT>::FLOATS (checked by a static_assert in the generated code)
+int win_floats(int aw, int wa, int wb, int nt) {
+  const int W = wb - wa + 1;
+  const bool vh = W > 8;
+  const int GL = wa < 0 ? roundup(-wa, 8) : 0;
+  const int GR = (wb > 0 ? roundup(wb, 8) : 0) + 8;
+  const int PLANE = GL + 8 * nt + GR;
+  const bool use_suf = vh ? (wa != 0) : true;
+  const bool use_pre = vh && (wb != 0);
+  const int npl = (use_suf ? 1 : 0) + (use_pre ? 1 : 0);
+  const int aggn = vh ? roundup(PLANE / 8, 4) : 0;
+  return aw * (npl * PLANE + aggn);
+}
+
+const char* sem_name(int sem) {
+  switch (sem) {
+    case SEM_CLASSIC: return "SEM_CLASSIC";
+    case SEM_SMOOTH: return "SEM_SMOOTH";
+    case SEM_CUMULATIVE: return "SEM_CUMULATIVE";
+    case SEM_AGM: return "SEM_AGM";
+    case SEM_DGMSR: return "SEM_DGMSR";
+    default: return "SEM_CLASSIC_SRC";
+  }
+}
+const char* mode_name(int m) { return m == MODE_AND ? "MODE_AND" : (m == MODE_OR ? "MODE_OR" : "MODE_SUM"); }
+
+bool is_window(const TInstr& in) { return in.op == T_WIN_DIRECT || in.op == T_WIN_VH; }
+
+struct Gen {
+  const Lowered& lw;
+  const TileProgram& P;
+  int D, nt, minb;
+  Src o;
+  std::vector<int> level;     // per slot
+  std::vector<int> ins_level; // per instruction: stage in which its result becomes available
+  std::vector<int> scr_off;   // per instruction: scratch offset (floats)
+  std::vector<int> stash_off; // per instruction: smooth operand stash
+  int smem_floats = 0;
+  int n_stages = 0;
+
+  Gen(const Lowered& l, int D_, int nt_, int minb_) : lw(l), P(l.prog), D(D_), nt(nt_), minb(minb_) {}
+
+  int vw() const { return P.sem == SEM_CUMULATIVE ? 2 : 1; }
+  int aw() const { return (P.sem == SEM_CLASSIC || P.sem == SEM_SMOOTH) ? 1 : 2; }
+
+  bool supported(std::string* why) const {
+    if (D < 1) {
+      *why = "bad D";
+      return false;
+    }
+    for (int i = 0; i < P.n_instr; ++i) {
+      const TInstr& in = P.ins[i];
+      if (in.op != T_NARY && !is_window(in)) {
+        *why = "until / open-ended windows are evaluated by the interpreter tier";
+        return false;
+      }
+    }
+    return true;
+  }
+
+  void plan() {
+    level.assign(kMaxSlots, 0);
+    ins_level.assign(P.n_instr, 0);
+    scr_off.assign(P.n_instr, 0);
+    stash_off.assign(P.n_instr, -1);
+    int max_level = 0;
+    for (int i = 0; i < P.n_instr; ++i) {
+      const TInstr& in = P.ins[i];
+      int l = 0;
+      for (int j = 0; j < in.nsrc; ++j) l = std::max(l, level[in.src[j]]);
+      if (is_window(in)) l += 1;
+      level[in.dst] = l;
+      ins_level[i] = l;
+      max_level = std::max(max_level, l);
+    }
+    n_stages = max_level + 1;
+    // shared memory: [reduction scratch][region 0][region 1]; windows of level l use region l & 1
+    const int nw = nt / 32;
+    const int red_floats = roundup(std::max(2 * std::max(P.n_preds, 1), 1) * nw, 32);
+    std::vector<int> used(max_level + 2, 0);
+    for (int i = 0; i < P.n_instr; ++i) {
+      const TInstr& in = P.ins[i];
+      if (!is_window(in)) continue;
+      const int l = ins_level[i];
+      scr_off[i] = used[l];
+      used[l] += win_floats(aw(), clamp_off(in.a, 8 * nt), clamp_off(in.b, 8 * nt), nt);
+      if (P.sem == SEM_SMOOTH) {
+        stash_off[i] = used[l];
+        used[l] += 8 * nt;
+      }
+    }
+    int reg[2] = {0, 0};
+    for (int l = 0; l <= max_level; ++l) reg[l & 1] = std::max(reg[l & 1], used[l]);
+    const int base0 = red_floats, base1 = red_floats + reg[0];
+    for (int i = 0; i < P.n_instr; ++i) {
+      if (!is_window(P.ins[i])) continue;
+      const int base = (ins_level[i] & 1) ? base1 : base0;
+      scr_off[i] += base;
+      if (stash_off[i] >= 0) stash_off[i] += base;
+    }
+    smem_floats = red_floats + reg[0] + reg[1];
+  }
+
+  // expression of operand j of instruction `in` at sample i
+  std::string operand(const TInstr& in, int j, const char* idx) const {
+    char buf[96];
+    const bool neg = (in.negmask >> j) & 1;
+    if (neg) snprintf(buf, sizeof(buf), "negate<SEM>(v%d[%s])", (int)in.src[j], idx);
+    else snprintf(buf, sizeof(buf), "v%d[%s]", (int)in.src[j], idx);
+    return buf;
+  }
+
+  void emit_predicates() {
+    o.line("// ---- predicates: rows -> registers (api.py:142-143)");
+    for (int q = 0; q < P.n_preds; ++q) o.line("V v%d[8];", (int)P.preds[q].dst);
+    o.line("{");
+    o.indent++;
+    if (D <= 8) {
+      o.line("float r[8][D];");
+      o.line("load_rows<D>(c, signal, g.T, r);");
+    }
+    for (int q = 0; q < P.n_preds; ++q) {
+      const TPred& pr = P.preds[q];
+      if (D > 8) {
+        for (int k = 0; k < pr.n_terms; ++k) {
+          o.line("float x%d_%d[8];", q, k);
+          o.line("load_channel(c, signal, g.T, D, %d, x%d_%d);", (int)pr.ch[k], q, k);
+        }
+      }
+      o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) {");
+      o.indent++;
+      auto term = [&](int k) {
+        char b[64];
+        if (D <= 8) snprintf(b, sizeof(b), "r[i][%d]", (int)pr.ch[k]);
+        else snprintf(b, sizeof(b), "x%d_%d[i]", q, k);
+        return std::string(b);
+      };
+      const bool f64 = P.sem == SEM_CLASSIC && pr.f64;
+      if (f64) {
+        // same operations and order as the reference's float64 evaluation, one final rounding
+        o.line("double a = 0.0;");
+        for (int k = 0; k < pr.n_terms; ++k)
+          o.line("a = fma((double)P.preds[%d].coeff[%d], (double)%s, a);", q, k, term(k).c_str());
+        o.line("const float acc = (float)(a + (double)P.preds[%d].bias);", q);
+      } else {
+        o.line("float acc = 0.f;");
+        for (int k = 0; k < pr.n_terms; ++k) o.line("acc = fmaf(P.preds[%d].coeff[%d], %s, acc);", q, k, term(k).c_str());
+        o.line("acc += P.preds[%d].bias;", q);
+      }
+      if (P.sem == SEM_CUMULATIVE) o.line("v%d[i] = V{{fmaxf(0.f, acc), fminf(0.f, acc)}};  // cumulative.py:29-30", (int)pr.dst);
+      else o.line("v%d[i] = V{{acc}};", (int)pr.dst);
+      o.indent--;
+      o.line("}");
+    }
+    o.indent--;
+    o.line("}");
+    if (P.sem == SEM_SMOOTH) {
+      o.line("// value range of every predicate over the tile: the windows shift their exponentials by it");
+      o.line("float bm[%d];", 2 * P.n_preds);
+      for (int q = 0; q < P.n_preds; ++q) o.line("minmax8(c, v%d, bm[%d], bm[%d]);", (int)P.preds[q].dst, 2 * q, 2 * q + 1);
+      o.line("block_max<NT, %d>(c, red, bm);", 2 * P.n_preds);
+      for (int q = 0; q < P.n_preds; ++q)
+        o.line("const float lo%d = -bm[%d], hi%d = bm[%d];", (int)P.preds[q].dst, 2 * q, (int)P.preds[q].dst, 2 * q + 1);
+    }
+  }
+
+  void win_decl(int i) {
+    const TInstr& in = P.ins[i];
+    const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
+    o.line("using R%d = Red<SEM, %s>;", i, mode_name(in.mode));
+    o.line("using W%d = WinOp<R%d, %d, %d, NT>;", i, i, a, b);
+    o.line("static_assert(W%d::FLOATS == %d, \"host / device scratch layout mismatch\");", i, win_floats(aw(), a, b, nt));
+  }
+
+  void win_phase1(int i) {
+    const TInstr& in = P.ins[i];
+    const bool neg = in.negmask & 1;
+    const int s = in.src[0];
+    o.line("// window %d, phase 1: lift, chunk scans -> shared", i);
+    win_decl(i);
+    o.line("R%d::A x%d[8], sf%d[8], pf%d[8];", i, i, i, i);
+    o.line("RP rp%d = rp;", i);
+    if (P.sem == SEM_SMOOTH) {
+      if (neg) o.line("const float olo%d = -hi%d, ohi%d = -lo%d;", i, s, i, s);
+      else o.line("const float olo%d = lo%d, ohi%d = hi%d;", i, s, i, s);
+      o.line("rp%d.shift = smooth_shift_of<%s>(rp, olo%d, ohi%d);", i, mode_name(in.mode), i, i);
+    }
+    o.line("{");
+    o.indent++;
+    o.line("V t[8];");
+    o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) t[i] = %s;", operand(in, 0, "i").c_str());
+    o.line("lift8<R%d, VW>(c, rp%d, t, x%d);", i, i, i);
+    if (P.sem == SEM_SMOOTH) o.line("stash8<VW>(smem + %d, c.tid, t, 0);", stash_off[i]);
+    o.line("W%d::phase1(smem + %d, c.tid, x%d, sf%d, pf%d);", i, scr_off[i], i, i, i);
+    o.indent--;
+    o.line("}");
+  }
+
+  void win_phase2(int i) {
+    const TInstr& in = P.ins[i];
+    const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
+    o.line("// window %d, phase 2: combine -> value", i);
+    o.line("V v%d[8];", (int)in.dst);
+    o.line("{");
+    o.indent++;
+    o.line("R%d::A acc[8];", i);
+    o.line("W%d::phase2(smem + %d, c.tid, x%d, sf%d, pf%d, acc);", i, scr_off[i], i, i, i);
+    o.line("fin8<R%d, %d, %d, VW>(c, rp%d, acc, v%d);", i, a, b, i, (int)in.dst);
+    if (P.sem == SEM_SMOOTH)
+      o.line("smooth_fix8<%s, %d, %d, NT>(c, rp%d, smem + %d, acc, v%d);", mode_name(in.mode), a, b, i, stash_off[i], (int)in.dst);
+    o.indent--;
+    o.line("}");
+    if (P.sem == SEM_SMOOTH) {
+      o.line("float lo%d, hi%d;", (int)in.dst, (int)in.dst);
+      o.line("smooth_bounds<%s>(rp, olo%d, ohi%d, %d.f, lo%d, hi%d);", mode_name(in.mode), i, i, b - a + 1, (int)in.dst, (int)in.dst);
+    }
+  }
+
+  void nary(int i) {
+    const TInstr& in = P.ins[i];
+    const int n = in.nsrc;
+    o.line("// n-ary %s (%d operands)", in.mode == MODE_AND ? "And" : "Or", n);
+    o.line("V v%d[8];", (int)in.dst);
+    o.line("{");
+    o.indent++;
+    std::string w = "const float w[" + std::to_string(n) + "] = {";
+    for (int j = 0; j < n; ++j) {
+      char b[64];
+      snprintf(b, sizeof(b), "%sP.ins[%d].w[%d]", j ? ", " : "", i, j);
+      w += b;
+    }
+    o.line("%s};", w.c_str());
+    o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) {");
+    o.indent++;
+    std::string a = "const V a[" + std::to_string(n) + "] = {";
+    for (int j = 0; j < n; ++j) a += (j ? ", " : "") + operand(in, j, "i");
+    o.line("%s};", a.c_str());
+    o.line("v%d[i] = nary1<SEM, %s, %d>(rp, a, w, P.ins[%d].sw);", (int)in.dst, mode_name(in.mode), n, i);
+    o.indent--;
+    o.line("}");
+    o.indent--;
+    o.line("}");
+    if (P.sem == SEM_SMOOTH) {
+      // min / max over the operands' ranges (tile_eval.h: op_nary)
+      const char* f = in.mode == MODE_AND ? "fminf" : "fmaxf";
+      std::string lo, hi;
+      for (int j = 0; j < n; ++j) {
+        const bool neg = (in.negmask >> j) & 1;
+        char l[32], h[32];
+        snprintf(l, sizeof(l), neg ? "-hi%d" : "lo%d", (int)in.src[j]);
+        snprintf(h, sizeof(h), neg ? "-lo%d" : "hi%d", (int)in.src[j]);
+        lo = j ? std::string(f) + "(" + lo + ", " + l + ")" : std::string(l);
+        hi = j ? std::string(f) + "(" + hi + ", " + h + ")" : std::string(h);
+      }
+      o.line("float lo%d, hi%d;", (int)in.dst, (int)in.dst);
+      o.line("smooth_bounds<%s>(rp, %s, %s, %d.f, lo%d, hi%d);", mode_name(in.mode), lo.c_str(), hi.c_str(), n, (int)in.dst, (int)in.dst);
+    }
+  }
+
+  std::string forward() {
+    plan();
+    o.indent = 0;
+    o.line("// generated by pystl_b200/csrc/codegen.cpp -- forward kernel of one formula (fused tier)");
+    o.line("#include \"fused_rt.cuh\"");
+    o.line("using namespace pystl;");
+    o.line("using namespace pystl::fused;");
+    o.line("constexpr int NT = %d, D = %d, SEM = %s, VW = Tr<SEM>::VW;", nt, D, sem_name(P.sem));
+    o.line("typedef Vec<VW> V;");
+    o.line("PF_KERNEL(NT, %d) pystl_fused(const PF_GRID_CONSTANT TileProgram P, const PF_GRID_CONSTANT TileGeom g,", minb);
+    o.line("    const float* __restrict__ signal, float* __restrict__ out, double* __restrict__ mean_acc) {");
+    o.indent = 1;
+    o.line("PF_DYN_SMEM(smem);");
+    o.line("const TC c = tile_begin<NT>(P, g, smem);");
+    o.line("const RP rp = c.rp;");
+    o.line("float* red = smem;");
+    o.line("(void)red; (void)rp;");
+    emit_predicates();
+    for (int st = 0; st < n_stages; ++st) {
+      o.line("// ================= stage %d", st);
+      for (int i = 0; i < P.n_instr; ++i) {
+        const TInstr& in = P.ins[i];
+        if (ins_level[i] != st) continue;
+        if (is_window(in)) win_phase2(i);
+        else nary(i);
+      }
+      bool any = false;
+      for (int i = 0; i < P.n_instr; ++i)
+        if (is_window(P.ins[i]) && ins_level[i] == st + 1) {
+          win_phase1(i);
+          any = true;
+        }
+      if (any) o.line("simt::sync();");
+    }
+    o.line("store_root<SEM, NT, %s>(c, g.T, v%d, out, mean_acc, red);", P.root_neg ? "true" : "false", (int)P.root);
+    o.indent = 0;
+    o.line("}");
+    return o.s;
+  }
+};
+
+}  // namespace
+
+// Tile geometry.  A CTA of nt threads stages 8*nt samples; forward tiles carry the formula's
+// look-ahead H as a right halo, backward tiles carry it on both sides.  Every multiple of 32
+// threads is a candidate: the cost is the number of samples staged per trace (halo + the idle
+// tail of the last tile), with a mild preference for CTAs of at most 256 threads (more resident
+// CTAs per SM hide each other's barriers).
+int fused_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_nt, bool backward, TileGeom* g, char* msg,
+                   int msg_len) {
+  auto fail = [&](int code, const char* what) {
+    if (msg && msg_len > 0) snprintf(msg, msg_len, "%s", what);
+    return code;
+  };
+  if (B < 0 || T < 0 || D < 1) return fail(PYSTL_E_INVALID, "bad shape");
+  if (lw.lookahead < 0) return fail(PYSTL_E_UNSUPPORTED, "open-ended look-ahead");
+  const TileProgram& P = lw.prog;
+  for (int q = 0; q < P.n_preds; ++q)
+    for (int k = 0; k < P.preds[q].n_terms; ++k)
+      if (P.preds[q].ch[k] < 0 || P.preds[q].ch[k] >= D) return fail(PYSTL_E_INVALID, "predicate reads a channel the signal does not have");
+  const int H = lw.lookahead;
+  const int hh = backward ? roundup(H, 8) : 0;
+  const int64_t Tn = std::max<int64_t>(T, 1);
+  auto build = [&](int nt, TileGeom* out) -> bool {
+    TileGeom t{};
+    t.B = B;
+    t.T = T;
+    t.D = D;
+    t.nt = nt;
+    t.lext = 8 * nt;
+    t.vw = P.sem == SEM_CUMULATIVE ? 2 : 1;
+    t.bwd = backward ? 1 : 0;
+    t.hh = hh;
+    t.n_slots = P.n_slots;
+    if (Tn <= t.lext) {
+      t.lout = t.lext;
+      t.n_tiles = 1;
+    } else {
+      t.lout = backward ? t.lext - 2 * hh : ((t.lext - H) / 8) * 8;
+      if (t.lout < 8 || t.lout * 4 < t.lext) return false;
+      t.n_tiles = (int)((Tn + t.lout - 1) / t.lout);
+    }
+    *out = t;
+    return true;
+  };
+  if (force_nt > 0) {
+    if (force_nt % 32 != 0 || force_nt > kMaxThreads) return fail(PYSTL_E_UNSUPPORTED, "forced CTA size is not a multiple of 32");
+    if (!build(force_nt, g)) return fail(PYSTL_E_UNSUPPORTED, "forced CTA size does not fit the formula's look-ahead");
+    return PYSTL_OK;
+  }
+  double best = 0;
+  bool have = false;
+  for (int nt = 64; nt <= kMaxThreads; nt += 32) {
+    if (nt > 512 && nt % 128 != 0) continue;
+    TileGeom t{};
+    if (!build(nt, &t)) continue;
+    double cost = (double)t.n_tiles * t.lext;
+    if (nt > 256) cost *= 1.0 + 0.12 * (nt - 256) / 256.0;
+    if (nt < 128) cost *= 1.05;
+    if (!have || cost < best * 0.995) {
+      have = true;
+      best = cost;
+      *g = t;
+    }
+  }
+  if (!have) return fail(PYSTL_E_UNSUPPORTED, "look-ahead does not fit a tile");
+  return PYSTL_OK;
+}
+
+int fused_generate(const Lowered& lw, int D, int nt, int minb, bool backward, FusedSource* out, char* msg, int msg_len) {
+  Gen g(lw, D, nt, minb);
+  std::string why;
+  if (backward) why = "the backward pass runs on the interpreter tier";
+  if (!why.empty() || !g.supported(&why)) {
+    if (msg && msg_len > 0) snprintf(msg, msg_len, "%s", why.c_str());
+    return PYSTL_E_UNSUPPORTED;
+  }
+  out->source = g.forward();
+  out->smem_floats = g.smem_floats;
+  out->nt = nt;
+  out->minb = minb;
+  return PYSTL_OK;
+}
+
+}  // namespace pystl

@@ -1,0 +1,589 @@
+// Runtime of the FUSED tier: register-resident tile kernels, specialised per formula.
+//
+// The interpreter tier (tile_eval.h) runs a lowered formula instruction by instruction and keeps
+// every node value in a shared-memory plane.  The fused tier runs the same lowered program as
+// straight-line code: codegen.cpp emits a short kernel body per (formula, CTA size, D) that calls
+// the templates below with every window offset, operand sign and plane offset as a compile-time
+// constant, so that
+//   * a thread keeps the 8 consecutive samples it owns of EVERY node value in registers for the
+//     whole kernel -- predicates, And / Or / Not never touch shared memory;
+//   * only what other threads must see goes through shared memory: the chunk suffix / prefix
+//     scans and chunk aggregates of the van Herk / Gil-Werman windows (api.py:215-253);
+//   * windows of the same nesting depth share one barrier;
+//   * chunk geometry (which aggregates lie inside the window of output i, where the partial
+//     chunks start) folds to constants: no selects, no index arithmetic in the inner loops.
+// The glue is compiled at run time by NVRTC (jit.cpp) or ahead of time into the cubin cache.
+//
+// Reference semantics restated: see the header of tile_eval.h (the reducers Red<SEM, MODE> are
+// shared with the interpreter tier).
+//
+// This header is written in plain SIMT style.  The CPU test tier compiles it with g++ against
+// tests/emu/simt_host.h (fibers); nothing in the product loads that build.
+#pragma once
+#include "tile_eval.h"
+
+#if defined(__CUDACC__)
+#define PF_DEV __device__ __forceinline__
+#define PF_KERNEL(NT, MINB) extern "C" __global__ void __launch_bounds__(NT, MINB)
+#define PF_GRID_CONSTANT __grid_constant__
+#define PF_DYN_SMEM(name) extern __shared__ __align__(128) float name[]
+namespace simt {
+PF_DEV int tid() { return (int)threadIdx.x; }
+PF_DEV int bid() { return (int)blockIdx.x; }
+PF_DEV void sync() { __syncthreads(); }
+PF_DEV float shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+PF_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+PF_DEV int redux_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }
+PF_DEV void atomic_add(float* p, float v) { atomicAdd(p, v); }
+PF_DEV void atomic_add(double* p, double v) { atomicAdd(p, v); }
+}  // namespace simt
+#else
+#include "simt_host.h"
+#define PF_DEV inline
+#define PF_KERNEL(NT, MINB) extern "C" void
+#define PF_GRID_CONSTANT
+#define PF_DYN_SMEM(name) float* name = simt::dyn_smem()
+#endif
+
+namespace pystl {
+namespace fused {
+
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------ tile context (registers)
+struct TC {
+  float* smem;
+  int tid;
+  int p0;       // first tile position this thread owns (8 * tid)
+  int nlive;    // tile positions that exist in the trace: min(T - origin, lext)
+  int last_ok;  // last tile position whose output does not raise (api.py:218-221); < 0: none
+  int p_lo;     // tile positions [p_lo, p_hi) are the ones this CTA writes to HBM
+  int p_hi;
+  long long b;       // trace
+  long long origin;  // trace time of tile position 0
+  RP rp;
+};
+
+template <int NT>
+PF_DEV TC tile_begin(const TileProgram& P, const TileGeom& g, float* smem) {
+  TC c;
+  c.smem = smem;
+  c.tid = simt::tid();
+  c.p0 = 8 * c.tid;
+  const unsigned tile = (unsigned)simt::bid();
+  const unsigned bu = tile / (unsigned)g.n_tiles;
+  const int j = (int)(tile - bu * (unsigned)g.n_tiles);
+  c.b = (long long)bu;
+  const long long e0 = (long long)j * g.lout;
+  c.origin = e0 > (long long)g.hh ? e0 - g.hh : 0;  // backward tiles carry a left halo
+  const long long live = g.T - c.origin;
+  c.nlive = live < (long long)(8 * NT) ? (int)live : 8 * NT;
+  const long long ok = P.raises_always ? -1 : g.T - 1 - P.start_slack - c.origin;
+  c.last_ok = ok > (long long)(1 << 30) ? (1 << 30) : (ok < -1 ? -1 : (int)ok);
+  c.p_lo = (int)(e0 - c.origin);
+  c.p_hi = c.p_lo + g.lout < c.nlive ? c.p_lo + g.lout : c.nlive;
+  c.rp = P.rp;
+  return c;
+}
+
+PF_DEV bool own_all_live(const TC& c) { return c.p0 + 8 <= c.nlive; }
+
+// ------------------------------------------------------------------ signal rows -> registers
+// The thread's 8 rows are 8*D consecutive floats of the trace: 128-bit loads when they all
+// exist and the address is 16-byte aligned, guarded scalar loads otherwise (rows past the
+// horizon read as 0 and are never consumed: the lifts replace them by the identity).
+template <int D>
+PF_DEV void load_rows(const TC& c, const float* __restrict__ signal, long long T, float (&r)[8][D]) {
+  const float* src = signal + ((c.b * T + c.origin + c.p0) * (long long)D);
+  if (own_all_live(c) && ((u64)src & 15ull) == 0ull) {
+    const F4* s4 = reinterpret_cast<const F4*>(src);
+#pragma unroll
+    for (int k = 0; k < 2 * D; ++k) {
+#if defined(__CUDA_ARCH__)
+      const float4 q = __ldg(reinterpret_cast<const float4*>(s4) + k);
+      const float t[4] = {q.x, q.y, q.z, q.w};
+#else
+      const F4 q = s4[k];
+      const float* t = q.v;
+#endif
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[(4 * k + e) / D][(4 * k + e) % D] = t[e];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = c.p0 + i < c.nlive;
+#pragma unroll
+      for (int d = 0; d < D; ++d) r[i][d] = ok ? src[i * D + d] : 0.f;
+    }
+  }
+}
+// one channel of a wide signal (D > 8): strided scalar loads
+PF_DEV void load_channel(const TC& c, const float* __restrict__ signal, long long T, int D, int ch, float (&x)[8]) {
+  const float* src = signal + ((c.b * T + c.origin + c.p0) * (long long)D) + ch;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = (c.p0 + i < c.nlive) ? src[(long long)i * D] : 0.f;
+}
+
+// ------------------------------------------------------------------ block reductions
+PF_DEV float warp_max(float v) {  // one REDUX: floats mapped to integers of the same order
+  int k = f2i(v);
+  k = k >= 0 ? k : k ^ 0x7fffffff;
+  k = simt::redux_max_i(k);
+  k = k >= 0 ? k : k ^ 0x7fffffff;
+  return i2f(k);
+}
+
+// in: per-thread maxima m[0..N) ; out: block-wide maxima in every thread.  red: N * NT/32 floats.
+template <int NT, int N>
+PF_DEV void block_max(const TC& c, float* red, float (&m)[N]) {
+  constexpr int NW = NT / 32;
+  const int lane = c.tid & 31, warp = c.tid >> 5;
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const float v = warp_max(m[q]);
+    if (lane == 0) red[q * NW + warp] = v;
+  }
+  simt::sync();
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    float a = red[q * NW];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) a = fmaxf(a, red[q * NW + w]);
+    m[q] = a;
+  }
+}
+
+// (-min, max) of the thread's live samples of a value
+PF_DEV void minmax8(const TC& c, const Vec<1> (&v)[8], float& nlo, float& hi) {
+  nlo = -f_inf();
+  hi = -f_inf();
+  if (own_all_live(c)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      nlo = fmaxf(nlo, -v[i].x[0]);
+      hi = fmaxf(hi, v[i].x[0]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c.p0 + i < c.nlive) {
+        nlo = fmaxf(nlo, -v[i].x[0]);
+        hi = fmaxf(hi, v[i].x[0]);
+      }
+  }
+}
+
+// smooth: range of softmin / softmax over n terms of operands within [lo, hi] (tile_eval.h)
+template <int MODE>
+PF_DEV void smooth_bounds(const RP& rp, float lo, float hi, float n, float& olo, float& ohi) {
+  const float pad = rp.invk * fast_lg2(n > 1.f ? n : 1.f) + 1e-6f * (fabsf(lo) + fabsf(hi));
+  olo = MODE == MODE_AND ? lo - pad : lo;
+  ohi = MODE == MODE_AND ? hi : hi + pad;
+}
+// block-wide upper bound of the exponent of an operand within [lo, hi]
+template <int MODE>
+PF_DEV float smooth_shift_of(const RP& rp, float lo, float hi) {
+  return (MODE == MODE_AND ? -lo : hi) * rp.k;
+}
+
+// ------------------------------------------------------------------ static chunk geometry
+template <int X>
+struct FloorDiv {
+  static constexpr int q8 = X >= 0 ? X / 8 : -((-X + 7) / 8);
+  static constexpr int r8 = X - 8 * q8;
+  static constexpr int q4 = X >= 0 ? X / 4 : -((-X + 3) / 4);
+  static constexpr int r4 = X - 4 * q4;
+};
+
+// 8 consecutive logical samples starting at 8 * chunk + OFF of a swizzled plane
+template <int OFF>
+PF_DEV void load_run_s(const float* plane, int chunk, float (&v)[8]) {
+  const F4* P4 = reinterpret_cast<const F4*>(plane);
+  constexpr int q4 = FloorDiv<OFF>::q4, r4 = FloorDiv<OFF>::r4;
+  const int f0 = 2 * chunk + q4;
+  if constexpr (r4 == 0) {
+    const F4 a = P4[pf4(f0)], b = P4[pf4(f0 + 1)];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = a.v[k];
+      v[4 + k] = b.v[k];
+    }
+  } else {
+    const F4 a = P4[pf4(f0)], b = P4[pf4(f0 + 1)], d = P4[pf4(f0 + 2)];
+    const float t[12] = {a.v[0], a.v[1], a.v[2], a.v[3], b.v[0], b.v[1], b.v[2], b.v[3], d.v[0], d.v[1], d.v[2], d.v[3]};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = t[i + r4];
+  }
+}
+
+template <int AW>
+PF_DEV void split_words(const Vec<AW> (&a)[8], int w, float (&t)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = a[i].x[w];
+}
+
+// ------------------------------------------------------------------ sliding window
+// out[p] = (+)_{k in [WA, WB]} x[p + k] over the tile for an associative (+) = R::comb with
+// identity R::ident(); operands are combined in time order.  WA <= WB, any signs (the adjoint
+// windows of the backward pass look back).  phase1 / phase2 are separated by ONE barrier, which
+// the generated kernel shares between all windows of the same depth.
+//
+//   W <= 8  direct: x is staged; every output folds its W samples with a doubling table
+//   W >= 9  van Herk / Gil-Werman over the 8-sample chunks the threads own:
+//           out[p] = SUF[p+WA] (+) AGG[chunks strictly inside] (+) PRE[p+WB]
+//           (own registers replace SUF when WA == 0 and PRE when WB == 0)
+template <class R, int WA, int WB, int NT>
+struct WinOp {
+  using A = typename R::A;
+  static constexpr int AW = (int)(sizeof(A) / sizeof(float));
+  static constexpr int LEXT = 8 * NT;
+  static constexpr int W = WB - WA + 1;
+  static constexpr bool VH = W > 8;
+  static constexpr int GL = WA < 0 ? ((-WA + 7) / 8) * 8 : 0;
+  static constexpr int GR = (WB > 0 ? ((WB + 7) / 8) * 8 : 0) + 8;
+  static constexpr int PLANE = GL + LEXT + GR;
+  static constexpr int NCHK = PLANE / 8;
+  static constexpr bool USE_SUF = VH ? (WA != 0) : true;  // direct: plane 0 holds x itself
+  static constexpr bool USE_PRE = VH && (WB != 0);
+  static constexpr int NPL = (USE_SUF ? 1 : 0) + (USE_PRE ? 1 : 0);
+  static constexpr int AGGN = VH ? ((NCHK + 3) / 4) * 4 : 0;
+  static constexpr int FLOATS = AW * (NPL * PLANE + AGGN);
+
+  PF_DEV static float* plane0(float* scr, int w) { return scr + (w * NPL) * PLANE + GL; }
+  PF_DEV static float* plane1(float* scr, int w) { return scr + (w * NPL + (USE_SUF ? 1 : 0)) * PLANE + GL; }
+  PF_DEV static float* agg(float* scr, int w) { return scr + AW * NPL * PLANE + w * AGGN + GL / 8; }
+
+  // identity into the guard bands (chunks [-GL/8, 0) and [NT, NT + GR/8))
+  PF_DEV static void fill_guards(float* scr, int tid) {
+    const A id = R::ident();
+    constexpr int NG = (GL + GR) / 8;
+    for (int g = tid; g < NG; g += NT) {
+      const int ch = g < GR / 8 ? NT + g : -(g - GR / 8) - 1;
+#pragma unroll
+      for (int w = 0; w < AW; ++w) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = id.x[w];
+        if constexpr (USE_SUF) store8(plane0(scr, w), ch, t);
+        if constexpr (USE_PRE) store8(plane1(scr, w), ch, t);
+        if constexpr (VH) agg(scr, w)[ch] = id.x[w];
+      }
+    }
+  }
+
+  // x: the thread's lifted samples.  suf / pre: its chunk scans, kept in registers for phase2.
+  PF_DEV static void phase1(float* scr, int tid, const A (&x)[8], A (&suf)[8], A (&pre)[8]) {
+    if constexpr (!VH) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) suf[i] = pre[i] = x[i];
+#pragma unroll
+      for (int w = 0; w < AW; ++w) {
+        float t[8];
+        split_words<AW>(x, w, t);
+        store8(plane0(scr, w), tid, t);
+      }
+    } else {
+      pre[0] = x[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) pre[i] = R::comb(pre[i - 1], x[i]);
+      suf[7] = x[7];
+#pragma unroll
+      for (int i = 6; i >= 0; --i) suf[i] = R::comb(x[i], suf[i + 1]);
+#pragma unroll
+      for (int w = 0; w < AW; ++w) {
+        float t[8];
+        if constexpr (USE_SUF) {
+          split_words<AW>(suf, w, t);
+          store8(plane0(scr, w), tid, t);
+        }
+        if constexpr (USE_PRE) {
+          split_words<AW>(pre, w, t);
+          store8(plane1(scr, w), tid, t);
+        }
+        agg(scr, w)[tid] = pre[7].x[w];
+      }
+    }
+    fill_guards(scr, tid);
+  }
+
+  PF_DEV static A load_agg(const float* scr, int ch) {
+    A r;
+#pragma unroll
+    for (int w = 0; w < AW; ++w) r.x[w] = agg(const_cast<float*>(scr), w)[ch];
+    return r;
+  }
+
+  // fold LEN consecutive entries of e[] starting at S with the doubling tables y2 / y4 / y8
+  template <int S, int LEN, int N>
+  PF_DEV static A fold(const A (&e)[N], const A (&y2)[N], const A (&y4)[N], const A (&y8)[N]) {
+    if constexpr (LEN == 1) return e[S];
+    else if constexpr (LEN == 2) return y2[S];
+    else if constexpr (LEN == 4) return y4[S];
+    else if constexpr (LEN == 8) return y8[S];
+    else if constexpr (LEN > 4) return R::comb(y4[S], fold<S + 4, LEN - 4, N>(e, y2, y4, y8));
+    else return R::comb(y2[S], e[S + 2]);  // LEN == 3
+  }
+
+  PF_DEV static void phase2(float* scr, int tid, const A (&x)[8], const A (&suf)[8], const A (&pre)[8], A (&acc)[8]) {
+    if constexpr (!VH) {
+      // e[j] = x[p0 + WA + j], j in [0, W + 7): own samples from registers, the rest from the plane
+      constexpr int N = W + 7;
+      A e[N], y2[N], y4[N], y8[N];
+      constexpr int f_lo = FloorDiv<WA>::q4, f_hi = FloorDiv<WB + 7>::q4;
+#pragma unroll
+      for (int f = f_lo; f <= f_hi; ++f) {
+        if (f == 0 || f == 1) continue;  // own chunk
+#pragma unroll
+        for (int w = 0; w < AW; ++w) {
+          const F4 q = reinterpret_cast<const F4*>(plane0(scr, w))[pf4(2 * tid + f)];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = 4 * f + k - WA;
+            if (j >= 0 && j < N) e[j].x[w] = q.v[k];
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = i - WA;
+        if (j >= 0 && j < N) e[j] = x[i];
+      }
+      if constexpr (W >= 2) {
+#pragma unroll
+        for (int j = 0; j + 1 < N; ++j) y2[j] = R::comb(e[j], e[j + 1]);
+      }
+      if constexpr (W >= 4) {
+#pragma unroll
+        for (int j = 0; j + 3 < N; ++j) y4[j] = R::comb(y2[j], y2[j + 2]);
+      }
+      if constexpr (W >= 8) {
+#pragma unroll
+        for (int j = 0; j + 7 < N; ++j) y8[j] = R::comb(y4[j], y4[j + 4]);
+      }
+      fold_all(e, y2, y4, y8, acc);
+      return;
+    } else {
+      constexpr int qa = FloorDiv<WA>::q8, ra = FloorDiv<WA>::r8, qb = FloorDiv<WB>::q8, rb = FloorDiv<WB>::r8;
+      A sv[8], ev[8];
+      if constexpr (WA == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sv[i] = suf[i];
+      } else {
+#pragma unroll
+        for (int w = 0; w < AW; ++w) {
+          float t[8];
+          load_run_s<WA>(plane0(scr, w), tid, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sv[i].x[w] = t[i];
+        }
+      }
+      if constexpr (WB == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ev[i] = pre[i];
+      } else {
+#pragma unroll
+        for (int w = 0; w < AW; ++w) {
+          float t[8];
+          load_run_s<WB>(plane1(scr, w), tid, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ev[i].x[w] = t[i];
+        }
+      }
+      // whole chunks strictly between the two partial ones: chunk tid + k for k in [lo_i, hi_i],
+      // lo_i = qa + ((ra + i) >> 3) + 1, hi_i = qb + ((rb + i) >> 3) - 1.  All i share the core
+      // [qa + 2, qb - 1]; chunk qa + 1 and chunk qb join it for some i only.
+      constexpr int NCORE = qb - qa - 2;
+      A core = R::ident();
+      if constexpr (NCORE > 0) {
+        core = load_agg(scr, tid + qa + 2);
+#pragma unroll
+        for (int k = 1; k < NCORE; ++k) core = R::comb(core, load_agg(scr, tid + qa + 2 + k));
+      }
+      constexpr bool any_l = (ra == 0) ? (qa + 1 <= qb - 1 || (qa + 1 <= qb && rb > 0)) : true;
+      (void)any_l;
+      const A agl = load_agg(scr, tid + qa + 1);
+      const A agr = load_agg(scr, tid + qb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int lo = qa + ((ra + i) >> 3) + 1, hi = qb + ((rb + i) >> 3) - 1;
+        const bool inc_l = (lo == qa + 1) && (qa + 1 <= hi);
+        const bool inc_r = (hi == qb) && (lo <= qb) && (qb != qa + 1 || !inc_l);
+        A a = sv[i];
+        if (inc_l) a = R::comb(a, agl);
+        if (NCORE > 0) a = R::comb(a, core);
+        if (inc_r) a = R::comb(a, agr);
+        acc[i] = R::comb(a, ev[i]);
+      }
+    }
+  }
+
+  template <int N>
+  PF_DEV static void fold_all(const A (&e)[N], const A (&y2)[N], const A (&y4)[N], const A (&y8)[N], A (&acc)[8]) {
+    acc[0] = fold<0, W, N>(e, y2, y4, y8);
+    acc[1] = fold<1, W, N>(e, y2, y4, y8);
+    acc[2] = fold<2, W, N>(e, y2, y4, y8);
+    acc[3] = fold<3, W, N>(e, y2, y4, y8);
+    acc[4] = fold<4, W, N>(e, y2, y4, y8);
+    acc[5] = fold<5, W, N>(e, y2, y4, y8);
+    acc[6] = fold<6, W, N>(e, y2, y4, y8);
+    acc[7] = fold<7, W, N>(e, y2, y4, y8);
+  }
+};
+
+// ------------------------------------------------------------------ lift / finish
+// the thread's operand samples -> accumulators; samples past the horizon become the identity
+template <class R, int VW>
+PF_DEV void lift8(const TC& c, const RP& rp, const Vec<VW> (&v)[8], typename R::A (&x)[8]) {
+  if (own_all_live(c)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = R::lift(v[i], rp, 1.f);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = (c.p0 + i < c.nlive) ? R::lift(v[i], rp, 1.f) : R::ident();
+  }
+}
+
+// accumulators -> values of the forward window [t + FA, min(t + FB, T - 1)] (api.py:49-54): the
+// normaliser is the clipped sample count.  Empty windows (the reference raises) are masked at
+// the root (start_slack), so any finite count will do for them.
+template <class R, int FA, int FB, int VW>
+PF_DEV void fin8(const TC& c, const RP& rp, const typename R::A (&acc)[8], Vec<VW> (&o)[8]) {
+  if (c.p0 + 7 + FB <= c.nlive - 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = R::fin(acc[i], (float)(FB - FA + 1), rp);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int hi = c.p0 + i + FB;
+      if (hi > c.nlive - 1) hi = c.nlive - 1;
+      const int n = hi - (c.p0 + i + FA) + 1;
+      o[i] = R::fin(acc[i], (float)(n > 0 ? n : 1), rp);
+    }
+  }
+}
+
+// smooth only: outputs whose block-shifted sum lost its precision to underflow are recomputed
+// exactly from the staged operand (rare: needs a dynamic range above 2^100 inside one tile)
+template <int MODE, int FA, int FB, int NT>
+PF_DEV void smooth_fix8(const TC& c, const RP& rp, const float* vplane, const Vec<1> (&acc)[8], Vec<1> (&o)[8]) {
+  using R = Red<SEM_SMOOTH, MODE>;
+  float m = acc[0].x[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fminf(m, acc[i].x[0]);
+  if (m >= kSmoothTiny) return;
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    float a_i = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j == i) a_i = acc[j].x[0];
+    if (a_i >= kSmoothTiny) continue;
+    int lo = c.p0 + i + FA, hi = c.p0 + i + FB;
+    if (hi > c.nlive - 1) hi = c.nlive - 1;
+    if (hi > 8 * NT - 1) hi = 8 * NT - 1;
+    float res = f_nan();
+    if (lo <= hi) {
+      float mx = -f_inf();
+      for (int q = lo; q <= hi; ++q) mx = fmaxf(mx, R::expo(Vec<1>{{vplane[pidx(q)]}}, rp));
+      float s = 0.f;
+      for (int q = lo; q <= hi; ++q) s += fast_ex2(R::expo(Vec<1>{{vplane[pidx(q)]}}, rp) - mx);
+      RP r2 = rp;
+      r2.shift = mx;
+      res = R::fin(Vec<1>{{s}}, 1.f, r2).x[0];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j == i) o[j].x[0] = res;
+  }
+}
+
+template <int VW>
+PF_DEV void stash8(float* plane, int tid, const Vec<VW> (&v)[8], int w) {
+  float t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = v[i].x[w];
+  store8(plane, tid, t);
+}
+
+// ------------------------------------------------------------------ n-ary And / Or of one sample
+template <int SEM, int MODE, int N>
+PF_DEV Vec<Tr<SEM>::VW> nary1(const RP& rp0, const Vec<Tr<SEM>::VW> (&a)[N], const float (&w)[N], float sw) {
+  using R = Red<SEM, MODE>;
+  if constexpr (SEM == SEM_SMOOTH) {
+    // exact max-shifted logsumexp (smooth.py:18-22)
+    float e[N];
+    float m = -f_inf();
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      e[j] = R::expo(a[j], rp0);
+      m = fmaxf(m, e[j]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s += fast_ex2(e[j] - m);
+    RP rp = rp0;
+    rp.shift = m;
+    return R::fin(Vec<1>{{s}}, sw, rp);
+  } else {
+    typename R::A acc = R::lift(a[0], rp0, w[0]);
+#pragma unroll
+    for (int j = 1; j < N; ++j) acc = R::comb(acc, R::lift(a[j], rp0, w[j]));
+    return R::fin(acc, sw, rp0);
+  }
+}
+
+// ------------------------------------------------------------------ root -> HBM (+ fused mean)
+// Writes the tile's outputs [p_lo, p_hi); NaN where the reference raises.  red: NT/32 floats.
+template <int SEM, int NT, bool NEG>
+PF_DEV void store_root(const TC& c, long long T, const Vec<Tr<SEM>::VW> (&v)[8], float* __restrict__ out,
+                       double* __restrict__ mean_acc, float* red) {
+  constexpr int VW = Tr<SEM>::VW;
+  Vec<VW> o[8];
+  float part = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] = NEG ? negate<SEM>(v[i]) : v[i];
+    const int p = c.p0 + i;
+    if (p > c.last_ok) {
+#pragma unroll
+      for (int w = 0; w < VW; ++w) o[i].x[w] = f_nan();
+    } else if (p >= c.p_lo && p < c.p_hi) {
+#pragma unroll
+      for (int w = 0; w < VW; ++w) part += o[i].x[w];
+    }
+  }
+  float* dst = out + (c.b * T + c.origin + c.p0) * (long long)VW;
+  if (c.p0 >= c.p_lo && c.p0 + 8 <= c.p_hi && ((u64)dst & 15ull) == 0ull) {
+    F4* d4 = reinterpret_cast<F4*>(dst);
+    if constexpr (VW == 1) {
+      d4[0] = F4{{o[0].x[0], o[1].x[0], o[2].x[0], o[3].x[0]}};
+      d4[1] = F4{{o[4].x[0], o[5].x[0], o[6].x[0], o[7].x[0]}};
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d4[k] = F4{{o[2 * k].x[0], o[2 * k].x[1], o[2 * k + 1].x[0], o[2 * k + 1].x[1]}};
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c.p0 + i >= c.p_lo && c.p0 + i < c.p_hi) {
+#pragma unroll
+        for (int w = 0; w < VW; ++w) dst[i * VW + w] = o[i].x[w];
+      }
+  }
+  if (mean_acc) {
+    float s = part;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += simt::shfl_xor(s, d);
+    if ((c.tid & 31) == 0) red[c.tid >> 5] = s;
+    simt::sync();
+    if (c.tid == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < NT / 32; ++w) tot += (double)red[w];
+      simt::atomic_add(mean_acc, tot);
+    }
+  }
+}
+
+}  // namespace fused
+}  // namespace pystl

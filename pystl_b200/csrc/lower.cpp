@@ -36,6 +36,7 @@ struct Fail {
 struct Lowerer {
   const pystl_formula_t* f = nullptr;
   bool backward = false;
+  bool ssa = false;  // fused tier: every value keeps its own slot
   Lowered* out = nullptr;
   char* msg = nullptr;
   int msg_len = 0;
@@ -71,7 +72,7 @@ struct Lowerer {
     return s;
   }
   void release(int slot) {
-    if (--slot_refs[slot] == 0 && !backward) free_slots.push_back(slot);  // backward: no reuse
+    if (--slot_refs[slot] == 0 && !backward && !ssa) free_slots.push_back(slot);  // backward / ssa: no reuse
   }
 
   TileProgram& P() { return out->prog; }
@@ -486,6 +487,10 @@ struct Lowerer {
 }  // namespace
 
 int lower_formula(const ::pystl_formula* f, bool backward, Lowered* out, char* msg, int msg_len) {
+  return lower_formula_ex(f, backward, false, out, msg, msg_len);
+}
+
+int lower_formula_ex(const ::pystl_formula* f, bool backward, bool ssa, Lowered* out, char* msg, int msg_len) {
   if (msg && msg_len > 0) msg[0] = 0;
   if (!f || !out) {
     if (msg) snprintf(msg, msg_len, "null formula");
@@ -494,6 +499,7 @@ int lower_formula(const ::pystl_formula* f, bool backward, Lowered* out, char* m
   Lowerer L;
   L.f = reinterpret_cast<const pystl_formula_t*>(f);
   L.backward = backward;
+  L.ssa = ssa;
   L.out = out;
   L.msg = msg;
   L.msg_len = msg_len;

@@ -7,7 +7,19 @@
 // passed to the kernel by value (__grid_constant__), so decoding is a uniform
 // constant-bank read.
 #pragma once
+#if defined(__CUDACC_RTC__)
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#else
 #include <stdint.h>
+#endif
 
 namespace pystl {
 
@@ -136,6 +148,8 @@ namespace pystl {
 // backward: every node keeps its own plane (values are re-read by the adjoint pass) and
 // constructs without a backward kernel are rejected
 int lower_formula(const ::pystl_formula* f, bool backward, Lowered* out, char* msg, int msg_len);
+// ssa: no plane-slot reuse (the fused tier keeps every value in its own registers)
+int lower_formula_ex(const ::pystl_formula* f, bool backward, bool ssa, Lowered* out, char* msg, int msg_len);
 // force_nt > 0 pins the CTA size (tests); 0 = choose
 int plan_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force_nt, bool backward, TileGeom* g, char* msg,
                   int msg_len);

@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "../../include/pystl_b200.h"
+#include "fused_host.h"
 #include "program.h"
 
 namespace pystl {
@@ -50,6 +51,75 @@ static int prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t D, bo
   return plan_geometry(*lw, B, T, D, forced_threads(), backward, g, g_err, sizeof(g_err));
 }
 
+// ---------------------------------------------------------------------- fused tier
+// PYSTL_B200_TIER = auto (default: fused when the formula is supported, else interpreter),
+// interp, or fused (fail instead of falling back; tests)
+enum { TIER_AUTO = 0, TIER_INTERP = 1, TIER_FUSED = 2 };
+static int tier_mode() {
+  const char* e = getenv("PYSTL_B200_TIER");
+  if (!e || !*e) return TIER_AUTO;
+  if (!strcmp(e, "interp")) return TIER_INTERP;
+  if (!strcmp(e, "fused")) return TIER_FUSED;
+  return TIER_AUTO;
+}
+
+// registers per thread the fused kernels are compiled for: min CTAs per SM by CTA size
+static int fused_minb(int nt) {
+  const char* e = getenv("PYSTL_B200_FUSED_MINB");
+  if (e && *e) return atoi(e) > 0 ? atoi(e) : 1;
+  const int target_regs = 96;
+  int minb = 65536 / (nt * target_regs);
+  return minb < 1 ? 1 : (minb > 8 ? 8 : minb);
+}
+
+static int fused_prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t D, bool backward, Lowered* lw, TileGeom* g,
+                         FusedSource* fs) {
+  int rc = lower_formula_ex(reinterpret_cast<const ::pystl_formula*>(f), backward, true, lw, g_err, sizeof(g_err));
+  if (rc) return rc;
+  rc = fused_geometry(*lw, B, T, D, forced_threads(), backward, g, g_err, sizeof(g_err));
+  if (rc) return rc;
+  rc = fused_generate(*lw, D, g->nt, fused_minb(g->nt), backward, fs, g_err, sizeof(g_err));
+  if (rc) return rc;
+  if (fs->smem_floats * 4 > 227 * 1024) return set_err(PYSTL_E_UNSUPPORTED, "fused kernel needs %d bytes of shared memory", fs->smem_floats * 4);
+  g->smem_floats = fs->smem_floats;
+  return PYSTL_OK;
+}
+
+static int fused_launch(const Lowered& lw, const TileGeom& g, const FusedSource& fs, void** args, cudaStream_t stream) {
+  FusedKernel fk;
+  int rc = fused_jit_get(fs, &fk, g_err, sizeof(g_err));
+  if (rc) return rc;
+  const int64_t grid = g.B * g.n_tiles;
+  if (grid > 0x7fffffffLL) return set_err(PYSTL_E_UNSUPPORTED, "grid of %lld tiles exceeds 2^31-1", (long long)grid);
+  cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(fk.kernel), dim3((unsigned)grid), dim3((unsigned)g.nt), args,
+                                   (size_t)fs.smem_floats * 4, stream);
+  if (e != cudaSuccess) return set_err(PYSTL_E_CUDA, "fused kernel launch: %s", cudaGetErrorString(e));
+  (void)lw;
+  return PYSTL_OK;
+}
+
+// Compile the fused kernel of (formula, T, D) into the on-disk cache; needs no GPU.
+// Returns PYSTL_E_UNSUPPORTED when the formula runs on the interpreter tier.
+extern "C" int pystl_b200_fused_precompile(const pystl_formula_t* f, int64_t T, int32_t D, int32_t backward) {
+  Lowered lw;
+  TileGeom g;
+  FusedSource fs;
+  int rc = fused_prepare(f, 1, T, D, backward != 0, &lw, &g, &fs);
+  if (rc) return rc;
+  return fused_jit_precompile(fs, g_err, sizeof(g_err));
+}
+
+// The generated source (debugging / inspection).  Returns its length, or a negative status.
+extern "C" int pystl_b200_fused_source(const pystl_formula_t* f, int64_t T, int32_t D, int32_t backward, char* buf, int32_t len) {
+  Lowered lw;
+  TileGeom g;
+  FusedSource fs;
+  int rc = fused_prepare(f, 1, T, D, backward != 0, &lw, &g, &fs);
+  if (rc) return rc;
+  if (buf && len > 0) snprintf(buf, (size_t)len, "%s", fs.source.c_str());
+  return (int)fs.source.size();
+}
+
 extern "C" int pystl_b200_abi_version(void) { return PYSTL_B200_ABI_VERSION; }
 extern "C" const char* pystl_b200_last_error(void) { return g_err; }
 
@@ -77,7 +147,20 @@ extern "C" int pystl_b200_eval_forward(const pystl_formula_t* f, const float* si
                                        float* out, double* mean_acc, void* stream) {
   Lowered lw;
   TileGeom g;
-  int rc = prepare(f, B, T, D, false, &lw, &g);
+  int rc;
+  const int tier = tier_mode();
+  if (tier != TIER_INTERP) {
+    FusedSource fs;
+    rc = fused_prepare(f, B, T, D, false, &lw, &g, &fs);
+    if (rc == PYSTL_OK) {
+      if (B == 0 || T == 0) return PYSTL_OK;
+      if (!signal || !out) return set_err(PYSTL_E_INVALID, "signal / out is NULL");
+      void* args[] = {(void*)&lw.prog, (void*)&g, (void*)&signal, (void*)&out, (void*)&mean_acc};
+      rc = fused_launch(lw, g, fs, args, reinterpret_cast<cudaStream_t>(stream));
+    }
+    if (rc != PYSTL_E_UNSUPPORTED || tier == TIER_FUSED) return rc;
+  }
+  rc = prepare(f, B, T, D, false, &lw, &g);
   if (rc) return rc;
   if (B == 0 || T == 0) return PYSTL_OK;
   if (!signal || !out) return set_err(PYSTL_E_INVALID, "signal / out is NULL");

@@ -25,9 +25,15 @@
 //   windows  [t+a, min(t+b, T-1)]           api.py:49-54
 //   until    OR_i AND(AND_{k<=i} l, r_i)    api.py:284-302 + each semantics' temporal_until
 #pragma once
+#if defined(__CUDACC_RTC__)
+// run-time compilation (jit.cpp): no host headers
+#define INFINITY __int_as_float(0x7f800000)
+#define NAN __int_as_float(0x7fffffff)
+#else
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#endif
 
 #include "program.h"
 

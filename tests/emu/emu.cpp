@@ -130,3 +130,35 @@ extern "C" int pystl_emu_eval_backward(const pystl_formula_t* f, const float* si
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------- fused tier
+// Lower (SSA) + plan + generate the fused kernel source; the test harness compiles that source
+// with g++ against simt_host.h (tests/emu/fused_runner.h) and runs it on the CPU.
+#include "fused_host.h"
+extern "C" int pystl_emu_fused_sizes(int32_t* prog_bytes, int32_t* geom_bytes) {
+  *prog_bytes = (int32_t)sizeof(TileProgram);
+  *geom_bytes = (int32_t)sizeof(TileGeom);
+  return 0;
+}
+extern "C" int pystl_emu_fused_prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t D, int32_t backward,
+                                       int32_t force_nt, char* src, int32_t src_len, void* prog, void* geom,
+                                       int32_t* smem_floats) {
+  Lowered lw;
+  int rc = lower_formula_ex(reinterpret_cast<const ::pystl_formula*>(f), backward != 0, true, &lw, g_err, sizeof(g_err));
+  if (rc) return rc;
+  TileGeom g;
+  rc = fused_geometry(lw, B, T, D, force_nt, backward != 0, &g, g_err, sizeof(g_err));
+  if (rc) return rc;
+  FusedSource fs;
+  rc = fused_generate(lw, D, g.nt, 1, backward != 0, &fs, g_err, sizeof(g_err));
+  if (rc) return rc;
+  if ((int)fs.source.size() + 1 > src_len) {
+    snprintf(g_err, sizeof(g_err), "source buffer too small");
+    return PYSTL_E_INVALID;
+  }
+  memcpy(src, fs.source.c_str(), fs.source.size() + 1);
+  memcpy(prog, &lw.prog, sizeof(TileProgram));
+  memcpy(geom, &g, sizeof(TileGeom));
+  *smem_floats = fs.smem_floats;
+  return 0;
+}

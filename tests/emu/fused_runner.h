@@ -1,0 +1,30 @@
+// Runs a generated fused kernel on the CPU (TEST INFRASTRUCTURE): included after the generated
+// source by the wrapper translation unit the test harness writes (tests/fused_emu_lib.py).
+#pragma once
+namespace {
+struct FusedArgs {
+  const pystl::TileProgram* P;
+  const pystl::TileGeom* g;
+  const float* signal;
+  float* out;
+  double* mean;
+  const float* grad_out;
+  float scale;
+  float* grad_signal;
+};
+void fused_body(void* a) {
+  FusedArgs* A = static_cast<FusedArgs*>(a);
+#if defined(PF_EMU_BACKWARD)
+  pystl_fused(*A->P, *A->g, A->signal, A->grad_out, A->scale, A->grad_signal);
+#else
+  pystl_fused(*A->P, *A->g, A->signal, A->out, A->mean);
+#endif
+}
+}  // namespace
+extern "C" int pystl_fused_emu_run(const void* P, const void* g, const float* signal, float* out, double* mean,
+                                   const float* grad_out, float scale, float* grad_signal, int smem_floats) {
+  FusedArgs a{static_cast<const pystl::TileProgram*>(P), static_cast<const pystl::TileGeom*>(g), signal, out, mean, grad_out, scale, grad_signal};
+  const long long grid = a.g->B * a.g->n_tiles;
+  for (long long b = 0; b < grid; ++b) simt::run_cta((int)b, a.g->nt, (size_t)smem_floats * 4, fused_body, &a);
+  return 0;
+}

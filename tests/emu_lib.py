@@ -18,11 +18,13 @@ from pystl_b200 import capi
 from pystl_b200.compiler import compile_formula
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = [os.path.join(ROOT, "tests", "emu", "emu.cpp"), os.path.join(ROOT, "pystl_b200", "csrc", "lower.cpp")]
+SRC = [os.path.join(ROOT, "tests", "emu", "emu.cpp"), os.path.join(ROOT, "pystl_b200", "csrc", "lower.cpp"),
+       os.path.join(ROOT, "pystl_b200", "csrc", "codegen.cpp")]
 DEPS = SRC + [
     os.path.join(ROOT, "pystl_b200", "csrc", "tile_eval.h"),
     os.path.join(ROOT, "pystl_b200", "csrc", "tile_bwd.h"),
     os.path.join(ROOT, "pystl_b200", "csrc", "program.h"),
+    os.path.join(ROOT, "pystl_b200", "csrc", "fused_host.h"),
     os.path.join(ROOT, "include", "pystl_b200.h"),
 ]
 OUT = os.path.join(ROOT, "tests", "_emu", "libpystl_emu.so")
@@ -33,8 +35,10 @@ def build(force: bool = False) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     stale = force or not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS)
     if stale:
-        cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", *SRC, "-o", OUT]
-        subprocess.run(cmd, check=True)
+        cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "pystl_b200", "csrc"), *SRC, "-o"]
+        tmp = f"{OUT}.{os.getpid()}.tmp"  # atomic publish: pytest-xdist workers may build concurrently
+        subprocess.run(cmd + [tmp], check=True)
+        os.replace(tmp, OUT)
     return OUT
 
 

@@ -1,0 +1,69 @@
+"""Corpus of the fused-tier parity tests, shared by the GPU test (tests/test_gpu_fused.py), the
+CPU emulation test (tests/test_emu_fused.py) and the build-time precompiler
+(tools/precompile.py), so that the kernels the GPU tests need are already in the cubin cache."""
+
+from __future__ import annotations
+
+import numpy as np
+
+from golden_cases import CASES
+from parity_util import SEM_KW, mixed_signal, random_spec
+from pystl_b200.formula import BASELINE_SPECS
+
+LONG_WINDOWS = [(0, 8), (1, 9), (3, 20), (7, 64), (8, 72), (5, 100), (0, 201), (13, 300), (2, 17), (6, 15), (0, 0), (4, 4),
+                (0, 5), (3, 7), (9, 16), (0, 50)]
+
+
+def forward_cases(light: bool = False):
+    """-> list of dicts: name, spec, sem, kw, B, T, D, threads, seed, scale."""
+    out = []
+    for cfg in ("cfg1", "cfg2", "cfg3"):
+        for sem, kw in SEM_KW:
+            for threads in (0, 64):
+                out.append(dict(name=f"{cfg}/{sem}{kw.get('p', '')}/nt{threads}", spec=BASELINE_SPECS[cfg], sem=sem, kw=kw, B=3,
+                                T=700, D=2, threads=threads, seed=7, scale=4.0 if sem == "cumulative" else 1.0))
+    for a, b in LONG_WINDOWS:
+        spec = ("always", (a, b), ("pred", {0: 1.0}, -0.25))
+        for sem, kw in SEM_KW[:4]:
+            out.append(dict(name=f"G[{a},{b}]/{sem}/nt64", spec=spec, sem=sem, kw=kw, B=2, T=900, D=1, threads=64, seed=5, scale=1.0))
+        spec = ("eventually", (a, b), ("not", ("pred", {0: 1.0}, -0.25)))
+        nt = 64 if b > 150 else 32
+        out.append(dict(name=f"F[{a},{b}]!/dgmsr/nt{nt}", spec=spec, sem="dgmsr", kw={"eps": 1e-8, "p": 2}, B=2, T=900, D=1, threads=nt,
+                        seed=6, scale=1.0))
+    n_seeds = 6 if light else 16
+    for seed in range(n_seeds):
+        rng = np.random.default_rng(2000 + seed)
+        D = int(rng.integers(1, 5))
+        T = int(rng.integers(40, 400))
+        spec = None
+        for _ in range(50):  # formulas the fused tier evaluates: no until, no open-ended interval
+            cand = random_spec(rng, D, depth=3, max_b=40, allow_open=False)
+            if "until" not in repr(cand):
+                spec = cand
+                break
+        if spec is None:
+            continue
+        for sem, kw in SEM_KW[:5]:
+            out.append(dict(name=f"rand{seed}/{sem}", spec=spec, sem=sem, kw=kw, B=2, T=T, D=D, threads=32 if seed % 2 else 0, seed=3000 + seed,
+                            scale=8.0 if sem == "cumulative" else 2.0))
+    for T in (999, 1001, 1002):
+        for sem, kw in (SEM_KW[0], SEM_KW[1]):
+            for threads in (32, 128, 256):
+                out.append(dict(name=f"unaligned/T{T}/{sem}/nt{threads}", spec=BASELINE_SPECS["cfg1"], sem=sem, kw=kw, B=5, T=T, D=2,
+                                threads=threads, seed=21, scale=1.0))
+    return out
+
+
+def backward_cases(light: bool = False):
+    out = []
+    for cfg in ("cfg1", "cfg2", "cfg3"):
+        for sem, kw in (SEM_KW[0], SEM_KW[1], SEM_KW[3], SEM_KW[4], SEM_KW[5]):
+            for threads in (0, 64):
+                out.append(dict(name=f"bwd/{cfg}/{sem}{kw.get('p', '')}/nt{threads}", spec=BASELINE_SPECS[cfg], sem=sem, kw=kw, B=2,
+                                T=520, D=2, threads=threads, seed=17))
+    return out
+
+
+def case_signal(case) -> np.ndarray:
+    rng = np.random.default_rng(case["seed"])
+    return mixed_signal(rng, case["B"], case["T"], case["D"])

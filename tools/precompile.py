@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Fill the fused tier's cubin cache (pystl_b200/csrc/build/fused) ahead of time.
+
+NVRTC needs no GPU, so the kernels of the BASELINE workloads (bench.py) and of the parity
+corpus (tests/fused_cases.py) are compiled here, in parallel, and travel with the tree; on the
+GPU box the library then only loads cubins.  A formula that is not in the cache is compiled
+on first use (a second or two), so this is an optimisation, not a requirement.
+
+    python tools/precompile.py [--tests] [--jobs 8]
+"""
+
+from __future__ import annotations
+
+import argparse
+import multiprocessing as mp
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+
+def _one(job):
+    spec, sem, kw, T, D, threads, backward = job
+    from pystl_b200 import capi
+    from pystl_b200.compiler import compile_formula
+    from pystl_b200.formula import from_spec
+
+    if threads:
+        os.environ["PYSTL_B200_FORCE_THREADS"] = str(threads)
+    else:
+        os.environ.pop("PYSTL_B200_FORCE_THREADS", None)
+    lib = capi.lib()
+    cf = compile_formula(from_spec(spec), sem, D, **kw)
+    rc = lib.pystl_b200_fused_precompile(cf.ptr(), T, D, int(backward))
+    return rc, (lib.pystl_b200_last_error().decode() if rc else "")
+
+
+def jobs(with_tests: bool):
+    from pystl_b200.formula import BASELINE_SHAPES, BASELINE_SPECS
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    out = []
+    for cfg, (sem, kw, bwd) in bench.WORKLOADS.items():
+        _, T, D = BASELINE_SHAPES[cfg[:4]]
+        out.append((BASELINE_SPECS[cfg[:4]], sem, kw, T, D, 0, False))
+        if bwd:
+            out.append((BASELINE_SPECS[cfg[:4]], sem, kw, T, D, 0, True))
+    if with_tests:
+        import fused_cases
+
+        for c in fused_cases.forward_cases():
+            out.append((c["spec"], c["sem"], c["kw"], c["T"], c["D"], c["threads"], False))
+        for c in fused_cases.backward_cases():
+            out.append((c["spec"], c["sem"], c["kw"], c["T"], c["D"], c["threads"], True))
+    return out
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tests", action="store_true", help="also the kernels of the parity corpus")
+    ap.add_argument("--jobs", type=int, default=os.cpu_count() or 4)
+    args = ap.parse_args(argv)
+    todo = jobs(args.tests)
+    t0 = time.time()
+    with mp.get_context("spawn").Pool(args.jobs) as pool:
+        res = pool.map(_one, todo, chunksize=4)
+    ok = sum(1 for rc, _ in res if rc == 0)
+    unsup = sum(1 for rc, _ in res if rc == -2)
+    bad = [(j, m) for j, (rc, m) in zip(todo, res) if rc not in (0, -2)]
+    print(f"precompile: {ok} kernels cached, {unsup} on the interpreter tier, {len(bad)} failed, {time.time() - t0:.1f}s")
+    for j, m in bad[:5]:
+        print("  FAILED", j[1], j[0], m[:300])
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
