@@ -79,6 +79,7 @@ struct Gen {
   std::vector<int> scr_off;   // per instruction: scratch offset (floats)
   std::vector<int> stash_off; // per instruction: smooth operand stash
   int smem_floats = 0;
+  int red_floats = 0;
   int n_stages = 0;
 
   Gen(const Lowered& l, int D_, int nt_, int minb_) : lw(l), P(l.prog), D(D_), nt(nt_), minb(minb_) {}
@@ -119,7 +120,7 @@ struct Gen {
     n_stages = max_level + 1;
     // shared memory: [reduction scratch][region 0][region 1]; windows of level l use region l & 1
     const int nw = nt / 32;
-    const int red_floats = roundup(std::max(2 * std::max(P.n_preds, 1), 1) * nw, 32);
+    red_floats = roundup(std::max(2 * std::max(P.n_preds, 1), 1) * nw, 32) + 32;  // + the mean reduction's own 32 floats
     std::vector<int> used(max_level + 2, 0);
     for (int i = 0; i < P.n_instr; ++i) {
       const TInstr& in = P.ins[i];
@@ -153,10 +154,32 @@ struct Gen {
     return buf;
   }
 
+  // ---- smooth only: which value-range bounds are consumed (a window shifts its exponentials by
+  // a bound of its operand; bounds propagate analytically through the operators above)
+  std::vector<char> need_lo, need_hi;
+  void plan_bounds() {
+    need_lo.assign(kMaxSlots, 0);
+    need_hi.assign(kMaxSlots, 0);
+    if (P.sem != SEM_SMOOTH) return;
+    for (int i = P.n_instr - 1; i >= 0; --i) {
+      const TInstr& in = P.ins[i];
+      const bool want_lo = need_lo[in.dst], want_hi = need_hi[in.dst];
+      for (int j = 0; j < in.nsrc; ++j) {
+        const bool neg = (in.negmask >> j) & 1;
+        bool olo = want_lo, ohi = want_hi;  // bounds of the (negated) operand that are consumed
+        if (is_window(in)) (in.mode == MODE_AND ? olo : ohi) = true;  // the shift
+        if (olo) (neg ? need_hi : need_lo)[in.src[j]] = 1;
+        if (ohi) (neg ? need_lo : need_hi)[in.src[j]] = 1;
+      }
+    }
+  }
+  std::string lo_of(int slot, bool neg) const { return (neg ? "-hi" : "lo") + std::to_string(slot); }
+  std::string hi_of(int slot, bool neg) const { return (neg ? "-lo" : "hi") + std::to_string(slot); }
+
   void emit_predicates() {
     o.line("// ---- predicates: rows -> registers (api.py:142-143)");
     for (int q = 0; q < P.n_preds; ++q) o.line("V v%d[8];", (int)P.preds[q].dst);
-    o.line("{");
+    o.line("if (live) {");
     o.indent++;
     if (D <= 8) {
       o.line("float r[8][D];");
@@ -198,12 +221,30 @@ struct Gen {
     o.indent--;
     o.line("}");
     if (P.sem == SEM_SMOOTH) {
-      o.line("// value range of every predicate over the tile: the windows shift their exponentials by it");
-      o.line("float bm[%d];", 2 * P.n_preds);
-      for (int q = 0; q < P.n_preds; ++q) o.line("minmax8(c, v%d, bm[%d], bm[%d]);", (int)P.preds[q].dst, 2 * q, 2 * q + 1);
-      o.line("block_max<NT, %d>(c, red, bm);", 2 * P.n_preds);
-      for (int q = 0; q < P.n_preds; ++q)
-        o.line("const float lo%d = -bm[%d], hi%d = bm[%d];", (int)P.preds[q].dst, 2 * q, (int)P.preds[q].dst, 2 * q + 1);
+      int nb = 0;
+      for (int q = 0; q < P.n_preds; ++q) nb += need_lo[P.preds[q].dst] + need_hi[P.preds[q].dst];
+      if (nb > 0) {
+        o.line("// value range of the predicates over the tile: the windows shift their exponentials by it");
+        o.line("float bm[%d];", nb);
+        o.line("_Pragma(\"unroll\") for (int q = 0; q < %d; ++q) bm[q] = -f_inf();", nb);
+        o.line("if (live) {");
+        o.indent++;
+        int k = 0;
+        for (int q = 0; q < P.n_preds; ++q) {
+          const int d = P.preds[q].dst;
+          if (need_lo[d]) o.line("bm[%d] = max8<true>(c, v%d);", k++, d);
+          if (need_hi[d]) o.line("bm[%d] = max8<false>(c, v%d);", k++, d);
+        }
+        o.indent--;
+        o.line("}");
+        o.line("block_max<NT, %d>(c, red, bm);", nb);
+        k = 0;
+        for (int q = 0; q < P.n_preds; ++q) {
+          const int d = P.preds[q].dst;
+          if (need_lo[d]) o.line("const float lo%d = -bm[%d];", d, k++);
+          if (need_hi[d]) o.line("const float hi%d = bm[%d];", d, k++);
+        }
+      }
     }
   }
 
@@ -224,11 +265,11 @@ struct Gen {
     o.line("R%d::A x%d[8], sf%d[8], pf%d[8];", i, i, i, i);
     o.line("RP rp%d = rp;", i);
     if (P.sem == SEM_SMOOTH) {
-      if (neg) o.line("const float olo%d = -hi%d, ohi%d = -lo%d;", i, s, i, s);
-      else o.line("const float olo%d = lo%d, ohi%d = hi%d;", i, s, i, s);
-      o.line("rp%d.shift = smooth_shift_of<%s>(rp, olo%d, ohi%d);", i, mode_name(in.mode), i, i);
+      if (in.mode == MODE_AND) o.line("rp%d.shift = -(%s) * rp.k;  // max exponent of the operand over the tile", i, lo_of(s, neg).c_str());
+      else o.line("rp%d.shift = (%s) * rp.k;", i, hi_of(s, neg).c_str());
     }
-    o.line("{");
+    o.line("W%d::fill_guards(smem + %d, c.tid);", i, scr_off[i]);
+    o.line("if (live) {");
     o.indent++;
     o.line("V t[8];");
     o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) t[i] = %s;", operand(in, 0, "i").c_str());
@@ -236,35 +277,41 @@ struct Gen {
     if (P.sem == SEM_SMOOTH) o.line("stash8<VW>(smem + %d, c.tid, t, 0);", stash_off[i]);
     o.line("W%d::phase1(smem + %d, c.tid, x%d, sf%d, pf%d);", i, scr_off[i], i, i, i);
     o.indent--;
+    o.line("} else {");
+    o.indent++;
+    o.line("W%d::phase1_dead(smem + %d, c.tid);", i, scr_off[i]);
+    o.indent--;
     o.line("}");
   }
 
   void win_phase2(int i) {
     const TInstr& in = P.ins[i];
     const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
+    const bool neg = in.negmask & 1;
+    const int s = in.src[0], d = in.dst;
     o.line("// window %d, phase 2: combine -> value", i);
-    o.line("V v%d[8];", (int)in.dst);
-    o.line("{");
+    o.line("V v%d[8];", d);
+    o.line("if (live) {");
     o.indent++;
     o.line("R%d::A acc[8];", i);
     o.line("W%d::phase2(smem + %d, c.tid, x%d, sf%d, pf%d, acc);", i, scr_off[i], i, i, i);
-    o.line("fin8<R%d, %d, %d, VW>(c, rp%d, acc, v%d);", i, a, b, i, (int)in.dst);
+    o.line("fin8<R%d, %d, %d, VW>(c, rp%d, acc, v%d);", i, a, b, i, d);
     if (P.sem == SEM_SMOOTH)
-      o.line("smooth_fix8<%s, %d, %d, NT>(c, rp%d, smem + %d, acc, v%d);", mode_name(in.mode), a, b, i, stash_off[i], (int)in.dst);
+      o.line("smooth_fix8<%s, %d, %d, NT>(c, rp%d, smem + %d, acc, v%d);", mode_name(in.mode), a, b, i, stash_off[i], d);
     o.indent--;
     o.line("}");
     if (P.sem == SEM_SMOOTH) {
-      o.line("float lo%d, hi%d;", (int)in.dst, (int)in.dst);
-      o.line("smooth_bounds<%s>(rp, olo%d, ohi%d, %d.f, lo%d, hi%d);", mode_name(in.mode), i, i, b - a + 1, (int)in.dst, (int)in.dst);
+      if (need_lo[d]) o.line("const float lo%d = smooth_lo<%s>(rp, %s, %d.f);", d, mode_name(in.mode), lo_of(s, neg).c_str(), b - a + 1);
+      if (need_hi[d]) o.line("const float hi%d = smooth_hi<%s>(rp, %s, %d.f);", d, mode_name(in.mode), hi_of(s, neg).c_str(), b - a + 1);
     }
   }
 
   void nary(int i) {
     const TInstr& in = P.ins[i];
-    const int n = in.nsrc;
+    const int n = in.nsrc, d = in.dst;
     o.line("// n-ary %s (%d operands)", in.mode == MODE_AND ? "And" : "Or", n);
-    o.line("V v%d[8];", (int)in.dst);
-    o.line("{");
+    o.line("V v%d[8];", d);
+    o.line("if (live) {");
     o.indent++;
     std::string w = "const float w[" + std::to_string(n) + "] = {";
     for (int j = 0; j < n; ++j) {
@@ -278,30 +325,29 @@ struct Gen {
     std::string a = "const V a[" + std::to_string(n) + "] = {";
     for (int j = 0; j < n; ++j) a += (j ? ", " : "") + operand(in, j, "i");
     o.line("%s};", a.c_str());
-    o.line("v%d[i] = nary1<SEM, %s, %d>(rp, a, w, P.ins[%d].sw);", (int)in.dst, mode_name(in.mode), n, i);
+    o.line("v%d[i] = nary1<SEM, %s, %d>(rp, a, w, P.ins[%d].sw);", d, mode_name(in.mode), n, i);
     o.indent--;
     o.line("}");
     o.indent--;
     o.line("}");
-    if (P.sem == SEM_SMOOTH) {
+    if (P.sem == SEM_SMOOTH && (need_lo[d] || need_hi[d])) {
       // min / max over the operands' ranges (tile_eval.h: op_nary)
       const char* f = in.mode == MODE_AND ? "fminf" : "fmaxf";
       std::string lo, hi;
       for (int j = 0; j < n; ++j) {
         const bool neg = (in.negmask >> j) & 1;
-        char l[32], h[32];
-        snprintf(l, sizeof(l), neg ? "-hi%d" : "lo%d", (int)in.src[j]);
-        snprintf(h, sizeof(h), neg ? "-lo%d" : "hi%d", (int)in.src[j]);
-        lo = j ? std::string(f) + "(" + lo + ", " + l + ")" : std::string(l);
-        hi = j ? std::string(f) + "(" + hi + ", " + h + ")" : std::string(h);
+        const std::string l = lo_of(in.src[j], neg), h = hi_of(in.src[j], neg);
+        lo = j ? std::string(f) + "(" + lo + ", " + l + ")" : l;
+        hi = j ? std::string(f) + "(" + hi + ", " + h + ")" : h;
       }
-      o.line("float lo%d, hi%d;", (int)in.dst, (int)in.dst);
-      o.line("smooth_bounds<%s>(rp, %s, %s, %d.f, lo%d, hi%d);", mode_name(in.mode), lo.c_str(), hi.c_str(), n, (int)in.dst, (int)in.dst);
+      if (need_lo[d]) o.line("const float lo%d = smooth_lo<%s>(rp, %s, %d.f);", d, mode_name(in.mode), lo.c_str(), n);
+      if (need_hi[d]) o.line("const float hi%d = smooth_hi<%s>(rp, %s, %d.f);", d, mode_name(in.mode), hi.c_str(), n);
     }
   }
 
   std::string forward() {
     plan();
+    plan_bounds();
     o.indent = 0;
     o.line("// generated by pystl_b200/csrc/codegen.cpp -- forward kernel of one formula (fused tier)");
     o.line("#include \"fused_rt.cuh\"");
@@ -316,6 +362,7 @@ struct Gen {
     o.line("const TC c = tile_begin<NT>(P, g, smem);");
     o.line("const RP rp = c.rp;");
     o.line("float* red = smem;");
+    o.line("const bool live = alive(c);  // threads past the horizon only keep the shared planes consistent");
     o.line("(void)red; (void)rp;");
     emit_predicates();
     for (int st = 0; st < n_stages; ++st) {
@@ -334,7 +381,9 @@ struct Gen {
         }
       if (any) o.line("simt::sync();");
     }
-    o.line("store_root<SEM, NT, %s>(c, g.T, v%d, out, mean_acc, red);", P.root_neg ? "true" : "false", (int)P.root);
+    o.line("float part = 0.f;");
+    o.line("if (live) part = store_root<SEM, %s>(c, g.T, v%d, out);", P.root_neg ? "true" : "false", (int)P.root);
+    o.line("if (mean_acc) block_sum_to<NT>(c, part, mean_acc, smem + %d);", red_floats - 32);
     o.indent = 0;
     o.line("}");
     return o.s;

@@ -29,7 +29,8 @@
 #define PF_DYN_SMEM(name) extern __shared__ __align__(128) float name[]
 namespace simt {
 PF_DEV int tid() { return (int)threadIdx.x; }
-PF_DEV int bid() { return (int)blockIdx.x; }
+PF_DEV int bid_x() { return (int)blockIdx.x; }
+PF_DEV int bid_y() { return (int)blockIdx.y; }
 PF_DEV void sync() { __syncthreads(); }
 PF_DEV float shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 PF_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
@@ -64,29 +65,30 @@ struct TC {
   RP rp;
 };
 
+// grid = (traces, tiles per trace): no division to find the tile
 template <int NT>
 PF_DEV TC tile_begin(const TileProgram& P, const TileGeom& g, float* smem) {
   TC c;
   c.smem = smem;
   c.tid = simt::tid();
   c.p0 = 8 * c.tid;
-  const unsigned tile = (unsigned)simt::bid();
-  const unsigned bu = tile / (unsigned)g.n_tiles;
-  const int j = (int)(tile - bu * (unsigned)g.n_tiles);
-  c.b = (long long)bu;
-  const long long e0 = (long long)j * g.lout;
-  c.origin = e0 > (long long)g.hh ? e0 - g.hh : 0;  // backward tiles carry a left halo
-  const long long live = g.T - c.origin;
+  c.b = (long long)simt::bid_x();
+  const int e0 = simt::bid_y() * g.lout;   // T < 2^31 / tile
+  const int origin = e0 > g.hh ? e0 - g.hh : 0;  // backward tiles carry a left halo
+  c.origin = origin;
+  const long long live = g.T - origin;
   c.nlive = live < (long long)(8 * NT) ? (int)live : 8 * NT;
-  const long long ok = P.raises_always ? -1 : g.T - 1 - P.start_slack - c.origin;
+  const long long ok = P.raises_always ? -1 : g.T - 1 - P.start_slack - origin;
   c.last_ok = ok > (long long)(1 << 30) ? (1 << 30) : (ok < -1 ? -1 : (int)ok);
-  c.p_lo = (int)(e0 - c.origin);
+  c.p_lo = e0 - origin;
   c.p_hi = c.p_lo + g.lout < c.nlive ? c.p_lo + g.lout : c.nlive;
   c.rp = P.rp;
   return c;
 }
 
 PF_DEV bool own_all_live(const TC& c) { return c.p0 + 8 <= c.nlive; }
+// threads whose 8 samples all lie past the horizon only keep the shared planes consistent
+PF_DEV bool alive(const TC& c) { return c.p0 < c.nlive; }
 
 // ------------------------------------------------------------------ signal rows -> registers
 // The thread's 8 rows are 8*D consecutive floats of the trace: 128-bit loads when they all
@@ -154,37 +156,30 @@ PF_DEV void block_max(const TC& c, float* red, float (&m)[N]) {
   }
 }
 
-// (-min, max) of the thread's live samples of a value
-PF_DEV void minmax8(const TC& c, const Vec<1> (&v)[8], float& nlo, float& hi) {
-  nlo = -f_inf();
-  hi = -f_inf();
+// max of +v (NEG: of -v) over the thread's live samples
+template <bool NEG>
+PF_DEV float max8(const TC& c, const Vec<1> (&v)[8]) {
+  float m = -f_inf();
   if (own_all_live(c)) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      nlo = fmaxf(nlo, -v[i].x[0]);
-      hi = fmaxf(hi, v[i].x[0]);
-    }
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, NEG ? -v[i].x[0] : v[i].x[0]);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (c.p0 + i < c.nlive) {
-        nlo = fmaxf(nlo, -v[i].x[0]);
-        hi = fmaxf(hi, v[i].x[0]);
-      }
+      if (c.p0 + i < c.nlive) m = fmaxf(m, NEG ? -v[i].x[0] : v[i].x[0]);
   }
+  return m;
 }
 
-// smooth: range of softmin / softmax over n terms of operands within [lo, hi] (tile_eval.h)
+// smooth: range of softmin / softmax over n terms of operands within [lo, hi]:
+//   min - tau ln n <= softmin <= min,   max <= softmax <= max + tau ln n   (+ rounding slack)
 template <int MODE>
-PF_DEV void smooth_bounds(const RP& rp, float lo, float hi, float n, float& olo, float& ohi) {
-  const float pad = rp.invk * fast_lg2(n > 1.f ? n : 1.f) + 1e-6f * (fabsf(lo) + fabsf(hi));
-  olo = MODE == MODE_AND ? lo - pad : lo;
-  ohi = MODE == MODE_AND ? hi : hi + pad;
+PF_DEV float smooth_lo(const RP& rp, float lo, float n) {
+  return MODE == MODE_AND ? lo - rp.invk * fast_lg2(n > 1.f ? n : 1.f) - 2e-6f * fabsf(lo) - 1e-30f : lo;
 }
-// block-wide upper bound of the exponent of an operand within [lo, hi]
 template <int MODE>
-PF_DEV float smooth_shift_of(const RP& rp, float lo, float hi) {
-  return (MODE == MODE_AND ? -lo : hi) * rp.k;
+PF_DEV float smooth_hi(const RP& rp, float hi, float n) {
+  return MODE == MODE_AND ? hi : hi + rp.invk * fast_lg2(n > 1.f ? n : 1.f) + 2e-6f * fabsf(hi) + 1e-30f;
 }
 
 // ------------------------------------------------------------------ static chunk geometry
@@ -304,7 +299,19 @@ struct WinOp {
         agg(scr, w)[tid] = pre[7].x[w];
       }
     }
-    fill_guards(scr, tid);
+  }
+  // a thread past the horizon: its chunk is the identity
+  PF_DEV static void phase1_dead(float* scr, int tid) {
+    const A id = R::ident();
+#pragma unroll
+    for (int w = 0; w < AW; ++w) {
+      float t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = id.x[w];
+      if constexpr (USE_SUF) store8(plane0(scr, w), tid, t);
+      if constexpr (USE_PRE) store8(plane1(scr, w), tid, t);
+      if constexpr (VH) agg(scr, w)[tid] = id.x[w];
+    }
   }
 
   PF_DEV static A load_agg(const float* scr, int ch) {
@@ -400,20 +407,22 @@ struct WinOp {
 #pragma unroll
         for (int k = 1; k < NCORE; ++k) core = R::comb(core, load_agg(scr, tid + qa + 2 + k));
       }
-      constexpr bool any_l = (ra == 0) ? (qa + 1 <= qb - 1 || (qa + 1 <= qb && rb > 0)) : true;
-      (void)any_l;
       const A agl = load_agg(scr, tid + qa + 1);
       const A agr = load_agg(scr, tid + qb);
+      // the (at most four) distinct sets of whole chunks, in time order
+      const A m_l = NCORE > 0 ? R::comb(agl, core) : agl;
+      const A m_r = NCORE > 0 ? R::comb(core, agr) : agr;
+      const A m_lr = R::comb(m_l, agr);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int lo = qa + ((ra + i) >> 3) + 1, hi = qb + ((rb + i) >> 3) - 1;
         const bool inc_l = (lo == qa + 1) && (qa + 1 <= hi);
         const bool inc_r = (hi == qb) && (lo <= qb) && (qb != qa + 1 || !inc_l);
-        A a = sv[i];
-        if (inc_l) a = R::comb(a, agl);
-        if (NCORE > 0) a = R::comb(a, core);
-        if (inc_r) a = R::comb(a, agr);
-        acc[i] = R::comb(a, ev[i]);
+        if (inc_l && inc_r) acc[i] = R::comb(R::comb(sv[i], m_lr), ev[i]);
+        else if (inc_l) acc[i] = R::comb(R::comb(sv[i], m_l), ev[i]);
+        else if (inc_r) acc[i] = R::comb(R::comb(sv[i], m_r), ev[i]);
+        else if (NCORE > 0) acc[i] = R::comb(R::comb(sv[i], core), ev[i]);
+        else acc[i] = R::comb(sv[i], ev[i]);
       }
     }
   }
@@ -478,7 +487,7 @@ PF_DEV void smooth_fix8(const TC& c, const RP& rp, const float* vplane, const Ve
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (j == i) a_i = acc[j].x[0];
-    if (a_i >= kSmoothTiny) continue;
+    if (a_i >= kSmoothTiny || c.p0 + i >= c.nlive) continue;
     int lo = c.p0 + i + FA, hi = c.p0 + i + FB;
     if (hi > c.nlive - 1) hi = c.nlive - 1;
     if (hi > 8 * NT - 1) hi = 8 * NT - 1;
@@ -510,7 +519,14 @@ PF_DEV void stash8(float* plane, int tid, const Vec<VW> (&v)[8], int w) {
 template <int SEM, int MODE, int N>
 PF_DEV Vec<Tr<SEM>::VW> nary1(const RP& rp0, const Vec<Tr<SEM>::VW> (&a)[N], const float (&w)[N], float sw) {
   using R = Red<SEM, MODE>;
-  if constexpr (SEM == SEM_SMOOTH) {
+  if constexpr (SEM == SEM_SMOOTH && N == 2) {
+    // max + log2(1 + 2^-|d|): the max-shifted logsumexp of two terms (smooth.py:18-22)
+    const float e0 = R::expo(a[0], rp0), e1 = R::expo(a[1], rp0);
+    const float m = fmaxf(e0, e1);
+    const float l = fast_lg2(1.f + fast_ex2(-fabsf(e0 - e1)));
+    const float sk = MODE == MODE_AND ? -rp0.invk : rp0.invk;
+    return Vec<1>{{(m + l) * sk}};
+  } else if constexpr (SEM == SEM_SMOOTH) {
     // exact max-shifted logsumexp (smooth.py:18-22)
     float e[N];
     float m = -f_inf();
@@ -534,27 +550,37 @@ PF_DEV Vec<Tr<SEM>::VW> nary1(const RP& rp0, const Vec<Tr<SEM>::VW> (&a)[N], con
 }
 
 // ------------------------------------------------------------------ root -> HBM (+ fused mean)
-// Writes the tile's outputs [p_lo, p_hi); NaN where the reference raises.  red: NT/32 floats.
-template <int SEM, int NT, bool NEG>
-PF_DEV void store_root(const TC& c, long long T, const Vec<Tr<SEM>::VW> (&v)[8], float* __restrict__ out,
-                       double* __restrict__ mean_acc, float* red) {
+// Writes the thread's outputs inside [p_lo, p_hi); NaN where the reference raises.  Returns the
+// sum of the valid outputs it wrote (for the fused mean).
+template <int SEM, bool NEG>
+PF_DEV float store_root(const TC& c, long long T, const Vec<Tr<SEM>::VW> (&v)[8], float* __restrict__ out) {
   constexpr int VW = Tr<SEM>::VW;
   Vec<VW> o[8];
   float part = 0.f;
+  float* dst = out + (c.b * T + c.origin + c.p0) * (long long)VW;
+  const bool inside = c.p0 >= c.p_lo && c.p0 + 8 <= c.p_hi;
+  if (inside && c.p0 + 7 <= c.last_ok) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    o[i] = NEG ? negate<SEM>(v[i]) : v[i];
-    const int p = c.p0 + i;
-    if (p > c.last_ok) {
-#pragma unroll
-      for (int w = 0; w < VW; ++w) o[i].x[w] = f_nan();
-    } else if (p >= c.p_lo && p < c.p_hi) {
+    for (int i = 0; i < 8; ++i) {
+      o[i] = NEG ? negate<SEM>(v[i]) : v[i];
 #pragma unroll
       for (int w = 0; w < VW; ++w) part += o[i].x[w];
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = NEG ? negate<SEM>(v[i]) : v[i];
+      const int p = c.p0 + i;
+      if (p > c.last_ok) {
+#pragma unroll
+        for (int w = 0; w < VW; ++w) o[i].x[w] = f_nan();
+      } else if (p >= c.p_lo && p < c.p_hi) {
+#pragma unroll
+        for (int w = 0; w < VW; ++w) part += o[i].x[w];
+      }
+    }
   }
-  float* dst = out + (c.b * T + c.origin + c.p0) * (long long)VW;
-  if (c.p0 >= c.p_lo && c.p0 + 8 <= c.p_hi && ((u64)dst & 15ull) == 0ull) {
+  if (inside && ((u64)dst & 15ull) == 0ull) {
     F4* d4 = reinterpret_cast<F4*>(dst);
     if constexpr (VW == 1) {
       d4[0] = F4{{o[0].x[0], o[1].x[0], o[2].x[0], o[3].x[0]}};
@@ -571,17 +597,21 @@ PF_DEV void store_root(const TC& c, long long T, const Vec<Tr<SEM>::VW> (&v)[8],
         for (int w = 0; w < VW; ++w) dst[i * VW + w] = o[i].x[w];
       }
   }
-  if (mean_acc) {
-    float s = part;
+  return part;
+}
+
+// block sum of `part` -> one atomicAdd(double) per CTA.  red: NT/32 floats.  All threads call it.
+template <int NT>
+PF_DEV void block_sum_to(const TC& c, float part, double* __restrict__ acc, float* red) {
+  float s = part;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += simt::shfl_xor(s, d);
-    if ((c.tid & 31) == 0) red[c.tid >> 5] = s;
-    simt::sync();
-    if (c.tid == 0) {
-      double tot = 0.0;
-      for (int w = 0; w < NT / 32; ++w) tot += (double)red[w];
-      simt::atomic_add(mean_acc, tot);
-    }
+  for (int d = 16; d > 0; d >>= 1) s += simt::shfl_xor(s, d);
+  if ((c.tid & 31) == 0) red[c.tid >> 5] = s;
+  simt::sync();
+  if (c.tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < NT / 32; ++w) tot += (double)red[w];
+    simt::atomic_add(acc, tot);
   }
 }
 

@@ -67,7 +67,8 @@ static int tier_mode() {
 static int fused_minb(int nt) {
   const char* e = getenv("PYSTL_B200_FUSED_MINB");
   if (e && *e) return atoi(e) > 0 ? atoi(e) : 1;
-  const int target_regs = 96;
+  const char* r = getenv("PYSTL_B200_FUSED_REGS");
+  const int target_regs = (r && atoi(r) >= 32) ? atoi(r) : 64;
   int minb = 65536 / (nt * target_regs);
   return minb < 1 ? 1 : (minb > 8 ? 8 : minb);
 }
@@ -89,9 +90,8 @@ static int fused_launch(const Lowered& lw, const TileGeom& g, const FusedSource&
   FusedKernel fk;
   int rc = fused_jit_get(fs, &fk, g_err, sizeof(g_err));
   if (rc) return rc;
-  const int64_t grid = g.B * g.n_tiles;
-  if (grid > 0x7fffffffLL) return set_err(PYSTL_E_UNSUPPORTED, "grid of %lld tiles exceeds 2^31-1", (long long)grid);
-  cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(fk.kernel), dim3((unsigned)grid), dim3((unsigned)g.nt), args,
+  if (g.B > 0x7fffffffLL || g.n_tiles > 65535) return set_err(PYSTL_E_UNSUPPORTED, "grid of %lld x %d tiles is too large", (long long)g.B, g.n_tiles);
+  cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(fk.kernel), dim3((unsigned)g.B, (unsigned)g.n_tiles), dim3((unsigned)g.nt), args,
                                    (size_t)fs.smem_floats * 4, stream);
   if (e != cudaSuccess) return set_err(PYSTL_E_CUDA, "fused kernel launch: %s", cudaGetErrorString(e));
   (void)lw;

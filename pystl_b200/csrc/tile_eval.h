@@ -158,11 +158,12 @@ struct Red<SEM_SMOOTH, MODE> {
   using A = Vec<1>;
   static PYSTL_HD float expo(V v, const RP& rp) { return (MODE == MODE_AND ? -v.x[0] : v.x[0]) * rp.k; }
   static PYSTL_HD A ident() { return A{{0.f}}; }
-  static PYSTL_HD A lift(V v, const RP& rp, float) { return A{{fast_ex2(expo(v, rp) - rp.shift)}}; }
+  // one FFMA + one MUFU each way: 2^(+-k v - shift), and +-invk (lg2 S + shift)
+  static PYSTL_HD A lift(V v, const RP& rp, float) { return A{{fast_ex2(fmaf(v.x[0], MODE == MODE_AND ? -rp.k : rp.k, -rp.shift))}}; }
   static PYSTL_HD A comb(A a, A b) { return A{{a.x[0] + b.x[0]}}; }
   static PYSTL_HD V fin(A a, float, const RP& rp) {
-    const float l = (fast_lg2(a.x[0]) + rp.shift) * rp.invk;
-    return V{{MODE == MODE_AND ? -l : l}};
+    const float sk = MODE == MODE_AND ? -rp.invk : rp.invk;
+    return V{{fmaf(fast_lg2(a.x[0]), sk, rp.shift * sk)}};
   }
 };
 

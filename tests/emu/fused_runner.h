@@ -24,7 +24,7 @@ void fused_body(void* a) {
 extern "C" int pystl_fused_emu_run(const void* P, const void* g, const float* signal, float* out, double* mean,
                                    const float* grad_out, float scale, float* grad_signal, int smem_floats) {
   FusedArgs a{static_cast<const pystl::TileProgram*>(P), static_cast<const pystl::TileGeom*>(g), signal, out, mean, grad_out, scale, grad_signal};
-  const long long grid = a.g->B * a.g->n_tiles;
-  for (long long b = 0; b < grid; ++b) simt::run_cta((int)b, a.g->nt, (size_t)smem_floats * 4, fused_body, &a);
+  for (long long b = 0; b < a.g->B; ++b)
+    for (int j = 0; j < a.g->n_tiles; ++j) simt::run_cta((int)b, j, a.g->nt, (size_t)smem_floats * 4, fused_body, &a);
   return 0;
 }

@@ -21,6 +21,7 @@ namespace simt {
 struct Launch {
   int nt = 0;
   int bid = 0;
+  int bid2 = 0;
   int cur = 0;  // fiber being run
   int alive = 0;
   unsigned long long bar_gen = 0;
@@ -43,7 +44,8 @@ inline Launch*& cur_launch() {
 }
 
 inline int tid() { return cur_launch()->cur; }
-inline int bid() { return cur_launch()->bid; }
+inline int bid_x() { return cur_launch()->bid; }
+inline int bid_y() { return cur_launch()->bid2; }
 inline int nthreads() { return cur_launch()->nt; }
 inline float* dyn_smem() { return cur_launch()->dyn_smem; }
 
@@ -145,7 +147,7 @@ inline void fiber_entry() {
 }
 
 // run one CTA: `body(arg)` is executed by nt fibers
-inline void run_cta(int bid_, int nt, size_t smem_bytes, void (*body)(void*), void* arg) {
+inline void run_cta(int bid_, int bid_y_, int nt, size_t smem_bytes, void (*body)(void*), void* arg) {
   static thread_local Launch L;
   static const size_t kStack = 256 * 1024;
   if ((int)L.stacks.size() < nt) {
@@ -155,6 +157,7 @@ inline void run_cta(int bid_, int nt, size_t smem_bytes, void (*body)(void*), vo
   }
   L.nt = nt;
   L.bid = bid_;
+  L.bid2 = bid_y_;
   L.cur = 0;
   L.alive = nt;
   L.bar_gen = 0;
