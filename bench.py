@@ -113,6 +113,14 @@ class ClockSampler(threading.Thread):
         }
 
 
+def tier_of(lib, cf, T: int, D: int, backward: bool) -> str:
+    """Which tier evaluates this formula: the run-time specialised fused kernels or the interpreter."""
+    if os.environ.get("PYSTL_B200_TIER") == "interp":
+        return "interpreter"
+    rc = lib.pystl_b200_fused_precompile(cf.ptr(), T, D, int(backward))
+    return "fused" if rc == 0 else "interpreter"
+
+
 def measured_peak_gbs() -> tuple[float, str]:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -255,23 +263,26 @@ def run_b200(args) -> None:
     plan = sem.plan(phi, T, D)
     n_valid = B * max(T - plan["start_slack"], 0)
     launches = 0
+    tier = tier_of(lib, cf, T, D, with_bwd)
+    # the interpreter tier has no fused value-and-gradient kernel: forward + backward launches
+    launches_per_step = 2 if (with_bwd and tier == "interpreter") else 1
 
     def step() -> int:
-        n = 0
         acc.zero_()
-        rc = lib.pystl_b200_eval_forward(cf.ptr(), signal.data_ptr(), B, T, D, out.data_ptr(), acc.data_ptr(), stream.cuda_stream)
-        capi.raise_for(rc, lib.pystl_b200_last_error())
-        n += 1
         if with_bwd:
-            # loss = mean robustness over the whole (sharded) batch: constant cotangent 1 / (world * n_valid)
-            rc = lib.pystl_b200_eval_backward(
-                cf.ptr(), signal.data_ptr(), B, T, D, None, 1.0 / (world * n_valid), grad.data_ptr(), stream.cuda_stream
+            # value AND gradient of the mean-robustness loss through the C ABI: one fused kernel reads
+            # the signal once, writes out[B,T], its mean accumulator and grad_signal[B,T,D]
+            # (constant cotangent 1 / (world * n_valid): the loss is the mean over the sharded batch)
+            rc = lib.pystl_b200_eval_value_and_grad(
+                cf.ptr(), signal.data_ptr(), B, T, D, None, 1.0 / (world * n_valid), out.data_ptr(), acc.data_ptr(),
+                grad.data_ptr(), stream.cuda_stream,
             )
-            capi.raise_for(rc, lib.pystl_b200_last_error())
-            n += 1
+        else:
+            rc = lib.pystl_b200_eval_forward(cf.ptr(), signal.data_ptr(), B, T, D, out.data_ptr(), acc.data_ptr(), stream.cuda_stream)
+        capi.raise_for(rc, lib.pystl_b200_last_error())
         if world > 1:
             dist.all_reduce(acc)
-        return n
+        return launches_per_step
 
     def barrier():
         if world > 1:
@@ -301,51 +312,39 @@ def run_b200(args) -> None:
     samples_per_step = world * B * T
     value = samples_per_step * args.steps / (ms * 1e-3)
 
-    # dominant kernel alone (forward), CUDA events on the launching stream
-    fwd_ms = []
-    for a, b_ in ev:
-        a.record(stream)
-        rc = lib.pystl_b200_eval_forward(cf.ptr(), signal.data_ptr(), B, T, D, out.data_ptr(), None, stream.cuda_stream)
-        b_.record(stream)
-    torch.cuda.synchronize(dev)
-    fwd_ms = [a.elapsed_time(b_) for a, b_ in ev]
-    k_ms = float(np.mean(fwd_ms))
-    peak, peak_src = measured_peak_gbs()
-    bytes_fwd = algorithmic_bytes_per_sample(cfg, False)
-    roofline = {
-        "bound": "hbm",
-        "kernel": f"fwd_kernel<{sem_name}>",
-        "achieved": bytes_fwd * B * T / (k_ms * 1e-3) / 1e9,
-        "peak": peak,
-        "unit": "GB/s",
-        "frac": bytes_fwd * B * T / (k_ms * 1e-3) / 1e9 / peak,
-        "traffic": None,
-        "peak_source": peak_src,
-        "algorithmic_bytes_per_sample": bytes_fwd,
-        "kernel_ms": k_ms,
-    }
-    if with_bwd:
-        bev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for a, b_ in bev:
+    # kernels alone, CUDA events on the launching stream
+    def time_kernel(fn) -> float:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b_ in evs:
             a.record(stream)
-            lib.pystl_b200_eval_backward(
-                cf.ptr(), signal.data_ptr(), B, T, D, None, 1.0 / (world * n_valid), grad.data_ptr(), stream.cuda_stream
-            )
+            capi.raise_for(fn(), lib.pystl_b200_last_error())
             b_.record(stream)
         torch.cuda.synchronize(dev)
-        b_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in bev]))
-        bytes_bwd = algorithmic_bytes_per_sample(cfg, True) - bytes_fwd
-        bwd = {
-            "kernel": f"bwd_kernel<{sem_name}>",
-            "achieved": bytes_bwd * B * T / (b_ms * 1e-3) / 1e9,
-            "frac": bytes_bwd * B * T / (b_ms * 1e-3) / 1e9 / peak,
-            "algorithmic_bytes_per_sample": bytes_bwd,
-            "kernel_ms": b_ms,
-        }
-        # the dominant kernel of the step is the one the headline roofline describes
-        if b_ms > k_ms:
-            roofline, bwd = {**roofline, **bwd}, {k: roofline[k] for k in bwd}
-        roofline["other_kernel"] = bwd
+        return float(np.mean([a.elapsed_time(b_) for a, b_ in evs]))
+
+    peak, peak_src = measured_peak_gbs()
+
+    def roof(name, ms_, bytes_per_sample):
+        gbs = bytes_per_sample * B * T / (ms_ * 1e-3) / 1e9
+        return {"kernel": name, "achieved": gbs, "frac": gbs / peak, "algorithmic_bytes_per_sample": bytes_per_sample, "kernel_ms": ms_}
+
+    k_ms = time_kernel(lambda: lib.pystl_b200_eval_forward(cf.ptr(), signal.data_ptr(), B, T, D, out.data_ptr(), None, stream.cuda_stream))
+    bytes_fwd = algorithmic_bytes_per_sample(cfg, False)
+    fwd_roof = roof(f"{tier}:forward<{sem_name}>", k_ms, bytes_fwd)
+    roofline = {"bound": "hbm", **fwd_roof, "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src}
+    if with_bwd:
+        scale = 1.0 / (world * n_valid)
+        b_ms = time_kernel(lambda: lib.pystl_b200_eval_backward(cf.ptr(), signal.data_ptr(), B, T, D, None, scale, grad.data_ptr(), stream.cuda_stream))
+        bwd_roof = roof(f"{tier}:backward<{sem_name}>", b_ms, algorithmic_bytes_per_sample(cfg, True) - bytes_fwd)
+        if launches_per_step == 1:
+            # the step's only kernel: reads the signal once, writes the trace and the gradient
+            vg_ms = time_kernel(lambda: lib.pystl_b200_eval_value_and_grad(
+                cf.ptr(), signal.data_ptr(), B, T, D, None, scale, out.data_ptr(), None, grad.data_ptr(), stream.cuda_stream))
+            vg = roof(f"{tier}:value_and_grad<{sem_name}>", vg_ms, bytes_fwd + 4 * D)
+            roofline = {**roofline, **vg, "other_kernels": [fwd_roof, bwd_roof]}
+        else:
+            dom, oth = (bwd_roof, fwd_roof) if b_ms > k_ms else (fwd_roof, bwd_roof)
+            roofline = {**roofline, **dom, "other_kernels": [oth]}
 
     # end to end through the public API with pinned host buffers
     e2e = None
@@ -358,11 +357,8 @@ def run_b200(args) -> None:
         def e2e_step():
             x = host.to(dev, non_blocking=True)
             if with_bwd:
-                x.requires_grad_(True)
-                rho = sem.robustness_trace(phi, x)
-                loss = rho.mean() if C_out == 1 else (rho.pos + rho.neg).mean()
-                loss.backward()
-                return float(loss.detach().cpu()), x.grad
+                loss, g_ = sem.mean_robustness_and_grad(phi, x)
+                return float(loss.cpu()), g_
             return float(sem.mean_robustness(phi, x).cpu()), None
 
         try:
@@ -409,6 +405,7 @@ def run_b200(args) -> None:
                 "pass": "forward+backward" if with_bwd else "forward",
                 "l2": "inputs larger than L2 (no flush needed)" if B * T * D * 4 > (1 << 28) else "input fits L2 (CPU-comparison config)",
                 "plan": plan,
+                "tier": tier,
             },
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -7,9 +7,9 @@ python bench.py --workload $w ${FLAGS} --steps 10 --no-cpu --no-e2e > gpurun_out
 python - <<PY
 import json
 try:
-    d=json.load(open('gpurun_out/sw_$w.json')); r=d['roofline']; o=r.get('other_kernel')
+    d=json.load(open('gpurun_out/sw_$w.json')); r=d['roofline']
     s='$w nt=$nt minb=$mb %.3e samples/s | %s %.3f ms frac %.3f' % (d['value'], r['kernel'], r['kernel_ms'], r['frac'])
-    if o: s+=' | %s %.3f ms frac %.3f' % (o['kernel'], o['kernel_ms'], o['frac'])
+    for o in r.get('other_kernels', []): s+=' | %s %.3f ms frac %.3f' % (o['kernel'], o['kernel_ms'], o['frac'])
     print(s)
 except Exception as e:
     print('$w nt=$nt minb=$mb FAILED', open('gpurun_out/sw_$w.err').read()[-300:])

@@ -152,6 +152,24 @@ int pystl_b200_eval_backward(const pystl_formula_t* formula, const float* signal
                              int64_t T, int32_t D, const float* grad_out, float grad_scale,
                              float* grad_signal, void* stream);
 
+/* Robustness AND gradient in one pass over the signal: what Formula.evaluate_with_grad
+ * (pystl/api.py:64-78 -> DgmsrSemantics.evaluate_with_grad, pystl/semantics/dgmsr.py:120-274)
+ * returns, for every t of every trace at once.  out / mean_acc as in eval_forward,
+ * grad_out / grad_scale / grad_signal as in eval_backward.  Formulas on the fused tier run
+ * ONE kernel (the signal is read once, no value is recomputed); the others run the forward
+ * and the backward kernel back to back. */
+int pystl_b200_eval_value_and_grad(const pystl_formula_t* formula, const float* signal, int64_t B,
+                                   int64_t T, int32_t D, const float* grad_out, float grad_scale,
+                                   float* out, double* mean_acc, float* grad_signal, void* stream);
+
+/* Fused tier (run-time specialised kernels, pystl_b200/csrc/codegen.cpp + jit.cpp).
+ * precompile: generate + compile the kernel of (formula, T, D) into the on-disk cubin cache;
+ * needs no GPU.  PYSTL_E_UNSUPPORTED: this formula runs on the interpreter tier.
+ * source: the generated CUDA source (inspection); returns its length. */
+int pystl_b200_fused_precompile(const pystl_formula_t* formula, int64_t T, int32_t D, int32_t backward);
+int pystl_b200_fused_source(const pystl_formula_t* formula, int64_t T, int32_t D, int32_t backward,
+                            char* buf, int32_t len);
+
 #ifdef __cplusplus
 }
 #endif

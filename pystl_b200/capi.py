@@ -89,6 +89,7 @@ EXPORTS = (
     "pystl_b200_plan",
     "pystl_b200_eval_forward",
     "pystl_b200_eval_backward",
+    "pystl_b200_eval_value_and_grad",
     "pystl_b200_fused_precompile",
     "pystl_b200_fused_source",
 )
@@ -122,6 +123,12 @@ def declare(lib: C.CDLL, prefix: str = "pystl_b200") -> None:
         f.argtypes = [
             C.POINTER(Formula), C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
             C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+        ]
+        f = lib.pystl_b200_eval_value_and_grad
+        f.restype = C.c_int
+        f.argtypes = [
+            C.POINTER(Formula), C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+            C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         ]
         f = lib.pystl_b200_fused_precompile
         f.restype = C.c_int

@@ -81,8 +81,12 @@ struct Gen {
   int smem_floats = 0;
   int red_floats = 0;
   int n_stages = 0;
+  bool bwd = false;                // generating the backward kernel
+  std::vector<int> bscr_off;       // per instruction: scratch of the adjoint window
+  int fix_off = 0, flag_off = 0;   // smooth backward: exact-scatter plane, per-window lost flags
 
-  Gen(const Lowered& l, int D_, int nt_, int minb_) : lw(l), P(l.prog), D(D_), nt(nt_), minb(minb_) {}
+  Gen(const Lowered& l, int D_, int nt_, int minb_, bool bwd_) : lw(l), P(l.prog), D(D_), nt(nt_), minb(minb_), bwd(bwd_) {}
+  int kw() const { return P.sem == SEM_SMOOTH ? 1 : 2; }  // words of an adjoint coefficient
 
   int vw() const { return P.sem == SEM_CUMULATIVE ? 2 : 1; }
   int aw() const { return (P.sem == SEM_CLASSIC || P.sem == SEM_SMOOTH) ? 1 : 2; }
@@ -90,6 +94,10 @@ struct Gen {
   bool supported(std::string* why) const {
     if (D < 1) {
       *why = "bad D";
+      return false;
+    }
+    if (bwd && !(P.sem == SEM_SMOOTH || P.sem == SEM_AGM || P.sem == SEM_DGMSR)) {
+      *why = "the classic gradient runs on the interpreter tier";
       return false;
     }
     for (int i = 0; i < P.n_instr; ++i) {
@@ -118,31 +126,57 @@ struct Gen {
       max_level = std::max(max_level, l);
     }
     n_stages = max_level + 1;
-    // shared memory: [reduction scratch][region 0][region 1]; windows of level l use region l & 1
+    // shared memory: [reduction scratch][persistent][region 0][region 1].  Forward windows of level
+    // l use region l & 1 (the barrier of level l+1 separates the readers of level l from the
+    // writers of level l+2); the adjoint windows of level l use region (l+1) & 1 for the same
+    // reason, walking the levels downwards.
     const int nw = nt / 32;
     red_floats = roundup(std::max(2 * std::max(P.n_preds, 1), 1) * nw, 32) + 32;  // + the mean reduction's own 32 floats
-    std::vector<int> used(max_level + 2, 0);
+    bscr_off.assign(P.n_instr, 0);
+    int persist = 0;
+    const bool stash_persists = bwd && P.sem == SEM_SMOOTH;  // the exact scatter re-reads the operands
+    if (stash_persists) {
+      for (int i = 0; i < P.n_instr; ++i)
+        if (is_window(P.ins[i])) {
+          stash_off[i] = red_floats + persist;
+          persist += 8 * nt;
+        }
+      fix_off = red_floats + persist;
+      persist += 8 * nt;
+      flag_off = red_floats + persist;
+      persist += roundup(P.n_instr, 4);
+    }
+    std::vector<int> used(max_level + 3, 0), bused(max_level + 3, 0);
     for (int i = 0; i < P.n_instr; ++i) {
       const TInstr& in = P.ins[i];
       if (!is_window(in)) continue;
       const int l = ins_level[i];
+      const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
       scr_off[i] = used[l];
-      used[l] += win_floats(aw(), clamp_off(in.a, 8 * nt), clamp_off(in.b, 8 * nt), nt);
-      if (P.sem == SEM_SMOOTH) {
+      used[l] += win_floats(aw(), a, b, nt);
+      if (P.sem == SEM_SMOOTH && !stash_persists) {
         stash_off[i] = used[l];
         used[l] += 8 * nt;
       }
+      if (bwd) {
+        bscr_off[i] = bused[l];
+        bused[l] += win_floats(kw(), -b, -a, nt);
+      }
     }
     int reg[2] = {0, 0};
-    for (int l = 0; l <= max_level; ++l) reg[l & 1] = std::max(reg[l & 1], used[l]);
-    const int base0 = red_floats, base1 = red_floats + reg[0];
+    for (int l = 0; l <= max_level; ++l) {
+      reg[l & 1] = std::max(reg[l & 1], used[l]);
+      reg[(l + 1) & 1] = std::max(reg[(l + 1) & 1], bused[l]);
+    }
+    const int base0 = red_floats + persist, base1 = base0 + reg[0];
     for (int i = 0; i < P.n_instr; ++i) {
       if (!is_window(P.ins[i])) continue;
-      const int base = (ins_level[i] & 1) ? base1 : base0;
-      scr_off[i] += base;
-      if (stash_off[i] >= 0) stash_off[i] += base;
+      const int l = ins_level[i];
+      scr_off[i] += (l & 1) ? base1 : base0;
+      if (stash_off[i] >= 0 && !stash_persists) stash_off[i] += (l & 1) ? base1 : base0;
+      bscr_off[i] += ((l + 1) & 1) ? base1 : base0;
     }
-    smem_floats = red_floats + reg[0] + reg[1];
+    smem_floats = base1 + reg[1];
   }
 
   // expression of operand j of instruction `in` at sample i
@@ -291,9 +325,11 @@ struct Gen {
     const int s = in.src[0], d = in.dst;
     o.line("// window %d, phase 2: combine -> value", i);
     o.line("V v%d[8];", d);
+    if (bwd) o.line("R%d::A acc%d[8];  // kept for the adjoint", i, i);
     o.line("if (live) {");
     o.indent++;
-    o.line("R%d::A acc[8];", i);
+    if (bwd) o.line("R%d::A (&acc)[8] = acc%d;", i, i);
+    else o.line("R%d::A acc[8];", i);
     o.line("W%d::phase2(smem + %d, c.tid, x%d, sf%d, pf%d, acc);", i, scr_off[i], i, i, i);
     o.line("fin8<R%d, %d, %d, VW>(c, rp%d, acc, v%d);", i, a, b, i, d);
     if (P.sem == SEM_SMOOTH)
@@ -345,25 +381,14 @@ struct Gen {
     }
   }
 
-  std::string forward() {
-    plan();
-    plan_bounds();
-    o.indent = 0;
-    o.line("// generated by pystl_b200/csrc/codegen.cpp -- forward kernel of one formula (fused tier)");
-    o.line("#include \"fused_rt.cuh\"");
-    o.line("using namespace pystl;");
-    o.line("using namespace pystl::fused;");
-    o.line("constexpr int NT = %d, D = %d, SEM = %s, VW = Tr<SEM>::VW;", nt, D, sem_name(P.sem));
-    o.line("typedef Vec<VW> V;");
-    o.line("PF_KERNEL(NT, %d) pystl_fused(const PF_GRID_CONSTANT TileProgram P, const PF_GRID_CONSTANT TileGeom g,", minb);
-    o.line("    const float* __restrict__ signal, float* __restrict__ out, double* __restrict__ mean_acc) {");
-    o.indent = 1;
+  void emit_forward_body() {
     o.line("PF_DYN_SMEM(smem);");
     o.line("const TC c = tile_begin<NT>(P, g, smem);");
     o.line("const RP rp = c.rp;");
     o.line("float* red = smem;");
     o.line("const bool live = alive(c);  // threads past the horizon only keep the shared planes consistent");
     o.line("(void)red; (void)rp;");
+    if (bwd && P.sem == SEM_SMOOTH) o.line("if (c.tid < %d) reinterpret_cast<int*>(smem + %d)[c.tid] = 0;  // lost flags", P.n_instr, flag_off);
     emit_predicates();
     for (int st = 0; st < n_stages; ++st) {
       o.line("// ================= stage %d", st);
@@ -381,9 +406,201 @@ struct Gen {
         }
       if (any) o.line("simt::sync();");
     }
+  }
+
+  void emit_header(const char* what) {
+    o.indent = 0;
+    o.line("// generated by pystl_b200/csrc/codegen.cpp -- %s kernel of one formula (fused tier)", what);
+    o.line("#include \"fused_rt.cuh\"");
+    o.line("using namespace pystl;");
+    o.line("using namespace pystl::fused;");
+    o.line("constexpr int NT = %d, D = %d, SEM = %s, VW = Tr<SEM>::VW;", nt, D, sem_name(P.sem));
+    o.line("typedef Vec<VW> V;");
+  }
+
+  std::string forward() {
+    plan();
+    plan_bounds();
+    emit_header("forward");
+    o.line("PF_KERNEL(NT, %d) pystl_fused(const PF_GRID_CONSTANT TileProgram P, const PF_GRID_CONSTANT TileGeom g,", minb);
+    o.line("    const float* __restrict__ signal, float* __restrict__ out, double* __restrict__ mean_acc) {");
+    o.indent = 1;
+    emit_forward_body();
     o.line("float part = 0.f;");
     o.line("if (live) part = store_root<SEM, %s>(c, g.T, v%d, out);", P.root_neg ? "true" : "false", (int)P.root);
     o.line("if (mean_acc) block_sum_to<NT>(c, part, mean_acc, smem + %d);", red_floats - 32);
+    o.indent = 0;
+    o.line("}");
+    return o.s;
+  }
+
+  // ---------------------------------------------------------------- backward
+  void nary_bwd(int i) {
+    const TInstr& in = P.ins[i];
+    const int n = in.nsrc, d = in.dst;
+    o.line("// adjoint of the n-ary %s %d", in.mode == MODE_AND ? "And" : "Or", i);
+    o.line("if (live) {");
+    o.indent++;
+    std::string w = "const float w[" + std::to_string(n) + "] = {";
+    for (int j = 0; j < n; ++j) {
+      char b[64];
+      snprintf(b, sizeof(b), "%sP.ins[%d].w[%d]", j ? ", " : "", i, j);
+      w += b;
+    }
+    o.line("%s};", w.c_str());
+    o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) {");
+    o.indent++;
+    std::string a = "const float a[" + std::to_string(n) + "] = {";
+    for (int j = 0; j < n; ++j) {
+      char b[64];
+      snprintf(b, sizeof(b), "%s%sv%d[i].x[0]", j ? ", " : "", ((in.negmask >> j) & 1) ? "-" : "", (int)in.src[j]);
+      a += b;
+    }
+    o.line("%s};", a.c_str());
+    o.line("float ga[%d];", n);
+    o.line("nary1_bwd<SEM, %s, %d>(rp, g%d[i], v%d[i].x[0], a, w, P.ins[%d].sw, ga);", mode_name(in.mode), n, d, d, i);
+    for (int j = 0; j < n; ++j) o.line("g%d[i] %s ga[%d];", (int)in.src[j], ((in.negmask >> j) & 1) ? "-=" : "+=", j);
+    o.indent--;
+    o.line("}");
+    o.indent--;
+    o.line("}");
+  }
+
+  void win_adj_a(int i) {
+    const TInstr& in = P.ins[i];
+    const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
+    const int d = in.dst;
+    o.line("// adjoint of window %d, phase A: per-output coefficients, chunk scans -> shared", i);
+    o.line("using BW%d = WinOp<SumOp<%d>, %d, %d, NT>;", i, kw(), -b, -a);
+    o.line("static_assert(BW%d::FLOATS == %d, \"host / device scratch layout mismatch\");", i, win_floats(kw(), -b, -a, nt));
+    o.line("Vec<%d> k%d[8], ksf%d[8], kpf%d[8];", kw(), i, i, i);
+    if (P.sem == SEM_SMOOTH) o.line("unsigned lost%d = 0;", i);
+    o.line("BW%d::fill_guards(smem + %d, c.tid);", i, bscr_off[i]);
+    o.line("if (live) {");
+    o.indent++;
+    if (P.sem == SEM_SMOOTH) {
+      o.line("lost%d = smooth_adj_coeff<%s, %d, %d>(c, g%d, acc%d, k%d);", i, mode_name(in.mode), a, b, d, i, i);
+      o.line("if (lost%d) reinterpret_cast<volatile int*>(smem + %d)[%d] = 1;", i, flag_off, i);
+    } else {
+      o.line("gm_adj_coeff<SEM, %s, %d, %d>(c, rp, g%d, v%d, k%d);", mode_name(in.mode), a, b, d, d, i);
+    }
+    o.line("BW%d::phase1(smem + %d, c.tid, k%d, ksf%d, kpf%d);", i, bscr_off[i], i, i, i);
+    o.indent--;
+    o.line("} else {");
+    o.indent++;
+    o.line("BW%d::phase1_dead(smem + %d, c.tid);", i, bscr_off[i]);
+    o.indent--;
+    o.line("}");
+  }
+
+  void win_adj_b(int i) {
+    const TInstr& in = P.ins[i];
+    const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
+    const bool neg = in.negmask & 1;
+    const int s = in.src[0], d = in.dst;
+    o.line("// adjoint of window %d, phase B: window sum of the coefficients x per-input factor", i);
+    o.line("if (live) {");
+    o.indent++;
+    o.line("Vec<%d> w[8];", kw());
+    o.line("BW%d::phase2(smem + %d, c.tid, k%d, ksf%d, kpf%d, w);", i, bscr_off[i], i, i, i);
+    if (P.sem == SEM_SMOOTH) o.line("smooth_adj_apply<%s>(w, x%d, g%d);", neg ? "true" : "false", i, s);
+    else o.line("gm_adj_apply<SEM, %s, %s>(c, rp, w, v%d, g%d);", mode_name(in.mode), neg ? "true" : "false", s, s);
+    o.indent--;
+    o.line("}");
+    if (P.sem == SEM_SMOOTH) {
+      o.line("if (reinterpret_cast<volatile int*>(smem + %d)[%d]) {  // rare: exact scatter of the outputs whose shifted sum underflowed", flag_off, i);
+      o.indent++;
+      o.line("float* fix = smem + %d;", fix_off);
+      o.line("{ const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; store8(fix, c.tid, z); }");
+      o.line("simt::sync();");
+      o.line("if (lost%d) smooth_adj_scatter<%s, %d, %d, NT>(c, rp, lost%d, g%d, v%d, smem + %d, fix);", i, mode_name(in.mode), a, b, i, d, d,
+             stash_off[i]);
+      o.line("simt::sync();");
+      o.line("{ float t[8]; load8(fix, c.tid, t); _Pragma(\"unroll\") for (int i = 0; i < 8; ++i) g%d[i] %s t[i]; }", s, neg ? "-=" : "+=");
+      o.line("simt::sync();");
+      o.indent--;
+      o.line("}");
+    }
+  }
+
+  std::string backward() {
+    plan();
+    plan_bounds();
+    emit_header("backward (value and gradient)");
+    o.line("PF_KERNEL(NT, %d) pystl_fused(const PF_GRID_CONSTANT TileProgram P, const PF_GRID_CONSTANT TileGeom g,", minb);
+    o.line("    const float* __restrict__ signal, const float* __restrict__ grad_out, float scale, float* __restrict__ grad_signal,");
+    o.line("    float* __restrict__ out, double* __restrict__ mean_acc) {");
+    o.indent = 1;
+    emit_forward_body();
+    o.line("// ================= value (optional) and cotangent");
+    o.line("if (out) {");
+    o.indent++;
+    o.line("float part = 0.f;");
+    o.line("if (live) part = store_root<SEM, %s>(c, g.T, v%d, out);", P.root_neg ? "true" : "false", (int)P.root);
+    o.line("if (mean_acc) block_sum_to<NT>(c, part, mean_acc, smem + %d);", red_floats - 32);
+    o.indent--;
+    o.line("}");
+    std::vector<char> has(kMaxSlots, 0);
+    has[P.root] = 1;
+    for (int i = 0; i < P.n_instr; ++i) {
+      has[P.ins[i].dst] = 1;
+      for (int j = 0; j < P.ins[i].nsrc; ++j) has[P.ins[i].src[j]] = 1;
+    }
+    for (int q = 0; q < P.n_preds; ++q) has[P.preds[q].dst] = 1;
+    for (int sl = 0; sl < kMaxSlots; ++sl)
+      if (has[sl]) o.line("float g%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", sl);
+    o.line("if (live) root_cotangent<%s>(c, g.T, grad_out, scale, g%d);", P.root_neg ? "true" : "false", (int)P.root);
+    for (int st = n_stages - 1; st >= 0; --st) {
+      o.line("// ================= adjoint stage %d", st);
+      for (int i = P.n_instr - 1; i >= 0; --i)
+        if (ins_level[i] == st && !is_window(P.ins[i])) nary_bwd(i);
+      bool any = false;
+      for (int i = P.n_instr - 1; i >= 0; --i)
+        if (ins_level[i] == st && is_window(P.ins[i])) {
+          win_adj_a(i);
+          any = true;
+        }
+      if (any) o.line("simt::sync();");
+      for (int i = P.n_instr - 1; i >= 0; --i)
+        if (ins_level[i] == st && is_window(P.ins[i])) win_adj_b(i);
+    }
+    o.line("// ================= gradient of the signal: chain rule through the affine predicates");
+    o.line("if (live) {");
+    o.indent++;
+    if (D <= 8) {
+      o.line("float gr[8][D];");
+      o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) {");
+      o.indent++;
+      for (int d = 0; d < D; ++d) {
+        std::string e;
+        for (int q = 0; q < P.n_preds; ++q)
+          for (int k = 0; k < P.preds[q].n_terms; ++k)
+            if (P.preds[q].ch[k] == d) {
+              char b[96];
+              snprintf(b, sizeof(b), "%sP.preds[%d].coeff[%d] * g%d[i]", e.empty() ? "" : " + ", q, k, (int)P.preds[q].dst);
+              e += b;
+            }
+        o.line("gr[i][%d] = %s;", d, e.empty() ? "0.f" : e.c_str());
+      }
+      o.indent--;
+      o.line("}");
+      o.line("store_grad_rows<D>(c, g.T, gr, grad_signal);");
+    } else {
+      for (int d = 0; d < D; ++d) {
+        std::string e;
+        for (int q = 0; q < P.n_preds; ++q)
+          for (int k = 0; k < P.preds[q].n_terms; ++k)
+            if (P.preds[q].ch[k] == d) {
+              char b[96];
+              snprintf(b, sizeof(b), "%sP.preds[%d].coeff[%d] * g%d[i]", e.empty() ? "" : " + ", q, k, (int)P.preds[q].dst);
+              e += b;
+            }
+        o.line("{ float gx[8]; _Pragma(\"unroll\") for (int i = 0; i < 8; ++i) gx[i] = %s; store_grad_channel(c, g.T, D, %d, gx, grad_signal); }",
+               e.empty() ? "0.f" : e.c_str(), d);
+      }
+    }
+    o.indent--;
+    o.line("}");
     o.indent = 0;
     o.line("}");
     return o.s;
@@ -459,14 +676,13 @@ int fused_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force
 }
 
 int fused_generate(const Lowered& lw, int D, int nt, int minb, bool backward, FusedSource* out, char* msg, int msg_len) {
-  Gen g(lw, D, nt, minb);
+  Gen g(lw, D, nt, minb, backward);
   std::string why;
-  if (backward) why = "the backward pass runs on the interpreter tier";
-  if (!why.empty() || !g.supported(&why)) {
+  if (!g.supported(&why)) {
     if (msg && msg_len > 0) snprintf(msg, msg_len, "%s", why.c_str());
     return PYSTL_E_UNSUPPORTED;
   }
-  out->source = g.forward();
+  out->source = backward ? g.backward() : g.forward();
   out->smem_floats = g.smem_floats;
   out->nt = nt;
   out->minb = minb;

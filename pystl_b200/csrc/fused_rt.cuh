@@ -20,7 +20,7 @@
 // This header is written in plain SIMT style.  The CPU test tier compiles it with g++ against
 // tests/emu/simt_host.h (fibers); nothing in the product loads that build.
 #pragma once
-#include "tile_eval.h"
+#include "tile_bwd.h"
 
 #if defined(__CUDACC__)
 #define PF_DEV __device__ __forceinline__
@@ -613,6 +613,154 @@ PF_DEV void block_sum_to(const TC& c, float part, double* __restrict__ acc, floa
     for (int w = 0; w < NT / 32; ++w) tot += (double)red[w];
     simt::atomic_add(acc, tot);
   }
+}
+
+// ====================================================================== backward pass
+// The generated backward kernel first runs the forward program (values stay in registers: nothing
+// was saved by the forward launch), then walks it in reverse.  Adjoints are register arrays
+// g<slot>[8]; the adjoint of a window is a backward-looking window SUM (same WinOp, offsets
+// [-b, -a]) of a per-output coefficient, times a per-input factor (tile_bwd.h: Adj<SEM, MODE>).
+
+// clipped sample count of the forward window of output p (api.py:49-54)
+template <int FA, int FB>
+PF_DEV float win_count(const TC& c, int p) {
+  int hi = p + FB;
+  if (hi > c.nlive - 1) hi = c.nlive - 1;
+  const int n = hi - (p + FA) + 1;
+  return (float)(n > 0 ? n : 0);
+}
+
+// cotangent of the root for the thread's samples: grad_out (or the constant `scale`) for the tile
+// positions below p_hi whose output exists, zero elsewhere
+template <bool NEG>
+PF_DEV void root_cotangent(const TC& c, long long T, const float* __restrict__ grad_out, float scale, float (&g)[8]) {
+  const float* src = grad_out ? grad_out + (c.b * T + c.origin + c.p0) : nullptr;
+  int hi = c.p_hi;
+  if (hi > c.last_ok + 1) hi = c.last_ok + 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v = 0.f;
+    if (c.p0 + i < hi) v = src ? src[i] : scale;
+    g[i] = NEG ? -v : v;
+  }
+}
+
+// ---- window adjoint, phase A: per-output coefficients k[8] (KW words)
+// smooth: d out_t / d x_q = xhat_q / S_t with the forward's block-shifted xhat and S: k_t = g_t / S_t.
+// Outputs whose shifted sum lost its precision (S_t < 2^-100, recomputed exactly by the forward
+// pass) are left out here and scattered exactly afterwards (lostmask).
+template <int MODE, int FA, int FB>
+PF_DEV unsigned smooth_adj_coeff(const TC& c, const float (&g)[8], const Vec<1> (&S)[8], Vec<1> (&k)[8]) {
+  unsigned lost = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool has = g[i] != 0.f && c.p0 + i + FA <= c.nlive - 1;
+    const bool ok = S[i].x[0] >= kSmoothTiny;
+    k[i].x[0] = (has && ok) ? g[i] / S[i].x[0] : 0.f;
+    if (has && !ok) lost |= 1u << i;
+  }
+  return lost;
+}
+template <int SEM, int MODE, int FA, int FB>
+PF_DEV void gm_adj_coeff(const TC& c, const RP& rp, const float (&g)[8], const Vec<1> (&o)[8], Vec<2> (&k)[8]) {
+  using AD = Adj<SEM, MODE>;
+  const bool interior = c.p0 + 7 + FB <= c.nlive - 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float n = interior ? (float)(FB - FA + 1) : win_count<FA, FB>(c, c.p0 + i);
+    bool lost;
+    k[i] = AD::out_coeff(g[i], o[i].x[0], n > 0.f ? n : 1.f, rp, lost);
+    if (!(g[i] != 0.f) || !(n > 0.f)) k[i] = Vec<2>{{0.f, 0.f}};
+  }
+}
+
+// ---- window adjoint, phase B: g_src[q] += sign * in_factor(x_q) * (window sum of k)[q]
+template <bool NEG>
+PF_DEV void smooth_adj_apply(const Vec<1> (&w)[8], const Vec<1> (&xhat)[8], float (&gs)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float d = w[i].x[0] * xhat[i].x[0];  // xhat is 0 past the horizon
+    gs[i] += NEG ? -d : d;
+  }
+}
+template <int SEM, int MODE, bool NEG>
+PF_DEV void gm_adj_apply(const TC& c, const RP& rp, const Vec<2> (&w)[8], const Vec<1> (&v)[8], float (&gs)[8]) {
+  using AD = Adj<SEM, MODE>;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float x = NEG ? -v[i].x[0] : v[i].x[0];
+    const float d = (c.p0 + i < c.nlive) ? AD::in_factor(w[i], x, 1.f, rp) : 0.f;
+    gs[i] += NEG ? -d : d;
+  }
+}
+
+// smooth: exact scatter of the outputs in `lostmask` (rare path, entered by the whole CTA when any
+// thread has one).  vplane: staged operand values (after negation); fix: zeroed plane.
+template <int MODE, int FA, int FB, int NT>
+PF_DEV void smooth_adj_scatter(const TC& c, const RP& rp, unsigned lostmask, const float (&g)[8], const Vec<1> (&o)[8],
+                               const float* vplane, float* fix) {
+  using AD = Adj<SEM_SMOOTH, MODE>;
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    if (!((lostmask >> i) & 1)) continue;
+    float gi = 0.f, oi = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j == i) {
+        gi = g[j];
+        oi = o[j].x[0];
+      }
+    const int p = c.p0 + i;
+    int lo = p + FA, hi = p + FB;
+    if (hi > c.nlive - 1) hi = c.nlive - 1;
+    if (hi > 8 * NT - 1) hi = 8 * NT - 1;
+    for (int q = lo; q <= hi; ++q) simt::atomic_add(&fix[pidx(q)], gi * AD::pair_weight(oi, vplane[pidx(q)], rp));
+  }
+}
+
+// ---- n-ary And / Or of one sample, backward: ga[j] = d out / d a_j * g
+template <int SEM, int MODE, int N>
+PF_DEV void nary1_bwd(const RP& rp, float g, float o, const float (&a)[N], const float (&w)[N], float sw, float (&ga)[N]) {
+  using AD = Adj<SEM, MODE>;
+  if constexpr (SEM == SEM_SMOOTH) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) ga[j] = (g != 0.f) ? g * AD::pair_weight(o, a[j], rp) : 0.f;
+  } else {
+    bool lost;
+    Vec<AD::KW> k = AD::out_coeff(g, o, sw, rp, lost);
+#pragma unroll
+    for (int j = 0; j < N; ++j) ga[j] = (g != 0.f) ? AD::in_factor(k, a[j], w[j], rp) : 0.f;
+  }
+}
+
+// ---- gradient rows -> HBM: the thread's 8 rows of D channels, positions inside [p_lo, p_hi)
+template <int D>
+PF_DEV void store_grad_rows(const TC& c, long long T, const float (&gr)[8][D], float* __restrict__ grad_signal) {
+  float* dst = grad_signal + ((c.b * T + c.origin + c.p0) * (long long)D);
+  if (c.p0 >= c.p_lo && c.p0 + 8 <= c.p_hi && ((u64)dst & 15ull) == 0ull) {
+    F4* d4 = reinterpret_cast<F4*>(dst);
+#pragma unroll
+    for (int k = 0; k < 2 * D; ++k) {
+      F4 q;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) q.v[e] = gr[(4 * k + e) / D][(4 * k + e) % D];
+      d4[k] = q;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c.p0 + i >= c.p_lo && c.p0 + i < c.p_hi) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) dst[i * D + d] = gr[i][d];
+      }
+  }
+}
+// wide signals (D > 8): one channel at a time
+PF_DEV void store_grad_channel(const TC& c, long long T, int D, int ch, const float (&gx)[8], float* __restrict__ grad_signal) {
+  float* dst = grad_signal + ((c.b * T + c.origin + c.p0) * (long long)D) + ch;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (c.p0 + i >= c.p_lo && c.p0 + i < c.p_hi) dst[(long long)i * D] = gx[i];
 }
 
 }  // namespace fused

@@ -176,16 +176,38 @@ extern "C" int pystl_b200_eval_forward(const pystl_formula_t* f, const float* si
   }
 }
 
-extern "C" int pystl_b200_eval_backward(const pystl_formula_t* f, const float* signal, int64_t B, int64_t T, int32_t D,
-                                        const float* grad_out, float grad_scale, float* grad_signal, void* stream) {
+// value (optional) and gradient through ONE fused kernel; PYSTL_E_UNSUPPORTED: not on the fused tier
+static int fused_value_and_grad(const pystl_formula_t* f, const float* signal, int64_t B, int64_t T, int32_t D,
+                                const float* grad_out, float grad_scale, float* grad_signal, float* out, double* mean_acc,
+                                cudaStream_t stream) {
   Lowered lw;
   TileGeom g;
-  int rc = prepare(f, B, T, D, true, &lw, &g);
+  FusedSource fs;
+  int rc = fused_prepare(f, B, T, D, true, &lw, &g, &fs);
+  if (rc) return rc;
+  if (B == 0 || T == 0) return PYSTL_OK;
+  if (!signal || !grad_signal) return set_err(PYSTL_E_INVALID, "signal / grad_signal is NULL");
+  void* args[] = {(void*)&lw.prog, (void*)&g,           (void*)&signal, (void*)&grad_out,
+                  (void*)&grad_scale, (void*)&grad_signal, (void*)&out,    (void*)&mean_acc};
+  return fused_launch(lw, g, fs, args, stream);
+}
+
+extern "C" int pystl_b200_eval_backward(const pystl_formula_t* f, const float* signal, int64_t B, int64_t T, int32_t D,
+                                        const float* grad_out, float grad_scale, float* grad_signal, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int tier = tier_mode();
+  int rc;
+  if (tier != TIER_INTERP) {
+    rc = fused_value_and_grad(f, signal, B, T, D, grad_out, grad_scale, grad_signal, nullptr, nullptr, s);
+    if (rc != PYSTL_E_UNSUPPORTED || tier == TIER_FUSED) return rc;
+  }
+  Lowered lw;
+  TileGeom g;
+  rc = prepare(f, B, T, D, true, &lw, &g);
   if (rc) return rc;
   if (B == 0 || T == 0) return PYSTL_OK;
   if (!signal || !grad_signal) return set_err(PYSTL_E_INVALID, "signal / grad_signal is NULL");
   if (g.nt % 32 != 0) return set_err(PYSTL_E_INVALID, "CTA size %d is not a multiple of 32", g.nt);
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int el = (int)sizeof(g_err);
   switch (lw.prog.sem) {
     case SEM_CLASSIC: return launch_bwd_sem<SEM_CLASSIC>(lw, g, signal, grad_out, grad_scale, grad_signal, s, g_err, el);
@@ -194,4 +216,23 @@ extern "C" int pystl_b200_eval_backward(const pystl_formula_t* f, const float* s
     case SEM_DGMSR: return launch_bwd_sem<SEM_DGMSR>(lw, g, signal, grad_out, grad_scale, grad_signal, s, g_err, el);
     default: return set_err(PYSTL_E_UNSUPPORTED, "no backward kernel for this semantics");
   }
+}
+
+// Robustness AND gradient in one pass over the signal (what Formula.evaluate_with_grad returns,
+// api.py:64-78, for every t at once): out / mean_acc as in eval_forward, grad_signal as in
+// eval_backward.  One fused kernel when the formula is on the fused tier (the signal is read
+// once, nothing is recomputed), otherwise the forward and the backward kernel back to back.
+extern "C" int pystl_b200_eval_value_and_grad(const pystl_formula_t* f, const float* signal, int64_t B, int64_t T, int32_t D,
+                                              const float* grad_out, float grad_scale, float* out, double* mean_acc,
+                                              float* grad_signal, void* stream) {
+  if (!out && B > 0 && T > 0) return set_err(PYSTL_E_INVALID, "out is NULL");
+  const int tier = tier_mode();
+  if (tier != TIER_INTERP) {
+    int rc = fused_value_and_grad(f, signal, B, T, D, grad_out, grad_scale, grad_signal, out, mean_acc,
+                                  reinterpret_cast<cudaStream_t>(stream));
+    if (rc != PYSTL_E_UNSUPPORTED || tier == TIER_FUSED) return rc;
+  }
+  int rc = pystl_b200_eval_forward(f, signal, B, T, D, out, mean_acc, stream);
+  if (rc) return rc;
+  return pystl_b200_eval_backward(f, signal, B, T, D, grad_out, grad_scale, grad_signal, stream);
 }

@@ -30,3 +30,15 @@ def all_reduce_mean(acc: torch.Tensor, *, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
     return acc[0] / acc[1]
+
+
+def all_reduce_count(n_local: float, device, *, group=None) -> float:
+    """Number of valid outputs over all ranks (the denominator of the sharded mean; its reciprocal
+    is the constant cotangent of the fused value-and-gradient kernel)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.tensor([n_local], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return float(t.item())
+    return float(n_local)

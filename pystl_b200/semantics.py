@@ -147,6 +147,39 @@ class _B200Semantics:
         acc[1] = float(sig.shape[0] * valid)
         return all_reduce_mean(acc, group=group)
 
+    def mean_robustness_and_grad(self, formula: Any, signal: Any, *, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``(mean robustness, d mean / d signal)`` in ONE pass over the signal.
+
+        The batched, all-``t`` counterpart of ``Formula.evaluate_with_grad`` (api.py:64-78): for
+        formulas on the fused tier a single kernel reads the signal once and writes the robustness
+        trace, its fused mean and the gradient (no forward recomputation); the cotangent of the
+        mean, ``1 / count``, is a constant and needs no tensor.  Sharded batches: ``count`` and the
+        mean are all-reduced over ``group``, the gradient needs no collective."""
+        from .distributed import all_reduce_mean, all_reduce_count
+
+        sig, squeeze, home = self._prepare(signal)
+        B, T, D = sig.shape
+        cf = self.compile(formula, D)
+        plan = self.plan(formula, T, D)
+        valid = 0 if plan["raises_always"] else max(T - plan["start_slack"], 0)
+        n_local = float(B * valid)
+        n_total = all_reduce_count(n_local, sig.device, group=group)
+        out = torch.empty((B, T, self.out_channels), dtype=torch.float32, device=sig.device)
+        acc = torch.zeros(2, dtype=torch.float64, device=sig.device)
+        grad = torch.empty_like(sig)
+        stream = torch.cuda.current_stream(sig.device).cuda_stream
+        with torch.cuda.device(sig.device):
+            rc = capi.lib().pystl_b200_eval_value_and_grad(
+                cf.ptr(), sig.data_ptr(), B, T, D, None, (1.0 / n_total) if n_total > 0 else 0.0,
+                out.data_ptr(), acc.data_ptr(), grad.data_ptr(), stream,
+            )
+        capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+        acc[1] = n_local
+        mean = all_reduce_mean(acc, group=group)
+        if home != grad.device:
+            grad = grad.to(home)
+        return mean, (grad[0] if squeeze else grad)
+
     def evaluate_formula(self, formula: Any, signal: Any, t: int = 0) -> Any:
         """``phi.evaluate(signal, sem, t)`` of the reference, for ``signal[T, D]`` or ``[B, T, D]``."""
         sig = torch.as_tensor(signal)

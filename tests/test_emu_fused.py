@@ -19,3 +19,29 @@ def test_forward(case):
     want = oracle_trace(case["spec"], case["sem"], case["kw"], sig)
     got = fused_emu_lib.eval_forward(from_spec(case["spec"]), case["sem"], sig, force_threads=case["threads"], **case["kw"])
     assert_parity(got, want, case["sem"], case["name"], scale=case["scale"])
+
+
+# ---------------------------------------------------------------------------- backward
+import numpy as np  # noqa: E402
+
+from fused_cases import backward_cases  # noqa: E402
+from test_emu_backward import check, grad_tol, oracle_grad  # noqa: E402
+
+BWD = [c for c in backward_cases(light=True) if c["sem"] != "classical"]
+
+
+@pytest.mark.parametrize("case", BWD, ids=[c["name"] for c in BWD])
+@pytest.mark.parametrize("cotangent", ["explicit", "constant"])
+def test_backward(case, cotangent):
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    B, T = sig.shape[:2]
+    if cotangent == "explicit":
+        g = rng.standard_normal((B, T)).astype(np.float32).astype(np.float64)
+        got = fused_emu_lib.eval_backward(from_spec(case["spec"]), case["sem"], sig, g, force_threads=case["threads"], **case["kw"])
+    else:
+        g = np.full((B, T), 0.25)
+        got = fused_emu_lib.eval_backward(from_spec(case["spec"]), case["sem"], sig, None, scale=0.25, force_threads=case["threads"], **case["kw"])
+    want = oracle_grad(case["spec"], case["sem"], case["kw"], sig, g)
+    rtol, atol = grad_tol(case["sem"], case["kw"])
+    check(got.astype(np.float64), want, case["sem"], case["name"], rtol, atol)

@@ -93,3 +93,83 @@ def test_mean_accumulator_matches():
         m = sem.mean_robustness(phi, x)
         out = sem.robustness_trace(phi, x)
     assert abs(float(m) - float(out.double().mean())) < 1e-6
+
+
+# ---------------------------------------------------------------------------- backward
+from fused_cases import backward_cases  # noqa: E402
+from test_emu_backward import check, grad_tol, oracle_grad  # noqa: E402
+
+BWD = [c for c in backward_cases() if c["sem"] != "classical"]
+
+
+def gpu_grad(spec, sem, kw, sig64, g64, which, threads=0, scale=None):
+    """grad_signal through the C ABI (explicit cotangent, or the constant `scale`)."""
+    from pystl_b200 import capi
+
+    s = create_semantics(sem, backend="b200", **kw)
+    x = torch.tensor(sig64, dtype=torch.float32, device="cuda")
+    B, T, D = x.shape
+    cf = s.compile(from_spec(spec), D)
+    grad = torch.full_like(x, -12345.0)
+    go = None if g64 is None else torch.tensor(g64, dtype=torch.float32, device="cuda").contiguous()
+    with tier(which, threads):
+        rc = capi.lib().pystl_b200_eval_backward(cf.ptr(), x.data_ptr(), B, T, D, None if go is None else go.data_ptr(),
+                                                 1.0 if scale is None else scale, grad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    torch.cuda.synchronize()
+    return grad.cpu().numpy().astype(np.float64)
+
+
+@pytest.mark.parametrize("case", BWD, ids=[c["name"] for c in BWD])
+def test_backward(case):
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    B, T = sig.shape[:2]
+    g = rng.standard_normal((B, T)).astype(np.float32).astype(np.float64)
+    rtol, atol = grad_tol(case["sem"], case["kw"])
+    got = gpu_grad(case["spec"], case["sem"], case["kw"], sig, g, "fused", case["threads"])
+    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"], rtol, atol)
+    got = gpu_grad(case["spec"], case["sem"], case["kw"], sig, None, "fused", case["threads"], scale=0.25)
+    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, np.full((B, T), 0.25)), case["sem"], case["name"] + "/const", rtol, atol)
+
+
+@pytest.mark.parametrize("cfg,sem,kw,shape", [
+    ("cfg2", "smooth", {"temperature": 1.0}, (1024, 4096, 2)),
+    ("cfg3", "agm", {}, (256, 8192, 2)),
+    ("cfg3", "dgmsr", {"eps": 1e-8, "p": 1}, (256, 8192, 2)),
+], ids=["cfg2", "cfg3-agm", "cfg3-dgmsr"])
+def test_value_and_grad_at_baseline_shapes(cfg, sem, kw, shape):
+    """One fused kernel == forward + backward of the interpreter tier, at the BASELINE trace lengths;
+    and the gradient of the mean sums to what the chain rule says (size-independent property)."""
+    g = torch.Generator(device="cuda").manual_seed(777)
+    x = torch.randn(shape, generator=g, device="cuda")
+    x[: shape[0] // 2] += 1.5
+    s = create_semantics(sem, backend="b200", **kw)
+    phi = from_spec(BASELINE_SPECS[cfg])
+    with tier("fused"):
+        mean_f, grad_f = s.mean_robustness_and_grad(phi, x)
+        out_f = s.robustness_trace(phi, x)
+    with tier("interp"):
+        xi = x.clone().requires_grad_(True)
+        out_i = s.robustness_trace(phi, xi)
+        out_i.mean().backward()
+    assert abs(float(mean_f) - float(out_f.double().mean())) < 1e-5
+    assert torch.allclose(out_f.double(), out_i.detach().double(), rtol=2e-5, atol=1e-5)
+    scale = 1.0 / out_f.numel()
+    err = (grad_f.double() - xi.grad.double()).abs().max().item()
+    assert err <= 4e-5 * scale + 2e-5 * xi.grad.abs().max().item(), err
+
+
+def test_smooth_extreme_dynamic_range_is_exact_on_the_fused_tier():
+    rng = np.random.default_rng(3)
+    sig = (rng.standard_normal((2, 300, 2)) * 5.0).astype(np.float32).astype(np.float64)
+    kw = {"temperature": 0.01}
+    rtol, atol = grad_tol("smooth", kw)
+    for cfg in ("cfg1", "cfg2"):
+        for threads in (0, 64):
+            x = torch.tensor(sig, dtype=torch.float32, device="cuda")
+            got = run(BASELINE_SPECS[cfg], "smooth", kw, x, "fused", threads).cpu().numpy()
+            assert_parity(got, oracle_trace(BASELINE_SPECS[cfg], "smooth", kw, sig), "smooth", cfg)
+            g = rng.standard_normal((2, 300)).astype(np.float32).astype(np.float64)
+            gb = gpu_grad(BASELINE_SPECS[cfg], "smooth", kw, sig, g, "fused", threads)
+            check(gb, oracle_grad(BASELINE_SPECS[cfg], "smooth", kw, sig, g), "smooth", cfg, rtol, atol)
