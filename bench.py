@@ -315,6 +315,7 @@ def run_b200(args) -> None:
     # kernels alone, CUDA events on the launching stream
     def time_kernel(fn) -> float:
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        capi.raise_for(fn(), lib.pystl_b200_last_error())  # warm-up (first use may compile the kernel)
         for a, b_ in evs:
             a.record(stream)
             capi.raise_for(fn(), lib.pystl_b200_last_error())

@@ -347,6 +347,8 @@ struct Gen {
     const int n = in.nsrc, d = in.dst;
     o.line("// n-ary %s (%d operands)", in.mode == MODE_AND ? "And" : "Or", n);
     o.line("V v%d[8];", d);
+    if (bwd)
+      for (int j = 0; j < n; ++j) o.line("float d%d_%d[8];  // d out / d operand %d, for the adjoint sweep", i, j, j);
     o.line("if (live) {");
     o.indent++;
     std::string w = "const float w[" + std::to_string(n) + "] = {";
@@ -361,7 +363,13 @@ struct Gen {
     std::string a = "const V a[" + std::to_string(n) + "] = {";
     for (int j = 0; j < n; ++j) a += (j ? ", " : "") + operand(in, j, "i");
     o.line("%s};", a.c_str());
-    o.line("v%d[i] = nary1<SEM, %s, %d>(rp, a, w, P.ins[%d].sw);", d, mode_name(in.mode), n, i);
+    if (bwd) {
+      o.line("float dd[%d];", n);
+      o.line("v%d[i] = nary1_partials<SEM, %s, %d>(rp, a, w, P.ins[%d].sw, dd);", d, mode_name(in.mode), n, i);
+      for (int j = 0; j < n; ++j) o.line("d%d_%d[i] = dd[%d];", i, j, j);
+    } else {
+      o.line("v%d[i] = nary1<SEM, %s, %d>(rp, a, w, P.ins[%d].sw);", d, mode_name(in.mode), n, i);
+    }
     o.indent--;
     o.line("}");
     o.indent--;
@@ -438,28 +446,13 @@ struct Gen {
   void nary_bwd(int i) {
     const TInstr& in = P.ins[i];
     const int n = in.nsrc, d = in.dst;
-    o.line("// adjoint of the n-ary %s %d", in.mode == MODE_AND ? "And" : "Or", i);
+    o.line("// adjoint of the n-ary %s %d: the partials were computed with the value", in.mode == MODE_AND ? "And" : "Or", i);
     o.line("if (live) {");
     o.indent++;
-    std::string w = "const float w[" + std::to_string(n) + "] = {";
-    for (int j = 0; j < n; ++j) {
-      char b[64];
-      snprintf(b, sizeof(b), "%sP.ins[%d].w[%d]", j ? ", " : "", i, j);
-      w += b;
-    }
-    o.line("%s};", w.c_str());
     o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) {");
     o.indent++;
-    std::string a = "const float a[" + std::to_string(n) + "] = {";
-    for (int j = 0; j < n; ++j) {
-      char b[64];
-      snprintf(b, sizeof(b), "%s%sv%d[i].x[0]", j ? ", " : "", ((in.negmask >> j) & 1) ? "-" : "", (int)in.src[j]);
-      a += b;
-    }
-    o.line("%s};", a.c_str());
-    o.line("float ga[%d];", n);
-    o.line("nary1_bwd<SEM, %s, %d>(rp, g%d[i], v%d[i].x[0], a, w, P.ins[%d].sw, ga);", mode_name(in.mode), n, d, d, i);
-    for (int j = 0; j < n; ++j) o.line("g%d[i] %s ga[%d];", (int)in.src[j], ((in.negmask >> j) & 1) ? "-=" : "+=", j);
+    for (int j = 0; j < n; ++j)
+      o.line("g%d[i] %s g%d[i] * d%d_%d[i];", (int)in.src[j], ((in.negmask >> j) & 1) ? "-=" : "+=", d, i, j);
     o.indent--;
     o.line("}");
     o.indent--;

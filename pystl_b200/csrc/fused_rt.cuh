@@ -637,6 +637,20 @@ PF_DEV void root_cotangent(const TC& c, long long T, const float* __restrict__ g
   const float* src = grad_out ? grad_out + (c.b * T + c.origin + c.p0) : nullptr;
   int hi = c.p_hi;
   if (hi > c.last_ok + 1) hi = c.last_ok + 1;
+  if (c.p0 + 8 <= hi && (!src || ((u64)src & 15ull) == 0ull)) {
+    if (src) {
+      const F4 a = reinterpret_cast<const F4*>(src)[0], b = reinterpret_cast<const F4*>(src)[1];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        g[i] = NEG ? -a.v[i] : a.v[i];
+        g[4 + i] = NEG ? -b.v[i] : b.v[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = NEG ? -scale : scale;
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float v = 0.f;
@@ -649,14 +663,31 @@ PF_DEV void root_cotangent(const TC& c, long long T, const float* __restrict__ g
 // smooth: d out_t / d x_q = xhat_q / S_t with the forward's block-shifted xhat and S: k_t = g_t / S_t.
 // Outputs whose shifted sum lost its precision (S_t < 2^-100, recomputed exactly by the forward
 // pass) are left out here and scattered exactly afterwards (lostmask).
+PF_DEV float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return 1.f / x;
+#endif
+}
 template <int MODE, int FA, int FB>
 PF_DEV unsigned smooth_adj_coeff(const TC& c, const float (&g)[8], const Vec<1> (&S)[8], Vec<1> (&k)[8]) {
+  float m = S[0].x[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fminf(m, S[i].x[0]);
+  if (m >= kSmoothTiny && c.p0 + 7 + FA <= c.nlive - 1) {  // every output has a window and a healthy sum
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k[i].x[0] = g[i] * fast_rcp(S[i].x[0]);
+    return 0u;
+  }
   unsigned lost = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const bool has = g[i] != 0.f && c.p0 + i + FA <= c.nlive - 1;
     const bool ok = S[i].x[0] >= kSmoothTiny;
-    k[i].x[0] = (has && ok) ? g[i] / S[i].x[0] : 0.f;
+    k[i].x[0] = (has && ok) ? g[i] * fast_rcp(S[i].x[0]) : 0.f;
     if (has && !ok) lost |= 1u << i;
   }
   return lost;
@@ -718,18 +749,35 @@ PF_DEV void smooth_adj_scatter(const TC& c, const RP& rp, unsigned lostmask, con
   }
 }
 
-// ---- n-ary And / Or of one sample, backward: ga[j] = d out / d a_j * g
+// ---- n-ary And / Or of one sample with its local partials d out / d a_j, computed together in the
+// forward sweep so that the backward sweep only multiplies (and the operands need not stay live)
 template <int SEM, int MODE, int N>
-PF_DEV void nary1_bwd(const RP& rp, float g, float o, const float (&a)[N], const float (&w)[N], float sw, float (&ga)[N]) {
+PF_DEV Vec<1> nary1_partials(const RP& rp, const Vec<1> (&a)[N], const float (&w)[N], float sw, float (&d)[N]) {
+  using R = Red<SEM, MODE>;
   using AD = Adj<SEM, MODE>;
-  if constexpr (SEM == SEM_SMOOTH) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) ga[j] = (g != 0.f) ? g * AD::pair_weight(o, a[j], rp) : 0.f;
+  if constexpr (SEM == SEM_SMOOTH && N == 2) {
+    // softmax / softmin weights of two terms: 1 / (1 + 2^-|d|) for the extremal one
+    const float e0 = R::expo(a[0], rp), e1 = R::expo(a[1], rp);
+    const float t = fast_ex2(-fabsf(e0 - e1));
+    const float s = 1.f + t;
+    const float wmax = fast_rcp(s), wmin = t * wmax;
+    const bool first = e0 >= e1;
+    d[0] = first ? wmax : wmin;
+    d[1] = first ? wmin : wmax;
+    const float sk = MODE == MODE_AND ? -rp.invk : rp.invk;
+    return Vec<1>{{(fmaxf(e0, e1) + fast_lg2(s)) * sk}};
   } else {
-    bool lost;
-    Vec<AD::KW> k = AD::out_coeff(g, o, sw, rp, lost);
+    const Vec<1> o = nary1<SEM, MODE, N>(rp, a, w, sw);
+    if constexpr (SEM == SEM_SMOOTH) {
 #pragma unroll
-    for (int j = 0; j < N; ++j) ga[j] = (g != 0.f) ? AD::in_factor(k, a[j], w[j], rp) : 0.f;
+      for (int j = 0; j < N; ++j) d[j] = AD::pair_weight(o.x[0], a[j].x[0], rp);
+    } else {
+      bool lost;
+      const Vec<AD::KW> k = AD::out_coeff(1.f, o.x[0], sw, rp, lost);
+#pragma unroll
+      for (int j = 0; j < N; ++j) d[j] = AD::in_factor(k, a[j].x[0], w[j], rp);
+    }
+    return o;
   }
 }
 

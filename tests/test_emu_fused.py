@@ -8,7 +8,7 @@ import pytest
 import fused_emu_lib
 from fused_cases import case_signal, forward_cases
 from parity_util import assert_parity, oracle_trace
-from pystl_b200.formula import from_spec
+from pystl_b200.formula import BASELINE_SPECS, from_spec
 
 FWD = forward_cases(light=True)
 
@@ -45,3 +45,18 @@ def test_backward(case, cotangent):
     want = oracle_grad(case["spec"], case["sem"], case["kw"], sig, g)
     rtol, atol = grad_tol(case["sem"], case["kw"])
     check(got.astype(np.float64), want, case["sem"], case["name"], rtol, atol)
+
+
+def test_smooth_extreme_dynamic_range_is_exact():
+    """tau = 0.01 on a signal of range ~30: the block-shifted sums underflow; the forward pass
+    recomputes those windows exactly, the backward pass scatters them term by term."""
+    rng = np.random.default_rng(3)
+    sig = (rng.standard_normal((2, 300, 2)) * 5.0).astype(np.float32).astype(np.float64)
+    kw = {"temperature": 0.01}
+    rtol, atol = grad_tol("smooth", kw)
+    spec = BASELINE_SPECS["cfg2"]
+    got = fused_emu_lib.eval_forward(from_spec(spec), "smooth", sig, force_threads=64, **kw)
+    assert_parity(got, oracle_trace(spec, "smooth", kw, sig), "smooth", "cfg2/tau0.01")
+    g = rng.standard_normal((2, 300)).astype(np.float32).astype(np.float64)
+    gb = fused_emu_lib.eval_backward(from_spec(spec), "smooth", sig, g, force_threads=64, **kw)
+    check(gb.astype(np.float64), oracle_grad(spec, "smooth", kw, sig, g), "smooth", "cfg2/tau0.01", rtol, atol)
