@@ -663,15 +663,6 @@ PF_DEV void root_cotangent(const TC& c, long long T, const float* __restrict__ g
 // smooth: d out_t / d x_q = xhat_q / S_t with the forward's block-shifted xhat and S: k_t = g_t / S_t.
 // Outputs whose shifted sum lost its precision (S_t < 2^-100, recomputed exactly by the forward
 // pass) are left out here and scattered exactly afterwards (lostmask).
-PF_DEV float fast_rcp(float x) {
-#if defined(__CUDA_ARCH__)
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-#else
-  return 1.f / x;
-#endif
-}
 template <int MODE, int FA, int FB>
 PF_DEV unsigned smooth_adj_coeff(const TC& c, const float (&g)[8], const Vec<1> (&S)[8], Vec<1> (&k)[8]) {
   float m = S[0].x[0];

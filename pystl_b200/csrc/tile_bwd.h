@@ -102,13 +102,13 @@ struct Adj<SEM_AGM, MODE> {
   static constexpr int KW = 2;
   static PYSTL_HD Vec<2> out_coeff(float g, float o, float sw, const RP&, bool& lost) {
     lost = false;
-    const float gn = g / sw;
+    const float gn = g * fast_rcp(sw);
     if constexpr (MODE == MODE_AND) return (o <= 0.f) ? Vec<2>{{gn, 0.f}} : Vec<2>{{0.f, gn * (o + 1.f)}};
     else return (o > 0.f) ? Vec<2>{{gn, 0.f}} : Vec<2>{{0.f, gn * (1.f - o)}};
   }
   static PYSTL_HD float in_factor(Vec<2> w, float x, float wt, const RP&) {
-    if constexpr (MODE == MODE_AND) return wt * (dmin0(x) * w.x[0] + (x > 0.f ? w.x[1] / (1.f + x) : 0.f));
-    else return wt * (dmax0(x) * w.x[0] + (x <= 0.f ? w.x[1] / (1.f - x) : 0.f));
+    if constexpr (MODE == MODE_AND) return wt * (dmin0(x) * w.x[0] + (x > 0.f ? w.x[1] * fast_rcp(1.f + x) : 0.f));
+    else return wt * (dmax0(x) * w.x[0] + (x <= 0.f ? w.x[1] * fast_rcp(1.f - x) : 0.f));
   }
 };
 
@@ -122,21 +122,21 @@ struct Adj<SEM_DGMSR, MODE> {
     if (h <= 0.f) {
       const float rmp = rp.sqrt_eps - h;  // sqrt(mp)
       // mp^(1/2 - p) / sw
-      const float c = rp.p == 1 ? 1.f / rmp : powf(rmp, 1.f - 2.f * (float)rp.p);
-      return Vec<2>{{g * c / sw, 0.f}};
+      const float c = rp.p == 1 ? fast_rcp(rmp) : fast_pow(rmp, 1.f - 2.f * (float)rp.p);
+      return Vec<2>{{g * c * fast_rcp(sw), 0.f}};
     }
     const float rm0 = h + rp.sqrt_eps;  // sqrt(m0)
-    const float ratio = expf(sw * (rp.ln_eps - 2.f * logf(rm0)));  // (eps / m0)^sw
-    return Vec<2>{{0.f, g * rm0 * (1.f - ratio) / sw}};
+    const float ratio = fast_exp(sw * (rp.ln_eps - 2.f * fast_ln(rm0)));  // (eps / m0)^sw
+    return Vec<2>{{0.f, g * rm0 * (1.f - ratio) * fast_rcp(sw)}};
   }
   static PYSTL_HD float in_factor(Vec<2> w, float x, float wt, const RP& rp) {
     const float u = MODE == MODE_AND ? x : -x;
     if (u <= 0.f) {
       const float au = -u;
-      const float pw = rp.p == 1 ? au : powf(au, 2.f * (float)rp.p - 1.f);
+      const float pw = rp.p == 1 ? au : (au > 0.f ? fast_pow(au, 2.f * (float)rp.p - 1.f) : 0.f);
       return wt * w.x[0] * pw;
     }
-    return wt * w.x[1] / u;
+    return wt * w.x[1] * fast_rcp(u);
   }
 };
 

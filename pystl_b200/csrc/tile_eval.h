@@ -96,6 +96,35 @@ PYSTL_HD float fast_lg2(float x) {
 #endif
 }
 
+// Hardware transcendentals (MUFU): 2-ulp ex2 / lg2 / rcp / sqrt.  The parity bar of the smooth,
+// agm and dgmsr semantics is |err| <= 5e-6 + 1e-5 |ref| (tests/parity_util.py); the absolute
+// error of lg2.approx is below 2^-22 and window means do not amplify it.
+PYSTL_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return 1.f / x;
+#endif
+}
+PYSTL_HD float fast_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return sqrtf(x);
+#endif
+}
+constexpr float kLn2 = 0.69314718055994531f;
+constexpr float kLog2e = 1.4426950408889634f;
+PYSTL_HD float fast_ln(float x) { return fast_lg2(x) * kLn2; }
+PYSTL_HD float fast_exp(float x) { return fast_ex2(x * kLog2e); }
+PYSTL_HD float fast_log1p(float x) { return fast_lg2(1.f + x) * kLn2; }
+PYSTL_HD float fast_expm1(float x) { return fast_ex2(x * kLog2e) - 1.f; }
+PYSTL_HD float fast_pow(float x, float y) { return fast_ex2(y * fast_lg2(x)); }  // x > 0
+
 // ------------------------------------------------------------------ values and accumulators
 template <int SEM>
 struct Tr {
@@ -195,16 +224,16 @@ struct Red<SEM_AGM, MODE> {
   static PYSTL_HD A lift(V v, const RP&, float w) {
     const float x = v.x[0];
     if constexpr (MODE == MODE_AND) {  // agm.py:71-73
-      return (x <= 0.f) ? A{{w * x, f_inf()}} : A{{0.f, w * log1pf(x)}};
+      return (x <= 0.f) ? A{{w * x, f_inf()}} : A{{0.f, w * fast_log1p(x)}};
     } else {  // agm.py:86-88
-      return (x > 0.f) ? A{{w * x, f_inf()}} : A{{0.f, w * log1pf(-x)}};
+      return (x > 0.f) ? A{{w * x, f_inf()}} : A{{0.f, w * fast_log1p(-x)}};
     }
   }
   static PYSTL_HD A comb(A a, A b) { return A{{a.x[0] + b.x[0], a.x[1] + b.x[1]}}; }
   static PYSTL_HD V fin(A a, float sw, const RP&) {
-    const float inv = 1.f / sw;
+    const float inv = fast_rcp(sw);
     if (a.x[1] == f_inf()) return V{{a.x[0] * inv}};
-    const float g = expm1f(a.x[1] * inv);
+    const float g = fast_expm1(a.x[1] * inv);
     return V{{MODE == MODE_AND ? g : -g}};
   }
 };
@@ -220,21 +249,21 @@ struct Red<SEM_DGMSR, MODE> {
     const float x = MODE == MODE_AND ? v.x[0] : -v.x[0];
     if (x <= 0.f) {
       const float x2 = x * x;
-      return A{{w * (rp.p == 1 ? x2 : powf(x2, (float)rp.p)), f_inf()}};
+      return A{{w * (rp.p == 1 ? x2 : (x2 > 0.f ? fast_pow(x2, (float)rp.p) : 0.f)), f_inf()}};
     }
-    return A{{0.f, 2.f * w * logf(x)}};
+    return A{{0.f, 2.f * w * fast_ln(x)}};
   }
   static PYSTL_HD A comb(A a, A b) { return A{{a.x[0] + b.x[0], a.x[1] + b.x[1]}}; }
   static PYSTL_HD V fin(A a, float sw, const RP& rp) {
     float h;
     if (a.x[1] == f_inf()) {  // _dgmsr.py:83-87
-      const float m = rp.eps_p + a.x[0] / sw;
-      h = rp.sqrt_eps - (rp.p == 1 ? sqrtf(m) : powf(m, rp.inv2p));
+      const float m = rp.eps_p + a.x[0] * fast_rcp(sw);
+      h = rp.sqrt_eps - (rp.p == 1 ? fast_sqrt(m) : fast_pow(m, rp.inv2p));
     } else {  // _dgmsr.py:96-102, in the log domain: ln m0 = logaddexp(sw ln eps, sum 2w ln v) / sw
       const float u = sw * rp.ln_eps, s = a.x[1];
       const float hi = fmaxf(u, s), lo = fminf(u, s);
-      const float lm0 = (hi + log1pf(expf(lo - hi))) / sw;
-      h = expf(0.5f * lm0) - rp.sqrt_eps;
+      const float lm0 = (hi + fast_log1p(fast_exp(lo - hi))) * fast_rcp(sw);
+      h = fast_exp(0.5f * lm0) - rp.sqrt_eps;
     }
     return V{{MODE == MODE_AND ? h : -h}};
   }

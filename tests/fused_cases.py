@@ -57,6 +57,15 @@ def forward_cases(light: bool = False):
             for threads in ((32,) if light else (32, 128, 256)):
                 out.append(dict(name=f"unaligned/T{T}/{sem}/nt{threads}", spec=BASELINE_SPECS["cfg1"], sem=sem, kw=kw, B=5, T=T, D=2,
                                 threads=threads, seed=21, scale=1.0))
+    if not light:
+        # the reference's own outputs (golden vectors) for the formulas the fused tier evaluates
+        for c in CASES:
+            if "until" in repr(c["spec"]) or "None" in repr(c["spec"]):
+                continue
+            if c["spec_name"] == "weighted" and c["sem"] in ("agm", "dgmsr"):
+                continue
+            out.append(dict(name="golden/" + c["name"], spec=c["spec"], sem=c["sem"], kw=c["kw"], golden=c, threads=0, scale=1.0,
+                            T=c["T"], D=c["D"]))
     return out
 
 
@@ -73,5 +82,22 @@ def backward_cases(light: bool = False):
 
 
 def case_signal(case) -> np.ndarray:
+    if "golden" in case:
+        import golden_cases
+
+        return golden_cases.case_signal(case["golden"])
     rng = np.random.default_rng(case["seed"])
     return mixed_signal(rng, case["B"], case["T"], case["D"])
+
+
+def expected(case, sig) -> np.ndarray:
+    """Reference values: the golden vectors (outputs of the unmodified reference) where the case has
+    them, the oracle otherwise."""
+    if "golden" in case:
+        import os
+
+        gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
+        return gold[f"{case['golden']['name']}/values"]
+    from parity_util import oracle_trace
+
+    return oracle_trace(case["spec"], case["sem"], case["kw"], sig)

@@ -18,6 +18,13 @@ from test_emu_backward import BWD_SEMS, GOLD, GRAD_CASES, check, grad_tol, has_u
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _interpreter_tier(monkeypatch):
+    """This file pins the INTERPRETER tier (the universal fallback); tests/test_gpu_fused.py runs
+    the same kind of corpus through the fused tier."""
+    monkeypatch.setenv("PYSTL_B200_TIER", "interp")
+
+
 def gpu_grad(spec, sem, kw, sig64, g64, threads: int = 0):
     s = create_semantics(sem, backend="b200", **kw)
     x = torch.tensor(sig64, dtype=torch.float32, device="cuda", requires_grad=True)

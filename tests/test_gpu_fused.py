@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from fused_cases import case_signal, forward_cases
+from fused_cases import case_signal, expected, forward_cases
 from parity_util import assert_parity, oracle_trace
 from pystl_b200 import create_semantics
 from pystl_b200.formula import BASELINE_SPECS, from_spec
@@ -52,7 +52,7 @@ def run(spec, sem, kw, x, which, threads=0):
 @pytest.mark.parametrize("case", FWD, ids=[c["name"] for c in FWD])
 def test_forward(case):
     sig = case_signal(case)
-    want = oracle_trace(case["spec"], case["sem"], case["kw"], sig)
+    want = expected(case, sig)
     x = torch.tensor(sig, dtype=torch.float32, device="cuda")
     got = run(case["spec"], case["sem"], case["kw"], x, "fused", case["threads"]).cpu().numpy()
     assert_parity(got, want, case["sem"], case["name"], scale=case["scale"])

@@ -16,6 +16,13 @@ from pystl_b200.formula import BASELINE_SPECS, from_spec
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _interpreter_tier(monkeypatch):
+    """This file pins the INTERPRETER tier (the universal fallback); tests/test_gpu_fused.py runs
+    the same kind of corpus through the fused tier."""
+    monkeypatch.setenv("PYSTL_B200_TIER", "interp")
+
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
 SUPPORTED = [c for c in CASES if not (c["spec_name"] == "weighted" and c["sem"] in ("agm", "dgmsr"))]
 
