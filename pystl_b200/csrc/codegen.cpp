@@ -68,6 +68,9 @@ const char* sem_name(int sem) {
 const char* mode_name(int m) { return m == MODE_AND ? "MODE_AND" : (m == MODE_OR ? "MODE_OR" : "MODE_SUM"); }
 
 bool is_window(const TInstr& in) { return in.op == T_WIN_DIRECT || in.op == T_WIN_VH; }
+bool is_scan(const TInstr& in) { return in.op == T_CLAMP_SCAN; }
+// instructions whose result needs one barrier (phase 1 | barrier | phase 2)
+bool is_staged(const TInstr& in) { return is_window(in) || is_scan(in); }
 
 struct Gen {
   const Lowered& lw;
@@ -102,6 +105,7 @@ struct Gen {
     }
     for (int i = 0; i < P.n_instr; ++i) {
       const TInstr& in = P.ins[i];
+      if (is_scan(in) && P.sem == SEM_CLASSIC && !bwd) continue;
       if (in.op != T_NARY && !is_window(in)) {
         *why = "until / open-ended windows are evaluated by the interpreter tier";
         return false;
@@ -120,7 +124,7 @@ struct Gen {
       const TInstr& in = P.ins[i];
       int l = 0;
       for (int j = 0; j < in.nsrc; ++j) l = std::max(l, level[in.src[j]]);
-      if (is_window(in)) l += 1;
+      if (is_staged(in)) l += 1;
       level[in.dst] = l;
       ins_level[i] = l;
       max_level = std::max(max_level, l);
@@ -149,6 +153,11 @@ struct Gen {
     std::vector<int> used(max_level + 3, 0), bused(max_level + 3, 0);
     for (int i = 0; i < P.n_instr; ++i) {
       const TInstr& in = P.ins[i];
+      if (is_scan(in)) {
+        scr_off[i] = used[ins_level[i]];
+        used[ins_level[i]] += 2 * 32;  // ClampScanOp<SEM_CLASSIC>::FLOATS
+        continue;
+      }
       if (!is_window(in)) continue;
       const int l = ins_level[i];
       const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
@@ -170,6 +179,7 @@ struct Gen {
     }
     const int base0 = red_floats + persist, base1 = base0 + reg[0];
     for (int i = 0; i < P.n_instr; ++i) {
+      if (is_scan(P.ins[i])) scr_off[i] += (ins_level[i] & 1) ? base1 : base0;
       if (!is_window(P.ins[i])) continue;
       const int l = ins_level[i];
       scr_off[i] += (l & 1) ? base1 : base0;
@@ -342,6 +352,24 @@ struct Gen {
     }
   }
 
+  void scan_phase1(int i) {
+    const TInstr& in = P.ins[i];
+    o.line("// classic until %d: clamp scan, phase 1 (chunk composition, warp scan)", i);
+    o.line("using CS%d = ClampScanOp<SEM, NT>;", i);
+    o.line("static_assert(CS%d::FLOATS == 64, \"host / device scratch layout mismatch\");", i);
+    o.line("CS%d::A cx%d[8], ce%d;", i, i, i);
+    o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i)");
+    o.line("  cx%d[i] = (live && c.p0 + i < c.nlive) ? ClampOp<SEM>::make(%s, %s) : ClampOp<SEM>::ident();", i, operand(in, 0, "i").c_str(),
+           operand(in, 1, "i").c_str());
+    o.line("CS%d::phase1(smem + %d, c, cx%d, ce%d);", i, scr_off[i], i, i);
+  }
+  void scan_phase2(int i) {
+    const TInstr& in = P.ins[i];
+    o.line("// classic until %d: clamp scan, phase 2", i);
+    o.line("V v%d[8];", (int)in.dst);
+    o.line("CS%d::phase2<VW>(smem + %d, c, cx%d, ce%d, v%d);", i, scr_off[i], i, i, (int)in.dst);
+  }
+
   void nary(int i) {
     const TInstr& in = P.ins[i];
     const int n = in.nsrc, d = in.dst;
@@ -404,16 +432,24 @@ struct Gen {
         const TInstr& in = P.ins[i];
         if (ins_level[i] != st) continue;
         if (is_window(in)) win_phase2(i);
+        else if (is_scan(in)) scan_phase2(i);
         else nary(i);
       }
       bool any = false;
       for (int i = 0; i < P.n_instr; ++i)
-        if (is_window(P.ins[i]) && ins_level[i] == st + 1) {
-          win_phase1(i);
+        if (is_staged(P.ins[i]) && ins_level[i] == st + 1) {
+          if (is_window(P.ins[i])) win_phase1(i);
+          else scan_phase1(i);
           any = true;
         }
       if (any) o.line("simt::sync();");
     }
+  }
+
+  // shows up in profiler launch lists: pystl_fused_<pass>_<semantics>
+  std::string kernel_name() const {
+    static const char* sems[] = {"classical", "smooth", "cumulative", "agm", "dgmsr"};
+    return std::string("pystl_fused_") + (bwd ? "value_and_grad_" : "forward_") + sems[P.sem];
   }
 
   void emit_header(const char* what) {
@@ -430,7 +466,7 @@ struct Gen {
     plan();
     plan_bounds();
     emit_header("forward");
-    o.line("PF_KERNEL(NT, %d) pystl_fused(const PF_GRID_CONSTANT TileProgram P, const PF_GRID_CONSTANT TileGeom g,", minb);
+    o.line("PF_KERNEL(NT, %d) %s(const PF_GRID_CONSTANT TileProgram P, const PF_GRID_CONSTANT TileGeom g,", minb, kernel_name().c_str());
     o.line("    const float* __restrict__ signal, float* __restrict__ out, double* __restrict__ mean_acc) {");
     o.indent = 1;
     emit_forward_body();
@@ -520,7 +556,7 @@ struct Gen {
     plan();
     plan_bounds();
     emit_header("backward (value and gradient)");
-    o.line("PF_KERNEL(NT, %d) pystl_fused(const PF_GRID_CONSTANT TileProgram P, const PF_GRID_CONSTANT TileGeom g,", minb);
+    o.line("PF_KERNEL(NT, %d) %s(const PF_GRID_CONSTANT TileProgram P, const PF_GRID_CONSTANT TileGeom g,", minb, kernel_name().c_str());
     o.line("    const float* __restrict__ signal, const float* __restrict__ grad_out, float scale, float* __restrict__ grad_signal,");
     o.line("    float* __restrict__ out, double* __restrict__ mean_acc) {");
     o.indent = 1;
@@ -676,6 +712,7 @@ int fused_generate(const Lowered& lw, int D, int nt, int minb, bool backward, Fu
     return PYSTL_E_UNSUPPORTED;
   }
   out->source = backward ? g.backward() : g.forward();
+  out->name = g.kernel_name();
   out->smem_floats = g.smem_floats;
   out->nt = nt;
   out->minb = minb;

@@ -10,7 +10,8 @@
 namespace pystl {
 
 struct FusedSource {
-  std::string source;  // CUDA source of the kernel `pystl_fused` (includes fused_rt.cuh)
+  std::string source;  // CUDA source of the kernel (includes fused_rt.cuh)
+  std::string name;    // its extern "C" name: pystl_fused_<pass>_<semantics>
   int smem_floats = 0;
   int nt = 0;
   int minb = 1;

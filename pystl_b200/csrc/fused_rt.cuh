@@ -440,6 +440,59 @@ struct WinOp {
   }
 };
 
+// ------------------------------------------------------------------ classic unbounded until
+// W(s) = min(l_s, max(r_s, W(s+1))): a suffix scan of the clamp functions x -> min(A, max(B, x))
+// over the tile (tile_eval.h: ClampOp).  Chunk-local composition in
+// registers, warp suffix scan with shuffles, warp totals through shared memory: one barrier.
+// Every thread of the CTA calls both phases (threads past the horizon pass the identity).
+template <int SEM, int NT>
+struct ClampScanOp {
+  using OP = ClampOp<SEM>;
+  using A = typename OP::A;
+  static constexpr int W = OP::W;
+  static constexpr int NW = NT / 32;
+  static constexpr int FLOATS = W * 32;
+
+  PF_DEV static void phase1(float* scr, const TC& c, const A (&x)[8], A& excl) {
+    A v = x[7];
+#pragma unroll
+    for (int i = 6; i >= 0; --i) v = OP::comb(x[i], v);
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      A other;
+#pragma unroll
+      for (int w = 0; w < W; ++w) other.x[w] = simt::shfl_down(v.x[w], o);
+      if (lane + o < 32) v = OP::comb(v, other);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) scr[w * 32 + warp] = v.x[w];
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) excl.x[w] = simt::shfl_down(v.x[w], 1);
+    if (lane == 31) excl = OP::ident();
+  }
+
+  template <int VW>
+  PF_DEV static void phase2(const float* scr, const TC& c, const A (&x)[8], A excl, Vec<VW> (&o)[8]) {
+    const int warp = c.tid >> 5;
+    A tail = OP::ident();
+    for (int ww = NW - 1; ww > warp; --ww) {
+      A t;
+#pragma unroll
+      for (int w = 0; w < W; ++w) t.x[w] = scr[w * 32 + ww];
+      tail = OP::comb(t, tail);
+    }
+    A run = OP::comb(excl, tail);
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      run = OP::comb(x[i], run);
+      o[i] = OP::value(run);
+    }
+  }
+};
+
 // ------------------------------------------------------------------ lift / finish
 // the thread's operand samples -> accumulators; samples past the horizon become the identity
 template <class R, int VW>

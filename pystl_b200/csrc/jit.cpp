@@ -237,7 +237,7 @@ int fused_jit_get(const FusedSource& src, FusedKernel* out, char* msg, int msg_l
   cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if (e != cudaSuccess) return fail(msg, msg_len, PYSTL_E_CUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e));
   cudaKernel_t k = nullptr;
-  e = cudaLibraryGetKernel(&k, lib, "pystl_fused");
+  e = cudaLibraryGetKernel(&k, lib, src.name.c_str());
   if (e != cudaSuccess) return fail(msg, msg_len, PYSTL_E_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e));
   e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, src.smem_floats * 4);
   if (e != cudaSuccess) return fail(msg, msg_len, PYSTL_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));

@@ -357,7 +357,8 @@ struct Lowerer {
             }
           }
           const Ref l = operand(child(i, 0)), r = operand(child(i, 1));
-          const bool decompose = sem == SEM_CLASSIC && (nd.b < 0 || nd.b > 16);
+          // (the fused tier always decomposes: every piece is O(1) per sample and fusable)
+          const bool decompose = sem == SEM_CLASSIC && (nd.b < 0 || nd.b > 16 || ssa);
           if (decompose) {
             // U[a,b] = min( G[0,a] l , W(t+a) , F[a,b] r ),  W = unbounded until (clamp scan)
             // (every slot below is held by one pending read until the final min consumes it)

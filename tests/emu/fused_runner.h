@@ -15,9 +15,9 @@ struct FusedArgs {
 void fused_body(void* a) {
   FusedArgs* A = static_cast<FusedArgs*>(a);
 #if defined(PF_EMU_BACKWARD)
-  pystl_fused(*A->P, *A->g, A->signal, A->grad_out, A->scale, A->grad_signal, A->out, A->mean);
+  PF_EMU_KERNEL(*A->P, *A->g, A->signal, A->grad_out, A->scale, A->grad_signal, A->out, A->mean);
 #else
-  pystl_fused(*A->P, *A->g, A->signal, A->out, A->mean);
+  PF_EMU_KERNEL(*A->P, *A->g, A->signal, A->out, A->mean);
 #endif
 }
 }  // namespace

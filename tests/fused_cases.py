@@ -52,6 +52,24 @@ def forward_cases(light: bool = False):
         for sem, kw in SEM_KW[:5]:
             out.append(dict(name=f"rand{seed}/{sem}", spec=spec, sem=sem, kw=kw, B=2, T=T, D=D, threads=32 if seed % 2 else 0, seed=3000 + seed,
                             scale=8.0 if sem == "cumulative" else 2.0))
+    # classic until: decomposed into two windows and a clamp scan
+    for cfg, D in (("cfg4", 4), ("cfg5", 8)):
+        for threads in ((64,) if light else (0, 64)):
+            out.append(dict(name=f"{cfg}/classical/nt{threads}", spec=BASELINE_SPECS[cfg], sem="classical", kw={}, B=3, T=700, D=D,
+                            threads=threads, seed=11, scale=1.0))
+    for seed in range(3 if light else 12):
+        rng = np.random.default_rng(5000 + seed)
+        D = int(rng.integers(1, 4))
+        T = int(rng.integers(60, 500))
+        spec = None
+        for _ in range(200):
+            cand = random_spec(rng, D, depth=3, max_b=30, allow_open=False)
+            if "until" in repr(cand):
+                spec = cand
+                break
+        if spec is not None:
+            out.append(dict(name=f"until{seed}/classical", spec=spec, sem="classical", kw={}, B=2, T=T, D=D, threads=64 if seed % 2 else 0,
+                            seed=5100 + seed, scale=1.0))
     for T in (999, 1001, 1002):
         for sem, kw in (SEM_KW[0], SEM_KW[1]):
             for threads in ((32,) if light else (32, 128, 256)):

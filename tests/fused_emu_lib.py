@@ -77,7 +77,10 @@ def kernel(source: str, backward: bool):
         with open(cu, "w") as fh:
             fh.write(source)
             fh.write('\n#include "fused_runner.h"\n')
-        cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", CSRC, "-I", EMU]
+        import re
+
+        name = re.search(r"PF_KERNEL\(NT, \d+\) (\w+)\(", source).group(1)
+        cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", CSRC, "-I", EMU, f"-DPF_EMU_KERNEL={name}"]
         if backward:
             cmd.append("-DPF_EMU_BACKWARD")
         tmp = so + f".{os.getpid()}.tmp"
