@@ -69,8 +69,9 @@ const char* mode_name(int m) { return m == MODE_AND ? "MODE_AND" : (m == MODE_OR
 
 bool is_window(const TInstr& in) { return in.op == T_WIN_DIRECT || in.op == T_WIN_VH; }
 bool is_scan(const TInstr& in) { return in.op == T_CLAMP_SCAN; }
+bool is_until(const TInstr& in) { return in.op == T_UNTIL && !in.unbounded; }
 // instructions whose result needs one barrier (phase 1 | barrier | phase 2)
-bool is_staged(const TInstr& in) { return is_window(in) || is_scan(in); }
+bool is_staged(const TInstr& in) { return is_window(in) || is_scan(in) || is_until(in); }
 
 struct Gen {
   const Lowered& lw;
@@ -87,6 +88,9 @@ struct Gen {
   bool bwd = false;                // generating the backward kernel
   std::vector<int> bscr_off;       // per instruction: scratch of the adjoint window
   int fix_off = 0, flag_off = 0;   // smooth backward: exact-scatter plane, per-window lost flags
+  int sp_off = 0;                  // cumulative backward: four scatter planes
+  bool cum_bwd() const { return bwd && P.sem == SEM_CUMULATIVE; }
+  bool arg_window(const TInstr& in) const { return cum_bwd() && is_window(in) && in.mode != MODE_SUM; }
 
   Gen(const Lowered& l, int D_, int nt_, int minb_, bool bwd_) : lw(l), P(l.prog), D(D_), nt(nt_), minb(minb_), bwd(bwd_) {}
   int kw() const { return P.sem == SEM_SMOOTH ? 1 : 2; }  // words of an adjoint coefficient
@@ -99,13 +103,14 @@ struct Gen {
       *why = "bad D";
       return false;
     }
-    if (bwd && !(P.sem == SEM_SMOOTH || P.sem == SEM_AGM || P.sem == SEM_DGMSR)) {
+    if (bwd && P.sem == SEM_CLASSIC) {
       *why = "the classic gradient runs on the interpreter tier";
       return false;
     }
     for (int i = 0; i < P.n_instr; ++i) {
       const TInstr& in = P.ins[i];
       if (is_scan(in) && P.sem == SEM_CLASSIC && !bwd) continue;
+      if (is_until(in) && (!bwd || P.sem == SEM_CUMULATIVE)) continue;
       if (in.op != T_NARY && !is_window(in)) {
         *why = "until / open-ended windows are evaluated by the interpreter tier";
         return false;
@@ -150,6 +155,15 @@ struct Gen {
       flag_off = red_floats + persist;
       persist += roundup(P.n_instr, 4);
     }
+    if (cum_bwd()) {
+      sp_off = red_floats + persist;
+      persist += 4 * 8 * nt;
+      for (int i = 0; i < P.n_instr; ++i)
+        if (is_until(P.ins[i])) {  // the adjoint re-reads the staged operands
+          scr_off[i] = red_floats + persist;
+          persist += 2 * vw() * 8 * nt;
+        }
+    }
     std::vector<int> used(max_level + 3, 0), bused(max_level + 3, 0);
     for (int i = 0; i < P.n_instr; ++i) {
       const TInstr& in = P.ins[i];
@@ -158,16 +172,22 @@ struct Gen {
         used[ins_level[i]] += 2 * 32;  // ClampScanOp<SEM_CLASSIC>::FLOATS
         continue;
       }
+      if (is_until(in)) {
+        if (cum_bwd()) continue;  // persistent (above)
+        scr_off[i] = used[ins_level[i]];
+        used[ins_level[i]] += 2 * vw() * 8 * nt;  // UntilOp::FLOATS
+        continue;
+      }
       if (!is_window(in)) continue;
       const int l = ins_level[i];
       const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
       scr_off[i] = used[l];
-      used[l] += win_floats(aw(), a, b, nt);
+      used[l] += arg_window(in) ? 2 * win_floats(2, a, b, nt) : win_floats(aw(), a, b, nt);
       if (P.sem == SEM_SMOOTH && !stash_persists) {
         stash_off[i] = used[l];
         used[l] += 8 * nt;
       }
-      if (bwd) {
+      if (bwd && !arg_window(in)) {
         bscr_off[i] = bused[l];
         bused[l] += win_floats(kw(), -b, -a, nt);
       }
@@ -179,7 +199,7 @@ struct Gen {
     }
     const int base0 = red_floats + persist, base1 = base0 + reg[0];
     for (int i = 0; i < P.n_instr; ++i) {
-      if (is_scan(P.ins[i])) scr_off[i] += (ins_level[i] & 1) ? base1 : base0;
+      if (is_scan(P.ins[i]) || (is_until(P.ins[i]) && !cum_bwd())) scr_off[i] += (ins_level[i] & 1) ? base1 : base0;
       if (!is_window(P.ins[i])) continue;
       const int l = ins_level[i];
       scr_off[i] += (l & 1) ? base1 : base0;
@@ -212,6 +232,11 @@ struct Gen {
         const bool neg = (in.negmask >> j) & 1;
         bool olo = want_lo, ohi = want_hi;  // bounds of the (negated) operand that are consumed
         if (is_window(in)) (in.mode == MODE_AND ? olo : ohi) = true;  // the shift
+        if (is_until(in)) {  // shift by the smaller operand; the result's range mixes all four bounds
+          olo = true;
+          ohi = want_lo || want_hi;
+          if (ohi) olo = true;
+        }
         if (olo) (neg ? need_hi : need_lo)[in.src[j]] = 1;
         if (ohi) (neg ? need_lo : need_hi)[in.src[j]] = 1;
       }
@@ -300,8 +325,53 @@ struct Gen {
     o.line("static_assert(W%d::FLOATS == %d, \"host / device scratch layout mismatch\");", i, win_floats(aw(), a, b, nt));
   }
 
+  // cumulative backward: minima / maxima on (value, position) pairs, one channel at a time
+  void argwin_phase1(int i) {
+    const TInstr& in = P.ins[i];
+    const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
+    const int half = win_floats(2, a, b, nt);
+    o.line("// window %d (arg%s), phase 1", i, in.mode == MODE_AND ? "min" : "max");
+    o.line("using W%d = WinOp<ArgRed<%s>, %d, %d, NT>;", i, mode_name(in.mode), a, b);
+    o.line("static_assert(W%d::FLOATS == %d, \"host / device scratch layout mismatch\");", i, half);
+    o.line("Vec<2> xa%d[8], sfa%d[8], pfa%d[8], xb%d[8], sfb%d[8], pfb%d[8];", i, i, i, i, i, i);
+    o.line("W%d::fill_guards(smem + %d, c.tid);", i, scr_off[i]);
+    o.line("W%d::fill_guards(smem + %d, c.tid);", i, scr_off[i] + half);
+    o.line("if (live) {");
+    o.indent++;
+    o.line("V t[8];");
+    o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) t[i] = %s;", operand(in, 0, "i").c_str());
+    o.line("arg_lift8<%s>(c, t, 0, xa%d);", mode_name(in.mode), i);
+    o.line("arg_lift8<%s>(c, t, 1, xb%d);", mode_name(in.mode), i);
+    o.line("W%d::phase1(smem + %d, c.tid, xa%d, sfa%d, pfa%d);", i, scr_off[i], i, i, i);
+    o.line("W%d::phase1(smem + %d, c.tid, xb%d, sfb%d, pfb%d);", i, scr_off[i] + half, i, i, i);
+    o.indent--;
+    o.line("} else {");
+    o.indent++;
+    o.line("W%d::phase1_dead(smem + %d, c.tid);", i, scr_off[i]);
+    o.line("W%d::phase1_dead(smem + %d, c.tid);", i, scr_off[i] + half);
+    o.indent--;
+    o.line("}");
+  }
+  void argwin_phase2(int i) {
+    const TInstr& in = P.ins[i];
+    const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
+    const int half = win_floats(2, a, b, nt);
+    const int d = in.dst;
+    o.line("// window %d (arg), phase 2", i);
+    o.line("V v%d[8];", d);
+    o.line("Vec<2> acca%d[8], accb%d[8];  // (value, position) of both channels, kept for the adjoint", i, i);
+    o.line("if (live) {");
+    o.indent++;
+    o.line("W%d::phase2(smem + %d, c.tid, xa%d, sfa%d, pfa%d, acca%d);", i, scr_off[i], i, i, i, i);
+    o.line("W%d::phase2(smem + %d, c.tid, xb%d, sfb%d, pfb%d, accb%d);", i, scr_off[i] + half, i, i, i, i);
+    o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) v%d[i] = V{{acca%d[i].x[0], accb%d[i].x[0]}};", d, i, i);
+    o.indent--;
+    o.line("}");
+  }
+
   void win_phase1(int i) {
     const TInstr& in = P.ins[i];
+    if (arg_window(in)) return argwin_phase1(i);
     const bool neg = in.negmask & 1;
     const int s = in.src[0];
     o.line("// window %d, phase 1: lift, chunk scans -> shared", i);
@@ -330,6 +400,7 @@ struct Gen {
 
   void win_phase2(int i) {
     const TInstr& in = P.ins[i];
+    if (arg_window(in)) return argwin_phase2(i);
     const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
     const bool neg = in.negmask & 1;
     const int s = in.src[0], d = in.dst;
@@ -370,12 +441,52 @@ struct Gen {
     o.line("CS%d::phase2<VW>(smem + %d, c, cx%d, ce%d, v%d);", i, scr_off[i], i, i, (int)in.dst);
   }
 
+  void until_phase1(int i) {
+    const TInstr& in = P.ins[i];
+    const bool nl = in.negmask & 1, nr = in.negmask & 2;
+    o.line("// until %d [%d, %d], phase 1: stage both operands", i, in.a, in.b);
+    o.line("using U%d = UntilOp<SEM, %d, %d, NT>;", i, in.a, in.b);
+    o.line("static_assert(U%d::FLOATS == %d, \"host / device scratch layout mismatch\");", i, 2 * vw() * 8 * nt);
+    o.line("RP rp%d = rp;", i);
+    if (P.sem == SEM_SMOOTH)
+      o.line("rp%d.shift = fmaxf(-(%s), -(%s)) * rp.k;  // max exponent of -l, -r over the tile", i, lo_of(in.src[0], nl).c_str(),
+             lo_of(in.src[1], nr).c_str());
+    o.line("if (live) {");
+    o.indent++;
+    o.line("V tl[8], tr[8];");
+    o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) { tl[i] = %s; tr[i] = %s; }", operand(in, 0, "i").c_str(), operand(in, 1, "i").c_str());
+    o.line("U%d::phase1(smem + %d, c.tid, tl, tr);", i, scr_off[i]);
+    o.indent--;
+    o.line("}");
+  }
+  void until_phase2(int i) {
+    const TInstr& in = P.ins[i];
+    const int d = in.dst;
+    const bool nl = in.negmask & 1, nr = in.negmask & 2;
+    o.line("// until %d, phase 2: O(b) walk with running state", i);
+    o.line("V v%d[8];", d);
+    o.line("if (live) {");
+    o.indent++;
+    o.line("UntilState<SEM> st[8];");
+    o.line("U%d::phase2(smem + %d, c, rp%d, P.ins[%d].w[0], P.ins[%d].w[1], v%d, st);", i, scr_off[i], i, i, i, d);
+    if (P.sem == SEM_SMOOTH) o.line("U%d::smooth_fix(smem + %d, c, rp%d, st, v%d);", i, scr_off[i], i, d);
+    o.indent--;
+    o.line("}");
+    if (P.sem == SEM_SMOOTH && (need_lo[d] || need_hi[d])) {
+      // softmin over <= b+2 terms inside a softmax over <= b+1 candidates (tile_eval.h: op_until)
+      o.line("const float pad%d = 2.f * rp.invk * fast_lg2(%d.f) + 2e-6f * (fabsf(%s) + fabsf(%s)) + 1e-30f;", i, in.b + 2,
+             lo_of(in.src[0], nl).c_str(), hi_of(in.src[1], nr).c_str());
+      if (need_lo[d]) o.line("const float lo%d = fminf(%s, %s) - pad%d;", d, lo_of(in.src[0], nl).c_str(), lo_of(in.src[1], nr).c_str(), i);
+      if (need_hi[d]) o.line("const float hi%d = fmaxf(%s, %s) + pad%d;", d, hi_of(in.src[0], nl).c_str(), hi_of(in.src[1], nr).c_str(), i);
+    }
+  }
+
   void nary(int i) {
     const TInstr& in = P.ins[i];
     const int n = in.nsrc, d = in.dst;
     o.line("// n-ary %s (%d operands)", in.mode == MODE_AND ? "And" : "Or", n);
     o.line("V v%d[8];", d);
-    if (bwd)
+    if (bwd && !cum_bwd())
       for (int j = 0; j < n; ++j) o.line("float d%d_%d[8];  // d out / d operand %d, for the adjoint sweep", i, j, j);
     o.line("if (live) {");
     o.indent++;
@@ -391,7 +502,7 @@ struct Gen {
     std::string a = "const V a[" + std::to_string(n) + "] = {";
     for (int j = 0; j < n; ++j) a += (j ? ", " : "") + operand(in, j, "i");
     o.line("%s};", a.c_str());
-    if (bwd) {
+    if (bwd && !cum_bwd()) {
       o.line("float dd[%d];", n);
       o.line("v%d[i] = nary1_partials<SEM, %s, %d>(rp, a, w, P.ins[%d].sw, dd);", d, mode_name(in.mode), n, i);
       for (int j = 0; j < n; ++j) o.line("d%d_%d[i] = dd[%d];", i, j, j);
@@ -433,12 +544,14 @@ struct Gen {
         if (ins_level[i] != st) continue;
         if (is_window(in)) win_phase2(i);
         else if (is_scan(in)) scan_phase2(i);
+        else if (is_until(in)) until_phase2(i);
         else nary(i);
       }
       bool any = false;
       for (int i = 0; i < P.n_instr; ++i)
         if (is_staged(P.ins[i]) && ins_level[i] == st + 1) {
           if (is_window(P.ins[i])) win_phase1(i);
+          else if (is_until(P.ins[i])) until_phase1(i);
           else scan_phase1(i);
           any = true;
         }
@@ -552,6 +665,104 @@ struct Gen {
     }
   }
 
+  // ---------------------------------------------------------------- cumulative backward
+  std::string adj_add(int src, bool neg, const char* expr) const {  // g_src += expr, through a Not
+    char b[256];
+    if (neg) snprintf(b, sizeof(b), "{ const V t_ = %s; g%d[i].x[0] -= t_.x[1]; g%d[i].x[1] -= t_.x[0]; }", expr, src, src);
+    else snprintf(b, sizeof(b), "{ const V t_ = %s; g%d[i].x[0] += t_.x[0]; g%d[i].x[1] += t_.x[1]; }", expr, src, src);
+    return b;
+  }
+  void cum_adjoints() {
+    const int L = 8 * nt;
+    for (int st = n_stages - 1; st >= 0; --st) {
+      o.line("// ================= adjoint stage %d", st);
+      for (int i = P.n_instr - 1; i >= 0; --i) {
+        const TInstr& in = P.ins[i];
+        if (ins_level[i] != st || is_staged(in)) continue;
+        const int n = in.nsrc, d = in.dst;
+        o.line("// adjoint of the n-ary %s %d: the cotangent goes to the first extremal operand", in.mode == MODE_AND ? "min" : "max", i);
+        o.line("if (live) {");
+        o.indent++;
+        o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) {");
+        o.indent++;
+        std::string a = "const V a[" + std::to_string(n) + "] = {";
+        for (int j = 0; j < n; ++j) a += (j ? ", " : "") + operand(in, j, "i");
+        o.line("%s};", a.c_str());
+        o.line("V ga[%d];", n);
+        o.line("cum_nary_bwd<%s, %d>(a, g%d[i], ga);", mode_name(in.mode), n, d);
+        for (int j = 0; j < n; ++j) {
+          char e[32];
+          snprintf(e, sizeof(e), "ga[%d]", j);
+          o.line("%s", adj_add(in.src[j], (in.negmask >> j) & 1, e).c_str());
+        }
+        o.indent--;
+        o.line("}");
+        o.indent--;
+        o.line("}");
+      }
+      for (int i = P.n_instr - 1; i >= 0; --i) {
+        const TInstr& in = P.ins[i];
+        if (ins_level[i] != st || !is_staged(in)) continue;
+        const int d = in.dst;
+        if (is_until(in)) {
+          const bool nl = in.negmask & 1, nr = in.negmask & 2;
+          o.line("// adjoint of until %d: every candidate routes to r_i or to the prefix minimum of l", i);
+          o.line("_Pragma(\"unroll\") for (int w = 0; w < 4; ++w) plane_zero8(smem + %d + w * %d, c.tid);", sp_off, L);
+          o.line("simt::sync();");
+          o.line("if (live) {");
+          o.indent++;
+          for (int w = 0; w < 2; ++w)
+            o.line("cum_until_scatter<%d, %d, NT>(c, g%d, %d, U%d::lplane(smem + %d, %d), U%d::rplane(smem + %d, %d), smem + %d, smem + %d);", in.a,
+                   in.b, d, w, i, scr_off[i], w, i, scr_off[i], w, sp_off + w * L, sp_off + (2 + w) * L);
+          o.indent--;
+          o.line("}");
+          o.line("simt::sync();");
+          o.line("if (live) {");
+          o.indent++;
+          o.line("cum_accumulate8<%s>(smem + %d, smem + %d, c.tid, g%d);", nl ? "true" : "false", sp_off, sp_off + L, (int)in.src[0]);
+          o.line("cum_accumulate8<%s>(smem + %d, smem + %d, c.tid, g%d);", nr ? "true" : "false", sp_off + 2 * L, sp_off + 3 * L, (int)in.src[1]);
+          o.indent--;
+          o.line("}");
+          o.line("simt::sync();");
+        } else if (arg_window(in)) {
+          const bool neg = in.negmask & 1;
+          o.line("// adjoint of window %d: scatter to the recorded arg%s", i, in.mode == MODE_AND ? "min" : "max");
+          o.line("plane_zero8(smem + %d, c.tid);", sp_off);
+          o.line("plane_zero8(smem + %d, c.tid);", sp_off + L);
+          o.line("simt::sync();");
+          o.line("if (live) {");
+          o.indent++;
+          o.line("arg_scatter8(smem + %d, acca%d, g%d, 0);", sp_off, i, d);
+          o.line("arg_scatter8(smem + %d, accb%d, g%d, 1);", sp_off + L, i, d);
+          o.indent--;
+          o.line("}");
+          o.line("simt::sync();");
+          o.line("if (live) cum_accumulate8<%s>(smem + %d, smem + %d, c.tid, g%d);", neg ? "true" : "false", sp_off, sp_off + L, (int)in.src[0]);
+          o.line("simt::sync();");
+        } else {  // Eventually: a sum
+          const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);
+          const bool neg = in.negmask & 1;
+          o.line("// adjoint of the sum window %d: backward-looking window sum of the cotangent", i);
+          o.line("using BW%d = WinOp<SumOp<2>, %d, %d, NT>;", i, -b, -a);
+          o.line("static_assert(BW%d::FLOATS == %d, \"host / device scratch layout mismatch\");", i, win_floats(2, -b, -a, nt));
+          o.line("Vec<2> ksf%d[8], kpf%d[8];", i, i);
+          o.line("BW%d::fill_guards(smem + %d, c.tid);", i, bscr_off[i]);
+          o.line("if (live) BW%d::phase1(smem + %d, c.tid, g%d, ksf%d, kpf%d);", i, bscr_off[i], d, i, i);
+          o.line("else BW%d::phase1_dead(smem + %d, c.tid);", i, bscr_off[i]);
+          o.line("simt::sync();");
+          o.line("if (live) {");
+          o.indent++;
+          o.line("Vec<2> w[8];");
+          o.line("BW%d::phase2(smem + %d, c.tid, g%d, ksf%d, kpf%d, w);", i, bscr_off[i], d, i, i);
+          o.line("cum_add8<%s>(w, g%d);", neg ? "true" : "false", (int)in.src[0]);
+          o.indent--;
+          o.line("}");
+          o.line("simt::sync();");
+        }
+      }
+    }
+  }
+
   std::string backward() {
     plan();
     plan_bounds();
@@ -576,22 +787,32 @@ struct Gen {
       for (int j = 0; j < P.ins[i].nsrc; ++j) has[P.ins[i].src[j]] = 1;
     }
     for (int q = 0; q < P.n_preds; ++q) has[P.preds[q].dst] = 1;
-    for (int sl = 0; sl < kMaxSlots; ++sl)
-      if (has[sl]) o.line("float g%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", sl);
-    o.line("if (live) root_cotangent<%s>(c, g.T, grad_out, scale, g%d);", P.root_neg ? "true" : "false", (int)P.root);
-    for (int st = n_stages - 1; st >= 0; --st) {
-      o.line("// ================= adjoint stage %d", st);
-      for (int i = P.n_instr - 1; i >= 0; --i)
-        if (ins_level[i] == st && !is_window(P.ins[i])) nary_bwd(i);
-      bool any = false;
-      for (int i = P.n_instr - 1; i >= 0; --i)
-        if (ins_level[i] == st && is_window(P.ins[i])) {
-          win_adj_a(i);
-          any = true;
+    if (cum_bwd()) {
+      for (int sl = 0; sl < kMaxSlots; ++sl)
+        if (has[sl]) {
+          o.line("V g%d[8];", sl);
+          o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) g%d[i] = V{{0.f, 0.f}};", sl);
         }
-      if (any) o.line("simt::sync();");
-      for (int i = P.n_instr - 1; i >= 0; --i)
-        if (ins_level[i] == st && is_window(P.ins[i])) win_adj_b(i);
+      o.line("if (live) root_cotangent2<%s>(c, g.T, grad_out, scale, g%d);", P.root_neg ? "true" : "false", (int)P.root);
+      cum_adjoints();
+    } else {
+      for (int sl = 0; sl < kMaxSlots; ++sl)
+        if (has[sl]) o.line("float g%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", sl);
+      o.line("if (live) root_cotangent<%s>(c, g.T, grad_out, scale, g%d);", P.root_neg ? "true" : "false", (int)P.root);
+      for (int st = n_stages - 1; st >= 0; --st) {
+        o.line("// ================= adjoint stage %d", st);
+        for (int i = P.n_instr - 1; i >= 0; --i)
+          if (ins_level[i] == st && !is_window(P.ins[i])) nary_bwd(i);
+        bool any = false;
+        for (int i = P.n_instr - 1; i >= 0; --i)
+          if (ins_level[i] == st && is_window(P.ins[i])) {
+            win_adj_a(i);
+            any = true;
+          }
+        if (any) o.line("simt::sync();");
+        for (int i = P.n_instr - 1; i >= 0; --i)
+          if (ins_level[i] == st && is_window(P.ins[i])) win_adj_b(i);
+      }
     }
     o.line("// ================= gradient of the signal: chain rule through the affine predicates");
     o.line("if (live) {");
@@ -606,7 +827,11 @@ struct Gen {
           for (int k = 0; k < P.preds[q].n_terms; ++k)
             if (P.preds[q].ch[k] == d) {
               char b[96];
-              snprintf(b, sizeof(b), "%sP.preds[%d].coeff[%d] * g%d[i]", e.empty() ? "" : " + ", q, k, (int)P.preds[q].dst);
+              if (cum_bwd())
+                snprintf(b, sizeof(b), "%sP.preds[%d].coeff[%d] * cum_pred_adj(v%d[i], g%d[i])", e.empty() ? "" : " + ", q, k, (int)P.preds[q].dst,
+                         (int)P.preds[q].dst);
+              else
+                snprintf(b, sizeof(b), "%sP.preds[%d].coeff[%d] * g%d[i]", e.empty() ? "" : " + ", q, k, (int)P.preds[q].dst);
               e += b;
             }
         o.line("gr[i][%d] = %s;", d, e.empty() ? "0.f" : e.c_str());
@@ -621,7 +846,11 @@ struct Gen {
           for (int k = 0; k < P.preds[q].n_terms; ++k)
             if (P.preds[q].ch[k] == d) {
               char b[96];
-              snprintf(b, sizeof(b), "%sP.preds[%d].coeff[%d] * g%d[i]", e.empty() ? "" : " + ", q, k, (int)P.preds[q].dst);
+              if (cum_bwd())
+                snprintf(b, sizeof(b), "%sP.preds[%d].coeff[%d] * cum_pred_adj(v%d[i], g%d[i])", e.empty() ? "" : " + ", q, k, (int)P.preds[q].dst,
+                         (int)P.preds[q].dst);
+              else
+                snprintf(b, sizeof(b), "%sP.preds[%d].coeff[%d] * g%d[i]", e.empty() ? "" : " + ", q, k, (int)P.preds[q].dst);
               e += b;
             }
         o.line("{ float gx[8]; _Pragma(\"unroll\") for (int i = 0; i < 8; ++i) gx[i] = %s; store_grad_channel(c, g.T, D, %d, gx, grad_signal); }",

@@ -440,6 +440,14 @@ struct WinOp {
   }
 };
 
+template <int VW>
+PF_DEV void stash8(float* plane, int tid, const Vec<VW> (&v)[8], int w) {
+  float t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = v[i].x[w];
+  store8(plane, tid, t);
+}
+
 // ------------------------------------------------------------------ classic unbounded until
 // W(s) = min(l_s, max(r_s, W(s+1))): a suffix scan of the clamp functions x -> min(A, max(B, x))
 // over the tile (tile_eval.h: ClampOp).  Chunk-local composition in
@@ -489,6 +497,122 @@ struct ClampScanOp {
     for (int i = 7; i >= 0; --i) {
       run = OP::comb(x[i], run);
       o[i] = OP::value(run);
+    }
+  }
+};
+
+// ------------------------------------------------------------------ until, O(b) per sample
+// OR_{i in [UA, UB]} AND(AND_{k<=i} l[t+k], r[t+i]) (api.py:284-302 + each semantics'
+// temporal_until) with the per-semantics running state of tile_eval.h (UntilState): 8 outputs
+// per thread are fed from 128-bit runs of the staged operands, no O(b^2) prefix recomputation.
+// phase1 stages both operands (negations applied); one barrier; phase2 walks the window.
+template <int SEM, int UA, int UB, int NT>
+struct UntilOp {
+  static constexpr int VW = Tr<SEM>::VW;
+  using V = Vec<VW>;
+  static constexpr int LEXT = 8 * NT;
+  static constexpr int FLOATS = 2 * VW * LEXT;
+  PF_DEV static float* lplane(float* scr, int w) { return scr + w * LEXT; }
+  PF_DEV static float* rplane(float* scr, int w) { return scr + (VW + w) * LEXT; }
+
+  PF_DEV static void phase1(float* scr, int tid, const V (&l)[8], const V (&r)[8]) {
+#pragma unroll
+    for (int w = 0; w < VW; ++w) {
+      stash8<VW>(lplane(scr, w), tid, l, w);
+      stash8<VW>(rplane(scr, w), tid, r, w);
+    }
+  }
+
+  // number of candidates of output p: min(UB, T-1-t) - UA + 1 (api.py:284-293 + classic.py:59)
+  PF_DEV static int ncand(const TC& c, int p) {
+    int last = c.nlive - 1 - p;
+    if (last > UB) last = UB;
+    return last - UA + 1;
+  }
+
+  PF_DEV static void phase2(float* scr, const TC& c, const RP& rp, float w0, float w1, V (&o)[8], UntilState<SEM> (&st)[8]) {
+    const int p0 = c.p0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st[i].init();
+    int q_hi = p0 + 7 + UB;
+    if (q_hi > c.nlive - 1) q_hi = c.nlive - 1;
+#pragma unroll 1
+    for (int f = p0 >> 2; f <= (q_hi >> 2); ++f) {
+      F4 ql[VW], qr[VW];
+#pragma unroll
+      for (int w = 0; w < VW; ++w) {
+        ql[w] = reinterpret_cast<const F4*>(lplane(scr, w))[pf4(f)];
+        qr[w] = reinterpret_cast<const F4*>(rplane(scr, w))[pf4(f)];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int q = 4 * f + k;
+        if (q > q_hi) break;
+        V l, r;
+#pragma unroll
+        for (int w = 0; w < VW; ++w) {
+          l.x[w] = ql[w].v[k];
+          r.x[w] = qr[w].v[k];
+        }
+        const int d = q - p0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int kk = d - i;  // offset inside output i's window
+          if (kk >= 0 && kk <= UB) st[i].step(l, r, kk >= UA, rp, w0, w1);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = ncand(c, p0 + i);
+      if (n <= 0 || p0 + i >= c.nlive) {
+#pragma unroll
+        for (int w = 0; w < VW; ++w) o[i].x[w] = f_nan();
+      } else {
+        o[i] = st[i].done(n, rp);
+      }
+    }
+  }
+
+  // smooth only: outputs whose shifted sums lost their precision, recomputed with per-term scales
+  PF_DEV static void smooth_fix(float* scr, const TC& c, const RP& rp, const UntilState<SEM_SMOOTH> (&st)[8], Vec<1> (&o)[8]) {
+    const float* pl = lplane(scr, 0);
+    const float* pr = rplane(scr, 0);
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      float a_i = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j == i) a_i = st[j].acc;
+      const int p = c.p0 + i;
+      const int n = ncand(c, p);
+      if (n <= 0 || p >= c.nlive || (a_i >= kSmoothTiny && a_i <= 1.0e30f)) continue;
+      const int last = n + UA - 1;
+      float mS = -f_inf(), S = 0.f, mA = -f_inf(), A = 0.f;
+      for (int kk = 0; kk <= last; ++kk) {
+        const float zl = -pl[pidx(p + kk)] * rp.k;
+        if (zl > mS) {
+          S = S * fast_ex2(mS - zl) + 1.f;
+          mS = zl;
+        } else {
+          S += fast_ex2(zl - mS);
+        }
+        if (kk >= UA) {
+          const float zr = -pr[pidx(p + kk)] * rp.k;
+          const float mc = fmaxf(mS, zr);
+          const float cl = -(mc + fast_lg2(S * fast_ex2(mS - mc) + fast_ex2(zr - mc)));  // log2 of the term
+          if (cl > mA) {
+            A = A * fast_ex2(mA - cl) + 1.f;
+            mA = cl;
+          } else {
+            A += fast_ex2(cl - mA);
+          }
+        }
+      }
+      const float res = (mA + fast_lg2(A)) * rp.invk;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j == i) o[j].x[0] = res;
     }
   }
 };
@@ -560,13 +684,6 @@ PF_DEV void smooth_fix8(const TC& c, const RP& rp, const float* vplane, const Ve
   }
 }
 
-template <int VW>
-PF_DEV void stash8(float* plane, int tid, const Vec<VW> (&v)[8], int w) {
-  float t[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) t[i] = v[i].x[w];
-  store8(plane, tid, t);
-}
 
 // ------------------------------------------------------------------ n-ary And / Or of one sample
 template <int SEM, int MODE, int N>
@@ -822,6 +939,132 @@ PF_DEV Vec<1> nary1_partials(const RP& rp, const Vec<1> (&a)[N], const float (&w
       for (int j = 0; j < N; ++j) d[j] = AD::in_factor(k, a[j].x[0], w[j], rp);
     }
     return o;
+  }
+}
+
+// ====================================================================== cumulative backward
+// Cumulative values are (pos, neg) pairs; And / Always are per-channel minima, Or maxima,
+// Eventually a SUM, Until a sum of minima (cumulative.py:35-103).  The adjoint of a sum window is
+// a backward-looking window sum like everywhere else; minima / maxima route their cotangent to ONE
+// operand, the first extremal one, like torch.min / max(dim) in the reference
+// (torch/semantics.py:253-275): the backward kernel evaluates those windows on (value, position)
+// pairs and scatters the cotangent through shared memory.
+template <int MODE>
+struct ArgRed {
+  using A = Vec<2>;  // (value, bits of the tile position)
+  static PYSTL_HD A ident() { return A{{MODE == MODE_AND ? f_inf() : -f_inf(), 0.f}}; }
+  static PYSTL_HD A comb(A a, A b) {  // a is the EARLIER operand: it keeps ties
+    const bool tb = MODE == MODE_AND ? (b.x[0] < a.x[0]) : (b.x[0] > a.x[0]);
+    return A{{tb ? b.x[0] : a.x[0], tb ? b.x[1] : a.x[1]}};
+  }
+};
+template <int MODE>
+PF_DEV void arg_lift8(const TC& c, const Vec<2> (&v)[8], int w, Vec<2> (&x)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = (c.p0 + i < c.nlive) ? Vec<2>{{v[i].x[w], i2f(c.p0 + i)}} : ArgRed<MODE>::ident();
+}
+PF_DEV void plane_zero8(float* plane, int tid) {
+  const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  store8(plane, tid, z);
+}
+// cotangent of the thread's outputs -> the positions their extremum came from
+PF_DEV void arg_scatter8(float* plane, const Vec<2> (&acc)[8], const Vec<2> (&g)[8], int w) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (g[i].x[w] != 0.f) simt::atomic_add(&plane[pidx(f2i(acc[i].x[1]))], g[i].x[w]);
+}
+// g_src (+)= the thread's chunk of the scatter planes; NEG: the operand was Not(src) = (-neg, -pos)
+template <bool NEG>
+PF_DEV void cum_accumulate8(const float* plane_pos, const float* plane_neg, int tid, Vec<2> (&gs)[8]) {
+  float a[8], b[8];
+  load8(plane_pos, tid, a);
+  load8(plane_neg, tid, b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    gs[i].x[0] += NEG ? -b[i] : a[i];
+    gs[i].x[1] += NEG ? -a[i] : b[i];
+  }
+}
+template <bool NEG>
+PF_DEV void cum_add8(const Vec<2> (&w)[8], Vec<2> (&gs)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    gs[i].x[0] += NEG ? -w[i].x[1] : w[i].x[0];
+    gs[i].x[1] += NEG ? -w[i].x[0] : w[i].x[1];
+  }
+}
+// n-ary min / max of one sample: the cotangent goes to the first extremal operand, per channel
+template <int MODE, int N>
+PF_DEV void cum_nary_bwd(const Vec<2> (&a)[N], Vec<2> g, Vec<2> (&ga)[N]) {
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    int best = 0;
+    float bv = a[0].x[w];
+#pragma unroll
+    for (int j = 1; j < N; ++j) {
+      const bool t = MODE == MODE_AND ? (a[j].x[w] < bv) : (a[j].x[w] > bv);
+      bv = t ? a[j].x[w] : bv;
+      best = t ? j : best;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) ga[j].x[w] = (j == best) ? g.x[w] : 0.f;
+  }
+}
+// root cotangent of a cumulative formula: grad_out[b, t, 2] or the constant for both channels
+template <bool NEG>
+PF_DEV void root_cotangent2(const TC& c, long long T, const float* __restrict__ grad_out, float scale, Vec<2> (&g)[8]) {
+  const float* src = grad_out ? grad_out + (c.b * T + c.origin + c.p0) * 2 : nullptr;
+  int hi = c.p_hi;
+  if (hi > c.last_ok + 1) hi = c.last_ok + 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a = 0.f, b = 0.f;
+    if (c.p0 + i < hi) {
+      a = src ? src[2 * i] : scale;
+      b = src ? src[2 * i + 1] : scale;
+    }
+    g[i] = NEG ? Vec<2>{{-b, -a}} : Vec<2>{{a, b}};
+  }
+}
+// predicate (pos, neg) = (max(0, v), min(0, v)): d/dv as torch.maximum / minimum give it
+PF_DEV float cum_pred_adj(Vec<2> v, Vec<2> g) {
+  const float x = v.x[0] + v.x[1];
+  return g.x[0] * dmax0(x) + g.x[1] * dmin0(x);
+}
+// Until: U = sum_{i in [UA, last]} min(r_i, min_{k<=i} l_k) per channel (cumulative.py:96-103).
+// Each candidate routes the cotangent to r_i or to the first prefix minimum of l (ties between
+// the two split, torch.minimum).  lpl / rpl: staged operands; gl / gr: zeroed scatter planes.
+template <int UA, int UB, int NT>
+PF_DEV void cum_until_scatter(const TC& c, const Vec<2> (&g)[8], int w, const float* lpl, const float* rpl, float* gl, float* gr) {
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    float gi = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j == i) gi = g[j].x[w];
+    if (gi == 0.f) continue;
+    const int p = c.p0 + i;
+    int last = c.nlive - 1 - p;
+    if (last > UB) last = UB;
+    float pm = f_inf();
+    int arg = p;
+    for (int kk = 0; kk <= last; ++kk) {
+      const int q = pidx(p + kk);
+      const float l = lpl[q];
+      if (l < pm) {
+        pm = l;
+        arg = q;
+      }
+      if (kk >= UA) {
+        const float r = rpl[q];
+        if (r < pm) simt::atomic_add(&gr[q], gi);
+        else if (pm < r) simt::atomic_add(&gl[arg], gi);
+        else {
+          simt::atomic_add(&gr[q], 0.5f * gi);
+          simt::atomic_add(&gl[arg], 0.5f * gi);
+        }
+      }
+    }
   }
 }
 

@@ -211,8 +211,8 @@ struct Lowerer {
       r.inv2p = (float)(0.5 / pp);
       r.p = pp;
     }
-    if (backward && sem == SEM_CUMULATIVE)
-      fail(PYSTL_E_UNSUPPORTED, "the gradient of the cumulative semantics is not implemented yet");
+    if (backward && sem == SEM_CUMULATIVE && !ssa)
+      fail(PYSTL_E_UNSUPPORTED, "the gradient of the cumulative semantics needs the fused tier (NVRTC)");
     if (sem == SEM_SMOOTH && !(f->temperature > 0.f)) fail(PYSTL_E_INVALID, "temperature must be > 0.");  // smooth.py:12-15
     if (sem == SEM_DGMSR && (!(f->eps > 0.f) || f->p < 1)) fail(PYSTL_E_INVALID, "dgmsr needs eps > 0 and p >= 1");
     const bool uses_weights = (sem == SEM_AGM || sem == SEM_DGMSR);
@@ -343,8 +343,8 @@ struct Lowerer {
           break;
         }
         case PYSTL_NODE_UNTIL: {
-          if (backward && sem != SEM_CLASSIC)
-            fail(PYSTL_E_UNSUPPORTED, "the gradient of Until is only implemented for the classical semantics so far");
+          if (backward && sem != SEM_CLASSIC && !(ssa && sem == SEM_CUMULATIVE))
+            fail(PYSTL_E_UNSUPPORTED, "the gradient of Until is implemented for the classical and cumulative semantics so far");
           if (uses_weights && (nd.w_off >= 0 || nd.w2_off >= 0))
             fail(PYSTL_E_UNSUPPORTED, "weights_left / weights_right on Until are not implemented for agm / dgmsr yet");
           float wp0 = 1.f, wp1 = 1.f;

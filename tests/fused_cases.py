@@ -52,11 +52,15 @@ def forward_cases(light: bool = False):
         for sem, kw in SEM_KW[:5]:
             out.append(dict(name=f"rand{seed}/{sem}", spec=spec, sem=sem, kw=kw, B=2, T=T, D=D, threads=32 if seed % 2 else 0, seed=3000 + seed,
                             scale=8.0 if sem == "cumulative" else 2.0))
-    # classic until: decomposed into two windows and a clamp scan
+    # until: classic is decomposed into two windows and a clamp scan,
+    # the other semantics walk the window with running state
     for cfg, D in (("cfg4", 4), ("cfg5", 8)):
-        for threads in ((64,) if light else (0, 64)):
-            out.append(dict(name=f"{cfg}/classical/nt{threads}", spec=BASELINE_SPECS[cfg], sem="classical", kw={}, B=3, T=700, D=D,
-                            threads=threads, seed=11, scale=1.0))
+        for si, (sem, kw) in enumerate(SEM_KW[:5]):
+            for threads in ((64,) if light else (0, 64)):
+                if light and si not in (0, 2):
+                    continue
+                out.append(dict(name=f"{cfg}/{sem}/nt{threads}", spec=BASELINE_SPECS[cfg], sem=sem, kw=kw, B=3, T=700, D=D,
+                                threads=threads, seed=11, scale=4.0 if sem == "cumulative" else 1.0))
     for seed in range(3 if light else 12):
         rng = np.random.default_rng(5000 + seed)
         D = int(rng.integers(1, 4))
@@ -67,9 +71,13 @@ def forward_cases(light: bool = False):
             if "until" in repr(cand):
                 spec = cand
                 break
-        if spec is not None:
-            out.append(dict(name=f"until{seed}/classical", spec=spec, sem="classical", kw={}, B=2, T=T, D=D, threads=64 if seed % 2 else 0,
-                            seed=5100 + seed, scale=1.0))
+        if spec is None:
+            continue
+        for si, (sem, kw) in enumerate(SEM_KW[:5]):
+            if light and si != seed % 5:
+                continue
+            out.append(dict(name=f"until{seed}/{sem}", spec=spec, sem=sem, kw=kw, B=2, T=T, D=D, threads=64 if seed % 2 else 0,
+                            seed=5100 + seed, scale=8.0 if sem == "cumulative" else 2.0))
     for T in (999, 1001, 1002):
         for sem, kw in (SEM_KW[0], SEM_KW[1]):
             for threads in ((32,) if light else (32, 128, 256)):
@@ -96,6 +104,24 @@ def backward_cases(light: bool = False):
                     continue
                 out.append(dict(name=f"bwd/{cfg}/{sem}{kw.get('p', '')}/nt{threads}", spec=BASELINE_SPECS[cfg], sem=sem, kw=kw, B=2,
                                 T=520, D=2, threads=threads, seed=17))
+    return out
+
+
+def cumulative_backward_cases(light: bool = False):
+    specs = {
+        "G": ("always", (0, 20), ("pred", {0: 1.0}, -0.25)),
+        "F": ("eventually", (2, 13), ("pred", {0: -1.0}, 0.5)),
+        "U": ("until", (0, 12), ("pred", {0: 1.0}, 0.0), ("pred", {1: 1.0}, -1.0)),
+        "cfg1": BASELINE_SPECS["cfg1"], "cfg2": BASELINE_SPECS["cfg2"], "cfg3": BASELINE_SPECS["cfg3"],
+        "cfg4": BASELINE_SPECS["cfg4"], "cfg5": BASELINE_SPECS["cfg5"],
+    }
+    out = []
+    for name, spec in specs.items():
+        if light and name in ("F", "cfg1", "cfg3"):
+            continue
+        for threads in ((64,) if light else (0, 64)):
+            out.append(dict(name=f"bwd/{name}/cumulative/nt{threads}", spec=spec, sem="cumulative", kw={}, B=2, T=400,
+                            D={"cfg4": 4, "cfg5": 8}.get(name, 2), threads=threads, seed=23))
     return out
 
 

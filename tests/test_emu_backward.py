@@ -44,10 +44,12 @@ GRAD_CASES = [c for c in CASES if c["grad"] and supported(c)]
 
 
 def oracle_grad(spec, sem, kw, sig64, g64):
+    """d sum(g * out) / d signal by autograd through the dense oracle (cumulative: g is [B, T, 2])."""
     x = torch.tensor(sig64, requires_grad=True)
     out = dense.robustness_trace(from_spec(spec), x, dense.make(sem, **kw))
     live = ~torch.isnan(out)
-    (torch.where(live, out, torch.zeros_like(out)) * torch.tensor(g64) * live).sum().backward()
+    g = torch.tensor(np.moveaxis(g64, -1, 0)) if sem == "cumulative" else torch.tensor(g64)
+    (torch.where(live, out, torch.zeros_like(out)) * g * live).sum().backward()
     return x.grad.numpy()
 
 

@@ -60,3 +60,20 @@ def test_smooth_extreme_dynamic_range_is_exact():
     g = rng.standard_normal((2, 300)).astype(np.float32).astype(np.float64)
     gb = fused_emu_lib.eval_backward(from_spec(spec), "smooth", sig, g, force_threads=64, **kw)
     check(gb.astype(np.float64), oracle_grad(spec, "smooth", kw, sig, g), "smooth", "cfg2/tau0.01", rtol, atol)
+
+
+from fused_cases import cumulative_backward_cases  # noqa: E402
+
+CBWD = cumulative_backward_cases(light=True)
+
+
+@pytest.mark.parametrize("case", CBWD, ids=[c["name"] for c in CBWD])
+def test_cumulative_backward(case):
+    """Sum windows, arg-min / arg-max routing, until: against autograd through the dense oracle
+    (torch.min / max(dim) and torch.minimum routing of the reference, torch/semantics.py:253-345)."""
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    B, T = sig.shape[:2]
+    g = rng.standard_normal((B, T, 2)).astype(np.float32).astype(np.float64)
+    got = fused_emu_lib.eval_backward(from_spec(case["spec"]), "cumulative", sig, g, force_threads=case["threads"])
+    check(got.astype(np.float64), oracle_grad(case["spec"], "cumulative", {}, sig, g), "cumulative", case["name"], 4e-5, 4e-5)

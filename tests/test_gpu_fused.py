@@ -173,3 +173,30 @@ def test_smooth_extreme_dynamic_range_is_exact_on_the_fused_tier():
             g = rng.standard_normal((2, 300)).astype(np.float32).astype(np.float64)
             gb = gpu_grad(BASELINE_SPECS[cfg], "smooth", kw, sig, g, "fused", threads)
             check(gb, oracle_grad(BASELINE_SPECS[cfg], "smooth", kw, sig, g), "smooth", cfg, rtol, atol)
+
+
+from fused_cases import cumulative_backward_cases  # noqa: E402
+
+CBWD = cumulative_backward_cases()
+
+
+@pytest.mark.parametrize("case", CBWD, ids=[c["name"] for c in CBWD])
+def test_cumulative_backward(case):
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    B, T = sig.shape[:2]
+    g = rng.standard_normal((B, T, 2)).astype(np.float32).astype(np.float64)
+    got = gpu_grad(case["spec"], "cumulative", {}, sig, g, "fused", case["threads"])
+    check(got, oracle_grad(case["spec"], "cumulative", {}, sig, g), "cumulative", case["name"], 4e-5, 4e-5)
+
+
+def test_cumulative_autograd_through_the_public_api():
+    rng = np.random.default_rng(31)
+    sig = (rng.uniform(-1, 3, size=(3, 1, 4)) + 0.5 * rng.standard_normal((3, 300, 4))).astype(np.float32)
+    x = torch.tensor(sig, device="cuda", requires_grad=True)
+    s = create_semantics("cumulative", backend="b200")
+    rho = s.robustness_trace(from_spec(BASELINE_SPECS["cfg4"]), x)
+    (rho.pos + rho.neg).mean().backward()
+    g = np.full((3, 300, 2), 1.0 / (3 * 300))
+    want = oracle_grad(BASELINE_SPECS["cfg4"], "cumulative", {}, sig.astype(np.float64), g)
+    check(x.grad.double().cpu().numpy(), want, "cumulative", "cfg4/autograd", 4e-5, 4e-5)
