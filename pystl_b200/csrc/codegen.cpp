@@ -90,6 +90,11 @@ struct Gen {
   int fix_off = 0, flag_off = 0;   // smooth backward: exact-scatter plane, per-window lost flags
   int sp_off = 0;                  // cumulative backward: four scatter planes
   bool cum_bwd() const { return bwd && P.sem == SEM_CUMULATIVE; }
+  bool has_until() const {
+    for (int i = 0; i < P.n_instr; ++i)
+      if (is_until(P.ins[i])) return true;
+    return false;
+  }
   bool arg_window(const TInstr& in) const { return cum_bwd() && is_window(in) && in.mode != MODE_SUM; }
 
   Gen(const Lowered& l, int D_, int nt_, int minb_, bool bwd_) : lw(l), P(l.prog), D(D_), nt(nt_), minb(minb_), bwd(bwd_) {}
@@ -110,7 +115,7 @@ struct Gen {
     for (int i = 0; i < P.n_instr; ++i) {
       const TInstr& in = P.ins[i];
       if (is_scan(in) && P.sem == SEM_CLASSIC && !bwd) continue;
-      if (is_until(in) && (!bwd || P.sem == SEM_CUMULATIVE)) continue;
+      if (is_until(in) && (!bwd || P.sem == SEM_CUMULATIVE || (P.sem == SEM_SMOOTH && in.b <= 1024))) continue;
       if (in.op != T_NARY && !is_window(in)) {
         *why = "until / open-ended windows are evaluated by the interpreter tier";
         return false;
@@ -155,7 +160,7 @@ struct Gen {
       flag_off = red_floats + persist;
       persist += roundup(P.n_instr, 4);
     }
-    if (cum_bwd()) {
+    if (cum_bwd() || (bwd && P.sem == SEM_SMOOTH && has_until())) {
       sp_off = red_floats + persist;
       persist += 4 * 8 * nt;
       for (int i = 0; i < P.n_instr; ++i)
@@ -173,7 +178,7 @@ struct Gen {
         continue;
       }
       if (is_until(in)) {
-        if (cum_bwd()) continue;  // persistent (above)
+        if (bwd) continue;  // persistent (above): the adjoint re-reads the staged operands
         scr_off[i] = used[ins_level[i]];
         used[ins_level[i]] += 2 * vw() * 8 * nt;  // UntilOp::FLOATS
         continue;
@@ -199,7 +204,7 @@ struct Gen {
     }
     const int base0 = red_floats + persist, base1 = base0 + reg[0];
     for (int i = 0; i < P.n_instr; ++i) {
-      if (is_scan(P.ins[i]) || (is_until(P.ins[i]) && !cum_bwd())) scr_off[i] += (ins_level[i] & 1) ? base1 : base0;
+      if (is_scan(P.ins[i]) || (is_until(P.ins[i]) && !bwd)) scr_off[i] += (ins_level[i] & 1) ? base1 : base0;
       if (!is_window(P.ins[i])) continue;
       const int l = ins_level[i];
       scr_off[i] += (l & 1) ? base1 : base0;
@@ -763,6 +768,26 @@ struct Gen {
     }
   }
 
+  void until_adj_smooth(int i) {
+    const TInstr& in = P.ins[i];
+    const int L = 8 * nt;
+    const bool nl = in.negmask & 1, nr = in.negmask & 2;
+    o.line("// adjoint of until %d: log-domain sweeps, scatter through shared memory", i);
+    o.line("plane_zero8(smem + %d, c.tid);", sp_off);
+    o.line("plane_zero8(smem + %d, c.tid);", sp_off + L);
+    o.line("simt::sync();");
+    o.line("if (live) smooth_until_scatter<%d, %d, NT>(c, rp, g%d, U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), smem + %d, smem + %d);",
+           in.a, in.b, (int)in.dst, i, scr_off[i], i, scr_off[i], sp_off, sp_off + L);
+    o.line("simt::sync();");
+    o.line("if (live) {");
+    o.indent++;
+    o.line("accumulate8<%s>(smem + %d, c.tid, g%d);", nl ? "true" : "false", sp_off, (int)in.src[0]);
+    o.line("accumulate8<%s>(smem + %d, c.tid, g%d);", nr ? "true" : "false", sp_off + L, (int)in.src[1]);
+    o.indent--;
+    o.line("}");
+    o.line("simt::sync();");
+  }
+
   std::string backward() {
     plan();
     plan_bounds();
@@ -802,7 +827,9 @@ struct Gen {
       for (int st = n_stages - 1; st >= 0; --st) {
         o.line("// ================= adjoint stage %d", st);
         for (int i = P.n_instr - 1; i >= 0; --i)
-          if (ins_level[i] == st && !is_window(P.ins[i])) nary_bwd(i);
+          if (ins_level[i] == st && !is_staged(P.ins[i])) nary_bwd(i);
+        for (int i = P.n_instr - 1; i >= 0; --i)
+          if (ins_level[i] == st && is_until(P.ins[i])) until_adj_smooth(i);
         bool any = false;
         for (int i = P.n_instr - 1; i >= 0; --i)
           if (ins_level[i] == st && is_window(P.ins[i])) {

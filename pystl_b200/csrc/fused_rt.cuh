@@ -942,6 +942,66 @@ PF_DEV Vec<1> nary1_partials(const RP& rp, const Vec<1> (&a)[N], const float (&w
   }
 }
 
+PF_DEV void plane_zero8(float* plane, int tid) {
+  const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  store8(plane, tid, z);
+}
+
+// ---- smooth until, backward.  U = tau ln A, A = sum_{i>=UA} t_i, t_i = 1 / (S_i + rho_i),
+// S_i = sum_{k<=i} lambda_k, lambda = e^{-l/tau}, rho = e^{-r/tau}, hence
+//   dU/dr_i = t_i^2 rho_i / A,   dU/dl_k = lambda_k (sum_{i >= max(k, UA)} t_i^2) / A.
+// Everything is carried in the log2 domain (c_i = log2 t_i in a per-thread scratch array), so the
+// weights are exact for any temperature: every exponent below is <= log2(b + 1).
+PF_DEV float lse2(float a, float b) {  // log2(2^a + 2^b)
+  const float m = fmaxf(a, b);
+  return m + fast_lg2(fast_ex2(a - m) + fast_ex2(b - m));
+}
+template <int UA, int UB, int NT>
+PF_DEV void smooth_until_scatter(const TC& c, const RP& rp, const float (&g)[8], const float* lpl, const float* rpl, float* gl,
+                                 float* gr) {
+  float cbuf[UB + 1];
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    float gi = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j == i) gi = g[j];
+    const int p = c.p0 + i;
+    int last = c.nlive - 1 - p;
+    if (last > UB) last = UB;
+    if (gi == 0.f || last < UA) continue;
+    float LS = -f_inf(), LA = -f_inf();
+    for (int kk = 0; kk <= last; ++kk) {
+      const int q = pidx(p + kk);
+      const float zl = -lpl[q] * rp.k;
+      LS = kk == 0 ? zl : lse2(LS, zl);
+      if (kk >= UA) {
+        const float ci = -lse2(LS, -rpl[q] * rp.k);
+        cbuf[kk] = ci;
+        LA = kk == UA ? ci : lse2(LA, ci);
+      }
+    }
+    float LD = -f_inf();
+    for (int kk = last; kk >= 0; --kk) {
+      const int q = pidx(p + kk);
+      if (kk >= UA) {
+        const float ci = cbuf[kk];
+        LD = kk == last ? 2.f * ci : lse2(LD, 2.f * ci);
+        simt::atomic_add(&gr[q], gi * fast_ex2(2.f * ci - rpl[q] * rp.k - LA));
+      }
+      simt::atomic_add(&gl[q], gi * fast_ex2(LD - lpl[q] * rp.k - LA));
+    }
+  }
+}
+// g_src (+)= the thread's chunk of a scatter plane
+template <bool NEG>
+PF_DEV void accumulate8(const float* plane, int tid, float (&gs)[8]) {
+  float t[8];
+  load8(plane, tid, t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gs[i] += NEG ? -t[i] : t[i];
+}
+
 // ====================================================================== cumulative backward
 // Cumulative values are (pos, neg) pairs; And / Always are per-channel minima, Or maxima,
 // Eventually a SUM, Until a sum of minima (cumulative.py:35-103).  The adjoint of a sum window is
@@ -962,10 +1022,6 @@ template <int MODE>
 PF_DEV void arg_lift8(const TC& c, const Vec<2> (&v)[8], int w, Vec<2> (&x)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = (c.p0 + i < c.nlive) ? Vec<2>{{v[i].x[w], i2f(c.p0 + i)}} : ArgRed<MODE>::ident();
-}
-PF_DEV void plane_zero8(float* plane, int tid) {
-  const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  store8(plane, tid, z);
 }
 // cotangent of the thread's outputs -> the positions their extremum came from
 PF_DEV void arg_scatter8(float* plane, const Vec<2> (&acc)[8], const Vec<2> (&g)[8], int w) {

@@ -343,8 +343,8 @@ struct Lowerer {
           break;
         }
         case PYSTL_NODE_UNTIL: {
-          if (backward && sem != SEM_CLASSIC && !(ssa && sem == SEM_CUMULATIVE))
-            fail(PYSTL_E_UNSUPPORTED, "the gradient of Until is implemented for the classical and cumulative semantics so far");
+          if (backward && sem != SEM_CLASSIC && !(ssa && (sem == SEM_CUMULATIVE || sem == SEM_SMOOTH)))
+            fail(PYSTL_E_UNSUPPORTED, "the gradient of Until is implemented for the classical, smooth and cumulative semantics so far");
           if (uses_weights && (nd.w_off >= 0 || nd.w2_off >= 0))
             fail(PYSTL_E_UNSUPPORTED, "weights_left / weights_right on Until are not implemented for agm / dgmsr yet");
           float wp0 = 1.f, wp1 = 1.f;

@@ -107,6 +107,23 @@ def backward_cases(light: bool = False):
     return out
 
 
+def smooth_until_backward_cases(light: bool = False):
+    specs = {
+        "U": ("until", (0, 12), ("pred", {0: 1.0}, 0.0), ("pred", {1: 1.0}, -1.0)),
+        "U2": ("until", (2, 9), ("not", ("pred", {0: 1.0}, 0.0)), ("pred", {1: 1.0}, -1.0)),
+        "cfg4": BASELINE_SPECS["cfg4"], "cfg5": BASELINE_SPECS["cfg5"],
+    }
+    out = []
+    for tau in (0.5, 0.02):
+        for name, spec in specs.items():
+            if light and (name == "U2") != (tau == 0.02):
+                continue
+            for threads in ((64,) if light else (0, 64)):
+                out.append(dict(name=f"bwd/{name}/smooth{tau}/nt{threads}", spec=spec, sem="smooth", kw={"temperature": tau}, B=2, T=300,
+                                D={"cfg4": 4, "cfg5": 8}.get(name, 2), threads=threads, seed=29))
+    return out
+
+
 def cumulative_backward_cases(light: bool = False):
     specs = {
         "G": ("always", (0, 20), ("pred", {0: 1.0}, -0.25)),

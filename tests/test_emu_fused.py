@@ -77,3 +77,19 @@ def test_cumulative_backward(case):
     g = rng.standard_normal((B, T, 2)).astype(np.float32).astype(np.float64)
     got = fused_emu_lib.eval_backward(from_spec(case["spec"]), "cumulative", sig, g, force_threads=case["threads"])
     check(got.astype(np.float64), oracle_grad(case["spec"], "cumulative", {}, sig, g), "cumulative", case["name"], 4e-5, 4e-5)
+
+
+from fused_cases import smooth_until_backward_cases  # noqa: E402
+
+UBWD = smooth_until_backward_cases(light=True)
+
+
+@pytest.mark.parametrize("case", UBWD, ids=[c["name"] for c in UBWD])
+def test_smooth_until_backward(case):
+    """Gradient of the smooth Until (closed form of SURVEY.md appendix A4, log-domain sweeps)."""
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    g = rng.standard_normal(sig.shape[:2]).astype(np.float32).astype(np.float64)
+    got = fused_emu_lib.eval_backward(from_spec(case["spec"]), "smooth", sig, g, force_threads=case["threads"], **case["kw"])
+    rtol, atol = grad_tol("smooth", case["kw"])
+    check(got.astype(np.float64), oracle_grad(case["spec"], "smooth", case["kw"], sig, g), "smooth", case["name"], rtol, atol)

@@ -200,3 +200,18 @@ def test_cumulative_autograd_through_the_public_api():
     g = np.full((3, 300, 2), 1.0 / (3 * 300))
     want = oracle_grad(BASELINE_SPECS["cfg4"], "cumulative", {}, sig.astype(np.float64), g)
     check(x.grad.double().cpu().numpy(), want, "cumulative", "cfg4/autograd", 4e-5, 4e-5)
+
+
+from fused_cases import smooth_until_backward_cases  # noqa: E402
+
+UBWD = smooth_until_backward_cases()
+
+
+@pytest.mark.parametrize("case", UBWD, ids=[c["name"] for c in UBWD])
+def test_smooth_until_backward(case):
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    g = rng.standard_normal(sig.shape[:2]).astype(np.float32).astype(np.float64)
+    got = gpu_grad(case["spec"], "smooth", case["kw"], sig, g, "fused", case["threads"])
+    rtol, atol = grad_tol("smooth", case["kw"])
+    check(got, oracle_grad(case["spec"], "smooth", case["kw"], sig, g), "smooth", case["name"], rtol, atol)
