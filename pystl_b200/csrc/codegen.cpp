@@ -573,6 +573,7 @@ struct Gen {
   void emit_header(const char* what) {
     o.indent = 0;
     o.line("// generated by pystl_b200/csrc/codegen.cpp -- %s kernel of one formula (fused tier)", what);
+    if (P.sem == SEM_DGMSR) o.line("#define PYSTL_CONST_P %d  // dgmsr exponent, baked in", (int)P.rp.p);
     o.line("#include \"fused_rt.cuh\"");
     o.line("using namespace pystl;");
     o.line("using namespace pystl::fused;");

@@ -119,24 +119,21 @@ struct Adj<SEM_DGMSR, MODE> {
   static PYSTL_HD Vec<2> out_coeff(float g, float o, float sw, const RP& rp, bool& lost) {
     lost = false;
     const float h = MODE == MODE_AND ? o : -o;
-    if (h <= 0.f) {
-      const float rmp = rp.sqrt_eps - h;  // sqrt(mp)
-      // mp^(1/2 - p) / sw
-      const float c = rp.p == 1 ? fast_rcp(rmp) : fast_pow(rmp, 1.f - 2.f * (float)rp.p);
-      return Vec<2>{{g * c * fast_rcp(sw), 0.f}};
-    }
-    const float rm0 = h + rp.sqrt_eps;  // sqrt(m0)
-    const float ratio = fast_exp(sw * (rp.ln_eps - 2.f * fast_ln(rm0)));  // (eps / m0)^sw
-    return Vec<2>{{0.f, g * rm0 * (1.f - ratio) * fast_rcp(sw)}};
+    const float gs = g * fast_rcp(sw);
+    // arithmetic branch (h <= 0): mp^(1/2 - p) / sw with sqrt(mp) = sqrt(eps) - h
+    const float rmp = rp.sqrt_eps - h;
+    const float cn = PYSTL_P(rp) == 1 ? fast_rcp(rmp) : fast_pow(fmaxf(rmp, 1e-30f), 1.f - 2.f * (float)PYSTL_P(rp));
+    // geometric branch: sqrt(m0) (1 - (eps / m0)^sw) / sw with sqrt(m0) = h + sqrt(eps)
+    const float rm0 = h + rp.sqrt_eps;
+    const float ratio = fast_exp(sw * (rp.ln_eps - 2.f * fast_ln(fmaxf(rm0, 1e-30f))));
+    const bool neg = h <= 0.f;
+    return Vec<2>{{neg ? gs * cn : 0.f, neg ? 0.f : gs * rm0 * (1.f - ratio)}};
   }
   static PYSTL_HD float in_factor(Vec<2> w, float x, float wt, const RP& rp) {
     const float u = MODE == MODE_AND ? x : -x;
-    if (u <= 0.f) {
-      const float au = -u;
-      const float pw = rp.p == 1 ? au : (au > 0.f ? fast_pow(au, 2.f * (float)rp.p - 1.f) : 0.f);
-      return wt * w.x[0] * pw;
-    }
-    return wt * w.x[1] * fast_rcp(u);
+    const float au = fabsf(u);
+    const float pw = PYSTL_P(rp) == 1 ? au : (au > 0.f ? fast_pow(au, 2.f * (float)PYSTL_P(rp) - 1.f) : 0.f);
+    return wt * ((u <= 0.f) ? w.x[0] * pw : w.x[1] * fast_rcp(au));
   }
 };
 

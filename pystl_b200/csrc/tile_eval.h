@@ -43,6 +43,14 @@
 #define PYSTL_HD inline
 #endif
 
+// D-GMSR exponent p: a run-time parameter of the interpreter tier; the fused tier bakes it into the
+// generated kernel (PYSTL_CONST_P) so that the p == 1 fast paths fold at compile time.
+#if defined(PYSTL_CONST_P)
+#define PYSTL_P(rp) (PYSTL_CONST_P)
+#else
+#define PYSTL_P(rp) ((rp).p)
+#endif
+
 #define PYSTL_FOR_THREADS(ex, tid) for (int tid = (ex).t0(), tid##_end_ = (ex).t1(); tid < tid##_end_; ++tid)
 
 namespace pystl {
@@ -232,9 +240,8 @@ struct Red<SEM_AGM, MODE> {
   static PYSTL_HD A comb(A a, A b) { return A{{a.x[0] + b.x[0], a.x[1] + b.x[1]}}; }
   static PYSTL_HD V fin(A a, float sw, const RP&) {
     const float inv = fast_rcp(sw);
-    if (a.x[1] == f_inf()) return V{{a.x[0] * inv}};
-    const float g = fast_expm1(a.x[1] * inv);
-    return V{{MODE == MODE_AND ? g : -g}};
+    const float g = fast_expm1(a.x[1] * inv);  // (+inf when an entry took the arithmetic branch: discarded)
+    return V{{(a.x[1] == f_inf()) ? a.x[0] * inv : (MODE == MODE_AND ? g : -g)}};
   }
 };
 
@@ -247,24 +254,23 @@ struct Red<SEM_DGMSR, MODE> {
   static PYSTL_HD A ident() { return A{{0.f, 0.f}}; }
   static PYSTL_HD A lift(V v, const RP& rp, float w) {
     const float x = MODE == MODE_AND ? v.x[0] : -v.x[0];
-    if (x <= 0.f) {
-      const float x2 = x * x;
-      return A{{w * (rp.p == 1 ? x2 : (x2 > 0.f ? fast_pow(x2, (float)rp.p) : 0.f)), f_inf()}};
-    }
-    return A{{0.f, 2.f * w * fast_ln(x)}};
+    const float x2 = x * x;
+    const bool neg = x <= 0.f;
+    const float pw = PYSTL_P(rp) == 1 ? x2 : (x2 > 0.f ? fast_pow(x2, (float)PYSTL_P(rp)) : 0.f);
+    // (the logarithm of a non-positive x is discarded by the select)
+    return A{{neg ? w * pw : 0.f, neg ? f_inf() : 2.f * w * fast_ln(x)}};
   }
   static PYSTL_HD A comb(A a, A b) { return A{{a.x[0] + b.x[0], a.x[1] + b.x[1]}}; }
   static PYSTL_HD V fin(A a, float sw, const RP& rp) {
-    float h;
-    if (a.x[1] == f_inf()) {  // _dgmsr.py:83-87
-      const float m = rp.eps_p + a.x[0] * fast_rcp(sw);
-      h = rp.sqrt_eps - (rp.p == 1 ? fast_sqrt(m) : fast_pow(m, rp.inv2p));
-    } else {  // _dgmsr.py:96-102, in the log domain: ln m0 = logaddexp(sw ln eps, sum 2w ln v) / sw
-      const float u = sw * rp.ln_eps, s = a.x[1];
-      const float hi = fmaxf(u, s), lo = fminf(u, s);
-      const float lm0 = (hi + fast_log1p(fast_exp(lo - hi))) * fast_rcp(sw);
-      h = fast_exp(0.5f * lm0) - rp.sqrt_eps;
-    }
+    const float inv = fast_rcp(sw);
+    // _dgmsr.py:83-87
+    const float m = rp.eps_p + a.x[0] * inv;
+    const float hn = rp.sqrt_eps - (PYSTL_P(rp) == 1 ? fast_sqrt(m) : fast_pow(m, rp.inv2p));
+    // _dgmsr.py:96-102, in the log domain: ln m0 = logaddexp(sw ln eps, sum 2w ln v) / sw
+    const float u = sw * rp.ln_eps, s = a.x[1];
+    const float lm0 = (fmaxf(u, s) + fast_log1p(fast_exp(-fabsf(u - s)))) * inv;
+    const float hp = fast_exp(0.5f * lm0) - rp.sqrt_eps;
+    const float h = (a.x[1] == f_inf()) ? hn : hp;
     return V{{MODE == MODE_AND ? h : -h}};
   }
 };
