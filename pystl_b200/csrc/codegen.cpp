@@ -89,6 +89,8 @@ struct Gen {
   std::vector<int> bscr_off;       // per instruction: scratch of the adjoint window
   int fix_off = 0, flag_off = 0;   // smooth backward: exact-scatter plane, per-window lost flags
   int sp_off = 0;                  // cumulative backward: four scatter planes
+  int stage_off = 0;               // cooperative row staging (aliases the scratch regions)
+  bool coop_stage() const { return D >= 4 && D <= 8; }
   bool cum_bwd() const { return bwd && P.sem == SEM_CUMULATIVE; }
   bool has_until() const {
     for (int i = 0; i < P.n_instr; ++i)
@@ -212,6 +214,10 @@ struct Gen {
       bscr_off[i] += ((l + 1) & 1) ? base1 : base0;
     }
     smem_floats = base1 + reg[1];
+    if (coop_stage()) {  // staging area of the signal rows: shares storage with the scratch regions
+      stage_off = base0;
+      smem_floats = std::max(smem_floats, base0 + 8 * nt * D);
+    }
   }
 
   // expression of operand j of instruction `in` at sample i
@@ -257,7 +263,9 @@ struct Gen {
     o.indent++;
     if (D <= 8) {
       o.line("float r[8][D];");
-      o.line("load_rows<D>(c, signal, g.T, r);");
+      if (coop_stage()) o.line("load_rows_coop<D>(c, signal, g.T, smem + %d, r);  // coalesced, transposed through shared memory", stage_off);
+      else o.line("load_rows<D>(c, signal, g.T, r);");
+      o.line("prefetch_rows<D>(c, signal, g.B, g.T, g.scr_planes);  // (scr_planes carries the prefetch distance in traces)");
     }
     for (int q = 0; q < P.n_preds; ++q) {
       const TPred& pr = P.preds[q];
@@ -294,6 +302,7 @@ struct Gen {
     }
     o.indent--;
     o.line("}");
+    if (coop_stage()) o.line("simt::sync();  // the staging area is reused as window scratch");
     if (P.sem == SEM_SMOOTH) {
       int nb = 0;
       for (int q = 0; q < P.n_preds; ++q) nb += need_lo[P.preds[q].dst] + need_hi[P.preds[q].dst];

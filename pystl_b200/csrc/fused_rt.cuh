@@ -32,6 +32,7 @@ PF_DEV int tid() { return (int)threadIdx.x; }
 PF_DEV int bid_x() { return (int)blockIdx.x; }
 PF_DEV int bid_y() { return (int)blockIdx.y; }
 PF_DEV void sync() { __syncthreads(); }
+PF_DEV void syncwarp() { __syncwarp(); }
 PF_DEV float shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 PF_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 PF_DEV int redux_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }
@@ -94,6 +95,30 @@ PF_DEV bool alive(const TC& c) { return c.p0 < c.nlive; }
 // The thread's 8 rows are 8*D consecutive floats of the trace: 128-bit loads when they all
 // exist and the address is 16-byte aligned, guarded scalar loads otherwise (rows past the
 // horizon read as 0 and are never consumed: the lifts replace them by the identity).
+// L2 prefetch of the rows the SAME tile of trace b + ahead will load: CTAs are scheduled in trace
+// order, so a CTA that starts `ahead` traces later finds its rows in L2 instead of HBM
+// (the load latency at the head of every CTA was the top stall reason in the ncu profiles).
+PF_DEV void prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+template <int D>
+PF_DEV void prefetch_rows(const TC& c, const float* __restrict__ signal, long long B, long long T, int ahead) {
+  if (ahead <= 0 || c.b + ahead >= B || !own_all_live(c)) return;
+  const char* src = reinterpret_cast<const char*>(signal + (((c.b + ahead) * T + c.origin + c.p0) * (long long)D));
+  constexpr int BYTES = 8 * D * 4;  // this thread's rows
+  if constexpr (BYTES >= 128) {
+#pragma unroll
+    for (int k = 0; k < BYTES / 128; ++k) prefetch_l2(src + 128 * k);
+  } else {
+    // several threads share a 128-byte line: one of them prefetches it
+    if ((c.tid % (128 / BYTES)) == 0) prefetch_l2(src);
+  }
+}
+
 template <int D>
 PF_DEV void load_rows(const TC& c, const float* __restrict__ signal, long long T, float (&r)[8][D]) {
   const float* src = signal + ((c.b * T + c.origin + c.p0) * (long long)D);
@@ -120,6 +145,44 @@ PF_DEV void load_rows(const TC& c, const float* __restrict__ signal, long long T
     }
   }
 }
+// Wide rows (D >= 4): a thread's 8 rows are 128+ bytes apart from its neighbour's, so per-thread
+// 128-bit loads touch 32 different lines per instruction and saturate the L1 pipeline (ncu: "Mem
+// Busy" 90 % on cfg5).  Instead the warp loads its 32 * 8 * D contiguous floats with fully
+// coalesced 128-bit loads and transposes them through its own slice of shared memory; the slice
+// is swizzled so that both the coalesced stores and the per-thread row reads are conflict-free.
+// Only the warp synchronises.  stage: this CTA's staging area (8 * NT * D floats).
+template <int D>
+PF_DEV void load_rows_coop(const TC& c, const float* __restrict__ signal, long long T, float* stage, float (&r)[8][D]) {
+  constexpr int R = 2 * D;  // 16-byte granules per thread
+  const int lane = c.tid & 31, w0 = c.tid & ~31;
+  const float* src = signal + ((c.b * T + c.origin + 8 * w0) * (long long)D);
+  const bool coop = 8 * w0 + 256 <= c.nlive && ((u64)src & 15ull) == 0ull;  // warp-uniform
+  if (!coop) {
+    load_rows<D>(c, signal, T, r);
+    return;
+  }
+  F4* st4 = reinterpret_cast<F4*>(stage) + w0 * R;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int gidx = k * 32 + lane;
+#if defined(__CUDA_ARCH__)
+    const float4 q = __ldg(reinterpret_cast<const float4*>(src) + gidx);
+    const F4 f = F4{{q.x, q.y, q.z, q.w}};
+#else
+    const F4 f = reinterpret_cast<const F4*>(src)[gidx];
+#endif
+    st4[gidx ^ ((gidx >> (R <= 8 ? 3 : 4)) & 7)] = f;
+  }
+  simt::syncwarp();
+#pragma unroll
+  for (int m = 0; m < R; ++m) {
+    const int gidx = R * lane + m;
+    const F4 f = st4[gidx ^ ((gidx >> (R <= 8 ? 3 : 4)) & 7)];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[(4 * m + e) / D][(4 * m + e) % D] = f.v[e];
+  }
+}
+
 // one channel of a wide signal (D > 8): strided scalar loads
 PF_DEV void load_channel(const TC& c, const float* __restrict__ signal, long long T, int D, int ch, float (&x)[8]) {
   const float* src = signal + ((c.b * T + c.origin + c.p0) * (long long)D) + ch;

@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 
 #include "../../include/pystl_b200.h"
@@ -84,6 +85,15 @@ static int fused_prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t
   if (rc) return rc;
   if (fs->smem_floats * 4 > 227 * 1024) return set_err(PYSTL_E_UNSUPPORTED, "fused kernel needs %d bytes of shared memory", fs->smem_floats * 4);
   g->smem_floats = fs->smem_floats;
+  // L2 prefetch distance in traces (fused_rt.cuh: prefetch_rows): a little more than one wave of
+  // resident CTAs ahead.  TileGeom::scr_planes is unused by the fused tier and carries it.
+  {
+    const char* e = getenv("PYSTL_B200_PREFETCH");
+    const int regs = backward ? 96 : 64;
+    int per_sm = std::min(65536 / (g->nt * regs), std::min(227 * 1024 / (fs->smem_floats * 4 + 1024), 2048 / g->nt));
+    if (per_sm < 1) per_sm = 1;
+    g->scr_planes = e ? atoi(e) : (148 * per_sm * 5) / 4;
+  }
   return PYSTL_OK;
 }
 

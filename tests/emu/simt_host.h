@@ -87,6 +87,8 @@ inline void warp_sync() {
   }
 }
 
+inline void syncwarp() { warp_sync(); }
+
 // warp collectives (all lanes of the warp must call them)
 inline float shfl_idx(float v, int src_lane) {
   Launch* L = cur_launch();
