@@ -31,6 +31,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -264,6 +266,12 @@ def run_b200(args) -> None:
     n_valid = B * max(T - plan["start_slack"], 0)
     launches = 0
     tier = tier_of(lib, cf, T, D, with_bwd)
+    if tier == "fused":  # report the geometry of the kernel that actually runs
+        import ctypes
+
+        fp = capi.Plan()
+        if lib.pystl_b200_fused_plan(cf.ptr(), T, D, int(with_bwd), ctypes.byref(fp)) == 0:
+            plan = fp.as_dict()
     # the interpreter tier has no fused value-and-gradient kernel: forward + backward launches
     launches_per_step = 2 if (with_bwd and tier == "interpreter") else 1
 

@@ -167,6 +167,9 @@ int pystl_b200_eval_value_and_grad(const pystl_formula_t* formula, const float* 
  * needs no GPU.  PYSTL_E_UNSUPPORTED: this formula runs on the interpreter tier.
  * source: the generated CUDA source (inspection); returns its length. */
 int pystl_b200_fused_precompile(const pystl_formula_t* formula, int64_t T, int32_t D, int32_t backward);
+/* tile geometry of the fused kernel (threads, tile_ext, tile_out, n_tiles, smem_bytes) */
+int pystl_b200_fused_plan(const pystl_formula_t* formula, int64_t T, int32_t D, int32_t backward,
+                          pystl_plan_t* plan);
 int pystl_b200_fused_source(const pystl_formula_t* formula, int64_t T, int32_t D, int32_t backward,
                             char* buf, int32_t len);
 

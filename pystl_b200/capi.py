@@ -91,6 +91,7 @@ EXPORTS = (
     "pystl_b200_eval_backward",
     "pystl_b200_eval_value_and_grad",
     "pystl_b200_fused_precompile",
+    "pystl_b200_fused_plan",
     "pystl_b200_fused_source",
 )
 
@@ -133,6 +134,9 @@ def declare(lib: C.CDLL, prefix: str = "pystl_b200") -> None:
         f = lib.pystl_b200_fused_precompile
         f.restype = C.c_int
         f.argtypes = [C.POINTER(Formula), C.c_int64, C.c_int32, C.c_int32]
+        f = lib.pystl_b200_fused_plan
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(Formula), C.c_int64, C.c_int32, C.c_int32, C.POINTER(Plan)]
         f = lib.pystl_b200_fused_source
         f.restype = C.c_int
         f.argtypes = [C.POINTER(Formula), C.c_int64, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]

@@ -70,8 +70,9 @@ const char* mode_name(int m) { return m == MODE_AND ? "MODE_AND" : (m == MODE_OR
 bool is_window(const TInstr& in) { return in.op == T_WIN_DIRECT || in.op == T_WIN_VH; }
 bool is_scan(const TInstr& in) { return in.op == T_CLAMP_SCAN; }
 bool is_until(const TInstr& in) { return in.op == T_UNTIL && !in.unbounded; }
+bool is_wwin(const TInstr& in) { return in.op == T_WIN_WEIGHTED; }
 // instructions whose result needs one barrier (phase 1 | barrier | phase 2)
-bool is_staged(const TInstr& in) { return is_window(in) || is_scan(in) || is_until(in); }
+bool is_staged(const TInstr& in) { return is_window(in) || is_scan(in) || is_until(in) || is_wwin(in); }
 
 struct Gen {
   const Lowered& lw;
@@ -118,6 +119,7 @@ struct Gen {
       const TInstr& in = P.ins[i];
       if (is_scan(in) && P.sem == SEM_CLASSIC && !bwd) continue;
       if (is_until(in) && (!bwd || P.sem == SEM_CUMULATIVE || (P.sem == SEM_SMOOTH && in.b <= 1024))) continue;
+      if (is_wwin(in) && !bwd) continue;
       if (in.op != T_NARY && !is_window(in)) {
         *why = "until / open-ended windows are evaluated by the interpreter tier";
         return false;
@@ -179,6 +181,11 @@ struct Gen {
         used[ins_level[i]] += 2 * 32;  // ClampScanOp<SEM_CLASSIC>::FLOATS
         continue;
       }
+      if (is_wwin(in)) {
+        scr_off[i] = used[ins_level[i]];
+        used[ins_level[i]] += 2 * 8 * nt;  // WeightedWinOp::FLOATS
+        continue;
+      }
       if (is_until(in)) {
         if (bwd) continue;  // persistent (above): the adjoint re-reads the staged operands
         scr_off[i] = used[ins_level[i]];
@@ -206,7 +213,7 @@ struct Gen {
     }
     const int base0 = red_floats + persist, base1 = base0 + reg[0];
     for (int i = 0; i < P.n_instr; ++i) {
-      if (is_scan(P.ins[i]) || (is_until(P.ins[i]) && !bwd)) scr_off[i] += (ins_level[i] & 1) ? base1 : base0;
+      if (is_scan(P.ins[i]) || is_wwin(P.ins[i]) || (is_until(P.ins[i]) && !bwd)) scr_off[i] += (ins_level[i] & 1) ? base1 : base0;
       if (!is_window(P.ins[i])) continue;
       const int l = ins_level[i];
       scr_off[i] += (l & 1) ? base1 : base0;
@@ -455,6 +462,28 @@ struct Gen {
     o.line("CS%d::phase2<VW>(smem + %d, c, cx%d, ce%d, v%d);", i, scr_off[i], i, i, (int)in.dst);
   }
 
+  void wwin_phase1(int i) {
+    const TInstr& in = P.ins[i];
+    o.line("// weighted window %d [%d, %d], phase 1: stage the unweighted lifted terms", i, in.a, in.b);
+    o.line("using WW%d = WeightedWinOp<SEM, %s, %d, %d, NT>;", i, mode_name(in.mode), in.a, in.b);
+    o.line("static_assert(WW%d::FLOATS == %d, \"host / device scratch layout mismatch\");", i, 2 * 8 * nt);
+    o.line("if (live) {");
+    o.indent++;
+    o.line("V t[8];");
+    o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) t[i] = %s;", operand(in, 0, "i").c_str());
+    o.line("WW%d::A x[8];", i);
+    o.line("lift8<WW%d::R, VW>(c, rp, t, x);", i);
+    o.line("WW%d::phase1(smem + %d, c.tid, x);", i, scr_off[i]);
+    o.indent--;
+    o.line("}");
+  }
+  void wwin_phase2(int i) {
+    const TInstr& in = P.ins[i];
+    o.line("// weighted window %d, phase 2: every output folds its window with its own weights", i);
+    o.line("V v%d[8];", (int)in.dst);
+    o.line("if (live) WW%d::phase2(smem + %d, c, rp, P.wbuf + %d, v%d);", i, scr_off[i], (int)in.w_off, (int)in.dst);
+  }
+
   void until_phase1(int i) {
     const TInstr& in = P.ins[i];
     const bool nl = in.negmask & 1, nr = in.negmask & 2;
@@ -481,9 +510,17 @@ struct Gen {
     o.line("V v%d[8];", d);
     o.line("if (live) {");
     o.indent++;
-    o.line("UntilState<SEM> st[8];");
-    o.line("U%d::phase2(smem + %d, c, rp%d, P.ins[%d].w[0], P.ins[%d].w[1], v%d, st);", i, scr_off[i], i, i, i, d);
-    if (P.sem == SEM_SMOOTH) o.line("U%d::smooth_fix(smem + %d, c, rp%d, st, v%d);", i, scr_off[i], i, d);
+    if (in.w_off >= 0 || in.w2_off >= 0) {
+      char wl[48] = "nullptr", wr[48] = "nullptr";
+      if (in.w_off >= 0) snprintf(wl, sizeof(wl), "P.wbuf + %d", (int)in.w_off);
+      if (in.w2_off >= 0) snprintf(wr, sizeof(wr), "P.wbuf + %d", (int)in.w2_off);
+      o.line("until_weighted_phase2<SEM, %d, %d, NT>(smem + %d, c, rp%d, P.ins[%d].w[0], P.ins[%d].w[1], %s, %s, v%d);", in.a, in.b,
+             scr_off[i], i, i, i, wl, wr, d);
+    } else {
+      o.line("UntilState<SEM> st[8];");
+      o.line("U%d::phase2(smem + %d, c, rp%d, P.ins[%d].w[0], P.ins[%d].w[1], v%d, st);", i, scr_off[i], i, i, i, d);
+      if (P.sem == SEM_SMOOTH) o.line("U%d::smooth_fix(smem + %d, c, rp%d, st, v%d);", i, scr_off[i], i, d);
+    }
     o.indent--;
     o.line("}");
     if (P.sem == SEM_SMOOTH && (need_lo[d] || need_hi[d])) {
@@ -559,6 +596,7 @@ struct Gen {
         if (is_window(in)) win_phase2(i);
         else if (is_scan(in)) scan_phase2(i);
         else if (is_until(in)) until_phase2(i);
+        else if (is_wwin(in)) wwin_phase2(i);
         else nary(i);
       }
       bool any = false;
@@ -566,6 +604,7 @@ struct Gen {
         if (is_staged(P.ins[i]) && ins_level[i] == st + 1) {
           if (is_window(P.ins[i])) win_phase1(i);
           else if (is_until(P.ins[i])) until_phase1(i);
+          else if (is_wwin(P.ins[i])) wwin_phase1(i);
           else scan_phase1(i);
           any = true;
         }

@@ -680,6 +680,120 @@ struct UntilOp {
   }
 };
 
+// ------------------------------------------------------------------ weighted windows (agm / dgmsr)
+// Always / Eventually with per-position weights (agm.py:18-35, dgmsr.py:13-25): weights[k] belongs
+// to the k-th sample of the window and the list is truncated to the clipped window, so the
+// reduction is a correlation -- O(W) per sample.  The unweighted lifted terms of every sample are
+// staged once (both accumulator words are linear in the weight), each output then folds its
+// window with its own weights.  The "an entry took the arithmetic branch" flag (+inf in word 1)
+// does not depend on the weight, like np.any(values <= 0) in the reference.
+template <int SEM, int MODE, int WA, int WB, int NT>
+struct WeightedWinOp {
+  using R = Red<SEM, MODE>;
+  using A = typename R::A;
+  static constexpr int LEXT = 8 * NT;
+  static constexpr int FLOATS = 2 * LEXT;
+  static constexpr int W = WB - WA + 1;
+
+  PF_DEV static void phase1(float* scr, int tid, const A (&x)[8]) {
+    float t[8];
+    split_words<2>(x, 0, t);
+    store8(scr, tid, t);
+    split_words<2>(x, 1, t);
+    store8(scr + LEXT, tid, t);
+  }
+  PF_DEV static void phase2(const float* scr, const TC& c, const RP& rp, const float* wts, Vec<1> (&o)[8]) {
+    A acc[8];
+    float sw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] = R::ident();
+      sw[i] = 0.f;
+    }
+    const int p0 = c.p0;
+    int q_hi = p0 + 7 + WB;
+    if (q_hi > c.nlive - 1) q_hi = c.nlive - 1;
+#pragma unroll 1
+    for (int f = (p0 + WA) >> 2; f <= (q_hi >> 2); ++f) {
+      const F4 t0 = reinterpret_cast<const F4*>(scr)[pf4(f)];
+      const F4 t1 = reinterpret_cast<const F4*>(scr + LEXT)[pf4(f)];
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int q = 4 * f + k4;
+        if (q > q_hi) break;
+        const int d = q - p0 - WA;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = d - i;  // position inside output i's window
+          if (k >= 0 && k < W) {
+            const float w = wts[k];
+            acc[i].x[0] += w * t0.v[k4];
+            acc[i].x[1] += (t1.v[k4] == f_inf()) ? f_inf() : w * t1.v[k4];
+            sw[i] += w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = sw[i] > 0.f ? R::fin(acc[i], sw[i], rp) : Vec<1>{{f_nan()}};
+  }
+};
+
+// Until with weights_left / weights_right (agm.py:90-130, dgmsr.py:88-118): weights_left[:i+1]
+// over the prefix l[0..i], weights_pair on AND(prefix, r_i), weights_right over the candidates.
+// wl / wr: null = uniform.  Same staging as UntilOp.
+template <int SEM, int UA, int UB, int NT>
+PF_DEV void until_weighted_phase2(float* scr, const TC& c, const RP& rp, float wp0, float wp1, const float* wl, const float* wr,
+                                  Vec<1> (&o)[8]) {
+  using U = UntilOp<SEM, UA, UB, NT>;
+  using RA = Red<SEM, MODE_AND>;
+  using RO = Red<SEM, MODE_OR>;
+  Vec<2> pre[8], orr[8];
+  float swl[8], swr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    pre[i] = RA::ident();
+    orr[i] = RO::ident();
+    swl[i] = swr[i] = 0.f;
+  }
+  const int p0 = c.p0;
+  int q_hi = p0 + 7 + UB;
+  if (q_hi > c.nlive - 1) q_hi = c.nlive - 1;
+#pragma unroll 1
+  for (int f = p0 >> 2; f <= (q_hi >> 2); ++f) {
+    const F4 ql = reinterpret_cast<const F4*>(U::lplane(scr, 0))[pf4(f)];
+    const F4 qr = reinterpret_cast<const F4*>(U::rplane(scr, 0))[pf4(f)];
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      const int q = 4 * f + k4;
+      if (q > q_hi) break;
+      const Vec<1> l{{ql.v[k4]}}, r{{qr.v[k4]}};
+      const int d = q - p0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int kk = d - i;
+        if (kk >= 0 && kk <= UB) {
+          const float wlk = wl ? wl[kk] : 1.f;
+          pre[i] = RA::comb(pre[i], RA::lift(l, rp, wlk));
+          swl[i] += wlk;
+          if (kk >= UA) {
+            const Vec<1> y = RA::fin(pre[i], swl[i], rp);
+            const Vec<2> pr = RA::comb(RA::lift(y, rp, wp0), RA::lift(r, rp, wp1));
+            const float wrj = wr ? wr[kk - UA] : 1.f;
+            orr[i] = RO::comb(orr[i], RO::lift(RA::fin(pr, wp0 + wp1, rp), rp, wrj));
+            swr[i] += wrj;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = U::ncand(c, p0 + i);
+    o[i] = (n <= 0 || p0 + i >= c.nlive || !(swr[i] > 0.f)) ? Vec<1>{{f_nan()}} : RO::fin(orr[i], swr[i], rp);
+  }
+}
+
 // ------------------------------------------------------------------ lift / finish
 // the thread's operand samples -> accumulators; samples past the horizon become the identity
 template <class R, int VW>

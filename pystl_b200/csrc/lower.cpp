@@ -113,6 +113,7 @@ struct Lowerer {
     std::memset(&in, 0, sizeof(in));
     in.op = (int16_t)op;
     in.mode = (int16_t)mode;
+    in.w_off = in.w2_off = -1;
     return in;
   }
   void add_src(TInstr& in, Ref r) {
@@ -151,6 +152,15 @@ struct Lowerer {
       if (s <= 0) fail(PYSTL_E_INVALID, "%s entries must contain at least one positive weight.", what);
     }
     return w;
+  }
+
+  // copy `n` window-position weights into the program (fused tier); returns their offset
+  int stash_weights(const float* w, int n) {
+    if (P().n_wbuf + n > kMaxWeights) fail(PYSTL_E_UNSUPPORTED, "more than %d window weights in one formula", kMaxWeights);
+    const int off = P().n_wbuf;
+    for (int i = 0; i < n; ++i) P().wbuf[off + i] = w[i];
+    P().n_wbuf += n;
+    return off;
   }
 
   // ---- structural resolution: which plane (and sign) does an operand read? ----
@@ -335,18 +345,35 @@ struct Lowerer {
         }
         case PYSTL_NODE_ALWAYS:
         case PYSTL_NODE_EVENTUALLY: {
-          if (uses_weights && nd.w_off >= 0)
-            fail(PYSTL_E_UNSUPPORTED, "window weights on Always/Eventually are not implemented for agm / dgmsr yet");
           int mode = nd.kind == PYSTL_NODE_ALWAYS ? MODE_AND : MODE_OR;
           if (sem == SEM_CUMULATIVE && nd.kind == PYSTL_NODE_EVENTUALLY) mode = MODE_SUM;  // cumulative.py:61-72
+          if (uses_weights && nd.w_off >= 0) {
+            // per-position weights, truncated to the clipped window (agm.py:28-35, dgmsr.py:20-25)
+            if (!ssa || backward)
+              fail(PYSTL_E_UNSUPPORTED, "window weights on Always / Eventually need the fused tier (forward pass only so far)");
+            if (nd.b < 0) fail(PYSTL_E_UNSUPPORTED, "window weights on an open-ended interval");
+            const int W = nd.b - nd.a + 1;
+            const float* w = weights_of(nd.w_off, nd.w_len, W, "weights", sem == SEM_AGM);
+            const Ref src = operand(child(i, 0));
+            const int dst = alloc_slot();
+            TInstr& in = emit(T_WIN_WEIGHTED, mode);
+            add_src(in, src);
+            in.dst = (int16_t)dst;
+            in.a = nd.a;
+            in.b = nd.b;
+            in.w_off = (int16_t)stash_weights(w, W);
+            res = Ref{dst, false};
+            break;
+          }
           res = window(operand(child(i, 0)), mode, nd.a, nd.b);
           break;
         }
         case PYSTL_NODE_UNTIL: {
           if (backward && sem != SEM_CLASSIC && !(ssa && (sem == SEM_CUMULATIVE || sem == SEM_SMOOTH)))
             fail(PYSTL_E_UNSUPPORTED, "the gradient of Until is implemented for the classical, smooth and cumulative semantics so far");
-          if (uses_weights && (nd.w_off >= 0 || nd.w2_off >= 0))
-            fail(PYSTL_E_UNSUPPORTED, "weights_left / weights_right on Until are not implemented for agm / dgmsr yet");
+          const bool until_weights = uses_weights && (nd.w_off >= 0 || nd.w2_off >= 0);
+          if (until_weights && (!ssa || backward || nd.b < 0))
+            fail(PYSTL_E_UNSUPPORTED, "weights_left / weights_right on Until need the fused tier (forward pass, bounded interval)");
           float wp0 = 1.f, wp1 = 1.f;
           if (uses_weights) {
             wp0 = nd.wp0;
@@ -404,6 +431,17 @@ struct Lowerer {
             in.b = nd.b < 0 ? 0 : nd.b;
             in.unbounded = nd.b < 0;
             in.dst = (int16_t)dst;
+            if (until_weights) {
+              // weights_left[:i+1] over the prefix, weights_right[:n] over the candidates (agm.py:112-130)
+              if (nd.w_off >= 0) {
+                const float* wl = weights_of(nd.w_off, nd.w_len, nd.b + 1, "weights_left", sem == SEM_AGM);
+                P().ins[P().n_instr - 1].w_off = (int16_t)stash_weights(wl, nd.b + 1);
+              }
+              if (nd.w2_off >= 0) {
+                const float* wr = weights_of(nd.w2_off, nd.w2_len, nd.b - nd.a + 1, "weights_right", sem == SEM_AGM);
+                P().ins[P().n_instr - 1].w2_off = (int16_t)stash_weights(wr, nd.b - nd.a + 1);
+              }
+            }
             res = Ref{dst, false};
           }
           break;

@@ -30,6 +30,7 @@ constexpr int kMaxPreds = 16;   // distinct affine predicates per formula
 constexpr int kMaxInstr = 40;   // lowered instructions per formula
 constexpr int kMaxThreads = 1024;
 constexpr int kMaxSlots = kMaxPreds + kMaxInstr + 8;  // value slots of one formula
+constexpr int kMaxWeights = 1024;  // window-position weights of one formula (agm / dgmsr, fused tier)
 
 enum Sem : int32_t {
   SEM_CLASSIC = 0,
@@ -55,7 +56,8 @@ enum TOp : int32_t {
   T_WIN_VH = 2,      // same, van Herk / Gil-Werman over 8-sample chunks, b-a+1 >= 9
   T_WIN_SUFFIX = 3,  // dst[t] = reduce_{k >= a} src[t+k] up to the horizon (tile must reach T)
   T_UNTIL = 4,       // dst[t] = OR_{i in [a,b]} AND(AND_{k<=i} l[t+k], r[t+i])   O(b) per sample
-  T_CLAMP_SCAN = 5   // classic unbounded until: W(t) = min(l_t, max(r_t, W(t+1)))
+  T_CLAMP_SCAN = 5,  // classic unbounded until: W(t) = min(l_t, max(r_t, W(t+1)))
+  T_WIN_WEIGHTED = 6 // agm / dgmsr window with per-position weights (agm.py:18-35): O(W) per sample, fused tier only
 };
 
 struct TPred {
@@ -79,6 +81,8 @@ struct TInstr {
   int32_t a, b;          // window offsets relative to t (signed: the backward pass looks back)
   float w[kMaxSrc];      // n-ary weights; T_UNTIL: w[0], w[1] = weights_pair
   float sw;              // sum of the n-ary weights
+  // offsets into TileProgram::wbuf, -1 = uniform: window weights / until weights_left, weights_right
+  int16_t w_off, w2_off;
 };
 
 // Scalars derived from the semantics' kwargs, computed once on the host (lower.cpp).
@@ -113,6 +117,8 @@ struct TileProgram {
   int32_t n_planes_bwd;
   TPred preds[kMaxPreds];
   TInstr ins[kMaxInstr];
+  int32_t n_wbuf;
+  float wbuf[kMaxWeights];  // window-relative weights (truncated to the clipped window, agm.py:28-35)
 };
 
 // Geometry of one launch.

@@ -120,6 +120,28 @@ extern "C" int pystl_b200_fused_precompile(const pystl_formula_t* f, int64_t T, 
   return fused_jit_precompile(fs, g_err, sizeof(g_err));
 }
 
+// Geometry the fused tier uses for (formula, T, D); PYSTL_E_UNSUPPORTED: interpreter tier.
+extern "C" int pystl_b200_fused_plan(const pystl_formula_t* f, int64_t T, int32_t D, int32_t backward, pystl_plan_t* plan) {
+  if (!plan) return set_err(PYSTL_E_INVALID, "plan is NULL");
+  Lowered lw;
+  TileGeom g;
+  FusedSource fs;
+  int rc = fused_prepare(f, 1, T, D, backward != 0, &lw, &g, &fs);
+  if (rc) return rc;
+  plan->out_channels = lw.out_channels;
+  plan->lookahead = lw.lookahead;
+  plan->start_slack = lw.prog.start_slack;
+  plan->raises_always = lw.prog.raises_always;
+  plan->threads = g.nt;
+  plan->tile_ext = g.lext;
+  plan->tile_out = g.lout;
+  plan->n_tiles = g.n_tiles;
+  plan->smem_bytes = fs.smem_floats * 4;
+  plan->n_instr = lw.prog.n_instr;
+  plan->n_planes = lw.prog.n_slots;
+  return PYSTL_OK;
+}
+
 // The generated source (debugging / inspection).  Returns its length, or a negative status.
 extern "C" int pystl_b200_fused_source(const pystl_formula_t* f, int64_t T, int32_t D, int32_t backward, char* buf, int32_t len) {
   Lowered lw;

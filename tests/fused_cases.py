@@ -78,6 +78,17 @@ def forward_cases(light: bool = False):
                 continue
             out.append(dict(name=f"until{seed}/{sem}", spec=spec, sem=sem, kw=kw, B=2, T=T, D=D, threads=64 if seed % 2 else 0,
                             seed=5100 + seed, scale=8.0 if sem == "cumulative" else 2.0))
+    # per-position weights (agm / dgmsr; the other semantics ignore them): windows and until
+    wspec = ("or", [
+        ("always", (0, 11), ("pred", {0: 1.0}, -0.25), [0.5, 1.0, 2.0, 1.5, 1.0, 0.25, 3.0, 1.0, 0.0, 2.0, 1.0, 0.75]),
+        ("eventually", (2, 9), ("not", ("pred", {1: 1.0}, -1.0)), [1.0, 0.5, 0.0, 2.0, 1.0, 1.0, 3.0, 0.5]),
+        ("until", (1, 6), ("pred", {0: 1.0}, 0.0), ("pred", {1: 1.0}, -0.5), [1.0, 2.0, 1.5, 1.0, 0.5, 2.5, 1.0], [1.0, 1.2, 0.8, 1.4, 2.0, 0.6],
+         [1.5, 0.5]),
+    ], [1.0, 2.0, 0.5])
+    for sem, kw in (SEM_KW[3:] if not light else SEM_KW[3:5]):
+        for threads in ((32,) if light else (0, 32)):
+            out.append(dict(name=f"weights/{sem}{kw.get('p', '')}/nt{threads}", spec=wspec, sem=sem, kw=kw, B=3, T=300, D=2, threads=threads,
+                            seed=41, scale=2.0))
     for T in (999, 1001, 1002):
         for sem, kw in (SEM_KW[0], SEM_KW[1]):
             for threads in ((32,) if light else (32, 128, 256)):
@@ -86,9 +97,7 @@ def forward_cases(light: bool = False):
     if not light:
         # the reference's own outputs (golden vectors) for the formulas the fused tier evaluates
         for c in CASES:
-            if "until" in repr(c["spec"]) or "None" in repr(c["spec"]):
-                continue
-            if c["spec_name"] == "weighted" and c["sem"] in ("agm", "dgmsr"):
+            if "None" in repr(c["spec"]):  # open-ended intervals: interpreter tier
                 continue
             out.append(dict(name="golden/" + c["name"], spec=c["spec"], sem=c["sem"], kw=c["kw"], golden=c, threads=0, scale=1.0,
                             T=c["T"], D=c["D"]))
