@@ -118,8 +118,8 @@ struct Gen {
     for (int i = 0; i < P.n_instr; ++i) {
       const TInstr& in = P.ins[i];
       if (is_scan(in) && P.sem == SEM_CLASSIC && !bwd) continue;
-      if (is_until(in) && (!bwd || P.sem == SEM_CUMULATIVE || (P.sem == SEM_SMOOTH && in.b <= 1024))) continue;
-      if (is_wwin(in) && !bwd) continue;
+      if (is_until(in) && (!bwd || P.sem == SEM_CUMULATIVE || in.b <= 1024)) continue;
+      if (is_wwin(in)) continue;
       if (in.op != T_NARY && !is_window(in)) {
         *why = "until / open-ended windows are evaluated by the interpreter tier";
         return false;
@@ -164,7 +164,7 @@ struct Gen {
       flag_off = red_floats + persist;
       persist += roundup(P.n_instr, 4);
     }
-    if (cum_bwd() || (bwd && P.sem == SEM_SMOOTH && has_until())) {
+    if (cum_bwd() || (bwd && has_until())) {
       sp_off = red_floats + persist;
       persist += 4 * 8 * nt;
       for (int i = 0; i < P.n_instr; ++i)
@@ -184,6 +184,10 @@ struct Gen {
       if (is_wwin(in)) {
         scr_off[i] = used[ins_level[i]];
         used[ins_level[i]] += 2 * 8 * nt;  // WeightedWinOp::FLOATS
+        if (bwd) {
+          bscr_off[i] = bused[ins_level[i]];
+          bused[ins_level[i]] += 2 * 8 * nt;  // WeightedWinAdj::FLOATS
+        }
         continue;
       }
       if (is_until(in)) {
@@ -214,6 +218,7 @@ struct Gen {
     const int base0 = red_floats + persist, base1 = base0 + reg[0];
     for (int i = 0; i < P.n_instr; ++i) {
       if (is_scan(P.ins[i]) || is_wwin(P.ins[i]) || (is_until(P.ins[i]) && !bwd)) scr_off[i] += (ins_level[i] & 1) ? base1 : base0;
+      if (is_wwin(P.ins[i])) bscr_off[i] += ((ins_level[i] + 1) & 1) ? base1 : base0;
       if (!is_window(P.ins[i])) continue;
       const int l = ins_level[i];
       scr_off[i] += (l & 1) ? base1 : base0;
@@ -655,7 +660,8 @@ struct Gen {
     o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) {");
     o.indent++;
     for (int j = 0; j < n; ++j)
-      o.line("g%d[i] %s g%d[i] * d%d_%d[i];", (int)in.src[j], ((in.negmask >> j) & 1) ? "-=" : "+=", d, i, j);
+      // (outputs the reference raises on are NaN with a zero cotangent: keep 0 * NaN out of the adjoints)
+      o.line("g%d[i] %s (g%d[i] != 0.f) ? g%d[i] * d%d_%d[i] : 0.f;", (int)in.src[j], ((in.negmask >> j) & 1) ? "-=" : "+=", d, d, i, j);
     o.indent--;
     o.line("}");
     o.indent--;
@@ -817,16 +823,37 @@ struct Gen {
     }
   }
 
+  void wwin_adj(int i) {
+    const TInstr& in = P.ins[i];
+    const bool neg = in.negmask & 1;
+    o.line("// adjoint of the weighted window %d: correlation of the output coefficients with the weights", i);
+    o.line("using WA%d = WeightedWinAdj<SEM, %s, %d, %d, NT>;", i, mode_name(in.mode), in.a, in.b);
+    o.line("if (live) WA%d::phase1(smem + %d, c, rp, P.wbuf + %d, g%d, v%d);", i, bscr_off[i], (int)in.w_off, (int)in.dst, (int)in.dst);
+    o.line("simt::sync();");
+    o.line("if (live) WA%d::phase2<%s>(smem + %d, c, rp, P.wbuf + %d, v%d, g%d);", i, neg ? "true" : "false", bscr_off[i], (int)in.w_off,
+           (int)in.src[0], (int)in.src[0]);
+    o.line("simt::sync();");
+  }
+
   void until_adj_smooth(int i) {
     const TInstr& in = P.ins[i];
     const int L = 8 * nt;
     const bool nl = in.negmask & 1, nr = in.negmask & 2;
-    o.line("// adjoint of until %d: log-domain sweeps, scatter through shared memory", i);
+    o.line("// adjoint of until %d: per-output sweeps, scatter through shared memory", i);
     o.line("plane_zero8(smem + %d, c.tid);", sp_off);
     o.line("plane_zero8(smem + %d, c.tid);", sp_off + L);
     o.line("simt::sync();");
-    o.line("if (live) smooth_until_scatter<%d, %d, NT>(c, rp, g%d, U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), smem + %d, smem + %d);",
-           in.a, in.b, (int)in.dst, i, scr_off[i], i, scr_off[i], sp_off, sp_off + L);
+    if (P.sem == SEM_SMOOTH) {
+      o.line("if (live) smooth_until_scatter<%d, %d, NT>(c, rp, g%d, U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), smem + %d, smem + %d);",
+             in.a, in.b, (int)in.dst, i, scr_off[i], i, scr_off[i], sp_off, sp_off + L);
+    } else {
+      char wl[48] = "nullptr", wr[48] = "nullptr";
+      if (in.w_off >= 0) snprintf(wl, sizeof(wl), "P.wbuf + %d", (int)in.w_off);
+      if (in.w2_off >= 0) snprintf(wr, sizeof(wr), "P.wbuf + %d", (int)in.w2_off);
+      o.line("if (live) gm_until_scatter<SEM, %d, %d, NT>(c, rp, P.ins[%d].w[0], P.ins[%d].w[1], %s, %s, g%d, U%d::lplane(smem + %d, 0),", in.a,
+             in.b, i, i, wl, wr, (int)in.dst, i, scr_off[i]);
+      o.line("    U%d::rplane(smem + %d, 0), smem + %d, smem + %d);", i, scr_off[i], sp_off, sp_off + L);
+    }
     o.line("simt::sync();");
     o.line("if (live) {");
     o.indent++;
@@ -879,6 +906,8 @@ struct Gen {
           if (ins_level[i] == st && !is_staged(P.ins[i])) nary_bwd(i);
         for (int i = P.n_instr - 1; i >= 0; --i)
           if (ins_level[i] == st && is_until(P.ins[i])) until_adj_smooth(i);
+        for (int i = P.n_instr - 1; i >= 0; --i)
+          if (ins_level[i] == st && is_wwin(P.ins[i])) wwin_adj(i);
         bool any = false;
         for (int i = P.n_instr - 1; i >= 0; --i)
           if (ins_level[i] == st && is_window(P.ins[i])) {

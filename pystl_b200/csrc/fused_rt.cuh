@@ -739,6 +739,79 @@ struct WeightedWinOp {
   }
 };
 
+// adjoint of a weighted window: d out_t / d x_q = in_factor(out_coeff(g_t, out_t, sw_t), x_q, w_{q-t-a}) is
+// linear in the two-word coefficient, so g_src[q] = in_factor(sum_t w_{q-t-a} k_t, x_q, 1): the
+// correlation of the staged coefficients with the weights, looking back over t in [q-b, q-a].
+template <int SEM, int MODE, int WA, int WB, int NT>
+struct WeightedWinAdj {
+  using AD = Adj<SEM, MODE>;
+  static constexpr int LEXT = 8 * NT;
+  static constexpr int FLOATS = 2 * LEXT;
+  static constexpr int W = WB - WA + 1;
+  // sum of the weights of the clipped window of output p (agm.py:28-35: weights[:len])
+  PF_DEV static float weight_sum(const TC& c, int p, const float* wts) {
+    int n = c.nlive - 1 - p - WA + 1;
+    if (n > W) n = W;
+    float s = 0.f;
+    for (int k = 0; k < n; ++k) s += wts[k];
+    return s;
+  }
+  PF_DEV static void phase1(float* scr, const TC& c, const RP& rp, const float* wts, const float (&g)[8], const Vec<1> (&o)[8]) {
+    Vec<2> k[8];
+    const bool interior = c.p0 + 7 + WB <= c.nlive - 1;
+    float sw_full = 0.f;
+    if (interior)
+      for (int j = 0; j < W; ++j) sw_full += wts[j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float sw = interior ? sw_full : weight_sum(c, c.p0 + i, wts);
+      bool lost;
+      k[i] = (g[i] != 0.f && sw > 0.f) ? AD::out_coeff(g[i], o[i].x[0], sw, rp, lost) : Vec<2>{{0.f, 0.f}};
+    }
+    float t[8];
+    split_words<2>(k, 0, t);
+    store8(scr, c.tid, t);
+    split_words<2>(k, 1, t);
+    store8(scr + LEXT, c.tid, t);
+  }
+  template <bool NEG>
+  PF_DEV static void phase2(const float* scr, const TC& c, const RP& rp, const float* wts, const Vec<1> (&v)[8], float (&gs)[8]) {
+    Vec<2> acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = Vec<2>{{0.f, 0.f}};
+    const int p0 = c.p0;
+    int t_lo = p0 - WB;
+    if (t_lo < 0) t_lo = 0;
+    int t_hi = p0 + 7 - WA;
+    if (t_hi > c.nlive - 1) t_hi = c.nlive - 1;
+#pragma unroll 1
+    for (int f = t_lo >> 2; f <= (t_hi >> 2); ++f) {
+      const F4 k0 = reinterpret_cast<const F4*>(scr)[pf4(f)];
+      const F4 k1 = reinterpret_cast<const F4*>(scr + LEXT)[pf4(f)];
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int t = 4 * f + k4;
+        if (t < t_lo || t > t_hi) continue;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = p0 + i - t - WA;  // position of sample p0 + i inside output t's window
+          if (k >= 0 && k < W) {
+            const float w = wts[k];
+            acc[i].x[0] += w * k0.v[k4];
+            acc[i].x[1] += w * k1.v[k4];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = NEG ? -v[i].x[0] : v[i].x[0];
+      const float d = (c.p0 + i < c.nlive) ? AD::in_factor(acc[i], x, 1.f, rp) : 0.f;
+      gs[i] += NEG ? -d : d;
+    }
+  }
+};
+
 // Until with weights_left / weights_right (agm.py:90-130, dgmsr.py:88-118): weights_left[:i+1]
 // over the prefix l[0..i], weights_pair on AND(prefix, r_i), weights_right over the candidates.
 // wl / wr: null = uniform.  Same staging as UntilOp.
@@ -1170,6 +1243,77 @@ PF_DEV void smooth_until_scatter(const TC& c, const RP& rp, const float (&g)[8],
     }
   }
 }
+// ---- agm / dgmsr until, backward (agm.py:90-130, dgmsr.py:88-118; optional weights).
+//   y_i = AND_{k<=i}(l_k; wl),  z_i = AND((y_i, r_i); wp),  U = OR_{i>=UA}(z_i; wr)
+// Sweep 1 recomputes y_i, z_i (kept in a per-thread scratch array) and U; sweep 2 walks i downwards:
+//   dU/dr_i = dOR/dz_i * dz_i/dr_i,   dU/dl_k = sum_{i >= max(k, UA)} dOR/dz_i * dz_i/dy_i * dy_i/dl_k,
+// where dy_i/dl_k = in_factor(out_coeff(y_i), l_k) factorises, so the sum over i is a running
+// suffix sum of the two-word coefficient -- no subtraction anywhere.
+template <int SEM, int UA, int UB, int NT>
+PF_DEV void gm_until_scatter(const TC& c, const RP& rp, float wp0, float wp1, const float* wl, const float* wr, const float (&g)[8],
+                             const float* lpl, const float* rpl, float* gl, float* gr) {
+  using RA = Red<SEM, MODE_AND>;
+  using RO = Red<SEM, MODE_OR>;
+  using AA = Adj<SEM, MODE_AND>;
+  using AO = Adj<SEM, MODE_OR>;
+  float ybuf[UB + 1], zbuf[UB + 1];
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    float gi = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j == i) gi = g[j];
+    const int p = c.p0 + i;
+    int last = c.nlive - 1 - p;
+    if (last > UB) last = UB;
+    if (gi == 0.f || last < UA) continue;
+    // sweep 1
+    Vec<2> pre = RA::ident(), orr = RO::ident();
+    float swl = 0.f, swr = 0.f;
+    for (int kk = 0; kk <= last; ++kk) {
+      const int q = pidx(p + kk);
+      const float wlk = wl ? wl[kk] : 1.f;
+      pre = RA::comb(pre, RA::lift(Vec<1>{{lpl[q]}}, rp, wlk));
+      swl += wlk;
+      if (kk >= UA) {
+        const Vec<1> y = RA::fin(pre, swl, rp);
+        const Vec<1> z = RA::fin(RA::comb(RA::lift(y, rp, wp0), RA::lift(Vec<1>{{rpl[q]}}, rp, wp1)), wp0 + wp1, rp);
+        const float wrj = wr ? wr[kk - UA] : 1.f;
+        orr = RO::comb(orr, RO::lift(z, rp, wrj));
+        swr += wrj;
+        ybuf[kk] = y.x[0];
+        zbuf[kk] = z.x[0];
+      }
+    }
+    if (!(swr > 0.f)) continue;
+    const float U = RO::fin(orr, swr, rp).x[0];
+    bool lost;
+    const Vec<2> kor = AO::out_coeff(gi, U, swr, rp, lost);
+    // sweep 2: suffix sum of a_i * out_coeff(y_i)
+    Vec<2> suf{{0.f, 0.f}};
+    for (int kk = last; kk >= 0; --kk) {
+      const int q = pidx(p + kk);
+      if (kk >= UA) {
+        const float wrj = wr ? wr[kk - UA] : 1.f;
+        const float dz = AO::in_factor(kor, zbuf[kk], wrj, rp);  // dU/dz_i * g
+        const Vec<2> kp = AA::out_coeff(dz, zbuf[kk], wp0 + wp1, rp, lost);
+        simt::atomic_add(&gr[q], AA::in_factor(kp, rpl[q], wp1, rp));
+        const float a = AA::in_factor(kp, ybuf[kk], wp0, rp);  // dU/dy_i * g
+        float swl_i = 0.f;  // sum of the prefix weights up to kk
+        if (wl) {
+          for (int k2 = 0; k2 <= kk; ++k2) swl_i += wl[k2];
+        } else {
+          swl_i = (float)(kk + 1);
+        }
+        const Vec<2> ky = AA::out_coeff(a, ybuf[kk], swl_i, rp, lost);
+        suf.x[0] += ky.x[0];
+        suf.x[1] += ky.x[1];
+      }
+      simt::atomic_add(&gl[q], AA::in_factor(suf, lpl[q], wl ? wl[kk] : 1.f, rp));
+    }
+  }
+}
+
 // g_src (+)= the thread's chunk of a scatter plane
 template <bool NEG>
 PF_DEV void accumulate8(const float* plane, int tid, float (&gs)[8]) {

@@ -125,7 +125,7 @@ void locate() {
   const char* c = getenv("PYSTL_B200_CACHE");
   g_cache_dir = (c && *c) ? std::string(c) : g_src_dir + "/build/fused";
   uint64_t h = 1469598103934665603ull;
-  for (const char* name : {"fused_rt.cuh", "tile_eval.h", "program.h"}) h = fnv1a(read_file(g_src_dir + "/" + name), h);
+  for (const char* name : {"fused_rt.cuh", "tile_eval.h", "tile_bwd.h", "program.h"}) h = fnv1a(read_file(g_src_dir + "/" + name), h);
   char buf[32];
   snprintf(buf, sizeof(buf), "%016llx", (unsigned long long)h);
   g_hdr_hash = buf;

@@ -349,8 +349,7 @@ struct Lowerer {
           if (sem == SEM_CUMULATIVE && nd.kind == PYSTL_NODE_EVENTUALLY) mode = MODE_SUM;  // cumulative.py:61-72
           if (uses_weights && nd.w_off >= 0) {
             // per-position weights, truncated to the clipped window (agm.py:28-35, dgmsr.py:20-25)
-            if (!ssa || backward)
-              fail(PYSTL_E_UNSUPPORTED, "window weights on Always / Eventually need the fused tier (forward pass only so far)");
+            if (!ssa) fail(PYSTL_E_UNSUPPORTED, "window weights on Always / Eventually need the fused tier (NVRTC)");
             if (nd.b < 0) fail(PYSTL_E_UNSUPPORTED, "window weights on an open-ended interval");
             const int W = nd.b - nd.a + 1;
             const float* w = weights_of(nd.w_off, nd.w_len, W, "weights", sem == SEM_AGM);
@@ -369,11 +368,11 @@ struct Lowerer {
           break;
         }
         case PYSTL_NODE_UNTIL: {
-          if (backward && sem != SEM_CLASSIC && !(ssa && (sem == SEM_CUMULATIVE || sem == SEM_SMOOTH)))
-            fail(PYSTL_E_UNSUPPORTED, "the gradient of Until is implemented for the classical, smooth and cumulative semantics so far");
+          if (backward && sem != SEM_CLASSIC && !ssa)
+            fail(PYSTL_E_UNSUPPORTED, "the gradient of a non-classical Until needs the fused tier (NVRTC)");
           const bool until_weights = uses_weights && (nd.w_off >= 0 || nd.w2_off >= 0);
-          if (until_weights && (!ssa || backward || nd.b < 0))
-            fail(PYSTL_E_UNSUPPORTED, "weights_left / weights_right on Until need the fused tier (forward pass, bounded interval)");
+          if (until_weights && (!ssa || nd.b < 0))
+            fail(PYSTL_E_UNSUPPORTED, "weights_left / weights_right on Until need the fused tier (bounded interval)");
           float wp0 = 1.f, wp1 = 1.f;
           if (uses_weights) {
             wp0 = nd.wp0;

@@ -161,6 +161,8 @@ extern "C" int pystl_b200_plan(const pystl_formula_t* f, int64_t T, int32_t D, i
   Lowered lw;
   TileGeom g;
   int rc = prepare(f, 1, T, D, backward != 0, &lw, &g);
+  // formulas only the fused tier evaluates (weights, non-classical Until gradients, ...)
+  if (rc == PYSTL_E_UNSUPPORTED && tier_mode() != TIER_INTERP) return pystl_b200_fused_plan(f, T, D, backward, plan);
   if (rc) return rc;
   plan->out_channels = lw.out_channels;
   plan->lookahead = lw.lookahead;

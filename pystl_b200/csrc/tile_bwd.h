@@ -104,7 +104,8 @@ struct Adj<SEM_AGM, MODE> {
     lost = false;
     const float gn = g * fast_rcp(sw);
     if constexpr (MODE == MODE_AND) return (o <= 0.f) ? Vec<2>{{gn, 0.f}} : Vec<2>{{0.f, gn * (o + 1.f)}};
-    else return (o > 0.f) ? Vec<2>{{gn, 0.f}} : Vec<2>{{0.f, gn * (1.f - o)}};
+    // (o == 0 is the arithmetic branch whose positive entries all carry weight 0)
+    else return (o >= 0.f) ? Vec<2>{{gn, 0.f}} : Vec<2>{{0.f, gn * (1.f - o)}};
   }
   static PYSTL_HD float in_factor(Vec<2> w, float x, float wt, const RP&) {
     if constexpr (MODE == MODE_AND) return wt * (dmin0(x) * w.x[0] + (x > 0.f ? w.x[1] * fast_rcp(1.f + x) : 0.f));

@@ -133,6 +133,26 @@ def smooth_until_backward_cases(light: bool = False):
     return out
 
 
+def gm_backward_cases(light: bool = False):
+    """agm / dgmsr gradients of Until (plain and weighted) and of weighted windows."""
+    U = ("until", (0, 12), ("pred", {0: 1.0}, 0.0), ("pred", {1: 1.0}, -1.0))
+    UW = ("until", (1, 6), ("pred", {0: 1.0}, 0.0), ("pred", {1: 1.0}, -0.5), [1.0, 2.0, 1.5, 1.0, 0.5, 2.5, 1.0],
+          [1.0, 1.2, 0.8, 1.4, 2.0, 0.6], [1.5, 0.5])
+    WG = ("always", (0, 11), ("pred", {0: 1.0}, -0.25), [0.5, 1.0, 2.0, 1.5, 1.0, 0.25, 3.0, 1.0, 0.0, 2.0, 1.0, 0.75])
+    WF = ("eventually", (2, 9), ("not", ("pred", {1: 1.0}, -1.0)), [1.0, 0.5, 0.0, 2.0, 1.0, 1.0, 3.0, 0.5])
+    specs = {"U": U, "UW": UW, "WG": WG, "mix": ("or", [WG, WF, UW], [1.0, 2.0, 0.5]), "cfg4": BASELINE_SPECS["cfg4"],
+             "cfg5": BASELINE_SPECS["cfg5"]}
+    out = []
+    for si, (sem, kw) in enumerate(SEM_KW[3:]):
+        for ni, (name, spec) in enumerate(specs.items()):
+            if light and (ni + si) % 3 != 0:
+                continue
+            for threads in ((64,) if light else (0, 64)):
+                out.append(dict(name=f"bwd/{name}/{sem}{kw.get('p', '')}/nt{threads}", spec=spec, sem=sem, kw=kw, B=2, T=300,
+                                D={"cfg4": 4, "cfg5": 8}.get(name, 2), threads=threads, seed=37))
+    return out
+
+
 def cumulative_backward_cases(light: bool = False):
     specs = {
         "G": ("always", (0, 20), ("pred", {0: 1.0}, -0.25)),

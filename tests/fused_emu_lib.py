@@ -24,7 +24,7 @@ ROOT = emu_lib.ROOT
 CSRC = os.path.join(ROOT, "pystl_b200", "csrc")
 EMU = os.path.join(ROOT, "tests", "emu")
 OUT = os.path.join(ROOT, "tests", "_emu", "fused")
-_HDRS = [os.path.join(CSRC, h) for h in ("fused_rt.cuh", "tile_eval.h", "program.h")] + [
+_HDRS = [os.path.join(CSRC, h) for h in ("fused_rt.cuh", "tile_eval.h", "tile_bwd.h", "program.h")] + [
     os.path.join(EMU, h) for h in ("simt_host.h", "fused_runner.h")
 ]
 _kernels: dict = {}

@@ -93,3 +93,19 @@ def test_smooth_until_backward(case):
     got = fused_emu_lib.eval_backward(from_spec(case["spec"]), "smooth", sig, g, force_threads=case["threads"], **case["kw"])
     rtol, atol = grad_tol("smooth", case["kw"])
     check(got.astype(np.float64), oracle_grad(case["spec"], "smooth", case["kw"], sig, g), "smooth", case["name"], rtol, atol)
+
+
+from fused_cases import gm_backward_cases  # noqa: E402
+
+GMB = gm_backward_cases(light=True)
+
+
+@pytest.mark.parametrize("case", GMB, ids=[c["name"] for c in GMB])
+def test_agm_dgmsr_until_and_weighted_backward(case):
+    """Until (agm.py:90-130, dgmsr.py:88-118; with weights_left / right / pair) and per-position
+    window weights: gradients against autograd through the dense oracle."""
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    g = rng.standard_normal(sig.shape[:2]).astype(np.float32).astype(np.float64)
+    got = fused_emu_lib.eval_backward(from_spec(case["spec"]), case["sem"], sig, g, force_threads=case["threads"], **case["kw"]).astype(np.float64)
+    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"], 4e-5, 4e-5)

@@ -215,3 +215,19 @@ def test_smooth_until_backward(case):
     got = gpu_grad(case["spec"], "smooth", case["kw"], sig, g, "fused", case["threads"])
     rtol, atol = grad_tol("smooth", case["kw"])
     check(got, oracle_grad(case["spec"], "smooth", case["kw"], sig, g), "smooth", case["name"], rtol, atol)
+
+
+from fused_cases import gm_backward_cases  # noqa: E402
+
+GMB = gm_backward_cases()
+
+
+@pytest.mark.parametrize("case", GMB, ids=[c["name"] for c in GMB])
+def test_agm_dgmsr_until_and_weighted_backward(case):
+    """Until (agm.py:90-130, dgmsr.py:88-118; with weights_left / right / pair) and per-position
+    window weights: gradients against autograd through the dense oracle."""
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    g = rng.standard_normal(sig.shape[:2]).astype(np.float32).astype(np.float64)
+    got = gpu_grad(case["spec"], case["sem"], case["kw"], sig, g, "fused", case["threads"])
+    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"], 4e-5, 4e-5)
