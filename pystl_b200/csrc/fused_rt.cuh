@@ -1106,13 +1106,21 @@ PF_DEV unsigned smooth_adj_coeff(const TC& c, const float (&g)[8], const Vec<1> 
 template <int SEM, int MODE, int FA, int FB>
 PF_DEV void gm_adj_coeff(const TC& c, const RP& rp, const float (&g)[8], const Vec<1> (&o)[8], Vec<2> (&k)[8]) {
   using AD = Adj<SEM, MODE>;
-  const bool interior = c.p0 + 7 + FB <= c.nlive - 1;
+  if (c.p0 + 7 + FB <= c.nlive - 1) {  // no window of this thread is clipped
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float n = interior ? (float)(FB - FA + 1) : win_count<FA, FB>(c, c.p0 + i);
-    bool lost;
-    k[i] = AD::out_coeff(g[i], o[i].x[0], n > 0.f ? n : 1.f, rp, lost);
-    if (!(g[i] != 0.f) || !(n > 0.f)) k[i] = Vec<2>{{0.f, 0.f}};
+    for (int i = 0; i < 8; ++i) {
+      bool lost;
+      k[i] = AD::out_coeff(g[i], o[i].x[0], (float)(FB - FA + 1), rp, lost);
+      if (!(g[i] != 0.f)) k[i] = Vec<2>{{0.f, 0.f}};  // (a NaN output has a zero cotangent)
+    }
+  } else {  // clipped at the horizon (or a halo output at the end of the tile)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float n = win_count<FA, FB>(c, c.p0 + i);
+      bool lost;
+      k[i] = AD::out_coeff(g[i], o[i].x[0], n > 0.f ? n : 1.f, rp, lost);
+      if (!(g[i] != 0.f) || !(n > 0.f)) k[i] = Vec<2>{{0.f, 0.f}};
+    }
   }
 }
 

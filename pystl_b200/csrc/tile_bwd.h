@@ -108,8 +108,13 @@ struct Adj<SEM_AGM, MODE> {
     else return (o >= 0.f) ? Vec<2>{{gn, 0.f}} : Vec<2>{{0.f, gn * (1.f - o)}};
   }
   static PYSTL_HD float in_factor(Vec<2> w, float x, float wt, const RP&) {
-    if constexpr (MODE == MODE_AND) return wt * (dmin0(x) * w.x[0] + (x > 0.f ? w.x[1] * fast_rcp(1.f + x) : 0.f));
-    else return wt * (dmax0(x) * w.x[0] + (x <= 0.f ? w.x[1] * fast_rcp(1.f - x) : 0.f));
+    // AND: d min(x,0) = 1 (x<0), 1/2 (x==0, torch.minimum); the log1p branch only for x > 0.  OR mirrored
+    // (agm.py:86 tests x > 0: x == 0 belongs to the geometric branch there, with the tie half of max(x,0)).
+    if constexpr (MODE == MODE_AND) {
+      return wt * (x > 0.f ? w.x[1] * fast_rcp(1.f + x) : (x < 0.f ? w.x[0] : 0.5f * w.x[0]));
+    } else {
+      return wt * (x > 0.f ? w.x[0] : (x < 0.f ? w.x[1] * fast_rcp(1.f - x) : 0.5f * w.x[0] + w.x[1]));
+    }
   }
 };
 
