@@ -977,6 +977,7 @@ PF_DEV float store_root(const TC& c, long long T, const Vec<Tr<SEM>::VW> (&v)[8]
   constexpr int VW = Tr<SEM>::VW;
   Vec<VW> o[8];
   float part = 0.f;
+  if (c.p0 + 8 <= c.p_lo || c.p0 >= c.p_hi) return 0.f;  // halo thread: nothing of it is written
   float* dst = out + (c.b * T + c.origin + c.p0) * (long long)VW;
   const bool inside = c.p0 >= c.p_lo && c.p0 + 8 <= c.p_hi;
   if (inside && c.p0 + 7 <= c.last_ok) {
@@ -1057,6 +1058,11 @@ PF_DEV void root_cotangent(const TC& c, long long T, const float* __restrict__ g
   const float* src = grad_out ? grad_out + (c.b * T + c.origin + c.p0) : nullptr;
   int hi = c.p_hi;
   if (hi > c.last_ok + 1) hi = c.last_ok + 1;
+  if (c.p0 >= hi) {  // right-halo thread: its outputs belong to the next tile
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = 0.f;
+    return;
+  }
   if (c.p0 + 8 <= hi && (!src || ((u64)src & 15ull) == 0ull)) {
     if (src) {
       const F4 a = reinterpret_cast<const F4*>(src)[0], b = reinterpret_cast<const F4*>(src)[1];
@@ -1456,6 +1462,7 @@ PF_DEV void cum_until_scatter(const TC& c, const Vec<2> (&g)[8], int w, const fl
 // ---- gradient rows -> HBM: the thread's 8 rows of D channels, positions inside [p_lo, p_hi)
 template <int D>
 PF_DEV void store_grad_rows(const TC& c, long long T, const float (&gr)[8][D], float* __restrict__ grad_signal) {
+  if (c.p0 + 8 <= c.p_lo || c.p0 >= c.p_hi) return;  // halo thread
   float* dst = grad_signal + ((c.b * T + c.origin + c.p0) * (long long)D);
   if (c.p0 >= c.p_lo && c.p0 + 8 <= c.p_hi && ((u64)dst & 15ull) == 0ull) {
     F4* d4 = reinterpret_cast<F4*>(dst);
