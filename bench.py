@@ -50,6 +50,11 @@ WORKLOADS = {
     "cfg3d": ("dgmsr", {"eps": 1e-8, "p": 1}, True),
     "cfg4": ("cumulative", {}, False),
     "cfg5": ("classical", {}, False),
+    # cfg5's formula under the other four semantics ("all five semantics")
+    "cfg5s": ("smooth", {"temperature": 1.0}, False),
+    "cfg5a": ("agm", {}, False),
+    "cfg5d": ("dgmsr", {"eps": 1e-8, "p": 1}, False),
+    "cfg5c": ("cumulative", {}, False),
 }
 DESCR = {
     "cfg1": "Classic G[0,10](x>0) & F[0,5](y<1), 1024x1000x2, forward",
@@ -59,6 +64,10 @@ DESCR = {
     "cfg3d": "D-GMSR G[0,100](F[0,10](x>0) & !(y>2)), 32768x8192x2, forward+backward",
     "cfg4": "Cumulative G[0,200]((x>0) U[0,64] (y>1)), 16384x16384x4, forward",
     "cfg5": "Classic 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
+    "cfg5s": "Smooth tau=1 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
+    "cfg5a": "AGM 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
+    "cfg5d": "D-GMSR 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
+    "cfg5c": "Cumulative 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
 }
 
 
@@ -66,8 +75,8 @@ def algorithmic_bytes_per_sample(cfg: str, backward: bool) -> float:
     """forward 4*D_ref + 4*C_out; backward 4*C_out(grad_out, 0 when the
     constant cotangent is fused) + 4*D_ref (re-read) + 4*D (grad write)."""
     _, _, D = BASELINE_SHAPES[cfg[:4]]
-    d_ref = {"cfg1": 2, "cfg1x": 2, "cfg2": 2, "cfg3": 2, "cfg3d": 2, "cfg4": 2, "cfg5": 8}[cfg]
-    c_out = 2 if cfg == "cfg4" else 1
+    d_ref = {"cfg1": 2, "cfg1x": 2, "cfg2": 2, "cfg3": 2, "cfg3d": 2, "cfg4": 2, "cfg5": 8}[cfg if cfg in ("cfg1x", "cfg3d") else cfg[:4]]
+    c_out = 2 if WORKLOADS[cfg][0] == "cumulative" else 1
     fwd = 4 * d_ref + 4 * c_out
     if not backward:
         return fwd
@@ -250,7 +259,7 @@ def run_b200(args) -> None:
         B = args.batch
     if cfg == "cfg1x" and not args.batch:
         B = 1 << 20
-    if cfg == "cfg5" and not args.batch:
+    if cfg[:4] == "cfg5" and not args.batch:
         # 2^20 traces are sharded over 8 GPUs in the BASELINE config: 2^17 per GPU
         B = (1 << 20) // 8
     phi = from_spec(BASELINE_SPECS[cfg[:4]])

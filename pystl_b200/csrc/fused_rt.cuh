@@ -593,8 +593,96 @@ struct UntilOp {
     return last - UA + 1;
   }
 
+  // Cumulative fast path (cumulative.py:96-103: U = sum_i min(r_i, min_{k<=i} l_k) per channel).
+  // Past the thread's own chunk the 8 outputs share everything: for q >= p0 + 8
+  //     min_{k in [p0+i, q]} l_k = min(h_i, M_q),   h_i = min l[p0+i .. p0+7],   M_q = min l[p0+8 .. q],
+  // so the candidate of output i at q is min(G_q, h_i) with G_q = min(r_q, M_q): two mins per
+  // position for the thread, one min + one add per (position, output), operands read once per
+  // thread (128-bit runs) instead of a guarded state update per (position, output).
+  // Valid when every window of the thread is complete, or on an interior tile (nlive == LEXT),
+  // where the outputs whose windows leave the tile are never consumed (loads are clamped).
+  PF_DEV static bool cum_fast_ok(const TC& c) { return c.p0 + 7 + UB <= c.nlive - 1 || c.nlive == LEXT; }
+  PF_DEV static void phase2_cum(float* scr, const TC& c, V (&o)[8]) {
+    static_assert(UA >= 0 && UB >= UA, "bounded until");
+    const int f0 = c.p0 >> 2;
+    constexpr int FMAX = LEXT / 4 - 1;
+    constexpr int KS0 = UA + 7 > 8 ? UA + 7 : 8;       // first offset at which every output has a candidate
+    constexpr int KS = (KS0 + 3) & ~3;                 // ... rounded up to a 128-bit group
+    constexpr int KE = ((UB + 1) & ~3) > KS ? ((UB + 1) & ~3) : KS;  // body = [KS, KE), every output active
+#pragma unroll
+    for (int w = 0; w < VW; ++w) {
+      const F4* L4 = reinterpret_cast<const F4*>(lplane(scr, w));
+      const F4* R4 = reinterpret_cast<const F4*>(rplane(scr, w));
+      float acc[8], h[8];
+      {  // own chunk: triangular
+        const F4 la = L4[pf4(f0)], lb = L4[pf4(f0 + 1)], ra = R4[pf4(f0)], rb = R4[pf4(f0 + 1)];
+        const float lo[8] = {la.v[0], la.v[1], la.v[2], la.v[3], lb.v[0], lb.v[1], lb.v[2], lb.v[3]};
+        const float ro[8] = {ra.v[0], ra.v[1], ra.v[2], ra.v[3], rb.v[0], rb.v[1], rb.v[2], rb.v[3]};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float pm = f_inf(), a = 0.f;
+#pragma unroll
+          for (int q = i; q < 8; ++q) {
+            pm = fminf(pm, lo[q]);
+            if (q - i >= UA && q - i <= UB) a += fminf(ro[q], pm);
+          }
+          acc[i] = a;
+          h[i] = pm;
+        }
+      }
+      float M = f_inf();
+      // one position at offset kq (compile-time) from p0: value pair (l, r)
+#define PF_CUM_STEP(KQ, LV, RV)                                            \
+  {                                                                        \
+    M = fminf(M, (LV));                                                    \
+    const float G = fminf((RV), M);                                        \
+    _Pragma("unroll") for (int i = 0; i < 8; ++i) {                        \
+      if ((KQ) - i >= UA && (KQ) - i <= UB) acc[i] += fminf(G, h[i]);      \
+    }                                                                      \
+  }
+      // head [8, KS): static conditions (offsets below UA only extend the running minimum)
+#pragma unroll
+      for (int g = 2; g < KS / 4; ++g) {
+        const int fc = (f0 + g) < FMAX ? (f0 + g) : FMAX;
+        const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) PF_CUM_STEP(4 * g + k, ql.v[k], qr.v[k])
+      }
+      // body [KS, KE): every output takes every position
+#pragma unroll 2
+      for (int g = KS / 4; g < KE / 4; ++g) {
+        const int fc = (f0 + g) < FMAX ? (f0 + g) : FMAX;
+        const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          M = fminf(M, ql.v[k]);
+          const float G = fminf(qr.v[k], M);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += fminf(G, h[i]);
+        }
+      }
+      // tail [KE, UB + 8): static conditions
+#pragma unroll
+      for (int g = KE / 4; g <= (UB + 7) / 4; ++g) {
+        const int fc = (f0 + g) < FMAX ? (f0 + g) : FMAX;
+        const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) PF_CUM_STEP(4 * g + k, ql.v[k], qr.v[k])
+      }
+#undef PF_CUM_STEP
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i].x[w] = acc[i];
+    }
+  }
+
   PF_DEV static void phase2(float* scr, const TC& c, const RP& rp, float w0, float w1, V (&o)[8], UntilState<SEM> (&st)[8]) {
     const int p0 = c.p0;
+    if constexpr (SEM == SEM_CUMULATIVE && UA <= 64) {
+      if (cum_fast_ok(c)) {
+        phase2_cum(scr, c, o);
+        return;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) st[i].init();
     int q_hi = p0 + 7 + UB;
