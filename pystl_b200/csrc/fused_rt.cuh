@@ -675,11 +675,96 @@ struct UntilOp {
     }
   }
 
+  // Smooth fast path (smooth.py:95-102 through SURVEY.md appendix A4): U = tau ln sum_i 1 / (S_i + rho_i),
+  // S_i = sum_{k<=i} lambda_k.  Same sharing as above with sums in place of minima: past the own
+  // chunk S_i(q) = hS_i + M_q, so lambda_q and rho_q are exponentiated once per thread and position
+  // (2 MUFU) and every candidate costs one reciprocal instead of two exponentials and a division.
+  PF_DEV static void phase2_smooth(float* scr, const TC& c, const RP& rp, V (&o)[8], UntilState<SEM> (&st)[8]) {
+    const int f0 = c.p0 >> 2;
+    constexpr int FMAX = LEXT / 4 - 1;
+    constexpr int KS0 = UA + 7 > 8 ? UA + 7 : 8;
+    constexpr int KS = (KS0 + 3) & ~3;
+    constexpr int KE = ((UB + 1) & ~3) > KS ? ((UB + 1) & ~3) : KS;
+    const F4* L4 = reinterpret_cast<const F4*>(lplane(scr, 0));
+    const F4* R4 = reinterpret_cast<const F4*>(rplane(scr, 0));
+    const float nk = -rp.k, ns = -rp.shift;
+    float acc[8], h[8];
+    {
+      const F4 la = L4[pf4(f0)], lb = L4[pf4(f0 + 1)], ra = R4[pf4(f0)], rb = R4[pf4(f0 + 1)];
+      float lo[8] = {la.v[0], la.v[1], la.v[2], la.v[3], lb.v[0], lb.v[1], lb.v[2], lb.v[3]};
+      float ro[8] = {ra.v[0], ra.v[1], ra.v[2], ra.v[3], rb.v[0], rb.v[1], rb.v[2], rb.v[3]};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        lo[q] = fast_ex2(fmaf(lo[q], nk, ns));
+        ro[q] = fast_ex2(fmaf(ro[q], nk, ns));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float S = 0.f, a = 0.f;
+#pragma unroll
+        for (int q = i; q < 8; ++q) {
+          S += lo[q];
+          if (q - i >= UA && q - i <= UB) a += fast_rcp(S + ro[q]);
+        }
+        acc[i] = a;
+        h[i] = S;
+      }
+    }
+    float M = 0.f;
+#define PF_SM_STEP(KQ, LV, RV)                                                   \
+  {                                                                              \
+    M += fast_ex2(fmaf((LV), nk, ns));                                           \
+    const float G = M + fast_ex2(fmaf((RV), nk, ns));                            \
+    _Pragma("unroll") for (int i = 0; i < 8; ++i) {                              \
+      if ((KQ) - i >= UA && (KQ) - i <= UB) acc[i] += fast_rcp(G + h[i]);        \
+    }                                                                            \
+  }
+#pragma unroll
+    for (int g = 2; g < KS / 4; ++g) {
+      const int fc = (f0 + g) < FMAX ? (f0 + g) : FMAX;
+      const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) PF_SM_STEP(4 * g + k, ql.v[k], qr.v[k])
+    }
+#pragma unroll 2
+    for (int g = KS / 4; g < KE / 4; ++g) {
+      const int fc = (f0 + g) < FMAX ? (f0 + g) : FMAX;
+      const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        M += fast_ex2(fmaf(ql.v[k], nk, ns));
+        const float G = M + fast_ex2(fmaf(qr.v[k], nk, ns));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += fast_rcp(G + h[i]);
+      }
+    }
+#pragma unroll
+    for (int g = KE / 4; g <= (UB + 7) / 4; ++g) {
+      const int fc = (f0 + g) < FMAX ? (f0 + g) : FMAX;
+      const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) PF_SM_STEP(4 * g + k, ql.v[k], qr.v[k])
+    }
+#undef PF_SM_STEP
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      st[i].S = 0.f;
+      st[i].acc = acc[i];  // (smooth_fix looks at it)
+      o[i] = st[i].done(UB - UA + 1, rp);
+    }
+  }
+
   PF_DEV static void phase2(float* scr, const TC& c, const RP& rp, float w0, float w1, V (&o)[8], UntilState<SEM> (&st)[8]) {
     const int p0 = c.p0;
     if constexpr (SEM == SEM_CUMULATIVE && UA <= 64) {
       if (cum_fast_ok(c)) {
         phase2_cum(scr, c, o);
+        return;
+      }
+    }
+    if constexpr (SEM == SEM_SMOOTH && UA <= 64) {
+      if (cum_fast_ok(c)) {
+        phase2_smooth(scr, c, rp, o, st);
         return;
       }
     }
