@@ -33,6 +33,17 @@ sys.path.insert(0, ROOT)
 
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
 
+# stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner) write to
+# file descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and the JSON line goes
+# to a private duplicate of the original stdout.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -84,7 +95,8 @@ def algorithmic_bytes_per_sample(cfg: str, backward: bool) -> float:
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process (one sample
+    every ~2 ms, so that even a 100 ms region yields a median under load), nvidia-smi as fallback."""
 
     QUERY = (
         "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -95,34 +107,71 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.source = "nvml"
         self._halt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[index]) if index < len(ids) else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)))
+            self._nvml = pynvml
+        except Exception:
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(
+            ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+            capture_output=True, text=True, timeout=5,
+        ).stdout.strip()
+        if not out:
+            return
+        r = [c.strip() for c in out.split(",")]
+        if r[0].replace(".", "").isdigit():
+            self.sm.append(float(r[0]))
+        if len(r) > 1 and r[1].replace(".", "").isdigit():
+            self.mx.append(float(r[1]))
+        for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            if v.lower().startswith("active"):
+                self.reasons.add(n)
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                    capture_output=True, text=True, timeout=5,
-                ).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.02)
+            self._halt.wait(0.002 if self._nvml is not None else 0.02)
 
     def stop(self) -> dict:
         self._halt.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": max(mx) if mx else None,
-            "reasons": reasons,
-            "samples": len(self.rows),
+            "sm_mhz": float(np.median(self.sm)) if self.sm else None,
+            "sm_max_mhz": max(self.mx) if self.mx else None,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.sm),
+            "source": self.source,
         }
 
 
@@ -163,24 +212,28 @@ def _cpu_worker(args):
     return done, time.perf_counter() - t0
 
 
-def cpu_port_throughput(cfg: str, budget_s: float, cores: int) -> dict:
+def cpu_port_throughput(cfg: str, budget_s: float, cores: int, pool=None, per: float | None = None) -> dict:
     """Oracle port of the reference recursion on a bounded sample: (trace, t) pairs per second.
-    One evaluation = one trace-sample of the forward pass (the reference has no batched path)."""
+    One evaluation = one trace-sample of the forward pass (the reference has no batched path).
+    `pool` / `per` (seconds per evaluation on one core) let a caller reuse the workers and the
+    calibration across steps."""
     import multiprocessing as mp
 
     _, T, _ = BASELINE_SHAPES[cfg[:4]]
     T_eval = min(T, 1024)
-    # calibrate on one core
-    n, dt = _cpu_worker((cfg, 0, 1, T_eval, 4, 0))
-    per = dt / max(n, 1)
+    if per is None:  # calibrate on one core
+        n, dt = _cpu_worker((cfg, 0, 1, T_eval, 4, 0))
+        per = dt / max(n, 1)
     total = max(int(budget_s / per), 8) * cores
     n_t = 8
     traces = max(total // n_t, cores)
     chunks = [(cfg, i * traces // cores, (i + 1) * traces // cores, T_eval, n_t, 100 + i) for i in range(cores)]
     t0 = time.perf_counter()
-    if cores > 1:
-        with mp.get_context("fork").Pool(cores) as pool:
-            res = pool.map(_cpu_worker, chunks)
+    if pool is not None:
+        res = pool.map(_cpu_worker, chunks)
+    elif cores > 1:
+        with mp.get_context("fork").Pool(cores) as own:
+            res = own.map(_cpu_worker, chunks)
     else:
         res = [_cpu_worker(chunks[0])]
     wall = time.perf_counter() - t0
@@ -192,6 +245,7 @@ def cpu_port_throughput(cfg: str, budget_s: float, cores: int) -> dict:
         "kind": "port",
         "sample": f"{done} (trace,t) pairs: {traces} traces x {n_t} random t, horizon {T_eval} of {T}, "
         f"slice identity (SURVEY A1), forward only, float64",
+        "sec_per_eval_one_core": per,
     }
 
 
@@ -202,15 +256,22 @@ def run_reference(args) -> None:
     cfg = args.workload
     cores = os.cpu_count() or 1
     steps = max(args.steps, 1)
+    import multiprocessing as mp
+
     vals = []
-    for _ in range(args.warmup):
-        cpu_port_throughput(cfg, 0.5, cores)
-    t0 = time.perf_counter()
-    base = None
-    for _ in range(steps):
-        base = cpu_port_throughput(cfg, max(20.0 / steps, 1.0), cores)
-        vals.append(base["value"])
-    wall = time.perf_counter() - t0
+    # every step is a bounded sample of the workload; the whole run (warm-up included) is sized
+    # for about a minute of wall clock whatever --steps / --warmup are
+    budget = max(60.0 / (steps + args.warmup), 0.25)
+    with mp.get_context("fork").Pool(cores) as pool:
+        per = cpu_port_throughput(cfg, 0.25, cores, pool)["sec_per_eval_one_core"]
+        for _ in range(args.warmup):
+            cpu_port_throughput(cfg, budget, cores, pool, per)
+        t0 = time.perf_counter()
+        base = None
+        for _ in range(steps):
+            base = cpu_port_throughput(cfg, budget, cores, pool, per)
+            vals.append(base["value"])
+        wall = time.perf_counter() - t0
     value = float(np.mean(vals))
     base["value"] = value
     line = {
@@ -232,7 +293,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -435,7 +496,7 @@ def run_b200(args) -> None:
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -1108,11 +1108,55 @@ PF_DEV void smooth_fix8(const TC& c, const RP& rp, const float* vplane, const Ve
 }
 
 
+// ------------------------------------------------------------------ AGM And / Or of TWO operands
+// (agm.py:60-88; partials as Adj<SEM_AGM, MODE> gives them).  Same arithmetic as the generic
+// lift / comb / fin / out_coeff / in_factor chain, written out for N = 2: two lg2, one ex2 and
+// (with partials) two rcp, instead of the accumulator pairs and their selects.
+template <int MODE, bool PARTIALS>
+PF_DEV float agm2(float x0, float x1, float w0, float w1, float sw, float& d0, float& d1) {
+  const float inv = fast_rcp(sw);
+  const float u0 = w0 * inv, u1 = w1 * inv;
+  if constexpr (MODE == MODE_AND) {
+    const bool arith = x0 <= 0.f || x1 <= 0.f;  // agm.py:71
+    const float E = fast_ex2(u0 * fast_lg2(1.f + x0) + u1 * fast_lg2(1.f + x1));
+    const float o = arith ? u0 * fminf(x0, 0.f) + u1 * fminf(x1, 0.f) : E - 1.f;
+    if constexpr (PARTIALS) {
+      if (o <= 0.f) {
+        d0 = x0 > 0.f ? 0.f : (x0 < 0.f ? u0 : 0.5f * u0);
+        d1 = x1 > 0.f ? 0.f : (x1 < 0.f ? u1 : 0.5f * u1);
+      } else {
+        const float k = o + 1.f;
+        d0 = x0 > 0.f ? u0 * k * fast_rcp(1.f + x0) : 0.f;
+        d1 = x1 > 0.f ? u1 * k * fast_rcp(1.f + x1) : 0.f;
+      }
+    }
+    return o;
+  } else {
+    const bool arith = x0 > 0.f || x1 > 0.f;  // agm.py:86
+    const float E = fast_ex2(u0 * fast_lg2(1.f - x0) + u1 * fast_lg2(1.f - x1));
+    const float o = arith ? u0 * fmaxf(x0, 0.f) + u1 * fmaxf(x1, 0.f) : 1.f - E;
+    if constexpr (PARTIALS) {
+      if (o >= 0.f) {
+        d0 = x0 > 0.f ? u0 : (x0 < 0.f ? 0.f : 0.5f * u0);
+        d1 = x1 > 0.f ? u1 : (x1 < 0.f ? 0.f : 0.5f * u1);
+      } else {
+        const float k = 1.f - o;
+        d0 = x0 > 0.f ? 0.f : u0 * k * fast_rcp(1.f - x0);
+        d1 = x1 > 0.f ? 0.f : u1 * k * fast_rcp(1.f - x1);
+      }
+    }
+    return o;
+  }
+}
+
 // ------------------------------------------------------------------ n-ary And / Or of one sample
 template <int SEM, int MODE, int N>
 PF_DEV Vec<Tr<SEM>::VW> nary1(const RP& rp0, const Vec<Tr<SEM>::VW> (&a)[N], const float (&w)[N], float sw) {
   using R = Red<SEM, MODE>;
-  if constexpr (SEM == SEM_SMOOTH && N == 2) {
+  if constexpr (SEM == SEM_AGM && N == 2) {
+    float d0, d1;
+    return Vec<1>{{agm2<MODE, false>(a[0].x[0], a[1].x[0], w[0], w[1], sw, d0, d1)}};
+  } else if constexpr (SEM == SEM_SMOOTH && N == 2) {
     // max + log2(1 + 2^-|d|): the max-shifted logsumexp of two terms (smooth.py:18-22)
     const float e0 = R::expo(a[0], rp0), e1 = R::expo(a[1], rp0);
     const float m = fmaxf(e0, e1);
@@ -1353,7 +1397,9 @@ template <int SEM, int MODE, int N>
 PF_DEV Vec<1> nary1_partials(const RP& rp, const Vec<1> (&a)[N], const float (&w)[N], float sw, float (&d)[N]) {
   using R = Red<SEM, MODE>;
   using AD = Adj<SEM, MODE>;
-  if constexpr (SEM == SEM_SMOOTH && N == 2) {
+  if constexpr (SEM == SEM_AGM && N == 2) {
+    return Vec<1>{{agm2<MODE, true>(a[0].x[0], a[1].x[0], w[0], w[1], sw, d[0], d[1])}};
+  } else if constexpr (SEM == SEM_SMOOTH && N == 2) {
     // softmax / softmin weights of two terms: 1 / (1 + 2^-|d|) for the extremal one
     const float e0 = R::expo(a[0], rp), e1 = R::expo(a[1], rp);
     const float t = fast_ex2(-fabsf(e0 - e1));
