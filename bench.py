@@ -56,6 +56,7 @@ UNIT = "trace-samples/s"
 WORKLOADS = {
     "cfg1": ("classical", {}, False),
     "cfg1x": ("classical", {}, False),  # cfg1's formula on 2^20 traces: the roofline figure (cfg1 itself is 8 MB, L2 resident)
+    "cfg1xb": ("classical", {}, True),  # ... with the one-hot gradient (value-and-gradient kernel)
     "cfg2": ("smooth", {"temperature": 1.0}, True),
     "cfg3": ("agm", {}, True),
     "cfg3d": ("dgmsr", {"eps": 1e-8, "p": 1}, True),
@@ -70,6 +71,7 @@ WORKLOADS = {
 DESCR = {
     "cfg1": "Classic G[0,10](x>0) & F[0,5](y<1), 1024x1000x2, forward",
     "cfg1x": "Classic G[0,10](x>0) & F[0,5](y<1), scaled to 1048576x1000x2, forward",
+    "cfg1xb": "Classic G[0,10](x>0) & F[0,5](y<1), scaled to 524288x1000x2, forward+backward",
     "cfg2": "Smooth tau=1 G[0,50](x>0) | F[0,20](y<0.5), 65536x4096x2, forward+backward",
     "cfg3": "AGM G[0,100](F[0,10](x>0) & !(y>2)), 32768x8192x2, forward+backward",
     "cfg3d": "D-GMSR G[0,100](F[0,10](x>0) & !(y>2)), 32768x8192x2, forward+backward",
@@ -86,7 +88,7 @@ def algorithmic_bytes_per_sample(cfg: str, backward: bool) -> float:
     """forward 4*D_ref + 4*C_out; backward 4*C_out(grad_out, 0 when the
     constant cotangent is fused) + 4*D_ref (re-read) + 4*D (grad write)."""
     _, _, D = BASELINE_SHAPES[cfg[:4]]
-    d_ref = {"cfg1": 2, "cfg1x": 2, "cfg2": 2, "cfg3": 2, "cfg3d": 2, "cfg4": 2, "cfg5": 8}[cfg if cfg in ("cfg1x", "cfg3d") else cfg[:4]]
+    d_ref = {"cfg1": 2, "cfg1x": 2, "cfg2": 2, "cfg3": 2, "cfg3d": 2, "cfg4": 2, "cfg5": 8}["cfg1x" if cfg.startswith("cfg1x") else ("cfg3d" if cfg == "cfg3d" else cfg[:4])]
     c_out = 2 if WORKLOADS[cfg][0] == "cumulative" else 1
     fwd = 4 * d_ref + 4 * c_out
     if not backward:
@@ -320,6 +322,8 @@ def run_b200(args) -> None:
         B = args.batch
     if cfg == "cfg1x" and not args.batch:
         B = 1 << 20
+    if cfg == "cfg1xb" and not args.batch:
+        B = 1 << 19
     if cfg[:4] == "cfg5" and not args.batch:
         # 2^20 traces are sharded over 8 GPUs in the BASELINE config: 2^17 per GPU
         B = (1 << 20) // 8

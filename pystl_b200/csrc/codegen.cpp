@@ -94,6 +94,9 @@ struct Gen {
   int stage_off = 0;               // cooperative row staging (aliases the scratch regions)
   bool coop_stage() const { return D >= 4 && D <= 8; }
   bool cum_bwd() const { return bwd && P.sem == SEM_CUMULATIVE; }
+  // classic value-and-gradient: the forward program runs on (value, source) pairs (SEM_CLASSIC_SRC,
+  // tile_eval.h) and the gradient is ONE scatter of the root cotangent through the recorded leaf
+  bool src_bwd() const { return bwd && P.sem == SEM_CLASSIC; }
   bool has_until() const {
     for (int i = 0; i < P.n_instr; ++i)
       if (is_until(P.ins[i])) return true;
@@ -104,21 +107,17 @@ struct Gen {
   Gen(const Lowered& l, int D_, int nt_, int minb_, bool bwd_) : lw(l), P(l.prog), D(D_), nt(nt_), minb(minb_), bwd(bwd_) {}
   int kw() const { return P.sem == SEM_SMOOTH ? 1 : 2; }  // words of an adjoint coefficient
 
-  int vw() const { return P.sem == SEM_CUMULATIVE ? 2 : 1; }
-  int aw() const { return (P.sem == SEM_CLASSIC || P.sem == SEM_SMOOTH) ? 1 : 2; }
+  int vw() const { return (P.sem == SEM_CUMULATIVE || src_bwd()) ? 2 : 1; }
+  int aw() const { return src_bwd() ? 2 : ((P.sem == SEM_CLASSIC || P.sem == SEM_SMOOTH) ? 1 : 2); }
 
   bool supported(std::string* why) const {
     if (D < 1) {
       *why = "bad D";
       return false;
     }
-    if (bwd && P.sem == SEM_CLASSIC) {
-      *why = "the classic gradient runs on the interpreter tier";
-      return false;
-    }
     for (int i = 0; i < P.n_instr; ++i) {
       const TInstr& in = P.ins[i];
-      if (is_scan(in) && P.sem == SEM_CLASSIC && !bwd) continue;
+      if (is_scan(in) && P.sem == SEM_CLASSIC) continue;
       if (is_until(in) && (!bwd || P.sem == SEM_CUMULATIVE || in.b <= 1024)) continue;
       if (is_wwin(in)) continue;
       if (in.op != T_NARY && !is_window(in)) {
@@ -165,6 +164,10 @@ struct Gen {
       flag_off = red_floats + persist;
       persist += roundup(P.n_instr, 4);
     }
+    if (src_bwd()) {  // one scatter plane per predicate
+      sp_off = red_floats + persist;
+      persist += P.n_preds * 8 * nt;
+    }
     if (cum_bwd() || (bwd && has_until())) {
       sp_off = red_floats + persist;
       persist += 4 * 8 * nt;
@@ -179,7 +182,7 @@ struct Gen {
       const TInstr& in = P.ins[i];
       if (is_scan(in)) {
         scr_off[i] = used[ins_level[i]];
-        used[ins_level[i]] += 2 * 32;  // ClampScanOp<SEM_CLASSIC>::FLOATS
+        used[ins_level[i]] += (src_bwd() ? 4 : 2) * 32;  // ClampScanOp<SEM>::FLOATS
         continue;
       }
       if (is_wwin(in)) {
@@ -206,7 +209,7 @@ struct Gen {
         stash_off[i] = used[l];
         used[l] += 8 * nt;
       }
-      if (bwd && !arg_window(in)) {
+      if (bwd && !arg_window(in) && !src_bwd()) {
         bscr_off[i] = bused[l];
         bused[l] += win_floats(kw(), -b, -a, nt);
       }
@@ -309,6 +312,7 @@ struct Gen {
         o.line("acc += P.preds[%d].bias;", q);
       }
       if (P.sem == SEM_CUMULATIVE) o.line("v%d[i] = V{{fmaxf(0.f, acc), fminf(0.f, acc)}};  // cumulative.py:29-30", (int)pr.dst);
+      else if (src_bwd()) o.line("v%d[i] = V{{acc, i2f(%d | (c.p0 + i))}};  // source: predicate << 24 | tile position", (int)pr.dst, q << 24);
       else o.line("v%d[i] = V{{acc}};", (int)pr.dst);
       o.indent--;
       o.line("}");
@@ -454,7 +458,7 @@ struct Gen {
     const TInstr& in = P.ins[i];
     o.line("// classic until %d: clamp scan, phase 1 (chunk composition, warp scan)", i);
     o.line("using CS%d = ClampScanOp<SEM, NT>;", i);
-    o.line("static_assert(CS%d::FLOATS == 64, \"host / device scratch layout mismatch\");", i);
+    o.line("static_assert(CS%d::FLOATS == %d, \"host / device scratch layout mismatch\");", i, src_bwd() ? 128 : 64);
     o.line("CS%d::A cx%d[8], ce%d;", i, i, i);
     o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i)");
     o.line("  cx%d[i] = (live && c.p0 + i < c.nlive) ? ClampOp<SEM>::make(%s, %s) : ClampOp<SEM>::ident();", i, operand(in, 0, "i").c_str(),
@@ -543,7 +547,7 @@ struct Gen {
     const int n = in.nsrc, d = in.dst;
     o.line("// n-ary %s (%d operands)", in.mode == MODE_AND ? "And" : "Or", n);
     o.line("V v%d[8];", d);
-    if (bwd && !cum_bwd())
+    if (bwd && !cum_bwd() && !src_bwd())
       for (int j = 0; j < n; ++j) o.line("float d%d_%d[8];  // d out / d operand %d, for the adjoint sweep", i, j, j);
     o.line("if (live) {");
     o.indent++;
@@ -559,7 +563,7 @@ struct Gen {
     std::string a = "const V a[" + std::to_string(n) + "] = {";
     for (int j = 0; j < n; ++j) a += (j ? ", " : "") + operand(in, j, "i");
     o.line("%s};", a.c_str());
-    if (bwd && !cum_bwd()) {
+    if (bwd && !cum_bwd() && !src_bwd()) {
       o.line("float dd[%d];", n);
       o.line("v%d[i] = nary1_partials<SEM, %s, %d>(rp, a, w, P.ins[%d].sw, dd);", d, mode_name(in.mode), n, i);
       for (int j = 0; j < n; ++j) o.line("d%d_%d[i] = dd[%d];", i, j, j);
@@ -631,7 +635,7 @@ struct Gen {
     o.line("#include \"fused_rt.cuh\"");
     o.line("using namespace pystl;");
     o.line("using namespace pystl::fused;");
-    o.line("constexpr int NT = %d, D = %d, SEM = %s, VW = Tr<SEM>::VW;", nt, D, sem_name(P.sem));
+    o.line("constexpr int NT = %d, D = %d, SEM = %s, VW = Tr<SEM>::VW;", nt, D, src_bwd() ? "SEM_CLASSIC_SRC" : sem_name(P.sem));
     o.line("typedef Vec<VW> V;");
   }
 
@@ -878,7 +882,8 @@ struct Gen {
     o.line("if (out) {");
     o.indent++;
     o.line("float part = 0.f;");
-    o.line("if (live) part = store_root<SEM, %s>(c, g.T, v%d, out);", P.root_neg ? "true" : "false", (int)P.root);
+    if (src_bwd()) o.line("if (live) part = store_root_src<%s>(c, g.T, v%d, out);", P.root_neg ? "true" : "false", (int)P.root);
+    else o.line("if (live) part = store_root<SEM, %s>(c, g.T, v%d, out);", P.root_neg ? "true" : "false", (int)P.root);
     o.line("if (mean_acc) block_sum_to<NT>(c, part, mean_acc, smem + %d);", red_floats - 32);
     o.indent--;
     o.line("}");
@@ -889,7 +894,19 @@ struct Gen {
       for (int j = 0; j < P.ins[i].nsrc; ++j) has[P.ins[i].src[j]] = 1;
     }
     for (int q = 0; q < P.n_preds; ++q) has[P.preds[q].dst] = 1;
-    if (cum_bwd()) {
+    if (src_bwd()) {
+      // Classic: every output routes its cotangent to ONE leaf sample (the arg-min / arg-max chain of
+      // torch.min / max(dim), first index on ties): scatter into one shared plane per predicate
+      o.line("// ================= one-hot routing of the root cotangent (classic.py:25-68 under autograd)");
+      for (int q = 0; q < P.n_preds; ++q) o.line("plane_zero8(smem + %d, c.tid);", sp_off + q * 8 * nt);
+      o.line("simt::sync();");
+      o.line("if (live) classic_scatter<%s, NT>(c, g.T, grad_out, scale, v%d, smem + %d);", P.root_neg ? "true" : "false", (int)P.root, sp_off);
+      o.line("simt::sync();");
+      for (int q = 0; q < P.n_preds; ++q) {
+        o.line("float g%d[8];", (int)P.preds[q].dst);
+        o.line("load8(smem + %d, c.tid, g%d);", sp_off + q * 8 * nt, (int)P.preds[q].dst);
+      }
+    } else if (cum_bwd()) {
       for (int sl = 0; sl < kMaxSlots; ++sl)
         if (has[sl]) {
           o.line("V g%d[8];", sl);

@@ -1302,6 +1302,52 @@ PF_DEV void root_cotangent(const TC& c, long long T, const float* __restrict__ g
   }
 }
 
+// ---- classic value-and-gradient (values carry their source, SEM_CLASSIC_SRC)
+// root (value, source) -> out; same masking and fused mean as store_root
+template <bool NEG>
+PF_DEV float store_root_src(const TC& c, long long T, const Vec<2> (&v)[8], float* __restrict__ out) {
+  Vec<1> o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i].x[0] = v[i].x[0];
+  return store_root<SEM_CLASSIC, NEG>(c, T, o, out);
+}
+// The gradient of a min / max chain is one-hot (torch.min / max(dim) route to the first extremal
+// index, torch/semantics.py:106,113): each output adds its cotangent to the
+// plane of its source predicate at its source position.  Consecutive outputs of a thread often share
+// the source (a window minimum serves every output whose window contains it): runs are merged
+// before the shared-memory atomic.  planes: one 8*NT plane per predicate, zeroed, store8 layout.
+template <bool NEG, int NT>
+PF_DEV void classic_scatter(const TC& c, long long T, const float* __restrict__ grad_out, float scale, const Vec<2> (&v)[8],
+                            float* planes) {
+  float g[8];
+  root_cotangent<false>(c, T, grad_out, scale, g);
+  int cur = 0;
+  float acc = 0.f;
+  bool open = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int s = f2i(v[i].x[1]);
+    const bool on = g[i] != 0.f;
+    if (open && (!on || s != cur)) {
+      const bool neg = (cur < 0) != NEG;
+      simt::atomic_add(&planes[((cur >> 24) & 0x7f) * (8 * NT) + pidx(cur & 0xffffff)], neg ? -acc : acc);
+      open = false;
+    }
+    if (on) {
+      if (!open) {
+        cur = s;
+        acc = 0.f;
+        open = true;
+      }
+      acc += g[i];
+    }
+  }
+  if (open) {
+    const bool neg = (cur < 0) != NEG;
+    simt::atomic_add(&planes[((cur >> 24) & 0x7f) * (8 * NT) + pidx(cur & 0xffffff)], neg ? -acc : acc);
+  }
+}
+
 // ---- window adjoint, phase A: per-output coefficients k[8] (KW words)
 // smooth: d out_t / d x_q = xhat_q / S_t with the forward's block-shifted xhat and S: k_t = g_t / S_t.
 // Outputs whose shifted sum lost its precision (S_t < 2^-100, recomputed exactly by the forward

@@ -99,7 +99,7 @@ def test_mean_accumulator_matches():
 from fused_cases import backward_cases  # noqa: E402
 from test_emu_backward import check, grad_tol, oracle_grad  # noqa: E402
 
-BWD = [c for c in backward_cases() if c["sem"] != "classical"]
+BWD = backward_cases()
 
 
 def gpu_grad(spec, sem, kw, sig64, g64, which, threads=0, scale=None):
@@ -231,3 +231,49 @@ def test_agm_dgmsr_until_and_weighted_backward(case):
     g = rng.standard_normal(sig.shape[:2]).astype(np.float32).astype(np.float64)
     got = gpu_grad(case["spec"], case["sem"], case["kw"], sig, g, "fused", case["threads"])
     check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"], 4e-5, 4e-5)
+
+
+# ---------------------------------------------------------------------------- classic gradient (fused tier)
+from parity_util import mixed_signal, random_spec  # noqa: E402
+from test_emu_backward import has_until  # noqa: E402
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_classic_gradient_random_formulas(seed):
+    """One-hot routing of torch.min / max(dim) (first index on ties) through nested windows, n-ary
+    operators and the decomposed Until, on signals quantised to 0.5 so that ties are frequent."""
+    rng = np.random.default_rng(4100 + seed)
+    D = int(rng.integers(1, 4))
+    T = int(rng.integers(60, 260))
+    spec = random_spec(rng, D, depth=3, max_b=24, allow_open=False)
+    sig = mixed_signal(rng, 2, T, D)
+    if seed % 2 and not has_until(spec):
+        # (the reference's Until goes through torch.minimum / maximum, which SPLIT ties between
+        # different leaves 0.5 / 0.5; no tier reproduces that, ties there have measure zero on real data)
+        sig = np.round(sig * 2.0) / 2.0
+    g = rng.uniform(0.25, 1.0, size=(2, T)).astype(np.float32).astype(np.float64)
+    want = oracle_grad(spec, "classical", {}, sig, g)
+    for threads in (0, 32):
+        try:
+            got = gpu_grad(spec, "classical", {}, sig, g, "fused", threads)
+        except NotImplementedError:
+            assert threads
+            continue
+        check(got, want, "classical", f"seed{seed}/nt{threads}/{spec}")
+
+
+def test_classic_value_and_grad_full_size_routing_is_one_hot():
+    """cfg1 at 4096 traces: every output routes to exactly one sample, so the gradient of sum(out)
+    sums to the number of valid outputs per trace, channel by channel signs included."""
+    from pystl_b200.formula import BASELINE_SPECS as SPECS
+
+    s = create_semantics("classical", backend="b200")
+    x = torch.randn(4096, 1000, 2, device="cuda")
+    phi = from_spec(SPECS["cfg1"])
+    mean, grad = s.mean_robustness_and_grad(phi, x)
+    out = s.robustness_trace(phi, x)
+    assert abs(float(mean) - float(out.double().mean())) < 1e-6
+    # G[0,10](x>0) routes +1 to channel 0, F[0,5](y<1) routes -1 to channel 1; the And picks one of them
+    tot = grad.double().abs().sum().item() * (4096 * 1000)
+    assert abs(tot - 4096 * 1000) < 1e-3 * 4096 * 1000
+    assert (grad[..., 0] >= 0).all() and (grad[..., 1] <= 0).all()
