@@ -879,14 +879,9 @@ struct Gen {
     o.indent = 1;
     emit_forward_body();
     o.line("// ================= value (optional) and cotangent");
-    o.line("if (out) {");
-    o.indent++;
-    o.line("float part = 0.f;");
-    if (src_bwd()) o.line("if (live) part = store_root_src<%s>(c, g.T, v%d, out);", P.root_neg ? "true" : "false", (int)P.root);
-    else o.line("if (live) part = store_root<SEM, %s>(c, g.T, v%d, out);", P.root_neg ? "true" : "false", (int)P.root);
-    o.line("if (mean_acc) block_sum_to<NT>(c, part, mean_acc, smem + %d);", red_floats - 32);
-    o.indent--;
-    o.line("}");
+    o.line("float part = 0.f;  // (its block sum joins the fused mean at the very end: a barrier there costs nothing)");
+    if (src_bwd()) o.line("if (live) part = out ? store_root_src<%s>(c, g.T, v%d, out) : 0.f;", P.root_neg ? "true" : "false", (int)P.root);
+    else o.line("if (live) part = out ? store_root<SEM, %s>(c, g.T, v%d, out) : 0.f;", P.root_neg ? "true" : "false", (int)P.root);
     std::vector<char> has(kMaxSlots, 0);
     has[P.root] = 1;
     for (int i = 0; i < P.n_instr; ++i) {
@@ -982,6 +977,7 @@ struct Gen {
     }
     o.indent--;
     o.line("}");
+    o.line("if (out && mean_acc) block_sum_to<NT>(c, part, mean_acc, smem + %d);", red_floats - 32);
     o.indent = 0;
     o.line("}");
     return o.s;
@@ -1017,6 +1013,7 @@ bool hoistable(const std::string& raw) {
   if (starts_with(t, "RP rp") || (starts_with(t, "rp") && t.find(".shift = ") != std::string::npos)) return true;
   if (t.find("::fill_guards(") != std::string::npos && t.find("if ") == std::string::npos) return true;
   if (starts_with(t, "unsigned lost") && ends_with(t, " = 0;")) return true;
+  if (t == "float part = 0.f;") return true;
   // array declarations: no initialiser, or a brace list of zeros
   if (t.find('(') == std::string::npos && t.find('[') != std::string::npos) {
     const size_t eq = t.find('=');

@@ -1157,12 +1157,11 @@ PF_DEV Vec<Tr<SEM>::VW> nary1(const RP& rp0, const Vec<Tr<SEM>::VW> (&a)[N], con
     float d0, d1;
     return Vec<1>{{agm2<MODE, false>(a[0].x[0], a[1].x[0], w[0], w[1], sw, d0, d1)}};
   } else if constexpr (SEM == SEM_SMOOTH && N == 2) {
-    // max + log2(1 + 2^-|d|): the max-shifted logsumexp of two terms (smooth.py:18-22)
-    const float e0 = R::expo(a[0], rp0), e1 = R::expo(a[1], rp0);
-    const float m = fmaxf(e0, e1);
-    const float l = fast_lg2(1.f + fast_ex2(-fabsf(e0 - e1)));
-    const float sk = MODE == MODE_AND ? -rp0.invk : rp0.invk;
-    return Vec<1>{{(m + l) * sk}};
+    // extremum +- tau ln(1 + e^-|d|/tau): the max-shifted logsumexp of two terms (smooth.py:18-22)
+    const float x0 = a[0].x[0], x1 = a[1].x[0];
+    const float l = fast_lg2(1.f + fast_ex2(-fabsf(x0 - x1) * rp0.k));
+    if constexpr (MODE == MODE_AND) return Vec<1>{{fmaf(l, -rp0.invk, fminf(x0, x1))}};
+    else return Vec<1>{{fmaf(l, rp0.invk, fmaxf(x0, x1))}};
   } else if constexpr (SEM == SEM_SMOOTH) {
     // exact max-shifted logsumexp (smooth.py:18-22)
     float e[N];
@@ -1447,15 +1446,15 @@ PF_DEV Vec<1> nary1_partials(const RP& rp, const Vec<1> (&a)[N], const float (&w
     return Vec<1>{{agm2<MODE, true>(a[0].x[0], a[1].x[0], w[0], w[1], sw, d[0], d[1])}};
   } else if constexpr (SEM == SEM_SMOOTH && N == 2) {
     // softmax / softmin weights of two terms: 1 / (1 + 2^-|d|) for the extremal one
-    const float e0 = R::expo(a[0], rp), e1 = R::expo(a[1], rp);
-    const float t = fast_ex2(-fabsf(e0 - e1));
+    const float x0 = a[0].x[0], x1 = a[1].x[0];
+    const float t = fast_ex2(-fabsf(x0 - x1) * rp.k);
     const float s = 1.f + t;
     const float wmax = fast_rcp(s), wmin = t * wmax;
-    const bool first = e0 >= e1;
+    const bool first = MODE == MODE_AND ? x0 <= x1 : x0 >= x1;  // operand 0 is the extremal one
     d[0] = first ? wmax : wmin;
     d[1] = first ? wmin : wmax;
-    const float sk = MODE == MODE_AND ? -rp.invk : rp.invk;
-    return Vec<1>{{(fmaxf(e0, e1) + fast_lg2(s)) * sk}};
+    if constexpr (MODE == MODE_AND) return Vec<1>{{fmaf(fast_lg2(s), -rp.invk, fminf(x0, x1))}};
+    else return Vec<1>{{fmaf(fast_lg2(s), rp.invk, fmaxf(x0, x1))}};
   } else {
     const Vec<1> o = nary1<SEM, MODE, N>(rp, a, w, sw);
     if constexpr (SEM == SEM_SMOOTH) {

@@ -65,12 +65,19 @@ static int tier_mode() {
 }
 
 // registers per thread the fused kernels are compiled for: min CTAs per SM by CTA size
-static int fused_minb(int nt, bool backward) {
+static int fused_minb(int nt, bool backward, int sem) {
   const char* e = getenv("PYSTL_B200_FUSED_MINB");
   if (e && *e) return atoi(e) > 0 ? atoi(e) : 1;
-  // the backward kernels keep the forward values AND the adjoints of 8 samples in registers
+  // The backward kernels keep the forward values AND the adjoints of 8 samples in registers, but
+  // they are latency bound: more resident warps beat fewer spills.  Register targets measured on
+  // B200 (profiles/README.md, sweep of CTA size x CTAs per SM on cfg2 / cfg3): smooth 80
+  // (1.81 -> 1.77 ms), agm 72 (3.20 -> 2.86 ms), dgmsr 56 (4.05 -> 3.55 ms).
+  int bwd_regs = 96;
+  if (sem == SEM_SMOOTH) bwd_regs = 80;
+  else if (sem == SEM_AGM) bwd_regs = 72;
+  else if (sem == SEM_DGMSR) bwd_regs = 56;
   const char* r = getenv(backward ? "PYSTL_B200_FUSED_REGS_BWD" : "PYSTL_B200_FUSED_REGS");
-  const int target_regs = (r && atoi(r) >= 32) ? atoi(r) : (backward ? 96 : 64);
+  const int target_regs = (r && atoi(r) >= 32) ? atoi(r) : (backward ? bwd_regs : 64);
   int minb = 65536 / (nt * target_regs);
   return minb < 1 ? 1 : (minb > 8 ? 8 : minb);
 }
@@ -81,7 +88,7 @@ static int fused_prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t
   if (rc) return rc;
   rc = fused_geometry(*lw, B, T, D, forced_threads(), backward, g, g_err, sizeof(g_err));
   if (rc) return rc;
-  rc = fused_generate(*lw, D, g->nt, fused_minb(g->nt, backward), backward, fs, g_err, sizeof(g_err));
+  rc = fused_generate(*lw, D, g->nt, fused_minb(g->nt, backward, lw->prog.sem), backward, fs, g_err, sizeof(g_err));
   if (rc) return rc;
   if (fs->smem_floats * 4 > 227 * 1024) return set_err(PYSTL_E_UNSUPPORTED, "fused kernel needs %d bytes of shared memory", fs->smem_floats * 4);
   g->smem_floats = fs->smem_floats;
