@@ -7,8 +7,12 @@ Predicates: the fused kernels evaluate affine predicates
 ``bias + sum_d coeff[d] * signal[t, d]``.  ``metadata["affine"]`` is used when
 present; otherwise ``Predicate.fn`` -- an opaque callable in the reference
 (api.py:24,133-143) -- is probed with float64 rows and accepted if it is an
-affine function of ``signal[t]`` alone.  Anything else raises
-``NotImplementedError`` (no silent host evaluation).
+affine function of ``signal[t]`` alone.  Any other callable becomes a *leaf channel*
+(the precedent is the leaf-tensor path of _dgmsr.py:281-305): the
+semantics object evaluates ``fn`` for every ``(trace, t)`` ON THE DEVICE with torch
+(``leaf_values``), appends the result to the signal as an extra channel and the kernels read it as
+the predicate ``1.0 * channel``; autograd carries the gradient back through ``fn``.  There is no
+host evaluation path: a callable torch cannot trace raises ``NotImplementedError``.
 """
 
 from __future__ import annotations
@@ -89,6 +93,13 @@ class CompiledFormula:
     n_channels_min: int  # highest channel referenced + 1
     channels_used: Tuple[int, ...]
     pred_terms: List[Tuple[Tuple[Tuple[int, float], ...], float]]
+    n_signal_channels: int = 0   # channels of the user's signal
+    leaf_preds: Tuple[Any, ...] = ()  # non-affine predicates: leaf j is channel n_signal_channels + j
+
+    @property
+    def n_channels(self) -> int:
+        """Channels of the tensor the kernels read (signal + leaf channels)."""
+        return self.n_signal_channels + len(self.leaf_preds)
 
     def ptr(self):
         return C.byref(self.struct)
@@ -110,6 +121,8 @@ def compile_formula(
     preds: List[Tuple[Tuple[Tuple[int, float], ...], float]] = []
     pred_index: Dict[Any, int] = {}
     memo: Dict[int, int] = {}
+    leaves: List[Any] = []
+    leaf_index: Dict[int, int] = {}
 
     def add_weights(w) -> Tuple[int, int]:
         if w is None:
@@ -141,11 +154,19 @@ def compile_formula(
         kids: List[int] = []
         if kind == "Predicate":
             n.kind = capi.NODE_PRED
-            terms, bias = affine_of(node, n_channels)
+            try:
+                terms, bias = affine_of(node, n_channels)
+            except NotImplementedError:
+                # not affine: evaluated with torch on the device into leaf channel n_channels + j
+                fkey = id(node.fn)
+                if fkey not in leaf_index:
+                    leaf_index[fkey] = len(leaves)
+                    leaves.append(node)
+                terms, bias = ((n_channels + leaf_index[fkey], 1.0),), 0.0
             if len(terms) > capi.MAX_TERMS:
                 raise NotImplementedError(f"Predicate '{node.name}' has more than {capi.MAX_TERMS} terms")
             for d, _ in terms:
-                if d < 0 or d >= n_channels:
+                if d < 0 or d >= n_channels + len(leaves):
                     raise ValueError(f"Predicate '{node.name}' reads channel {d} of a {n_channels}-channel signal")
             pkey = (terms, bias)
             if pkey not in pred_index:
@@ -221,4 +242,41 @@ def compile_formula(
         n_channels_min=(max(used) + 1) if used else 1,
         channels_used=tuple(sorted(used)),
         pred_terms=preds,
+        n_signal_channels=int(n_channels),
+        leaf_preds=tuple(leaves),
     )
+
+
+def leaf_values(cf: CompiledFormula, sig):
+    """``sig[B, T, D]`` (torch, on the device) -> ``[B, T, D + L]`` with one channel per leaf predicate.
+
+    ``fn(signal, t)`` is the reference's per-trace callable (api.py:24,133-143): it is mapped over
+    the batch with ``torch.func.vmap`` and over ``t`` either with a second vmap (callables that only
+    index with ``t``) or with a Python loop (callables that compute with ``t``)."""
+    import torch
+
+    if not cf.leaf_preds:
+        return sig
+    B, T, _ = sig.shape
+    cols = []
+    for pred in cf.leaf_preds:
+        fn = pred.fn
+        val = None
+        try:
+            t_idx = torch.arange(T, device=sig.device)
+            per_trace = torch.func.vmap(lambda s, t: torch.as_tensor(fn(s, t), dtype=s.dtype), in_dims=(None, 0))
+            val = torch.func.vmap(per_trace, in_dims=(0, None))(sig, t_idx)  # [B, T]
+        except Exception:
+            val = None
+        if val is None or tuple(val.shape) != (B, T):
+            try:
+                rows = [torch.func.vmap(lambda s, tt=tt: torch.as_tensor(fn(s, tt), dtype=s.dtype))(sig) for tt in range(T)]
+                val = torch.stack(rows, dim=1)
+            except Exception as exc:
+                raise NotImplementedError(
+                    f"Predicate '{pred.name}': fn(signal, t) is neither affine nor traceable by torch on the device ({exc!r})"
+                ) from exc
+        if tuple(val.shape) != (B, T):
+            raise NotImplementedError(f"Predicate '{pred.name}': fn(signal, t) must return a scalar")
+        cols.append(val.to(sig.dtype))
+    return torch.cat([sig, torch.stack(cols, dim=-1)], dim=-1).contiguous()

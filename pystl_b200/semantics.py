@@ -33,7 +33,7 @@ from typing import Any, Dict, Optional, Sequence, Tuple
 import torch
 
 from . import capi
-from .compiler import CompiledFormula, compile_formula
+from .compiler import CompiledFormula, compile_formula, leaf_values
 from .formula import Predicate, affine_predicate
 
 
@@ -80,7 +80,7 @@ class _B200Semantics:
         """Tiling / validity report for ``formula`` on traces of ``horizon`` samples (host only)."""
         cf = self.compile(formula, n_channels)
         p = capi.Plan()
-        rc = capi.lib().pystl_b200_plan(cf.ptr(), int(horizon), int(n_channels), 0, C.byref(p))
+        rc = capi.lib().pystl_b200_plan(cf.ptr(), int(horizon), cf.n_channels, 0, C.byref(p))
         capi.raise_for(rc, capi.lib().pystl_b200_last_error())
         return p.as_dict()
 
@@ -120,8 +120,13 @@ class _B200Semantics:
         if torch.is_grad_enabled() and isinstance(signal, torch.Tensor) and signal.requires_grad:
             from .autograd import RobustnessFn
 
-            out = RobustnessFn.apply(signal if not squeeze else signal.unsqueeze(0), self, cf)
+            src = signal if not squeeze else signal.unsqueeze(0)
+            if cf.leaf_preds:  # non-affine predicates: leaf channels computed by torch, inside the graph
+                src = leaf_values(cf, src.to(device=sig.device, dtype=torch.float32))
+            out = RobustnessFn.apply(src, self, cf)
         else:
+            with torch.no_grad():
+                sig = leaf_values(cf, sig)
             out = self._forward_raw(cf, sig, None)
         if home != out.device:
             out = out.to(home)
@@ -142,6 +147,8 @@ class _B200Semantics:
         cf = self.compile(formula, sig.shape[-1])
         acc = torch.zeros(2, dtype=torch.float64, device=sig.device)
         plan = self.plan(formula, sig.shape[1], sig.shape[2])
+        with torch.no_grad():
+            sig = leaf_values(cf, sig)
         self._forward_raw(cf, sig, acc)
         valid = 0 if plan["raises_always"] else max(sig.shape[1] - plan["start_slack"], 0)
         acc[1] = float(sig.shape[0] * valid)
@@ -166,14 +173,22 @@ class _B200Semantics:
         n_total = all_reduce_count(n_local, sig.device, group=group)
         out = torch.empty((B, T, self.out_channels), dtype=torch.float32, device=sig.device)
         acc = torch.zeros(2, dtype=torch.float64, device=sig.device)
-        grad = torch.empty_like(sig)
+        base = sig
+        if cf.leaf_preds:  # the kernel differentiates up to the leaf channels, autograd through fn
+            base = sig.detach().requires_grad_(True)
+            with torch.enable_grad():
+                sig = leaf_values(cf, base)
+        kin = sig.detach()
+        grad = torch.empty_like(kin)
         stream = torch.cuda.current_stream(sig.device).cuda_stream
         with torch.cuda.device(sig.device):
             rc = capi.lib().pystl_b200_eval_value_and_grad(
-                cf.ptr(), sig.data_ptr(), B, T, D, None, (1.0 / n_total) if n_total > 0 else 0.0,
+                cf.ptr(), kin.data_ptr(), B, T, cf.n_channels, None, (1.0 / n_total) if n_total > 0 else 0.0,
                 out.data_ptr(), acc.data_ptr(), grad.data_ptr(), stream,
             )
         capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+        if cf.leaf_preds:
+            (grad,) = torch.autograd.grad(sig, base, grad)
         acc[1] = n_local
         mean = all_reduce_mean(acc, group=group)
         if home != grad.device:

@@ -162,3 +162,18 @@ def test_no_cuda_device_is_an_error_not_a_fallback():
     sem = create_semantics("classical", backend="b200")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         sem.robustness_trace(gt(0, 0.0).always((0, 3)), np.zeros((2, 10, 1), np.float32))
+
+
+def test_non_affine_predicates_become_leaf_channels():
+    """Opaque callables that are not affine in signal[t] are compiled to leaf channels behind the
+    signal's own (compiler.leaf_values evaluates them with torch on the device)."""
+    from pystl_b200.compiler import compile_formula
+    from pystl_b200.formula import Always, And, Interval, Predicate
+
+    sq = Predicate("sq", fn=lambda s, t: s[t, 0] ** 2 - 1.0)
+    lin = Predicate("lin", fn=lambda s, t: 0.5 - s[t, 1])
+    phi = And(Always(sq, Interval(0, 3)), lin, Always(sq, Interval(1, 2)))
+    cf = compile_formula(phi, "smooth", 2, temperature=1.0)
+    assert len(cf.leaf_preds) == 1 and cf.n_signal_channels == 2 and cf.n_channels == 3
+    terms = sorted(cf.pred_terms)
+    assert (((1, -1.0),), 0.5) in terms and (((2, 1.0),), 0.0) in terms
