@@ -97,6 +97,7 @@ struct Gen {
   // classic value-and-gradient: the forward program runs on (value, source) pairs (SEM_CLASSIC_SRC,
   // tile_eval.h) and the gradient is ONE scatter of the root cotangent through the recorded leaf
   bool src_bwd() const { return bwd && P.sem == SEM_CLASSIC; }
+  bool src_image() const { return src_bwd() && D <= 4; }
   bool has_until() const {
     for (int i = 0; i < P.n_instr; ++i)
       if (is_until(P.ins[i])) return true;
@@ -164,9 +165,12 @@ struct Gen {
       flag_off = red_floats + persist;
       persist += roundup(P.n_instr, 4);
     }
-    if (src_bwd()) {  // one scatter plane per predicate
+    if (src_bwd()) {
+      persist = roundup(red_floats + persist, 32) - red_floats;  // (128-byte aligned for the TMA store)
       sp_off = red_floats + persist;
-      persist += P.n_preds * 8 * nt;
+      // narrow signals: the gradient tile as it lies in HBM (8 * nt rows of D floats); wide ones: one
+      // scatter plane per predicate (a 64 KB image would halve the resident CTAs on cfg5)
+      persist += src_image() ? 8 * nt * D : P.n_preds * 8 * nt;
     }
     if (cum_bwd() || (bwd && has_until())) {
       sp_off = red_floats + persist;
@@ -893,13 +897,27 @@ struct Gen {
       // Classic: every output routes its cotangent to ONE leaf sample (the arg-min / arg-max chain of
       // torch.min / max(dim), first index on ties): scatter into one shared plane per predicate
       o.line("// ================= one-hot routing of the root cotangent (classic.py:25-68 under autograd)");
-      for (int q = 0; q < P.n_preds; ++q) o.line("plane_zero8(smem + %d, c.tid);", sp_off + q * 8 * nt);
+      if (!src_image()) {
+        for (int q = 0; q < P.n_preds; ++q) o.line("plane_zero8(smem + %d, c.tid);", sp_off + q * 8 * nt);
+        o.line("simt::sync();");
+        o.line("if (live) classic_scatter<%s, NT>(c, g.T, grad_out, scale, v%d, smem + %d);", P.root_neg ? "true" : "false", (int)P.root, sp_off);
+        o.line("simt::sync();");
+        for (int q = 0; q < P.n_preds; ++q) {
+          o.line("float g%d[8];", (int)P.preds[q].dst);
+          o.line("load8(smem + %d, c.tid, g%d);", sp_off + q * 8 * nt, (int)P.preds[q].dst);
+        }
+      } else {
+      o.line("zero_grad_image<NT, D>(smem + %d, c.tid);", sp_off);
       o.line("simt::sync();");
-      o.line("if (live) classic_scatter<%s, NT>(c, g.T, grad_out, scale, v%d, smem + %d);", P.root_neg ? "true" : "false", (int)P.root, sp_off);
+      o.line("if (live) classic_scatter_rows<%s, NT, D>(c, P, g.T, grad_out, scale, v%d, smem + %d);", P.root_neg ? "true" : "false", (int)P.root,
+             sp_off);
+      o.line("simt::fence_async_smem();");
       o.line("simt::sync();");
-      for (int q = 0; q < P.n_preds; ++q) {
-        o.line("float g%d[8];", (int)P.preds[q].dst);
-        o.line("load8(smem + %d, c.tid, g%d);", sp_off + q * 8 * nt, (int)P.preds[q].dst);
+      o.line("store_grad_image<NT, D>(c, g.T, smem + %d, grad_signal);", sp_off);
+      o.line("if (out && mean_acc) block_sum_to<NT>(c, part, mean_acc, smem + %d);", red_floats - 32);
+      o.indent = 0;
+      o.line("}");
+      return o.s;
       }
     } else if (cum_bwd()) {
       for (int sl = 0; sl < kMaxSlots; ++sl)

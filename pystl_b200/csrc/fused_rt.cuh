@@ -38,6 +38,18 @@ PF_DEV float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m
 PF_DEV int redux_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }
 PF_DEV void atomic_add(float* p, float v) { atomicAdd(p, v); }
 PF_DEV void atomic_add(double* p, double v) { atomicAdd(p, v); }
+// shared -> global bulk copy by the TMA engine (SASS UBLKCP.G.S): `bytes` % 16 == 0, both addresses
+// 16-byte aligned.  The caller has made the shared image visible to the async proxy
+// (fence_async_smem by every writer, then a barrier); the issuing thread waits until the engine has
+// read the image, so that the CTA may exit.
+PF_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+PF_DEV void bulk_store_and_wait(void* dst_global, const void* src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global),
+               "r"((unsigned)__cvta_generic_to_shared(src_smem)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 }  // namespace simt
 #else
 #include "simt_host.h"
@@ -1344,6 +1356,66 @@ PF_DEV void classic_scatter(const TC& c, long long T, const float* __restrict__ 
   if (open) {
     const bool neg = (cur < 0) != NEG;
     simt::atomic_add(&planes[((cur >> 24) & 0x7f) * (8 * NT) + pidx(cur & 0xffffff)], neg ? -acc : acc);
+  }
+}
+
+// Same routing, but straight into the GRADIENT TILE as it lies in HBM: image[pos][d] (8*NT rows of D
+// floats, zeroed).  Each run adds sign * coeff[k] * cotangent to the channels of its source predicate;
+// the finished image leaves through ONE TMA bulk store per CTA (store_grad_image) instead of
+// per-thread row stores -- the value-and-gradient kernel of the classic semantics is bound by the
+// LSU data pipe (ncu: 86 %), and the uncoalesced 64-byte row stores were a quarter of its wavefronts.
+template <bool NEG, int NT, int D>
+PF_DEV void classic_scatter_rows(const TC& c, const TileProgram& P, long long T, const float* __restrict__ grad_out, float scale,
+                                 const Vec<2> (&v)[8], float* image) {
+  float g[8];
+  root_cotangent<false>(c, T, grad_out, scale, g);
+  int cur = 0;
+  float acc = 0.f;
+  bool open = false;
+  auto flush = [&]() {
+    const bool neg = (cur < 0) != NEG;
+    const float a = neg ? -acc : acc;
+    const int q = (cur >> 24) & 0x7f;
+    float* row = image + (cur & 0xffffff) * D;
+    for (int k = 0; k < P.preds[q].n_terms; ++k) simt::atomic_add(&row[P.preds[q].ch[k]], P.preds[q].coeff[k] * a);
+  };
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int s = f2i(v[i].x[1]);
+    const bool on = g[i] != 0.f;
+    if (open && (!on || s != cur)) {
+      flush();
+      open = false;
+    }
+    if (on) {
+      if (!open) {
+        cur = s;
+        acc = 0.f;
+        open = true;
+      }
+      acc += g[i];
+    }
+  }
+  if (open) flush();
+}
+// zero the image with conflict-free 128-bit stores (all threads)
+template <int NT, int D>
+PF_DEV void zero_grad_image(float* image, int tid) {
+  F4* p = reinterpret_cast<F4*>(image);
+#pragma unroll
+  for (int k = 0; k < 2 * D; ++k) p[k * NT + tid] = F4{{0.f, 0.f, 0.f, 0.f}};
+}
+// rows [p_lo, p_hi) of the image -> grad_signal.  All threads call it (after a barrier).
+template <int NT, int D>
+PF_DEV void store_grad_image(const TC& c, long long T, const float* image, float* __restrict__ grad_signal) {
+  if (c.p_hi <= c.p_lo) return;
+  float* dst = grad_signal + ((c.b * T + c.origin + c.p_lo) * (long long)D);
+  const float* src = image + c.p_lo * D;
+  const int n = (c.p_hi - c.p_lo) * D;  // floats; p_lo, p_hi multiples of 8 except at the end of the trace
+  if ((((u64)dst | (u64)src) & 15ull) == 0ull && (n & 3) == 0) {
+    if (c.tid == 0) simt::bulk_store_and_wait(dst, src, (unsigned)n * 4u);
+  } else {
+    for (int j = c.tid; j < n; j += NT) dst[j] = src[j];
   }
 }
 

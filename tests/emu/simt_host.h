@@ -124,6 +124,8 @@ inline int redux_max_i(int v) {
 
 inline void atomic_add(float* p, float v) { *p += v; }
 inline void atomic_add(double* p, double v) { *p += v; }
+inline void fence_async_smem() {}
+inline void bulk_store_and_wait(void* dst_global, const void* src_smem, unsigned bytes) { memcpy(dst_global, src_smem, bytes); }
 
 inline void fiber_entry() {
   Launch* L = cur_launch();
