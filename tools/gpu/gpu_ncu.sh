@@ -1,4 +1,4 @@
-# usage: W=cfg2 TAG=r1f FLAGS="--forward-only" KERNEL=pystl_fused bash gpu_ncu.sh   -- launch list + one full capture
+# usage: W=cfg2 TAG=r1f FLAGS="--forward-only" KERNEL=pystl_fused bash tools/gpu/gpu_ncu.sh   -- launch list + one full capture
 mkdir -p gpurun_out
 export PYSTL_B200_NVRTC_FLAGS=-lineinfo
 W=${W:-cfg2}; TAG=${TAG:-x}; K=${KERNEL:-pystl_fused_value_and_grad}

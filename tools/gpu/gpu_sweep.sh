@@ -1,4 +1,4 @@
-# usage: WORKLOADS="cfg2" NTS="128 192 256 512" MINBS="0" FLAGS="--forward-only" bash gpu_sweep.sh
+# usage: WORKLOADS="cfg2" NTS="128 192 256 512" MINBS="0" FLAGS="--forward-only" bash tools/gpu/gpu_sweep.sh
 mkdir -p gpurun_out
 for w in ${WORKLOADS:-cfg2}; do for nt in ${NTS:-0}; do for mb in ${MINBS:-0}; do
 if [ "$nt" != "0" ]; then export PYSTL_B200_FORCE_THREADS=$nt; else unset PYSTL_B200_FORCE_THREADS; fi
