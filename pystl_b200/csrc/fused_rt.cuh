@@ -576,6 +576,11 @@ struct ClampScanOp {
   }
 };
 
+template <bool B>
+struct BoolC {
+  static constexpr bool value = B;
+};
+
 // ------------------------------------------------------------------ until, O(b) per sample
 // OR_{i in [UA, UB]} AND(AND_{k<=i} l[t+k], r[t+i]) (api.py:284-302 + each semantics'
 // temporal_until) with the per-semantics running state of tile_eval.h (UntilState): 8 outputs
@@ -766,8 +771,99 @@ struct UntilOp {
     }
   }
 
+  // AGM fast path (agm.py:112-130, uniform weights_left / weights_right).  The running state of
+  // UntilState<SEM_AGM> with (a) the shared tail -- the prefix accumulator of output i at q >= p0 + 8
+  // is h_i + M_q, so l_q and r_q are lifted (one lg2 each) once per thread and position -- and (b)
+  // the exp / log round trip between the prefix And and the pair And removed: when every l is
+  // positive, log1p(y_i) IS the prefix mean of log1p(l) (y_i = expm1 of it), so the pair And reads the
+  // accumulator directly.  Per candidate: one rcp (1 / k), one ex2 (geometric pair), one lg2 (Or
+  // lift) instead of about seven transcendentals.  Sums of logarithms are carried in log2 units.
+  PF_DEV static void phase2_agm(float* scr, const TC& c, float w0, float w1, V (&o)[8]) {
+    const int f0 = c.p0 >> 2;
+    constexpr int FMAX = LEXT / 4 - 1;
+    const F4* L4 = reinterpret_cast<const F4*>(lplane(scr, 0));
+    const F4* R4 = reinterpret_cast<const F4*>(rplane(scr, 0));
+    const float invsw = fast_rcp(w0 + w1);
+    float hneg[8], hlog[8], o0[8], o1[8];
+    // one candidate of output i: prefix accumulator (pneg, plog) over k samples, right operand r
+    auto cand = [&](int i, float pneg, float plog, float kf, float rnegw, float rlogw, bool rpos) {
+      const float invk = fast_rcp(kf);
+      const bool flag = plog == f_inf();  // some l <= 0: arithmetic prefix (agm.py:71)
+      const float zA = fmaf(w0, flag ? pneg * invk : 0.f, rnegw) * invsw;
+      const float zG = fast_ex2(fmaf(w0 * invk, plog, rlogw) * invsw) - 1.f;
+      const float z = (flag || !rpos) ? zA : zG;
+      const bool pos = z > 0.f;  // agm.py:86
+      o0[i] += pos ? z : 0.f;
+      o1[i] += pos ? f_inf() : fast_lg2(1.f - z);
+    };
+    {  // own chunk: triangular
+      const F4 la = L4[pf4(f0)], lb = L4[pf4(f0 + 1)], ra = R4[pf4(f0)], rb = R4[pf4(f0 + 1)];
+      const float lo[8] = {la.v[0], la.v[1], la.v[2], la.v[3], lb.v[0], lb.v[1], lb.v[2], lb.v[3]};
+      const float ro[8] = {ra.v[0], ra.v[1], ra.v[2], ra.v[3], rb.v[0], rb.v[1], rb.v[2], rb.v[3]};
+      float ln[8], ll[8], rn[8], rl[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        ln[q] = fminf(lo[q], 0.f);
+        ll[q] = lo[q] <= 0.f ? f_inf() : fast_lg2(1.f + lo[q]);
+        rn[q] = w1 * fminf(ro[q], 0.f);
+        rl[q] = w1 * fast_lg2(1.f + ro[q]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float pn = 0.f, pl = 0.f;
+        o0[i] = 0.f;
+        o1[i] = 0.f;
+#pragma unroll
+        for (int q = i; q < 8; ++q) {
+          pn += ln[q];
+          pl += ll[q];
+          if (q - i >= UA && q - i <= UB) cand(i, pn, pl, (float)(q - i + 1), rn[q], rl[q], ro[q] > 0.f);
+        }
+        hneg[i] = pn;
+        hlog[i] = pl;
+      }
+    }
+    float Mn = 0.f, Ml = 0.f;
+    constexpr int KS0 = UA + 7 > 8 ? UA + 7 : 8;
+    constexpr int KS = (KS0 + 3) & ~3;
+    constexpr int KE = ((UB + 1) & ~3) > KS ? ((UB + 1) & ~3) : KS;  // body [KS, KE): every output takes every position
+    // one 128-bit group of positions at offset 4 * g from p0; ALL: no per-candidate window test
+    auto group = [&](int g, auto all) {
+      const int fc = (f0 + g) < FMAX ? (f0 + g) : FMAX;
+      const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int kq = 4 * g + k;
+        const float l = ql.v[k], r = qr.v[k];
+        Mn += fminf(l, 0.f);
+        Ml += l <= 0.f ? f_inf() : fast_lg2(1.f + l);
+        const float rn = w1 * fminf(r, 0.f), rl = w1 * fast_lg2(1.f + r);
+        const bool rpos = r > 0.f;
+        const float kf = (float)(kq + 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (decltype(all)::value || (kq - i >= UA && kq - i <= UB)) cand(i, hneg[i] + Mn, hlog[i] + Ml, kf - (float)i, rn, rl, rpos);
+      }
+    };
+#pragma unroll
+    for (int g = 2; g < KS / 4; ++g) group(g, BoolC<false>{});
+#pragma unroll 1
+    for (int g = KS / 4; g < KE / 4; ++g) group(g, BoolC<true>{});
+#pragma unroll
+    for (int g = KE / 4; g <= (UB + 7) / 4; ++g) group(g, BoolC<false>{});
+    const float invn = fast_rcp((float)(UB - UA + 1));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i].x[0] = (o1[i] == f_inf()) ? o0[i] * invn : 1.f - fast_ex2(o1[i] * invn);
+  }
+
   PF_DEV static void phase2(float* scr, const TC& c, const RP& rp, float w0, float w1, V (&o)[8], UntilState<SEM> (&st)[8]) {
     const int p0 = c.p0;
+    if constexpr (SEM == SEM_AGM && UA <= 64) {
+      if (cum_fast_ok(c)) {
+        phase2_agm(scr, c, w0, w1, o);
+        return;
+      }
+    }
     if constexpr (SEM == SEM_CUMULATIVE && UA <= 64) {
       if (cum_fast_ok(c)) {
         phase2_cum(scr, c, o);

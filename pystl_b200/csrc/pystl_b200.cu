@@ -65,7 +65,10 @@ static int tier_mode() {
 }
 
 // registers per thread the fused kernels are compiled for: min CTAs per SM by CTA size
-static int fused_minb(int nt, bool backward, int sem) {
+static int fused_minb(int nt, bool backward, const TileProgram& prog) {
+  const int sem = prog.sem;
+  bool has_until = false;  // the O(b) walks keep 8 running states live: they want their registers
+  for (int i = 0; i < prog.n_instr; ++i) has_until |= prog.ins[i].op == T_UNTIL;
   const char* e = getenv("PYSTL_B200_FUSED_MINB");
   if (e && *e) return atoi(e) > 0 ? atoi(e) : 1;
   // The backward kernels keep the forward values AND the adjoints of 8 samples in registers, but
@@ -78,7 +81,7 @@ static int fused_minb(int nt, bool backward, int sem) {
   else if (sem == SEM_DGMSR) bwd_regs = 56;
   const char* r = getenv(backward ? "PYSTL_B200_FUSED_REGS_BWD" : "PYSTL_B200_FUSED_REGS");
   // forward kernels: 56 registers (cfg2 0.785 -> 0.773 ms), 48 for agm / dgmsr (cfg3 1.05 -> 0.97 ms)
-  const int fwd_regs = (sem == SEM_AGM || sem == SEM_DGMSR) ? 48 : 56;
+  const int fwd_regs = has_until ? 64 : ((sem == SEM_AGM || sem == SEM_DGMSR) ? 48 : 56);
   const int target_regs = (r && atoi(r) >= 32) ? atoi(r) : (backward ? bwd_regs : fwd_regs);
   int minb = 65536 / (nt * target_regs);
   return minb < 1 ? 1 : (minb > 8 ? 8 : minb);
@@ -90,7 +93,7 @@ static int fused_prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t
   if (rc) return rc;
   rc = fused_geometry(*lw, B, T, D, forced_threads(), backward, g, g_err, sizeof(g_err));
   if (rc) return rc;
-  rc = fused_generate(*lw, D, g->nt, fused_minb(g->nt, backward, lw->prog.sem), backward, fs, g_err, sizeof(g_err));
+  rc = fused_generate(*lw, D, g->nt, fused_minb(g->nt, backward, lw->prog), backward, fs, g_err, sizeof(g_err));
   if (rc) return rc;
   if (fs->smem_floats * 4 > 227 * 1024) return set_err(PYSTL_E_UNSUPPORTED, "fused kernel needs %d bytes of shared memory", fs->smem_floats * 4);
   g->smem_floats = fs->smem_floats;
