@@ -31,6 +31,14 @@ OUT = os.path.join(ROOT, "tests", "_emu", "libpystl_emu.so")
 _lib = None
 
 
+def _affine_only(cf):
+    """The host emulators run the kernels only: leaf channels (non-affine predicates) are computed
+    by torch on the device in the product and have no place here."""
+    if cf.leaf_preds:
+        raise NotImplementedError("the host emulator does not evaluate leaf (non-affine) predicates")
+    return cf
+
+
 def build(force: bool = False) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     stale = force or not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS)
@@ -61,7 +69,7 @@ def lib() -> C.CDLL:
 
 
 def plan(formula, semantics: str, T: int, D: int, **kw) -> dict:
-    cf = compile_formula(formula, semantics, D, **kw)
+    cf = _affine_only(compile_formula(formula, semantics, D, **kw))
     p = capi.Plan()
     rc = lib().pystl_emu_plan(cf.ptr(), T, D, 0, C.byref(p))
     capi.raise_for(rc, lib().pystl_emu_last_error())
@@ -72,7 +80,7 @@ def eval_forward(formula, semantics: str, signal: np.ndarray, *, force_threads: 
     """signal [B, T, D] float32 -> out [B, T] (cumulative [B, T, 2]) float32."""
     sig = np.ascontiguousarray(signal, dtype=np.float32)
     B, T, D = sig.shape
-    cf = compile_formula(formula, semantics, D, **kw)
+    cf = _affine_only(compile_formula(formula, semantics, D, **kw))
     ch = 2 if semantics == "cumulative" else 1
     out = np.full((B, T, ch), np.float32(-12345.0), dtype=np.float32)
     acc = np.zeros(2, dtype=np.float64)
@@ -89,7 +97,7 @@ def eval_backward(formula, semantics: str, signal: np.ndarray, grad_out=None, *,
     """d sum(grad_out * out) / d signal, [B, T, D] float32 (grad_out None: constant cotangent `scale`)."""
     sig = np.ascontiguousarray(signal, dtype=np.float32)
     B, T, D = sig.shape
-    cf = compile_formula(formula, semantics, D, **kw)
+    cf = _affine_only(compile_formula(formula, semantics, D, **kw))
     go = None if grad_out is None else np.ascontiguousarray(grad_out, dtype=np.float32)
     gs = np.full((B, T, D), np.float32(-12345.0), dtype=np.float32)
     rc = lib().pystl_emu_eval_backward(

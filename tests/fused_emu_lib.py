@@ -31,6 +31,14 @@ _kernels: dict = {}
 _sizes = None
 
 
+def _affine_only(cf):
+    """The host emulators run the kernels only: leaf channels (non-affine predicates) are computed
+    by torch on the device in the product and have no place here."""
+    if cf.leaf_preds:
+        raise NotImplementedError("the host emulator does not evaluate leaf (non-affine) predicates")
+    return cf
+
+
 def _lib():
     h = emu_lib.lib()
     if not hasattr(h, "_fused_declared"):
@@ -97,7 +105,7 @@ def kernel(source: str, backward: bool):
 def eval_forward(formula, semantics: str, signal: np.ndarray, *, force_threads: int = 0, mean: bool = False, **kw):
     sig = np.ascontiguousarray(signal, dtype=np.float32)
     B, T, D = sig.shape
-    cf = compile_formula(formula, semantics, D, **kw)
+    cf = _affine_only(compile_formula(formula, semantics, D, **kw))
     src, prog, geom, smem = prepare(cf, B, T, D, False, force_threads)
     k = kernel(src, False)
     ch = 2 if semantics == "cumulative" else 1
@@ -112,7 +120,7 @@ def eval_backward(formula, semantics: str, signal: np.ndarray, grad_out=None, *,
                   force_threads: int = 0, **kw) -> np.ndarray:
     sig = np.ascontiguousarray(signal, dtype=np.float32)
     B, T, D = sig.shape
-    cf = compile_formula(formula, semantics, D, **kw)
+    cf = _affine_only(compile_formula(formula, semantics, D, **kw))
     src, prog, geom, smem = prepare(cf, B, T, D, True, force_threads)
     k = kernel(src, True)
     go = None if grad_out is None else np.ascontiguousarray(grad_out, dtype=np.float32)
