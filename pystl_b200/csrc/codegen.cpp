@@ -93,6 +93,9 @@ struct Gen {
   int sp_off = 0;                  // cumulative backward: four scatter planes
   int stage_off = 0;               // cooperative row staging (aliases the scratch regions)
   bool coop_stage() const { return D >= 4 && D <= 8; }
+  // D == 2: the kernel can take its tile through one TMA tensor copy (run-time flag TileGeom::use_tma)
+  bool tma_capable() const { return D == 2 && nt % ((nt + 255) / 256) == 0; }
+  int bar_off = 0;                 // the TMA load's mbarrier
   bool cum_bwd() const { return bwd && P.sem == SEM_CUMULATIVE; }
   // classic value-and-gradient: the forward program runs on (value, source) pairs (SEM_CLASSIC_SRC,
   // tile_eval.h) and the gradient is ONE scatter of the root cotangent through the recorded leaf
@@ -150,7 +153,12 @@ struct Gen {
     // writers of level l+2); the adjoint windows of level l use region (l+1) & 1 for the same
     // reason, walking the levels downwards.
     const int nw = nt / 32;
-    red_floats = roundup(std::max(2 * std::max(P.n_preds, 1), 1) * nw, 32) + 32;  // + the mean reduction's own 32 floats
+    red_floats = roundup(std::max(2 * std::max(P.n_preds, 1), 1) * nw, 32);
+    if (tma_capable()) {
+      bar_off = red_floats;
+      red_floats += 32;
+    }
+    red_floats += 32;  // + the mean reduction's own 32 floats
     bscr_off.assign(P.n_instr, 0);
     int persist = 0;
     const bool stash_persists = bwd && P.sem == SEM_SMOOTH;  // the exact scatter re-reads the operands
@@ -238,6 +246,10 @@ struct Gen {
       stage_off = base0;
       smem_floats = std::max(smem_floats, base0 + 8 * nt * D);
     }
+    if (tma_capable()) {  // the same, 1024-byte aligned for the swizzled TMA box
+      stage_off = roundup(base0, 256);
+      smem_floats = std::max(smem_floats, stage_off + 8 * nt * D);
+    }
   }
 
   // expression of operand j of instruction `in` at sample i
@@ -279,11 +291,16 @@ struct Gen {
   void emit_predicates() {
     o.line("// ---- predicates: rows -> registers (api.py:142-143)");
     for (int q = 0; q < P.n_preds; ++q) o.line("V v%d[8];", (int)P.preds[q].dst);
+    if (tma_capable()) {
+      o.line("float r[8][D];");
+      o.line("if (g.use_tma) load_rows_tma<D, NT>(c, g, smem + %d, smem + %d, r);  // one TMA tensor copy per CTA", stage_off, bar_off);
+    }
     o.line("if (live) {");
     o.indent++;
     if (D <= 8) {
-      o.line("float r[8][D];");
+      if (!tma_capable()) o.line("float r[8][D];");
       if (coop_stage()) o.line("load_rows_coop<D>(c, signal, g.T, smem + %d, r);  // coalesced, transposed through shared memory", stage_off);
+      else if (tma_capable()) o.line("if (!g.use_tma) load_rows<D>(c, signal, g.T, r);");
       else o.line("load_rows<D>(c, signal, g.T, r);");
       o.line("prefetch_rows<D>(c, signal, g.B, g.T, g.scr_planes);  // (scr_planes carries the prefetch distance in traces)");
     }
@@ -324,6 +341,7 @@ struct Gen {
     o.indent--;
     o.line("}");
     if (coop_stage()) o.line("simt::sync();  // the staging area is reused as window scratch");
+    if (tma_capable()) o.line("if (g.use_tma) simt::sync();  // the staging area is reused as window scratch");
     if (P.sem == SEM_SMOOTH) {
       int nb = 0;
       for (int q = 0; q < P.n_preds; ++q) nb += need_lo[P.preds[q].dst] + need_hi[P.preds[q].dst];

@@ -26,7 +26,7 @@
 #define PF_DEV __device__ __forceinline__
 #define PF_KERNEL(NT, MINB) extern "C" __global__ void __launch_bounds__(NT, MINB)
 #define PF_GRID_CONSTANT __grid_constant__
-#define PF_DYN_SMEM(name) extern __shared__ __align__(128) float name[]
+#define PF_DYN_SMEM(name) extern __shared__ __align__(1024) float name[]
 namespace simt {
 PF_DEV int tid() { return (int)threadIdx.x; }
 PF_DEV int bid_x() { return (int)blockIdx.x; }
@@ -43,6 +43,34 @@ PF_DEV void atomic_add(double* p, double v) { atomicAdd(p, v); }
 // (fence_async_smem by every writer, then a barrier); the issuing thread waits until the engine has
 // read the image, so that the CTA may exit.
 PF_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// mbarrier + 2-D TMA tensor load (SASS UTMALDG): one thread arms the barrier with the byte count
+// and issues the copy, everybody waits on the phase bit
+PF_DEV void mbar_init(void* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PF_DEV void mbar_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+PF_DEV void mbar_wait(void* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+PF_DEV void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, void* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
 PF_DEV void bulk_store_and_wait(void* dst_global, const void* src_smem, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global),
                "r"((unsigned)__cvta_generic_to_shared(src_smem)), "r"(bytes)
@@ -155,6 +183,38 @@ PF_DEV void load_rows(const TC& c, const float* __restrict__ signal, long long T
 #pragma unroll
       for (int d = 0; d < D; ++d) r[i][d] = ok ? src[i * D + d] : 0.f;
     }
+  }
+}
+// D == 2: a thread's 8 rows are 64 bytes, so a 128-bit load of a warp touches 16 lines where a
+// coalesced one touches 4, and the LSU data pipe -- not HBM -- is what the Classic kernels saturate
+// (ncu: 97 % on cfg1x).  When the launch qualifies (TileGeom::use_tma) the CTA's tile is fetched by ONE
+// TMA tensor copy instead: the signal is described as rows of 64 bytes with SWIZZLE_64B, so that
+// the per-thread 128-bit reads of the staged tile (thread t owns row t, chunk k of it lives at
+// k ^ ((t >> 1) & 3)) are bank-conflict free: 4 wavefronts per instruction instead of 16, and no
+// global-load instructions at all.  Rows past the end of the tensor arrive as zeros; rows past the end
+// of the trace belong to the next trace and are never consumed (the lifts replace them).
+// All threads call it (it contains a barrier).  stage: 1024-byte aligned, 8 * NT * D floats.
+template <int D, int NT>
+PF_DEV void load_rows_tma(const TC& c, const TileGeom& g, float* stage, float* bar, float (&r)[8][D]) {
+  static_assert(D == 2, "64-byte rows per thread");
+  if (c.tid == 0) simt::mbar_init(bar);
+  simt::sync();
+  constexpr int NBOX = (NT + 255) / 256, ROWS = NT / NBOX;  // a TMA box has at most 256 rows
+  static_assert(NT % NBOX == 0, "the tile splits into equal boxes");
+  if (c.tid == 0) {
+    simt::mbar_expect_tx(bar, 8u * NT * D * 4u);
+    const long long row = ((c.b * g.T + c.origin) * (long long)D) >> 4;  // 16 floats per row
+#pragma unroll
+    for (int k = 0; k < NBOX; ++k) simt::tma_load_2d(stage + k * ROWS * 16, &g.tmap, 0, (int)row + k * ROWS, bar);
+  }
+  simt::mbar_wait(bar, 0u);
+  const char* base = reinterpret_cast<const char*>(stage) + c.tid * 64;
+  const int sw = (c.tid >> 1) & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const F4 q = *reinterpret_cast<const F4*>(base + ((k ^ sw) << 4));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[(4 * k + e) / D][(4 * k + e) % D] = q.v[e];
   }
 }
 // Wide rows (D >= 4): a thread's 8 rows are 128+ bytes apart from its neighbour's, so per-thread

@@ -138,6 +138,10 @@ struct TileGeom {
                        // hold the identity so that window reads need no bounds checks
   // shared-memory carve-up, in floats
   int32_t off_planes, off_scratch, off_chunk, off_red, smem_floats;
+  // fused tier, D == 2: the signal viewed as rows of 64 bytes, fetched tile by tile with one TMA
+  // tensor copy (SWIZZLE_64B) when the launch qualifies (pystl_b200.cu: fused_tma_setup)
+  int32_t use_tma;
+  alignas(64) unsigned long long tmap[16];  // CUtensorMap, opaque here
 };
 
 // Lowering result (host only).

@@ -7,6 +7,7 @@
 // root robustness goes back to HBM.  Bandwidth-bound windowed reductions: no
 // tensor cores on purpose.  Kernels: kernels.cuh, instantiated per semantics in
 // kernels_sem.cu.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -109,6 +110,51 @@ static int fused_prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t
   return PYSTL_OK;
 }
 
+// D == 2: describe the signal as rows of 64 bytes for the TMA tile load of the fused kernels
+// (fused_rt.cuh: load_rows_tma).  The launch qualifies when every tile starts on a 64-byte row
+// (tile origins are multiples of 8 samples = 64 bytes; the trace stride T * D * 4 must be one too),
+// the box of one tile has at most 256 rows and the driver offers cuTensorMapEncodeTiled.
+// PYSTL_B200_TMA=0 switches the path off.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+static void fused_tma_setup(TileGeom* g, const float* signal, int sem) {
+  g->use_tma = 0;
+  // (measured: +17 % on cfg1x, +5 % on cfg2 forward; the agm / dgmsr kernels are latency bound and
+  // do not gain from it: 2.93 vs 2.95 ms on cfg3)
+  if (sem == SEM_AGM || sem == SEM_DGMSR) return;
+  static_assert(sizeof(CUtensorMap) == sizeof(g->tmap), "CUtensorMap is 128 bytes");
+  const char* e = getenv("PYSTL_B200_TMA");
+  if (e && atoi(e) == 0) return;
+  const int nbox = (g->nt + 255) / 256;  // boxes of at most 256 rows (fused_rt.cuh: load_rows_tma)
+  if (g->D != 2 || g->nt % nbox != 0 || g->B <= 0 || g->T <= 0) return;
+  if ((g->T * g->D) % 16 != 0 || (reinterpret_cast<uintptr_t>(signal) & 63u) != 0) return;
+  const uint64_t rows = (uint64_t)g->B * (uint64_t)g->T * (uint64_t)g->D / 16u;
+  if (rows > 0x7fffffffull) return;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return;
+  const cuuint64_t dims[2] = {16, rows};
+  const cuuint64_t strides[1] = {64};
+  const cuuint32_t box[2] = {16, (cuuint32_t)(g->nt / nbox)};  // one row per thread
+  const cuuint32_t estr[2] = {1, 1};
+  CUtensorMap tm;
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(signal), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return;
+  memcpy(g->tmap, &tm, sizeof(tm));
+  g->use_tma = 1;
+}
+
 static int fused_launch(const Lowered& lw, const TileGeom& g, const FusedSource& fs, void** args, cudaStream_t stream) {
   FusedKernel fk;
   int rc = fused_jit_get(fs, &fk, g_err, sizeof(g_err));
@@ -202,6 +248,7 @@ extern "C" int pystl_b200_eval_forward(const pystl_formula_t* f, const float* si
     if (rc == PYSTL_OK) {
       if (B == 0 || T == 0) return PYSTL_OK;
       if (!signal || !out) return set_err(PYSTL_E_INVALID, "signal / out is NULL");
+      fused_tma_setup(&g, signal, lw.prog.sem);
       void* args[] = {(void*)&lw.prog, (void*)&g, (void*)&signal, (void*)&out, (void*)&mean_acc};
       rc = fused_launch(lw, g, fs, args, reinterpret_cast<cudaStream_t>(stream));
     }
@@ -234,6 +281,7 @@ static int fused_value_and_grad(const pystl_formula_t* f, const float* signal, i
   if (rc) return rc;
   if (B == 0 || T == 0) return PYSTL_OK;
   if (!signal || !grad_signal) return set_err(PYSTL_E_INVALID, "signal / grad_signal is NULL");
+  fused_tma_setup(&g, signal, lw.prog.sem);
   void* args[] = {(void*)&lw.prog, (void*)&g,           (void*)&signal, (void*)&grad_out,
                   (void*)&grad_scale, (void*)&grad_signal, (void*)&out,    (void*)&mean_acc};
   return fused_launch(lw, g, fs, args, stream);

@@ -125,6 +125,11 @@ inline int redux_max_i(int v) {
 inline void atomic_add(float* p, float v) { *p += v; }
 inline void atomic_add(double* p, double v) { *p += v; }
 inline void fence_async_smem() {}
+// (TileGeom::use_tma is never set on the host: the TMA tile load is a GPU-only path)
+inline void mbar_init(void*) { abort(); }
+inline void mbar_expect_tx(void*, unsigned) { abort(); }
+inline void mbar_wait(void*, unsigned) { abort(); }
+inline void tma_load_2d(void*, const void*, int, int, void*) { abort(); }
 inline void bulk_store_and_wait(void* dst_global, const void* src_smem, unsigned bytes) { memcpy(dst_global, src_smem, bytes); }
 
 inline void fiber_entry() {
