@@ -969,10 +969,12 @@ struct Gen {
       }
     }
     o.line("// ================= gradient of the signal: chain rule through the affine predicates");
+    const bool tma_st = tma_capable();
+    if (tma_st) o.line("float gr[8][D];");
     o.line("if (live) {");
     o.indent++;
     if (D <= 8) {
-      o.line("float gr[8][D];");
+      if (!tma_st) o.line("float gr[8][D];");
       o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) {");
       o.indent++;
       for (int d = 0; d < D; ++d) {
@@ -992,7 +994,7 @@ struct Gen {
       }
       o.indent--;
       o.line("}");
-      o.line("store_grad_rows<D>(c, g.T, gr, grad_signal);");
+      if (!tma_st) o.line("store_grad_rows<D>(c, g.T, gr, grad_signal);");
     } else {
       for (int d = 0; d < D; ++d) {
         std::string e;
@@ -1013,6 +1015,7 @@ struct Gen {
     }
     o.indent--;
     o.line("}");
+    if (tma_st) o.line("store_grad_rows_tma<D, NT>(c, g, live, gr, grad_signal, smem + %d);", stage_off);
     o.line("if (out && mean_acc) block_sum_to<NT>(c, part, mean_acc, smem + %d);", red_floats - 32);
     o.indent = 0;
     o.line("}");
@@ -1176,7 +1179,8 @@ int fused_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force
     for (int k = 0; k < P.preds[q].n_terms; ++k)
       if (P.preds[q].ch[k] < 0 || P.preds[q].ch[k] >= D) return fail(PYSTL_E_INVALID, "predicate reads a channel the signal does not have");
   const int H = lw.lookahead;
-  const int hh = backward ? roundup(H, 8) : 0;
+  // (two-channel signals: 16, so that the first row a tile stores starts a 128-byte line of the TMA staging area)
+  const int hh = backward ? roundup(H, D == 2 ? 16 : 8) : 0;
   const int64_t Tn = std::max<int64_t>(T, 1);
   auto build = [&](int nt, TileGeom* out) -> bool {
     TileGeom t{};

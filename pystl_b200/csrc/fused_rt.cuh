@@ -65,6 +65,15 @@ PF_DEV void mbar_wait(void* bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+PF_DEV void tma_store_3d(const void* tmap, const void* src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"((unsigned)__cvta_generic_to_shared(src_smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+PF_DEV void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 PF_DEV void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, void* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                    (unsigned)__cvta_generic_to_shared(dst_smem)),
@@ -1972,6 +1981,37 @@ PF_DEV void store_grad_rows(const TC& c, long long T, const float (&gr)[8][D], f
 #pragma unroll
         for (int d = 0; d < D; ++d) dst[i * D + d] = gr[i][d];
       }
+  }
+}
+// D == 2, qualifying launches (TileGeom::use_tma_st): the tile's gradient rows leave through the TMA
+// engine.  Each thread parks its 64 bytes in the staging area with the SWIZZLE_64B pattern of
+// load_rows_tma (conflict-free 128-bit stores: 4 wavefronts per instruction where the global row
+// stores took 16), then one thread issues the tensor store of rows [p_lo, p_hi); the tensor is
+// [trace][row][16 floats], so a last, shorter tile is clipped at the end of its trace by the
+// hardware.  All threads call it.  stage: 1024-byte aligned, aliases the window scratch.
+template <int D, int NT>
+PF_DEV void store_grad_rows_tma(const TC& c, const TileGeom& g, bool live, const float (&gr)[8][D], float* __restrict__ grad_signal,
+                                float* stage) {
+  static_assert(D == 2, "64-byte rows per thread");
+  if (!g.use_tma_st) {
+    if (live) store_grad_rows<D>(c, g.T, gr, grad_signal);
+    return;
+  }
+  simt::sync();  // the last adjoint stage may still be reading the scratch this aliases
+  if (live && c.p0 >= c.p_lo && c.p0 + 8 <= c.p_hi) {
+    char* base = reinterpret_cast<char*>(stage) + c.tid * 64;
+    const int sw = (c.tid >> 1) & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      *reinterpret_cast<F4*>(base + ((k ^ sw) << 4)) = F4{{gr[2 * k][0], gr[2 * k][1], gr[2 * k + 1][0], gr[2 * k + 1][1]}};
+  }
+  simt::fence_async_smem();
+  simt::sync();
+  if (c.tid == 0) {
+    const int row0 = (int)((c.origin + c.p_lo) >> 3);  // 64-byte row inside the trace: 8 samples of 2 channels
+    for (int k = 0; k < g.st_nbox; ++k)
+      simt::tma_store_3d(&g.tmap_st, stage + ((c.p_lo >> 3) + k * g.st_rows) * 16, 0, row0 + k * g.st_rows, (int)c.b);
+    simt::tma_store_commit_wait();
   }
 }
 // wide signals (D > 8): one channel at a time

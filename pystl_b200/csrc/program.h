@@ -141,7 +141,11 @@ struct TileGeom {
   // fused tier, D == 2: the signal viewed as rows of 64 bytes, fetched tile by tile with one TMA
   // tensor copy (SWIZZLE_64B) when the launch qualifies (pystl_b200.cu: fused_tma_setup)
   int32_t use_tma;
-  alignas(64) unsigned long long tmap[16];  // CUtensorMap, opaque here
+  // ... and grad_signal as [trace][64-byte row][16 floats] for the TMA store of a tile's gradient rows
+  // (clipped at the end of the trace by the tensor bounds): st_nbox boxes of st_rows rows each
+  int32_t use_tma_st, st_rows, st_nbox;
+  alignas(64) unsigned long long tmap[16];     // CUtensorMap, opaque here
+  alignas(64) unsigned long long tmap_st[16];
 };
 
 // Lowering result (host only).

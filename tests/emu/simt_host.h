@@ -130,6 +130,8 @@ inline void mbar_init(void*) { abort(); }
 inline void mbar_expect_tx(void*, unsigned) { abort(); }
 inline void mbar_wait(void*, unsigned) { abort(); }
 inline void tma_load_2d(void*, const void*, int, int, void*) { abort(); }
+inline void tma_store_3d(const void*, const void*, int, int, int) { abort(); }
+inline void tma_store_commit_wait() { abort(); }
 inline void bulk_store_and_wait(void* dst_global, const void* src_smem, unsigned bytes) { memcpy(dst_global, src_smem, bytes); }
 
 inline void fiber_entry() {
