@@ -94,7 +94,12 @@ struct Gen {
   int stage_off = 0;               // cooperative row staging (aliases the scratch regions)
   bool coop_stage() const { return D >= 4 && D <= 8; }
   // D == 2: the kernel can take its tile through one TMA tensor copy (run-time flag TileGeom::use_tma)
-  bool tma_capable() const { return D == 2 && nt % ((nt + 255) / 256) == 0; }
+  bool tma_capable() const {
+    if (D != 2 && D != 4 && D != 8) return false;
+    const int rows = nt * (D == 8 ? 2 : 1);  // 64-byte rows for D = 2, 128-byte rows for D = 4, 8
+    return rows % ((rows + 255) / 256) == 0;
+  }
+  bool tma_store_capable() const { return D == 2 && tma_capable(); }
   int bar_off = 0;                 // the TMA load's mbarrier
   bool cum_bwd() const { return bwd && P.sem == SEM_CUMULATIVE; }
   // classic value-and-gradient: the forward program runs on (value, source) pairs (SEM_CLASSIC_SRC,
@@ -299,7 +304,9 @@ struct Gen {
     o.indent++;
     if (D <= 8) {
       if (!tma_capable()) o.line("float r[8][D];");
-      if (coop_stage()) o.line("load_rows_coop<D>(c, signal, g.T, smem + %d, r);  // coalesced, transposed through shared memory", stage_off);
+      if (coop_stage())
+        o.line("%sload_rows_coop<D>(c, signal, g.T, smem + %d, r);  // coalesced, transposed through shared memory",
+               tma_capable() ? "if (!g.use_tma) " : "", stage_off);
       else if (tma_capable()) o.line("if (!g.use_tma) load_rows<D>(c, signal, g.T, r);");
       else o.line("load_rows<D>(c, signal, g.T, r);");
       o.line("prefetch_rows<D>(c, signal, g.B, g.T, g.scr_planes);  // (scr_planes carries the prefetch distance in traces)");
@@ -341,7 +348,7 @@ struct Gen {
     o.indent--;
     o.line("}");
     if (coop_stage()) o.line("simt::sync();  // the staging area is reused as window scratch");
-    if (tma_capable()) o.line("if (g.use_tma) simt::sync();  // the staging area is reused as window scratch");
+    else if (tma_capable()) o.line("if (g.use_tma) simt::sync();  // the staging area is reused as window scratch");
     if (P.sem == SEM_SMOOTH) {
       int nb = 0;
       for (int q = 0; q < P.n_preds; ++q) nb += need_lo[P.preds[q].dst] + need_hi[P.preds[q].dst];
@@ -969,7 +976,7 @@ struct Gen {
       }
     }
     o.line("// ================= gradient of the signal: chain rule through the affine predicates");
-    const bool tma_st = tma_capable();
+    const bool tma_st = tma_store_capable();
     if (tma_st) o.line("float gr[8][D];");
     o.line("if (live) {");
     o.indent++;

@@ -205,23 +205,27 @@ PF_DEV void load_rows(const TC& c, const float* __restrict__ signal, long long T
 // All threads call it (it contains a barrier).  stage: 1024-byte aligned, 8 * NT * D floats.
 template <int D, int NT>
 PF_DEV void load_rows_tma(const TC& c, const TileGeom& g, float* stage, float* bar, float (&r)[8][D]) {
-  static_assert(D == 2, "64-byte rows per thread");
+  static_assert(D == 2 || D == 4 || D == 8, "rows of 64 bytes (D = 2) or 128 bytes (D = 4, 8)");
+  // D = 4 / 8: rows of 128 bytes with SWIZZLE_128B (chunk ^= row & 7); a thread owns one row (D = 4,
+  // conflict-free) or two (D = 8, two-way conflicts -- still half the wavefronts of the
+  // load + transpose through shared memory it replaces, and no global-load instructions)
+  constexpr int ROWB = D == 2 ? 64 : 128, RPT = 32 * D / ROWB, SWZ = D == 2 ? 3 : 7;
+  constexpr int TROWS = NT * RPT, NBOX = (TROWS + 255) / 256, ROWS = TROWS / NBOX;  // a TMA box has at most 256 rows
+  static_assert(TROWS % NBOX == 0, "the tile splits into equal boxes");
   if (c.tid == 0) simt::mbar_init(bar);
   simt::sync();
-  constexpr int NBOX = (NT + 255) / 256, ROWS = NT / NBOX;  // a TMA box has at most 256 rows
-  static_assert(NT % NBOX == 0, "the tile splits into equal boxes");
   if (c.tid == 0) {
     simt::mbar_expect_tx(bar, 8u * NT * D * 4u);
-    const long long row = ((c.b * g.T + c.origin) * (long long)D) >> 4;  // 16 floats per row
+    const long long row = ((c.b * g.T + c.origin) * (long long)D * 4) / ROWB;
 #pragma unroll
-    for (int k = 0; k < NBOX; ++k) simt::tma_load_2d(stage + k * ROWS * 16, &g.tmap, 0, (int)row + k * ROWS, bar);
+    for (int k = 0; k < NBOX; ++k) simt::tma_load_2d(stage + k * ROWS * (ROWB / 4), &g.tmap, 0, (int)row + k * ROWS, bar);
   }
   simt::mbar_wait(bar, 0u);
-  const char* base = reinterpret_cast<const char*>(stage) + c.tid * 64;
-  const int sw = (c.tid >> 1) & 3;
+  const char* base = reinterpret_cast<const char*>(stage);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const F4 q = *reinterpret_cast<const F4*>(base + ((k ^ sw) << 4));
+  for (int k = 0; k < 2 * D; ++k) {
+    const unsigned o = (unsigned)c.tid * (32u * D) + 16u * k;  // linear byte offset of the 16-byte chunk
+    const F4 q = *reinterpret_cast<const F4*>(base + (o ^ (((o >> 7) & SWZ) << 4)));
 #pragma unroll
     for (int e = 0; e < 4; ++e) r[(4 * k + e) / D][(4 * k + e) % D] = q.v[e];
   }

@@ -133,23 +133,29 @@ static void fused_tma_setup(TileGeom* g, const float* signal, int sem) {
   // (measured: +17 % on cfg1x, +5 % on cfg2 forward; the agm / dgmsr kernels are latency bound and
   // do not gain from it: 2.93 vs 2.95 ms on cfg3)
   if (sem == SEM_AGM || sem == SEM_DGMSR) return;
+  // (value-and-gradient kernels other than the classic one: 1.646 ms without, 1.671 ms with it on cfg2)
+  if (g->bwd && sem != SEM_CLASSIC) return;
   static_assert(sizeof(CUtensorMap) == sizeof(g->tmap), "CUtensorMap is 128 bytes");
   const char* e = getenv("PYSTL_B200_TMA");
   if (e && atoi(e) == 0) return;
-  const int nbox = (g->nt + 255) / 256;  // boxes of at most 256 rows (fused_rt.cuh: load_rows_tma)
-  if (g->D != 2 || g->nt % nbox != 0 || g->B <= 0 || g->T <= 0) return;
-  if ((g->T * g->D) % 16 != 0 || (reinterpret_cast<uintptr_t>(signal) & 63u) != 0) return;
-  const uint64_t rows = (uint64_t)g->B * (uint64_t)g->T * (uint64_t)g->D / 16u;
+  if (g->D != 2 && g->D != 4 && g->D != 8) return;
+  const int rowb = g->D == 2 ? 64 : 128;                 // bytes per tensor row (fused_rt.cuh: load_rows_tma)
+  const int trows = g->nt * (32 * g->D / rowb);          // rows of one tile
+  const int nbox = (trows + 255) / 256;                  // boxes of at most 256 rows
+  if (trows % nbox != 0 || g->B <= 0 || g->T <= 0) return;
+  if ((g->T * g->D * 4) % rowb != 0 || (reinterpret_cast<uintptr_t>(signal) & (uintptr_t)(rowb - 1)) != 0) return;
+  const uint64_t rows = (uint64_t)g->B * (uint64_t)g->T * (uint64_t)g->D * 4u / (uint64_t)rowb;
   if (rows > 0x7fffffffull) return;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return;
-  const cuuint64_t dims[2] = {16, rows};
-  const cuuint64_t strides[1] = {64};
-  const cuuint32_t box[2] = {16, (cuuint32_t)(g->nt / nbox)};  // one row per thread
+  const cuuint64_t dims[2] = {(cuuint64_t)(rowb / 4), rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)rowb};
+  const cuuint32_t box[2] = {(cuuint32_t)(rowb / 4), (cuuint32_t)(trows / nbox)};
   const cuuint32_t estr[2] = {1, 1};
   CUtensorMap tm;
   if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(signal), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          g->D == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return;
   memcpy(g->tmap, &tm, sizeof(tm));
   g->use_tma = 1;
