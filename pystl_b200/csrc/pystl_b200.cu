@@ -135,6 +135,9 @@ static void fused_tma_setup(TileGeom* g, const float* signal, int sem) {
   if (sem == SEM_AGM || sem == SEM_DGMSR) return;
   // (value-and-gradient kernels other than the classic one: 1.646 ms without, 1.671 ms with it on cfg2)
   if (g->bwd && sem != SEM_CLASSIC) return;
+  // a launch of a few waves is latency bound: the barrier + TMA round trip at the head of every CTA
+  // costs more than the wavefronts it saves (cfg1, 1024 CTAs: 47 us without, 70 us with it)
+  if (g->B * (int64_t)g->n_tiles < 8192) return;
   static_assert(sizeof(CUtensorMap) == sizeof(g->tmap), "CUtensorMap is 128 bytes");
   const char* e = getenv("PYSTL_B200_TMA");
   if (e && atoi(e) == 0) return;
