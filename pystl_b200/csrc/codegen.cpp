@@ -1022,8 +1022,11 @@ struct Gen {
     }
     o.indent--;
     o.line("}");
-    if (tma_st) o.line("store_grad_rows_tma<D, NT>(c, g, live, gr, grad_signal, smem + %d);", stage_off);
-    o.line("if (out && mean_acc) block_sum_to<NT>(c, part, mean_acc, smem + %d);", red_floats - 32);
+    if (tma_st)
+      o.line("store_grad_rows_tma<D, NT>(c, g, live, gr, grad_signal, smem + %d, part, out ? mean_acc : nullptr, smem + %d);", stage_off,
+             red_floats - 32);
+    else
+      o.line("if (out && mean_acc) block_sum_to<NT>(c, part, mean_acc, smem + %d);", red_floats - 32);
     o.indent = 0;
     o.line("}");
     return o.s;

@@ -1993,15 +1993,29 @@ PF_DEV void store_grad_rows(const TC& c, long long T, const float (&gr)[8][D], f
 // stores took 16), then one thread issues the tensor store of rows [p_lo, p_hi); the tensor is
 // [trace][row][16 floats], so a last, shorter tile is clipped at the end of its trace by the
 // hardware.  All threads call it.  stage: 1024-byte aligned, aliases the window scratch.
+// The fused mean rides along: its block reduction shares the first barrier, and its atomic is in
+// flight while the tile is staged and stored (acc == nullptr: no mean; red: NT / 32 floats).
 template <int D, int NT>
 PF_DEV void store_grad_rows_tma(const TC& c, const TileGeom& g, bool live, const float (&gr)[8][D], float* __restrict__ grad_signal,
-                                float* stage) {
+                                float* stage, float part, double* __restrict__ acc, float* red) {
   static_assert(D == 2, "64-byte rows per thread");
   if (!g.use_tma_st) {
     if (live) store_grad_rows<D>(c, g.T, gr, grad_signal);
+    if (acc) block_sum_to<NT>(c, part, acc, red);
     return;
   }
+  if (acc) {
+    float s = part;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += simt::shfl_xor(s, d);
+    if ((c.tid & 31) == 0) red[c.tid >> 5] = s;
+  }
   simt::sync();  // the last adjoint stage may still be reading the scratch this aliases
+  if (acc && c.tid == 32 % NT) {  // (not thread 0: that one issues the tensor store below)
+    double tot = 0.0;
+    for (int w = 0; w < NT / 32; ++w) tot += (double)red[w];
+    simt::atomic_add(acc, tot);
+  }
   if (live && c.p0 >= c.p_lo && c.p0 + 8 <= c.p_hi) {
     char* base = reinterpret_cast<char*>(stage) + c.tid * 64;
     const int sw = (c.tid >> 1) & 3;
