@@ -1330,6 +1330,34 @@ PF_DEV float agm2(float x0, float x1, float w0, float w1, float sw, float& d0, f
   }
 }
 
+// ------------------------------------------------------------------ D-GMSR And / Or of TWO operands
+// (_dgmsr.py:66-119 with p = 1 and unit weights, sw = 2), written out without the log domain:
+//   some u <= 0:  h = sqrt(eps) - sqrt(eps + (sum_{u<=0} u^2) / 2),       dh/du_i = |u_i| / (2 sqrt(mp))  (u_i <= 0)
+//   else:         m0 = sqrt(eps^2 + (u0 u1)^2),  h = sqrt(m0) - sqrt(eps),  dh/du_i = u0 u1 u_{1-i} / (2 m0^(3/2))
+// with u = v (And) or -v (Or, which is -And(-v), _dgmsr.py:110-119).  Three square roots and two
+// reciprocals instead of the thirteen transcendentals of the generic lift / fin / coefficient chain.
+// The caller checks p == 1, w0 == w1 == 1 and |u0 u1| < 1e18 (the product is squared in fp32).
+template <int MODE, bool PARTIALS>
+PF_DEV float dgmsr2_unit(float x0, float x1, const RP& rp, float& d0, float& d1) {
+  const float u0 = MODE == MODE_AND ? x0 : -x0, u1 = MODE == MODE_AND ? x1 : -x1;
+  const bool arith = u0 <= 0.f || u1 <= 0.f;
+  const float n0 = fminf(u0, 0.f), n1 = fminf(u1, 0.f);
+  const float smp = fast_sqrt(fmaf(fmaf(n0, n0, n1 * n1), 0.5f, rp.eps_p));
+  const float q = u0 * u1;
+  const float m0 = fast_sqrt(fmaf(q, q, rp.eps_p * rp.eps_p));
+  const float r0 = fast_sqrt(m0);
+  const float h = arith ? rp.sqrt_eps - smp : r0 - rp.sqrt_eps;
+  if constexpr (PARTIALS) {
+    // (the coefficient branch of Adj<SEM_DGMSR>::out_coeff is chosen by h <= 0, like there)
+    const bool neg = h <= 0.f;
+    const float cn = 0.5f * fast_rcp(smp);
+    const float cp = 0.5f * q * fast_rcp(m0 * r0);
+    d0 = neg ? (u0 <= 0.f ? -n0 * cn : 0.f) : (u0 > 0.f ? cp * u1 : 0.f);
+    d1 = neg ? (u1 <= 0.f ? -n1 * cn : 0.f) : (u1 > 0.f ? cp * u0 : 0.f);
+  }
+  return MODE == MODE_AND ? h : -h;
+}
+
 // ------------------------------------------------------------------ n-ary And / Or of one sample
 template <int SEM, int MODE, int N>
 PF_DEV Vec<Tr<SEM>::VW> nary1(const RP& rp0, const Vec<Tr<SEM>::VW> (&a)[N], const float (&w)[N], float sw) {
@@ -1337,6 +1365,13 @@ PF_DEV Vec<Tr<SEM>::VW> nary1(const RP& rp0, const Vec<Tr<SEM>::VW> (&a)[N], con
   if constexpr (SEM == SEM_AGM && N == 2) {
     float d0, d1;
     return Vec<1>{{agm2<MODE, false>(a[0].x[0], a[1].x[0], w[0], w[1], sw, d0, d1)}};
+  } else if constexpr (SEM == SEM_DGMSR && N == 2) {
+    if (PYSTL_P(rp0) == 1 && w[0] == 1.f && w[1] == 1.f && fabsf(a[0].x[0] * a[1].x[0]) < 1e18f) {
+      float d0, d1;
+      return Vec<1>{{dgmsr2_unit<MODE, false>(a[0].x[0], a[1].x[0], rp0, d0, d1)}};
+    }
+    typename R::A acc = R::comb(R::lift(a[0], rp0, w[0]), R::lift(a[1], rp0, w[1]));
+    return R::fin(acc, sw, rp0);
   } else if constexpr (SEM == SEM_SMOOTH && N == 2) {
     // extremum +- tau ln(1 + e^-|d|/tau): the max-shifted logsumexp of two terms (smooth.py:18-22)
     const float x0 = a[0].x[0], x1 = a[1].x[0];
@@ -1685,6 +1720,15 @@ PF_DEV Vec<1> nary1_partials(const RP& rp, const Vec<1> (&a)[N], const float (&w
   using AD = Adj<SEM, MODE>;
   if constexpr (SEM == SEM_AGM && N == 2) {
     return Vec<1>{{agm2<MODE, true>(a[0].x[0], a[1].x[0], w[0], w[1], sw, d[0], d[1])}};
+  } else if constexpr (SEM == SEM_DGMSR && N == 2) {
+    if (PYSTL_P(rp) == 1 && w[0] == 1.f && w[1] == 1.f && fabsf(a[0].x[0] * a[1].x[0]) < 1e18f)
+      return Vec<1>{{dgmsr2_unit<MODE, true>(a[0].x[0], a[1].x[0], rp, d[0], d[1])}};
+    const Vec<1> o = nary1<SEM, MODE, N>(rp, a, w, sw);
+    bool lost;
+    const Vec<AD::KW> k = AD::out_coeff(1.f, o.x[0], sw, rp, lost);
+#pragma unroll
+    for (int j = 0; j < N; ++j) d[j] = AD::in_factor(k, a[j].x[0], w[j], rp);
+    return o;
   } else if constexpr (SEM == SEM_SMOOTH && N == 2) {
     // softmax / softmin weights of two terms: 1 / (1 + 2^-|d|) for the extremal one
     const float x0 = a[0].x[0], x1 = a[1].x[0];
