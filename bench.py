@@ -61,6 +61,7 @@ WORKLOADS = {
     "cfg3": ("agm", {}, True),
     "cfg3d": ("dgmsr", {"eps": 1e-8, "p": 1}, True),
     "cfg4": ("cumulative", {}, False),
+    "cfg4b": ("cumulative", {}, True),  # ... with the gradient of mean(pos + neg)
     "cfg5": ("classical", {}, False),
     # cfg5's formula under the other four semantics ("all five semantics")
     "cfg5s": ("smooth", {"temperature": 1.0}, False),
@@ -76,6 +77,7 @@ DESCR = {
     "cfg3": "AGM G[0,100](F[0,10](x>0) & !(y>2)), 32768x8192x2, forward+backward",
     "cfg3d": "D-GMSR G[0,100](F[0,10](x>0) & !(y>2)), 32768x8192x2, forward+backward",
     "cfg4": "Cumulative G[0,200]((x>0) U[0,64] (y>1)), 16384x16384x4, forward",
+    "cfg4b": "Cumulative G[0,200]((x>0) U[0,64] (y>1)), 16384x16384x4, forward+backward",
     "cfg5": "Classic 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
     "cfg5s": "Smooth tau=1 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
     "cfg5a": "AGM 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",

@@ -800,21 +800,28 @@ struct Gen {
         const int d = in.dst;
         if (is_until(in)) {
           const bool nl = in.negmask & 1, nr = in.negmask & 2;
-          o.line("// adjoint of until %d: every candidate routes to r_i or to the prefix minimum of l", i);
-          o.line("_Pragma(\"unroll\") for (int w = 0; w < 4; ++w) plane_zero8(smem + %d + w * %d, c.tid);", sp_off, L);
+          o.line("// adjoint of until %d: the r-routes are gathered into registers, the l-routes scattered with merged runs", i);
+          o.line("plane_zero8(smem + %d, c.tid);", sp_off);
+          o.line("plane_zero8(smem + %d, c.tid);", sp_off + L);
+          o.line("stash8<2>(smem + %d, c.tid, g%d, 0);  // the cotangent of the until, for the gather (zeros past the horizon)", sp_off + 2 * L, d);
+          o.line("stash8<2>(smem + %d, c.tid, g%d, 1);", sp_off + 3 * L, d);
           o.line("simt::sync();");
+          o.line("float ra%d[8], rb%d[8];", i, i);
           o.line("if (live) {");
           o.indent++;
           for (int w = 0; w < 2; ++w)
-            o.line("cum_until_scatter<%d, %d, NT>(c, g%d, %d, U%d::lplane(smem + %d, %d), U%d::rplane(smem + %d, %d), smem + %d, smem + %d);", in.a,
-                   in.b, d, w, i, scr_off[i], w, i, scr_off[i], w, sp_off + w * L, sp_off + (2 + w) * L);
+            o.line("cum_until_gather_r<%d, %d, NT>(c, g%d, %d, U%d::lplane(smem + %d, %d), U%d::rplane(smem + %d, %d), smem + %d, %s%d);", in.a, in.b, d,
+                   w, i, scr_off[i], w, i, scr_off[i], w, sp_off + (2 + w) * L, w ? "rb" : "ra", i);
+          for (int w = 0; w < 2; ++w)
+            o.line("cum_until_scatter_l<%d, %d, NT>(c, g%d, %d, U%d::lplane(smem + %d, %d), U%d::rplane(smem + %d, %d), smem + %d);", in.a, in.b, d, w,
+                   i, scr_off[i], w, i, scr_off[i], w, sp_off + w * L);
           o.indent--;
           o.line("}");
           o.line("simt::sync();");
           o.line("if (live) {");
           o.indent++;
           o.line("cum_accumulate8<%s>(smem + %d, smem + %d, c.tid, g%d);", nl ? "true" : "false", sp_off, sp_off + L, (int)in.src[0]);
-          o.line("cum_accumulate8<%s>(smem + %d, smem + %d, c.tid, g%d);", nr ? "true" : "false", sp_off + 2 * L, sp_off + 3 * L, (int)in.src[1]);
+          o.line("cum_add_ab8<%s>(ra%d, rb%d, g%d);", nr ? "true" : "false", i, i, (int)in.src[1]);
           o.indent--;
           o.line("}");
           o.line("simt::sync();");

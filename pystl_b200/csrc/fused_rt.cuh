@@ -1925,6 +1925,15 @@ PF_DEV void cum_accumulate8(const float* plane_pos, const float* plane_neg, int 
     gs[i].x[1] += NEG ? -a[i] : b[i];
   }
 }
+// the same from registers (the gathered r-routes of the Until adjoint): a = pos channel, b = neg channel
+template <bool NEG>
+PF_DEV void cum_add_ab8(const float (&a)[8], const float (&b)[8], Vec<2> (&gs)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    gs[i].x[0] += NEG ? -b[i] : a[i];
+    gs[i].x[1] += NEG ? -a[i] : b[i];
+  }
+}
 template <bool NEG>
 PF_DEV void cum_add8(const Vec<2> (&w)[8], Vec<2> (&gs)[8]) {
 #pragma unroll
@@ -1974,8 +1983,157 @@ PF_DEV float cum_pred_adj(Vec<2> v, Vec<2> g) {
 // Until: U = sum_{i in [UA, last]} min(r_i, min_{k<=i} l_k) per channel (cumulative.py:96-103).
 // Each candidate routes the cotangent to r_i or to the first prefix minimum of l (ties between
 // the two split, torch.minimum).  lpl / rpl: staged operands; gl / gr: zeroed scatter planes.
+// ---- adjoint of the cumulative Until, U_t = sum_{i in [UA, UB]} min(r_{t+i}, P_t(t+i)), P_t(q) = min l[t..q]
+// (cumulative.py:96-103; torch.minimum routes the cotangent of a candidate to r_q when r_q < P, to the
+// first prefix minimum of l when P < r_q, and splits it on a tie).
+//
+// r-routes as a GATHER: grad_r[q] = sum_{t in [q - UB, q - UA]} g_t [r_q < P_t(q)] lands in the
+// registers of the thread that owns q -- no atomics.  For an output t before the thread's chunk,
+// P_t(q) = min(Mb_t, hf_q): Mb_t = min l[t .. p0 - 1] is one running minimum of the backward walk,
+// hf_q = min l[p0 .. q] a prefix minimum of the own chunk.  gpl: the cotangent plane (store8 layout,
+// zero where no output exists).
+PF_DEV float cum_route_r(float r, float P, float g) { return r < P ? g : (r == P ? 0.5f * g : 0.f); }
 template <int UA, int UB, int NT>
-PF_DEV void cum_until_scatter(const TC& c, const Vec<2> (&g)[8], int w, const float* lpl, const float* rpl, float* gl, float* gr) {
+PF_DEV void cum_until_gather_r(const TC& c, const Vec<2> (&g)[8], int w, const float* lpl, const float* rpl, const float* gpl,
+                               float (&racc)[8]) {
+  const int f0 = c.p0 >> 2;
+  const F4* L4 = reinterpret_cast<const F4*>(lpl);
+  const F4* R4 = reinterpret_cast<const F4*>(rpl);
+  const F4* G4 = reinterpret_cast<const F4*>(gpl);
+  const F4 la = L4[pf4(f0)], lb = L4[pf4(f0 + 1)], ra = R4[pf4(f0)], rb = R4[pf4(f0 + 1)];
+  const float lo[8] = {la.v[0], la.v[1], la.v[2], la.v[3], lb.v[0], lb.v[1], lb.v[2], lb.v[3]};
+  const float ro[8] = {ra.v[0], ra.v[1], ra.v[2], ra.v[3], rb.v[0], rb.v[1], rb.v[2], rb.v[3]};
+  float hf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    racc[j] = 0.f;
+    hf[j] = j ? fminf(hf[j - 1], lo[j]) : lo[0];
+  }
+  // outputs of the own chunk
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float pm = f_inf();
+#pragma unroll
+    for (int q = i; q < 8; ++q) {
+      pm = fminf(pm, lo[q]);
+      if (q - i >= UA && q - i <= UB) racc[q] += cum_route_r(ro[q], pm, g[i].x[w]);
+    }
+  }
+  // outputs before it: t = p0 - m, m = 1 .. UB; position q = p0 + j is candidate m + j of output t
+  float Mb = f_inf();
+  constexpr int G0 = UA > 0 ? (UA - 1 + 3) / 4 : 0;            // first group whose every (m, j) has m + j >= UA ... m >= UA
+  constexpr int G1 = UB >= 11 ? (UB - 11) / 4 + 1 : 0;         // groups below G1 have m + 7 <= UB
+  constexpr int GB0 = G0 < G1 ? G0 : G1, GB1 = G1;             // body [GB0, GB1)
+  constexpr int GN = (UB + 3) / 4;                             // groups holding m <= UB
+  auto group = [&](int gg, auto all) {
+    const int fb = f0 - 1 - gg;
+    const bool ok = fb >= 0;  // (outputs before the tile do not exist for this CTA)
+    const F4 ql = L4[pf4(ok ? fb : 0)];
+    F4 qg = G4[pf4(ok ? fb : 0)];
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+      const int m = 4 * gg + (4 - k);
+      const float gt = ok ? qg.v[k] : 0.f;
+      Mb = fminf(Mb, ql.v[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (decltype(all)::value || (m + j >= UA && m + j <= UB)) racc[j] += cum_route_r(ro[j], fminf(Mb, hf[j]), gt);
+    }
+  };
+#pragma unroll
+  for (int gg = 0; gg < GB0; ++gg) group(gg, BoolC<false>{});
+#pragma unroll 1
+  for (int gg = GB0; gg < GB1; ++gg) group(gg, BoolC<true>{});
+#pragma unroll
+  for (int gg = GB1 > GB0 ? GB1 : GB0; gg < GN; ++gg) group(gg, BoolC<false>{});
+}
+// l-routes as a SCATTER with the runs merged, the adjoint of UntilOp::phase2_cum: the 8 outputs of a
+// thread walk their candidates together.  Past the own chunk the prefix minimum of output i at
+// position q is min(h_i, M_q) (h_i is the earlier one: it wins ties); the cotangent routed to a
+// prefix minimum stays in a register while that minimum stands: one shared-memory atomic per record
+// low of M and one per output for its own-chunk minimum, instead of one per candidate.
+template <int UA, int UB, int NT>
+PF_DEV void cum_until_scatter_l_fast(const TC& c, const Vec<2> (&g)[8], int w, const float* lpl, const float* rpl, float* gl) {
+  constexpr int LEXT = 8 * NT, FMAX = LEXT / 4 - 1;
+  const int p0 = c.p0, f0 = p0 >> 2;
+  const F4* L4 = reinterpret_cast<const F4*>(lpl);
+  const F4* R4 = reinterpret_cast<const F4*>(rpl);
+  float gi[8], h[8], hacc[8];
+  int harg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gi[i] = g[i].x[w];
+  {  // own chunk: triangular
+    const F4 la = L4[pf4(f0)], lb = L4[pf4(f0 + 1)], ra = R4[pf4(f0)], rb = R4[pf4(f0 + 1)];
+    const float lo[8] = {la.v[0], la.v[1], la.v[2], la.v[3], lb.v[0], lb.v[1], lb.v[2], lb.v[3]};
+    const float ro[8] = {ra.v[0], ra.v[1], ra.v[2], ra.v[3], rb.v[0], rb.v[1], rb.v[2], rb.v[3]};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float pm = f_inf(), run = 0.f;
+      int arg = p0 + i;
+#pragma unroll
+      for (int q = i; q < 8; ++q) {
+        if (lo[q] < pm) {  // a new prefix minimum (first index wins ties): settle the old one
+          if (run != 0.f) simt::atomic_add(&gl[pidx(arg)], run);
+          run = 0.f;
+          pm = lo[q];
+          arg = p0 + q;
+        }
+        if (q - i >= UA && q - i <= UB) run += gi[i] - cum_route_r(ro[q], pm, gi[i]);
+      }
+      h[i] = pm;
+      harg[i] = arg;
+      hacc[i] = run;
+    }
+  }
+  float M = f_inf(), accM = 0.f;
+  int argM = p0 + 8;
+  constexpr int KS0 = UA + 7 > 8 ? UA + 7 : 8;
+  constexpr int KS = (KS0 + 3) & ~3;
+  constexpr int KE = ((UB + 1) & ~3) > KS ? ((UB + 1) & ~3) : KS;  // body [KS, KE): every output takes every position
+  auto group = [&](int gq, auto all) {
+    const int fc = (f0 + gq) < FMAX ? (f0 + gq) : FMAX;
+    const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int kq = 4 * gq + k;
+      const float l = ql.v[k], r = qr.v[k];
+      if (l < M) {
+        if (accM != 0.f) simt::atomic_add(&gl[pidx(argM)], accM);
+        accM = 0.f;
+        M = l;
+        argM = p0 + kq;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (decltype(all)::value || (kq - i >= UA && kq - i <= UB)) {
+          const bool own = h[i] <= M;
+          const float tl = gi[i] - cum_route_r(r, own ? h[i] : M, gi[i]);
+          hacc[i] += own ? tl : 0.f;
+          accM += own ? 0.f : tl;
+        }
+    }
+  };
+#pragma unroll
+  for (int gq = 2; gq < KS / 4; ++gq) group(gq, BoolC<false>{});
+#pragma unroll 1
+  for (int gq = KS / 4; gq < KE / 4; ++gq) group(gq, BoolC<true>{});
+#pragma unroll
+  for (int gq = KE / 4; gq <= (UB + 7) / 4; ++gq) group(gq, BoolC<false>{});
+  if (accM != 0.f) simt::atomic_add(&gl[pidx(argM)], accM);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (hacc[i] != 0.f) simt::atomic_add(&gl[pidx(harg[i])], hacc[i]);
+}
+// the l-routes of one channel: fast path when every window of the thread is complete (or on an
+// interior tile, where the outputs whose windows leave it have a zero cotangent), else output by output
+template <int UA, int UB, int NT>
+PF_DEV void cum_until_scatter_l(const TC& c, const Vec<2> (&g)[8], int w, const float* lpl, const float* rpl, float* gl) {
+  if constexpr (UA <= 64) {
+    if (c.p0 + 7 + UB <= c.nlive - 1 || c.nlive == 8 * NT) {
+      cum_until_scatter_l_fast<UA, UB, NT>(c, g, w, lpl, rpl, gl);
+      return;
+    }
+  }
 #pragma unroll 1
   for (int i = 0; i < 8; ++i) {
     float gi = 0.f;
@@ -1986,25 +2144,20 @@ PF_DEV void cum_until_scatter(const TC& c, const Vec<2> (&g)[8], int w, const fl
     const int p = c.p0 + i;
     int last = c.nlive - 1 - p;
     if (last > UB) last = UB;
-    float pm = f_inf();
+    float pm = f_inf(), run = 0.f;
     int arg = p;
     for (int kk = 0; kk <= last; ++kk) {
       const int q = pidx(p + kk);
       const float l = lpl[q];
       if (l < pm) {
+        if (run != 0.f) simt::atomic_add(&gl[arg], run);
+        run = 0.f;
         pm = l;
         arg = q;
       }
-      if (kk >= UA) {
-        const float r = rpl[q];
-        if (r < pm) simt::atomic_add(&gr[q], gi);
-        else if (pm < r) simt::atomic_add(&gl[arg], gi);
-        else {
-          simt::atomic_add(&gr[q], 0.5f * gi);
-          simt::atomic_add(&gl[arg], 0.5f * gi);
-        }
-      }
+      if (kk >= UA) run += gi - cum_route_r(rpl[q], pm, gi);
     }
+    if (run != 0.f) simt::atomic_add(&gl[arg], run);
   }
 }
 
