@@ -68,6 +68,10 @@ WORKLOADS = {
     "cfg5a": ("agm", {}, False),
     "cfg5d": ("dgmsr", {"eps": 1e-8, "p": 1}, False),
     "cfg5c": ("cumulative", {}, False),
+    # ... and with the gradient (value-and-gradient kernels; the Until adjoints are O(b) scatters)
+    "cfg5b": ("classical", {}, True),
+    "cfg5sb": ("smooth", {"temperature": 1.0}, True),
+    "cfg5ab": ("agm", {}, True),
 }
 DESCR = {
     "cfg1": "Classic G[0,10](x>0) & F[0,5](y<1), 1024x1000x2, forward",
@@ -83,6 +87,9 @@ DESCR = {
     "cfg5a": "AGM 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
     "cfg5d": "D-GMSR 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
     "cfg5c": "Cumulative 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward",
+    "cfg5b": "Classic 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward+backward",
+    "cfg5sb": "Smooth tau=1 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward+backward",
+    "cfg5ab": "AGM 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward+backward",
 }
 
 
