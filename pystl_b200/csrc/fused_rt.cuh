@@ -110,6 +110,7 @@ struct TC {
   int last_ok;  // last tile position whose output does not raise (api.py:218-221); < 0: none
   int p_lo;     // tile positions [p_lo, p_hi) are the ones this CTA writes to HBM
   int p_hi;
+  bool interior;  // the trace goes on past this tile: windows that leave the tile belong to halo outputs nobody consumes
   long long b;       // trace
   long long origin;  // trace time of tile position 0
   RP rp;
@@ -128,6 +129,7 @@ PF_DEV TC tile_begin(const TileProgram& P, const TileGeom& g, float* smem) {
   c.origin = origin;
   const long long live = g.T - origin;
   c.nlive = live < (long long)(8 * NT) ? (int)live : 8 * NT;
+  c.interior = live > (long long)(8 * NT);
   const long long ok = P.raises_always ? -1 : g.T - 1 - P.start_slack - origin;
   c.last_ok = ok > (long long)(1 << 30) ? (1 << 30) : (ok < -1 ? -1 : (int)ok);
   c.p_lo = e0 - origin;
@@ -689,12 +691,16 @@ struct UntilOp {
   // so the candidate of output i at q is min(G_q, h_i) with G_q = min(r_q, M_q): two mins per
   // position for the thread, one min + one add per (position, output), operands read once per
   // thread (128-bit runs) instead of a guarded state update per (position, output).
-  // Valid when every window of the thread is complete, or on an interior tile (nlive == LEXT),
-  // where the outputs whose windows leave the tile are never consumed (loads are clamped).
-  PF_DEV static bool cum_fast_ok(const TC& c) { return c.p0 + 7 + UB <= c.nlive - 1 || c.nlive == LEXT; }
+  // On an interior tile (the trace goes on past it) the outputs whose windows leave the tile are never
+  // consumed and the loads are simply clamped.  On the last tile of a trace the windows are clipped at
+  // the horizon (api.py:49-54): positions past kmax = nlive - 1 - p0 are skipped, outputs without a
+  // candidate are NaN (the reference raises).
+  PF_DEV static int clip_kmax(const TC& c) { return c.interior ? 0x3fffffff : c.nlive - 1 - c.p0; }
+  PF_DEV static bool cum_fast_ok(const TC&) { return true; }
   PF_DEV static void phase2_cum(float* scr, const TC& c, V (&o)[8]) {
     static_assert(UA >= 0 && UB >= UA, "bounded until");
     const int f0 = c.p0 >> 2;
+    const int kmax = clip_kmax(c);
     constexpr int FMAX = LEXT / 4 - 1;
     constexpr int KS0 = UA + 7 > 8 ? UA + 7 : 8;       // first offset at which every output has a candidate
     constexpr int KS = (KS0 + 3) & ~3;                 // ... rounded up to a 128-bit group
@@ -714,7 +720,7 @@ struct UntilOp {
 #pragma unroll
           for (int q = i; q < 8; ++q) {
             pm = fminf(pm, lo[q]);
-            if (q - i >= UA && q - i <= UB) a += fminf(ro[q], pm);
+            if (q - i >= UA && q - i <= UB && q <= kmax) a += fminf(ro[q], pm);
           }
           acc[i] = a;
           h[i] = pm;
@@ -723,7 +729,7 @@ struct UntilOp {
       float M = f_inf();
       // one position at offset kq (compile-time) from p0: value pair (l, r)
 #define PF_CUM_STEP(KQ, LV, RV)                                            \
-  {                                                                        \
+  if ((KQ) <= kmax) {                                                      \
     M = fminf(M, (LV));                                                    \
     const float G = fminf((RV), M);                                        \
     _Pragma("unroll") for (int i = 0; i < 8; ++i) {                        \
@@ -745,6 +751,7 @@ struct UntilOp {
         const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+          if (4 * g + k > kmax) break;
           M = fminf(M, ql.v[k]);
           const float G = fminf(qr.v[k], M);
 #pragma unroll
@@ -761,7 +768,7 @@ struct UntilOp {
       }
 #undef PF_CUM_STEP
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i].x[w] = acc[i];
+      for (int i = 0; i < 8; ++i) o[i].x[w] = (kmax - i < UA) ? f_nan() : acc[i];
     }
   }
 
@@ -778,6 +785,7 @@ struct UntilOp {
     const F4* L4 = reinterpret_cast<const F4*>(lplane(scr, 0));
     const F4* R4 = reinterpret_cast<const F4*>(rplane(scr, 0));
     const float nk = -rp.k, ns = -rp.shift;
+    const int kmax = clip_kmax(c);
     float acc[8], h[8];
     {
       const F4 la = L4[pf4(f0)], lb = L4[pf4(f0 + 1)], ra = R4[pf4(f0)], rb = R4[pf4(f0 + 1)];
@@ -794,7 +802,7 @@ struct UntilOp {
 #pragma unroll
         for (int q = i; q < 8; ++q) {
           S += lo[q];
-          if (q - i >= UA && q - i <= UB) a += fast_rcp(S + ro[q]);
+          if (q - i >= UA && q - i <= UB && q <= kmax) a += fast_rcp(S + ro[q]);
         }
         acc[i] = a;
         h[i] = S;
@@ -802,7 +810,7 @@ struct UntilOp {
     }
     float M = 0.f;
 #define PF_SM_STEP(KQ, LV, RV)                                                   \
-  {                                                                              \
+  if ((KQ) <= kmax) {                                                            \
     M += fast_ex2(fmaf((LV), nk, ns));                                           \
     const float G = M + fast_ex2(fmaf((RV), nk, ns));                            \
     _Pragma("unroll") for (int i = 0; i < 8; ++i) {                              \
@@ -822,6 +830,7 @@ struct UntilOp {
       const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
+        if (4 * g + k > kmax) break;
         M += fast_ex2(fmaf(ql.v[k], nk, ns));
         const float G = M + fast_ex2(fmaf(qr.v[k], nk, ns));
 #pragma unroll
@@ -841,6 +850,7 @@ struct UntilOp {
       st[i].S = 0.f;
       st[i].acc = acc[i];  // (smooth_fix looks at it)
       o[i] = st[i].done(UB - UA + 1, rp);
+      if (kmax - i < UA) o[i].x[0] = f_nan();
     }
   }
 
@@ -857,6 +867,7 @@ struct UntilOp {
     const F4* L4 = reinterpret_cast<const F4*>(lplane(scr, 0));
     const F4* R4 = reinterpret_cast<const F4*>(rplane(scr, 0));
     const float invsw = fast_rcp(w0 + w1);
+    const int kmax = clip_kmax(c);
     float hneg[8], hlog[8], o0[8], o1[8];
     // one candidate of output i: prefix accumulator (pneg, plog) over k samples, right operand r
     auto cand = [&](int i, float pneg, float plog, float kf, float rnegw, float rlogw, bool rpos) {
@@ -890,7 +901,7 @@ struct UntilOp {
         for (int q = i; q < 8; ++q) {
           pn += ln[q];
           pl += ll[q];
-          if (q - i >= UA && q - i <= UB) cand(i, pn, pl, (float)(q - i + 1), rn[q], rl[q], ro[q] > 0.f);
+          if (q - i >= UA && q - i <= UB && q <= kmax) cand(i, pn, pl, (float)(q - i + 1), rn[q], rl[q], ro[q] > 0.f);
         }
         hneg[i] = pn;
         hlog[i] = pl;
@@ -907,6 +918,7 @@ struct UntilOp {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int kq = 4 * g + k;
+        if (kq > kmax) break;
         const float l = ql.v[k], r = qr.v[k];
         Mn += fminf(l, 0.f);
         Ml += l <= 0.f ? f_inf() : fast_lg2(1.f + l);
@@ -924,9 +936,12 @@ struct UntilOp {
     for (int g = KS / 4; g < KE / 4; ++g) group(g, BoolC<true>{});
 #pragma unroll
     for (int g = KE / 4; g <= (UB + 7) / 4; ++g) group(g, BoolC<false>{});
-    const float invn = fast_rcp((float)(UB - UA + 1));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i].x[0] = (o1[i] == f_inf()) ? o0[i] * invn : 1.f - fast_ex2(o1[i] * invn);
+    for (int i = 0; i < 8; ++i) {
+      const int last = kmax - i < UB ? kmax - i : UB;  // clipped candidate count (agm.py:25-26)
+      const float invn = fast_rcp((float)(last - UA + 1));
+      o[i].x[0] = last < UA ? f_nan() : ((o1[i] == f_inf()) ? o0[i] * invn : 1.f - fast_ex2(o1[i] * invn));
+    }
   }
 
   PF_DEV static void phase2(float* scr, const TC& c, const RP& rp, float w0, float w1, V (&o)[8], UntilState<SEM> (&st)[8]) {
@@ -2056,6 +2071,7 @@ template <int UA, int UB, int NT>
 PF_DEV void cum_until_scatter_l_fast(const TC& c, const Vec<2> (&g)[8], int w, const float* lpl, const float* rpl, float* gl) {
   constexpr int LEXT = 8 * NT, FMAX = LEXT / 4 - 1;
   const int p0 = c.p0, f0 = p0 >> 2;
+  const int kmax = c.interior ? 0x3fffffff : c.nlive - 1 - p0;  // windows are clipped at the horizon on the last tile
   const F4* L4 = reinterpret_cast<const F4*>(lpl);
   const F4* R4 = reinterpret_cast<const F4*>(rpl);
   float gi[8], h[8], hacc[8];
@@ -2072,6 +2088,7 @@ PF_DEV void cum_until_scatter_l_fast(const TC& c, const Vec<2> (&g)[8], int w, c
       int arg = p0 + i;
 #pragma unroll
       for (int q = i; q < 8; ++q) {
+        if (q > kmax) break;
         if (lo[q] < pm) {  // a new prefix minimum (first index wins ties): settle the old one
           if (run != 0.f) simt::atomic_add(&gl[pidx(arg)], run);
           run = 0.f;
@@ -2096,6 +2113,7 @@ PF_DEV void cum_until_scatter_l_fast(const TC& c, const Vec<2> (&g)[8], int w, c
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int kq = 4 * gq + k;
+      if (kq > kmax) break;
       const float l = ql.v[k], r = qr.v[k];
       if (l < M) {
         if (accM != 0.f) simt::atomic_add(&gl[pidx(argM)], accM);
@@ -2129,10 +2147,8 @@ PF_DEV void cum_until_scatter_l_fast(const TC& c, const Vec<2> (&g)[8], int w, c
 template <int UA, int UB, int NT>
 PF_DEV void cum_until_scatter_l(const TC& c, const Vec<2> (&g)[8], int w, const float* lpl, const float* rpl, float* gl) {
   if constexpr (UA <= 64) {
-    if (c.p0 + 7 + UB <= c.nlive - 1 || c.nlive == 8 * NT) {
-      cum_until_scatter_l_fast<UA, UB, NT>(c, g, w, lpl, rpl, gl);
-      return;
-    }
+    cum_until_scatter_l_fast<UA, UB, NT>(c, g, w, lpl, rpl, gl);
+    return;
   }
 #pragma unroll 1
   for (int i = 0; i < 8; ++i) {

@@ -89,6 +89,14 @@ def forward_cases(light: bool = False):
         for threads in ((32,) if light else (0, 32)):
             out.append(dict(name=f"weights/{sem}{kw.get('p', '')}/nt{threads}", spec=wspec, sem=sem, kw=kw, B=3, T=300, D=2, threads=threads,
                             seed=41, scale=2.0))
+    # a tile that ends EXACTLY at the end of the trace (T = 8 * threads, and T = n * tile + 8 * threads):
+    # its last outputs have clipped windows, it is not an "interior" tile for the shared-tail Until paths
+    for sem, kw in SEM_KW:
+        for T, threads in ((512, 64), (256, 32)) if light else ((512, 64), (256, 32), (2048, 256), (512 + 488, 64)):
+            out.append(dict(name=f"tile_end/T{T}/{sem}{kw.get('p', '')}/nt{threads}", spec=BASELINE_SPECS["cfg5"], sem=sem, kw=kw, B=2, T=T, D=8,
+                            threads=threads, seed=53, scale=30.0 if sem == "dgmsr" else 2.0))
+            # (D-GMSR is steep around 0 -- SURVEY.md appendix A10: relative errors up to 6e-5 for |rho| < 1e-3 --
+            # and this 10-node formula composes it four levels deep; a tiling or clipping error would be O(1))
     for T in (999, 1001, 1002):
         for sem, kw in (SEM_KW[0], SEM_KW[1]):
             for threads in ((32,) if light else (32, 128, 256)):
@@ -168,6 +176,9 @@ def cumulative_backward_cases(light: bool = False):
         for threads in ((64,) if light else (0, 64)):
             out.append(dict(name=f"bwd/{name}/cumulative/nt{threads}", spec=spec, sem="cumulative", kw={}, B=2, T=400,
                             D={"cfg4": 4, "cfg5": 8}.get(name, 2), threads=threads, seed=23))
+    # the trace ends exactly where a tile ends (see forward_cases: tile_end)
+    out.append(dict(name="bwd/U/cumulative/tile_end", spec=specs["U"], sem="cumulative", kw={}, B=2, T=512, D=2, threads=64, seed=27))
+    out.append(dict(name="bwd/cfg5/cumulative/tile_end", spec=specs["cfg5"], sem="cumulative", kw={}, B=2, T=512, D=8, threads=64, seed=27))
     return out
 
 
