@@ -130,17 +130,18 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 static void fused_tma_setup(TileGeom* g, const float* signal, int sem) {
   g->use_tma = 0;
+  const char* e = getenv("PYSTL_B200_TMA");  // 0: off, 2: on wherever the shape qualifies (tests)
+  if (e && atoi(e) == 0) return;
+  const bool force = e && atoi(e) == 2;
   // (measured: +17 % on cfg1x, +5 % on cfg2 forward; the agm / dgmsr kernels are latency bound and
   // do not gain from it: 2.93 vs 2.95 ms on cfg3)
-  if (sem == SEM_AGM || sem == SEM_DGMSR) return;
+  if (!force && (sem == SEM_AGM || sem == SEM_DGMSR)) return;
   // (value-and-gradient kernels other than the classic one: 1.646 ms without, 1.671 ms with it on cfg2)
-  if (g->bwd && sem != SEM_CLASSIC) return;
+  if (!force && g->bwd && sem != SEM_CLASSIC) return;
   // a launch of a few waves is latency bound: the barrier + TMA round trip at the head of every CTA
   // costs more than the wavefronts it saves (cfg1, 1024 CTAs: 47 us without, 70 us with it)
-  if (g->B * (int64_t)g->n_tiles < 8192) return;
+  if (!force && g->B * (int64_t)g->n_tiles < 8192) return;
   static_assert(sizeof(CUtensorMap) == sizeof(g->tmap), "CUtensorMap is 128 bytes");
-  const char* e = getenv("PYSTL_B200_TMA");
-  if (e && atoi(e) == 0) return;
   if (g->D != 2 && g->D != 4 && g->D != 8) return;
   const int rowb = g->D == 2 ? 64 : 128;                 // bytes per tensor row (fused_rt.cuh: load_rows_tma)
   const int trows = g->nt * (32 * g->D / rowb);          // rows of one tile

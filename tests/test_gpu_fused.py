@@ -277,3 +277,32 @@ def test_classic_value_and_grad_full_size_routing_is_one_hot():
     tot = grad.double().abs().sum().item() * (4096 * 1000)
     assert abs(tot - 4096 * 1000) < 1e-3 * 4096 * 1000
     assert (grad[..., 0] >= 0).all() and (grad[..., 1] <= 0).all()
+
+
+# ---------------------------------------------------------------------------- TMA tile load on the parity corpus
+# The launches of this corpus are a handful of CTAs, below the size at which the library switches the
+# TMA tile load on by itself; PYSTL_B200_TMA=2 forces it wherever the shape qualifies (2 / 4 / 8
+# channels, rows on 64- / 128-byte boundaries), for every semantics and for the value-and-gradient kernels.
+from parity_util import SEM_KW  # noqa: E402
+
+TMA_FWD, TMA_BWD = [], []
+for _cfg, _D, _T in (("cfg1", 2, 528), ("cfg2", 2, 1040), ("cfg3", 2, 528), ("cfg4", 4, 1024), ("cfg5", 8, 512)):
+    for _sem, _kw in SEM_KW:
+        for _nt in (64, 0):
+            _c = dict(name=f"tma/{_cfg}/{_sem}{_kw.get('p', '')}/T{_T}/nt{_nt}", spec=BASELINE_SPECS[_cfg], sem=_sem, kw=_kw, B=3, T=_T, D=_D,
+                      threads=_nt, seed=61, scale=30.0 if _sem == "dgmsr" else 4.0)
+            TMA_FWD.append(_c)
+            if _cfg in ("cfg1", "cfg2", "cfg3") and _sem != "cumulative":
+                TMA_BWD.append(_c)
+
+
+@pytest.mark.parametrize("case", TMA_FWD, ids=[c["name"] for c in TMA_FWD])
+def test_forward_with_tma_forced(case, monkeypatch):
+    monkeypatch.setenv("PYSTL_B200_TMA", "2")
+    test_forward(case)
+
+
+@pytest.mark.parametrize("case", TMA_BWD, ids=[c["name"] for c in TMA_BWD])
+def test_backward_with_tma_forced(case, monkeypatch):
+    monkeypatch.setenv("PYSTL_B200_TMA", "2")
+    test_backward(case)
