@@ -85,22 +85,54 @@ PYSTL_HD float i2f(int i) {
 #endif
 }
 
+// Host builds only (tests/emu): PYSTL_EMU_MUFU=<mask> perturbs the libm results by the documented
+// error bounds of the hardware approximations (1: ex2 2^-22 relative, 2: lg2 2^-22 absolute inside
+// (0.5, 2) and relative outside, 4: rcp 2^-23, 8: sqrt 2^-23, 16: flush denormals), with a sign and
+// size derived from the argument's bits, so that the CPU tier can measure how sensitive a formula
+// is to them (tests/error_table.py --backend emu).
+#if !defined(__CUDA_ARCH__) && defined(PYSTL_EMU_MUFU)
+inline float emu_unit(float x) {  // deterministic pseudo-random number in [-1, 1] from the bits of x
+  unsigned u;
+  memcpy(&u, &x, 4);
+  u = (u ^ 0x9e3779b9u) * 0x85ebca6bu;
+  u ^= u >> 13;
+  u *= 0xc2b2ae35u;
+  u ^= u >> 16;
+  return (float)((double)u / 2147483648.0 - 1.0);
+}
+inline float emu_ftz(float x) { return ((PYSTL_EMU_MUFU & 16) && fabsf(x) < 1.17549435e-38f) ? 0.f * x : x; }
+#define PYSTL_EMU_REL(bit, y, x, mag) (((PYSTL_EMU_MUFU) & (bit)) ? (y) * (1.f + (mag) * emu_unit(x)) : (y))
+#else
+#define PYSTL_EMU_REL(bit, y, x, mag) (y)
+inline float emu_ftz(float x) { return x; }
+#endif
+
+// Device builds: PYSTL_PRECISE_MATH=<mask> (an NVRTC flag, experiments only) swaps an approximation
+// for the correctly rounded / 1-2 ulp library function (1: ex2, 2: lg2, 4: rcp, 8: sqrt).
+#if !defined(PYSTL_PRECISE_MATH)
+#define PYSTL_PRECISE_MATH 0
+#endif
 PYSTL_HD float fast_ex2(float x) {
 #if defined(__CUDA_ARCH__)
+  if (PYSTL_PRECISE_MATH & 1) return exp2f(x);
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 #else
-  return exp2f(x);
+  return emu_ftz(PYSTL_EMU_REL(1, exp2f(emu_ftz(x)), x, 2.3841858e-7f));
 #endif
 }
 PYSTL_HD float fast_lg2(float x) {
 #if defined(__CUDA_ARCH__)
+  if (PYSTL_PRECISE_MATH & 2) return log2f(x);
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 #else
-  return log2f(x);
+#if defined(PYSTL_EMU_MUFU)
+  if ((PYSTL_EMU_MUFU & 2) && x > 0.5f && x < 2.f) return log2f(x) + 2.3841858e-7f * emu_unit(x);
+#endif
+  return PYSTL_EMU_REL(2, log2f(emu_ftz(x)), x, 2.3841858e-7f);
 #endif
 }
 
@@ -109,20 +141,22 @@ PYSTL_HD float fast_lg2(float x) {
 // error of lg2.approx is below 2^-22 and window means do not amplify it.
 PYSTL_HD float fast_rcp(float x) {
 #if defined(__CUDA_ARCH__)
+  if (PYSTL_PRECISE_MATH & 4) return __frcp_rn(x);
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 #else
-  return 1.f / x;
+  return emu_ftz(PYSTL_EMU_REL(4, 1.f / emu_ftz(x), x, 1.1920929e-7f));
 #endif
 }
 PYSTL_HD float fast_sqrt(float x) {
 #if defined(__CUDA_ARCH__)
+  if (PYSTL_PRECISE_MATH & 8) return __fsqrt_rn(x);
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 #else
-  return sqrtf(x);
+  return PYSTL_EMU_REL(8, sqrtf(emu_ftz(x)), x, 1.1920929e-7f);
 #endif
 }
 constexpr float kLn2 = 0.69314718055994531f;

@@ -75,7 +75,8 @@ def kernel(source: str, backward: bool):
     hdr = hashlib.sha1()
     for h in _HDRS:
         hdr.update(open(h, "rb").read())
-    key = hashlib.sha1((source + hdr.hexdigest() + str(backward)).encode()).hexdigest()[:20]
+    mufu = os.environ.get("PYSTL_EMU_MUFU", "")  # perturb the transcendentals like the hardware approximations (tile_eval.h)
+    key = hashlib.sha1((source + hdr.hexdigest() + str(backward) + mufu).encode()).hexdigest()[:20]
     if key in _kernels:
         return _kernels[key]
     os.makedirs(OUT, exist_ok=True)
@@ -91,6 +92,8 @@ def kernel(source: str, backward: bool):
         cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", CSRC, "-I", EMU, f"-DPF_EMU_KERNEL={name}"]
         if backward:
             cmd.append("-DPF_EMU_BACKWARD")
+        if mufu:
+            cmd.append(f"-DPYSTL_EMU_MUFU={int(mufu)}")
         tmp = so + f".{os.getpid()}.tmp"
         subprocess.run(cmd + [cu, "-o", tmp], check=True)
         os.replace(tmp, so)
