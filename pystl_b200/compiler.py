@@ -34,9 +34,26 @@ _SEM_IDS = {
 }
 
 
-def affine_of(pred: Any, n_channels: int) -> Tuple[Tuple[Tuple[int, float], ...], float]:
-    """``((channel, coeff), ...), bias`` of a predicate, or NotImplementedError."""
+def wants_leaf(pred: Any) -> bool:
+    """A predicate can opt out of the affine fast path: ``metadata={"affine": None}`` or
+    ``metadata={"leaf": True}`` routes it to a leaf channel whatever its ``fn`` looks like."""
     meta = getattr(pred, "metadata", None) or {}
+    return bool(meta.get("leaf")) or ("affine" in meta and meta["affine"] is None)
+
+
+_PROBE_ROWS = 24
+
+
+def affine_of(pred: Any, n_channels: int) -> Tuple[Tuple[Tuple[int, float], ...], float]:
+    """``((channel, coeff), ...), bias`` of a predicate, or NotImplementedError.
+
+    Without ``metadata["affine"]`` the callable is PROBED: a fast reject only.  A predicate that
+    passes is checked again against ``fn`` on the first real signal of every new shape
+    (``verify_probed``) and demoted to a leaf channel when it disagrees there -- e.g. a function of
+    ``t`` beyond the probe's rows, or one that is only affine close to the origin."""
+    meta = getattr(pred, "metadata", None) or {}
+    if wants_leaf(pred):
+        raise NotImplementedError(f"Predicate '{pred.name}' asks for the leaf path")
     if "affine" in meta:
         terms, bias = meta["affine"]
         if isinstance(terms, dict):
@@ -46,26 +63,27 @@ def affine_of(pred: Any, n_channels: int) -> Tuple[Tuple[Tuple[int, float], ...]
     if fn is None:  # classic.py:16-19
         raise ValueError(f"Predicate '{pred.name}' does not define `fn(signal, t)`.")
     D = int(n_channels)
+    R = _PROBE_ROWS
 
     def call(sig: np.ndarray, t: int) -> float:
         return float(fn(sig, t))
 
     try:
-        zero = np.zeros((3, D))
+        zero = np.zeros((R, D))
         bias = call(zero, 1)
         coeffs = np.zeros(D)
         for d in range(D):
-            probe = np.zeros((3, D))
+            probe = np.zeros((R, D))
             probe[1, d] = 1.0
             coeffs[d] = call(probe, 1) - bias
         rng = np.random.default_rng(12345)
         ok = True
-        for _ in range(4):
-            sig = rng.normal(size=(3, D)) * 3.0
-            for t in (0, 1, 2):
+        for scale in (3.0, 1e3, 1e-3, 50.0):  # a function that is affine near the origin only fails the wide rows
+            sig = rng.normal(size=(R, D)) * scale
+            for t in (0, 1, 2, 3, 7, R // 2, R - 2, R - 1):
                 want = bias + float(coeffs @ sig[t])
                 got = call(sig, t)
-                if not np.isfinite(got) or abs(got - want) > 1e-9 * (1.0 + abs(want)):
+                if not np.isfinite(got) or abs(got - want) > 1e-9 * (abs(bias) + float(np.abs(coeffs) @ np.abs(sig[t])) + 1e-300):
                     ok = False
     except Exception as exc:  # the callable needs something the probe cannot give it
         raise NotImplementedError(
@@ -79,6 +97,37 @@ def affine_of(pred: Any, n_channels: int) -> Tuple[Tuple[Tuple[int, float], ...]
         )
     terms = tuple((d, float(c)) for d, c in enumerate(coeffs) if c != 0.0)
     return terms, float(bias)
+
+
+def verify_probed(cf: "CompiledFormula", traces: np.ndarray) -> Tuple[int, ...]:
+    """Check the predicates whose affine form came from probing against ``fn`` on real traces
+    (``traces[n, T, D]`` float64, a few rows of the caller's batch).  Returns ``id(fn)`` of those
+    that disagree anywhere in the sample: the caller recompiles with them forced onto leaf channels."""
+    bad = []
+    n, T, _ = traces.shape
+    rng = np.random.default_rng(T)
+    ts = sorted({0, 1, 2, 3, T // 3, T // 2, max(T - 2, 0), T - 1, *rng.integers(0, T, size=8).tolist()})
+    for pred, terms, bias in cf.probed_preds:
+        ok = True
+        try:
+            for b in range(n):
+                sig = traces[b]
+                for t in ts:
+                    if t < 0 or t >= T:
+                        continue
+                    want = bias + sum(c * sig[t, d] for d, c in terms)
+                    got = float(pred.fn(sig, t))
+                    mag = abs(bias) + sum(abs(c * sig[t, d]) for d, c in terms) + 1e-300
+                    if not np.isfinite(got) or abs(got - want) > 1e-9 * mag:
+                        ok = False
+                        break
+                if not ok:
+                    break
+        except Exception:
+            ok = False
+        if not ok:
+            bad.append(id(pred.fn))
+    return tuple(sorted(bad))
 
 
 @dataclass
@@ -95,6 +144,7 @@ class CompiledFormula:
     pred_terms: List[Tuple[Tuple[Tuple[int, float], ...], float]]
     n_signal_channels: int = 0   # channels of the user's signal
     leaf_preds: Tuple[Any, ...] = ()  # non-affine predicates: leaf j is channel n_signal_channels + j
+    probed_preds: Tuple[Any, ...] = ()  # (predicate, terms, bias) recognised as affine by probing only
 
     @property
     def n_channels(self) -> int:
@@ -113,6 +163,7 @@ def compile_formula(
     temperature: float = 1.0,
     eps: float = 1e-8,
     p: int = 1,
+    force_leaf: Tuple[int, ...] = (),
 ) -> CompiledFormula:
     sem_id = _SEM_IDS[semantics]
     nodes: List[capi.Node] = []
@@ -123,6 +174,8 @@ def compile_formula(
     memo: Dict[int, int] = {}
     leaves: List[Any] = []
     leaf_index: Dict[int, int] = {}
+    probed: List[Any] = []
+    probed_seen: set = set()
 
     def add_weights(w) -> Tuple[int, int]:
         if w is None:
@@ -155,7 +208,13 @@ def compile_formula(
         if kind == "Predicate":
             n.kind = capi.NODE_PRED
             try:
+                if id(getattr(node, "fn", None)) in force_leaf:
+                    raise NotImplementedError("demoted: fn disagreed with its probed affine form on a real signal")
                 terms, bias = affine_of(node, n_channels)
+                meta = getattr(node, "metadata", None) or {}
+                if "affine" not in meta and id(node.fn) not in probed_seen:
+                    probed_seen.add(id(node.fn))
+                    probed.append((node, terms, bias))
             except NotImplementedError:
                 # not affine: evaluated with torch on the device into leaf channel n_channels + j
                 fkey = id(node.fn)
@@ -244,6 +303,7 @@ def compile_formula(
         pred_terms=preds,
         n_signal_channels=int(n_channels),
         leaf_preds=tuple(leaves),
+        probed_preds=tuple(probed),
     )
 
 

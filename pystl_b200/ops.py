@@ -1,0 +1,162 @@
+"""``torch.library`` custom ops around the C ABI.
+
+Three entry points of ``include/pystl_b200.h`` become dispatcher ops
+
+    pystl_b200::robustness(signal[B, T, D], handle)                    -> out[B, T, C]
+    pystl_b200::robustness_grad(signal, grad_out[B, T, C], handle)     -> grad_signal[B, T, D]
+    pystl_b200::value_and_grad(signal, scale, handle)                  -> (out, acc[2] float64, grad_signal)
+
+with fake (meta) kernels, an autograd formula for ``robustness`` and batching rules, so that
+``torch.compile`` traces through a robustness evaluation without a graph break and
+``torch.func.vmap / grad`` compose with it (the precedent is ``jax.vmap`` over the reference's JAX
+backend, tests/test_jax_semantics.py:310-368 of the reference).  A compiled formula
+(``compiler.CompiledFormula``: ctypes arrays, not a tensor) is passed as an integer handle.
+
+PyTorch is plumbing here: the ops hand raw device pointers and the current stream to
+``libpystl_b200.so``; there is no CPU implementation to fall back to.
+"""
+
+from __future__ import annotations
+
+import itertools
+from typing import Dict, Tuple
+
+import torch
+
+from . import capi
+
+_HANDLES: Dict[int, Tuple[object, int]] = {}  # handle -> (CompiledFormula, out_channels)
+_next = itertools.count(1)
+
+
+def handle_of(cf, out_channels: int) -> int:
+    h = getattr(cf, "_op_handle", None)
+    if h is None:
+        h = next(_next)
+        cf._op_handle = h
+        if len(_HANDLES) > 4096:  # formulas compiled long ago: their semantics object still caches them
+            for k in list(_HANDLES)[:2048]:
+                _HANDLES.pop(k, None)
+    _HANDLES[h] = (cf, int(out_channels))
+    return h
+
+
+def _lookup(handle: int):
+    try:
+        return _HANDLES[int(handle)]
+    except KeyError:
+        raise RuntimeError(f"pystl_b200: unknown formula handle {handle} (compile the formula in this process first)") from None
+
+
+def _check(signal: torch.Tensor) -> None:
+    if not signal.is_cuda:
+        raise RuntimeError("pystl_b200 ops need a CUDA tensor; there is no CPU fallback")
+    if signal.dim() != 3 or signal.dtype != torch.float32:
+        raise ValueError("signal must be float32 with shape (batch, time, state_dim)")
+
+
+@torch.library.custom_op("pystl_b200::robustness", mutates_args=(), device_types="cuda")
+def robustness(signal: torch.Tensor, handle: int) -> torch.Tensor:
+    _check(signal)
+    cf, C = _lookup(handle)
+    sig = signal.contiguous()
+    B, T, D = sig.shape
+    out = torch.empty((B, T, C), dtype=torch.float32, device=sig.device)
+    with torch.cuda.device(sig.device):
+        rc = capi.lib().pystl_b200_eval_forward(cf.ptr(), sig.data_ptr(), B, T, D, out.data_ptr(), None,
+                                                torch.cuda.current_stream(sig.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return out
+
+
+@robustness.register_fake
+def _(signal, handle):
+    _, C = _lookup(handle)
+    return signal.new_empty((signal.shape[0], signal.shape[1], C))
+
+
+@torch.library.custom_op("pystl_b200::robustness_grad", mutates_args=(), device_types="cuda")
+def robustness_grad(signal: torch.Tensor, grad_out: torch.Tensor, handle: int) -> torch.Tensor:
+    _check(signal)
+    cf, C = _lookup(handle)
+    sig = signal.contiguous()
+    B, T, D = sig.shape
+    g = grad_out.to(dtype=torch.float32).contiguous()
+    if tuple(g.shape) != (B, T, C):
+        raise ValueError(f"grad_out must have shape {(B, T, C)}, got {tuple(g.shape)}")
+    grad = torch.empty_like(sig)
+    with torch.cuda.device(sig.device):
+        rc = capi.lib().pystl_b200_eval_backward(cf.ptr(), sig.data_ptr(), B, T, D, g.data_ptr(), 1.0, grad.data_ptr(),
+                                                 torch.cuda.current_stream(sig.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return grad
+
+
+@robustness_grad.register_fake
+def _(signal, grad_out, handle):
+    return torch.empty_like(signal)
+
+
+@torch.library.custom_op("pystl_b200::value_and_grad", mutates_args=(), device_types="cuda")
+def value_and_grad(signal: torch.Tensor, scale: float, handle: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Robustness trace, its (sum, 0) accumulator and the gradient of ``scale * sum(valid outputs)``
+    in ONE pass over the signal (pystl_b200_eval_value_and_grad)."""
+    _check(signal)
+    cf, C = _lookup(handle)
+    sig = signal.contiguous()
+    B, T, D = sig.shape
+    out = torch.empty((B, T, C), dtype=torch.float32, device=sig.device)
+    acc = torch.zeros(2, dtype=torch.float64, device=sig.device)
+    grad = torch.empty_like(sig)
+    with torch.cuda.device(sig.device):
+        rc = capi.lib().pystl_b200_eval_value_and_grad(cf.ptr(), sig.data_ptr(), B, T, D, None, float(scale), out.data_ptr(),
+                                                       acc.data_ptr(), grad.data_ptr(),
+                                                       torch.cuda.current_stream(sig.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return out, acc, grad
+
+
+@value_and_grad.register_fake
+def _(signal, scale, handle):
+    _, C = _lookup(handle)
+    return (signal.new_empty((signal.shape[0], signal.shape[1], C)), signal.new_empty((2,), dtype=torch.float64),
+            torch.empty_like(signal))
+
+
+# ---- autograd: d robustness / d signal is the backward entry point of the C ABI
+def _setup_context(ctx, inputs, output):
+    signal, handle = inputs
+    ctx.save_for_backward(signal)
+    ctx.handle = handle
+
+
+def _backward(ctx, grad_out):
+    (signal,) = ctx.saved_tensors
+    return robustness_grad(signal, grad_out, ctx.handle), None
+
+
+torch.library.register_autograd("pystl_b200::robustness", _backward, setup_context=_setup_context)
+
+
+# ---- batching rules: traces are independent, so a vmapped dimension folds into the batch
+def _fold(x: torch.Tensor, dim):
+    x = x.movedim(dim, 0)
+    return x.reshape((x.shape[0] * x.shape[1],) + tuple(x.shape[2:])), x.shape[0]
+
+
+@torch.library.register_vmap("pystl_b200::robustness")
+def _(info, in_dims, signal, handle):
+    flat, n = _fold(signal, in_dims[0])
+    out = robustness(flat, handle)
+    return out.reshape((n, -1) + tuple(out.shape[1:])), 0
+
+
+@torch.library.register_vmap("pystl_b200::robustness_grad")
+def _(info, in_dims, signal, grad_out, handle):
+    n = info.batch_size
+    sig = signal.movedim(in_dims[0], 0) if in_dims[0] is not None else signal.unsqueeze(0).expand((n,) + tuple(signal.shape))
+    g = grad_out.movedim(in_dims[1], 0) if in_dims[1] is not None else grad_out.unsqueeze(0).expand((n,) + tuple(grad_out.shape))
+    fs = sig.reshape((-1,) + tuple(sig.shape[2:]))
+    fg = g.reshape((-1,) + tuple(g.shape[2:]))
+    out = robustness_grad(fs, fg, handle)
+    return out.reshape((n, -1) + tuple(out.shape[1:])), 0

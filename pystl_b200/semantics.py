@@ -53,32 +53,75 @@ def _device_of(signal: torch.Tensor) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-class _B200Semantics:
+try:  # plug into the reference's class hierarchy when it is installed (semantics/base.py:18-75)
+    from pystl.semantics.base import Semantics as _ReferenceSemantics  # type: ignore
+except Exception:  # the GPU box has no `pystl`: same interface, no common base
+    _ReferenceSemantics = object
+
+
+class _B200Semantics(_ReferenceSemantics):
     syntax = ""
     out_channels = 1
 
     def __init__(self) -> None:
-        self._cache: Dict[Tuple[int, int], Tuple[Any, CompiledFormula]] = {}
+        self._cache: Dict[Tuple, Tuple[Any, CompiledFormula]] = {}
+        self._verified: Dict[Tuple, Tuple[Any, Tuple[int, ...]]] = {}
+        self._list_formulas: Dict[Tuple, Any] = {}
 
     # ---- kwargs forwarded to the C ABI -------------------------------------------------
     def _params(self) -> dict:
         return {}
 
     # ---- formula cache (the only mutable state; keyed by object identity + D) ----------
-    def compile(self, formula: Any, n_channels: int) -> CompiledFormula:
-        key = (id(formula), int(n_channels))
+    def compile(self, formula: Any, n_channels: int, force_leaf: Tuple[int, ...] = ()) -> CompiledFormula:
+        # the semantics' own parameters are part of the key: changing sem.temperature / eps / p
+        # after the first call recompiles instead of being silently ignored
+        key = (id(formula), int(n_channels), tuple(sorted(self._params().items())), tuple(force_leaf))
         hit = self._cache.get(key)
         if hit is not None and hit[0] is formula:
             return hit[1]
-        cf = compile_formula(formula, self.syntax, n_channels, **self._params())
+        cf = compile_formula(formula, self.syntax, n_channels, force_leaf=force_leaf, **self._params())
         if len(self._cache) > 256:
             self._cache.clear()
         self._cache[key] = (formula, cf)
         return cf
 
-    def plan(self, formula: Any, horizon: int, n_channels: int) -> dict:
+    def _checked_compile(self, formula: Any, sig: torch.Tensor) -> CompiledFormula:
+        """``compile`` + the check the probe alone cannot give: predicates recognised as affine by
+        probing ``fn`` are compared with ``fn`` on rows of the REAL signal (first and last trace, a
+        sample of ``t`` including the last one) once per (formula, D, T); a predicate that disagrees is
+        recompiled as a leaf channel (``compiler.verify_probed``)."""
+        B, T, D = sig.shape
+        cf = self.compile(formula, D)
+        if not cf.probed_preds or B == 0 or T == 0:
+            return cf
+        vkey = (id(formula), D, T)
+        hit = self._verified.get(vkey)
+        if hit is None or hit[0] is not formula:
+            from .compiler import verify_probed
+
+            rows = sig[[0, B - 1]] if B > 1 else sig[:1]
+            force = verify_probed(cf, rows.detach().to(torch.float64).cpu().numpy())
+            if len(self._verified) > 256:
+                self._verified.clear()
+            hit = self._verified[vkey] = (formula, force)
+        return self.compile(formula, D, hit[1]) if hit[1] else cf
+
+    def invalidate(self, formula: Any = None) -> None:
+        """Forget what was compiled for ``formula`` (all formulas when None): a predicate's ``fn`` is
+        sampled once, so rebinding a value its closure reads needs this call to take effect."""
+        if formula is None:
+            self._cache.clear()
+            self._verified.clear()
+            return
+        for d in (self._cache, self._verified):
+            for k in [k for k in d if k[0] == id(formula)]:
+                d.pop(k, None)
+
+    def plan(self, formula: Any, horizon: int, n_channels: int, cf: Optional[CompiledFormula] = None) -> dict:
         """Tiling / validity report for ``formula`` on traces of ``horizon`` samples (host only)."""
-        cf = self.compile(formula, n_channels)
+        if cf is None:
+            cf = self.compile(formula, n_channels)
         p = capi.Plan()
         rc = capi.lib().pystl_b200_plan(cf.ptr(), int(horizon), cf.n_channels, 0, C.byref(p))
         capi.raise_for(rc, capi.lib().pystl_b200_last_error())
@@ -114,20 +157,16 @@ class _B200Semantics:
 
         Cumulative returns ``B200CumulativeRobustness(pos, neg)`` of such tensors.  Entries the
         reference would raise ``ValueError`` on (empty window, api.py:218-221) are NaN.
-        """
-        sig, squeeze, home = self._prepare(signal)
-        cf = self.compile(formula, sig.shape[-1])
-        if torch.is_grad_enabled() and isinstance(signal, torch.Tensor) and signal.requires_grad:
-            from .autograd import RobustnessFn
+        Differentiable: the evaluation is the dispatcher op ``pystl_b200::robustness`` (ops.py), whose
+        autograd formula is the backward entry point of the C ABI; it also carries a fake kernel and a
+        batching rule, so ``torch.compile`` and ``torch.func.vmap / grad`` work through it."""
+        from . import ops
 
-            src = signal if not squeeze else signal.unsqueeze(0)
-            if cf.leaf_preds:  # non-affine predicates: leaf channels computed by torch, inside the graph
-                src = leaf_values(cf, src.to(device=sig.device, dtype=torch.float32))
-            out = RobustnessFn.apply(src, self, cf)
-        else:
-            with torch.no_grad():
-                sig = leaf_values(cf, sig)
-            out = self._forward_raw(cf, sig, None)
+        sig, squeeze, home = self._prepare(signal)  # (stays connected to `signal` in the autograd graph)
+        cf = self._checked_compile(formula, sig)
+        if cf.leaf_preds:  # non-affine predicates: leaf channels computed by torch, inside the graph
+            sig = leaf_values(cf, sig)
+        out = ops.robustness(sig, ops.handle_of(cf, self.out_channels))
         if home != out.device:
             out = out.to(home)
         if squeeze:
@@ -144,9 +183,9 @@ class _B200Semantics:
         from .distributed import all_reduce_mean
 
         sig, _, _ = self._prepare(signal)
-        cf = self.compile(formula, sig.shape[-1])
+        cf = self._checked_compile(formula, sig)
         acc = torch.zeros(2, dtype=torch.float64, device=sig.device)
-        plan = self.plan(formula, sig.shape[1], sig.shape[2])
+        plan = self.plan(formula, sig.shape[1], sig.shape[2], cf)
         with torch.no_grad():
             sig = leaf_values(cf, sig)
         self._forward_raw(cf, sig, acc)
@@ -165,9 +204,10 @@ class _B200Semantics:
         from .distributed import all_reduce_mean, all_reduce_count
 
         sig, squeeze, home = self._prepare(signal)
+        sig = sig.detach()
         B, T, D = sig.shape
-        cf = self.compile(formula, D)
-        plan = self.plan(formula, T, D)
+        cf = self._checked_compile(formula, sig)
+        plan = self.plan(formula, T, D, cf)
         valid = 0 if plan["raises_always"] else max(T - plan["start_slack"], 0)
         n_local = float(B * valid)
         n_total = all_reduce_count(n_local, sig.device, group=group)
@@ -229,8 +269,12 @@ class _B200Semantics:
         return value, np.asarray(grad.detach().cpu().numpy(), dtype=float)
 
     # ---- the reference's operator interface (base.py:21-75) -------------------------------
-    # Values are torch tensors of any (broadcastable) shape on a CUDA device; a list of n
-    # values is stacked into an n-channel signal and reduced by the same fused kernel.
+    # This is what the reference's own recursion (api.py:142-302) calls, once per node and t, with
+    # LISTS of backend-native values.  Values here are torch tensors of any (broadcastable) shape on
+    # a CUDA device.  A list of n values is laid out along the TIME axis of a one-channel signal and
+    # reduced by the fused window kernel -- Always / Eventually over [0, n-1] read at t = 0 is the
+    # same reduction (base.py:47-61), and a window has no limit on n where an n-ary And / Or
+    # instruction takes at most 8 operands.
     def predicate(self, predicate: Any, signal: Any, t: int) -> Any:
         if predicate.fn is None:
             raise ValueError(f"Predicate '{predicate.name}' does not define `fn(signal, t)`.")
@@ -254,16 +298,26 @@ class _B200Semantics:
         vals = torch.broadcast_tensors(*[v.to(dev) for v in vals])
         return torch.stack(vals, dim=-1)  # [..., n]
 
-    def _reduce(self, values: Sequence[Any], kind: str, weights, where: str) -> torch.Tensor:
-        from .formula import And, Or
+    def _list_formula(self, kind: str, n: int, weights) -> Any:
+        """``Always`` / ``Eventually`` over ``[0, n-1]`` of channel 0, cached per (kind, n, weights)."""
+        from .formula import Always, Eventually
 
-        x = self._stack(values, where)
+        w = None if weights is None else tuple(float(x) for x in weights)
+        key = (kind, n, w)
+        phi = self._list_formulas.get(key)
+        if phi is None:
+            if len(self._list_formulas) > 128:
+                self._list_formulas.clear()
+            leaf = affine_predicate("v", {0: 1.0}, 0.0)
+            phi = (Always if kind == "and" else Eventually)(leaf, (0, n - 1), weights=w)
+            self._list_formulas[key] = phi
+        return phi
+
+    def _reduce(self, values: Sequence[Any], kind: str, weights, where: str) -> torch.Tensor:
+        x = self._stack(values, where)  # [..., n]
         n = x.shape[-1]
-        leaves = [affine_predicate(f"v{i}", {i: 1.0}, 0.0) for i in range(n)]
-        phi = (And if kind == "and" else Or)(*leaves, weights=weights)
-        flat = x.reshape(1, -1, n)
-        out = self.robustness_trace(phi, flat)
-        return out.reshape(x.shape[:-1])
+        out = self.robustness_trace(self._list_formula(kind, n, weights), x.reshape(-1, n, 1))
+        return out[:, 0].reshape(x.shape[:-1])
 
     def boolean_and(self, values: Sequence[Any], *, weights: Optional[Sequence[float]] = None) -> Any:
         return self._reduce(values, "and", weights, "boolean_and")
@@ -272,10 +326,45 @@ class _B200Semantics:
         return self._reduce(values, "or", weights, "boolean_or")
 
     def temporal_always(self, values: Sequence[Any], *, weights: Optional[Sequence[float]] = None) -> Any:
-        return self.boolean_and(values, weights=weights)
+        return self._reduce(values, "and", weights, "temporal_always")
 
     def temporal_eventually(self, values: Sequence[Any], *, weights: Optional[Sequence[float]] = None) -> Any:
-        return self.boolean_or(values, weights=weights)
+        return self._reduce(values, "or", weights, "temporal_eventually")
+
+    @staticmethod
+    def _until_window(left_trace, right_trace, start: int, end: Optional[int]) -> Tuple[int, int]:
+        # same checks, same messages as classic.py:50-61 / cumulative.py:85-94
+        if len(left_trace) == 0 or len(right_trace) == 0:
+            raise ValueError("UNTIL traces must be non-empty.")
+        if len(left_trace) != len(right_trace):
+            raise ValueError("UNTIL traces must have the same length.")
+        if start < 0:
+            raise ValueError("UNTIL start must be >= 0.")
+        n = len(left_trace)
+        last = n - 1 if end is None else min(end, n - 1)
+        if start > last:
+            raise ValueError("UNTIL temporal window is empty.")
+        return n, last
+
+    def _until_value(self, l: torch.Tensor, r: torch.Tensor, start: int, last: int, weights_left, weights_right, weights_pair):
+        """``l, r``: ``[..., n]``; Until over ``[start, last]`` (already clipped to the traces) at t = 0."""
+        from .formula import Until
+
+        l, r = torch.broadcast_tensors(l, r)
+        n = l.shape[-1]
+        sig = torch.stack((l, r), dim=-1).reshape(-1, n, 2)  # [batch, time, (l, r)]
+        key = ("until", start, last, None if weights_left is None else tuple(weights_left),
+               None if weights_right is None else tuple(weights_right), tuple(weights_pair))
+        phi = self._list_formulas.get(key)
+        if phi is None:
+            if len(self._list_formulas) > 128:
+                self._list_formulas.clear()
+            phi = Until(
+                affine_predicate("l", {0: 1.0}), affine_predicate("r", {1: 1.0}), (start, last),
+                weights_left=weights_left, weights_right=weights_right, weights_pair=weights_pair,
+            )
+            self._list_formulas[key] = phi
+        return self.robustness_trace(phi, sig), l.shape[:-1]
 
     def temporal_until(
         self,
@@ -288,28 +377,11 @@ class _B200Semantics:
         weights_right: Optional[Sequence[float]] = None,
         weights_pair: Sequence[float] = (1.0, 1.0),
     ) -> Any:
-        from .formula import Until
-
-        if len(left_trace) == 0 or len(right_trace) == 0:
-            raise ValueError("UNTIL traces must be non-empty.")
-        if len(left_trace) != len(right_trace):
-            raise ValueError("UNTIL traces must have the same length.")
-        if start < 0:
-            raise ValueError("UNTIL start must be >= 0.")
-        n = len(left_trace)
-        last = n - 1 if end is None else min(end, n - 1)
-        if start > last:
-            raise ValueError("UNTIL temporal window is empty.")
+        _, last = self._until_window(left_trace, right_trace, start, end)
         l = self._stack(left_trace, "temporal_until")  # [..., n]
         r = self._stack(right_trace, "temporal_until")
-        l, r = torch.broadcast_tensors(l, r)
-        sig = torch.stack((l, r), dim=-1).reshape(-1, n, 2)  # [batch, time, (l, r)]
-        phi = Until(
-            affine_predicate("l", {0: 1.0}), affine_predicate("r", {1: 1.0}), (start, end),
-            weights_left=weights_left, weights_right=weights_right, weights_pair=weights_pair,
-        )
-        out = self.robustness_trace(phi, sig)[:, 0]
-        return out.reshape(l.shape[:-1])
+        out, shape = self._until_value(l, r, start, last, weights_left, weights_right, weights_pair)
+        return out[:, 0].reshape(shape)
 
 
 class B200ClassicRobustSemantics(_B200Semantics):
@@ -346,39 +418,56 @@ class B200CumulativeSemantics(_B200Semantics):
     def boolean_not(self, value: Any) -> Any:
         return B200CumulativeRobustness(pos=-value.neg, neg=-value.pos)
 
-    # (pos, neg) lists: each channel is reduced independently by the same kernel, fed with
-    # predicates that are already clipped (pos >= 0, neg <= 0 pass through the leaf unchanged)
-    def _pair_reduce(self, values, op: str):
+    # (pos, neg) lists (cumulative.py:35-103).  The two channels never mix, pos >= 0 and neg <= 0
+    # throughout (predicates clip, Not swaps and negates, min / max / sum keep the sign), and a
+    # cumulative predicate maps a non-negative scalar p to (p, 0) and a non-positive n to (0, n): so the
+    # list of pos values goes through the cumulative kernel as a one-channel signal and the answer is the
+    # pos channel of the result, likewise neg.  min / max are the Always / Eventually windows of the
+    # classic kernel (cumulative Eventually is a SUM, cumulative.py:61-72, so max cannot use it).
+    def _channels(self, values, where: str):
         if len(values) == 0:
-            raise ValueError(f"{op} requires at least one value.")
-        pos = [v.pos for v in values]
-        neg = [v.neg for v in values]
-        helper = B200ClassicRobustSemantics()
-        if op == "sum":
-            return B200CumulativeRobustness(
-                pos=torch.stack(list(torch.broadcast_tensors(*pos)), 0).sum(0),
-                neg=torch.stack(list(torch.broadcast_tensors(*neg)), 0).sum(0),
-            )
-        red = helper.boolean_and if op == "min" else helper.boolean_or
+            raise ValueError(f"{where} requires at least one value.")
+        return [v.pos for v in values], [v.neg for v in values]
+
+    def _minmax(self, values, kind: str, where: str):
+        pos, neg = self._channels(values, where)
+        helper = self._helper()
+        red = helper.temporal_always if kind == "min" else helper.temporal_eventually
         return B200CumulativeRobustness(pos=red(pos), neg=red(neg))
 
+    def _helper(self):
+        h = getattr(self, "_classic_helper", None)
+        if h is None:
+            h = self._classic_helper = B200ClassicRobustSemantics()
+        return h
+
     def boolean_and(self, values, *, weights=None):
-        return self._pair_reduce(values, "min")
+        return self._minmax(values, "min", "boolean_and")
 
     def boolean_or(self, values, *, weights=None):
-        return self._pair_reduce(values, "max")
+        return self._minmax(values, "max", "boolean_or")
 
     def temporal_always(self, values, *, weights=None):
-        return self._pair_reduce(values, "min")
+        return self._minmax(values, "min", "temporal_always")
 
     def temporal_eventually(self, values, *, weights=None):
-        return self._pair_reduce(values, "sum")
+        pos, neg = self._channels(values, "temporal_eventually")
+        xp, xn = self._stack(pos, "temporal_eventually"), self._stack(neg, "temporal_eventually")
+        n = xp.shape[-1]
+        phi = self._list_formula("or", n, None)  # Eventually[0, n-1]: the sum window under this semantics
+        sp = self.robustness_trace(phi, xp.reshape(-1, n, 1))
+        sn = self.robustness_trace(phi, xn.reshape(-1, n, 1))
+        return B200CumulativeRobustness(pos=sp.pos[:, 0].reshape(xp.shape[:-1]), neg=sn.neg[:, 0].reshape(xn.shape[:-1]))
 
     def temporal_until(self, *, left_trace, right_trace, start, end, weights_left=None, weights_right=None,
                        weights_pair=(1.0, 1.0)):
-        raise NotImplementedError(
-            "cumulative temporal_until on (pos, neg) lists: use robustness_trace / evaluate_formula on the formula"
-        )
+        """``sum_i min(r_i, min_{k<=i} l_k)`` per channel (cumulative.py:74-103) on lists of pairs."""
+        _, last = self._until_window(left_trace, right_trace, start, end)
+        lp, ln = self._channels(left_trace, "temporal_until")
+        rp, rn = self._channels(right_trace, "temporal_until")
+        up, shape = self._until_value(self._stack(lp, "temporal_until"), self._stack(rp, "temporal_until"), start, last, None, None, (1.0, 1.0))
+        un, _ = self._until_value(self._stack(ln, "temporal_until"), self._stack(rn, "temporal_until"), start, last, None, None, (1.0, 1.0))
+        return B200CumulativeRobustness(pos=up.pos[:, 0].reshape(shape), neg=un.neg[:, 0].reshape(shape))
 
 
 class B200AgmRobustSemantics(_B200Semantics):

@@ -138,6 +138,11 @@ def smooth_until_backward_cases(light: bool = False):
             for threads in ((64,) if light else (0, 64)):
                 out.append(dict(name=f"bwd/{name}/smooth{tau}/nt{threads}", spec=spec, sem="smooth", kw={"temperature": tau}, B=2, T=300,
                                 D={"cfg4": 4, "cfg5": 8}.get(name, 2), threads=threads, seed=29))
+    # the trace ends exactly where a tile ends (see forward_cases: tile_end)
+    out.append(dict(name="bwd/U/smooth0.5/tile_end", spec=specs["U"], sem="smooth", kw={"temperature": 0.5}, B=2, T=512, D=2, threads=64, seed=31))
+    if not light:
+        out.append(dict(name="bwd/cfg5/smooth0.5/tile_end", spec=specs["cfg5"], sem="smooth", kw={"temperature": 0.5}, B=2, T=512, D=8, threads=64,
+                        seed=31))
     return out
 
 
@@ -158,6 +163,11 @@ def gm_backward_cases(light: bool = False):
             for threads in ((64,) if light else (0, 64)):
                 out.append(dict(name=f"bwd/{name}/{sem}{kw.get('p', '')}/nt{threads}", spec=spec, sem=sem, kw=kw, B=2, T=300,
                                 D={"cfg4": 4, "cfg5": 8}.get(name, 2), threads=threads, seed=37))
+    # the trace ends exactly where a tile ends (see forward_cases: tile_end)
+    for si, (sem, kw) in enumerate(SEM_KW[3:5]):
+        out.append(dict(name=f"bwd/U/{sem}/tile_end", spec=U, sem=sem, kw=kw, B=2, T=512, D=2, threads=64, seed=39))
+        if not light:
+            out.append(dict(name=f"bwd/cfg5/{sem}/tile_end", spec=BASELINE_SPECS["cfg5"], sem=sem, kw=kw, B=2, T=512, D=8, threads=64, seed=39))
     return out
 
 

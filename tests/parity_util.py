@@ -19,7 +19,27 @@ def oracle_trace(spec, sem: str, kw: dict, sig64: np.ndarray) -> np.ndarray:
     return np.moveaxis(out, 0, -1) if sem == "cumulative" else out
 
 
+def parity_log(kind: str, what: str, sem: str, ratio: float, scale: float) -> None:
+    """PYSTL_PARITY_LOG=<file>: append the worst error / stated-bar ratio of every comparison (the
+    measured table under profiles/ is made from it: tests/error_table.py --from-log)."""
+    import os
+
+    path = os.environ.get("PYSTL_PARITY_LOG")
+    if path:
+        with open(path, "a") as fh:
+            fh.write(f"{kind}\t{sem}\t{ratio:.4g}\t{scale:g}\t{what}\n")
+
+
+def scale_cap(scale: float) -> float:
+    """PYSTL_PARITY_SCALE_CAP=<x>: tighten every tolerance multiplier to at most x (experiments)."""
+    import os
+
+    cap = os.environ.get("PYSTL_PARITY_SCALE_CAP")
+    return min(scale, float(cap)) if cap else scale
+
+
 def assert_parity(got: np.ndarray, want64: np.ndarray, sem: str, what: str = "", scale: float = 1.0) -> None:
+    scale = scale_cap(scale)
     assert got.shape == want64.shape, (what, got.shape, want64.shape)
     assert np.array_equal(np.isnan(got), np.isnan(want64)), f"{what}: NaN pattern differs"
     if sem == "classical":
@@ -29,6 +49,8 @@ def assert_parity(got: np.ndarray, want64: np.ndarray, sem: str, what: str = "",
         return
     err = np.abs(got.astype(np.float64) - want64)
     tol = scale * (ATOL + RTOL * np.abs(want64))
+    with np.errstate(invalid="ignore"):
+        parity_log("value", what, sem, float(np.nanmax(np.where(np.isnan(want64), 0.0, err / (ATOL + RTOL * np.abs(want64))), initial=0.0)), scale)
     bad = err > tol
     bad &= ~np.isnan(want64)
     assert not bad.any(), (

@@ -138,3 +138,9 @@ def test_classic_gradient_random_formulas(seed):
             assert threads  # the two-sided halo does not fit the forced tile
             continue
         check(got.astype(np.float64), want, "classical", f"seed{seed}/nt{threads}/{spec}")
+
+
+def test_classic_until_tie_routing_touches_active_leaves_only():
+    from test_emu_backward import tie_routing_report
+
+    tie_routing_report(lambda spec, sig, g: fused_emu_lib.eval_backward(from_spec(spec), "classical", sig, g))

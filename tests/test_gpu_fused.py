@@ -315,3 +315,57 @@ def test_forward_with_tma_forced(case, monkeypatch):
 def test_backward_with_tma_forced(case, monkeypatch):
     monkeypatch.setenv("PYSTL_B200_TMA", "2")
     test_backward(case)
+
+
+def test_classic_until_tie_routing_touches_active_leaves_only():
+    """The documented deviation from torch.minimum / maximum's 0.5 / 0.5 tie split (test_emu_backward.py)."""
+    from test_emu_backward import tie_routing_report
+
+    for which in ("fused", "interp"):
+        tie_routing_report(lambda spec, sig, g: gpu_grad(spec, "classical", {}, sig, g, which))
+
+
+# ---------------------------------------------------------------------------- value + gradient at the BASELINE horizons
+HORIZON_CASES = [(cfg, sem, kw, shape) for cfg, shape in (("cfg4", (3, 16384, 4)), ("cfg5", (4, 2048, 8))) for sem, kw in SEM_KW[:5]]
+
+
+@pytest.mark.parametrize("cfg,sem,kw,shape", HORIZON_CASES, ids=[f"{c}-{s}" for c, s, _, _ in HORIZON_CASES])
+def test_value_and_grad_at_baseline_horizons_of_the_until_formulas(cfg, sem, kw, shape):
+    """cfg4 at T = 16384 and cfg5 at T = 2048 (exactly one 256-thread tile: the case that hid a forward
+    bug in round 1), every semantics, the ONE-kernel value-and-gradient path against the float64 oracle
+    on every trace: robustness, its fused mean, and the gradient for an explicit and for the constant
+    cotangent."""
+    from pystl_b200 import capi
+
+    rng = np.random.default_rng(91)
+    sig = mixed_signal(rng, *shape)
+    B, T, D = shape
+    spec = BASELINE_SPECS[cfg]
+    s = create_semantics(sem, backend="b200", **kw)
+    x = torch.tensor(sig, dtype=torch.float32, device="cuda")
+    cf = s.compile(from_spec(spec), D)
+    C = s.out_channels
+    g64 = rng.standard_normal((B, T, C) if C == 2 else (B, T)).astype(np.float32).astype(np.float64)
+    go = torch.tensor(g64, dtype=torch.float32, device="cuda").contiguous()
+    out = torch.empty((B, T, C), dtype=torch.float32, device="cuda")
+    acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    grad = torch.full_like(x, -12345.0)
+    with tier("fused"):
+        rc = capi.lib().pystl_b200_eval_value_and_grad(cf.ptr(), x.data_ptr(), B, T, D, go.data_ptr(), 1.0, out.data_ptr(), acc.data_ptr(),
+                                                       grad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+        mean_c, grad_c = s.mean_robustness_and_grad(from_spec(spec), x)
+    torch.cuda.synchronize()
+    want = oracle_trace(spec, sem, kw, sig)
+    got = out.cpu().numpy()
+    assert_parity(got if C == 2 else got[..., 0], want, sem, f"horizon/{cfg}/{sem}", scale=4.0 if sem == "cumulative" else 2.0)
+    assert abs(float(acc[0]) - float(np.nansum(want))) <= 1e-5 * float(np.nansum(np.abs(want))) + 1e-3
+    rtol, atol = grad_tol(sem, kw)
+    k = 2.0  # gradients of sums over up to 265 candidates per output
+    check(grad.cpu().numpy().astype(np.float64), oracle_grad(spec, sem, kw, sig, g64), sem, f"horizon/{cfg}/{sem}/grad", k * rtol, k * atol)
+    n_valid = float(np.isfinite(want).sum()) / C
+    gc = np.full_like(g64, 1.0 / n_valid)
+    check(grad_c.cpu().numpy().astype(np.float64) * n_valid, oracle_grad(spec, sem, kw, sig, gc) * n_valid, sem,
+          f"horizon/{cfg}/{sem}/mean-grad", k * rtol, k * atol)
+    wsum = np.nansum(want, axis=-1) if C == 2 else want
+    assert abs(float(mean_c) - float(np.nanmean(wsum))) <= 1e-5 * (1.0 + abs(float(np.nanmean(wsum))))

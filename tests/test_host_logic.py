@@ -177,3 +177,109 @@ def test_non_affine_predicates_become_leaf_channels():
     assert len(cf.leaf_preds) == 1 and cf.n_signal_channels == 2 and cf.n_channels == 3
     terms = sorted(cf.pred_terms)
     assert (((1, -1.0),), 0.5) in terms and (((2, 1.0),), 0.0) in terms
+
+
+# ---------------------------------------------------------------------------- probing is only a fast reject
+def test_probe_rejects_what_it_can_and_real_signals_catch_the_rest():
+    """a predicate that depends on t beyond the probe's rows, or is affine only near the
+    origin, must not be compiled as an affine predicate."""
+    from pystl_b200.compiler import verify_probed
+
+    ref = np.array([0.0] * 4 + [1.0] * 200)
+    with pytest.raises(NotImplementedError):  # t-dependence inside the probe's rows
+        affine_of(Predicate("a", fn=lambda s, t: 0.5 - abs(ref[t]) + s[t, 0]), 2)
+    with pytest.raises(NotImplementedError):  # saturates far from the origin
+        affine_of(Predicate("b", fn=lambda s, t: min(s[t, 0], 50.0)), 2)
+    # t-dependence beyond the probe's rows: passes the probe, is caught on the real signal
+    late = np.array([0.0] * 100 + [1.0] * 100)
+    p = Predicate("late", fn=lambda s, t: 0.5 - late[t] + s[t, 0])
+    assert affine_of(p, 2) == (((0, 1.0),), 0.5)
+    phi = Always(p, Interval(0, 3)) & Predicate("ok", fn=lambda s, t: s[t, 1] - 0.25)
+    cf = compile_formula(phi, "classical", 2)
+    assert len(cf.probed_preds) == 2 and not cf.leaf_preds
+    traces = np.random.default_rng(0).normal(size=(2, 200, 2))
+    bad = verify_probed(cf, traces)
+    assert bad == (id(p.fn),)
+    cf2 = compile_formula(phi, "classical", 2, force_leaf=bad)
+    assert len(cf2.leaf_preds) == 1 and cf2.leaf_preds[0] is p and cf2.n_channels == 3
+    assert verify_probed(cf2, traces) == ()
+    # metadata gives the structured form: never probed, never second-guessed
+    assert compile_formula(gt(0, 0.5).always((0, 3)), "classical", 2).probed_preds == ()
+    # opting out of the affine path
+    forced = Predicate("leaf", fn=lambda s, t: s[t, 0] - 1.0, metadata={"affine": None})
+    assert len(compile_formula(forced.always((0, 2)), "smooth", 2).leaf_preds) == 1
+    forced2 = Predicate("leaf", fn=lambda s, t: s[t, 0] - 1.0, metadata={"leaf": True})
+    assert len(compile_formula(forced2.always((0, 2)), "smooth", 2).leaf_preds) == 1
+
+
+def test_semantics_parameters_are_part_of_the_compile_cache_key():
+    sem = create_semantics("smooth", backend="b200", temperature=1.0)
+    phi = gt(0, 0.0).always((0, 5))
+    a = sem.compile(phi, 1)
+    assert sem.compile(phi, 1) is a
+    sem.temperature = 0.25
+    b = sem.compile(phi, 1)
+    assert b is not a and b.struct.temperature == pytest.approx(0.25)
+    sem.invalidate(phi)
+    assert sem.compile(phi, 1) is not b
+
+
+def test_backend_classes_subclass_the_reference_abc_when_it_is_importable():
+    try:
+        from pystl.semantics.base import Semantics
+    except ImportError:
+        pytest.skip("the reference package is not importable here")
+    import importlib
+
+    import pystl_b200.semantics as mod
+
+    if mod._ReferenceSemantics is object:  # pystl_b200 was imported before the reference became importable
+        mod = importlib.reload(mod)
+    for cls in (mod.B200ClassicRobustSemantics, mod.B200SmoothRobustSemantics, mod.B200CumulativeSemantics,
+                mod.B200AgmRobustSemantics, mod.B200DgmsrSemantics):
+        assert issubclass(cls, Semantics)
+        cls()  # every abstract method is implemented
+
+
+def test_custom_ops_are_registered_with_fake_kernels():
+    """pystl_b200::robustness / robustness_grad / value_and_grad: shapes propagate through fake
+    tensors without a GPU (what torch.compile traces with)."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from pystl_b200 import ops
+
+    sem = create_semantics("cumulative", backend="b200")
+    cf = sem.compile(from_spec(BASELINE_SPECS["cfg4"]), 4)
+    h = ops.handle_of(cf, sem.out_channels)
+    assert ops.handle_of(cf, sem.out_channels) == h
+    with FakeTensorMode():
+        x = torch.empty(5, 100, 4, device="cuda")
+        out = torch.ops.pystl_b200.robustness(x, h)
+        assert tuple(out.shape) == (5, 100, 2) and out.device.type == "cuda"
+        g = torch.ops.pystl_b200.robustness_grad(x, out, h)
+        assert tuple(g.shape) == (5, 100, 4)
+        o, acc, gs = torch.ops.pystl_b200.value_and_grad(x, 0.5, h)
+        assert tuple(o.shape) == (5, 100, 2) and acc.dtype == torch.float64 and tuple(gs.shape) == (5, 100, 4)
+    with pytest.raises(RuntimeError, match="unknown formula handle"):
+        ops._lookup(10 ** 9)
+
+
+def test_operator_interface_validates_like_the_reference():
+    """Argument checks of the list-based interface happen before anything touches the device
+    (classic.py:28-29,50-61; cumulative.py:85-94)."""
+    sem = create_semantics("classical", backend="b200")
+    with pytest.raises(ValueError, match="at least one value"):
+        sem.boolean_and([])
+    with pytest.raises(ValueError, match="non-empty"):
+        sem.temporal_until(left_trace=[], right_trace=[], start=0, end=None)
+    with pytest.raises(ValueError, match="same length"):
+        sem.temporal_until(left_trace=[1.0, 2.0], right_trace=[1.0], start=0, end=None)
+    with pytest.raises(ValueError, match="start must be >= 0"):
+        sem.temporal_until(left_trace=[1.0], right_trace=[1.0], start=-1, end=None)
+    with pytest.raises(ValueError, match="window is empty"):
+        sem.temporal_until(left_trace=[1.0, 2.0], right_trace=[1.0, 2.0], start=5, end=7)
+    cum = create_semantics("cumulative", backend="b200")
+    with pytest.raises(ValueError, match="window is empty"):
+        cum.temporal_until(left_trace=[cum._leaf(__import__("torch").zeros(()))], right_trace=[cum._leaf(__import__("torch").zeros(()))],
+                           start=3, end=4)
