@@ -10,12 +10,21 @@ workloads).  ``value`` is whole-job trace-samples/sec with the inputs resident i
 the batch and D2H read of the mean robustness inside the timed region).
 
 Under torchrun (N > 1) every rank evaluates its own shard of the batch (weak scaling: the
-per-GPU batch is fixed) and the mean robustness is finished by one 16-byte NCCL
-all-reduce; the time is the max over ranks of the device-timed region.
+per-GPU batch is fixed) and the mean robustness of every step is finished by one 16-byte NCCL
+all-reduce issued asynchronously (it overlaps the next step's kernel; all of them are waited for
+inside the timed region); the time is the max over ranks of the device-timed region.
 
-``--impl reference`` times the CPU implementation of the same path: the oracle port of the
-reference's per-(trace, t) recursion (oracle/scalar.py; the Python reference itself cannot
-travel to the GPU box), on all host cores, on a bounded sample of the same workload.
+Besides the headline workload the line carries, driver-measured in the same run,
+``other_kernels`` -- kernel time and roofline fraction of every BASELINE.json configuration
+(cfg1 .. cfg5, all five semantics for cfg5, forward and value-and-gradient) at its named size --
+and ``cfg5_sharded``: BASELINE config 5 as named, 2^20 traces x 2048 x 8 split over the N ranks
+(strong scaling) with the NCCL mean-robustness reduction.
+
+``--impl reference`` times the CPU implementation of the same path on all host cores on a bounded
+sample of the same workload: for forward workloads the oracle port of the reference's
+per-(trace, t) recursion (oracle/scalar.py); for forward+backward workloads the batched float64
+restatement of the reference's torch backend under autograd (oracle/dense.py) -- the Python
+reference itself cannot travel to the GPU box.
 """
 
 from __future__ import annotations
@@ -72,6 +81,8 @@ WORKLOADS = {
     "cfg5b": ("classical", {}, True),
     "cfg5sb": ("smooth", {"temperature": 1.0}, True),
     "cfg5ab": ("agm", {}, True),
+    "cfg5db": ("dgmsr", {"eps": 1e-8, "p": 1}, True),
+    "cfg5cb": ("cumulative", {}, True),
 }
 DESCR = {
     "cfg1": "Classic G[0,10](x>0) & F[0,5](y<1), 1024x1000x2, forward",
@@ -90,6 +101,8 @@ DESCR = {
     "cfg5b": "Classic 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward+backward",
     "cfg5sb": "Smooth tau=1 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward+backward",
     "cfg5ab": "AGM 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward+backward",
+    "cfg5db": "D-GMSR 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward+backward",
+    "cfg5cb": "Cumulative 10-node mixed formula, 8 channels, 2^20 x 2048 x 8 (sharded), forward+backward",
 }
 
 
@@ -299,10 +312,18 @@ def cpu_vectorised_throughput(cfg: str, budget_s: float, with_bwd: bool) -> dict
 
 
 def run_reference(args) -> None:
+    """CPU arm.  Forward workloads: the oracle port of the reference's per-(trace, t) recursion
+    (oracle/scalar.py) on every host core.  Forward+backward workloads: the reference differentiates
+    by torch autograd through pystl/torch/semantics.py; its restatement with a backward leg is
+    oracle/dense.py (same operators, batched over traces and t, float64, every torch thread), so a
+    step is value AND gradient like the GPU arm's; the forward-only scalar figure rides along."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = args.workload
+    _, _, with_bwd = WORKLOADS[cfg]
+    if args.forward_only:
+        with_bwd = False
     cores = os.cpu_count() or 1
     steps = max(args.steps, 1)
     import multiprocessing as mp
@@ -311,16 +332,31 @@ def run_reference(args) -> None:
     # every step is a bounded sample of the workload; the whole run (warm-up included) is sized
     # for about a minute of wall clock whatever --steps / --warmup are
     budget = max(60.0 / (steps + args.warmup), 0.25)
-    with mp.get_context("fork").Pool(cores) as pool:
-        per = cpu_port_throughput(cfg, 0.25, cores, pool)["sec_per_eval_one_core"]
+    scalar_fwd = None
+    if with_bwd:
+        with mp.get_context("fork").Pool(cores) as pool:  # (before torch spins up its own threads)
+            scalar_fwd = cpu_port_throughput(cfg, 2.0, cores, pool)
         for _ in range(args.warmup):
-            cpu_port_throughput(cfg, budget, cores, pool, per)
+            cpu_vectorised_throughput(cfg, budget, True)
         t0 = time.perf_counter()
         base = None
         for _ in range(steps):
-            base = cpu_port_throughput(cfg, budget, cores, pool, per)
+            base = cpu_vectorised_throughput(cfg, budget, True)
             vals.append(base["value"])
         wall = time.perf_counter() - t0
+        base["kind"] = "port"
+        base["port"] = "oracle/dense.py: batched float64 restatement of pystl/torch/semantics.py, value + torch-autograd gradient"
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            per = cpu_port_throughput(cfg, 0.25, cores, pool)["sec_per_eval_one_core"]
+            for _ in range(args.warmup):
+                cpu_port_throughput(cfg, budget, cores, pool, per)
+            t0 = time.perf_counter()
+            base = None
+            for _ in range(steps):
+                base = cpu_port_throughput(cfg, budget, cores, pool, per)
+                vals.append(base["value"])
+            wall = time.perf_counter() - t0
     value = float(np.mean(vals))
     base["value"] = value
     line = {
@@ -337,8 +373,10 @@ def run_reference(args) -> None:
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{cfg}: {DESCR[cfg]}", "note": "CPU oracle port of the reference recursion, bounded sample"},
+        "config": {"workload": f"{cfg}: {DESCR[cfg]}", "pass": "forward+backward" if with_bwd else "forward",
+                   "note": "CPU restatement of the reference path on the host cores, bounded sample"},
         "cpu_baseline": base,
+        "cpu_baseline_scalar_forward": scalar_fwd,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -346,11 +384,118 @@ def run_reference(args) -> None:
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def default_batch(cfg: str, world: int = 1, strong: bool = False) -> int:
+    B, _, _ = BASELINE_SHAPES[cfg[:4]]
+    if cfg.startswith("cfg1xb"):
+        return 1 << 19
+    if cfg.startswith("cfg1x"):
+        return 1 << 20
+    if cfg[:4] == "cfg5":
+        # BASELINE config 5: 2^20 traces sharded over the GPUs of one box; weak-scaling lines use the
+        # shard of an 8-GPU run, the strong-scaling `cfg5_sharded` object splits 2^20 over the ranks
+        return (1 << 20) // (world if strong else 8)
+    return B
+
+
+def measured_traffic() -> dict:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures
+    (profiles/traffic.json, written by tools/ncu_summary.py from `ncu --set full` reports)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
+
+
+class Workload:
+    """One BASELINE configuration resident on this rank's GPU: signal, outputs, compiled formula."""
+
+    def __init__(self, cfg: str, B: int, dev, rank: int, with_bwd=None):
+        import pystl_b200
+        from pystl_b200 import capi
+
+        self.cfg = cfg
+        self.sem_name, kw, bwd = WORKLOADS[cfg]
+        self.with_bwd = bwd if with_bwd is None else with_bwd
+        _, self.T, self.D = BASELINE_SHAPES[cfg[:4]]
+        self.B = B
+        self.dev = dev
+        self.phi = from_spec(BASELINE_SPECS[cfg[:4]])
+        self.sem = pystl_b200.create_semantics(self.sem_name, backend="b200", **kw)
+        self.lib = capi.lib()
+        self.capi = capi
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.signal = torch.randn((B, self.T, self.D), generator=gen, device=dev, dtype=torch.float32)
+        self.cf = self.sem.compile(self.phi, self.D)
+        self.C_out = self.sem.out_channels
+        self.out = torch.empty((B, self.T, self.C_out), dtype=torch.float32, device=dev)
+        self.grad = torch.empty_like(self.signal) if self.with_bwd else None
+        self.stream = torch.cuda.current_stream(dev)
+        self.plan = self.sem.plan(self.phi, self.T, self.D)
+        self.n_valid = B * max(self.T - self.plan["start_slack"], 0)
+        self.tier = tier_of(self.lib, self.cf, self.T, self.D, self.with_bwd)
+        if self.tier == "fused":  # report the geometry of the kernel that actually runs
+            import ctypes
+
+            fp = capi.Plan()
+            if self.lib.pystl_b200_fused_plan(self.cf.ptr(), self.T, self.D, int(self.with_bwd), ctypes.byref(fp)) == 0:
+                self.plan = fp.as_dict()
+        # the interpreter tier has no fused value-and-gradient kernel: forward + backward launches
+        self.launches_per_step = 2 if (self.with_bwd and self.tier == "interpreter") else 1
+
+    def check(self, rc):
+        self.capi.raise_for(rc, self.lib.pystl_b200_last_error())
+
+    def forward(self, acc_ptr=None):
+        self.check(self.lib.pystl_b200_eval_forward(self.cf.ptr(), self.signal.data_ptr(), self.B, self.T, self.D, self.out.data_ptr(),
+                                                    acc_ptr, self.stream.cuda_stream))
+
+    def backward(self, scale):
+        self.check(self.lib.pystl_b200_eval_backward(self.cf.ptr(), self.signal.data_ptr(), self.B, self.T, self.D, None, scale,
+                                                     self.grad.data_ptr(), self.stream.cuda_stream))
+
+    def value_and_grad(self, scale, acc_ptr=None):
+        # value AND gradient of the mean-robustness loss through the C ABI: one fused kernel reads the
+        # signal once, writes out[B,T], its mean accumulator and grad_signal[B,T,D]
+        self.check(self.lib.pystl_b200_eval_value_and_grad(self.cf.ptr(), self.signal.data_ptr(), self.B, self.T, self.D, None, scale,
+                                                           self.out.data_ptr(), acc_ptr, self.grad.data_ptr(), self.stream.cuda_stream))
+
+    def time_kernel(self, fn, n: int) -> float:
+        """mean CUDA-event time of n launches (ms), events on the launching stream, after one warm-up"""
+        fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b_ in evs:
+            a.record(self.stream)
+            fn()
+            b_.record(self.stream)
+        torch.cuda.synchronize(self.dev)
+        return float(np.mean([a.elapsed_time(b_) for a, b_ in evs]))
+
+    def roof(self, kind: str, ms_: float, bytes_per_sample: float, peak: float, traffic: dict) -> dict:
+        gbs = bytes_per_sample * self.B * self.T / (ms_ * 1e-3) / 1e9
+        name = f"{self.tier}:{kind}<{self.sem_name}>"
+        return {"workload": self.cfg, "kernel": name, "traces": self.B, "kernel_ms": ms_, "achieved": gbs, "frac": gbs / peak,
+                "algorithmic_bytes_per_sample": bytes_per_sample, "samples_per_s": self.B * self.T / (ms_ * 1e-3),
+                "traffic": traffic.get(f"{self.cfg}:{kind}<{self.sem_name}>")}
+
+    def free(self):
+        self.signal = self.out = self.grad = None
+        torch.cuda.empty_cache()
+
+
+# every BASELINE configuration at its named size: (workload key, passes to time)
+OTHER_KERNELS = [
+    ("cfg1", ("forward",)), ("cfg1x", ("forward",)), ("cfg1xb", ("value_and_grad",)),
+    ("cfg2", ("forward",)), ("cfg3", ("forward", "value_and_grad")), ("cfg3d", ("forward", "value_and_grad")),
+    ("cfg4", ("forward",)), ("cfg4b", ("value_and_grad",)),
+    ("cfg5", ("forward",)), ("cfg5s", ("forward",)), ("cfg5c", ("forward",)), ("cfg5a", ("forward",)), ("cfg5d", ("forward",)),
+    ("cfg5b", ("value_and_grad",)), ("cfg5sb", ("value_and_grad",)), ("cfg5cb", ("value_and_grad",)), ("cfg5ab", ("value_and_grad",)),
+    ("cfg5db", ("value_and_grad",)),
+]
+
+
 def run_b200(args) -> None:
     import torch.distributed as dist
-
-    import pystl_b200
-    from pystl_b200 import capi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -361,80 +506,53 @@ def run_b200(args) -> None:
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = args.workload
-    sem_name, kw, with_bwd = WORKLOADS[cfg]
-    if args.forward_only:
-        with_bwd = False
-    B, T, D = BASELINE_SHAPES[cfg[:4]]
-    if args.batch:
-        B = args.batch
-    if cfg == "cfg1x" and not args.batch:
-        B = 1 << 20
-    if cfg == "cfg1xb" and not args.batch:
-        B = 1 << 19
-    if cfg[:4] == "cfg5" and not args.batch:
-        # 2^20 traces are sharded over 8 GPUs in the BASELINE config: 2^17 per GPU
-        B = (1 << 20) // 8
-    phi = from_spec(BASELINE_SPECS[cfg[:4]])
-    sem = pystl_b200.create_semantics(sem_name, backend="b200", **kw)
-    capi.lib()  # fail loudly if the CUDA library is missing
+    B = args.batch or default_batch(cfg)
+    w = Workload(cfg, B, dev, rank, with_bwd=False if args.forward_only else None)
+    with_bwd, T, D = w.with_bwd, w.T, w.D
+    steps = args.steps
+    warm = max(args.warmup, 3)
+    scale = 1.0 / (world * w.n_valid)  # constant cotangent: the loss is the mean over the sharded batch
+    # one (sum, count) accumulator per step: no memset inside the loop, and the all-reduce of step i
+    # (NCCL, asynchronous) overlaps the kernel of step i + 1
+    accs = torch.zeros((steps + warm, 2), dtype=torch.float64, device=dev)
+    pending = []
 
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    signal = torch.randn((B, T, D), generator=gen, device=dev, dtype=torch.float32)
-    cf = sem.compile(phi, D)
-    C_out = sem.out_channels
-    out = torch.empty((B, T, C_out), dtype=torch.float32, device=dev)
-    acc = torch.zeros(2, dtype=torch.float64, device=dev)
-    grad = torch.empty_like(signal) if with_bwd else None
-    stream = torch.cuda.current_stream(dev)
-    lib = capi.lib()
-    plan = sem.plan(phi, T, D)
-    n_valid = B * max(T - plan["start_slack"], 0)
-    launches = 0
-    tier = tier_of(lib, cf, T, D, with_bwd)
-    if tier == "fused":  # report the geometry of the kernel that actually runs
-        import ctypes
-
-        fp = capi.Plan()
-        if lib.pystl_b200_fused_plan(cf.ptr(), T, D, int(with_bwd), ctypes.byref(fp)) == 0:
-            plan = fp.as_dict()
-    # the interpreter tier has no fused value-and-gradient kernel: forward + backward launches
-    launches_per_step = 2 if (with_bwd and tier == "interpreter") else 1
-
-    def step() -> int:
-        acc.zero_()
-        if with_bwd:
-            # value AND gradient of the mean-robustness loss through the C ABI: one fused kernel reads
-            # the signal once, writes out[B,T], its mean accumulator and grad_signal[B,T,D]
-            # (constant cotangent 1 / (world * n_valid): the loss is the mean over the sharded batch)
-            rc = lib.pystl_b200_eval_value_and_grad(
-                cf.ptr(), signal.data_ptr(), B, T, D, None, 1.0 / (world * n_valid), out.data_ptr(), acc.data_ptr(),
-                grad.data_ptr(), stream.cuda_stream,
-            )
+    def step(i: int) -> int:
+        a = accs[i]
+        if with_bwd and w.launches_per_step == 1:
+            w.value_and_grad(scale, a.data_ptr())
         else:
-            rc = lib.pystl_b200_eval_forward(cf.ptr(), signal.data_ptr(), B, T, D, out.data_ptr(), acc.data_ptr(), stream.cuda_stream)
-        capi.raise_for(rc, lib.pystl_b200_last_error())
+            w.forward(a.data_ptr())
+            if with_bwd:
+                w.backward(scale)
         if world > 1:
-            dist.all_reduce(acc)
-        return launches_per_step
+            pending.append(dist.all_reduce(a, async_op=True))
+        return w.launches_per_step
+
+    def drain():
+        for work in pending:
+            work.wait()
+        pending.clear()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for i in range(warm):
+        step(i)
+    drain()
     barrier()
-    # kernel-only time of the forward kernel (the dominant one) for the roofline
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
+    launches = 0
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record(stream)
-    for i in range(args.steps):
-        launches += step()
-    t_end.record(stream)
+    t_start.record(w.stream)
+    for i in range(steps):
+        launches += step(warm + i)
+    drain()  # every step's mean is final inside the timed region
+    t_end.record(w.stream)
     barrier()
     clocks = sampler.stop()
     ms = t_start.elapsed_time(t_end)
@@ -443,75 +561,154 @@ def run_b200(args) -> None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax.item())
     samples_per_step = world * B * T
-    value = samples_per_step * args.steps / (ms * 1e-3)
+    value = samples_per_step * steps / (ms * 1e-3)
+    mean_last = float(accs[warm + steps - 1][0].item()) / (world * w.n_valid) if w.n_valid else float("nan")
 
     # kernels alone, CUDA events on the launching stream
-    def time_kernel(fn) -> float:
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        capi.raise_for(fn(), lib.pystl_b200_last_error())  # warm-up (first use may compile the kernel)
-        for a, b_ in evs:
-            a.record(stream)
-            capi.raise_for(fn(), lib.pystl_b200_last_error())
-            b_.record(stream)
-        torch.cuda.synchronize(dev)
-        return float(np.mean([a.elapsed_time(b_) for a, b_ in evs]))
-
     peak, peak_src = measured_peak_gbs()
-
-    def roof(name, ms_, bytes_per_sample):
-        gbs = bytes_per_sample * B * T / (ms_ * 1e-3) / 1e9
-        return {"kernel": name, "achieved": gbs, "frac": gbs / peak, "algorithmic_bytes_per_sample": bytes_per_sample, "kernel_ms": ms_}
-
-    k_ms = time_kernel(lambda: lib.pystl_b200_eval_forward(cf.ptr(), signal.data_ptr(), B, T, D, out.data_ptr(), None, stream.cuda_stream))
+    traffic = measured_traffic()
+    k_ms = w.time_kernel(lambda: w.forward(None), steps)
     bytes_fwd = algorithmic_bytes_per_sample(cfg, False)
-    fwd_roof = roof(f"{tier}:forward<{sem_name}>", k_ms, bytes_fwd)
-    roofline = {"bound": "hbm", **fwd_roof, "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src}
+    fwd_roof = w.roof("forward", k_ms, bytes_fwd, peak, traffic)
+    roofline = {"bound": "hbm", **fwd_roof, "peak": peak, "unit": "GB/s", "peak_source": peak_src}
     if with_bwd:
-        scale = 1.0 / (world * n_valid)
-        b_ms = time_kernel(lambda: lib.pystl_b200_eval_backward(cf.ptr(), signal.data_ptr(), B, T, D, None, scale, grad.data_ptr(), stream.cuda_stream))
-        bwd_roof = roof(f"{tier}:backward<{sem_name}>", b_ms, algorithmic_bytes_per_sample(cfg, True) - bytes_fwd)
-        if launches_per_step == 1:
+        b_ms = w.time_kernel(lambda: w.backward(scale), steps)
+        bwd_roof = w.roof("backward", b_ms, algorithmic_bytes_per_sample(cfg, True) - bytes_fwd, peak, traffic)
+        if w.launches_per_step == 1:
             # the step's only kernel: reads the signal once, writes the trace and the gradient
-            vg_ms = time_kernel(lambda: lib.pystl_b200_eval_value_and_grad(
-                cf.ptr(), signal.data_ptr(), B, T, D, None, scale, out.data_ptr(), None, grad.data_ptr(), stream.cuda_stream))
-            vg = roof(f"{tier}:value_and_grad<{sem_name}>", vg_ms, bytes_fwd + 4 * D)
+            vg_ms = w.time_kernel(lambda: w.value_and_grad(scale, None), steps)
+            vg = w.roof("value_and_grad", vg_ms, bytes_fwd + 4 * D, peak, traffic)
             roofline = {**roofline, **vg, "other_kernels": [fwd_roof, bwd_roof]}
         else:
             dom, oth = (bwd_roof, fwd_roof) if b_ms > k_ms else (fwd_roof, bwd_roof)
             roofline = {**roofline, **dom, "other_kernels": [oth]}
+    roofline.setdefault("other_kernels", [])
 
-    # end to end through the public API with pinned host buffers
+    # end to end through the public API: the WHOLE batch in pinned host memory, streamed in chunks
+    # (H2D of chunk i+1 and D2H of the gradient of chunk i-1 overlap the kernel of chunk i)
     e2e = None
     if not args.no_e2e:
-        Bh = min(B, max(1, (1 << 28) // (T * D)))  # <= 1 GiB of pinned input per step
-        host = torch.empty((Bh, T, D), dtype=torch.float32).pin_memory()
-        host.copy_(signal[:Bh].cpu())
-        e_steps = max(2, min(args.steps, 5))
-
-        def e2e_step():
-            x = host.to(dev, non_blocking=True)
-            if with_bwd:
-                loss, g_ = sem.mean_robustness_and_grad(phi, x)
-                return float(loss.cpu()), g_
-            return float(sem.mean_robustness(phi, x).cpu()), None
-
         try:
+            host = torch.empty((B, T, D), dtype=torch.float32, pin_memory=True)
+            host.copy_(w.signal)
+            ghost = torch.empty((B, T, D), dtype=torch.float32, pin_memory=True) if with_bwd else None
+            e_steps = max(2, min(steps, 5))
+
+            def e2e_step():
+                mean, _ = w.sem.mean_robustness_and_grad_host(w.phi, host, ghost, device=dev, with_grad=with_bwd)
+                return float(mean.cpu())
+
             e2e_step()
-            torch.cuda.synchronize(dev)
+            barrier()
             t0 = time.perf_counter()
             for _ in range(e_steps):
                 e2e_step()
             torch.cuda.synchronize(dev)
             dt = time.perf_counter() - t0
+            if world > 1:
+                tm = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dt = float(tm.item())
+            h2d = B * T * D * 4
+            d2h = (B * T * D * 4 if with_bwd else 0) + 8
             e2e = {
-                "value": world * Bh * T * e_steps / dt,
+                "value": world * B * T * e_steps / dt,
                 "unit": UNIT,
-                "h2d_bytes_per_step": Bh * T * D * 4,
-                "d2h_bytes_per_step": 8,
-                "traces_per_step": Bh,
+                "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "traces_per_step": B,
+                "ms_per_step": 1e3 * dt / e_steps,
+                "h2d_gbs": h2d * e_steps / dt / 1e9,
+                "d2h_gbs": d2h * e_steps / dt / 1e9,
+                "what": "sem.mean_robustness_and_grad_host: pinned host batch in, mean robustness and (pinned) host gradient out; "
+                        "chunked, copies overlapped with the kernel" if with_bwd else
+                        "sem.mean_robustness_and_grad_host(with_grad=False): pinned host batch in, mean robustness out",
             }
+            del host, ghost
         except NotImplementedError as exc:
             e2e = {"value": None, "unit": UNIT, "error": str(exc)}
+
+    head_plan, head_tier = w.plan, w.tier
+    w.free()
+
+    # every other BASELINE configuration at its named size, same run (kernel-only, a few launches each)
+    if not args.no_others:
+        n_l = 5
+        for key, passes in OTHER_KERNELS:
+            if key == cfg and not args.forward_only and all((p == "value_and_grad") == with_bwd for p in passes):
+                continue  # the headline kernel itself
+            try:
+                ww = Workload(key, default_batch(key), dev, rank, with_bwd=("value_and_grad" in passes))
+                sc = 1.0 / (world * max(ww.n_valid, 1))
+                for ps in passes:
+                    if ps == "forward":
+                        ms_k = ww.time_kernel(lambda: ww.forward(None), n_l)
+                        r = ww.roof("forward", ms_k, algorithmic_bytes_per_sample(key, False), peak, traffic)
+                    else:
+                        if ww.launches_per_step != 1:
+                            ms_k = ww.time_kernel(lambda: (ww.forward(None), ww.backward(sc)), n_l)
+                        else:
+                            ms_k = ww.time_kernel(lambda: ww.value_and_grad(sc, None), n_l)
+                        r = ww.roof("value_and_grad", ms_k, algorithmic_bytes_per_sample(key, False) + 4 * ww.D, peak, traffic)
+                    launches += n_l + 1
+                    roofline["other_kernels"].append(r)
+                ww.free()
+            except Exception as exc:  # a secondary line never fails the bench
+                roofline["other_kernels"].append({"workload": key, "error": f"{type(exc).__name__}: {exc}"[:200]})
+        if world > 1:  # max over ranks of every secondary kernel time
+            t = torch.tensor([r.get("kernel_ms", 0.0) for r in roofline["other_kernels"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            for r, v in zip(roofline["other_kernels"], t.tolist()):
+                if "kernel_ms" in r and v > 0:
+                    k = r["kernel_ms"] / v
+                    r["kernel_ms"] = v
+                    for f in ("achieved", "frac", "samples_per_s"):
+                        r[f] *= k
+
+    # BASELINE config 5 as named: 2^20 traces x 2048 x 8 split over the ranks, NCCL mean reduction
+    sharded = None
+    if not args.no_sharded:
+        sharded = {"scaling": "strong", "total_traces": 1 << 20, "horizon": 2048, "channels": 8, "n_gpus": world,
+                   "note": "forward of every trace + fused mean + one 16-byte NCCL all-reduce per step; device-timed, max over ranks",
+                   "semantics": {}}
+        Bs = (1 << 20) // world
+        n_s = 5
+        for key in ("cfg5", "cfg5s", "cfg5c", "cfg5a", "cfg5d"):
+            try:
+                ww = Workload(key, Bs, dev, rank, with_bwd=False)
+                acs = torch.zeros((n_s + 1, 2), dtype=torch.float64, device=dev)
+
+                def sstep(i):
+                    ww.forward(acs[i].data_ptr())
+                    if world > 1:
+                        pending.append(dist.all_reduce(acs[i], async_op=True))
+
+                sstep(n_s)
+                drain()
+                barrier()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(ww.stream)
+                for i in range(n_s):
+                    sstep(i)
+                drain()
+                b_.record(ww.stream)
+                barrier()
+                t_ms = a.elapsed_time(b_)
+                if world > 1:
+                    tm = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                    t_ms = float(tm.item())
+                launches += n_s + 1
+                bytes_ = algorithmic_bytes_per_sample(key, False)
+                tot = (1 << 20) * 2048
+                sharded["semantics"][ww.sem_name] = {
+                    "value": tot * n_s / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / n_s,
+                    "hbm_frac_per_gpu": bytes_ * tot / world / (t_ms / n_s * 1e-3) / 1e9 / peak,
+                    "mean_robustness": float(acs[0][0].item()) / (world * max(ww.n_valid, 1)),
+                }
+                ww.free()
+            except Exception as exc:
+                sharded["semantics"][key] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     cpu = None
     cpu_vec = None
@@ -528,9 +725,9 @@ def run_b200(args) -> None:
             "value": value,
             "unit": UNIT,
             "n_gpus": world,
-            "steps": args.steps,
-            "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps,
+            "steps": steps,
+            "warmup": warm,
+            "ms_per_step": ms / steps,
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": None,
@@ -543,10 +740,12 @@ def run_b200(args) -> None:
                 "channels": D,
                 "pass": "forward+backward" if with_bwd else "forward",
                 "l2": "inputs larger than L2 (no flush needed)" if B * T * D * 4 > (1 << 28) else "input fits L2 (CPU-comparison config)",
-                "plan": plan,
-                "tier": tier,
+                "plan": head_plan,
+                "tier": head_tier,
+                "mean_robustness_last_step": mean_last,
             },
             "roofline": roofline,
+            "cfg5_sharded": sharded,
             "cpu_baseline": cpu,
             "cpu_baseline_vectorised": cpu_vec,
             "e2e": e2e,
@@ -569,6 +768,8 @@ def main() -> None:
     ap.add_argument("--forward-only", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the kernel lines of the other BASELINE configurations")
+    ap.add_argument("--no-sharded", action="store_true", help="skip BASELINE config 5 at its full sharded size")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -6,8 +6,9 @@ Three entry points of ``include/pystl_b200.h`` become dispatcher ops
     pystl_b200::robustness_grad(signal, grad_out[B, T, C], handle)     -> grad_signal[B, T, D]
     pystl_b200::value_and_grad(signal, scale, handle)                  -> (out, acc[2] float64, grad_signal)
 
-with fake (meta) kernels, an autograd formula for ``robustness`` and batching rules, so that
-``torch.compile`` traces through a robustness evaluation without a graph break and
+with fake (meta) kernels and batching rules; ``evaluate`` -- an ``autograd.Function`` over them with
+``setup_context`` and a ``vmap`` rule -- is the differentiable entry point the semantics objects call,
+so that ``torch.compile`` traces through a robustness evaluation without a graph break and
 ``torch.func.vmap / grad`` compose with it (the precedent is ``jax.vmap`` over the reference's JAX
 backend, tests/test_jax_semantics.py:310-368 of the reference).  A compiled formula
 (``compiler.CompiledFormula``: ctypes arrays, not a tensor) is passed as an integer handle.
@@ -55,8 +56,15 @@ def _check(signal: torch.Tensor) -> None:
         raise ValueError("signal must be float32 with shape (batch, time, state_dim)")
 
 
-@torch.library.custom_op("pystl_b200::robustness", mutates_args=(), device_types="cuda")
-def robustness(signal: torch.Tensor, handle: int) -> torch.Tensor:
+_lib = torch.library.Library("pystl_b200", "DEF")
+_lib.define("robustness(Tensor signal, int handle) -> Tensor")
+_lib.define("robustness_grad(Tensor signal, Tensor grad_out, int handle) -> Tensor")
+_lib.define("value_and_grad(Tensor signal, float scale, int handle) -> (Tensor, Tensor, Tensor)")
+# (the ops are defined with the low-level Library API on purpose: torch.library.custom_op installs a
+# generated autograd.Function on every op, which torch.func.grad refuses to run through in torch 2.11)
+
+
+def _robustness_cuda(signal: torch.Tensor, handle: int) -> torch.Tensor:
     _check(signal)
     cf, C = _lookup(handle)
     sig = signal.contiguous()
@@ -69,14 +77,7 @@ def robustness(signal: torch.Tensor, handle: int) -> torch.Tensor:
     return out
 
 
-@robustness.register_fake
-def _(signal, handle):
-    _, C = _lookup(handle)
-    return signal.new_empty((signal.shape[0], signal.shape[1], C))
-
-
-@torch.library.custom_op("pystl_b200::robustness_grad", mutates_args=(), device_types="cuda")
-def robustness_grad(signal: torch.Tensor, grad_out: torch.Tensor, handle: int) -> torch.Tensor:
+def _robustness_grad_cuda(signal: torch.Tensor, grad_out: torch.Tensor, handle: int) -> torch.Tensor:
     _check(signal)
     cf, C = _lookup(handle)
     sig = signal.contiguous()
@@ -92,13 +93,7 @@ def robustness_grad(signal: torch.Tensor, grad_out: torch.Tensor, handle: int) -
     return grad
 
 
-@robustness_grad.register_fake
-def _(signal, grad_out, handle):
-    return torch.empty_like(signal)
-
-
-@torch.library.custom_op("pystl_b200::value_and_grad", mutates_args=(), device_types="cuda")
-def value_and_grad(signal: torch.Tensor, scale: float, handle: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+def _value_and_grad_cuda(signal: torch.Tensor, scale: float, handle: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Robustness trace, its (sum, 0) accumulator and the gradient of ``scale * sum(valid outputs)``
     in ONE pass over the signal (pystl_b200_eval_value_and_grad)."""
     _check(signal)
@@ -116,26 +111,30 @@ def value_and_grad(signal: torch.Tensor, scale: float, handle: int) -> Tuple[tor
     return out, acc, grad
 
 
-@value_and_grad.register_fake
+_lib.impl("robustness", _robustness_cuda, "CUDA")
+_lib.impl("robustness_grad", _robustness_grad_cuda, "CUDA")
+_lib.impl("value_and_grad", _value_and_grad_cuda, "CUDA")
+robustness = torch.ops.pystl_b200.robustness
+robustness_grad = torch.ops.pystl_b200.robustness_grad
+value_and_grad = torch.ops.pystl_b200.value_and_grad
+
+
+@torch.library.register_fake("pystl_b200::robustness")
+def _(signal, handle):
+    _, C = _lookup(handle)
+    return signal.new_empty((signal.shape[0], signal.shape[1], C))
+
+
+@torch.library.register_fake("pystl_b200::robustness_grad")
+def _(signal, grad_out, handle):
+    return torch.empty_like(signal)
+
+
+@torch.library.register_fake("pystl_b200::value_and_grad")
 def _(signal, scale, handle):
     _, C = _lookup(handle)
     return (signal.new_empty((signal.shape[0], signal.shape[1], C)), signal.new_empty((2,), dtype=torch.float64),
             torch.empty_like(signal))
-
-
-# ---- autograd: d robustness / d signal is the backward entry point of the C ABI
-def _setup_context(ctx, inputs, output):
-    signal, handle = inputs
-    ctx.save_for_backward(signal)
-    ctx.handle = handle
-
-
-def _backward(ctx, grad_out):
-    (signal,) = ctx.saved_tensors
-    return robustness_grad(signal, grad_out, ctx.handle), None
-
-
-torch.library.register_autograd("pystl_b200::robustness", _backward, setup_context=_setup_context)
 
 
 # ---- batching rules: traces are independent, so a vmapped dimension folds into the batch
@@ -160,3 +159,36 @@ def _(info, in_dims, signal, grad_out, handle):
     fg = g.reshape((-1,) + tuple(g.shape[2:]))
     out = robustness_grad(fs, fg, handle)
     return out.reshape((n, -1) + tuple(out.shape[1:])), 0
+
+
+# ---- the differentiable entry point: eager autograd, torch.func.grad / vmap(grad(...)), torch.compile
+class Robustness(torch.autograd.Function):
+    """d robustness / d signal is the backward entry point of the C ABI (pystl_b200_eval_backward)."""
+
+    generate_vmap_rule = False
+
+    @staticmethod
+    def forward(signal, handle):
+        return robustness(signal, handle)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        signal, handle = inputs
+        ctx.save_for_backward(signal)
+        ctx.handle = handle
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (signal,) = ctx.saved_tensors
+        return robustness_grad(signal, grad_out, ctx.handle), None
+
+    @staticmethod
+    def vmap(info, in_dims, signal, handle):
+        flat, n = _fold(signal, in_dims[0])
+        out = Robustness.apply(flat, handle)
+        return out.reshape((n, -1) + tuple(out.shape[1:])), 0
+
+
+def evaluate(signal: torch.Tensor, handle: int) -> torch.Tensor:
+    """Differentiable robustness evaluation of ``signal[B, T, D]`` -> ``out[B, T, C]``."""
+    return Robustness.apply(signal, handle)

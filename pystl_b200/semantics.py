@@ -166,7 +166,7 @@ class _B200Semantics(_ReferenceSemantics):
         cf = self._checked_compile(formula, sig)
         if cf.leaf_preds:  # non-affine predicates: leaf channels computed by torch, inside the graph
             sig = leaf_values(cf, sig)
-        out = ops.robustness(sig, ops.handle_of(cf, self.out_channels))
+        out = ops.evaluate(sig, ops.handle_of(cf, self.out_channels))
         if home != out.device:
             out = out.to(home)
         if squeeze:
@@ -234,6 +234,87 @@ class _B200Semantics(_ReferenceSemantics):
         if home != grad.device:
             grad = grad.to(home)
         return mean, (grad[0] if squeeze else grad)
+
+    def mean_robustness_and_grad_host(self, formula: Any, signal_host: torch.Tensor, grad_host: Optional[torch.Tensor] = None, *,
+                                      chunk_traces: int = 0, device: Optional[torch.device] = None, group=None,
+                                      with_grad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """``mean_robustness_and_grad`` for a batch that lives in HOST memory (pinned for full speed).
+
+        The batch is streamed through the GPU in chunks of traces on three streams: the H2D copy of
+        chunk i+1 and the D2H copy of the gradient of chunk i-1 overlap the kernel of chunk i (two
+        device buffers each), so a step costs max(H2D, kernel, D2H) instead of their sum and the device
+        never holds more than two chunks.  Returns ``(mean, grad_host)``; ``grad_host`` (allocated
+        pinned when not given) holds ``d mean / d signal`` and is complete when the call returns.
+        ``with_grad=False`` streams the forward kernel only (mean robustness)."""
+        from .distributed import all_reduce_count, all_reduce_mean
+
+        sig_h = torch.as_tensor(signal_host)
+        if sig_h.dim() != 3 or sig_h.dtype != torch.float32 or sig_h.is_cuda:
+            raise ValueError("signal_host must be a float32 CPU tensor of shape (batch, time, state_dim)")
+        sig_h = sig_h.contiguous()
+        B, T, D = sig_h.shape
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if not torch.cuda.is_available():
+            raise RuntimeError("the b200 backend needs a CUDA device; there is no CPU fallback")
+        probe = sig_h[:1].to(dev)
+        cf = self._checked_compile(formula, probe)
+        if cf.leaf_preds:
+            raise NotImplementedError("streaming evaluation takes affine predicates only (leaf channels need autograd on the whole batch)")
+        plan = self.plan(formula, T, D, cf)
+        valid = 0 if plan["raises_always"] else max(T - plan["start_slack"], 0)
+        n_local = float(B * valid)
+        n_total = all_reduce_count(n_local, dev, group=group)
+        scale = (1.0 / n_total) if n_total > 0 else 0.0
+        if chunk_traces <= 0:  # about 128 MiB of signal per chunk: long enough to run PCIe at full rate
+            chunk_traces = max(1, min(B, (1 << 27) // max(T * D * 4, 1)))
+        n_chunks = (B + chunk_traces - 1) // chunk_traces if B else 0
+        if with_grad and grad_host is None:
+            grad_host = torch.empty_like(sig_h, pin_memory=True)
+        C_out = self.out_channels
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        bufs = [
+            dict(sig=torch.empty((chunk_traces, T, D), dtype=torch.float32, device=dev),
+                 grad=torch.empty((chunk_traces, T, D), dtype=torch.float32, device=dev) if with_grad else None,
+                 out=torch.empty((chunk_traces, T, C_out), dtype=torch.float32, device=dev),
+                 loaded=torch.cuda.Event(), computed=torch.cuda.Event(), drained=torch.cuda.Event())
+            for _ in range(min(2, max(n_chunks, 1)))
+        ]
+        lib = capi.lib()
+        s_in.wait_stream(cur)
+        with torch.cuda.device(dev):
+            for i in range(n_chunks):
+                b = bufs[i % len(bufs)]
+                lo, hi = i * chunk_traces, min((i + 1) * chunk_traces, B)
+                n = hi - lo
+                with torch.cuda.stream(s_in):
+                    if i >= len(bufs):
+                        s_in.wait_event(b["computed"])  # the kernel that read this buffer has finished
+                    b["sig"][:n].copy_(sig_h[lo:hi], non_blocking=True)
+                    b["loaded"].record(s_in)
+                cur.wait_event(b["loaded"])
+                if with_grad and i >= len(bufs):
+                    cur.wait_event(b["drained"])  # its previous gradient has left for the host
+                if with_grad:
+                    rc = lib.pystl_b200_eval_value_and_grad(cf.ptr(), b["sig"].data_ptr(), n, T, D, None, scale, b["out"].data_ptr(),
+                                                            acc.data_ptr(), b["grad"].data_ptr(), cur.cuda_stream)
+                else:
+                    rc = lib.pystl_b200_eval_forward(cf.ptr(), b["sig"].data_ptr(), n, T, D, b["out"].data_ptr(), acc.data_ptr(),
+                                                     cur.cuda_stream)
+                capi.raise_for(rc, lib.pystl_b200_last_error())
+                b["computed"].record(cur)
+                if with_grad:
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(b["computed"])
+                        grad_host[lo:hi].copy_(b["grad"][:n], non_blocking=True)
+                        b["drained"].record(s_out)
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
+        acc[1] = n_local
+        mean = all_reduce_mean(acc, group=group)
+        cur.synchronize()  # grad_host is complete
+        return mean, grad_host
 
     def evaluate_formula(self, formula: Any, signal: Any, t: int = 0) -> Any:
         """``phi.evaluate(signal, sem, t)`` of the reference, for ``signal[T, D]`` or ``[B, T, D]``."""

@@ -23,7 +23,7 @@ def forward_cases(light: bool = False):
                 if light and (threads == 0) != (cfg == "cfg2"):
                     continue  # CPU tier: one tiling per formula (every kernel costs a g++ compile)
                 out.append(dict(name=f"{cfg}/{sem}{kw.get('p', '')}/nt{threads}", spec=BASELINE_SPECS[cfg], sem=sem, kw=kw, B=3,
-                                T=700, D=2, threads=threads, seed=7, scale=4.0 if sem == "cumulative" else 1.0))
+                                T=700, D=2, threads=threads, seed=7, scale=1.0))
     for wi, (a, b) in enumerate(LONG_WINDOWS):
         spec = ("always", (a, b), ("pred", {0: 1.0}, -0.25))
         for si, (sem, kw) in enumerate(SEM_KW[:4]):
@@ -51,7 +51,7 @@ def forward_cases(light: bool = False):
             continue
         for sem, kw in SEM_KW[:5]:
             out.append(dict(name=f"rand{seed}/{sem}", spec=spec, sem=sem, kw=kw, B=2, T=T, D=D, threads=32 if seed % 2 else 0, seed=3000 + seed,
-                            scale=8.0 if sem == "cumulative" else 2.0))
+                            scale=1.0))
     # until: classic is decomposed into two windows and a clamp scan,
     # the other semantics walk the window with running state
     for cfg, D in (("cfg4", 4), ("cfg5", 8)):
@@ -60,7 +60,7 @@ def forward_cases(light: bool = False):
                 if light and si not in (0, 2):
                     continue
                 out.append(dict(name=f"{cfg}/{sem}/nt{threads}", spec=BASELINE_SPECS[cfg], sem=sem, kw=kw, B=3, T=700, D=D,
-                                threads=threads, seed=11, scale=4.0 if sem == "cumulative" else 1.0))
+                                threads=threads, seed=11, scale=1.0))
     for seed in range(3 if light else 12):
         rng = np.random.default_rng(5000 + seed)
         D = int(rng.integers(1, 4))
@@ -77,7 +77,7 @@ def forward_cases(light: bool = False):
             if light and si != seed % 5:
                 continue
             out.append(dict(name=f"until{seed}/{sem}", spec=spec, sem=sem, kw=kw, B=2, T=T, D=D, threads=64 if seed % 2 else 0,
-                            seed=5100 + seed, scale=8.0 if sem == "cumulative" else 2.0))
+                            seed=5100 + seed, scale=1.0))
     # per-position weights (agm / dgmsr; the other semantics ignore them): windows and until
     wspec = ("or", [
         ("always", (0, 11), ("pred", {0: 1.0}, -0.25), [0.5, 1.0, 2.0, 1.5, 1.0, 0.25, 3.0, 1.0, 0.0, 2.0, 1.0, 0.75]),
@@ -88,15 +88,16 @@ def forward_cases(light: bool = False):
     for sem, kw in (SEM_KW[3:] if not light else SEM_KW[3:5]):
         for threads in ((32,) if light else (0, 32)):
             out.append(dict(name=f"weights/{sem}{kw.get('p', '')}/nt{threads}", spec=wspec, sem=sem, kw=kw, B=3, T=300, D=2, threads=threads,
-                            seed=41, scale=2.0))
+                            seed=41, scale=1.0))
     # a tile that ends EXACTLY at the end of the trace (T = 8 * threads, and T = n * tile + 8 * threads):
     # its last outputs have clipped windows, it is not an "interior" tile for the shared-tail Until paths
     for sem, kw in SEM_KW:
         for T, threads in ((512, 64), (256, 32)) if light else ((512, 64), (256, 32), (2048, 256), (512 + 488, 64)):
             out.append(dict(name=f"tile_end/T{T}/{sem}{kw.get('p', '')}/nt{threads}", spec=BASELINE_SPECS["cfg5"], sem=sem, kw=kw, B=2, T=T, D=8,
-                            threads=threads, seed=53, scale=30.0 if sem == "dgmsr" else 2.0))
-            # (D-GMSR is steep around 0 -- SURVEY.md appendix A10: relative errors up to 6e-5 for |rho| < 1e-3 --
-            # and this 10-node formula composes it four levels deep; a tiling or clipping error would be O(1))
+                            threads=threads, seed=53, scale=1.0))
+            # (every tolerance multiplier of this corpus is 1: the measured worst error / bar over the whole GPU suite is
+            # 0.2, profiles/round2_error_table.md.  The one exception is an ILL-CONDITIONED D-GMSR output of the p = 2
+            # case at T = 1000, admitted by the conditioning rule of parity_util.assert_parity, not by a wider bar.)
     for T in (999, 1001, 1002):
         for sem, kw in (SEM_KW[0], SEM_KW[1]):
             for threads in ((32,) if light else (32, 128, 256)):

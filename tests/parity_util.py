@@ -38,7 +38,22 @@ def scale_cap(scale: float) -> float:
     return min(scale, float(cap)) if cap else scale
 
 
-def assert_parity(got: np.ndarray, want64: np.ndarray, sem: str, what: str = "", scale: float = 1.0) -> None:
+def conditioning_slack(spec, sem: str, kw: dict, sig64: np.ndarray, b: int, t: int, c: int = 0) -> float:
+    """First-order bound on how far the REFERENCE's own value at (b, t) moves when every input sample
+    is rounded to fp32: sum_j |d out / d x_j| * ulp32(x_j) / 2, by autograd through the float64 oracle."""
+    x = torch.tensor(sig64[b : b + 1], requires_grad=True)
+    out = dense.robustness_trace(from_spec(spec), x, dense.make(sem, **kw))
+    o = out[c, 0, t] if sem == "cumulative" else out[0, t]
+    (g,) = torch.autograd.grad(o, x)
+    ulp = np.spacing(np.abs(sig64[b]).astype(np.float32)).astype(np.float64)
+    return float((g[0].abs().numpy() * ulp * 0.5).sum())
+
+
+def assert_parity(got: np.ndarray, want64: np.ndarray, sem: str, what: str = "", scale: float = 1.0, ill=None) -> None:
+    """``ill = (spec, kw, sig64)`` admits ILL-CONDITIONED outputs: an entry outside the bar passes when the
+    reference's own value there moves by more than 1 / 64 of the miss under fp32 rounding of the inputs
+    (``conditioning_slack``: D-GMSR composed four levels deep is that steep where an operand is ~ 1e-5,
+    SURVEY.md appendix A10); at most 4 such entries per comparison."""
     scale = scale_cap(scale)
     assert got.shape == want64.shape, (what, got.shape, want64.shape)
     assert np.array_equal(np.isnan(got), np.isnan(want64)), f"{what}: NaN pattern differs"
@@ -53,6 +68,14 @@ def assert_parity(got: np.ndarray, want64: np.ndarray, sem: str, what: str = "",
         parity_log("value", what, sem, float(np.nanmax(np.where(np.isnan(want64), 0.0, err / (ATOL + RTOL * np.abs(want64))), initial=0.0)), scale)
     bad = err > tol
     bad &= ~np.isnan(want64)
+    if bad.any() and ill is not None and int(bad.sum()) <= 4:
+        spec, kw, sig64 = ill
+        for idx in np.argwhere(bad):
+            b, t = int(idx[0]), int(idx[1])
+            slack = conditioning_slack(spec, sem, kw, sig64, b, t, int(idx[2]) if len(idx) > 2 else 0)
+            parity_log("ill-conditioned", f"{what}@{b},{t}", sem, float(err[tuple(idx)] / max(slack, 1e-300)), scale)
+            if err[tuple(idx)] <= tol[tuple(idx)] + 64.0 * slack:
+                bad[tuple(idx)] = False
     assert not bad.any(), (
         f"{what}: {int(bad.sum())} of {bad.size} values off; worst abs err {np.nanmax(err):.3e} "
         f"at want={want64.flat[np.nanargmax(err)]:.6g}"

@@ -18,7 +18,8 @@ def test_forward(case):
     sig = case_signal(case)
     want = oracle_trace(case["spec"], case["sem"], case["kw"], sig)
     got = fused_emu_lib.eval_forward(from_spec(case["spec"]), case["sem"], sig, force_threads=case["threads"], **case["kw"])
-    assert_parity(got, want, case["sem"], case["name"], scale=case["scale"])
+    ill = (case["spec"], case["kw"], sig) if case["sem"] == "dgmsr" else None
+    assert_parity(got, want, case["sem"], case["name"], scale=case["scale"], ill=ill)
 
 
 # ---------------------------------------------------------------------------- backward
@@ -76,7 +77,7 @@ def test_cumulative_backward(case):
     B, T = sig.shape[:2]
     g = rng.standard_normal((B, T, 2)).astype(np.float32).astype(np.float64)
     got = fused_emu_lib.eval_backward(from_spec(case["spec"]), "cumulative", sig, g, force_threads=case["threads"])
-    check(got.astype(np.float64), oracle_grad(case["spec"], "cumulative", {}, sig, g), "cumulative", case["name"], 4e-5, 4e-5)
+    check(got.astype(np.float64), oracle_grad(case["spec"], "cumulative", {}, sig, g), "cumulative", case["name"], 4e-5, 4e-5)  # (twice the bar: scatter-sums, see test_gpu_fused.CUM_GTOL)
 
 
 from fused_cases import smooth_until_backward_cases  # noqa: E402
@@ -108,7 +109,7 @@ def test_agm_dgmsr_until_and_weighted_backward(case):
     rng = np.random.default_rng(case["seed"] + 1)
     g = rng.standard_normal(sig.shape[:2]).astype(np.float32).astype(np.float64)
     got = fused_emu_lib.eval_backward(from_spec(case["spec"]), case["sem"], sig, g, force_threads=case["threads"], **case["kw"]).astype(np.float64)
-    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"], 4e-5, 4e-5)
+    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"])
 
 
 # ---------------------------------------------------------------------------- classic gradient (fused tier)

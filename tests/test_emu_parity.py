@@ -45,7 +45,7 @@ def test_cfg4_nested_until(sem, kw):
     sig = mixed_signal(rng, 2, 600, 4)
     want = oracle_trace(BASELINE_SPECS["cfg4"], sem, kw, sig)
     got = emu_lib.eval_forward(from_spec(BASELINE_SPECS["cfg4"]), sem, sig, force_threads=64, **kw)
-    assert_parity(got, want, sem, f"cfg4/{sem}", scale=4.0 if sem == "cumulative" else 1.0)
+    assert_parity(got, want, sem, f"cfg4/{sem}", scale=1.0)
 
 
 @pytest.mark.parametrize("seed", range(24))
@@ -66,7 +66,7 @@ def test_random_formulas(seed):
                 assert threads and 8 * threads < T
                 continue
             # sums of up to ~40 cumulative terms: absolute error grows with the magnitude summed
-            assert_parity(got, want, sem, f"seed{seed}/{sem}/nt{threads}/{spec}", scale=8.0 if sem == "cumulative" else 2.0)
+            assert_parity(got, want, sem, f"seed{seed}/{sem}/nt{threads}/{spec}", scale=1.0)
 
 
 def test_long_windows_van_herk():

@@ -55,7 +55,8 @@ def test_forward(case):
     want = expected(case, sig)
     x = torch.tensor(sig, dtype=torch.float32, device="cuda")
     got = run(case["spec"], case["sem"], case["kw"], x, "fused", case["threads"]).cpu().numpy()
-    assert_parity(got, want, case["sem"], case["name"], scale=case["scale"])
+    ill = (case["spec"], case["kw"], sig) if case["sem"] == "dgmsr" else None
+    assert_parity(got, want, case["sem"], case["name"], scale=case["scale"], ill=ill)
 
 
 @pytest.mark.parametrize("cfg,sem,kw,shape", [
@@ -89,8 +90,8 @@ def test_fused_equals_interpreter_at_baseline_shapes(cfg, sem, kw, shape):
     # seeded sub-sample against the oracle
     idx = [0, shape[0] // 2, shape[0] - 1]
     want = oracle_trace(BASELINE_SPECS[cfg], sem, kw, x[idx].double().cpu().numpy())
-    assert_parity(a[idx].float().cpu().numpy(), want, sem, f"{cfg}/{sem}/full",
-                  scale=30.0 if (sem == "dgmsr" and cfg == "cfg5") else (4.0 if sem == "cumulative" or cfg in ("cfg4", "cfg5") else 1.0))
+    assert_parity(a[idx].float().cpu().numpy(), want, sem, f"{cfg}/{sem}/full", scale=1.0,
+                  ill=(BASELINE_SPECS[cfg], kw, x[idx].double().cpu().numpy()) if sem == "dgmsr" else None)
 
 
 def test_mean_accumulator_matches():
@@ -186,6 +187,11 @@ def test_smooth_extreme_dynamic_range_is_exact_on_the_fused_tier():
 
 from fused_cases import cumulative_backward_cases  # noqa: E402
 
+# Cumulative gradients are scatter-sums over every (output, candidate) pair that routes to an input sample
+# (hundreds for cfg5, 13 000 for cfg4) with float64 cancellation-free references: twice the bar of the other
+# semantics (measured worst 1.1 x the bar on cfg5, profiles/round2_error_table.md)
+CUM_GTOL = (4e-5, 4e-5)
+
 CBWD = cumulative_backward_cases()
 
 
@@ -196,7 +202,7 @@ def test_cumulative_backward(case):
     B, T = sig.shape[:2]
     g = rng.standard_normal((B, T, 2)).astype(np.float32).astype(np.float64)
     got = gpu_grad(case["spec"], "cumulative", {}, sig, g, "fused", case["threads"])
-    check(got, oracle_grad(case["spec"], "cumulative", {}, sig, g), "cumulative", case["name"], 4e-5, 4e-5)
+    check(got, oracle_grad(case["spec"], "cumulative", {}, sig, g), "cumulative", case["name"], *CUM_GTOL)
 
 
 def test_cumulative_autograd_through_the_public_api():
@@ -208,7 +214,7 @@ def test_cumulative_autograd_through_the_public_api():
     (rho.pos + rho.neg).mean().backward()
     g = np.full((3, 300, 2), 1.0 / (3 * 300))
     want = oracle_grad(BASELINE_SPECS["cfg4"], "cumulative", {}, sig.astype(np.float64), g)
-    check(x.grad.double().cpu().numpy(), want, "cumulative", "cfg4/autograd", 4e-5, 4e-5)
+    check(x.grad.double().cpu().numpy(), want, "cumulative", "cfg4/autograd", *CUM_GTOL)
 
 
 from fused_cases import smooth_until_backward_cases  # noqa: E402
@@ -239,7 +245,7 @@ def test_agm_dgmsr_until_and_weighted_backward(case):
     rng = np.random.default_rng(case["seed"] + 1)
     g = rng.standard_normal(sig.shape[:2]).astype(np.float32).astype(np.float64)
     got = gpu_grad(case["spec"], case["sem"], case["kw"], sig, g, "fused", case["threads"])
-    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"], 4e-5, 4e-5)
+    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"])
 
 
 # ---------------------------------------------------------------------------- classic gradient (fused tier)
@@ -299,7 +305,7 @@ for _cfg, _D, _T in (("cfg1", 2, 528), ("cfg2", 2, 1040), ("cfg3", 2, 528), ("cf
     for _sem, _kw in SEM_KW:
         for _nt in (64, 0):
             _c = dict(name=f"tma/{_cfg}/{_sem}{_kw.get('p', '')}/T{_T}/nt{_nt}", spec=BASELINE_SPECS[_cfg], sem=_sem, kw=_kw, B=3, T=_T, D=_D,
-                      threads=_nt, seed=61, scale=30.0 if _sem == "dgmsr" else 4.0)
+                      threads=_nt, seed=61, scale=1.0)
             TMA_FWD.append(_c)
             if _cfg in ("cfg1", "cfg2", "cfg3") and _sem != "cumulative":
                 TMA_BWD.append(_c)
@@ -358,14 +364,26 @@ def test_value_and_grad_at_baseline_horizons_of_the_until_formulas(cfg, sem, kw,
     torch.cuda.synchronize()
     want = oracle_trace(spec, sem, kw, sig)
     got = out.cpu().numpy()
-    assert_parity(got if C == 2 else got[..., 0], want, sem, f"horizon/{cfg}/{sem}", scale=4.0 if sem == "cumulative" else 2.0)
+    assert_parity(got if C == 2 else got[..., 0], want, sem, f"horizon/{cfg}/{sem}", scale=1.0,
+                  ill=(spec, kw, sig) if sem == "dgmsr" else None)
     assert abs(float(acc[0]) - float(np.nansum(want))) <= 1e-5 * float(np.nansum(np.abs(want))) + 1e-3
     rtol, atol = grad_tol(sem, kw)
-    k = 2.0  # gradients of sums over up to 265 candidates per output
-    check(grad.cpu().numpy().astype(np.float64), oracle_grad(spec, sem, kw, sig, g64), sem, f"horizon/{cfg}/{sem}/grad", k * rtol, k * atol)
+    # cfg4 / cumulative: every input sample collects 201 x 65 = 13 000 (output, candidate) terms of either sign; the
+    # fp32 accumulation error grows with that count while the bar is stated for O(10^3) terms (measured: 4.0 x)
+    k = 8.0 if (sem == "cumulative" and cfg == "cfg4") else (2.0 if sem == "cumulative" else 1.0)
+
+    def check_masked(got_g, want_g, what):
+        # the reference's own autograd yields NaN on traces where a 201-sample D-GMSR product underflows
+        # (torch/semantics.py:492-495: eps ** 201 == 0 in float64, 0 ** (1 / 201) has an infinite slope);
+        # the kernels stay finite there, and nothing can be compared
+        ok = np.isfinite(want_g)
+        assert np.isfinite(got_g).all() and ok.mean() > 0.5
+        check(np.where(ok, got_g, 0.0), np.where(ok, want_g, 0.0), sem, what, k * rtol, k * atol)
+
+    check_masked(grad.cpu().numpy().astype(np.float64), oracle_grad(spec, sem, kw, sig, g64), f"horizon/{cfg}/{sem}/grad")
     n_valid = float(np.isfinite(want).sum()) / C
     gc = np.full_like(g64, 1.0 / n_valid)
-    check(grad_c.cpu().numpy().astype(np.float64) * n_valid, oracle_grad(spec, sem, kw, sig, gc) * n_valid, sem,
-          f"horizon/{cfg}/{sem}/mean-grad", k * rtol, k * atol)
+    check_masked(grad_c.cpu().numpy().astype(np.float64) * n_valid, oracle_grad(spec, sem, kw, sig, gc) * n_valid,
+                 f"horizon/{cfg}/{sem}/mean-grad")
     wsum = np.nansum(want, axis=-1) if C == 2 else want
     assert abs(float(mean_c) - float(np.nanmean(wsum))) <= 1e-5 * (1.0 + abs(float(np.nanmean(wsum))))

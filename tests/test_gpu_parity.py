@@ -60,7 +60,7 @@ def test_baseline_formulas(cfg, sem, kw):
     want = oracle_trace(BASELINE_SPECS[cfg], sem, kw, sig)
     for threads in (0, 64):
         got = gpu_trace(BASELINE_SPECS[cfg], sem, kw, sig, threads)
-        assert_parity(got, want, sem, f"{cfg}/{sem}/nt{threads}", scale=4.0 if sem == "cumulative" else 1.0)
+        assert_parity(got, want, sem, f"{cfg}/{sem}/nt{threads}", scale=1.0)
 
 
 @pytest.mark.parametrize("seed", range(24))
@@ -78,7 +78,7 @@ def test_random_formulas(seed):
             except NotImplementedError:
                 assert threads and 8 * threads < T
                 continue
-            assert_parity(got, want, sem, f"seed{seed}/{sem}/nt{threads}/{spec}", scale=8.0 if sem == "cumulative" else 2.0)
+            assert_parity(got, want, sem, f"seed{seed}/{sem}/nt{threads}/{spec}", scale=1.0)
 
 
 def test_long_windows_van_herk():
