@@ -15,6 +15,10 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
 
 #include "../../include/pystl_b200.h"
 #include "fused_host.h"
@@ -110,6 +114,94 @@ static int fused_prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t
   return PYSTL_OK;
 }
 
+// ---------------------------------------------------------------------- prepared launches
+// Lowering a formula, choosing the geometry, generating the kernel source and hashing it cost tens of
+// microseconds per call -- more than the kernel of a small launch (cfg1: 29 us).  A call is therefore
+// keyed by the BYTES of everything that determines the launch except the buffers and the batch size:
+// the formula (structure and numerics), T, D, the pass, the device and the experiment switches.  The
+// entry holds the lowered program, the geometry, the loaded kernel and the last tensor maps that were
+// encoded, so a steady-state call is one hash lookup and one cudaLaunchKernel (and nothing in it
+// synchronises or allocates: the path can be captured into a CUDA graph).
+struct Prepared {
+  int rc = PYSTL_OK;  // PYSTL_E_UNSUPPORTED: this formula runs on the interpreter tier
+  std::string err;
+  Lowered lw;
+  TileGeom g;  // B = 1, no tensor maps
+  std::string name;
+  int smem_floats = 0;
+  FusedSource fs;        // kept until the kernel is loaded
+  FusedKernel fk;        // loaded on the first launch (planning and precompiling need no GPU)
+  bool loaded = false;
+  std::mutex mu;         // guards fk / loaded and the tensor-map memos
+  const void* ld_ptr = nullptr;
+  int64_t ld_B = -1;
+  int ld_use = 0;
+  unsigned long long ld_map[16];
+  const void* st_ptr = nullptr;
+  int64_t st_B = -1;
+  int st_use = 0, st_rows = 0, st_nbox = 0;
+  unsigned long long st_map[16];
+};
+static std::mutex g_prep_mu;
+static std::unordered_map<std::string, std::shared_ptr<Prepared>> g_prep;
+static const char* const kKnobs[] = {"PYSTL_B200_FORCE_THREADS", "PYSTL_B200_FUSED_MINB", "PYSTL_B200_FUSED_REGS", "PYSTL_B200_FUSED_REGS_BWD",
+                                     "PYSTL_B200_PREFETCH",      "PYSTL_B200_MERGE",      "PYSTL_B200_NVRTC_FLAGS", "PYSTL_B200_TMA",
+                                     "PYSTL_B200_TMA_STORE",     "PYSTL_B200_CACHE"};
+
+template <class X>
+static void key_put(std::string* k, const X* p, size_t n) {
+  if (p && n) k->append(reinterpret_cast<const char*>(p), n * sizeof(X));
+  k->push_back('|');
+}
+static bool prepared_key(const pystl_formula_t* f, int64_t T, int32_t D, bool backward, std::string* k) {
+  if (!f || f->n_nodes < 0 || f->n_children < 0 || f->n_preds < 0 || f->n_weights < 0) return false;
+  if ((f->n_nodes && !f->nodes) || (f->n_children && !f->children) || (f->n_preds && !f->preds) || (f->n_weights && !f->weights)) return false;
+  k->reserve(512);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int64_t head[8] = {f->semantics, f->p, f->n_nodes, f->n_children, T, D, backward ? 1 : 0, dev};
+  key_put(k, head, 8);
+  key_put(k, &f->temperature, 1);
+  key_put(k, &f->eps, 1);
+  key_put(k, f->nodes, (size_t)f->n_nodes);
+  key_put(k, f->children, (size_t)f->n_children);
+  key_put(k, f->preds, (size_t)f->n_preds);
+  key_put(k, f->weights, (size_t)f->n_weights);
+  for (const char* name : kKnobs) {
+    const char* e = getenv(name);
+    if (e) k->append(e);
+    k->push_back('|');
+  }
+  return true;
+}
+
+// the prepared launch of (formula, T, D, pass); built on a miss.  Never null.
+static std::shared_ptr<Prepared> fused_prepared(const pystl_formula_t* f, int64_t T, int32_t D, bool backward) {
+  std::string key;
+  const bool cacheable = prepared_key(f, T, D, backward, &key);
+  if (cacheable) {
+    std::lock_guard<std::mutex> lk(g_prep_mu);
+    auto it = g_prep.find(key);
+    if (it != g_prep.end()) return it->second;
+  }
+  auto p = std::make_shared<Prepared>();
+  p->rc = fused_prepare(f, 1, T, D, backward, &p->lw, &p->g, &p->fs);
+  if (p->rc) {
+    p->err = g_err;
+    p->fs = FusedSource();
+  } else {
+    p->name = p->fs.name;
+    p->smem_floats = p->fs.smem_floats;
+  }
+  if (cacheable) {
+    std::lock_guard<std::mutex> lk(g_prep_mu);
+    // (a training loop that moves a threshold makes a new key every step: bound the table)
+    if (g_prep.size() >= 1024) g_prep.clear();
+    g_prep[key] = p;
+  }
+  return p;
+}
+
 // D == 2: describe the signal as rows of 64 bytes for the TMA tile load of the fused kernels
 // (fused_rt.cuh: load_rows_tma).  The launch qualifies when every tile starts on a 64-byte row
 // (tile origins are multiples of 8 samples = 64 bytes; the trace stride T * D * 4 must be one too),
@@ -193,16 +285,57 @@ static void fused_tma_setup_store(TileGeom* g, float* grad_signal, int sem) {
   g->use_tma_st = 1;
 }
 
-static int fused_launch(const Lowered& lw, const TileGeom& g, const FusedSource& fs, void** args, cudaStream_t stream) {
-  FusedKernel fk;
-  int rc = fused_jit_get(fs, &fk, g_err, sizeof(g_err));
-  if (rc) return rc;
+static int fused_launch(Prepared& p, const TileGeom& g, void** args, cudaStream_t stream) {
+  void* kernel = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(p.mu);
+    if (!p.loaded) {
+      int rc = fused_jit_get(p.fs, &p.fk, g_err, sizeof(g_err));
+      if (rc) return rc;
+      p.loaded = true;
+      p.fs.source.clear();
+      p.fs.source.shrink_to_fit();
+    }
+    kernel = p.fk.kernel;
+  }
   if (g.B > 0x7fffffffLL || g.n_tiles > 65535) return set_err(PYSTL_E_UNSUPPORTED, "grid of %lld x %d tiles is too large", (long long)g.B, g.n_tiles);
-  cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(fk.kernel), dim3((unsigned)g.B, (unsigned)g.n_tiles), dim3((unsigned)g.nt), args,
-                                   (size_t)fs.smem_floats * 4, stream);
+  cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(kernel), dim3((unsigned)g.B, (unsigned)g.n_tiles), dim3((unsigned)g.nt), args,
+                                   (size_t)p.smem_floats * 4, stream);
   if (e != cudaSuccess) return set_err(PYSTL_E_CUDA, "fused kernel launch: %s", cudaGetErrorString(e));
-  (void)lw;
   return PYSTL_OK;
+}
+
+// this call's geometry: the prepared one with the batch size and the tensor maps of these buffers
+// (the maps are re-encoded only when a buffer or the batch size changes)
+static void fused_bind(Prepared& p, int64_t B, const float* signal, float* grad_signal, TileGeom* g) {
+  *g = p.g;
+  g->B = B;
+  std::lock_guard<std::mutex> lk(p.mu);
+  if (p.ld_ptr != signal || p.ld_B != B) {
+    fused_tma_setup(g, signal, p.lw.prog.sem);
+    p.ld_ptr = signal;
+    p.ld_B = B;
+    p.ld_use = g->use_tma;
+    memcpy(p.ld_map, g->tmap, sizeof(p.ld_map));
+  } else {
+    g->use_tma = p.ld_use;
+    if (p.ld_use) memcpy(g->tmap, p.ld_map, sizeof(p.ld_map));
+  }
+  if (!grad_signal) return;
+  if (p.st_ptr != grad_signal || p.st_B != B) {
+    fused_tma_setup_store(g, grad_signal, p.lw.prog.sem);
+    p.st_ptr = grad_signal;
+    p.st_B = B;
+    p.st_use = g->use_tma_st;
+    p.st_rows = g->st_rows;
+    p.st_nbox = g->st_nbox;
+    memcpy(p.st_map, g->tmap_st, sizeof(p.st_map));
+  } else {
+    g->use_tma_st = p.st_use;
+    g->st_rows = p.st_rows;
+    g->st_nbox = p.st_nbox;
+    if (p.st_use) memcpy(g->tmap_st, p.st_map, sizeof(p.st_map));
+  }
 }
 
 // Compile the fused kernel of (formula, T, D) into the on-disk cache; needs no GPU.
@@ -281,14 +414,17 @@ extern "C" int pystl_b200_eval_forward(const pystl_formula_t* f, const float* si
   int rc;
   const int tier = tier_mode();
   if (tier != TIER_INTERP) {
-    FusedSource fs;
-    rc = fused_prepare(f, B, T, D, false, &lw, &g, &fs);
+    if (B < 0) return set_err(PYSTL_E_INVALID, "bad shape");
+    std::shared_ptr<Prepared> p = fused_prepared(f, T, D, false);
+    rc = p->rc;
     if (rc == PYSTL_OK) {
       if (B == 0 || T == 0) return PYSTL_OK;
       if (!signal || !out) return set_err(PYSTL_E_INVALID, "signal / out is NULL");
-      fused_tma_setup(&g, signal, lw.prog.sem);
-      void* args[] = {(void*)&lw.prog, (void*)&g, (void*)&signal, (void*)&out, (void*)&mean_acc};
-      rc = fused_launch(lw, g, fs, args, reinterpret_cast<cudaStream_t>(stream));
+      fused_bind(*p, B, signal, nullptr, &g);
+      void* args[] = {(void*)&p->lw.prog, (void*)&g, (void*)&signal, (void*)&out, (void*)&mean_acc};
+      rc = fused_launch(*p, g, args, reinterpret_cast<cudaStream_t>(stream));
+    } else {
+      snprintf(g_err, sizeof(g_err), "%s", p->err.c_str());
     }
     if (rc != PYSTL_E_UNSUPPORTED || tier == TIER_FUSED) return rc;
   }
@@ -312,18 +448,19 @@ extern "C" int pystl_b200_eval_forward(const pystl_formula_t* f, const float* si
 static int fused_value_and_grad(const pystl_formula_t* f, const float* signal, int64_t B, int64_t T, int32_t D,
                                 const float* grad_out, float grad_scale, float* grad_signal, float* out, double* mean_acc,
                                 cudaStream_t stream) {
-  Lowered lw;
-  TileGeom g;
-  FusedSource fs;
-  int rc = fused_prepare(f, B, T, D, true, &lw, &g, &fs);
-  if (rc) return rc;
+  if (B < 0) return set_err(PYSTL_E_INVALID, "bad shape");
+  std::shared_ptr<Prepared> p = fused_prepared(f, T, D, true);
+  if (p->rc) {
+    snprintf(g_err, sizeof(g_err), "%s", p->err.c_str());
+    return p->rc;
+  }
   if (B == 0 || T == 0) return PYSTL_OK;
   if (!signal || !grad_signal) return set_err(PYSTL_E_INVALID, "signal / grad_signal is NULL");
-  fused_tma_setup(&g, signal, lw.prog.sem);
-  fused_tma_setup_store(&g, grad_signal, lw.prog.sem);
-  void* args[] = {(void*)&lw.prog, (void*)&g,           (void*)&signal, (void*)&grad_out,
+  TileGeom g;
+  fused_bind(*p, B, signal, grad_signal, &g);
+  void* args[] = {(void*)&p->lw.prog, (void*)&g,           (void*)&signal, (void*)&grad_out,
                   (void*)&grad_scale, (void*)&grad_signal, (void*)&out,    (void*)&mean_acc};
-  return fused_launch(lw, g, fs, args, stream);
+  return fused_launch(*p, g, args, stream);
 }
 
 extern "C" int pystl_b200_eval_backward(const pystl_formula_t* f, const float* signal, int64_t B, int64_t T, int32_t D,
