@@ -88,9 +88,12 @@ struct Gen {
   int red_floats = 0;
   int n_stages = 0;
   bool bwd = false;                // generating the backward kernel
+  int fold_root = -1;              // backward: the root n-ary whose adjoint is folded into its forward loop (no partial arrays)
   std::vector<int> bscr_off;       // per instruction: scratch of the adjoint window
-  int fix_off = 0, flag_off = 0;   // smooth backward: exact-scatter plane, per-window lost flags
+  int flag_off = 0;                // smooth backward: per-window lost flags
+  std::vector<int> fix_off;        // smooth backward: per window, the exact-scatter plane (aliases the dead forward scratch of its level)
   int sp_off = 0;                  // cumulative backward: four scatter planes
+  std::vector<int> hand_off, aux_off;  // lockstep until adjoints: hand-off planes (dead forward scratch of the level) / staged operands (the other region)
   int stage_off = 0;               // cooperative row staging (aliases the scratch regions)
   bool coop_stage() const { return D >= 4 && D <= 8; }
   // D == 2: the kernel can take its tile through one TMA tensor copy (run-time flag TileGeom::use_tma)
@@ -112,6 +115,13 @@ struct Gen {
     return false;
   }
   bool arg_window(const TInstr& in) const { return cum_bwd() && is_window(in) && in.mode != MODE_SUM; }
+  // Until adjoints on the lockstep shared-tail walk (fused_rt.cuh: smooth_until_adj_walk, agm_until_adj_walk)
+  bool lockstep_adj(const TInstr& in) const {
+    if (!bwd || !is_until(in)) return false;
+    return P.sem == SEM_SMOOTH || (P.sem == SEM_AGM && in.w_off < 0 && in.w2_off < 0 && in.a <= 64);
+  }
+  int hand_planes() const { return P.sem == SEM_SMOOTH ? 2 : 3; }
+  int aux_floats() const { return P.sem == SEM_SMOOTH ? 2 * 8 * nt + roundup(nt, 32) : 2 * roundup(nt, 32); }
 
   Gen(const Lowered& l, int D_, int nt_, int minb_, bool bwd_) : lw(l), P(l.prog), D(D_), nt(nt_), minb(minb_), bwd(bwd_) {}
   int kw() const { return P.sem == SEM_SMOOTH ? 1 : 2; }  // words of an adjoint coefficient
@@ -173,8 +183,6 @@ struct Gen {
           stash_off[i] = red_floats + persist;
           persist += 8 * nt;
         }
-      fix_off = red_floats + persist;
-      persist += 8 * nt;
       flag_off = red_floats + persist;
       persist += roundup(P.n_instr, 4);
     }
@@ -186,8 +194,12 @@ struct Gen {
       persist += src_image() ? 8 * nt * D : P.n_preds * 8 * nt;
     }
     if (cum_bwd() || (bwd && has_until())) {
-      sp_off = red_floats + persist;
-      persist += 4 * 8 * nt;
+      bool need_sp = cum_bwd();  // scatter planes of the cumulative adjoints and of the per-output until adjoints
+      for (int i = 0; i < P.n_instr; ++i) need_sp |= is_until(P.ins[i]) && !lockstep_adj(P.ins[i]);
+      if (need_sp) {
+        sp_off = red_floats + persist;
+        persist += 4 * 8 * nt;
+      }
       for (int i = 0; i < P.n_instr; ++i)
         if (is_until(P.ins[i])) {  // the adjoint re-reads the staged operands
           scr_off[i] = red_floats + persist;
@@ -236,7 +248,30 @@ struct Gen {
       reg[l & 1] = std::max(reg[l & 1], used[l]);
       reg[(l + 1) & 1] = std::max(reg[(l + 1) & 1], bused[l]);
     }
+    // smooth backward: the exact scatter of a window of level l (rare path of its adjoint) needs one plane; the
+    // forward scratch of that level (region l & 1) is dead by then and the adjoint windows live in the other region
+    fix_off.assign(P.n_instr, 0);
+    if (stash_persists)
+      for (int i = 0; i < P.n_instr; ++i)
+        if (is_window(P.ins[i])) reg[ins_level[i] & 1] = std::max(reg[ins_level[i] & 1], 8 * nt);
+    // lockstep until adjoints of level l: the hand-off planes take the dead forward scratch of that level (region
+    // l & 1); the staged operands take the other region, which the adjoint windows of level l only fill afterwards
+    hand_off.assign(P.n_instr, 0);
+    aux_off.assign(P.n_instr, 0);
+    for (int i = 0; i < P.n_instr; ++i)
+      if (lockstep_adj(P.ins[i])) {
+        const int l = ins_level[i];
+        reg[l & 1] = std::max(reg[l & 1], hand_planes() * 8 * nt);
+        reg[(l + 1) & 1] = std::max(reg[(l + 1) & 1], aux_floats());
+      }
     const int base0 = red_floats + persist, base1 = base0 + reg[0];
+    for (int i = 0; i < P.n_instr; ++i) {
+      if (is_window(P.ins[i])) fix_off[i] = (ins_level[i] & 1) ? base1 : base0;
+      if (lockstep_adj(P.ins[i])) {
+        hand_off[i] = (ins_level[i] & 1) ? base1 : base0;
+        aux_off[i] = ((ins_level[i] + 1) & 1) ? base1 : base0;
+      }
+    }
     for (int i = 0; i < P.n_instr; ++i) {
       if (is_scan(P.ins[i]) || is_wwin(P.ins[i]) || (is_until(P.ins[i]) && !bwd)) scr_off[i] += (ins_level[i] & 1) ? base1 : base0;
       if (is_wwin(P.ins[i])) bscr_off[i] += ((ins_level[i] + 1) & 1) ? base1 : base0;
@@ -247,12 +282,11 @@ struct Gen {
       bscr_off[i] += ((l + 1) & 1) ? base1 : base0;
     }
     smem_floats = base1 + reg[1];
-    if (coop_stage()) {  // staging area of the signal rows: shares storage with the scratch regions
-      stage_off = base0;
-      smem_floats = std::max(smem_floats, base0 + 8 * nt * D);
-    }
-    if (tma_capable()) {  // the same, 1024-byte aligned for the swizzled TMA box
-      stage_off = roundup(base0, 256);
+    // staging area of the signal rows (cooperative loads, TMA box; the TMA store of the gradient rows at the very
+    // end): nothing else is alive in shared memory at either time except the reduction scratch, so it starts right
+    // behind that (1024-byte aligned for the swizzled TMA box)
+    if (coop_stage() || tma_capable()) {
+      stage_off = roundup(red_floats, 256);
       smem_floats = std::max(smem_floats, stage_off + 8 * nt * D);
     }
   }
@@ -335,9 +369,14 @@ struct Gen {
           o.line("a = fma((double)P.preds[%d].coeff[%d], (double)%s, a);", q, k, term(k).c_str());
         o.line("const float acc = (float)(a + (double)P.preds[%d].bias);", q);
       } else {
-        o.line("float acc = 0.f;");
-        for (int k = 0; k < pr.n_terms; ++k) o.line("acc = fmaf(P.preds[%d].coeff[%d], %s, acc);", q, k, term(k).c_str());
-        o.line("acc += P.preds[%d].bias;", q);
+        // (coeff * x + bias in ONE rounding for a single term: what "+-x + c" needs to match the reference bit for bit)
+        if (pr.n_terms == 1) {
+          o.line("const float acc = fmaf(P.preds[%d].coeff[0], %s, P.preds[%d].bias);", q, term(0).c_str(), q);
+        } else {
+          o.line("float acc = 0.f;");
+          for (int k = 0; k < pr.n_terms; ++k) o.line("acc = fmaf(P.preds[%d].coeff[%d], %s, acc);", q, k, term(k).c_str());
+          o.line("acc += P.preds[%d].bias;", q);
+        }
       }
       if (P.sem == SEM_CUMULATIVE) o.line("v%d[i] = V{{fmaxf(0.f, acc), fminf(0.f, acc)}};  // cumulative.py:29-30", (int)pr.dst);
       else if (src_bwd()) o.line("v%d[i] = V{{acc, i2f(%d | (c.p0 + i))}};  // source: predicate << 24 | tile position", (int)pr.dst, q << 24);
@@ -547,6 +586,8 @@ struct Gen {
     const bool nl = in.negmask & 1, nr = in.negmask & 2;
     o.line("// until %d, phase 2: O(b) walk with running state", i);
     o.line("V v%d[8];", d);
+    const bool keep_a = bwd && P.sem == SEM_SMOOTH;
+    if (keep_a) o.line("float ua%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // A_t = sum of the candidates' terms, kept for the adjoint", i);
     o.line("if (live) {");
     o.indent++;
     if (in.w_off >= 0 || in.w2_off >= 0) {
@@ -559,6 +600,7 @@ struct Gen {
       o.line("UntilState<SEM> st[8];");
       o.line("U%d::phase2(smem + %d, c, rp%d, P.ins[%d].w[0], P.ins[%d].w[1], v%d, st);", i, scr_off[i], i, i, i, d);
       if (P.sem == SEM_SMOOTH) o.line("U%d::smooth_fix(smem + %d, c, rp%d, st, v%d);", i, scr_off[i], i, d);
+      if (keep_a) o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) ua%d[i] = st[i].acc;", i);
     }
     o.indent--;
     o.line("}");
@@ -576,10 +618,12 @@ struct Gen {
     const int n = in.nsrc, d = in.dst;
     o.line("// n-ary %s (%d operands)", in.mode == MODE_AND ? "And" : "Or", n);
     o.line("V v%d[8];", d);
-    if (bwd && !cum_bwd() && !src_bwd())
+    const bool fold = bwd && fold_root == i;  // the cotangent of the root is known now: multiply at once
+    if (bwd && !cum_bwd() && !src_bwd() && !fold)
       for (int j = 0; j < n; ++j) o.line("float d%d_%d[8];  // d out / d operand %d, for the adjoint sweep", i, j, j);
     o.line("if (live) {");
     o.indent++;
+    if (fold) o.line("root_cotangent<%s>(c, g.T, grad_out, scale, g%d);", P.root_neg ? "true" : "false", d);
     std::string w = "const float w[" + std::to_string(n) + "] = {";
     for (int j = 0; j < n; ++j) {
       char b[64];
@@ -595,7 +639,10 @@ struct Gen {
     if (bwd && !cum_bwd() && !src_bwd()) {
       o.line("float dd[%d];", n);
       o.line("v%d[i] = nary1_partials<SEM, %s, %d>(rp, a, w, P.ins[%d].sw, dd);", d, mode_name(in.mode), n, i);
-      for (int j = 0; j < n; ++j) o.line("d%d_%d[i] = dd[%d];", i, j, j);
+      for (int j = 0; j < n; ++j) {
+        if (fold) o.line("%s", adj_mul(in, j, d, ("dd[" + std::to_string(j) + "]").c_str()).c_str());
+        else o.line("d%d_%d[i] = dd[%d];", i, j, j);
+      }
     } else {
       o.line("v%d[i] = nary1<SEM, %s, %d>(rp, a, w, P.ins[%d].sw);", d, mode_name(in.mode), n, i);
     }
@@ -625,8 +672,9 @@ struct Gen {
     o.line("float* red = smem;");
     o.line("const bool live = alive(c);  // threads past the horizon only keep the shared planes consistent");
     o.line("(void)red; (void)rp;");
-    if (bwd && P.sem == SEM_SMOOTH) o.line("if (c.tid < %d) reinterpret_cast<int*>(smem + %d)[c.tid] = 0;  // lost flags", P.n_instr, flag_off);
     emit_predicates();
+    // (after the tile load: the staging area aliases them; the first barrier of the forward sweep orders the store)
+    if (bwd && P.sem == SEM_SMOOTH) o.line("if (c.tid < %d) reinterpret_cast<int*>(smem + %d)[c.tid] = 0;  // lost flags", P.n_instr, flag_off);
     for (int st = 0; st < n_stages; ++st) {
       o.line("// ================= stage %d", st);
       for (int i = 0; i < P.n_instr; ++i) {
@@ -685,7 +733,17 @@ struct Gen {
   }
 
   // ---------------------------------------------------------------- backward
+  // g_src[i] (+)= g_dst[i] * partial.  Outputs the reference raises on are NaN with a zero cotangent: the select keeps
+  // 0 * NaN out of the adjoints -- except for the two-operand smooth And / Or, whose partials are finite by construction
+  std::string adj_mul(const TInstr& in, int j, int d, const char* partial) const {
+    char b[160];
+    const char* op = ((in.negmask >> j) & 1) ? "-=" : "+=";
+    if (P.sem == SEM_SMOOTH && in.nsrc == 2) snprintf(b, sizeof(b), "g%d[i] %s g%d[i] * %s;", (int)in.src[j], op, d, partial);
+    else snprintf(b, sizeof(b), "g%d[i] %s (g%d[i] != 0.f) ? g%d[i] * %s : 0.f;", (int)in.src[j], op, d, d, partial);
+    return b;
+  }
   void nary_bwd(int i) {
+    if (i == fold_root) return;  // done in the forward sweep
     const TInstr& in = P.ins[i];
     const int n = in.nsrc, d = in.dst;
     o.line("// adjoint of the n-ary %s %d: the partials were computed with the value", in.mode == MODE_AND ? "And" : "Or", i);
@@ -693,9 +751,11 @@ struct Gen {
     o.indent++;
     o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) {");
     o.indent++;
-    for (int j = 0; j < n; ++j)
-      // (outputs the reference raises on are NaN with a zero cotangent: keep 0 * NaN out of the adjoints)
-      o.line("g%d[i] %s (g%d[i] != 0.f) ? g%d[i] * d%d_%d[i] : 0.f;", (int)in.src[j], ((in.negmask >> j) & 1) ? "-=" : "+=", d, d, i, j);
+    for (int j = 0; j < n; ++j) {
+      char e[32];
+      snprintf(e, sizeof(e), "d%d_%d[i]", i, j);
+      o.line("%s", adj_mul(in, j, d, e).c_str());
+    }
     o.indent--;
     o.line("}");
     o.indent--;
@@ -746,7 +806,7 @@ struct Gen {
     if (P.sem == SEM_SMOOTH) {
       o.line("if (reinterpret_cast<volatile int*>(smem + %d)[%d]) {  // rare: exact scatter of the outputs whose shifted sum underflowed", flag_off, i);
       o.indent++;
-      o.line("float* fix = smem + %d;", fix_off);
+      o.line("float* fix = smem + %d;", fix_off[i]);
       o.line("{ const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; store8(fix, c.tid, z); }");
       o.line("simt::sync();");
       o.line("if (lost%d) smooth_adj_scatter<%s, %d, %d, NT>(c, rp, lost%d, g%d, v%d, smem + %d, fix);", i, mode_name(in.mode), a, b, i, d, d,
@@ -880,14 +940,68 @@ struct Gen {
     const TInstr& in = P.ins[i];
     const int L = 8 * nt;
     const bool nl = in.negmask & 1, nr = in.negmask & 2;
+    if (P.sem == SEM_SMOOTH) {
+      const int GL = hand_off[i], GR = hand_off[i] + L, LA = aux_off[i], RH = aux_off[i] + L, ag_off = aux_off[i] + 2 * L, d = in.dst;
+      o.line("// adjoint of until %d: shared-tail walk downwards in the shifted linear domain, chunks in lockstep (no atomics)", i);
+      o.line("float uc%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("float ugl%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("float ugr%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("unsigned ulost%d = 0;", i);
+      o.line("smooth_until_adj_stage<NT>(c, rp%d, U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), smem + %d, smem + %d, smem + %d);",
+             i, i, scr_off[i], i, scr_off[i], LA, RH, ag_off);
+      o.line("if (live) {");
+      o.indent++;
+      o.line("ulost%d = smooth_until_adj_coeff<%d, %d>(c, g%d, ua%d, uc%d);", i, in.a, in.b, d, i, i);
+      o.line("if (ulost%d) reinterpret_cast<volatile int*>(smem + %d)[%d] = 1;", i, flag_off, i);
+      o.indent--;
+      o.line("}");
+      o.line("simt::sync();");
+      o.line("smooth_until_adj_walk<%d, %d, NT>(c, live, smem + %d, smem + %d, smem + %d, smem + %d, smem + %d, uc%d, ugl%d, ugr%d);",
+             in.a, in.b, LA, RH, ag_off, GL, GR, i, i, i);
+      o.line("if (live) smooth_until_adj_finish<%s, %s>(smem + %d, smem + %d, c.tid, ugl%d, ugr%d, g%d, g%d);", nl ? "true" : "false",
+             nr ? "true" : "false", LA, RH, i, i, (int)in.src[0], (int)in.src[1]);
+      o.line("if (reinterpret_cast<volatile int*>(smem + %d)[%d]) {  // rare: exact log-domain scatter of the outputs whose A left the healthy range",
+             flag_off, i);
+      o.indent++;
+      o.line("simt::sync();");
+      o.line("plane_zero8(smem + %d, c.tid);", GL);
+      o.line("plane_zero8(smem + %d, c.tid);", GR);
+      o.line("simt::sync();");
+      o.line("if (ulost%d) smooth_until_scatter<%d, %d, NT>(c, rp, ulost%d, g%d, U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), smem + %d, smem + %d);",
+             i, in.a, in.b, i, d, i, scr_off[i], i, scr_off[i], GL, GR);
+      o.line("simt::sync();");
+      o.line("if (c.p0 < c.nlive) {");
+      o.line("  accumulate8<%s>(smem + %d, c.tid, g%d);", nl ? "true" : "false", GL, (int)in.src[0]);
+      o.line("  accumulate8<%s>(smem + %d, c.tid, g%d);", nr ? "true" : "false", GR, (int)in.src[1]);
+      o.line("}");
+      o.indent--;
+      o.line("}");
+      o.line("simt::sync();");
+      return;
+    }
+    if (lockstep_adj(in)) {  // agm, uniform weights
+      const int G0 = hand_off[i], G1 = hand_off[i] + L, GR = hand_off[i] + 2 * L, AN = aux_off[i], AL = aux_off[i] + roundup(nt, 32), d = in.dst;
+      o.line("// adjoint of until %d: shared-tail walk downwards, chunks in lockstep (no atomics)", i);
+      o.line("float uk%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("float uz0%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("float uz1%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("float urr%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("unsigned upos%d = 0;", i);
+      o.line("agm_until_adj_stage<NT>(c, U%d::lplane(smem + %d, 0), smem + %d, smem + %d);", i, scr_off[i], AN, AL);
+      o.line("if (live) upos%d = agm_until_adj_coeff<%d, %d>(c, g%d, v%d, uk%d);", i, in.a, in.b, d, d, i);
+      o.line("simt::sync();");
+      o.line("agm_until_adj_walk<%d, %d, NT>(c, live, P.ins[%d].w[0], P.ins[%d].w[1], U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), smem + %d, smem + %d,",
+             in.a, in.b, i, i, i, scr_off[i], i, scr_off[i], AN, AL);
+      o.line("    smem + %d, smem + %d, smem + %d, uk%d, upos%d, uz0%d, uz1%d, urr%d);", G0, G1, GR, i, i, i, i, i);
+      o.line("if (live) agm_until_adj_finish<%s, %s>(U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), c.tid, P.ins[%d].w[1], uz0%d, uz1%d, urr%d, g%d, g%d);",
+             nl ? "true" : "false", nr ? "true" : "false", i, scr_off[i], i, scr_off[i], i, i, i, i, (int)in.src[0], (int)in.src[1]);
+      return;
+    }
     o.line("// adjoint of until %d: per-output sweeps, scatter through shared memory", i);
     o.line("plane_zero8(smem + %d, c.tid);", sp_off);
     o.line("plane_zero8(smem + %d, c.tid);", sp_off + L);
     o.line("simt::sync();");
-    if (P.sem == SEM_SMOOTH) {
-      o.line("if (live) smooth_until_scatter<%d, %d, NT>(c, rp, g%d, U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), smem + %d, smem + %d);",
-             in.a, in.b, (int)in.dst, i, scr_off[i], i, scr_off[i], sp_off, sp_off + L);
-    } else {
+    {
       char wl[48] = "nullptr", wr[48] = "nullptr";
       if (in.w_off >= 0) snprintf(wl, sizeof(wl), "P.wbuf + %d", (int)in.w_off);
       if (in.w2_off >= 0) snprintf(wr, sizeof(wr), "P.wbuf + %d", (int)in.w2_off);
@@ -913,11 +1027,6 @@ struct Gen {
     o.line("    const float* __restrict__ signal, const float* __restrict__ grad_out, float scale, float* __restrict__ grad_signal,");
     o.line("    float* __restrict__ out, double* __restrict__ mean_acc) {");
     o.indent = 1;
-    emit_forward_body();
-    o.line("// ================= value (optional) and cotangent");
-    o.line("float part = 0.f;  // (its block sum joins the fused mean at the very end: a barrier there costs nothing)");
-    if (src_bwd()) o.line("if (live) part = out ? store_root_src<%s>(c, g.T, v%d, out) : 0.f;", P.root_neg ? "true" : "false", (int)P.root);
-    else o.line("if (live) part = out ? store_root<SEM, %s>(c, g.T, v%d, out) : 0.f;", P.root_neg ? "true" : "false", (int)P.root);
     std::vector<char> has(kMaxSlots, 0);
     has[P.root] = 1;
     for (int i = 0; i < P.n_instr; ++i) {
@@ -925,6 +1034,17 @@ struct Gen {
       for (int j = 0; j < P.ins[i].nsrc; ++j) has[P.ins[i].src[j]] = 1;
     }
     for (int q = 0; q < P.n_preds; ++q) has[P.preds[q].dst] = 1;
+    if (!src_bwd() && !cum_bwd()) {
+      for (int i = 0; i < P.n_instr; ++i)
+        if (P.ins[i].op == T_NARY && P.ins[i].dst == P.root) fold_root = i;
+      for (int sl = 0; sl < kMaxSlots; ++sl)
+        if (has[sl]) o.line("float g%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", sl);
+    }
+    emit_forward_body();
+    o.line("// ================= value (optional) and cotangent");
+    o.line("float part = 0.f;  // (its block sum joins the fused mean at the very end: a barrier there costs nothing)");
+    if (src_bwd()) o.line("if (live) part = out ? store_root_src<%s>(c, g.T, v%d, out) : 0.f;", P.root_neg ? "true" : "false", (int)P.root);
+    else o.line("if (live) part = out ? store_root<SEM, %s>(c, g.T, v%d, out) : 0.f;", P.root_neg ? "true" : "false", (int)P.root);
     if (src_bwd()) {
       // Classic: every output routes its cotangent to ONE leaf sample (the arg-min / arg-max chain of
       // torch.min / max(dim), first index on ties): scatter into one shared plane per predicate
@@ -960,9 +1080,7 @@ struct Gen {
       o.line("if (live) root_cotangent2<%s>(c, g.T, grad_out, scale, g%d);", P.root_neg ? "true" : "false", (int)P.root);
       cum_adjoints();
     } else {
-      for (int sl = 0; sl < kMaxSlots; ++sl)
-        if (has[sl]) o.line("float g%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", sl);
-      o.line("if (live) root_cotangent<%s>(c, g.T, grad_out, scale, g%d);", P.root_neg ? "true" : "false", (int)P.root);
+      if (fold_root < 0) o.line("if (live) root_cotangent<%s>(c, g.T, grad_out, scale, g%d);", P.root_neg ? "true" : "false", (int)P.root);
       for (int st = n_stages - 1; st >= 0; --st) {
         o.line("// ================= adjoint stage %d", st);
         for (int i = P.n_instr - 1; i >= 0; --i)
@@ -1191,6 +1309,7 @@ int fused_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force
   };
   if (B < 0 || T < 0 || D < 1) return fail(PYSTL_E_INVALID, "bad shape");
   if (lw.lookahead < 0) return fail(PYSTL_E_UNSUPPORTED, "open-ended look-ahead");
+  if (T >= (int64_t(1) << 31) - 65536) return fail(PYSTL_E_UNSUPPORTED, "horizon beyond 2^31 samples (tile arithmetic is 32-bit)");
   const TileProgram& P = lw.prog;
   for (int q = 0; q < P.n_preds; ++q)
     for (int k = 0; k < P.preds[q].n_terms; ++k)

@@ -116,7 +116,8 @@ struct TC {
   RP rp;
 };
 
-// grid = (traces, tiles per trace): no division to find the tile
+// grid = (traces, tiles per trace): no division to find the tile.  Tile arithmetic is 32-bit: the host only plans
+// the fused tier for T < 2^31 - 2^16 (fused_geometry); 64 bits are for the element offsets c.b * T.
 template <int NT>
 PF_DEV TC tile_begin(const TileProgram& P, const TileGeom& g, float* smem) {
   TC c;
@@ -124,14 +125,17 @@ PF_DEV TC tile_begin(const TileProgram& P, const TileGeom& g, float* smem) {
   c.tid = simt::tid();
   c.p0 = 8 * c.tid;
   c.b = (long long)simt::bid_x();
-  const int e0 = simt::bid_y() * g.lout;   // T < 2^31 / tile
+  const int T = (int)g.T;
+  const int e0 = simt::bid_y() * g.lout;
   const int origin = e0 > g.hh ? e0 - g.hh : 0;  // backward tiles carry a left halo
   c.origin = origin;
-  const long long live = g.T - origin;
-  c.nlive = live < (long long)(8 * NT) ? (int)live : 8 * NT;
-  c.interior = live > (long long)(8 * NT);
-  const long long ok = P.raises_always ? -1 : g.T - 1 - P.start_slack - origin;
-  c.last_ok = ok > (long long)(1 << 30) ? (1 << 30) : (ok < -1 ? -1 : (int)ok);
+  const int live = T - origin;
+  c.nlive = live < 8 * NT ? live : 8 * NT;
+  c.interior = live > 8 * NT;
+  // last tile position whose output exists: T - 1 - start_slack - origin, clamped to [-1, 2^30]
+  int ok = T - 1 - origin;  // >= -1 ... (a tile always starts inside the trace; T == 0 launches nothing)
+  ok = (P.raises_always || P.start_slack > ok) ? -1 : ok - P.start_slack;
+  c.last_ok = ok > (1 << 30) ? (1 << 30) : ok;
   c.p_lo = e0 - origin;
   c.p_hi = c.p_lo + g.lout < c.nlive ? c.p_lo + g.lout : c.nlive;
   c.rp = P.rp;
@@ -1746,8 +1750,10 @@ PF_DEV Vec<1> nary1_partials(const RP& rp, const Vec<1> (&a)[N], const float (&w
     return o;
   } else if constexpr (SEM == SEM_SMOOTH && N == 2) {
     // softmax / softmin weights of two terms: 1 / (1 + 2^-|d|) for the extremal one
+    // (two operands at the identity -- both windows empty, the reference raises -- give inf - inf: the minimum
+    // drops the NaN, so the partials are finite everywhere and the adjoint sweep needs no guard)
     const float x0 = a[0].x[0], x1 = a[1].x[0];
-    const float t = fast_ex2(-fabsf(x0 - x1) * rp.k);
+    const float t = fast_ex2(-fminf(fabsf(x0 - x1), 3.0e38f) * rp.k);
     const float s = 1.f + t;
     const float wmax = fast_rcp(s), wmin = t * wmax;
     const bool first = MODE == MODE_AND ? x0 <= x1 : x0 >= x1;  // operand 0 is the extremal one
@@ -1785,11 +1791,12 @@ PF_DEV float lse2(float a, float b) {  // log2(2^a + 2^b)
   return m + fast_lg2(fast_ex2(a - m) + fast_ex2(b - m));
 }
 template <int UA, int UB, int NT>
-PF_DEV void smooth_until_scatter(const TC& c, const RP& rp, const float (&g)[8], const float* lpl, const float* rpl, float* gl,
+PF_DEV void smooth_until_scatter(const TC& c, const RP& rp, unsigned mask, const float (&g)[8], const float* lpl, const float* rpl, float* gl,
                                  float* gr) {
   float cbuf[UB + 1];
 #pragma unroll 1
   for (int i = 0; i < 8; ++i) {
+    if (!((mask >> i) & 1u)) continue;
     float gi = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -1821,6 +1828,423 @@ PF_DEV void smooth_until_scatter(const TC& c, const RP& rp, const float (&g)[8],
     }
   }
 }
+// ---- smooth until, backward, FAST PATH: the adjoint of UntilOp::phase2_smooth in the block-shifted linear domain.
+// With L_k = 2^(-k l_k - shift), R_q = 2^(-k r_q - shift), S_t(q) = sum_{k = t..q} L_k, T_t(q) = 1 / (S_t(q) + R_q) and
+// A_t = sum_q T_t(q) (what the forward pass kept), c_t = g_t / A_t:
+//     grad_r[q] = R_q sum_t c_t T_t(q)^2,        grad_l[k] = L_k sum_t c_t Z_t(k),   Z_t(k) = sum_{q >= max(k, t + UA)} T_t(q)^2.
+// The 8 outputs of a thread walk their candidates together, like the forward pass: past the own chunk S_i(q) = hS_i + M_q, so
+// a candidate costs one add, one reciprocal and three multiply-adds.  The walk runs DOWNWARDS in q, so that the suffix sums
+// Z_i accumulate without any subtraction (sums of positive terms only); M_q comes from the staged chunk aggregates
+// (cs[]: running sums of whole chunks, built upwards first) plus an in-register prefix of the chunk at hand.  Per position
+// the thread hands TWO numbers to the position's owner (the sum over its outputs of Z_i -- a running sum of the other
+// number -- and of c_i T^2) instead of two shared-memory atomics per candidate; the own chunk is triangular and stays in registers.  L_k and R_q are exponentiated once per position by their owner and
+// staged (la / rh / ag), and applied by the owner at the very end.
+// Outputs whose A_t left the healthy range (the forward pass recomputed them exactly, smooth_fix) get c = 0 here and go
+// through the exact log-domain scatter above (lost mask; block-uniform rare path).
+template <int NT>
+PF_DEV void smooth_until_adj_stage(const TC& c, const RP& rp, const float* lpl, const float* rpl, float* la, float* rh, float* ag) {
+  float l[8], r[8], lam[8], rho[8];
+  load8(lpl, c.tid, l);
+  load8(rpl, c.tid, r);
+  const float nk = -rp.k, ns = -rp.shift;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool ok = c.p0 + i < c.nlive;
+    lam[i] = ok ? fast_ex2(fmaf(l[i], nk, ns)) : 0.f;
+    rho[i] = ok ? fast_ex2(fmaf(r[i], nk, ns)) : 0.f;
+    s += lam[i];
+  }
+  store8(la, c.tid, lam);
+  store8(rh, c.tid, rho);
+  ag[c.tid] = s;
+}
+// c_i = g_i / A_i for the outputs with a cotangent and a healthy sum; returns the mask of the outputs for the exact path
+template <int UA, int UB>
+PF_DEV unsigned smooth_until_adj_coeff(const TC& c, const float (&g)[8], const float (&A)[8], float (&ci)[8]) {
+  unsigned lost = 0;
+  const int kmax = c.nlive - 1 - c.p0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool has = g[i] != 0.f && kmax - i >= UA;
+    const bool ok = A[i] >= kSmoothTiny && A[i] <= 1.0e30f;
+    ci[i] = (has && ok) ? g[i] * fast_rcp(A[i]) : 0.f;
+    if (has && !ok) lost |= 1u << i;
+  }
+  return lost;
+}
+// All threads of the CTA call it (it contains barriers).  The chunks are visited in LOCKSTEP: in step cc every thread
+// finishes the positions of chunk tid + cc and hands the two partial sums per position to that chunk's owner through
+// gl / gr -- one writer per chunk and step, so plain 128-bit stores instead of atomics (a shared-memory float atomic is a
+// compare-and-swap loop); the owner adds them to its registers between the step's two barriers.
+template <int UA, int UB, int NT>
+PF_DEV void smooth_until_adj_walk(const TC& c, bool live, const float* la, const float* rh, const float* ag, float* gl, float* gr,
+                                  const float (&ci)[8], float (&gl_own)[8], float (&gr_own)[8]) {
+  static_assert(UA >= 0 && UB >= UA, "bounded until");
+  constexpr int CMAX = (UB + 7) / 8;  // last chunk (relative to the own one) that holds a candidate
+  const int kmax = c.interior ? 0x3fffffff : c.nlive - 1 - c.p0;  // windows are clipped at the horizon on the last tile
+  bool active = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) active = active || ci[i] != 0.f;
+  active = active && live;
+  float lam[8], rho[8], hS[8], Z[8];
+  load8(la, c.tid, lam);
+  load8(rh, c.tid, rho);
+  {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      s += lam[i];
+      hS[i] = ci[i] != 0.f ? s : 1.f;  // outputs without a cotangent: keep their reciprocals finite (0 * inf)
+      Z[i] = 0.f;
+    }
+  }
+  // chunks past the tile (interior tiles: only outputs with a zero cotangent reach them) or past the horizon are skipped
+  int cend = CMAX;
+  if (cend > NT - 1 - c.tid) cend = NT - 1 - c.tid;
+  if (cend > (kmax >> 3)) cend = kmax >> 3;
+  if (!active) cend = 0;
+  float cs[CMAX + 1];  // cs[j] = sum of the aggregates of chunks tid + 1 .. tid + j
+  cs[0] = 0.f;
+#pragma unroll 1
+  for (int cc = 1; cc <= cend; ++cc) cs[cc] = cs[cc - 1] + ag[c.tid + cc];
+  float zs = 0.f;  // sum over the thread's outputs of Z_i: the running sum of the per-position sums
+  // the positions of chunk tid + cc, walked downwards.  ALL: every (position, output) pair is a candidate;
+  // CLIP: the chunk straddles the horizon
+  auto chunk = [&](int cc, auto all, auto clip, float (&zc)[8], float (&rc)[8]) {
+    float L[8], R[8];
+    load8(la, c.tid + cc, L);
+    load8(rh, c.tid + cc, R);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) L[k] += L[k - 1];
+    const float base = cs[cc - 1];
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+      float rs = 0.f;
+      if (!decltype(clip)::value || 8 * cc + k <= kmax) {
+        const float G = base + L[k] + R[k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
+            const float t = fast_rcp(G + hS[i]);
+            const float v = t * ci[i];
+            Z[i] = fmaf(v, t, Z[i]);
+            rs = fmaf(v, t, rs);
+          }
+      }
+      zs += rs;
+      zc[k] = zs;
+      rc[k] = rs;
+    }
+  };
+  auto step = [&](int cc, auto all) {
+    float zc[8], rc[8];
+    if (cc <= cend) {
+      if (8 * cc + 7 <= kmax) chunk(cc, all, BoolC<false>{}, zc, rc);
+      else chunk(cc, all, BoolC<true>{}, zc, rc);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) zc[k] = rc[k] = 0.f;
+    }
+    if (c.tid + cc < NT) {
+      store8(gl, c.tid + cc, zc);
+      store8(gr, c.tid + cc, rc);
+    }
+    simt::sync();
+    if (c.tid >= cc) {
+      float a[8], b[8];
+      load8(gl, c.tid, a);
+      load8(gr, c.tid, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        gl_own[k] += a[k];
+        gr_own[k] += b[k];
+      }
+    }
+    simt::sync();
+  };
+  // static classification of the chunks: cc is full when 8 cc - 7 >= UA and 8 cc + 7 <= UB
+  constexpr int CF0 = (UA + 7 + 7) / 8 > 1 ? (UA + 7 + 7) / 8 : 1;  // first full chunk
+  constexpr int CF1 = UB >= 15 ? (UB - 7) / 8 : 0;                   // last full chunk (0: none)
+  if constexpr (CF1 >= CF0) {
+#pragma unroll
+    for (int cc = CMAX; cc > CF1; --cc) step(cc, BoolC<false>{});
+#pragma unroll 1
+    for (int cc = CF1; cc >= CF0; --cc) step(cc, BoolC<true>{});
+#pragma unroll
+    for (int cc = CF0 - 1; cc >= 1; --cc) step(cc, BoolC<false>{});
+  } else {
+#pragma unroll
+    for (int cc = CMAX; cc >= 1; --cc) step(cc, BoolC<false>{});
+  }
+  if (!active) return;
+  // own chunk: triangular, in registers
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float tmp[8];
+    float S = ci[i] != 0.f ? 0.f : 1.f;
+#pragma unroll
+    for (int q = i; q < 8; ++q) {
+      S += lam[q];
+      tmp[q] = 0.f;
+      if (q - i >= UA && q - i <= UB && q <= kmax) {
+        const float t = fast_rcp(S + rho[q]);
+        const float e = (t * ci[i]) * t;
+        tmp[q] = e;
+        gr_own[q] += e;
+      }
+    }
+    float run = Z[i];
+#pragma unroll
+    for (int q = 7; q >= i; --q) {
+      run += tmp[q];
+      gl_own[q] += run;
+    }
+  }
+}
+// owner: apply L_k / R_q, route through the operands' negations
+template <bool NL, bool NR>
+PF_DEV void smooth_until_adj_finish(const float* la, const float* rh, int tid, const float (&gl_own)[8], const float (&gr_own)[8],
+                                    float (&gsl)[8], float (&gsr)[8]) {
+  float lam[8], rho[8];
+  load8(la, tid, lam);
+  load8(rh, tid, rho);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float dl = lam[i] * gl_own[i], dr = rho[i] * gr_own[i];
+    gsl[i] += NL ? -dl : dl;
+    gsr[i] += NR ? -dr : dr;
+  }
+}
+// ---- agm until, backward, FAST PATH (uniform weights_left / weights_right): the adjoint of UntilOp::phase2_agm on the
+// same lockstep scheme as smooth_until_adj_walk.  With y_i the prefix And of l over cnt samples, z = And((y_i, r_q); w0, w1)
+// and U = Or_q z (agm.py:112-130), the chain of Adj<SEM_AGM> partials collapses per candidate to
+//     dz  = g dU/dz                       (U >= 0: [z > 0] / n, else (1 - U) / (n (1 - z)))
+//     kp0 = [z <= 0] dz / sw,  kp1 = [z > 0] dz (1 + z) / sw                              (pair And, out_coeff)
+//     r-route:  (r > 0 ? kp1 / (1 + r) : kp0 [r < 0]) w1          -- the factor in r is applied by the owner of q
+//     l-route:  two-word suffix sums over the candidates  Z0 += w0 kp0 [y < 0] / cnt,  Z1 += w0 kp1 / cnt
+//               (the (1 + y) of in_factor and of out_coeff cancel), applied by the owner of k as
+//               l_k > 0 ? Z1 / (1 + l_k) : Z0 [l_k < 0]   (ties: one half, torch.minimum)
+// so a candidate costs the forward's rcp + ex2 plus one rcp (geometric Or only) and about twenty selects / FMAs.
+template <int NT>
+PF_DEV void agm_until_adj_stage(const TC& c, const float* lpl, float* agn, float* agl) {
+  float l[8];
+  load8(lpl, c.tid, l);
+  float sn = 0.f, sl = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (c.p0 + i < c.nlive) {
+      sn += fminf(l[i], 0.f);
+      sl += l[i] <= 0.f ? f_inf() : fast_lg2(1.f + l[i]);
+    }
+  agn[c.tid] = sn;
+  agl[c.tid] = sl;
+}
+// kg_i = g_i / n_i (U_i >= 0) or g_i (1 - U_i) / n_i: the output-level coefficient of the Or; upos: bit i = (U_i >= 0)
+template <int UA, int UB>
+PF_DEV unsigned agm_until_adj_coeff(const TC& c, const float (&g)[8], const Vec<1> (&U)[8], float (&kg)[8]) {
+  unsigned upos = 0;
+  const int kmax = c.nlive - 1 - c.p0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int last = kmax - i;
+    if (last > UB) last = UB;
+    const int n = last - UA + 1;
+    const bool has = g[i] != 0.f && n > 0;
+    const bool pos = U[i].x[0] >= 0.f;
+    const float gn = g[i] * fast_rcp((float)(n > 0 ? n : 1));
+    kg[i] = has ? (pos ? gn : gn * (1.f - U[i].x[0])) : 0.f;
+    if (pos) upos |= 1u << i;
+  }
+  return upos;
+}
+template <int UA, int UB, int NT>
+PF_DEV void agm_until_adj_walk(const TC& c, bool live, float w0, float w1, const float* lpl, const float* rpl, const float* agn,
+                               const float* agl, float* g0p, float* g1p, float* grp, const float (&kg)[8], unsigned upos,
+                               float (&z0_own)[8], float (&z1_own)[8], float (&r_own)[8]) {
+  static_assert(UA >= 0 && UB >= UA, "bounded until");
+  constexpr int CMAX = (UB + 7) / 8;
+  const int kmax = c.interior ? 0x3fffffff : c.nlive - 1 - c.p0;
+  const float invsw = fast_rcp(w0 + w1);
+  bool active = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) active = active || kg[i] != 0.f;
+  active = active && live;
+  float lo[8], ro[8], lnq[8], llq[8], hneg[8], hlog[8], Z0[8], Z1[8];
+  load8(lpl, c.tid, lo);
+  load8(rpl, c.tid, ro);
+  {
+    float sn = 0.f, sl = 0.f;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      const bool ok = c.p0 + i < c.nlive;
+      lnq[i] = ok ? fminf(lo[i], 0.f) : 0.f;
+      llq[i] = ok ? (lo[i] <= 0.f ? f_inf() : fast_lg2(1.f + lo[i])) : 0.f;
+      sn += lnq[i];
+      sl += llq[i];
+      // outputs without a cotangent take the arithmetic branch everywhere: nothing of theirs can overflow
+      hneg[i] = kg[i] != 0.f ? sn : 0.f;
+      hlog[i] = kg[i] != 0.f ? sl : f_inf();
+      Z0[i] = Z1[i] = 0.f;
+    }
+  }
+  // one candidate of output i: prefix accumulator (pn, pl) over cnt samples, right operand (rn = w1 min(r, 0),
+  // rl = w1 lg2(1 + r), rpos = r > 0)  ->  d0 / d1: its contributions to Z0 / Z1, kr: to the r-route
+  auto cand = [&](int i, float pn, float pl, float cntf, float rn, float rl, bool rpos, float& d0, float& d1, float& kr) {
+    const float invk = fast_rcp(cntf);
+    const bool flag = pl == f_inf();  // some l <= 0: arithmetic prefix (agm.py:71)
+    const float u = w0 * invk;
+    const float zA = fmaf(u, flag ? pn : 0.f, rn) * invsw;
+    const float E = fast_ex2(fmaf(u, pl, rl) * invsw);  // 1 + z of the geometric pair
+    const bool arith = flag || !rpos;
+    const float z = arith ? zA : E - 1.f;
+    const float k = kg[i];
+    const float dz = ((upos >> i) & 1u) ? (z > 0.f ? k : (z < 0.f ? 0.f : 0.5f * k)) : (z < 0.f ? k * fast_rcp(1.f - z) : k);
+    const float kp0 = z <= 0.f ? dz * invsw : 0.f;
+    const float kp1 = z <= 0.f ? 0.f : dz * E * invsw;
+    const float ydn = flag ? (pn < 0.f ? 1.f : 0.5f) : 0.f;
+    d0 = u * kp0 * ydn;
+    d1 = u * kp1;
+    kr = rpos ? kp1 : kp0;
+  };
+  int cend = CMAX;
+  if (cend > NT - 1 - c.tid) cend = NT - 1 - c.tid;
+  if (cend > (kmax >> 3)) cend = kmax >> 3;
+  if (!active) cend = 0;
+  float csn[CMAX + 1], csl[CMAX + 1];  // running sums of the aggregates of chunks tid + 1 .. tid + j
+  csn[0] = csl[0] = 0.f;
+#pragma unroll 1
+  for (int cc = 1; cc <= cend; ++cc) {
+    csn[cc] = csn[cc - 1] + agn[c.tid + cc];
+    csl[cc] = csl[cc - 1] + agl[c.tid + cc];
+  }
+  float zs0 = 0.f, zs1 = 0.f;
+  auto chunk = [&](int cc, auto all, auto clip, float (&zc0)[8], float (&zc1)[8], float (&rc)[8]) {
+    float l[8], r[8], Ln[8], Ll[8];
+    load8(lpl, c.tid + cc, l);
+    load8(rpl, c.tid + cc, r);
+    {
+      float sn = csn[cc - 1], sl = csl[cc - 1];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        sn += fminf(l[k], 0.f);
+        sl += l[k] <= 0.f ? f_inf() : fast_lg2(1.f + l[k]);
+        Ln[k] = sn;
+        Ll[k] = sl;
+      }
+    }
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+      float rs = 0.f, q0 = 0.f, q1 = 0.f;
+      if (!decltype(clip)::value || 8 * cc + k <= kmax) {
+        const float rk = r[k];
+        const bool rpos = rk > 0.f;
+        const float rn = w1 * fminf(rk, 0.f), rl = w1 * fast_lg2(1.f + rk);
+        const float cf = (float)(8 * cc + k + 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
+            float d0, d1, kr;
+            cand(i, hneg[i] + Ln[k], hlog[i] + Ll[k], cf - (float)i, rn, rl, rpos, d0, d1, kr);
+            Z0[i] += d0;
+            Z1[i] += d1;
+            q0 += d0;
+            q1 += d1;
+            rs += kr;
+          }
+      }
+      zs0 += q0;
+      zs1 += q1;
+      zc0[k] = zs0;
+      zc1[k] = zs1;
+      rc[k] = rs;
+    }
+  };
+  auto step = [&](int cc, auto all) {
+    float zc0[8], zc1[8], rc[8];
+    if (cc <= cend) {
+      if (8 * cc + 7 <= kmax) chunk(cc, all, BoolC<false>{}, zc0, zc1, rc);
+      else chunk(cc, all, BoolC<true>{}, zc0, zc1, rc);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) zc0[k] = zc1[k] = rc[k] = 0.f;
+    }
+    if (c.tid + cc < NT) {
+      store8(g0p, c.tid + cc, zc0);
+      store8(g1p, c.tid + cc, zc1);
+      store8(grp, c.tid + cc, rc);
+    }
+    simt::sync();
+    if (c.tid >= cc) {
+      float a[8], b[8], d[8];
+      load8(g0p, c.tid, a);
+      load8(g1p, c.tid, b);
+      load8(grp, c.tid, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        z0_own[k] += a[k];
+        z1_own[k] += b[k];
+        r_own[k] += d[k];
+      }
+    }
+    simt::sync();
+  };
+  constexpr int CF0 = (UA + 7 + 7) / 8 > 1 ? (UA + 7 + 7) / 8 : 1;  // first chunk whose every pair is a candidate
+  constexpr int CF1 = UB >= 15 ? (UB - 7) / 8 : 0;                   // last such chunk (0: none)
+  if constexpr (CF1 >= CF0) {
+#pragma unroll
+    for (int cc = CMAX; cc > CF1; --cc) step(cc, BoolC<false>{});
+#pragma unroll 1
+    for (int cc = CF1; cc >= CF0; --cc) step(cc, BoolC<true>{});
+#pragma unroll
+    for (int cc = CF0 - 1; cc >= 1; --cc) step(cc, BoolC<false>{});
+  } else {
+#pragma unroll
+    for (int cc = CMAX; cc >= 1; --cc) step(cc, BoolC<false>{});
+  }
+  if (!active) return;
+  // own chunk: triangular, in registers
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float t0[8], t1[8];
+    float pn = 0.f, pl = kg[i] != 0.f ? 0.f : f_inf();
+#pragma unroll
+    for (int q = i; q < 8; ++q) {
+      pn += lnq[q];
+      pl += llq[q];
+      t0[q] = t1[q] = 0.f;
+      if (q - i >= UA && q - i <= UB && q <= kmax) {
+        float kr;
+        cand(i, pn, pl, (float)(q - i + 1), w1 * fminf(ro[q], 0.f), w1 * fast_lg2(1.f + ro[q]), ro[q] > 0.f, t0[q], t1[q], kr);
+        r_own[q] += kr;
+      }
+    }
+    float run0 = Z0[i], run1 = Z1[i];
+#pragma unroll
+    for (int q = 7; q >= i; --q) {
+      run0 += t0[q];
+      run1 += t1[q];
+      z0_own[q] += run0;
+      z1_own[q] += run1;
+    }
+  }
+}
+// owner: the factors in l_k and r_q (Adj<SEM_AGM, MODE_AND>::in_factor), routed through the operands' negations
+template <bool NL, bool NR>
+PF_DEV void agm_until_adj_finish(const float* lpl, const float* rpl, int tid, float w1, const float (&z0)[8], const float (&z1)[8],
+                                 const float (&rr)[8], float (&gsl)[8], float (&gsr)[8]) {
+  float l[8], r[8];
+  load8(lpl, tid, l);
+  load8(rpl, tid, r);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float dl = l[i] > 0.f ? z1[i] * fast_rcp(1.f + l[i]) : (l[i] < 0.f ? z0[i] : 0.5f * z0[i]);
+    const float dr = w1 * rr[i] * (r[i] > 0.f ? fast_rcp(1.f + r[i]) : (r[i] < 0.f ? 1.f : 0.5f));
+    gsl[i] += NL ? -dl : dl;
+    gsr[i] += NR ? -dr : dr;
+  }
+}
+
 // ---- agm / dgmsr until, backward (agm.py:90-130, dgmsr.py:88-118; optional weights).
 //   y_i = AND_{k<=i}(l_k; wl),  z_i = AND((y_i, r_i); wp),  U = OR_{i>=UA}(z_i; wr)
 // Sweep 1 recomputes y_i, z_i (kept in a per-thread scratch array) and U; sweep 2 walks i downwards:

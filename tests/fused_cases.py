@@ -144,6 +144,14 @@ def smooth_until_backward_cases(light: bool = False):
     if not light:
         out.append(dict(name="bwd/cfg5/smooth0.5/tile_end", spec=specs["cfg5"], sem="smooth", kw={"temperature": 0.5}, B=2, T=512, D=8, threads=64,
                         seed=31))
+    # several tiles per trace (interior tiles: the shared-tail walk runs past the outputs the tile writes), a lower
+    # bound above one chunk, and an upper bound that ends inside a chunk
+    specs["U3"] = ("until", (9, 41), ("pred", {0: 1.0}, 0.0), ("not", ("pred", {1: 1.0}, -1.0)))
+    multi = [("U3", 0.5, 1100, 64)] if light else [("U", 0.5, 1100, 64), ("U2", 0.02, 1100, 64), ("U3", 0.5, 1100, 64), ("U3", 0.1, 1100, 32),
+                                                   ("cfg5", 0.5, 1100, 64), ("cfg5", 0.05, 1024, 64)]
+    for name, tau, T, threads in multi:
+        out.append(dict(name=f"bwd/{name}/smooth{tau}/T{T}/nt{threads}", spec=specs[name], sem="smooth", kw={"temperature": tau}, B=2, T=T,
+                        D=8 if name == "cfg5" else 2, threads=threads, seed=77))
     return out
 
 
@@ -164,6 +172,15 @@ def gm_backward_cases(light: bool = False):
             for threads in ((64,) if light else (0, 64)):
                 out.append(dict(name=f"bwd/{name}/{sem}{kw.get('p', '')}/nt{threads}", spec=spec, sem=sem, kw=kw, B=2, T=300,
                                 D={"cfg4": 4, "cfg5": 8}.get(name, 2), threads=threads, seed=37))
+    # several tiles per trace (interior tiles of the lockstep shared-tail walks), lower bound above one chunk
+    U3 = ("until", (9, 41), ("pred", {0: 1.0}, 0.0), ("not", ("pred", {1: 1.0}, -1.0)))
+    multi = [("U3", U3, 1100, 64, 2)] if light else [("U", U, 1100, 64, 2), ("U3", U3, 1100, 64, 2), ("U3", U3, 1100, 32, 2),
+                                                     ("cfg5", BASELINE_SPECS["cfg5"], 1100, 64, 8), ("cfg5", BASELINE_SPECS["cfg5"], 1024, 64, 8)]
+    for si, (sem, kw) in enumerate(SEM_KW[3:5]):
+        for name, spec, T, threads, D in multi:
+            if light and sem != "agm":
+                continue
+            out.append(dict(name=f"bwd/{name}/{sem}/T{T}/nt{threads}", spec=spec, sem=sem, kw=kw, B=2, T=T, D=D, threads=threads, seed=77))
     # the trace ends exactly where a tile ends (see forward_cases: tile_end)
     for si, (sem, kw) in enumerate(SEM_KW[3:5]):
         out.append(dict(name=f"bwd/U/{sem}/tile_end", spec=U, sem=sem, kw=kw, B=2, T=512, D=2, threads=64, seed=39))
