@@ -993,8 +993,8 @@ struct Gen {
       o.line("agm_until_adj_walk<%d, %d, NT>(c, live, P.ins[%d].w[0], P.ins[%d].w[1], U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), smem + %d, smem + %d,",
              in.a, in.b, i, i, i, scr_off[i], i, scr_off[i], AN, AL);
       o.line("    smem + %d, smem + %d, smem + %d, uk%d, upos%d, uz0%d, uz1%d, urr%d);", G0, G1, GR, i, i, i, i, i);
-      o.line("if (live) agm_until_adj_finish<%s, %s>(U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), c.tid, P.ins[%d].w[1], uz0%d, uz1%d, urr%d, g%d, g%d);",
-             nl ? "true" : "false", nr ? "true" : "false", i, scr_off[i], i, scr_off[i], i, i, i, i, (int)in.src[0], (int)in.src[1]);
+      o.line("if (live) agm_until_adj_finish<%s, %s>(U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), c.tid, P.ins[%d].w[0], P.ins[%d].w[1], uz0%d, uz1%d, urr%d, g%d, g%d);",
+             nl ? "true" : "false", nr ? "true" : "false", i, scr_off[i], i, scr_off[i], i, i, i, i, i, (int)in.src[0], (int)in.src[1]);
       return;
     }
     o.line("// adjoint of until %d: per-output sweeps, scatter through shared memory", i);
@@ -1038,7 +1038,8 @@ struct Gen {
       for (int i = 0; i < P.n_instr; ++i)
         if (P.ins[i].op == T_NARY && P.ins[i].dst == P.root) fold_root = i;
       for (int sl = 0; sl < kMaxSlots; ++sl)
-        if (has[sl]) o.line("float g%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", sl);
+        // (-0.f: x + (-0) == x for every x, so the first accumulation into an adjoint folds to a move)
+        if (has[sl]) o.line("float g%d[8] = {-0.f, -0.f, -0.f, -0.f, -0.f, -0.f, -0.f, -0.f};", sl);
     }
     emit_forward_body();
     o.line("// ================= value (optional) and cotangent");
@@ -1193,7 +1194,7 @@ bool hoistable(const std::string& raw) {
     const size_t eq = t.find('=');
     if (eq == std::string::npos) return true;
     const std::string init = t.substr(eq + 1);
-    return init.find_first_not_of(" {}0.f,;") == std::string::npos;
+    return init.find_first_not_of(" {}-0.f,;") == std::string::npos;
   }
   return false;
 }

@@ -2025,7 +2025,8 @@ PF_DEV void smooth_until_adj_finish(const float* la, const float* rh, int tid, c
 //     l-route:  two-word suffix sums over the candidates  Z0 += w0 kp0 [y < 0] / cnt,  Z1 += w0 kp1 / cnt
 //               (the (1 + y) of in_factor and of out_coeff cancel), applied by the owner of k as
 //               l_k > 0 ? Z1 / (1 + l_k) : Z0 [l_k < 0]   (ties: one half, torch.minimum)
-// so a candidate costs the forward's rcp + ex2 plus one rcp (geometric Or only) and about twenty selects / FMAs.
+// so a candidate costs an ex2 and a rcp (1 / cnt comes from a 15-entry table per chunk) and about thirty selects / FMAs;
+// a chunk behind some l <= 0 (every prefix that reaches it is arithmetic) takes a variant without the exponential.
 template <int NT>
 PF_DEV void agm_until_adj_stage(const TC& c, const float* lpl, float* agn, float* agl) {
   float l[8];
@@ -2066,10 +2067,16 @@ PF_DEV void agm_until_adj_walk(const TC& c, bool live, float w0, float w1, const
   constexpr int CMAX = (UB + 7) / 8;
   const int kmax = c.interior ? 0x3fffffff : c.nlive - 1 - c.p0;
   const float invsw = fast_rcp(w0 + w1);
+  const float w0p = w0 * invsw, w1p = w1 * invsw;  // (the r-route's own 1 / sw is applied by the owner)
   bool active = false;
 #pragma unroll
   for (int i = 0; i < 8; ++i) active = active || kg[i] != 0.f;
   active = active && live;
+  // coefficient of the Or per output: kS for a candidate z > 0, kG / (1 - z) for z < 0 (zero when U >= 0: the arithmetic
+  // Or ignores its negative entries), their mean on the tie z == 0 (Adj<SEM_AGM, MODE_OR>::in_factor)
+  float kG[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) kG[i] = ((upos >> i) & 1u) ? 0.f : kg[i];
   float lo[8], ro[8], lnq[8], llq[8], hneg[8], hlog[8], Z0[8], Z1[8];
   load8(lpl, c.tid, lo);
   load8(rpl, c.tid, ro);
@@ -2088,24 +2095,28 @@ PF_DEV void agm_until_adj_walk(const TC& c, bool live, float w0, float w1, const
       Z0[i] = Z1[i] = 0.f;
     }
   }
-  // one candidate of output i: prefix accumulator (pn, pl) over cnt samples, right operand (rn = w1 min(r, 0),
-  // rl = w1 lg2(1 + r), rpos = r > 0)  ->  d0 / d1: its contributions to Z0 / Z1, kr: to the r-route
-  auto cand = [&](int i, float pn, float pl, float cntf, float rn, float rl, bool rpos, float& d0, float& d1, float& kr) {
-    const float invk = fast_rcp(cntf);
+  // one candidate of output i.  pn / pl: prefix accumulator (sum of min(l, 0); sum of lg2(1 + l) or +inf once some l <= 0),
+  // up = w0 / (sw cnt), rnp = w1 min(r, 0) / sw, rlp = w1 lg2(1 + r) / sw, rpos = r > 0.
+  //   -> d0 / d1: contributions to Z0 / Z1, kr: to the r-route (times sw)
+  auto cand = [&](int i, float pn, float pl, float up, float rnp, float rlp, bool rpos, float& d0, float& d1, float& kr) {
     const bool flag = pl == f_inf();  // some l <= 0: arithmetic prefix (agm.py:71)
-    const float u = w0 * invk;
-    const float zA = fmaf(u, flag ? pn : 0.f, rn) * invsw;
-    const float E = fast_ex2(fmaf(u, pl, rl) * invsw);  // 1 + z of the geometric pair
-    const bool arith = flag || !rpos;
-    const float z = arith ? zA : E - 1.f;
-    const float k = kg[i];
-    const float dz = ((upos >> i) & 1u) ? (z > 0.f ? k : (z < 0.f ? 0.f : 0.5f * k)) : (z < 0.f ? k * fast_rcp(1.f - z) : k);
-    const float kp0 = z <= 0.f ? dz * invsw : 0.f;
-    const float kp1 = z <= 0.f ? 0.f : dz * E * invsw;
-    const float ydn = flag ? (pn < 0.f ? 1.f : 0.5f) : 0.f;
-    d0 = u * kp0 * ydn;
-    d1 = u * kp1;
-    kr = rpos ? kp1 : kp0;
+    const float zA = fmaf(up, flag ? pn : 0.f, rnp);
+    const float E = fast_ex2(fmaf(up, pl, rlp));  // 1 + z of the geometric pair
+    const float z = (flag || !rpos) ? zA : E - 1.f;
+    const float rz = fast_rcp(1.f - fminf(z, 0.f));
+    float dz = z > 0.f ? kg[i] : kG[i] * rz;
+    dz = z == 0.f ? 0.5f * (kg[i] + kG[i]) : dz;
+    const float tE = z > 0.f ? dz * E : 0.f;
+    d0 = flag ? up * dz * (pn < 0.f ? 1.f : 0.5f) : 0.f;
+    d1 = up * tE;
+    kr = rpos ? tE : dz;
+  };
+  // the same when the prefix is known to hold some l <= 0 (pl = +inf): arithmetic pair, z <= 0, no exponential
+  auto cand_arith = [&](int i, float pn, float up, float rnp, float& d0, float& dz) {
+    const float z = fmaf(up, pn, rnp);
+    const float rz = fast_rcp(1.f - z);
+    dz = z < 0.f ? kG[i] * rz : 0.5f * (kg[i] + kG[i]);
+    d0 = up * dz * (pn < 0.f ? 1.f : 0.5f);
   };
   int cend = CMAX;
   if (cend > NT - 1 - c.tid) cend = NT - 1 - c.tid;
@@ -2119,8 +2130,10 @@ PF_DEV void agm_until_adj_walk(const TC& c, bool live, float w0, float w1, const
     csl[cc] = csl[cc - 1] + agl[c.tid + cc];
   }
   float zs0 = 0.f, zs1 = 0.f;
-  auto chunk = [&](int cc, auto all, auto clip, float (&zc0)[8], float (&zc1)[8], float (&rc)[8]) {
-    float l[8], r[8], Ln[8], Ll[8];
+  // the positions of chunk tid + cc, walked downwards.  ALL: every (position, output) pair is a candidate; CLIP: the
+  // chunk straddles the horizon; ARITH: some l <= 0 before the chunk, every candidate of it has an arithmetic prefix
+  auto chunk = [&](int cc, auto all, auto clip, auto arith, float (&zc0)[8], float (&zc1)[8], float (&rc)[8]) {
+    float l[8], r[8], Ln[8], Ll[8], ut[15];
     load8(lpl, c.tid + cc, l);
     load8(rpl, c.tid + cc, r);
     {
@@ -2128,30 +2141,49 @@ PF_DEV void agm_until_adj_walk(const TC& c, bool live, float w0, float w1, const
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         sn += fminf(l[k], 0.f);
-        sl += l[k] <= 0.f ? f_inf() : fast_lg2(1.f + l[k]);
         Ln[k] = sn;
-        Ll[k] = sl;
+        if constexpr (!decltype(arith)::value) {
+          sl += l[k] <= 0.f ? f_inf() : fast_lg2(1.f + l[k]);
+          Ll[k] = sl;
+        }
       }
     }
+    // w0 / (sw cnt) for cnt = 8 cc + (k - i) + 1, k - i in [-7, 7]
+#pragma unroll
+    for (int j = 0; j < 15; ++j) ut[j] = w0p * fast_rcp((float)(8 * cc + j - 6));
 #pragma unroll
     for (int k = 7; k >= 0; --k) {
       float rs = 0.f, q0 = 0.f, q1 = 0.f;
       if (!decltype(clip)::value || 8 * cc + k <= kmax) {
         const float rk = r[k];
         const bool rpos = rk > 0.f;
-        const float rn = w1 * fminf(rk, 0.f), rl = w1 * fast_lg2(1.f + rk);
-        const float cf = (float)(8 * cc + k + 1);
+        const float rnp = w1p * fminf(rk, 0.f);
+        if constexpr (decltype(arith)::value) {
+          float sdz = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
-            float d0, d1, kr;
-            cand(i, hneg[i] + Ln[k], hlog[i] + Ll[k], cf - (float)i, rn, rl, rpos, d0, d1, kr);
-            Z0[i] += d0;
-            Z1[i] += d1;
-            q0 += d0;
-            q1 += d1;
-            rs += kr;
-          }
+          for (int i = 0; i < 8; ++i)
+            if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
+              float d0, dz;
+              cand_arith(i, hneg[i] + Ln[k], ut[k - i + 7], rnp, d0, dz);
+              Z0[i] += d0;
+              q0 += d0;
+              sdz += dz;
+            }
+          rs = rpos ? 0.f : sdz;
+        } else {
+          const float rlp = w1p * fast_lg2(1.f + rk);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
+              float d0, d1, kr;
+              cand(i, hneg[i] + Ln[k], hlog[i] + Ll[k], ut[k - i + 7], rnp, rlp, rpos, d0, d1, kr);
+              Z0[i] += d0;
+              Z1[i] += d1;
+              q0 += d0;
+              q1 += d1;
+              rs += kr;
+            }
+        }
       }
       zs0 += q0;
       zs1 += q1;
@@ -2163,8 +2195,13 @@ PF_DEV void agm_until_adj_walk(const TC& c, bool live, float w0, float w1, const
   auto step = [&](int cc, auto all) {
     float zc0[8], zc1[8], rc[8];
     if (cc <= cend) {
-      if (8 * cc + 7 <= kmax) chunk(cc, all, BoolC<false>{}, zc0, zc1, rc);
-      else chunk(cc, all, BoolC<true>{}, zc0, zc1, rc);
+      const bool ar = csl[cc - 1] == f_inf();
+      if (8 * cc + 7 <= kmax) {
+        if (ar) chunk(cc, all, BoolC<false>{}, BoolC<true>{}, zc0, zc1, rc);
+        else chunk(cc, all, BoolC<false>{}, BoolC<false>{}, zc0, zc1, rc);
+      } else {
+        chunk(cc, all, BoolC<true>{}, BoolC<false>{}, zc0, zc1, rc);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) zc0[k] = zc1[k] = rc[k] = 0.f;
@@ -2215,7 +2252,7 @@ PF_DEV void agm_until_adj_walk(const TC& c, bool live, float w0, float w1, const
       t0[q] = t1[q] = 0.f;
       if (q - i >= UA && q - i <= UB && q <= kmax) {
         float kr;
-        cand(i, pn, pl, (float)(q - i + 1), w1 * fminf(ro[q], 0.f), w1 * fast_lg2(1.f + ro[q]), ro[q] > 0.f, t0[q], t1[q], kr);
+        cand(i, pn, pl, w0p * (1.f / (float)(q - i + 1)), w1p * fminf(ro[q], 0.f), w1p * fast_lg2(1.f + ro[q]), ro[q] > 0.f, t0[q], t1[q], kr);
         r_own[q] += kr;
       }
     }
@@ -2231,15 +2268,16 @@ PF_DEV void agm_until_adj_walk(const TC& c, bool live, float w0, float w1, const
 }
 // owner: the factors in l_k and r_q (Adj<SEM_AGM, MODE_AND>::in_factor), routed through the operands' negations
 template <bool NL, bool NR>
-PF_DEV void agm_until_adj_finish(const float* lpl, const float* rpl, int tid, float w1, const float (&z0)[8], const float (&z1)[8],
-                                 const float (&rr)[8], float (&gsl)[8], float (&gsr)[8]) {
+PF_DEV void agm_until_adj_finish(const float* lpl, const float* rpl, int tid, float w0, float w1, const float (&z0)[8],
+                                 const float (&z1)[8], const float (&rr)[8], float (&gsl)[8], float (&gsr)[8]) {
+  const float w1p = w1 * fast_rcp(w0 + w1);
   float l[8], r[8];
   load8(lpl, tid, l);
   load8(rpl, tid, r);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float dl = l[i] > 0.f ? z1[i] * fast_rcp(1.f + l[i]) : (l[i] < 0.f ? z0[i] : 0.5f * z0[i]);
-    const float dr = w1 * rr[i] * (r[i] > 0.f ? fast_rcp(1.f + r[i]) : (r[i] < 0.f ? 1.f : 0.5f));
+    const float dr = w1p * rr[i] * (r[i] > 0.f ? fast_rcp(1.f + r[i]) : (r[i] < 0.f ? 1.f : 0.5f));
     gsl[i] += NL ? -dl : dl;
     gsr[i] += NR ? -dr : dr;
   }

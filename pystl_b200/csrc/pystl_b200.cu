@@ -98,9 +98,18 @@ static int fused_prepare(const pystl_formula_t* f, int64_t B, int64_t T, int32_t
   if (rc) return rc;
   rc = fused_geometry(*lw, B, T, D, forced_threads(), backward, g, g_err, sizeof(g_err));
   if (rc) return rc;
-  rc = fused_generate(*lw, D, g->nt, fused_minb(g->nt, backward, lw->prog), backward, fs, g_err, sizeof(g_err));
+  const int minb = fused_minb(g->nt, backward, lw->prog);
+  rc = fused_generate(*lw, D, g->nt, minb, backward, fs, g_err, sizeof(g_err));
   if (rc) return rc;
   if (fs->smem_floats * 4 > 227 * 1024) return set_err(PYSTL_E_UNSUPPORTED, "fused kernel needs %d bytes of shared memory", fs->smem_floats * 4);
+  {
+    // shared memory may admit fewer CTAs per SM than the register target assumes: give the registers back
+    const int by_smem = std::max(1, 228 * 1024 / (fs->smem_floats * 4 + 1024));
+    if (by_smem < minb && !getenv("PYSTL_B200_FUSED_MINB")) {
+      rc = fused_generate(*lw, D, g->nt, by_smem, backward, fs, g_err, sizeof(g_err));
+      if (rc) return rc;
+    }
+  }
   g->smem_floats = fs->smem_floats;
   // L2 prefetch distance in traces (fused_rt.cuh: prefetch_rows): a little more than one wave of
   // resident CTAs ahead.  TileGeom::scr_planes is unused by the fused tier and carries it.
