@@ -118,6 +118,40 @@ def algorithmic_bytes_per_sample(cfg: str, backward: bool) -> float:
     return fwd + 4 * d_ref + 4 * D  # constant cotangent fused: no grad_out read
 
 
+# Secondary ceiling ("when it binds"): instructions per trace-sample on the pipe that binds the
+# O(b) Until walks of the non-lattice semantics, derived in DESIGN.md section 4 ("Pipe floors").  B200 SM: FMA pipe 128,
+# ALU pipe 64 (FMNMX, compares, selects), XU pipe 16 (MUFU: ex2 / lg2 / rcp / sqrt) lanes per clock.
+PIPE_LANES = {"xu": 16, "alu": 64}
+try:  # the clock the floors are computed at: the measured maximum SM clock of this pool's B200s
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as _fh:
+        SM_MAX_MHZ = float(json.load(_fh).get("sm_max_mhz", 1965.0))
+except (OSError, ValueError):
+    SM_MAX_MHZ = 1965.0
+PIPE_OPS = {
+    # cumulative Until [0, 64]: per candidate and channel one FMNMX (+ one FADD on the FMA pipe); G[0, 200] adds ~6
+    ("cfg4", "forward"): ("alu", 65 * 2 + 2 * 2 + 6),
+    # cfg5's Until [0, 24]: 25 candidates per sample
+    ("cfg5c", "forward"): ("alu", 25 * 2 + 2 * 2 + 12),
+    ("cfg5s", "forward"): ("xu", 25 + 2 * (25 + 8) / 8.0 + 2 * 2 + 3 * 2),   # one rcp per candidate, lifts shared by 8 outputs
+    ("cfg5a", "forward"): ("xu", 3 * 25 + 2 * (25 + 8) / 8.0 + 2 * 2 + 3 * 2),  # rcp + ex2 + lg2 per candidate
+    ("cfg5d", "forward"): ("xu", 13 * 25 + 2 * 4 + 2 * 6),                    # generic walk, 13 transcendentals per candidate
+    ("cfg5sb", "value_and_grad"): ("xu", 2 * 25 + 4 * (25 + 8) / 8.0 + 2 * 5 + 3 * 2),  # forward + one rcp per candidate again
+    ("cfg5ab", "value_and_grad"): ("xu", 5 * 25 + 40),
+}
+
+
+def pipe_floor(cfg: str, kind: str, B: int, T: int, ms_: float, sm_mhz: float) -> dict | None:
+    """{"pipe", "ops_per_sample", "floor_ms", "frac"}: time the binding instruction pipe needs at 100 % utilisation
+    over the measured kernel time, or None where HBM is the only ceiling stated."""
+    ent = PIPE_OPS.get((cfg, kind))
+    if ent is None:
+        return None
+    pipe, ops = ent
+    floor_ms = ops * B * T / (148.0 * PIPE_LANES[pipe] * sm_mhz * 1e6) * 1e3
+    return {"pipe": pipe, "ops_per_sample": ops, "lanes_per_clk_per_sm": PIPE_LANES[pipe], "sm_mhz": sm_mhz, "floor_ms": floor_ms,
+            "frac": floor_ms / ms_}
+
+
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons sampled DURING the timed region: NVML in-process (one sample
     every ~2 ms, so that even a 100 ms region yields a median under load), nvidia-smi as fallback."""
@@ -474,9 +508,13 @@ class Workload:
     def roof(self, kind: str, ms_: float, bytes_per_sample: float, peak: float, traffic: dict) -> dict:
         gbs = bytes_per_sample * self.B * self.T / (ms_ * 1e-3) / 1e9
         name = f"{self.tier}:{kind}<{self.sem_name}>"
-        return {"workload": self.cfg, "kernel": name, "traces": self.B, "kernel_ms": ms_, "achieved": gbs, "frac": gbs / peak,
+        line = {"workload": self.cfg, "kernel": name, "traces": self.B, "kernel_ms": ms_, "achieved": gbs, "frac": gbs / peak,
                 "algorithmic_bytes_per_sample": bytes_per_sample, "samples_per_s": self.B * self.T / (ms_ * 1e-3),
                 "traffic": traffic.get(f"{self.cfg}:{kind}<{self.sem_name}>")}
+        floor = pipe_floor(self.cfg, kind, self.B, self.T, ms_, SM_MAX_MHZ)
+        if floor:
+            line["pipe_floor"] = floor  # the ceiling that binds this kernel; `frac` above stays the HBM fraction
+        return line
 
     def free(self):
         self.signal = self.out = self.grad = None

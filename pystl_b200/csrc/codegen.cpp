@@ -125,6 +125,7 @@ struct Gen {
 
   Gen(const Lowered& l, int D_, int nt_, int minb_, bool bwd_) : lw(l), P(l.prog), D(D_), nt(nt_), minb(minb_), bwd(bwd_) {}
   int kw() const { return P.sem == SEM_SMOOTH ? 1 : 2; }  // words of an adjoint coefficient
+  static bool relift() { const char* e = getenv("PYSTL_B200_RELIFT"); return e && atoi(e) != 0; }
 
   int vw() const { return (P.sem == SEM_CUMULATIVE || src_bwd()) ? 2 : 1; }
   int aw() const { return src_bwd() ? 2 : ((P.sem == SEM_CLASSIC || P.sem == SEM_SMOOTH) ? 1 : 2); }
@@ -799,7 +800,17 @@ struct Gen {
     o.indent++;
     o.line("Vec<%d> w[8];", kw());
     o.line("BW%d::phase2(smem + %d, c.tid, k%d, ksf%d, kpf%d, w);", i, bscr_off[i], i, i, i);
-    if (P.sem == SEM_SMOOTH) o.line("smooth_adj_apply<%s>(w, x%d, g%d);", neg ? "true" : "false", i, s);
+    if (P.sem == SEM_SMOOTH) {
+      if (relift()) {  // experiment: the lifted operand is not kept in registers, it is lifted again from the stash
+        o.line("V ts[8];");
+        o.line("{ float tt[8]; load8(smem + %d, c.tid, tt); _Pragma(\"unroll\") for (int i = 0; i < 8; ++i) ts[i] = V{{tt[i]}}; }", stash_off[i]);
+        o.line("R%d::A xh[8];", i);
+        o.line("lift8<R%d, VW>(c, rp%d, ts, xh);", i, i);
+        o.line("smooth_adj_apply<%s>(w, xh, g%d);", neg ? "true" : "false", s);
+      } else {
+        o.line("smooth_adj_apply<%s>(w, x%d, g%d);", neg ? "true" : "false", i, s);
+      }
+    }
     else o.line("gm_adj_apply<SEM, %s, %s>(c, rp, w, v%d, g%d);", mode_name(in.mode), neg ? "true" : "false", s, s);
     o.indent--;
     o.line("}");

@@ -24,6 +24,7 @@
 
 #if defined(__CUDACC__)
 #define PF_DEV __device__ __forceinline__
+#define PF_COLD __device__ __noinline__  // rare exact paths: kept out of the hot instruction stream (scalars in, scalar out)
 #define PF_KERNEL(NT, MINB) extern "C" __global__ void __launch_bounds__(NT, MINB)
 #define PF_GRID_CONSTANT __grid_constant__
 #define PF_DYN_SMEM(name) extern __shared__ __align__(1024) float name[]
@@ -91,6 +92,7 @@ PF_DEV void bulk_store_and_wait(void* dst_global, const void* src_smem, unsigned
 #else
 #include "simt_host.h"
 #define PF_DEV inline
+#define PF_COLD inline
 #define PF_KERNEL(NT, MINB) extern "C" void
 #define PF_GRID_CONSTANT
 #define PF_DYN_SMEM(name) float* name = simt::dyn_smem()
@@ -655,6 +657,33 @@ struct ClampScanOp {
   }
 };
 
+// smooth until: one output recomputed exactly in the log2 domain (rare path of UntilOp::smooth_fix)
+template <int UA>
+PF_COLD float smooth_until_fix_one(int p, int last, float k, float invk, const float* pl, const float* pr) {
+  float mS = -f_inf(), S = 0.f, mA = -f_inf(), A = 0.f;
+  for (int kk = 0; kk <= last; ++kk) {
+    const float zl = -pl[pidx(p + kk)] * k;
+    if (zl > mS) {
+      S = S * fast_ex2(mS - zl) + 1.f;
+      mS = zl;
+    } else {
+      S += fast_ex2(zl - mS);
+    }
+    if (kk >= UA) {
+      const float zr = -pr[pidx(p + kk)] * k;
+      const float mc = fmaxf(mS, zr);
+      const float cl = -(mc + fast_lg2(S * fast_ex2(mS - mc) + fast_ex2(zr - mc)));  // log2 of the term
+      if (cl > mA) {
+        A = A * fast_ex2(mA - cl) + 1.f;
+        mA = cl;
+      } else {
+        A += fast_ex2(cl - mA);
+      }
+    }
+  }
+  return (mA + fast_lg2(A)) * invk;
+}
+
 template <bool B>
 struct BoolC {
   static constexpr bool value = B;
@@ -1012,43 +1041,13 @@ struct UntilOp {
 
   // smooth only: outputs whose shifted sums lost their precision, recomputed with per-term scales
   PF_DEV static void smooth_fix(float* scr, const TC& c, const RP& rp, const UntilState<SEM_SMOOTH> (&st)[8], Vec<1> (&o)[8]) {
-    const float* pl = lplane(scr, 0);
-    const float* pr = rplane(scr, 0);
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-      float a_i = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j == i) a_i = st[j].acc;
+    for (int i = 0; i < 8; ++i) {
+      const float a_i = st[i].acc;
       const int p = c.p0 + i;
       const int n = ncand(c, p);
       if (n <= 0 || p >= c.nlive || (a_i >= kSmoothTiny && a_i <= 1.0e30f)) continue;
-      const int last = n + UA - 1;
-      float mS = -f_inf(), S = 0.f, mA = -f_inf(), A = 0.f;
-      for (int kk = 0; kk <= last; ++kk) {
-        const float zl = -pl[pidx(p + kk)] * rp.k;
-        if (zl > mS) {
-          S = S * fast_ex2(mS - zl) + 1.f;
-          mS = zl;
-        } else {
-          S += fast_ex2(zl - mS);
-        }
-        if (kk >= UA) {
-          const float zr = -pr[pidx(p + kk)] * rp.k;
-          const float mc = fmaxf(mS, zr);
-          const float cl = -(mc + fast_lg2(S * fast_ex2(mS - mc) + fast_ex2(zr - mc)));  // log2 of the term
-          if (cl > mA) {
-            A = A * fast_ex2(mA - cl) + 1.f;
-            mA = cl;
-          } else {
-            A += fast_ex2(cl - mA);
-          }
-        }
-      }
-      const float res = (mA + fast_lg2(A)) * rp.invk;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j == i) o[j].x[0] = res;
+      o[i].x[0] = smooth_until_fix_one<UA>(p, n + UA - 1, rp.k, rp.invk, lplane(scr, 0), rplane(scr, 0));
     }
   }
 };
@@ -1274,36 +1273,33 @@ PF_DEV void fin8(const TC& c, const RP& rp, const typename R::A (&acc)[8], Vec<V
 
 // smooth only: outputs whose block-shifted sum lost its precision to underflow are recomputed
 // exactly from the staged operand (rare: needs a dynamic range above 2^100 inside one tile)
+template <int MODE>
+PF_COLD float smooth_fix_one(int lo, int hi, float k, float invk, const float* vplane) {
+  using R = Red<SEM_SMOOTH, MODE>;
+  if (lo > hi) return f_nan();
+  RP rp{};
+  rp.k = k;
+  rp.invk = invk;
+  float mx = -f_inf();
+  for (int q = lo; q <= hi; ++q) mx = fmaxf(mx, R::expo(Vec<1>{{vplane[pidx(q)]}}, rp));
+  float s = 0.f;
+  for (int q = lo; q <= hi; ++q) s += fast_ex2(R::expo(Vec<1>{{vplane[pidx(q)]}}, rp) - mx);
+  rp.shift = mx;
+  return R::fin(Vec<1>{{s}}, 1.f, rp).x[0];
+}
 template <int MODE, int FA, int FB, int NT>
 PF_DEV void smooth_fix8(const TC& c, const RP& rp, const float* vplane, const Vec<1> (&acc)[8], Vec<1> (&o)[8]) {
-  using R = Red<SEM_SMOOTH, MODE>;
   float m = acc[0].x[0];
 #pragma unroll
   for (int i = 1; i < 8; ++i) m = fminf(m, acc[i].x[0]);
   if (m >= kSmoothTiny) return;
-#pragma unroll 1
-  for (int i = 0; i < 8; ++i) {
-    float a_i = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j == i) a_i = acc[j].x[0];
-    if (a_i >= kSmoothTiny || c.p0 + i >= c.nlive) continue;
-    int lo = c.p0 + i + FA, hi = c.p0 + i + FB;
+  for (int i = 0; i < 8; ++i) {
+    if (acc[i].x[0] >= kSmoothTiny || c.p0 + i >= c.nlive) continue;
+    int hi = c.p0 + i + FB;
     if (hi > c.nlive - 1) hi = c.nlive - 1;
     if (hi > 8 * NT - 1) hi = 8 * NT - 1;
-    float res = f_nan();
-    if (lo <= hi) {
-      float mx = -f_inf();
-      for (int q = lo; q <= hi; ++q) mx = fmaxf(mx, R::expo(Vec<1>{{vplane[pidx(q)]}}, rp));
-      float s = 0.f;
-      for (int q = lo; q <= hi; ++q) s += fast_ex2(R::expo(Vec<1>{{vplane[pidx(q)]}}, rp) - mx);
-      RP r2 = rp;
-      r2.shift = mx;
-      res = R::fin(Vec<1>{{s}}, 1.f, r2).x[0];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j == i) o[j].x[0] = res;
+    o[i].x[0] = smooth_fix_one<MODE>(c.p0 + i + FA, hi, rp.k, rp.invk, vplane);
   }
 }
 
@@ -1709,25 +1705,24 @@ PF_DEV void gm_adj_apply(const TC& c, const RP& rp, const Vec<2> (&w)[8], const 
 
 // smooth: exact scatter of the outputs in `lostmask` (rare path, entered by the whole CTA when any
 // thread has one).  vplane: staged operand values (after negation); fix: zeroed plane.
+template <int MODE>
+PF_COLD void smooth_adj_scatter_one(int lo, int hi, float gi, float oi, float k, const float* vplane, float* fix) {
+  using AD = Adj<SEM_SMOOTH, MODE>;
+  RP rp{};
+  rp.k = k;
+  for (int q = lo; q <= hi; ++q) simt::atomic_add(&fix[pidx(q)], gi * AD::pair_weight(oi, vplane[pidx(q)], rp));
+}
 template <int MODE, int FA, int FB, int NT>
 PF_DEV void smooth_adj_scatter(const TC& c, const RP& rp, unsigned lostmask, const float (&g)[8], const Vec<1> (&o)[8],
                                const float* vplane, float* fix) {
-  using AD = Adj<SEM_SMOOTH, MODE>;
-#pragma unroll 1
+#pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (!((lostmask >> i) & 1)) continue;
-    float gi = 0.f, oi = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j == i) {
-        gi = g[j];
-        oi = o[j].x[0];
-      }
     const int p = c.p0 + i;
-    int lo = p + FA, hi = p + FB;
+    int hi = p + FB;
     if (hi > c.nlive - 1) hi = c.nlive - 1;
     if (hi > 8 * NT - 1) hi = 8 * NT - 1;
-    for (int q = lo; q <= hi; ++q) simt::atomic_add(&fix[pidx(q)], gi * AD::pair_weight(oi, vplane[pidx(q)], rp));
+    smooth_adj_scatter_one<MODE>(p + FA, hi, g[i], o[i].x[0], rp.k, vplane, fix);
   }
 }
 
@@ -1790,42 +1785,42 @@ PF_DEV float lse2(float a, float b) {  // log2(2^a + 2^b)
   const float m = fmaxf(a, b);
   return m + fast_lg2(fast_ex2(a - m) + fast_ex2(b - m));
 }
+template <int UA, int UB>
+PF_COLD void smooth_until_scatter_one(int p, int last, float gi, float k, const float* lpl, const float* rpl, float* gl, float* gr) {
+  float cbuf[UB + 1];
+  float LS = -f_inf(), LA = -f_inf();
+  for (int kk = 0; kk <= last; ++kk) {
+    const int q = pidx(p + kk);
+    const float zl = -lpl[q] * k;
+    LS = kk == 0 ? zl : lse2(LS, zl);
+    if (kk >= UA) {
+      const float ci = -lse2(LS, -rpl[q] * k);
+      cbuf[kk] = ci;
+      LA = kk == UA ? ci : lse2(LA, ci);
+    }
+  }
+  float LD = -f_inf();
+  for (int kk = last; kk >= 0; --kk) {
+    const int q = pidx(p + kk);
+    if (kk >= UA) {
+      const float ci = cbuf[kk];
+      LD = kk == last ? 2.f * ci : lse2(LD, 2.f * ci);
+      simt::atomic_add(&gr[q], gi * fast_ex2(2.f * ci - rpl[q] * k - LA));
+    }
+    simt::atomic_add(&gl[q], gi * fast_ex2(LD - lpl[q] * k - LA));
+  }
+}
 template <int UA, int UB, int NT>
 PF_DEV void smooth_until_scatter(const TC& c, const RP& rp, unsigned mask, const float (&g)[8], const float* lpl, const float* rpl, float* gl,
                                  float* gr) {
-  float cbuf[UB + 1];
-#pragma unroll 1
+#pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (!((mask >> i) & 1u)) continue;
-    float gi = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j == i) gi = g[j];
     const int p = c.p0 + i;
     int last = c.nlive - 1 - p;
     if (last > UB) last = UB;
-    if (gi == 0.f || last < UA) continue;
-    float LS = -f_inf(), LA = -f_inf();
-    for (int kk = 0; kk <= last; ++kk) {
-      const int q = pidx(p + kk);
-      const float zl = -lpl[q] * rp.k;
-      LS = kk == 0 ? zl : lse2(LS, zl);
-      if (kk >= UA) {
-        const float ci = -lse2(LS, -rpl[q] * rp.k);
-        cbuf[kk] = ci;
-        LA = kk == UA ? ci : lse2(LA, ci);
-      }
-    }
-    float LD = -f_inf();
-    for (int kk = last; kk >= 0; --kk) {
-      const int q = pidx(p + kk);
-      if (kk >= UA) {
-        const float ci = cbuf[kk];
-        LD = kk == last ? 2.f * ci : lse2(LD, 2.f * ci);
-        simt::atomic_add(&gr[q], gi * fast_ex2(2.f * ci - rpl[q] * rp.k - LA));
-      }
-      simt::atomic_add(&gl[q], gi * fast_ex2(LD - lpl[q] * rp.k - LA));
-    }
+    if (g[i] == 0.f || last < UA) continue;
+    smooth_until_scatter_one<UA, UB>(p, last, g[i], rp.k, lpl, rpl, gl, gr);
   }
 }
 // ---- smooth until, backward, FAST PATH: the adjoint of UntilOp::phase2_smooth in the block-shifted linear domain.

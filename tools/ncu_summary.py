@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise ncu captures from gpurun_out/ into profiles/ (tracked evidence).
 
-    python tools/ncu_summary.py <tag> <prof.ncu-rep> [<launches.csv>]
+    python tools/ncu_summary.py <tag> <prof.ncu-rep> [<launches.csv>] [--traffic <cfg>:<kind><<semantics>>]
 
 Writes profiles/<tag>_key_metrics.csv (one `--set full` capture of the dominant kernel: time, DRAM
 bytes, issue utilisation, occupancy, registers, shared memory), profiles/<tag>_details.txt (the
@@ -46,8 +46,14 @@ KEYS = [
 
 
 def main() -> None:
-    tag, rep = sys.argv[1], sys.argv[2]
-    launches = sys.argv[3] if len(sys.argv) > 3 else None
+    args = list(sys.argv[1:])
+    traffic_key = None
+    if "--traffic" in args:  # record dram__bytes_read + dram__bytes_write of this launch for bench.py's roofline.traffic
+        k = args.index("--traffic")
+        traffic_key = args[k + 1]
+        del args[k:k + 2]
+    tag, rep = args[0], args[1]
+    launches = args[2] if len(args) > 2 else None
     os.makedirs("profiles", exist_ok=True)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -58,6 +64,19 @@ def main() -> None:
             if k in hdr:
                 i = hdr.index(k)
                 f.write(f"{k},{vals[i]},{units[i]}\n")
+    if traffic_key:
+        import json
+
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(k)
+            tot += float(vals[i]) * scale[units[i]]
+        path = "profiles/traffic.json"
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur[traffic_key] = tot
+        with open(path, "w") as f:
+            json.dump(cur, f, indent=1, sort_keys=True)
     det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
     with open(f"profiles/{tag}_details.txt", "w") as f:
         f.write(det)
