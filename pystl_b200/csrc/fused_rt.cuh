@@ -892,8 +892,9 @@ struct UntilOp {
   // is h_i + M_q, so l_q and r_q are lifted (one lg2 each) once per thread and position -- and (b)
   // the exp / log round trip between the prefix And and the pair And removed: when every l is
   // positive, log1p(y_i) IS the prefix mean of log1p(l) (y_i = expm1 of it), so the pair And reads the
-  // accumulator directly.  Per candidate: one rcp (1 / k), one ex2 (geometric pair), one lg2 (Or
-  // lift) instead of about seven transcendentals.  Sums of logarithms are carried in log2 units.
+  // accumulator directly.  Per candidate: one ex2 (geometric pair) and one lg2 (Or lift) -- 1 / cnt comes from an
+  // eleven-entry table per group of four positions -- instead of about seven transcendentals.  Sums of logarithms
+  // are carried in log2 units.
   PF_DEV static void phase2_agm(float* scr, const TC& c, float w0, float w1, V (&o)[8]) {
     const int f0 = c.p0 >> 2;
     constexpr int FMAX = LEXT / 4 - 1;
@@ -903,8 +904,7 @@ struct UntilOp {
     const int kmax = clip_kmax(c);
     float hneg[8], hlog[8], o0[8], o1[8];
     // one candidate of output i: prefix accumulator (pneg, plog) over k samples, right operand r
-    auto cand = [&](int i, float pneg, float plog, float kf, float rnegw, float rlogw, bool rpos) {
-      const float invk = fast_rcp(kf);
+    auto cand = [&](int i, float pneg, float plog, float invk, float rnegw, float rlogw, bool rpos) {
       const bool flag = plog == f_inf();  // some l <= 0: arithmetic prefix (agm.py:71)
       const float zA = fmaf(w0, flag ? pneg * invk : 0.f, rnegw) * invsw;
       const float zG = fast_ex2(fmaf(w0 * invk, plog, rlogw) * invsw) - 1.f;
@@ -934,7 +934,7 @@ struct UntilOp {
         for (int q = i; q < 8; ++q) {
           pn += ln[q];
           pl += ll[q];
-          if (q - i >= UA && q - i <= UB && q <= kmax) cand(i, pn, pl, (float)(q - i + 1), rn[q], rl[q], ro[q] > 0.f);
+          if (q - i >= UA && q - i <= UB && q <= kmax) cand(i, pn, pl, 1.f / (float)(q - i + 1), rn[q], rl[q], ro[q] > 0.f);
         }
         hneg[i] = pn;
         hlog[i] = pl;
@@ -948,6 +948,10 @@ struct UntilOp {
     auto group = [&](int g, auto all) {
       const int fc = (f0 + g) < FMAX ? (f0 + g) : FMAX;
       const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
+      // 1 / cnt for cnt = 4 g + (k - i) + 1, k - i in [-7, 3]: eleven reciprocals serve the group's 32 candidates
+      float ik[11];
+#pragma unroll
+      for (int j = 0; j < 11; ++j) ik[j] = fast_rcp((float)(4 * g + j - 6));
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int kq = 4 * g + k;
@@ -957,10 +961,9 @@ struct UntilOp {
         Ml += l <= 0.f ? f_inf() : fast_lg2(1.f + l);
         const float rn = w1 * fminf(r, 0.f), rl = w1 * fast_lg2(1.f + r);
         const bool rpos = r > 0.f;
-        const float kf = (float)(kq + 1);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (decltype(all)::value || (kq - i >= UA && kq - i <= UB)) cand(i, hneg[i] + Mn, hlog[i] + Ml, kf - (float)i, rn, rl, rpos);
+          if (decltype(all)::value || (kq - i >= UA && kq - i <= UB)) cand(i, hneg[i] + Mn, hlog[i] + Ml, ik[k - i + 7], rn, rl, rpos);
       }
     };
 #pragma unroll
@@ -977,8 +980,144 @@ struct UntilOp {
     }
   }
 
+  // D-GMSR fast path (dgmsr.py:88-118 with p = 1, unit weights_pair, uniform weights_left / weights_right).  Same shared
+  // tail as the AGM path on the prefix accumulator (sum of l^2 over l <= 0; sum of 2 lg2 l, or +inf once some l <= 0), and
+  // the chain  y = And(prefix), z = And(y, r), U = Or(z)  written out per case instead of through the generic
+  // lift / fin chain (thirteen transcendentals per candidate):
+  //   prefix holds some l <= 0:  y = sqrt(eps) - sqrt(eps + a0 / cnt) <= 0,  z = sqrt(eps) - sqrt(eps + (y^2 + min(r, 0)^2) / 2)
+  //                              -- two square roots, and one lg2 for the Or lift of z < 0;
+  //   every l > 0, r <= 0:       z = sqrt(eps) - sqrt(eps + r^2 / 2) depends on the position only (y > 0 carries no weight);
+  //   every l > 0, r > 0:        y = 2^(logaddexp2(cnt lg2 eps, a1) / (2 cnt)) - sqrt(eps),  z = (eps^2 + (y r)^2)^(1/4) - sqrt(eps)
+  //                              (the two-operand form of dgmsr2_unit: two square roots, no logarithm); z > 0 joins the Or squared.
+  // A group of positions behind some l <= 0 of the shared tail holds flagged prefixes only and takes the first case alone.
+  // Assumes |l|, |r| < 1e9 (y r is squared in fp32).
+  PF_DEV static void phase2_dgmsr(float* scr, const TC& c, const RP& rp, V (&o)[8]) {
+    const int f0 = c.p0 >> 2;
+    constexpr int FMAX = LEXT / 4 - 1;
+    const F4* L4 = reinterpret_cast<const F4*>(lplane(scr, 0));
+    const F4* R4 = reinterpret_cast<const F4*>(rplane(scr, 0));
+    const int kmax = clip_kmax(c);
+    const float eps = rp.eps_p, se = rp.sqrt_eps, lge = rp.ln_eps * kLog2e;  // (p = 1: eps_p = eps)
+    float hn[8], hl[8], o0[8], o1[8];
+    // the Or accumulator of output i takes candidate z (dgmsr.py:110-119: Or = -And(-z))
+    auto take = [&](int i, float z) {
+      const bool nn = z >= 0.f;
+      o0[i] += nn ? z * z : 0.f;
+      o1[i] += nn ? f_inf() : 2.f * fast_lg2(-z);
+    };
+    // candidate with a flagged prefix: a0 = sum of l^2 over the l <= 0 of the prefix, r2n = min(r, 0)^2
+    auto cand_flag = [&](int i, float a0, float invk, float r2n) {
+      const float y = se - fast_sqrt(fmaf(a0, invk, eps));
+      take(i, se - fast_sqrt(fmaf(0.5f, fmaf(y, y, r2n), eps)));
+    };
+    // general candidate; zr: the value of an all-positive prefix paired with this r <= 0
+    auto cand = [&](int i, float a0, float a1, float invk, float kf, float r, float r2n, float zr) {
+      const bool flag = a1 == f_inf();
+      const float yf = se - fast_sqrt(fmaf(a0, invk, eps));
+      const float zf = se - fast_sqrt(fmaf(0.5f, fmaf(yf, yf, r2n), eps));
+      const float u = kf * lge;
+      const float lae = fmaxf(u, a1) + fast_lg2(1.f + fast_ex2(-fabsf(u - a1)));
+      const float yg = fast_ex2(0.5f * invk * lae) - se;
+      const float q = yg * r;
+      const float zg = fast_sqrt(fast_sqrt(fmaf(q, q, eps * eps))) - se;
+      take(i, flag ? zf : (r > 0.f ? zg : zr));
+    };
+    {  // own chunk: triangular
+      const F4 la = L4[pf4(f0)], lb = L4[pf4(f0 + 1)], ra = R4[pf4(f0)], rb = R4[pf4(f0 + 1)];
+      const float lo[8] = {la.v[0], la.v[1], la.v[2], la.v[3], lb.v[0], lb.v[1], lb.v[2], lb.v[3]};
+      const float ro[8] = {ra.v[0], ra.v[1], ra.v[2], ra.v[3], rb.v[0], rb.v[1], rb.v[2], rb.v[3]};
+      float l2[8], ll[8], r2[8], zr[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float ln = fminf(lo[q], 0.f), rn = fminf(ro[q], 0.f);
+        l2[q] = ln * ln;
+        ll[q] = lo[q] <= 0.f ? f_inf() : 2.f * fast_lg2(lo[q]);
+        r2[q] = rn * rn;
+        zr[q] = se - fast_sqrt(fmaf(0.5f, r2[q], eps));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float pn = 0.f, pl = 0.f;
+        o0[i] = 0.f;
+        o1[i] = 0.f;
+#pragma unroll
+        for (int q = i; q < 8; ++q) {
+          pn += l2[q];
+          pl += ll[q];
+          if (q - i >= UA && q - i <= UB && q <= kmax) cand(i, pn, pl, 1.f / (float)(q - i + 1), (float)(q - i + 1), ro[q], r2[q], zr[q]);
+        }
+        hn[i] = pn;
+        hl[i] = pl;
+      }
+    }
+    float Mn = 0.f, Ml = 0.f;
+    constexpr int KS0 = UA + 7 > 8 ? UA + 7 : 8;
+    constexpr int KS = (KS0 + 3) & ~3;
+    constexpr int KE = ((UB + 1) & ~3) > KS ? ((UB + 1) & ~3) : KS;
+    auto group = [&](int g, auto all) {
+      const int fc = (f0 + g) < FMAX ? (f0 + g) : FMAX;
+      const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
+      float ik[11];  // 1 / cnt for cnt = 4 g + (k - i) + 1, k - i in [-7, 3]
+#pragma unroll
+      for (int j = 0; j < 11; ++j) ik[j] = fast_rcp((float)(4 * g + j - 6));
+      if (Ml == f_inf()) {  // some l <= 0 in the shared tail already: every candidate of the group is flagged
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int kq = 4 * g + k;
+          if (kq > kmax) break;
+          const float ln = fminf(ql.v[k], 0.f), rn = fminf(qr.v[k], 0.f);
+          Mn = fmaf(ln, ln, Mn);
+          const float r2n = rn * rn;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (decltype(all)::value || (kq - i >= UA && kq - i <= UB)) cand_flag(i, hn[i] + Mn, ik[k - i + 7], r2n);
+        }
+        return;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int kq = 4 * g + k;
+        if (kq > kmax) break;
+        const float l = ql.v[k], r = qr.v[k];
+        const float ln = fminf(l, 0.f), rn = fminf(r, 0.f);
+        Mn = fmaf(ln, ln, Mn);
+        Ml += l <= 0.f ? f_inf() : 2.f * fast_lg2(l);
+        const float r2n = rn * rn;
+        const float zr = se - fast_sqrt(fmaf(0.5f, r2n, eps));
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (decltype(all)::value || (kq - i >= UA && kq - i <= UB))
+            cand(i, hn[i] + Mn, hl[i] + Ml, ik[k - i + 7], (float)(kq - i + 1), r, r2n, zr);
+      }
+    };
+#pragma unroll
+    for (int g = 2; g < KS / 4; ++g) group(g, BoolC<false>{});
+#pragma unroll 1
+    for (int g = KS / 4; g < KE / 4; ++g) group(g, BoolC<true>{});
+#pragma unroll
+    for (int g = KE / 4; g <= (UB + 7) / 4; ++g) group(g, BoolC<false>{});
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int last = kmax - i < UB ? kmax - i : UB;  // clipped candidate count (dgmsr.py:13-25)
+      const float nf = (float)(last - UA + 1);
+      const float invn = fast_rcp(nf);
+      // Or = -And(-z): some z >= 0 -> arithmetic branch over those; else the geometric branch over -z > 0
+      const float ha = se - fast_sqrt(fmaf(o0[i], invn, eps));
+      const float u = nf * lge;
+      const float lae = fmaxf(u, o1[i]) + fast_lg2(1.f + fast_ex2(-fabsf(u - o1[i])));
+      const float hg = fast_ex2(0.5f * invn * lae) - se;
+      o[i].x[0] = last < UA ? f_nan() : -((o1[i] == f_inf()) ? ha : hg);
+    }
+  }
+
   PF_DEV static void phase2(float* scr, const TC& c, const RP& rp, float w0, float w1, V (&o)[8], UntilState<SEM> (&st)[8]) {
     const int p0 = c.p0;
+    if constexpr (SEM == SEM_DGMSR && UA <= 64) {
+      if (PYSTL_P(rp) == 1 && w0 == 1.f && w1 == 1.f) {
+        phase2_dgmsr(scr, c, rp, o);
+        return;
+      }
+    }
     if constexpr (SEM == SEM_AGM && UA <= 64) {
       if (cum_fast_ok(c)) {
         phase2_agm(scr, c, w0, w1, o);

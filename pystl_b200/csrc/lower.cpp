@@ -505,7 +505,7 @@ struct Lowerer {
       for (int j = 0; j < in.nsrc; ++j) {
         if (p.adj_of[in.src[j]] < 0) {
           p.adj_of[in.src[j]] = (int16_t)take();
-          in.adj_first |= (uint8_t)(1u << j);
+          in.adj_first |= (uint16_t)(1u << j);
         }
       }
       // the result's adjoint and value are dead now; so is any operand value this was the last reader of

@@ -24,10 +24,10 @@ typedef unsigned long long uintptr_t;
 namespace pystl {
 
 constexpr int kChunk = 8;       // samples per thread (two float4)
-constexpr int kMaxSrc = 8;      // operands of one n-ary instruction
+constexpr int kMaxSrc = 16;     // operands of one n-ary instruction
 constexpr int kMaxTerms = 8;    // == PYSTL_MAX_TERMS
-constexpr int kMaxPreds = 16;   // distinct affine predicates per formula
-constexpr int kMaxInstr = 40;   // lowered instructions per formula
+constexpr int kMaxPreds = 32;   // distinct affine predicates per formula
+constexpr int kMaxInstr = 64;   // lowered instructions per formula (the kernel parameter block stays below 16 KB of the 32 KB limit)
 constexpr int kMaxThreads = 1024;
 constexpr int kMaxSlots = kMaxPreds + kMaxInstr + 8;  // value slots of one formula
 constexpr int kMaxWeights = 1024;  // window-position weights of one formula (agm / dgmsr, fused tier)
@@ -76,8 +76,8 @@ struct TInstr {
   int16_t nsrc;
   int16_t src[kMaxSrc];  // plane slots
   uint16_t negmask;      // bit i: operand i is negated (Not folded into the consumer)
-  int8_t unbounded;      // T_UNTIL: b is the horizon
-  uint8_t adj_first;     // backward: bit i: this instruction is the first to write operand i's adjoint
+  int16_t unbounded;     // T_UNTIL: b is the horizon
+  uint16_t adj_first;    // backward: bit i: this instruction is the first to write operand i's adjoint
   int32_t a, b;          // window offsets relative to t (signed: the backward pass looks back)
   float w[kMaxSrc];      // n-ary weights; T_UNTIL: w[0], w[1] = weights_pair
   float sw;              // sum of the n-ary weights
