@@ -1006,6 +1006,7 @@ struct Gen {
       o.line("    smem + %d, smem + %d, smem + %d, uk%d, upos%d, uz0%d, uz1%d, urr%d);", G0, G1, GR, i, i, i, i, i);
       o.line("if (live) agm_until_adj_finish<%s, %s>(U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), c.tid, P.ins[%d].w[0], P.ins[%d].w[1], uz0%d, uz1%d, urr%d, g%d, g%d);",
              nl ? "true" : "false", nr ? "true" : "false", i, scr_off[i], i, scr_off[i], i, i, i, i, i, (int)in.src[0], (int)in.src[1]);
+      o.line("simt::sync();  // the hand-off planes go back to the window scratch");
       return;
     }
     o.line("// adjoint of until %d: per-output sweeps, scatter through shared memory", i);

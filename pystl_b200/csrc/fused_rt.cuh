@@ -2008,9 +2008,9 @@ PF_DEV unsigned smooth_until_adj_coeff(const TC& c, const float (&g)[8], const f
   return lost;
 }
 // All threads of the CTA call it (it contains barriers).  The chunks are visited in LOCKSTEP: in step cc every thread
-// finishes the positions of chunk tid + cc and hands the two partial sums per position to that chunk's owner through
-// gl / gr -- one writer per chunk and step, so plain 128-bit stores instead of atomics (a shared-memory float atomic is a
-// compare-and-swap loop); the owner adds them to its registers between the step's two barriers.
+// finishes the positions of chunk tid + cc and adds its two partial sums per position to that chunk's slots of gl / gr --
+// one writer per chunk and step, so a plain 128-bit read-modify-write instead of atomics (a shared-memory float atomic
+// is a compare-and-swap loop) and ONE barrier per step; the owner collects its slots once, after the last step.
 template <int UA, int UB, int NT>
 PF_DEV void smooth_until_adj_walk(const TC& c, bool live, const float* la, const float* rh, const float* ag, float* gl, float* gr,
                                   const float (&ci)[8], float (&gl_own)[8], float (&gr_own)[8]) {
@@ -2080,20 +2080,26 @@ PF_DEV void smooth_until_adj_walk(const TC& c, bool live, const float* la, const
 #pragma unroll
       for (int k = 0; k < 8; ++k) zc[k] = rc[k] = 0.f;
     }
-    if (c.tid + cc < NT) {
-      store8(gl, c.tid + cc, zc);
-      store8(gr, c.tid + cc, rc);
-    }
-    simt::sync();
-    if (c.tid >= cc) {
+    if (cc == CMAX) {  // the first step initialises every slot: its writer's numbers, or zeros where there is no writer
+      if (c.tid + cc < NT) {
+        store8(gl, c.tid + cc, zc);
+        store8(gr, c.tid + cc, rc);
+      }
+      if (c.tid < CMAX) {
+        plane_zero8(gl, c.tid);
+        plane_zero8(gr, c.tid);
+      }
+    } else if (c.tid + cc < NT && cc <= cend) {  // one writer per chunk and step: a plain read-modify-write
       float a[8], b[8];
-      load8(gl, c.tid, a);
-      load8(gr, c.tid, b);
+      load8(gl, c.tid + cc, a);
+      load8(gr, c.tid + cc, b);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        gl_own[k] += a[k];
-        gr_own[k] += b[k];
+        a[k] += zc[k];
+        b[k] += rc[k];
       }
+      store8(gl, c.tid + cc, a);
+      store8(gr, c.tid + cc, b);
     }
     simt::sync();
   };
@@ -2110,6 +2116,16 @@ PF_DEV void smooth_until_adj_walk(const TC& c, bool live, const float* la, const
   } else {
 #pragma unroll
     for (int cc = CMAX; cc >= 1; --cc) step(cc, BoolC<false>{});
+  }
+  if (live) {  // what the threads before this one handed over
+    float a[8], b[8];
+    load8(gl, c.tid, a);
+    load8(gr, c.tid, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      gl_own[k] += a[k];
+      gr_own[k] += b[k];
+    }
   }
   if (!active) return;
   // own chunk: triangular, in registers
@@ -2340,23 +2356,31 @@ PF_DEV void agm_until_adj_walk(const TC& c, bool live, float w0, float w1, const
 #pragma unroll
       for (int k = 0; k < 8; ++k) zc0[k] = zc1[k] = rc[k] = 0.f;
     }
-    if (c.tid + cc < NT) {
-      store8(g0p, c.tid + cc, zc0);
-      store8(g1p, c.tid + cc, zc1);
-      store8(grp, c.tid + cc, rc);
-    }
-    simt::sync();
-    if (c.tid >= cc) {
+    if (cc == CMAX) {  // the first step initialises every slot: its writer's numbers, or zeros where there is no writer
+      if (c.tid + cc < NT) {
+        store8(g0p, c.tid + cc, zc0);
+        store8(g1p, c.tid + cc, zc1);
+        store8(grp, c.tid + cc, rc);
+      }
+      if (c.tid < CMAX) {
+        plane_zero8(g0p, c.tid);
+        plane_zero8(g1p, c.tid);
+        plane_zero8(grp, c.tid);
+      }
+    } else if (c.tid + cc < NT && cc <= cend) {  // one writer per chunk and step: a plain read-modify-write
       float a[8], b[8], d[8];
-      load8(g0p, c.tid, a);
-      load8(g1p, c.tid, b);
-      load8(grp, c.tid, d);
+      load8(g0p, c.tid + cc, a);
+      load8(g1p, c.tid + cc, b);
+      load8(grp, c.tid + cc, d);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        z0_own[k] += a[k];
-        z1_own[k] += b[k];
-        r_own[k] += d[k];
+        a[k] += zc0[k];
+        b[k] += zc1[k];
+        d[k] += rc[k];
       }
+      store8(g0p, c.tid + cc, a);
+      store8(g1p, c.tid + cc, b);
+      store8(grp, c.tid + cc, d);
     }
     simt::sync();
   };
@@ -2372,6 +2396,18 @@ PF_DEV void agm_until_adj_walk(const TC& c, bool live, float w0, float w1, const
   } else {
 #pragma unroll
     for (int cc = CMAX; cc >= 1; --cc) step(cc, BoolC<false>{});
+  }
+  if (live) {  // what the threads before this one handed over
+    float a[8], b[8], d[8];
+    load8(g0p, c.tid, a);
+    load8(g1p, c.tid, b);
+    load8(grp, c.tid, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      z0_own[k] += a[k];
+      z1_own[k] += b[k];
+      r_own[k] += d[k];
+    }
   }
   if (!active) return;
   // own chunk: triangular, in registers
