@@ -301,6 +301,19 @@ struct Gen {
     return buf;
   }
 
+  // ---- which values can be NaN: an Until without a candidate (lower bound above the rest of the trace) and a weighted
+  // window whose clipped weights sum to zero write NaN where the reference raises, and NaN flows through everything above
+  std::vector<char> may_nan;
+  void plan_nan() {
+    may_nan.assign(kMaxSlots, 0);
+    for (int i = 0; i < P.n_instr; ++i) {
+      const TInstr& in = P.ins[i];
+      bool n = (is_until(in) && in.a > 0) || is_wwin(in);
+      for (int j = 0; j < in.nsrc; ++j) n |= may_nan[in.src[j]] != 0;
+      may_nan[in.dst] = n;
+    }
+  }
+
   // ---- smooth only: which value-range bounds are consumed (a window shifts its exponentials by
   // a bound of its operand; bounds propagate analytically through the operators above)
   std::vector<char> need_lo, need_hi;
@@ -806,12 +819,12 @@ struct Gen {
         o.line("{ float tt[8]; load8(smem + %d, c.tid, tt); _Pragma(\"unroll\") for (int i = 0; i < 8; ++i) ts[i] = V{{tt[i]}}; }", stash_off[i]);
         o.line("R%d::A xh[8];", i);
         o.line("lift8<R%d, VW>(c, rp%d, ts, xh);", i, i);
-        o.line("smooth_adj_apply<%s>(w, xh, g%d);", neg ? "true" : "false", s);
+        o.line("smooth_adj_apply<%s, %s>(w, xh, g%d);", neg ? "true" : "false", may_nan[s] ? "true" : "false", s);
       } else {
-        o.line("smooth_adj_apply<%s>(w, x%d, g%d);", neg ? "true" : "false", i, s);
+        o.line("smooth_adj_apply<%s, %s>(w, x%d, g%d);", neg ? "true" : "false", may_nan[s] ? "true" : "false", i, s);
       }
     }
-    else o.line("gm_adj_apply<SEM, %s, %s>(c, rp, w, v%d, g%d);", mode_name(in.mode), neg ? "true" : "false", s, s);
+    else o.line("gm_adj_apply<SEM, %s, %s, %s>(c, rp, w, v%d, g%d);", mode_name(in.mode), neg ? "true" : "false", may_nan[s] ? "true" : "false", s, s);
     o.indent--;
     o.line("}");
     if (P.sem == SEM_SMOOTH) {
@@ -1034,6 +1047,7 @@ struct Gen {
   std::string backward() {
     plan();
     plan_bounds();
+    plan_nan();
     emit_header("backward (value and gradient)");
     o.line("PF_KERNEL(NT, %d) %s(const PF_GRID_CONSTANT TileProgram P, const PF_GRID_CONSTANT TileGeom g,", minb, kernel_name().c_str());
     o.line("    const float* __restrict__ signal, const float* __restrict__ grad_out, float scale, float* __restrict__ grad_signal,");

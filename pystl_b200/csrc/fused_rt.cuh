@@ -730,10 +730,17 @@ struct UntilOp {
   // candidate are NaN (the reference raises).
   PF_DEV static int clip_kmax(const TC& c) { return c.interior ? 0x3fffffff : c.nlive - 1 - c.p0; }
   PF_DEV static bool cum_fast_ok(const TC&) { return true; }
+  // CLIP = false: no window of this thread reaches the horizon (every thread of an interior tile, most threads of the last
+  // one) -- the per-position horizon tests fold away (the walk is ALU-pipe bound: they were 10 % of its instructions)
   PF_DEV static void phase2_cum(float* scr, const TC& c, V (&o)[8]) {
+    if (clip_kmax(c) >= UB + 7) phase2_cum_t<false>(scr, c, o);
+    else phase2_cum_t<true>(scr, c, o);
+  }
+  template <bool CLIP>
+  PF_DEV static void phase2_cum_t(float* scr, const TC& c, V (&o)[8]) {
     static_assert(UA >= 0 && UB >= UA, "bounded until");
     const int f0 = c.p0 >> 2;
-    const int kmax = clip_kmax(c);
+    const int kmax = CLIP ? clip_kmax(c) : 0x3fffffff;
     constexpr int FMAX = LEXT / 4 - 1;
     constexpr int KS0 = UA + 7 > 8 ? UA + 7 : 8;       // first offset at which every output has a candidate
     constexpr int KS = (KS0 + 3) & ~3;                 // ... rounded up to a 128-bit group
@@ -1317,7 +1324,7 @@ struct WeightedWinAdj {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float x = NEG ? -v[i].x[0] : v[i].x[0];
-      const float d = (c.p0 + i < c.nlive) ? AD::in_factor(acc[i], x, 1.f, rp) : 0.f;
+      const float d = (c.p0 + i < c.nlive && x == x) ? AD::in_factor(acc[i], x, 1.f, rp) : 0.f;  // (x NaN: the reference raises there)
       gs[i] += NEG ? -d : d;
     }
   }
@@ -1781,11 +1788,23 @@ PF_DEV void store_grad_image(const TC& c, long long T, const float* image, float
 // smooth: d out_t / d x_q = xhat_q / S_t with the forward's block-shifted xhat and S: k_t = g_t / S_t.
 // Outputs whose shifted sum lost its precision (S_t < 2^-100, recomputed exactly by the forward
 // pass) are left out here and scattered exactly afterwards (lostmask).
+// minimum that PROPAGATES a NaN (fminf drops it): SASS FMNMX.NAN
+PF_DEV float fmin_nan(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+#else
+  return (a != a || b != b) ? f_nan() : fminf(a, b);
+#endif
+}
 template <int MODE, int FA, int FB>
 PF_DEV unsigned smooth_adj_coeff(const TC& c, const float (&g)[8], const Vec<1> (&S)[8], Vec<1> (&k)[8]) {
+  // (a window over an operand that is NaN where the reference raises -- an Until with a lower bound, near the end of the
+  // trace -- has a NaN sum and a zero cotangent: the NaN must send the thread down the guarded path, 0 * rcp(NaN) is NaN)
   float m = S[0].x[0];
 #pragma unroll
-  for (int i = 1; i < 8; ++i) m = fminf(m, S[i].x[0]);
+  for (int i = 1; i < 8; ++i) m = fmin_nan(m, S[i].x[0]);
   if (m >= kSmoothTiny && c.p0 + 7 + FA <= c.nlive - 1) {  // every output has a window and a healthy sum
 #pragma unroll
     for (int i = 0; i < 8; ++i) k[i].x[0] = g[i] * fast_rcp(S[i].x[0]);
@@ -1823,21 +1842,26 @@ PF_DEV void gm_adj_coeff(const TC& c, const RP& rp, const float (&g)[8], const V
 }
 
 // ---- window adjoint, phase B: g_src[q] += sign * in_factor(x_q) * (window sum of k)[q]
-template <bool NEG>
+// NANSAFE: the operand can be NaN (where the reference raises: an Until with a lower bound or a weighted window near the end
+// of the trace; codegen.cpp: may_nan).  Every output that reads such a sample has a zero cotangent, so its window sum w is 0
+// there -- and 0 * NaN must not become the operand's adjoint.
+template <bool NEG, bool NANSAFE>
 PF_DEV void smooth_adj_apply(const Vec<1> (&w)[8], const Vec<1> (&xhat)[8], float (&gs)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float d = w[i].x[0] * xhat[i].x[0];  // xhat is 0 past the horizon
+    float d = w[i].x[0] * xhat[i].x[0];  // xhat is 0 past the horizon
+    if (NANSAFE) d = xhat[i].x[0] == xhat[i].x[0] ? d : 0.f;
     gs[i] += NEG ? -d : d;
   }
 }
-template <int SEM, int MODE, bool NEG>
+template <int SEM, int MODE, bool NEG, bool NANSAFE>
 PF_DEV void gm_adj_apply(const TC& c, const RP& rp, const Vec<2> (&w)[8], const Vec<1> (&v)[8], float (&gs)[8]) {
   using AD = Adj<SEM, MODE>;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float x = NEG ? -v[i].x[0] : v[i].x[0];
-    const float d = (c.p0 + i < c.nlive) ? AD::in_factor(w[i], x, 1.f, rp) : 0.f;
+    const bool ok = c.p0 + i < c.nlive && (!NANSAFE || x == x);
+    const float d = ok ? AD::in_factor(w[i], x, 1.f, rp) : 0.f;
     gs[i] += NEG ? -d : d;
   }
 }

@@ -189,6 +189,65 @@ def gm_backward_cases(light: bool = False):
     return out
 
 
+def random_until_backward_cases(light: bool = False):
+    """Randomised Until adjoints for the lockstep walks (smooth, agm) and the per-output sweeps (dgmsr): window bounds on
+    both sides of the chunk size, lower bounds up to 70 (> 64: no shared-tail path), upper bounds up to 150 (walks of 19
+    chunks), operands negated, the Until nested under Always / inside And, several tiles per trace."""
+    out = []
+    n = 4 if light else 36
+    for k in range(n):
+        rng = np.random.default_rng(8800 + k)
+        a = int(rng.choice([0, 0, 1, 3, 7, 8, 9, 17, 40, 70]))
+        b = a + int(rng.choice([0, 1, 5, 7, 8, 15, 16, 23, 24, 31, 50, 80]))
+        l = ("pred", {0: 1.0}, float(rng.normal(0.0, 0.5)))
+        r = ("pred", {1: float(rng.choice([-1.0, 1.0]))}, float(rng.normal(0.0, 0.5)))
+        if rng.random() < 0.3:
+            l = ("not", l)
+        if rng.random() < 0.3:
+            r = ("not", r)
+        spec = ("until", (a, b), l, r)
+        wrap = int(rng.integers(0, 4))
+        if wrap == 1:
+            spec = ("always", (0, int(rng.integers(1, 30))), spec)
+        elif wrap == 2:
+            spec = ("and", [spec, ("eventually", (0, 9), ("pred", {0: -1.0}, 0.3))])
+        elif wrap == 3:
+            spec = ("not", spec)
+        threads = int(rng.choice([32, 64, 96]))
+        T = int(rng.integers(8 * threads + 40, 8 * threads * 3)) if rng.random() < 0.7 else int(rng.integers(b + 2, 8 * threads))
+        sem, kw = [("smooth", {"temperature": float(rng.choice([1.0, 0.3, 0.05]))}), ("agm", {}), ("dgmsr", {"eps": 1e-8, "p": 1})][k % 3]
+        if light and sem == "dgmsr":
+            sem, kw = "agm", {}
+        if sem == "dgmsr" and b > 40:
+            b = a + 24
+            spec = ("until", (a, b), l, r)
+        out.append(dict(name=f"bwd/randU{k}[{a},{b}]w{wrap}/{sem}/T{T}/nt{threads}", spec=spec, sem=sem, kw=kw, B=2, T=T, D=2, threads=threads,
+                        seed=8900 + k))
+    return out
+
+
+def nan_flow_backward_cases(light: bool = False):
+    """An Until with a lower bound has no candidate near the end of the trace: its value is NaN there (the reference raises) and
+    flows as NaN through the windows / And / Or above it.  Every output that reads it has a zero cotangent -- and 0 * NaN must
+    not reach the adjoints of the samples before it (round 1 leaked it through the fast path of the Smooth window adjoint)."""
+    l, r = ("pred", {0: 1.0}, -0.68), ("pred", {1: -1.0}, -0.096)
+    U = ("until", (3, 45), l, r)
+    specs = {
+        "F5G29U": ("eventually", (0, 5), ("always", (2, 9), U)),
+        "G9(FxorU)": ("always", (0, 9), ("or", [("eventually", (4, 11), l), U])),
+        "F14(notU&Gy)": ("eventually", (1, 4), ("and", [("not", U), ("always", (0, 3), r)])),
+        "G9U7085": ("always", (0, 9), ("until", (70, 85), l, r)),
+    }
+    out = []
+    for si, (sem, kw) in enumerate([("smooth", {"temperature": 0.2})] + list(SEM_KW)):
+        for ni, (name, spec) in enumerate(specs.items()):
+            if light and (si + ni) % 4 != 0:
+                continue
+            out.append(dict(name=f"bwd/nanflow/{name}/{sem}{kw.get('p', '')}{kw.get('temperature', '')}", spec=spec, sem=sem, kw=kw, B=2, T=134, D=2,
+                            threads=96, seed=5))
+    return out
+
+
 def cumulative_backward_cases(light: bool = False):
     specs = {
         "G": ("always", (0, 20), ("pred", {0: 1.0}, -0.25)),

@@ -96,6 +96,44 @@ def test_smooth_until_backward(case):
     check(got.astype(np.float64), oracle_grad(case["spec"], "smooth", case["kw"], sig, g), "smooth", case["name"], rtol, atol)
 
 
+from fused_cases import random_until_backward_cases  # noqa: E402
+
+RUB = random_until_backward_cases(light=True)
+
+
+@pytest.mark.parametrize("case", RUB, ids=[c["name"] for c in RUB])
+def test_random_until_backward(case):
+    """Randomised Until adjoints (see tests/test_gpu_fused.py: the same generator, four cases here)."""
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    g = rng.standard_normal(sig.shape[:2]).astype(np.float32).astype(np.float64)
+    try:
+        got = fused_emu_lib.eval_backward(from_spec(case["spec"]), case["sem"], sig, g, force_threads=case["threads"], **case["kw"])
+    except NotImplementedError as e:
+        pytest.skip(str(e))
+    rtol, atol = grad_tol(case["sem"], case["kw"])
+    check(got.astype(np.float64), oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"], rtol, atol)
+
+
+from fused_cases import nan_flow_backward_cases  # noqa: E402
+
+NFB = nan_flow_backward_cases(light=True)
+
+
+@pytest.mark.parametrize("case", NFB, ids=[c["name"] for c in NFB])
+def test_nan_values_do_not_leak_into_gradients(case):
+    """Values that are NaN where the reference raises (an Until with a lower bound, near the end of the trace) sit under
+    windows and And / Or: the gradient of the valid outputs must be finite and equal to the oracle's."""
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    C = 2 if case["sem"] == "cumulative" else 1
+    g = rng.standard_normal(sig.shape[:2] + ((2,) if C == 2 else ())).astype(np.float32).astype(np.float64)
+    got = fused_emu_lib.eval_backward(from_spec(case["spec"]), case["sem"], sig, g, force_threads=case["threads"], **case["kw"]).astype(np.float64)
+    rtol, atol = grad_tol(case["sem"], case["kw"])
+    k = 2.0 if case["sem"] == "cumulative" else 1.0
+    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"], k * rtol, k * atol)
+
+
 from fused_cases import gm_backward_cases  # noqa: E402
 
 GMB = gm_backward_cases(light=True)

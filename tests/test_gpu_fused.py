@@ -248,6 +248,46 @@ def test_agm_dgmsr_until_and_weighted_backward(case):
     check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"])
 
 
+from fused_cases import random_until_backward_cases  # noqa: E402
+
+RUB = random_until_backward_cases()
+
+
+@pytest.mark.parametrize("case", RUB, ids=[c["name"] for c in RUB])
+def test_random_until_backward(case):
+    """Randomised window bounds, nesting, negations and tilings for the Until adjoints (the lockstep walks of smooth /
+    agm, the per-output sweep of dgmsr and of lower bounds above 64) against autograd through the dense oracle."""
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    g = rng.standard_normal(sig.shape[:2]).astype(np.float32).astype(np.float64)
+    try:
+        got = gpu_grad(case["spec"], case["sem"], case["kw"], sig, g, "fused", case["threads"])
+    except NotImplementedError as e:
+        assert "fit" in str(e) or "look-ahead" in str(e), e  # the forced CTA size is smaller than the formula's halo
+        pytest.skip(str(e))
+    rtol, atol = grad_tol(case["sem"], case["kw"])
+    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"], rtol, atol)
+
+
+from fused_cases import nan_flow_backward_cases  # noqa: E402
+
+NFB = nan_flow_backward_cases()
+
+
+@pytest.mark.parametrize("case", NFB, ids=[c["name"] for c in NFB])
+def test_nan_values_do_not_leak_into_gradients(case):
+    """Values that are NaN where the reference raises (an Until with a lower bound, near the end of the trace) sit under
+    windows and And / Or: the gradient of the valid outputs must be finite and equal to the oracle's."""
+    sig = case_signal(case)
+    rng = np.random.default_rng(case["seed"] + 1)
+    C = 2 if case["sem"] == "cumulative" else 1
+    g = rng.standard_normal(sig.shape[:2] + ((2,) if C == 2 else ())).astype(np.float32).astype(np.float64)
+    got = gpu_grad(case["spec"], case["sem"], case["kw"], sig, g, "fused", case["threads"])
+    rtol, atol = grad_tol(case["sem"], case["kw"])
+    k = 2.0 if case["sem"] == "cumulative" else 1.0
+    check(got, oracle_grad(case["spec"], case["sem"], case["kw"], sig, g), case["sem"], case["name"], k * rtol, k * atol)
+
+
 # ---------------------------------------------------------------------------- classic gradient (fused tier)
 from parity_util import mixed_signal, random_spec  # noqa: E402
 from test_emu_backward import has_until  # noqa: E402

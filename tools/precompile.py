@@ -54,7 +54,7 @@ def jobs(with_tests: bool):
 
         for c in fused_cases.forward_cases():
             out.append((c["spec"], c["sem"], c["kw"], c["T"], c["D"], c["threads"], False))
-        for c in fused_cases.backward_cases() + fused_cases.cumulative_backward_cases() + fused_cases.smooth_until_backward_cases() + fused_cases.gm_backward_cases():
+        for c in fused_cases.backward_cases() + fused_cases.cumulative_backward_cases() + fused_cases.smooth_until_backward_cases() + fused_cases.gm_backward_cases() + fused_cases.random_until_backward_cases() + fused_cases.nan_flow_backward_cases():
             out.append((c["spec"], c["sem"], c["kw"], c["T"], c["D"], c["threads"], True))
     return out
 
