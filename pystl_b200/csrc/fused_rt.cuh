@@ -730,17 +730,12 @@ struct UntilOp {
   // candidate are NaN (the reference raises).
   PF_DEV static int clip_kmax(const TC& c) { return c.interior ? 0x3fffffff : c.nlive - 1 - c.p0; }
   PF_DEV static bool cum_fast_ok(const TC&) { return true; }
-  // CLIP = false: no window of this thread reaches the horizon (every thread of an interior tile, most threads of the last
-  // one) -- the per-position horizon tests fold away (the walk is ALU-pipe bound: they were 10 % of its instructions)
+  // (a second instantiation without the per-position horizon tests for the threads no window of which is clipped was
+  // measured: cfg4 4.58 -> 4.51 ms, but cfg5 2.74 -> 3.19 ms -- two copies of the walk cost more than the tests)
   PF_DEV static void phase2_cum(float* scr, const TC& c, V (&o)[8]) {
-    if (clip_kmax(c) >= UB + 7) phase2_cum_t<false>(scr, c, o);
-    else phase2_cum_t<true>(scr, c, o);
-  }
-  template <bool CLIP>
-  PF_DEV static void phase2_cum_t(float* scr, const TC& c, V (&o)[8]) {
     static_assert(UA >= 0 && UB >= UA, "bounded until");
     const int f0 = c.p0 >> 2;
-    const int kmax = CLIP ? clip_kmax(c) : 0x3fffffff;
+    const int kmax = clip_kmax(c);
     constexpr int FMAX = LEXT / 4 - 1;
     constexpr int KS0 = UA + 7 > 8 ? UA + 7 : 8;       // first offset at which every output has a candidate
     constexpr int KS = (KS0 + 3) & ~3;                 // ... rounded up to a 128-bit group

@@ -125,7 +125,8 @@ void locate() {
   const char* c = getenv("PYSTL_B200_CACHE");
   g_cache_dir = (c && *c) ? std::string(c) : g_src_dir + "/build/fused";
   uint64_t h = 1469598103934665603ull;
-  for (const char* name : {"fused_rt.cuh", "tile_eval.h", "tile_bwd.h", "program.h"}) h = fnv1a(read_file(g_src_dir + "/" + name), h);
+  for (const char* name : {"fused_rt.cuh", "tile_eval.h", "tile_bwd.h", "program.h", "fused_host.h", "../../include/pystl_b200.h"})
+    h = fnv1a(read_file(g_src_dir + "/" + name), h);
   char buf[32];
   snprintf(buf, sizeof(buf), "%016llx", (unsigned long long)h);
   g_hdr_hash = buf;
@@ -145,11 +146,35 @@ int fail(char* msg, int msg_len, int code, const std::string& what) {
   return code;
 }
 
+// Next to every <key>.cubin (a plain cubin: cuobjdump / nvdisasm read it as it is) lies <key>.meta = [magic "PYSTLCB2"]
+// [u64 source length][u64 second hash of the source (FNV-1a, other seed)][u64 cubin length]: a truncated or foreign file,
+// or another formula's kernel under a colliding 64-bit key, is recognised and recompiled instead of being loaded.
+constexpr char kCacheMagic[8] = {'P', 'Y', 'S', 'T', 'L', 'C', 'B', '2'};
+struct CacheHeader {
+  char magic[8];
+  uint64_t src_len, src_hash2, cubin_len;
+};
+uint64_t second_hash(const std::string& s) { return fnv1a(s, 0x9e3779b97f4a7c15ull); }
+bool cache_entry_ok(const std::string& meta, const std::string& cubin, const FusedSource& src) {
+  if (meta.size() != sizeof(CacheHeader) || cubin.empty()) return false;
+  CacheHeader h;
+  memcpy(&h, meta.data(), sizeof(h));
+  return memcmp(h.magic, kCacheMagic, 8) == 0 && h.src_len == src.source.size() && h.src_hash2 == second_hash(src.source) &&
+         h.cubin_len == cubin.size();
+}
+
 // source -> cubin bytes (disk cache, else NVRTC)
-int get_cubin(const FusedSource& src, const std::string& key, std::string* cubin, char* msg, int msg_len) {
+int get_cubin(const FusedSource& src, const std::string& key, std::string* cubin, char* msg, int msg_len, bool ignore_cache = false) {
   const std::string path = g_cache_dir + "/" + key + ".cubin";
-  *cubin = read_file(path);
-  if (!cubin->empty()) return PYSTL_OK;
+  const std::string mpath = g_cache_dir + "/" + key + ".meta";
+  if (!ignore_cache) {
+    *cubin = read_file(path);
+    if (!cubin->empty()) {
+      if (cache_entry_ok(read_file(mpath), *cubin, src)) return PYSTL_OK;
+      unlink(path.c_str());  // stale, truncated or colliding entry: recompile (a read-only directory just recompiles every time)
+      unlink(mpath.c_str());
+    }
+  }
   if (!g_nvrtc.load()) return fail(msg, msg_len, PYSTL_E_UNSUPPORTED, g_nvrtc.why);
   nvrtcProgram prog = nullptr;
   nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.source.c_str(), "pystl_fused.cu", 0, nullptr, nullptr);
@@ -194,7 +219,18 @@ int get_cubin(const FusedSource& src, const std::string& key, std::string* cubin
     if (f) {
       f.write(cubin->data(), (std::streamsize)cubin->size());
       f.close();
+      CacheHeader h;
+      memcpy(h.magic, kCacheMagic, 8);
+      h.src_len = src.source.size();
+      h.src_hash2 = second_hash(src.source);
+      h.cubin_len = cubin->size();
+      const std::string tmeta = mpath + tmp;
+      std::ofstream fm(tmeta, std::ios::binary);
+      fm.write(reinterpret_cast<const char*>(&h), sizeof(h));
+      fm.close();
+      // the cubin first, then its descriptor: a reader that finds no (or a stale) descriptor recompiles
       if (rename(tpath.c_str(), path.c_str()) != 0) unlink(tpath.c_str());
+      if (!fm || rename(tmeta.c_str(), mpath.c_str()) != 0) unlink(tmeta.c_str());
     }
   }
   if (getenv("PYSTL_B200_KEEP_SOURCE")) {
@@ -235,6 +271,12 @@ int fused_jit_get(const FusedSource& src, FusedKernel* out, char* msg, int msg_l
   if (rc) return rc;
   cudaLibrary_t lib = nullptr;
   cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e != cudaSuccess) {  // a cached image the driver rejects (another toolkit, a damaged file): compile once more, past the cache
+    cudaGetLastError();
+    rc = get_cubin(src, key, &cubin, msg, msg_len, true);
+    if (rc) return rc;
+    e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  }
   if (e != cudaSuccess) return fail(msg, msg_len, PYSTL_E_CUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e));
   cudaKernel_t k = nullptr;
   e = cudaLibraryGetKernel(&k, lib, src.name.c_str());

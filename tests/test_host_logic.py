@@ -283,3 +283,44 @@ def test_operator_interface_validates_like_the_reference():
     with pytest.raises(ValueError, match="window is empty"):
         cum.temporal_until(left_trace=[cum._leaf(__import__("torch").zeros(()))], right_trace=[cum._leaf(__import__("torch").zeros(()))],
                            start=3, end=4)
+
+
+def test_cubin_cache_rejects_damaged_and_foreign_entries(tmp_path, monkeypatch):
+    """The on-disk cubin cache (jit.cpp): an entry is trusted only with its descriptor (source length, second hash, cubin
+    length); a truncated cubin, a missing descriptor or a descriptor of another source is recompiled, not loaded."""
+    import subprocess
+    import sys
+    import textwrap
+
+    code = textwrap.dedent("""
+        import os, sys, glob
+        from pystl_b200 import capi
+        from pystl_b200.compiler import compile_formula
+        from pystl_b200.formula import from_spec, BASELINE_SPECS
+        lib = capi.lib()
+        cf = compile_formula(from_spec(BASELINE_SPECS["cfg1"]), "classical", 2)
+        def build():
+            rc = lib.pystl_b200_fused_precompile(cf.ptr(), 1000, 2, 0)
+            assert rc == 0, lib.pystl_b200_last_error()
+            (cub,) = glob.glob(os.path.join(os.environ["PYSTL_B200_CACHE"], "*.cubin"))
+            return cub, cub[:-6] + ".meta"
+        cub, meta = build()
+        full = os.path.getsize(cub)
+        assert full > 1000 and os.path.getsize(meta) == 32
+        with open(cub, "r+b") as fh:            # truncated image
+            fh.truncate(full // 2)
+        cub, meta = build()
+        assert os.path.getsize(cub) == full
+        os.unlink(meta)                         # image without its descriptor
+        cub, meta = build()
+        assert os.path.getsize(meta) == 32
+        blob = bytearray(open(meta, "rb").read())  # descriptor of another source (a colliding key)
+        blob[16] ^= 0xFF
+        open(meta, "wb").write(bytes(blob))
+        cub, meta = build()
+        assert bytes(open(meta, "rb").read()) != bytes(blob) and os.path.getsize(cub) == full
+        print("ok")
+    """)
+    env = dict(os.environ, PYSTL_B200_CACHE=str(tmp_path), PYTHONPATH=ROOT)
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
