@@ -93,6 +93,7 @@ struct Gen {
   int flag_off = 0;                // smooth backward: per-window lost flags
   std::vector<int> fix_off;        // smooth backward: per window, the exact-scatter plane (aliases the dead forward scratch of its level)
   int sp_off = 0;                  // cumulative backward: four scatter planes
+  std::vector<int> cum_sp;         // cumulative backward: per instruction, its borrowed scatter / hand-off planes
   std::vector<int> hand_off, aux_off;  // lockstep until adjoints: hand-off planes (dead forward scratch of the level) / staged operands (the other region)
   int stage_off = 0;               // cooperative row staging (aliases the scratch regions)
   bool coop_stage() const { return D >= 4 && D <= 8; }
@@ -119,6 +120,13 @@ struct Gen {
   bool lockstep_adj(const TInstr& in) const {
     if (!bwd || !is_until(in)) return false;
     return P.sem == SEM_SMOOTH || (P.sem == SEM_AGM && in.w_off < 0 && in.w2_off < 0 && in.a <= 64);
+  }
+  bool cum_lockstep(const TInstr& in) const { return cum_bwd() && is_until(in) && in.a <= 64; }
+  // cumulative backward: floats of dead forward scratch an instruction's adjoint borrows (scatter / hand-off planes)
+  int cum_sp_floats(const TInstr& in) const {
+    if (cum_lockstep(in)) return 3 * 8 * nt + 2 * roundup(nt, 32);
+    if (arg_window(in)) return 2 * 8 * nt;
+    return 0;
   }
   int hand_planes() const { return P.sem == SEM_SMOOTH ? 2 : 3; }
   int aux_floats() const { return P.sem == SEM_SMOOTH ? 2 * 8 * nt + roundup(nt, 32) : 2 * roundup(nt, 32); }
@@ -195,8 +203,10 @@ struct Gen {
       persist += src_image() ? 8 * nt * D : P.n_preds * 8 * nt;
     }
     if (cum_bwd() || (bwd && has_until())) {
-      bool need_sp = cum_bwd();  // scatter planes of the cumulative adjoints and of the per-output until adjoints
-      for (int i = 0; i < P.n_instr; ++i) need_sp |= is_until(P.ins[i]) && !lockstep_adj(P.ins[i]);
+      // persistent scatter planes only for the per-output until adjoints; the lockstep walks and the cumulative
+      // arg-min / arg-max scatters take the dead forward scratch of their level (cum_sp below)
+      bool need_sp = false;
+      for (int i = 0; i < P.n_instr; ++i) need_sp |= is_until(P.ins[i]) && !lockstep_adj(P.ins[i]) && !cum_lockstep(P.ins[i]);
       if (need_sp) {
         sp_off = red_floats + persist;
         persist += 4 * 8 * nt;
@@ -265,8 +275,12 @@ struct Gen {
         reg[l & 1] = std::max(reg[l & 1], hand_planes() * 8 * nt);
         reg[(l + 1) & 1] = std::max(reg[(l + 1) & 1], aux_floats());
       }
+    cum_sp.assign(P.n_instr, 0);
+    if (cum_bwd())
+      for (int i = 0; i < P.n_instr; ++i) reg[ins_level[i] & 1] = std::max(reg[ins_level[i] & 1], cum_sp_floats(P.ins[i]));
     const int base0 = red_floats + persist, base1 = base0 + reg[0];
     for (int i = 0; i < P.n_instr; ++i) {
+      cum_sp[i] = (ins_level[i] & 1) ? base1 : base0;
       if (is_window(P.ins[i])) fix_off[i] = (ins_level[i] & 1) ? base1 : base0;
       if (lockstep_adj(P.ins[i])) {
         hand_off[i] = (ins_level[i] & 1) ? base1 : base0;
@@ -882,7 +896,33 @@ struct Gen {
         const TInstr& in = P.ins[i];
         if (ins_level[i] != st || !is_staged(in)) continue;
         const int d = in.dst;
-        if (is_until(in)) {
+        if (cum_lockstep(in)) {
+          const bool nl = in.negmask & 1, nr = in.negmask & 2;
+          const int OWN = cum_sp[i], HL = cum_sp[i] + L, HR = cum_sp[i] + 2 * L, CM = cum_sp[i] + 3 * L;
+          o.line("// adjoint of until %d: lockstep shared-tail walk per channel (hand-off planes, no atomics)", i);
+          o.line("float la%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+          o.line("float lb%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+          o.line("float ra%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+          o.line("float rb%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+          o.line("simt::sync();  // (the planes below are the forward scratch of this level: its last readers may still be in phase 2)");
+          for (int w = 0; w < 2; ++w)
+            o.line("cum_until_adj_stage<NT>(c, U%d::lplane(smem + %d, %d), smem + %d);", i, scr_off[i], w, CM + w * roundup(nt, 32));
+          o.line("simt::sync();");
+          for (int w = 0; w < 2; ++w) {
+            o.line("{");
+            o.line("  float gw[8];");
+            o.line("  _Pragma(\"unroll\") for (int i = 0; i < 8; ++i) gw[i] = g%d[i].x[%d];", d, w);
+            o.line("  cum_until_adj_walk<%d, %d, NT>(c, live, U%d::lplane(smem + %d, %d), U%d::rplane(smem + %d, %d), smem + %d, smem + %d, smem + %d, smem + %d, gw, %s%d, %s%d);",
+                   in.a, in.b, i, scr_off[i], w, i, scr_off[i], w, CM + w * roundup(nt, 32), HL, HR, OWN, w ? "lb" : "la", i, w ? "rb" : "ra", i);
+            o.line("}");
+          }
+          o.line("if (live) {");
+          o.indent++;
+          o.line("cum_add_ab8<%s>(la%d, lb%d, g%d);", nl ? "true" : "false", i, i, (int)in.src[0]);
+          o.line("cum_add_ab8<%s>(ra%d, rb%d, g%d);", nr ? "true" : "false", i, i, (int)in.src[1]);
+          o.indent--;
+          o.line("}");
+        } else if (is_until(in)) {
           const bool nl = in.negmask & 1, nr = in.negmask & 2;
           o.line("// adjoint of until %d: the r-routes are gathered into registers, the l-routes scattered with merged runs", i);
           o.line("plane_zero8(smem + %d, c.tid);", sp_off);
@@ -912,17 +952,19 @@ struct Gen {
         } else if (arg_window(in)) {
           const bool neg = in.negmask & 1;
           o.line("// adjoint of window %d: scatter to the recorded arg%s", i, in.mode == MODE_AND ? "min" : "max");
-          o.line("plane_zero8(smem + %d, c.tid);", sp_off);
-          o.line("plane_zero8(smem + %d, c.tid);", sp_off + L);
+          const int SP = cum_sp[i];  // (the window's own forward planes: its results are in registers by now)
+          o.line("simt::sync();  // (the planes below were read by the previous adjoint / the forward sweep of this level)");
+          o.line("plane_zero8(smem + %d, c.tid);", SP);
+          o.line("plane_zero8(smem + %d, c.tid);", SP + L);
           o.line("simt::sync();");
           o.line("if (live) {");
           o.indent++;
-          o.line("arg_scatter8(smem + %d, acca%d, g%d, 0);", sp_off, i, d);
-          o.line("arg_scatter8(smem + %d, accb%d, g%d, 1);", sp_off + L, i, d);
+          o.line("arg_scatter8(smem + %d, acca%d, g%d, 0);", SP, i, d);
+          o.line("arg_scatter8(smem + %d, accb%d, g%d, 1);", SP + L, i, d);
           o.indent--;
           o.line("}");
           o.line("simt::sync();");
-          o.line("if (live) cum_accumulate8<%s>(smem + %d, smem + %d, c.tid, g%d);", neg ? "true" : "false", sp_off, sp_off + L, (int)in.src[0]);
+          o.line("if (live) cum_accumulate8<%s>(smem + %d, smem + %d, c.tid, g%d);", neg ? "true" : "false", SP, SP + L, (int)in.src[0]);
           o.line("simt::sync();");
         } else {  // Eventually: a sum
           const int a = clamp_off(in.a, 8 * nt), b = clamp_off(in.b, 8 * nt);

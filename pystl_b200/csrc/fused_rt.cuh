@@ -2828,6 +2828,203 @@ PF_DEV void cum_until_scatter_l(const TC& c, const Vec<2> (&g)[8], int w, const 
   }
 }
 
+// ---- cumulative until, backward, LOCKSTEP walk (one channel; UA <= 64).  Same hand-off scheme as the smooth / agm walks.
+// With P_i(q) = min(h_i, M_q) (h_i: minimum of l over the rest of the own chunk, M_q: running minimum of the shared tail) a
+// candidate routes its cotangent g_i to r_q when r_q < P_i(q), else to the first argmin of l[t_i .. q].  ONE threshold per
+// position decides all 8 outputs:  thr = min(r_q, M_q);
+//     thr <  h_i:  the cotangent leaves the thread -- to r_q when r_q < M_q, else to the tail's argmin (then h_i > M_q): the
+//                  SUM of those g_i is routed once per position; the tail's argmin is the last record low of l at or below q,
+//                  and in a downward walk it is reached exactly when its amount is complete: flush at the record;
+//     thr >= h_i:  h_i <= min(r_q, M_q): the own-chunk argmin takes it; only COUNTED (g_i times the count at the end).
+// Two compares, one add and one count per candidate instead of the select chains and shared-memory atomics of
+// cum_until_gather_r / cum_until_scatter_l_fast.  Ties (torch.minimum splits them): r_q == M_q is position-level;
+// r_q == h_i <= M_q is detected by the second compare and repaired in a side block.  That block is NOT rare -- the (pos,
+// neg) channels are max(0, v) / min(0, v), exactly 0 half of the time -- yet a branch-free variant (selected adds and
+// counts for the tie in the main path, 12 instructions per candidate) measured slower: cfg4b 35.2 -> 42.1 ms.
+template <int NT>
+PF_DEV void cum_until_adj_stage(const TC& c, const float* lpl, float* cm) {
+  float l[8];
+  load8(lpl, c.tid, l);
+  float m = f_inf();
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (c.p0 + i < c.nlive) m = fminf(m, l[i]);
+  cm[c.tid] = m;
+}
+template <int UA, int UB, int NT>
+PF_DEV void cum_until_adj_walk(const TC& c, bool live, const float* lpl, const float* rpl, const float* cm, float* hl, float* hr,
+                               float* own, const float (&g)[8], float (&gl_own)[8], float (&gr_own)[8]) {
+  static_assert(UA >= 0 && UB >= UA, "bounded until");
+  constexpr int CMAX = (UB + 7) / 8;
+  const int p0 = c.p0;
+  const int kmax = c.interior ? 0x3fffffff : c.nlive - 1 - p0;
+  bool active = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) active = active || g[i] != 0.f;
+  active = active && live;
+  float lo[8], ro[8], h[8], hacc[8], cnt[8];
+  int harg[8];
+  load8(lpl, c.tid, lo);
+  load8(rpl, c.tid, ro);
+  plane_zero8(own, c.tid);  // (private to this thread: only the owner touches its chunk of `own`)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = f_inf();
+    hacc[i] = 0.f;
+    cnt[i] = 0.f;
+    harg[i] = p0 + i;
+  }
+  if (active) {  // own chunk: triangular (the l-routes' runs settle into `own`, the r-routes stay in registers)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float pm = f_inf(), run = 0.f;
+      int arg = p0 + i;
+#pragma unroll
+      for (int q = i; q < 8; ++q) {
+        if (q > kmax) break;
+        if (lo[q] < pm) {  // a new prefix minimum (first index wins ties): settle the old one
+          if (run != 0.f) own[pidx(arg)] += run;
+          run = 0.f;
+          pm = lo[q];
+          arg = p0 + q;
+        }
+        if (q - i >= UA && q - i <= UB) {
+          const float tr = cum_route_r(ro[q], pm, g[i]);
+          gr_own[q] += tr;
+          run += g[i] - tr;
+        }
+      }
+      h[i] = pm;
+      harg[i] = arg;
+      hacc[i] = run;
+    }
+  }
+  int cend = CMAX;
+  if (cend > NT - 1 - c.tid) cend = NT - 1 - c.tid;
+  if (cend > (kmax >> 3)) cend = kmax >> 3;
+  if (!active) cend = 0;
+  float cmin[CMAX + 1];  // cmin[j] = minimum of l over chunks tid + 1 .. tid + j
+  cmin[0] = f_inf();
+#pragma unroll 1
+  for (int cc = 1; cc <= cend; ++cc) cmin[cc] = fminf(cmin[cc - 1], cm[c.tid + cc]);
+  float accM = 0.f;  // cotangent routed to the tail's current argmin, not yet settled
+  auto chunk = [&](int cc, auto all, auto clip, float (&zl)[8], float (&zr)[8]) {
+    float l[8], r[8], Lm[8];
+    load8(lpl, c.tid + cc, l);
+    load8(rpl, c.tid + cc, r);
+    const float m0 = cmin[cc - 1];
+    {
+      float m = m0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        m = fminf(m, l[k]);
+        Lm[k] = m;
+      }
+    }
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+      float rs = 0.f;
+      if (!decltype(clip)::value || 8 * cc + k <= kmax) {
+        const float M = Lm[k], rq = r[k];
+        const float thr = fminf(rq, M);
+        float sA = 0.f;
+        bool tie = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
+            if (thr < h[i]) sA += g[i];
+            else cnt[i] += 1.f;
+            tie = tie || rq == h[i];
+          }
+        if (tie) {  // r_q equals the own-chunk minimum of an output that keeps its cotangent: half of it belongs to r_q
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
+              if (rq == h[i] && h[i] <= M) {
+                cnt[i] -= 0.5f;
+                rs += 0.5f * g[i];
+              }
+            }
+        }
+        const float tr = rq < M ? sA : (rq == M ? 0.5f * sA : 0.f);
+        rs += tr;
+        accM += sA - tr;
+      }
+      // a record low of the tail (first index wins ties): everything routed to "the argmin" so far belongs to q
+      const bool rec = l[k] < (k ? Lm[k > 0 ? k - 1 : 0] : m0);
+      zl[k] = rec ? accM : 0.f;
+      accM = rec ? 0.f : accM;
+      zr[k] = rs;
+    }
+  };
+  auto step = [&](int cc, auto all) {
+    float zl[8], zr[8];
+    if (cc <= cend) {
+      if (8 * cc + 7 <= kmax) chunk(cc, all, BoolC<false>{}, zl, zr);
+      else chunk(cc, all, BoolC<true>{}, zl, zr);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) zl[k] = zr[k] = 0.f;
+    }
+    if (cc == CMAX) {  // the first step initialises every slot: its writer's numbers, or zeros where there is no writer
+      if (c.tid + cc < NT) {
+        store8(hl, c.tid + cc, zl);
+        store8(hr, c.tid + cc, zr);
+      }
+      if (c.tid < CMAX) {
+        plane_zero8(hl, c.tid);
+        plane_zero8(hr, c.tid);
+      }
+    } else if (c.tid + cc < NT && cc <= cend) {  // one writer per chunk and step: a plain read-modify-write
+      float a[8], b[8];
+      load8(hl, c.tid + cc, a);
+      load8(hr, c.tid + cc, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a[k] += zl[k];
+        b[k] += zr[k];
+      }
+      store8(hl, c.tid + cc, a);
+      store8(hr, c.tid + cc, b);
+    }
+    simt::sync();
+  };
+  constexpr int CF0 = (UA + 7 + 7) / 8 > 1 ? (UA + 7 + 7) / 8 : 1;
+  constexpr int CF1 = UB >= 15 ? (UB - 7) / 8 : 0;
+  if constexpr (CF1 >= CF0) {
+#pragma unroll
+    for (int cc = CMAX; cc > CF1; --cc) step(cc, BoolC<false>{});
+#pragma unroll 1
+    for (int cc = CF1; cc >= CF0; --cc) step(cc, BoolC<true>{});
+#pragma unroll
+    for (int cc = CF0 - 1; cc >= 1; --cc) step(cc, BoolC<false>{});
+  } else {
+#pragma unroll
+    for (int cc = CMAX; cc >= 1; --cc) step(cc, BoolC<false>{});
+  }
+  if (live) {  // what the threads before this one handed over
+    float a[8], b[8];
+    load8(hl, c.tid, a);
+    load8(hr, c.tid, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      gl_own[k] += a[k];
+      gr_own[k] += b[k];
+    }
+  }
+  simt::sync();  // (the hand-off planes are reused by the other channel's walk)
+  if (!active) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float tot = fmaf(cnt[i], g[i], hacc[i]);
+    if (tot != 0.f) own[pidx(harg[i])] += tot;
+  }
+  float t[8];
+  load8(own, c.tid, t);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) gl_own[k] += t[k];
+}
+
 // ---- gradient rows -> HBM: the thread's 8 rows of D channels, positions inside [p_lo, p_hi)
 template <int D>
 PF_DEV void store_grad_rows(const TC& c, long long T, const float (&gr)[8][D], float* __restrict__ grad_signal) {
