@@ -2836,11 +2836,11 @@ PF_DEV void cum_until_scatter_l(const TC& c, const Vec<2> (&g)[8], int w, const 
 //                  SUM of those g_i is routed once per position; the tail's argmin is the last record low of l at or below q,
 //                  and in a downward walk it is reached exactly when its amount is complete: flush at the record;
 //     thr >= h_i:  h_i <= min(r_q, M_q): the own-chunk argmin takes it; only COUNTED (g_i times the count at the end).
-// Two compares, one add and one count per candidate instead of the select chains and shared-memory atomics of
-// cum_until_gather_r / cum_until_scatter_l_fast.  Ties (torch.minimum splits them): r_q == M_q is position-level;
-// r_q == h_i <= M_q is detected by the second compare and repaired in a side block.  That block is NOT rare -- the (pos,
-// neg) channels are max(0, v) / min(0, v), exactly 0 half of the time -- yet a branch-free variant (selected adds and
-// counts for the tie in the main path, 12 instructions per candidate) measured slower: cfg4b 35.2 -> 42.1 ms.
+// Two compares that yield 1.0 / 0.0 (FSET), two FMAs and two adds per candidate instead of the select chains and
+// shared-memory atomics of cum_until_gather_r / cum_until_scatter_l_fast.  Ties (torch.minimum splits them) are COMMON here --
+// the (pos, neg) channels are max(0, v) / min(0, v), exactly 0 half of the time -- so they stay in the main path: r_q == M_q
+// is position-level; r_q == h_i only counts when r_q <= M_q, also position-level, so it is one compare against a comparand
+// that is NaN otherwise.
 template <int NT>
 PF_DEV void cum_until_adj_stage(const TC& c, const float* lpl, float* cm) {
   float l[8];
@@ -2862,7 +2862,7 @@ PF_DEV void cum_until_adj_walk(const TC& c, bool live, const float* lpl, const f
 #pragma unroll
   for (int i = 0; i < 8; ++i) active = active || g[i] != 0.f;
   active = active && live;
-  float lo[8], ro[8], h[8], hacc[8], cnt[8];
+  float lo[8], ro[8], h[8], hacc[8], cgt[8], ceq[8];  // per output: candidates of the tail that left / tied (exact small integers)
   int harg[8];
   load8(lpl, c.tid, lo);
   load8(rpl, c.tid, ro);
@@ -2871,7 +2871,7 @@ PF_DEV void cum_until_adj_walk(const TC& c, bool live, const float* lpl, const f
   for (int i = 0; i < 8; ++i) {
     h[i] = f_inf();
     hacc[i] = 0.f;
-    cnt[i] = 0.f;
+    cgt[i] = ceq[i] = 0.f;
     harg[i] = p0 + i;
   }
   if (active) {  // own chunk: triangular (the l-routes' runs settle into `own`, the r-routes stay in registers)
@@ -2927,25 +2927,21 @@ PF_DEV void cum_until_adj_walk(const TC& c, bool live, const float* lpl, const f
       if (!decltype(clip)::value || 8 * cc + k <= kmax) {
         const float M = Lm[k], rq = r[k];
         const float thr = fminf(rq, M);
-        float sA = 0.f;
-        bool tie = false;
+        // a tie r_q == h_i only counts when the own-chunk argmin holds the minimum (h_i <= M_q), i.e. when r_q <= M_q: a
+        // position-level condition, folded into the comparand (NaN never compares equal)
+        const float xr = rq <= M ? rq : f_nan();
+        float sA = 0.f, sT = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
-            if (thr < h[i]) sA += g[i];
-            else cnt[i] += 1.f;
-            tie = tie || rq == h[i];
+            const float a = thr < h[i] ? 1.f : 0.f;  // the cotangent leaves the thread (FSET)
+            const float e = xr == h[i] ? 1.f : 0.f;  // half of it goes to r_q
+            sA = fmaf(a, g[i], sA);
+            sT = fmaf(e, g[i], sT);
+            cgt[i] += a;
+            ceq[i] += e;
           }
-        if (tie) {  // r_q equals the own-chunk minimum of an output that keeps its cotangent: half of it belongs to r_q
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
-              if (rq == h[i] && h[i] <= M) {
-                cnt[i] -= 0.5f;
-                rs += 0.5f * g[i];
-              }
-            }
-        }
+        rs = 0.5f * sT;
         const float tr = rq < M ? sA : (rq == M ? 0.5f * sA : 0.f);
         rs += tr;
         accM += sA - tr;
@@ -3016,7 +3012,13 @@ PF_DEV void cum_until_adj_walk(const TC& c, bool live, const float* lpl, const f
   if (!active) return;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float tot = fmaf(cnt[i], g[i], hacc[i]);
+    // candidates of output i the tail walk visited: offsets [max(8, i + UA), min(i + UB, kmax, 8 cend + 7)] from p0
+    int hi = i + UB;
+    if (hi > kmax) hi = kmax;
+    if (hi > 8 * cend + 7) hi = 8 * cend + 7;
+    const int lo_k = i + UA > 8 ? i + UA : 8;
+    const int n = hi - lo_k + 1;
+    const float tot = fmaf((float)(n > 0 ? n : 0) - cgt[i] - 0.5f * ceq[i], g[i], hacc[i]);
     if (tot != 0.f) own[pidx(harg[i])] += tot;
   }
   float t[8];
