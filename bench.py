@@ -359,6 +359,8 @@ def run_reference(args) -> None:
     if args.forward_only:
         with_bwd = False
     cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm is to use every host thread it can, at any N
+    torch.set_num_threads(cores)
     steps = max(args.steps, 1)
     import multiprocessing as mp
 
