@@ -119,7 +119,10 @@ struct Gen {
   // Until adjoints on the lockstep shared-tail walk (fused_rt.cuh: smooth_until_adj_walk, agm_until_adj_walk)
   bool lockstep_adj(const TInstr& in) const {
     if (!bwd || !is_until(in)) return false;
-    return P.sem == SEM_SMOOTH || (P.sem == SEM_AGM && in.w_off < 0 && in.w2_off < 0 && in.a <= 64);
+    if (P.sem == SEM_SMOOTH) return true;
+    const bool uniform = in.w_off < 0 && in.w2_off < 0 && in.a <= 64;
+    // (dgmsr: p = 1 is baked into the kernel; unit weights_pair are a run-time condition, the per-output sweep stays as the other branch)
+    return uniform && (P.sem == SEM_AGM || (P.sem == SEM_DGMSR && P.p == 1));
   }
   bool cum_lockstep(const TInstr& in) const { return cum_bwd() && is_until(in) && in.a <= 64; }
   // cumulative backward: floats of dead forward scratch an instruction's adjoint borrows (scatter / hand-off planes)
@@ -1045,7 +1048,7 @@ struct Gen {
       o.line("simt::sync();");
       return;
     }
-    if (lockstep_adj(in)) {  // agm, uniform weights
+    if (P.sem == SEM_AGM && lockstep_adj(in)) {  // agm, uniform weights
       const int G0 = hand_off[i], G1 = hand_off[i] + L, GR = hand_off[i] + 2 * L, AN = aux_off[i], AL = aux_off[i] + roundup(nt, 32), d = in.dst;
       o.line("// adjoint of until %d: shared-tail walk downwards, chunks in lockstep (no atomics)", i);
       o.line("float uk%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
@@ -1064,9 +1067,35 @@ struct Gen {
       o.line("simt::sync();  // the hand-off planes go back to the window scratch");
       return;
     }
+    int GLo = sp_off, GRo = sp_off + L;  // scatter planes of the per-output sweep
+    const bool dg_fast = P.sem == SEM_DGMSR && lockstep_adj(in);
+    if (dg_fast) {
+      const int G0 = hand_off[i], G1 = hand_off[i] + L, GR = hand_off[i] + 2 * L, A0 = aux_off[i], A1 = aux_off[i] + roundup(nt, 32), d = in.dst;
+      GLo = G0;
+      GRo = G1;
+      o.line("if (P.ins[%d].w[0] == 1.f && P.ins[%d].w[1] == 1.f) {  // unit weights_pair: lockstep shared-tail walk, closed forms per case", i, i);
+      o.indent++;
+      o.line("float ukA%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("float ukG%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("float uz0%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("float uz1%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("float urr%d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};", i);
+      o.line("dgmsr_until_adj_stage<NT>(c, U%d::lplane(smem + %d, 0), smem + %d, smem + %d);", i, scr_off[i], A0, A1);
+      o.line("if (live) dgmsr_until_adj_coeff<%d, %d>(c, rp, g%d, v%d, ukA%d, ukG%d);", in.a, in.b, d, d, i, i);
+      o.line("simt::sync();");
+      o.line("dgmsr_until_adj_walk<%d, %d, NT>(c, live, rp, U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), smem + %d, smem + %d,", in.a, in.b, i,
+             scr_off[i], i, scr_off[i], A0, A1);
+      o.line("    smem + %d, smem + %d, smem + %d, ukA%d, ukG%d, uz0%d, uz1%d, urr%d);", G0, G1, GR, i, i, i, i, i);
+      o.line("if (live) dgmsr_until_adj_finish<%s, %s>(U%d::lplane(smem + %d, 0), U%d::rplane(smem + %d, 0), c.tid, uz0%d, uz1%d, urr%d, g%d, g%d);",
+             nl ? "true" : "false", nr ? "true" : "false", i, scr_off[i], i, scr_off[i], i, i, i, (int)in.src[0], (int)in.src[1]);
+      o.line("simt::sync();  // the hand-off planes go back to the window scratch");
+      o.indent--;
+      o.line("} else {");
+      o.indent++;
+    }
     o.line("// adjoint of until %d: per-output sweeps, scatter through shared memory", i);
-    o.line("plane_zero8(smem + %d, c.tid);", sp_off);
-    o.line("plane_zero8(smem + %d, c.tid);", sp_off + L);
+    o.line("plane_zero8(smem + %d, c.tid);", GLo);
+    o.line("plane_zero8(smem + %d, c.tid);", GRo);
     o.line("simt::sync();");
     {
       char wl[48] = "nullptr", wr[48] = "nullptr";
@@ -1074,16 +1103,20 @@ struct Gen {
       if (in.w2_off >= 0) snprintf(wr, sizeof(wr), "P.wbuf + %d", (int)in.w2_off);
       o.line("if (live) gm_until_scatter<SEM, %d, %d, NT>(c, rp, P.ins[%d].w[0], P.ins[%d].w[1], %s, %s, g%d, U%d::lplane(smem + %d, 0),", in.a,
              in.b, i, i, wl, wr, (int)in.dst, i, scr_off[i]);
-      o.line("    U%d::rplane(smem + %d, 0), smem + %d, smem + %d);", i, scr_off[i], sp_off, sp_off + L);
+      o.line("    U%d::rplane(smem + %d, 0), smem + %d, smem + %d);", i, scr_off[i], GLo, GRo);
     }
     o.line("simt::sync();");
     o.line("if (live) {");
     o.indent++;
-    o.line("accumulate8<%s>(smem + %d, c.tid, g%d);", nl ? "true" : "false", sp_off, (int)in.src[0]);
-    o.line("accumulate8<%s>(smem + %d, c.tid, g%d);", nr ? "true" : "false", sp_off + L, (int)in.src[1]);
+    o.line("accumulate8<%s>(smem + %d, c.tid, g%d);", nl ? "true" : "false", GLo, (int)in.src[0]);
+    o.line("accumulate8<%s>(smem + %d, c.tid, g%d);", nr ? "true" : "false", GRo, (int)in.src[1]);
     o.indent--;
     o.line("}");
     o.line("simt::sync();");
+    if (dg_fast) {
+      o.indent--;
+      o.line("}");
+    }
   }
 
   std::string backward() {

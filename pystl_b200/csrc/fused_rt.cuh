@@ -903,18 +903,20 @@ struct UntilOp {
     const F4* L4 = reinterpret_cast<const F4*>(lplane(scr, 0));
     const F4* R4 = reinterpret_cast<const F4*>(rplane(scr, 0));
     const float invsw = fast_rcp(w0 + w1);
+    const float w0p = w0 * invsw, w1p = w1 * invsw;  // weights_pair / their sum
     const int kmax = clip_kmax(c);
     float hneg[8], hlog[8], o0[8], o1[8];
-    // one candidate of output i: prefix accumulator (pneg, plog) over k samples, right operand r
-    auto cand = [&](int i, float pneg, float plog, float invk, float rnegw, float rlogw, bool rpos) {
+    // one candidate of output i: prefix accumulator (pneg, plog), u = w0 / (sw cnt), right operand r (weighted by w1 / sw)
+    auto cand = [&](int i, float pneg, float plog, float u, float rnegw, float rlogw, bool rpos) {
       const bool flag = plog == f_inf();  // some l <= 0: arithmetic prefix (agm.py:71)
-      const float zA = fmaf(w0, flag ? pneg * invk : 0.f, rnegw) * invsw;
-      const float zG = fast_ex2(fmaf(w0 * invk, plog, rlogw) * invsw) - 1.f;
+      const float zA = fmaf(u, flag ? pneg : 0.f, rnegw);
+      const float zG = fast_ex2(fmaf(u, plog, rlogw)) - 1.f;
       const float z = (flag || !rpos) ? zA : zG;
       const bool pos = z > 0.f;  // agm.py:86
       o0[i] += pos ? z : 0.f;
       o1[i] += pos ? f_inf() : fast_lg2(1.f - z);
     };
+
     {  // own chunk: triangular
       const F4 la = L4[pf4(f0)], lb = L4[pf4(f0 + 1)], ra = R4[pf4(f0)], rb = R4[pf4(f0 + 1)];
       const float lo[8] = {la.v[0], la.v[1], la.v[2], la.v[3], lb.v[0], lb.v[1], lb.v[2], lb.v[3]};
@@ -924,8 +926,8 @@ struct UntilOp {
       for (int q = 0; q < 8; ++q) {
         ln[q] = fminf(lo[q], 0.f);
         ll[q] = lo[q] <= 0.f ? f_inf() : fast_lg2(1.f + lo[q]);
-        rn[q] = w1 * fminf(ro[q], 0.f);
-        rl[q] = w1 * fast_lg2(1.f + ro[q]);
+        rn[q] = w1p * fminf(ro[q], 0.f);
+        rl[q] = w1p * fast_lg2(1.f + ro[q]);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -936,7 +938,7 @@ struct UntilOp {
         for (int q = i; q < 8; ++q) {
           pn += ln[q];
           pl += ll[q];
-          if (q - i >= UA && q - i <= UB && q <= kmax) cand(i, pn, pl, 1.f / (float)(q - i + 1), rn[q], rl[q], ro[q] > 0.f);
+          if (q - i >= UA && q - i <= UB && q <= kmax) cand(i, pn, pl, w0p * (1.f / (float)(q - i + 1)), rn[q], rl[q], ro[q] > 0.f);
         }
         hneg[i] = pn;
         hlog[i] = pl;
@@ -950,10 +952,12 @@ struct UntilOp {
     auto group = [&](int g, auto all) {
       const int fc = (f0 + g) < FMAX ? (f0 + g) : FMAX;
       const F4 ql = L4[pf4(fc)], qr = R4[pf4(fc)];
-      // 1 / cnt for cnt = 4 g + (k - i) + 1, k - i in [-7, 3]: eleven reciprocals serve the group's 32 candidates
+      // w0 / (sw cnt) for cnt = 4 g + (k - i) + 1, k - i in [-7, 3]: eleven reciprocals serve the group's 32 candidates
       float ik[11];
 #pragma unroll
-      for (int j = 0; j < 11; ++j) ik[j] = fast_rcp((float)(4 * g + j - 6));
+      for (int j = 0; j < 11; ++j) ik[j] = w0p * fast_rcp((float)(4 * g + j - 6));
+      // (a variant of the group without the exponential for groups behind some l <= 0 was measured: cfg5-agm 6.39 -> 7.33 ms --
+      // the lanes of a warp cross that point in different groups and then run both variants)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int kq = 4 * g + k;
@@ -961,7 +965,7 @@ struct UntilOp {
         const float l = ql.v[k], r = qr.v[k];
         Mn += fminf(l, 0.f);
         Ml += l <= 0.f ? f_inf() : fast_lg2(1.f + l);
-        const float rn = w1 * fminf(r, 0.f), rl = w1 * fast_lg2(1.f + r);
+        const float rn = w1p * fminf(r, 0.f), rl = w1p * fast_lg2(1.f + r);
         const bool rpos = r > 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -2467,6 +2471,304 @@ PF_DEV void agm_until_adj_finish(const float* lpl, const float* rpl, int tid, fl
   for (int i = 0; i < 8; ++i) {
     const float dl = l[i] > 0.f ? z1[i] * fast_rcp(1.f + l[i]) : (l[i] < 0.f ? z0[i] : 0.5f * z0[i]);
     const float dr = w1p * rr[i] * (r[i] > 0.f ? fast_rcp(1.f + r[i]) : (r[i] < 0.f ? 1.f : 0.5f));
+    gsl[i] += NL ? -dl : dl;
+    gsr[i] += NR ? -dr : dr;
+  }
+}
+
+// ---- dgmsr until, backward, FAST PATH (p = 1, unit weights_pair, uniform weights_left / weights_right): the adjoint of
+// UntilOp::phase2_dgmsr on the lockstep walk, with the chain of Adj<SEM_DGMSR> partials written out per case
+// (eps: rp.eps_p, s = sqrt(eps); a0 / a1: the prefix accumulator, sum of l^2 over l <= 0 / sum of 2 lg2 l or +inf):
+//   Or (U = -And(-z) over n candidates):  U >= 0:  g dU/dz = kA z [z >= 0],  kA = g / (n (U + s));
+//                                          U <  0:  g dU/dz = kG / (-z),      kG = g (s - U) (1 - (eps / (s - U)^2)^n) / n;
+//   flagged prefix (some l <= 0):  sy = sqrt(eps + a0 / cnt), y = s - sy <= 0, sz = sqrt(eps + (y^2 + min(r, 0)^2) / 2), z = s - sz:
+//        half = dz / (2 sz);   r-route  half |r| [r <= 0];   l-route  Z0 += half (sy - s) / (cnt sy),  applied as |l_k| Z0 [l_k <= 0];
+//   all l > 0, r <= 0:  z depends on the position only and y carries no weight: r-route  dz |r| / (2 sz_r), no l-route;
+//   all l > 0, r >  0:  ey = 2^(lae / (2 cnt)) (lae = logaddexp2(cnt lg2 eps, a1)), y = ey - s, q = y r, m2 = eps^2 + q^2,
+//        ez = m2^(1/4), z = ez - s:   c = dz ez q / (2 m2);   r-route  c y;   l-route  Z1 += c r ey (1 - 2^(cnt lg2 eps - lae)) / cnt,
+//        applied as Z1 / l_k [l_k > 0].
+// A chunk behind some l <= 0 of the shared tail holds flagged prefixes only (five transcendentals per candidate).
+template <int NT>
+PF_DEV void dgmsr_until_adj_stage(const TC& c, const float* lpl, float* ag0, float* ag1) {
+  float l[8];
+  load8(lpl, c.tid, l);
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (c.p0 + i < c.nlive) {
+      const float ln = fminf(l[i], 0.f);
+      s0 = fmaf(ln, ln, s0);
+      s1 += l[i] <= 0.f ? f_inf() : 2.f * fast_lg2(l[i]);
+    }
+  ag0[c.tid] = s0;
+  ag1[c.tid] = s1;
+}
+// kA_i / kG_i: the output-level coefficients of the Or (one of them is zero)
+template <int UA, int UB>
+PF_DEV void dgmsr_until_adj_coeff(const TC& c, const RP& rp, const float (&g)[8], const Vec<1> (&U)[8], float (&kA)[8], float (&kG)[8]) {
+  const int kmax = c.nlive - 1 - c.p0;
+  const float se = rp.sqrt_eps, lge = rp.ln_eps * kLog2e;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int last = kmax - i;
+    if (last > UB) last = UB;
+    const int n = last - UA + 1;
+    const bool has = g[i] != 0.f && n > 0;
+    const float nf = (float)(n > 0 ? n : 1);
+    const float u = U[i].x[0];
+    const float gn = g[i] * fast_rcp(nf);
+    const float rm0 = se - u;  // sqrt(m0) of the geometric Or
+    const float ratio = fast_ex2(nf * (lge - 2.f * fast_lg2(fmaxf(rm0, 1e-30f))));
+    kA[i] = (has && u >= 0.f) ? gn * fast_rcp(u + se) : 0.f;
+    kG[i] = (has && !(u >= 0.f)) ? gn * rm0 * (1.f - ratio) : 0.f;
+  }
+}
+template <int UA, int UB, int NT>
+PF_DEV void dgmsr_until_adj_walk(const TC& c, bool live, const RP& rp, const float* lpl, const float* rpl, const float* ag0,
+                                 const float* ag1, float* g0p, float* g1p, float* grp, const float (&kA)[8], const float (&kG)[8],
+                                 float (&z0_own)[8], float (&z1_own)[8], float (&r_own)[8]) {
+  static_assert(UA >= 0 && UB >= UA, "bounded until");
+  constexpr int CMAX = (UB + 7) / 8;
+  const int kmax = c.interior ? 0x3fffffff : c.nlive - 1 - c.p0;
+  const float eps = rp.eps_p, se = rp.sqrt_eps, lge = rp.ln_eps * kLog2e;
+  bool active = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) active = active || kA[i] != 0.f || kG[i] != 0.f;
+  active = active && live;
+  float lo[8], ro[8], l2q[8], llq[8], h0[8], h1[8], Z0[8], Z1[8];
+  load8(lpl, c.tid, lo);
+  load8(rpl, c.tid, ro);
+  {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      const bool ok = c.p0 + i < c.nlive;
+      const float ln = fminf(lo[i], 0.f);
+      l2q[i] = ok ? ln * ln : 0.f;
+      llq[i] = ok ? (lo[i] <= 0.f ? f_inf() : 2.f * fast_lg2(lo[i])) : 0.f;
+      s0 += l2q[i];
+      s1 += llq[i];
+      h0[i] = s0;
+      h1[i] = s1;
+      Z0[i] = Z1[i] = 0.f;
+    }
+  }
+  // flagged candidate of output i: a0 = sum of l^2 over the l <= 0 of the prefix, invk = 1 / cnt, r2n = min(r, 0)^2
+  //   -> d0: contribution to Z0; kr: to the r-route (the owner multiplies by |r|; nothing when r > 0)
+  auto cand_flag = [&](int i, float a0, float invk, float r2n, bool rpos, float& d0, float& kr) {
+    const float sy = fast_sqrt(fmaf(a0, invk, eps));
+    const float y = se - sy;
+    const float sz = fast_sqrt(fmaf(0.5f, fmaf(y, y, r2n), eps));
+    const float nz = sz - se;  // -z >= 0
+    const float dz = nz > 0.f ? kG[i] * fast_rcp(nz) : 0.f;  // (z == 0 joins an arithmetic Or with weight z = 0)
+    const float half = 0.5f * dz * fast_rcp(sz);
+    kr = rpos ? 0.f : half;
+    d0 = half * (sy - se) * invk * fast_rcp(sy);
+  };
+  // general candidate; szr / crz: sqrt(eps + r^2 / 2) and 1 / (2 szr (szr - s)) of this position (r <= 0)
+  auto cand = [&](int i, float a0, float a1, float invk, float kf, float r, float r2n, float szr, float crz, float& d0, float& d1, float& kr) {
+    const bool flag = a1 == f_inf();
+    float d0f, krf;
+    cand_flag(i, a0, invk, r2n, r > 0.f, d0f, krf);
+    // all l > 0
+    const float u = kf * lge;
+    const float lae = fmaxf(u, a1) + fast_lg2(1.f + fast_ex2(-fabsf(u - a1)));
+    const float ey = fast_ex2(0.5f * invk * lae);
+    const float y = ey - se;
+    const float q = y * r;
+    const float m2 = fmaf(q, q, eps * eps);
+    const float ez = fast_sqrt(fast_sqrt(m2));
+    const float z = ez - se;
+    const float cg = 0.5f * (kA[i] * z) * ez * q * fast_rcp(m2);  // (z > 0 belongs to an arithmetic Or: g dU/dz = kA z)
+    const float ry = 1.f - fast_ex2(u - lae);
+    const float d1g = cg * r * ey * ry * invk;
+    // all l > 0, r <= 0: z = s - szr < 0 (or 0 when r == 0), only the r-route
+    const float krn = (szr > se) ? kG[i] * crz : 0.f;
+    const bool rpos = r > 0.f;
+    d0 = flag ? d0f : 0.f;
+    d1 = (!flag && rpos) ? d1g : 0.f;
+    kr = flag ? krf : (rpos ? cg * y : krn);
+  };
+  int cend = CMAX;
+  if (cend > NT - 1 - c.tid) cend = NT - 1 - c.tid;
+  if (cend > (kmax >> 3)) cend = kmax >> 3;
+  if (!active) cend = 0;
+  float cs0[CMAX + 1], cs1[CMAX + 1];  // running sums of the aggregates of chunks tid + 1 .. tid + j
+  cs0[0] = cs1[0] = 0.f;
+#pragma unroll 1
+  for (int cc = 1; cc <= cend; ++cc) {
+    cs0[cc] = cs0[cc - 1] + ag0[c.tid + cc];
+    cs1[cc] = cs1[cc - 1] + ag1[c.tid + cc];
+  }
+  float zs0 = 0.f, zs1 = 0.f;
+  auto chunk = [&](int cc, auto all, auto clip, auto flagged, float (&zc0)[8], float (&zc1)[8], float (&rc)[8]) {
+    float l[8], r[8], L0[8], L1[8], it[15];
+    load8(lpl, c.tid + cc, l);
+    load8(rpl, c.tid + cc, r);
+    {
+      float s0 = cs0[cc - 1], s1 = cs1[cc - 1];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float ln = fminf(l[k], 0.f);
+        s0 = fmaf(ln, ln, s0);
+        L0[k] = s0;
+        if constexpr (!decltype(flagged)::value) {
+          s1 += l[k] <= 0.f ? f_inf() : 2.f * fast_lg2(l[k]);
+          L1[k] = s1;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 15; ++j) it[j] = fast_rcp((float)(8 * cc + j - 6));  // 1 / cnt, cnt = 8 cc + (k - i) + 1
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+      float rs = 0.f, q0 = 0.f, q1 = 0.f;
+      if (!decltype(clip)::value || 8 * cc + k <= kmax) {
+        const float rk = r[k];
+        const float rn = fminf(rk, 0.f);
+        const float r2n = rn * rn;
+        if constexpr (decltype(flagged)::value) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
+              float d0, kr;
+              cand_flag(i, h0[i] + L0[k], it[k - i + 7], r2n, rk > 0.f, d0, kr);
+              Z0[i] += d0;
+              q0 += d0;
+              rs += kr;
+            }
+        } else {
+          const float szr = fast_sqrt(fmaf(0.5f, r2n, eps));
+          const float crz = 0.5f * fast_rcp(szr * fmaxf(szr - se, 1e-30f));
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
+              float d0, d1, kr;
+              cand(i, h0[i] + L0[k], h1[i] + L1[k], it[k - i + 7], (float)(8 * cc + k - i + 1), rk, r2n, szr, crz, d0, d1, kr);
+              Z0[i] += d0;
+              Z1[i] += d1;
+              q0 += d0;
+              q1 += d1;
+              rs += kr;
+            }
+        }
+      }
+      zs0 += q0;
+      zs1 += q1;
+      zc0[k] = zs0;
+      zc1[k] = zs1;
+      rc[k] = rs;
+    }
+  };
+  auto step = [&](int cc, auto all) {
+    float zc0[8], zc1[8], rc[8];
+    if (cc <= cend) {
+      const bool fl = cs1[cc - 1] == f_inf();
+      if (8 * cc + 7 <= kmax) {
+        if (fl) chunk(cc, all, BoolC<false>{}, BoolC<true>{}, zc0, zc1, rc);
+        else chunk(cc, all, BoolC<false>{}, BoolC<false>{}, zc0, zc1, rc);
+      } else {
+        chunk(cc, all, BoolC<true>{}, BoolC<false>{}, zc0, zc1, rc);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) zc0[k] = zc1[k] = rc[k] = 0.f;
+    }
+    if (cc == CMAX) {  // the first step initialises every slot: its writer's numbers, or zeros where there is no writer
+      if (c.tid + cc < NT) {
+        store8(g0p, c.tid + cc, zc0);
+        store8(g1p, c.tid + cc, zc1);
+        store8(grp, c.tid + cc, rc);
+      }
+      if (c.tid < CMAX) {
+        plane_zero8(g0p, c.tid);
+        plane_zero8(g1p, c.tid);
+        plane_zero8(grp, c.tid);
+      }
+    } else if (c.tid + cc < NT && cc <= cend) {  // one writer per chunk and step: a plain read-modify-write
+      float a[8], b[8], d[8];
+      load8(g0p, c.tid + cc, a);
+      load8(g1p, c.tid + cc, b);
+      load8(grp, c.tid + cc, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a[k] += zc0[k];
+        b[k] += zc1[k];
+        d[k] += rc[k];
+      }
+      store8(g0p, c.tid + cc, a);
+      store8(g1p, c.tid + cc, b);
+      store8(grp, c.tid + cc, d);
+    }
+    simt::sync();
+  };
+  constexpr int CF0 = (UA + 7 + 7) / 8 > 1 ? (UA + 7 + 7) / 8 : 1;
+  constexpr int CF1 = UB >= 15 ? (UB - 7) / 8 : 0;
+  if constexpr (CF1 >= CF0) {
+#pragma unroll
+    for (int cc = CMAX; cc > CF1; --cc) step(cc, BoolC<false>{});
+#pragma unroll 1
+    for (int cc = CF1; cc >= CF0; --cc) step(cc, BoolC<true>{});
+#pragma unroll
+    for (int cc = CF0 - 1; cc >= 1; --cc) step(cc, BoolC<false>{});
+  } else {
+#pragma unroll
+    for (int cc = CMAX; cc >= 1; --cc) step(cc, BoolC<false>{});
+  }
+  if (live) {  // what the threads before this one handed over
+    float a[8], b[8], d[8];
+    load8(g0p, c.tid, a);
+    load8(g1p, c.tid, b);
+    load8(grp, c.tid, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      z0_own[k] += a[k];
+      z1_own[k] += b[k];
+      r_own[k] += d[k];
+    }
+  }
+  if (!active) return;
+  // own chunk: triangular, in registers
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float t0[8], t1[8];
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int q = i; q < 8; ++q) {
+      a0 += l2q[q];
+      a1 += llq[q];
+      t0[q] = t1[q] = 0.f;
+      if (q - i >= UA && q - i <= UB && q <= kmax) {
+        const float rn = fminf(ro[q], 0.f);
+        const float r2n = rn * rn;
+        const float szr = fast_sqrt(fmaf(0.5f, r2n, eps));
+        const float crz = 0.5f * fast_rcp(szr * fmaxf(szr - se, 1e-30f));
+        float kr;
+        cand(i, a0, a1, 1.f / (float)(q - i + 1), (float)(q - i + 1), ro[q], r2n, szr, crz, t0[q], t1[q], kr);
+        r_own[q] += kr;
+      }
+    }
+    float run0 = Z0[i], run1 = Z1[i];
+#pragma unroll
+    for (int q = 7; q >= i; --q) {
+      run0 += t0[q];
+      run1 += t1[q];
+      z0_own[q] += run0;
+      z1_own[q] += run1;
+    }
+  }
+}
+// owner: the factors in l_k and r_q (Adj<SEM_DGMSR, MODE_AND>::in_factor with p = 1), routed through the operands' negations
+template <bool NL, bool NR>
+PF_DEV void dgmsr_until_adj_finish(const float* lpl, const float* rpl, int tid, const float (&z0)[8], const float (&z1)[8],
+                                   const float (&rr)[8], float (&gsl)[8], float (&gsr)[8]) {
+  float l[8], r[8];
+  load8(lpl, tid, l);
+  load8(rpl, tid, r);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float dl = l[i] <= 0.f ? z0[i] * -l[i] : z1[i] * fast_rcp(l[i]);
+    const float dr = r[i] <= 0.f ? rr[i] * -r[i] : rr[i];
     gsl[i] += NL ? -dl : dl;
     gsr[i] += NR ? -dr : dr;
   }

@@ -86,7 +86,7 @@ static int fused_minb(int nt, bool backward, const TileProgram& prog) {
   else if (sem == SEM_DGMSR) bwd_regs = 56;
   // the lockstep Until adjoints keep two sets of 8 running states and the hand-off numbers live: at 80 registers the
   // spills reach DRAM (ncu: 1.6 x the algorithmic traffic); 128 registers, cfg5 Smooth value + gradient 10.0 -> 8.7 ms
-  if (has_until && (sem == SEM_SMOOTH || sem == SEM_AGM)) bwd_regs = 128;
+  if (has_until && (sem == SEM_SMOOTH || sem == SEM_AGM || sem == SEM_DGMSR)) bwd_regs = 128;
   const char* r = getenv(backward ? "PYSTL_B200_FUSED_REGS_BWD" : "PYSTL_B200_FUSED_REGS");
   // forward kernels: 56 registers (cfg2 0.785 -> 0.773 ms), 48 for agm / dgmsr (cfg3 1.05 -> 0.97 ms)
   const int fwd_regs = has_until ? 64 : ((sem == SEM_AGM || sem == SEM_DGMSR) ? 48 : 56);
