@@ -689,6 +689,17 @@ struct BoolC {
   static constexpr bool value = B;
 };
 
+// Two reciprocals from ONE MUFU: 1 / a = b / (a b), 1 / b = a / (a b).  The smooth Until walks are bound by the XU pipe (one
+// rcp per candidate, ncu: 83 %); this trades every second rcp for three multiplies on the FMA pipe.  The product must stay
+// normal: the walks call an output healthy only while its sum of terms is below kSmoothUntilMax = 2^60, i.e. while each of
+// its denominators is above 2^-60; a product that underflows makes both terms inf, which sends both outputs to the exact path.
+constexpr float kSmoothUntilMax = 1.15292150e18f;  // 2^60
+PF_DEV void rcp2(float a, float b, float& ra, float& rb) {
+  const float r = fast_rcp(a * b);
+  ra = r * b;
+  rb = r * a;
+}
+
 // ------------------------------------------------------------------ until, O(b) per sample
 // OR_{i in [UA, UB]} AND(AND_{k<=i} l[t+k], r[t+i]) (api.py:284-302 + each semantics'
 // temporal_until) with the per-semantics running state of tile_eval.h (UntilState): 8 outputs
@@ -848,8 +859,19 @@ struct UntilOp {
   if ((KQ) <= kmax) {                                                            \
     M += fast_ex2(fmaf((LV), nk, ns));                                           \
     const float G = M + fast_ex2(fmaf((RV), nk, ns));                            \
-    _Pragma("unroll") for (int i = 0; i < 8; ++i) {                              \
-      if ((KQ) - i >= UA && (KQ) - i <= UB) acc[i] += fast_rcp(G + h[i]);        \
+    _Pragma("unroll") for (int i = 0; i < 8; i += 2) {                           \
+      const bool c0 = (KQ) - i >= UA && (KQ) - i <= UB;                          \
+      const bool c1 = (KQ) - i - 1 >= UA && (KQ) - i - 1 <= UB;                  \
+      if (c0 && c1) {                                                            \
+        float t0, t1;                                                            \
+        rcp2(G + h[i], G + h[i + 1], t0, t1);                                    \
+        acc[i] += t0;                                                            \
+        acc[i + 1] += t1;                                                        \
+      } else if (c0) {                                                           \
+        acc[i] += fast_rcp(G + h[i]);                                            \
+      } else if (c1) {                                                           \
+        acc[i + 1] += fast_rcp(G + h[i + 1]);                                    \
+      }                                                                          \
     }                                                                            \
   }
 #pragma unroll
@@ -869,7 +891,12 @@ struct UntilOp {
         M += fast_ex2(fmaf(ql.v[k], nk, ns));
         const float G = M + fast_ex2(fmaf(qr.v[k], nk, ns));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += fast_rcp(G + h[i]);
+        for (int i = 0; i < 8; i += 2) {
+          float t0, t1;
+          rcp2(G + h[i], G + h[i + 1], t0, t1);
+          acc[i] += t0;
+          acc[i + 1] += t1;
+        }
       }
     }
 #pragma unroll
@@ -1191,7 +1218,7 @@ struct UntilOp {
       const float a_i = st[i].acc;
       const int p = c.p0 + i;
       const int n = ncand(c, p);
-      if (n <= 0 || p >= c.nlive || (a_i >= kSmoothTiny && a_i <= 1.0e30f)) continue;
+      if (n <= 0 || p >= c.nlive || (a_i >= kSmoothTiny && a_i <= kSmoothUntilMax)) continue;
       o[i].x[0] = smooth_until_fix_one<UA>(p, n + UA - 1, rp.k, rp.invk, lplane(scr, 0), rplane(scr, 0));
     }
   }
@@ -2024,7 +2051,7 @@ PF_DEV unsigned smooth_until_adj_coeff(const TC& c, const float (&g)[8], const f
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const bool has = g[i] != 0.f && kmax - i >= UA;
-    const bool ok = A[i] >= kSmoothTiny && A[i] <= 1.0e30f;
+    const bool ok = A[i] >= kSmoothTiny && A[i] <= kSmoothUntilMax;
     ci[i] = (has && ok) ? g[i] * fast_rcp(A[i]) : 0.f;
     if (has && !ok) lost |= 1u << i;
   }
@@ -2080,14 +2107,27 @@ PF_DEV void smooth_until_adj_walk(const TC& c, bool live, const float* la, const
       float rs = 0.f;
       if (!decltype(clip)::value || 8 * cc + k <= kmax) {
         const float G = base + L[k] + R[k];
+        if constexpr (decltype(all)::value) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (decltype(all)::value || (8 * cc + k - i >= UA && 8 * cc + k - i <= UB)) {
-            const float t = fast_rcp(G + hS[i]);
-            const float v = t * ci[i];
-            Z[i] = fmaf(v, t, Z[i]);
-            rs = fmaf(v, t, rs);
+          for (int i = 0; i < 8; i += 2) {
+            float t0, t1;
+            rcp2(G + hS[i], G + hS[i + 1], t0, t1);
+            const float v0 = t0 * ci[i], v1 = t1 * ci[i + 1];
+            Z[i] = fmaf(v0, t0, Z[i]);
+            Z[i + 1] = fmaf(v1, t1, Z[i + 1]);
+            rs = fmaf(v0, t0, rs);
+            rs = fmaf(v1, t1, rs);
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (8 * cc + k - i >= UA && 8 * cc + k - i <= UB) {
+              const float t = fast_rcp(G + hS[i]);
+              const float v = t * ci[i];
+              Z[i] = fmaf(v, t, Z[i]);
+              rs = fmaf(v, t, rs);
+            }
+        }
       }
       zs += rs;
       zc[k] = zs;
