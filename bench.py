@@ -130,13 +130,15 @@ except (OSError, ValueError):
 PIPE_OPS = {
     # cumulative Until [0, 64]: per candidate and channel one FMNMX (+ one FADD on the FMA pipe); G[0, 200] adds ~6
     ("cfg4", "forward"): ("alu", 65 * 2 + 2 * 2 + 6),
-    # cfg5's Until [0, 24]: 25 candidates per sample
+    # cfg5's Until [0, 24]: 25 candidates per sample and channel
     ("cfg5c", "forward"): ("alu", 25 * 2 + 2 * 2 + 12),
-    ("cfg5s", "forward"): ("xu", 25 + 2 * (25 + 8) / 8.0 + 2 * 2 + 3 * 2),   # one rcp per candidate, lifts shared by 8 outputs
-    ("cfg5a", "forward"): ("xu", 3 * 25 + 2 * (25 + 8) / 8.0 + 2 * 2 + 3 * 2),  # rcp + ex2 + lg2 per candidate
-    ("cfg5d", "forward"): ("xu", 13 * 25 + 2 * 4 + 2 * 6),                    # generic walk, 13 transcendentals per candidate
-    ("cfg5sb", "value_and_grad"): ("xu", 2 * 25 + 4 * (25 + 8) / 8.0 + 2 * 5 + 3 * 2),  # forward + one rcp per candidate again
-    ("cfg5ab", "value_and_grad"): ("xu", 5 * 25 + 40),
+    # MUFU per sample as ncu counts them (smsp__inst_executed_pipe_xu x 32 / samples, profiles/round2/results.md):
+    ("cfg5s", "forward"): ("xu", 32.4),   # one rcp per TWO candidates (rcp2), lifts shared by 8 outputs, window lifts / finishes
+    ("cfg5a", "forward"): ("xu", 76.6),   # ex2 + lg2 per candidate, 1 / cnt from a table
+    ("cfg5d", "forward"): ("xu", 205.7),  # 3 (flagged groups) to 8 (general groups) per candidate
+    ("cfg5sb", "value_and_grad"): ("xu", 56.4),
+    ("cfg5ab", "value_and_grad"): ("xu", 145.9),
+    ("cfg5db", "value_and_grad"): ("xu", 514.7),
 }
 
 
