@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PYSTL_B200_ABI_VERSION 1
+#define PYSTL_B200_ABI_VERSION 2
 #define PYSTL_MAX_TERMS 8 /* affine terms per predicate */
 
 typedef enum pystl_status {
@@ -91,6 +91,9 @@ typedef struct pystl_pred {
   int32_t channel[PYSTL_MAX_TERMS];
   float coeff[PYSTL_MAX_TERMS];
   float bias;
+  int32_t slack; /* ABI 2.  0 for a predicate on the signal.  > 0: the channel holds values the host computed
+                    (pystl_b200_open_window_forward) that do not exist at t > T-1-slack -- the reference raises
+                    there (api.py:218-221) and the outputs that depend on them are NaN; -1: it raises for every t */
 } pystl_pred_t;
 
 typedef struct pystl_formula {
@@ -172,6 +175,21 @@ int pystl_b200_fused_plan(const pystl_formula_t* formula, int64_t T, int32_t D, 
                           pystl_plan_t* plan);
 int pystl_b200_fused_source(const pystl_formula_t* formula, int64_t T, int32_t D, int32_t backward,
                             char* buf, int32_t len);
+
+/* Open-ended windows on traces longer than one tile (ABI 2).  G[a, inf) / F[a, inf) of a VALUE TRACE y[B, T]
+ * (the operand's robustness, produced by eval_forward): out[b, t] = the semantics' temporal_always (mode 0) /
+ * temporal_eventually (mode 1) of y[b, t+a .. T-1] -- Always / Eventually.evaluate with Interval.end None,
+ * pystl/api.py:49-54,208-243 -> classic.py:39-57, smooth.py:47-65, agm.py:92-110, dgmsr.py:58-86 -- as one suffix
+ * scan per trace (pystl_b200/csrc/scan.cu).  The host feeds `out` back to the formula kernels as a leaf channel
+ * with pystl_pred_t.slack = a.  Outputs at t > T-1-a (empty window) hold a finite filler.
+ *   arg   int32[B, T], classical only (may be NULL otherwise): the window's arg-min / arg-max for the gradient
+ * Cumulative values are pairs and are not offered here (PYSTL_E_UNSUPPORTED), nor are window weights. */
+int pystl_b200_open_window_forward(int32_t semantics, int32_t mode, int32_t a, float temperature, float eps, int32_t p,
+                                   const float* y, int64_t B, int64_t T, float* out, int32_t* arg, void* stream);
+/* grad_y[B, T] (fully overwritten) = d sum(grad_out * out) / d y over the outputs that exist (t <= T-1-a). */
+int pystl_b200_open_window_backward(int32_t semantics, int32_t mode, int32_t a, float temperature, float eps, int32_t p,
+                                    const float* y, const float* out, const int32_t* arg, const float* grad_out,
+                                    int64_t B, int64_t T, float* grad_y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ import ctypes as C
 import os
 from typing import Optional
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_TERMS = 8
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA = 0, -1, -2, -3
@@ -44,6 +44,7 @@ class Pred(C.Structure):
         ("channel", C.c_int32 * MAX_TERMS),
         ("coeff", C.c_float * MAX_TERMS),
         ("bias", C.c_float),
+        ("slack", C.c_int32),  # ABI 2: > 0 for a host-computed channel that ends before the horizon, -1 = never valid
     ]
 
 
@@ -93,6 +94,8 @@ EXPORTS = (
     "pystl_b200_fused_precompile",
     "pystl_b200_fused_plan",
     "pystl_b200_fused_source",
+    "pystl_b200_open_window_forward",
+    "pystl_b200_open_window_backward",
 )
 
 # PYSTL_B200_LIB points at an alternative build of the same library (A/B timing of kernel variants)
@@ -140,6 +143,18 @@ def declare(lib: C.CDLL, prefix: str = "pystl_b200") -> None:
         f = lib.pystl_b200_fused_source
         f.restype = C.c_int
         f.argtypes = [C.POINTER(Formula), C.c_int64, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+        f = lib.pystl_b200_open_window_forward
+        f.restype = C.c_int
+        f.argtypes = [
+            C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,
+            C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+        ]
+        f = lib.pystl_b200_open_window_backward
+        f.restype = C.c_int
+        f.argtypes = [
+            C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+        ]
 
 
 def lib() -> C.CDLL:

@@ -13,6 +13,13 @@ semantics object evaluates ``fn`` for every ``(trace, t)`` ON THE DEVICE with to
 (``leaf_values``), appends the result to the signal as an extra channel and the kernels read it as
 the predicate ``1.0 * channel``; autograd carries the gradient back through ``fn``.  There is no
 host evaluation path: a callable torch cannot trace raises ``NotImplementedError``.
+
+Open-ended windows beyond one tile (``open_leaf=True``): the formula kernels keep the whole trace of an
+``Always / Eventually`` without an end in ONE tile, which bounds T (8192 samples at most, fewer for large
+formulas).  For longer traces the node becomes a leaf channel too (``OpenLeaf``): its operand's robustness trace
+is evaluated by the formula kernels, reduced by the suffix-scan kernels of ``csrc/scan.cu``
+(``pystl_b200_open_window_forward / _backward``) and read back as the predicate ``1.0 * channel`` whose ``slack``
+tells the lowering where the values end (api.py:218-221: the reference raises at ``t + a > T - 1``).
 """
 
 from __future__ import annotations
@@ -32,6 +39,40 @@ _SEM_IDS = {
     "agm": capi.SEM_AGM,
     "dgmsr": capi.SEM_DGMSR,
 }
+
+
+NEVER = 1 << 29  # start slack of a node the reference raises on at every t (lower.cpp: kNever)
+OPEN_LEAF_SEMANTICS = ("classical", "smooth", "agm", "dgmsr")  # cumulative values are pairs: not offered
+
+
+@dataclass(frozen=True)
+class OpenLeaf:
+    """``Always / Eventually`` of ``child`` over ``[t + start, T - 1]``, computed outside the formula kernel."""
+
+    child: Any
+    mode: int  # 0 always, 1 eventually
+    start: int
+    name: str = "open-ended window"
+
+
+def start_slack(node: Any) -> int:
+    """Samples at the end of the trace where ``node`` raises (empty window); mirrors lower.cpp."""
+    kind = type(node).__name__
+    if kind == "Predicate":
+        return 0
+    if kind == "Not":
+        return start_slack(node.child)
+    if kind in ("And", "Or"):
+        return max(start_slack(c) for c in node.children)
+    kids = (node.left, node.right) if kind == "Until" else (node.child,)
+    cs = max(start_slack(c) for c in kids)
+    a = int(node.interval.start)
+    b = node.interval.end
+    if cs == 0:
+        return a
+    if kind == "Until" or b is None or cs >= NEVER:
+        return NEVER
+    return min(NEVER, cs + int(b))
 
 
 def wants_leaf(pred: Any) -> bool:
@@ -143,7 +184,8 @@ class CompiledFormula:
     channels_used: Tuple[int, ...]
     pred_terms: List[Tuple[Tuple[Tuple[int, float], ...], float]]
     n_signal_channels: int = 0   # channels of the user's signal
-    leaf_preds: Tuple[Any, ...] = ()  # non-affine predicates: leaf j is channel n_signal_channels + j
+    leaf_preds: Tuple[Any, ...] = ()  # non-affine predicates / OpenLeaf: leaf j is channel n_signal_channels + j
+    has_open: bool = False  # an Always / Eventually without an end is evaluated inside the kernel (one tile)
     probed_preds: Tuple[Any, ...] = ()  # (predicate, terms, bias) recognised as affine by probing only
 
     @property
@@ -164,8 +206,11 @@ def compile_formula(
     eps: float = 1e-8,
     p: int = 1,
     force_leaf: Tuple[int, ...] = (),
+    open_leaf: bool = False,
 ) -> CompiledFormula:
     sem_id = _SEM_IDS[semantics]
+    pred_slack: Dict[int, int] = {}
+    has_open = [False]
     nodes: List[capi.Node] = []
     children: List[int] = []
     weights: List[float] = []
@@ -241,11 +286,29 @@ def compile_formula(
                 raise ValueError(f"{kind} requires at least one child.")
             kids = [visit(c) for c in node.children]
             n.w_off, n.w_len = add_weights(node.weights)
+        elif kind in ("Always", "Eventually") and node.interval.end is None and open_leaf:
+            # beyond one tile: the operand's trace goes through the suffix-scan kernel and comes back as a channel
+            a, _ = interval_of(node)
+            if semantics not in OPEN_LEAF_SEMANTICS:
+                raise NotImplementedError(
+                    f"{kind} without an interval end on a trace longer than one tile: not offered for the {semantics} semantics"
+                )
+            if node.weights is not None:
+                raise NotImplementedError(f"{kind} without an interval end on a trace longer than one tile takes no weights")
+            n.kind = capi.NODE_PRED
+            leaf_index[key] = len(leaves)
+            leaves.append(OpenLeaf(node.child, 0 if kind == "Always" else 1, a))
+            pkey = (((n_channels + leaf_index[key], 1.0),), 0.0)
+            pred_index[pkey] = len(preds)
+            preds.append(pkey)
+            n.pred = pred_index[pkey]
+            pred_slack[n.pred] = a if start_slack(node.child) == 0 else -1
         elif kind in ("Always", "Eventually"):
             n.kind = capi.NODE_ALWAYS if kind == "Always" else capi.NODE_EVENTUALLY
             kids = [visit(node.child)]
             n.a, n.b = interval_of(node)
             n.w_off, n.w_len = add_weights(node.weights)
+            has_open[0] |= n.b < 0
         elif kind == "Until":
             n.kind = capi.NODE_UNTIL
             kids = [visit(node.left), visit(node.right)]
@@ -279,6 +342,7 @@ def compile_formula(
             pred_arr[i].coeff[k] = c
             used.add(d)
         pred_arr[i].bias = bias
+        pred_arr[i].slack = pred_slack.get(i, 0)
     st = capi.Formula()
     st.semantics = sem_id
     st.temperature = float(temperature)
@@ -304,11 +368,14 @@ def compile_formula(
         n_signal_channels=int(n_channels),
         leaf_preds=tuple(leaves),
         probed_preds=tuple(probed),
+        has_open=has_open[0],
     )
 
 
-def leaf_values(cf: CompiledFormula, sig):
+def leaf_values(cf: CompiledFormula, sig, sem=None):
     """``sig[B, T, D]`` (torch, on the device) -> ``[B, T, D + L]`` with one channel per leaf predicate.
+
+    An ``OpenLeaf`` channel is ``sem.robustness_trace(child, sig)`` through ``ops.open_window`` (differentiable).
 
     ``fn(signal, t)`` is the reference's per-trace callable (api.py:24,133-143): it is mapped over
     the batch with ``torch.func.vmap`` and over ``t`` either with a second vmap (callables that only
@@ -320,6 +387,15 @@ def leaf_values(cf: CompiledFormula, sig):
     B, T, _ = sig.shape
     cols = []
     for pred in cf.leaf_preds:
+        if isinstance(pred, OpenLeaf):
+            from . import ops
+
+            if sem is None:
+                raise RuntimeError("an open-ended window leaf needs the semantics object that compiled it")
+            y = sem.robustness_trace(pred.child, sig)  # [B, T]; nested open-ended windows recurse here
+            cols.append(ops.open_window(y.contiguous(), cf.struct.semantics, pred.mode, pred.start,
+                                        cf.struct.temperature, cf.struct.eps, cf.struct.p))
+            continue
         fn = pred.fn
         val = None
         try:

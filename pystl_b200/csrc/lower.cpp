@@ -256,6 +256,8 @@ struct Lowerer {
           if (nd.pred < 0 || nd.pred >= f->n_preds) fail(PYSTL_E_INVALID, "node %d: predicate index out of range", i);
           const pystl_pred_t& pr = f->preds[nd.pred];
           if (pr.n_terms < 0 || pr.n_terms > kMaxTerms) fail(PYSTL_E_UNSUPPORTED, "predicate with more than %d terms", kMaxTerms);
+          // a channel of values the host computed (open-ended window beyond one tile) that end before the horizon
+          slack[i] = pr.slack < 0 ? kNever : std::min(pr.slack, kNever);
           break;
         }
         case PYSTL_NODE_NOT:

@@ -397,6 +397,25 @@ extern "C" int pystl_b200_fused_source(const pystl_formula_t* f, int64_t T, int3
 extern "C" int pystl_b200_abi_version(void) { return PYSTL_B200_ABI_VERSION; }
 extern "C" const char* pystl_b200_last_error(void) { return g_err; }
 
+// open-ended windows beyond one tile: scan.cu
+namespace pystl {
+int open_window_forward(int32_t semantics, int32_t mode, int32_t a, float temperature, float eps, int32_t p, const float* y,
+                        int64_t B, int64_t T, float* out, int32_t* arg, void* stream, char* err, size_t err_cap);
+int open_window_backward(int32_t semantics, int32_t mode, int32_t a, float temperature, float eps, int32_t p, const float* y,
+                         const float* out, const int32_t* arg, const float* grad_out, int64_t B, int64_t T, float* grad_y,
+                         void* stream, char* err, size_t err_cap);
+}  // namespace pystl
+extern "C" int pystl_b200_open_window_forward(int32_t semantics, int32_t mode, int32_t a, float temperature, float eps, int32_t p,
+                                              const float* y, int64_t B, int64_t T, float* out, int32_t* arg, void* stream) {
+  return pystl::open_window_forward(semantics, mode, a, temperature, eps, p, y, B, T, out, arg, stream, g_err, sizeof(g_err));
+}
+extern "C" int pystl_b200_open_window_backward(int32_t semantics, int32_t mode, int32_t a, float temperature, float eps, int32_t p,
+                                               const float* y, const float* out, const int32_t* arg, const float* grad_out,
+                                               int64_t B, int64_t T, float* grad_y, void* stream) {
+  return pystl::open_window_backward(semantics, mode, a, temperature, eps, p, y, out, arg, grad_out, B, T, grad_y, stream, g_err,
+                                     sizeof(g_err));
+}
+
 extern "C" int pystl_b200_plan(const pystl_formula_t* f, int64_t T, int32_t D, int32_t backward, pystl_plan_t* plan) {
   if (!plan) return set_err(PYSTL_E_INVALID, "plan is NULL");
   Lowered lw;

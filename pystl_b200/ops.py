@@ -6,7 +6,8 @@ Three entry points of ``include/pystl_b200.h`` become dispatcher ops
     pystl_b200::robustness_grad(signal, grad_out[B, T, C], handle)     -> grad_signal[B, T, D]
     pystl_b200::value_and_grad(signal, scale, handle)                  -> (out, acc[2] float64, grad_signal)
 
-with fake (meta) kernels and batching rules; ``evaluate`` -- an ``autograd.Function`` over them with
+(plus ``open_window / open_window_grad`` for the suffix-scan kernels of csrc/scan.cu: open-ended windows on
+traces longer than one tile) with fake (meta) kernels and batching rules; ``evaluate`` -- an ``autograd.Function`` over them with
 ``setup_context`` and a ``vmap`` rule -- is the differentiable entry point the semantics objects call,
 so that ``torch.compile`` traces through a robustness evaluation without a graph break and
 ``torch.func.vmap / grad`` compose with it (the precedent is ``jax.vmap`` over the reference's JAX
@@ -192,3 +193,89 @@ class Robustness(torch.autograd.Function):
 def evaluate(signal: torch.Tensor, handle: int) -> torch.Tensor:
     """Differentiable robustness evaluation of ``signal[B, T, D]`` -> ``out[B, T, C]``."""
     return Robustness.apply(signal, handle)
+
+
+# ---- open-ended windows beyond one tile: suffix scan of a value trace (csrc/scan.cu) -------------------------------
+_lib.define("open_window_fwd(Tensor y, int semantics, int mode, int start, float temperature, float eps, int p) -> (Tensor, Tensor)")
+_lib.define("open_window_grad(Tensor y, Tensor out, Tensor arg, Tensor grad_out, int semantics, int mode, int start, "
+            "float temperature, float eps, int p) -> Tensor")
+
+
+def _check_trace(y: torch.Tensor) -> None:
+    if not y.is_cuda:
+        raise RuntimeError("pystl_b200 ops need a CUDA tensor; there is no CPU fallback")
+    if y.dim() != 2 or y.dtype != torch.float32:
+        raise ValueError("the value trace must be float32 with shape (batch, time)")
+
+
+def _open_window_fwd_cuda(y, semantics, mode, start, temperature, eps, p):
+    _check_trace(y)
+    y = y.contiguous()
+    B, T = y.shape
+    out = torch.empty_like(y)
+    arg = torch.empty((B, T) if semantics == capi.SEM_CLASSIC else (0,), dtype=torch.int32, device=y.device)
+    with torch.cuda.device(y.device):
+        rc = capi.lib().pystl_b200_open_window_forward(int(semantics), int(mode), int(start), float(temperature), float(eps), int(p),
+                                                       y.data_ptr(), B, T, out.data_ptr(), arg.data_ptr() if arg.numel() else None,
+                                                       torch.cuda.current_stream(y.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return out, arg
+
+
+def _open_window_grad_cuda(y, out, arg, grad_out, semantics, mode, start, temperature, eps, p):
+    _check_trace(y)
+    y, out = y.contiguous(), out.contiguous()
+    g = grad_out.to(dtype=torch.float32).contiguous()
+    B, T = y.shape
+    if tuple(g.shape) != (B, T) or tuple(out.shape) != (B, T):
+        raise ValueError(f"out / grad_out must have shape {(B, T)}")
+    grad = torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        rc = capi.lib().pystl_b200_open_window_backward(int(semantics), int(mode), int(start), float(temperature), float(eps), int(p),
+                                                        y.data_ptr(), out.data_ptr(), arg.data_ptr() if arg.numel() else None,
+                                                        g.data_ptr(), B, T, grad.data_ptr(),
+                                                        torch.cuda.current_stream(y.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return grad
+
+
+_lib.impl("open_window_fwd", _open_window_fwd_cuda, "CUDA")
+_lib.impl("open_window_grad", _open_window_grad_cuda, "CUDA")
+open_window_fwd = torch.ops.pystl_b200.open_window_fwd
+open_window_grad = torch.ops.pystl_b200.open_window_grad
+
+
+@torch.library.register_fake("pystl_b200::open_window_fwd")
+def _(y, semantics, mode, start, temperature, eps, p):
+    return torch.empty_like(y), y.new_empty(tuple(y.shape) if semantics == capi.SEM_CLASSIC else (0,), dtype=torch.int32)
+
+
+@torch.library.register_fake("pystl_b200::open_window_grad")
+def _(y, out, arg, grad_out, semantics, mode, start, temperature, eps, p):
+    return torch.empty_like(y)
+
+
+class OpenWindow(torch.autograd.Function):
+    """``out[b, t]`` = Always / Eventually of ``y[b, t + start .. T - 1]``; the adjoint is the mirrored prefix scan."""
+
+    @staticmethod
+    def forward(y, semantics, mode, start, temperature, eps, p):
+        out, arg = open_window_fwd(y, semantics, mode, start, temperature, eps, p)
+        return out, arg
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        y, *ctx.params = inputs
+        out, arg = output
+        ctx.mark_non_differentiable(arg)
+        ctx.save_for_backward(y, out, arg)
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_arg):
+        y, out, arg = ctx.saved_tensors
+        return (open_window_grad(y, out, arg, grad_out, *ctx.params),) + (None,) * 6
+
+
+def open_window(y: torch.Tensor, semantics: int, mode: int, start: int, temperature: float, eps: float, p: int) -> torch.Tensor:
+    """Differentiable ``G[start, inf)`` (mode 0) / ``F[start, inf)`` (mode 1) of the value trace ``y[B, T]``."""
+    return OpenWindow.apply(y, int(semantics), int(mode), int(start), float(temperature), float(eps), int(p))[0]

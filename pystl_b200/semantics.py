@@ -27,6 +27,7 @@ every call raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Any, Dict, Optional, Sequence, Tuple
 
@@ -62,25 +63,27 @@ except Exception:  # the GPU box has no `pystl`: same interface, no common base
 class _B200Semantics(_ReferenceSemantics):
     syntax = ""
     out_channels = 1
+    force_open_leaf = False  # True: open-ended Always / Eventually always go through the suffix-scan kernels
 
     def __init__(self) -> None:
         self._cache: Dict[Tuple, Tuple[Any, CompiledFormula]] = {}
         self._verified: Dict[Tuple, Tuple[Any, Tuple[int, ...]]] = {}
         self._list_formulas: Dict[Tuple, Any] = {}
+        self._open: Dict[Tuple, Tuple[Any, bool]] = {}
 
     # ---- kwargs forwarded to the C ABI -------------------------------------------------
     def _params(self) -> dict:
         return {}
 
     # ---- formula cache (the only mutable state; keyed by object identity + D) ----------
-    def compile(self, formula: Any, n_channels: int, force_leaf: Tuple[int, ...] = ()) -> CompiledFormula:
+    def compile(self, formula: Any, n_channels: int, force_leaf: Tuple[int, ...] = (), open_leaf: bool = False) -> CompiledFormula:
         # the semantics' own parameters are part of the key: changing sem.temperature / eps / p
         # after the first call recompiles instead of being silently ignored
-        key = (id(formula), int(n_channels), tuple(sorted(self._params().items())), tuple(force_leaf))
+        key = (id(formula), int(n_channels), tuple(sorted(self._params().items())), tuple(force_leaf), bool(open_leaf))
         hit = self._cache.get(key)
         if hit is not None and hit[0] is formula:
             return hit[1]
-        cf = compile_formula(formula, self.syntax, n_channels, force_leaf=force_leaf, **self._params())
+        cf = compile_formula(formula, self.syntax, n_channels, force_leaf=force_leaf, open_leaf=open_leaf, **self._params())
         if len(self._cache) > 256:
             self._cache.clear()
         self._cache[key] = (formula, cf)
@@ -93,6 +96,9 @@ class _B200Semantics(_ReferenceSemantics):
         recompiled as a leaf channel (``compiler.verify_probed``)."""
         B, T, D = sig.shape
         cf = self.compile(formula, D)
+        open_leaf = cf.has_open and self._needs_open_leaf(formula, cf, T)
+        if open_leaf:
+            cf = self.compile(formula, D, open_leaf=True)
         if not cf.probed_preds or B == 0 or T == 0:
             return cf
         vkey = (id(formula), D, T)
@@ -105,7 +111,33 @@ class _B200Semantics(_ReferenceSemantics):
             if len(self._verified) > 256:
                 self._verified.clear()
             hit = self._verified[vkey] = (formula, force)
-        return self.compile(formula, D, hit[1]) if hit[1] else cf
+        return self.compile(formula, D, hit[1], open_leaf) if hit[1] else cf
+
+    def _needs_open_leaf(self, formula: Any, cf: CompiledFormula, T: int) -> bool:
+        """An ``Always / Eventually`` without an end is evaluated inside the formula kernel while the whole trace
+        fits one tile (the plan says so); beyond that it goes through the suffix-scan kernels as a leaf channel
+        (``compiler.OpenLeaf``).  Decided once per (formula, D, T, parameters)."""
+        if self.force_open_leaf or os.environ.get("PYSTL_B200_OPEN_LEAF") == "1":
+            return True  # (tests: the scan path against the in-kernel path at any T)
+        key = (id(formula), cf.n_signal_channels, int(T), tuple(sorted(self._params().items())))
+        hit = self._open.get(key)
+        if hit is None or hit[0] is not formula:
+            fails = []
+            for backward in (0, 1):  # the gradient kernel keeps more planes per tile: its limit on T is lower
+                p = capi.Plan()
+                rc = capi.lib().pystl_b200_plan(cf.ptr(), int(T), cf.n_channels, backward, C.byref(p))
+                # (lower.cpp: plan_geometry / codegen.cpp: fused_geometry; any other status is reported by the evaluation)
+                fails.append(rc == capi.E_UNSUPPORTED and b"open-ended" in (capi.lib().pystl_b200_last_error() or b""))
+            need = any(fails)
+            if need and not fails[0]:  # values still fit one tile: keep them there when the scan path cannot take over
+                try:
+                    self.compile(formula, cf.n_signal_channels, open_leaf=True)
+                except NotImplementedError:
+                    need = False
+            if len(self._open) > 256:
+                self._open.clear()
+            hit = self._open[key] = (formula, need)
+        return hit[1]
 
     def invalidate(self, formula: Any = None) -> None:
         """Forget what was compiled for ``formula`` (all formulas when None): a predicate's ``fn`` is
@@ -113,8 +145,9 @@ class _B200Semantics(_ReferenceSemantics):
         if formula is None:
             self._cache.clear()
             self._verified.clear()
+            self._open.clear()
             return
-        for d in (self._cache, self._verified):
+        for d in (self._cache, self._verified, self._open):
             for k in [k for k in d if k[0] == id(formula)]:
                 d.pop(k, None)
 
@@ -122,6 +155,8 @@ class _B200Semantics(_ReferenceSemantics):
         """Tiling / validity report for ``formula`` on traces of ``horizon`` samples (host only)."""
         if cf is None:
             cf = self.compile(formula, n_channels)
+            if cf.has_open and self._needs_open_leaf(formula, cf, int(horizon)):
+                cf = self.compile(formula, n_channels, open_leaf=True)
         p = capi.Plan()
         rc = capi.lib().pystl_b200_plan(cf.ptr(), int(horizon), cf.n_channels, 0, C.byref(p))
         capi.raise_for(rc, capi.lib().pystl_b200_last_error())
@@ -165,7 +200,7 @@ class _B200Semantics(_ReferenceSemantics):
         sig, squeeze, home = self._prepare(signal)  # (stays connected to `signal` in the autograd graph)
         cf = self._checked_compile(formula, sig)
         if cf.leaf_preds:  # non-affine predicates: leaf channels computed by torch, inside the graph
-            sig = leaf_values(cf, sig)
+            sig = leaf_values(cf, sig, self)
         out = ops.evaluate(sig, ops.handle_of(cf, self.out_channels))
         if home != out.device:
             out = out.to(home)
@@ -187,7 +222,7 @@ class _B200Semantics(_ReferenceSemantics):
         acc = torch.zeros(2, dtype=torch.float64, device=sig.device)
         plan = self.plan(formula, sig.shape[1], sig.shape[2], cf)
         with torch.no_grad():
-            sig = leaf_values(cf, sig)
+            sig = leaf_values(cf, sig, self)
         self._forward_raw(cf, sig, acc)
         valid = 0 if plan["raises_always"] else max(sig.shape[1] - plan["start_slack"], 0)
         acc[1] = float(sig.shape[0] * valid)
@@ -217,7 +252,7 @@ class _B200Semantics(_ReferenceSemantics):
         if cf.leaf_preds:  # the kernel differentiates up to the leaf channels, autograd through fn
             base = sig.detach().requires_grad_(True)
             with torch.enable_grad():
-                sig = leaf_values(cf, base)
+                sig = leaf_values(cf, base, self)
         kin = sig.detach()
         grad = torch.empty_like(kin)
         stream = torch.cuda.current_stream(sig.device).cuda_stream

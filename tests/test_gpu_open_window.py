@@ -1,0 +1,212 @@
+"""GPU tier: ``Always / Eventually`` without an interval end (api.py:49-54: the window runs to the horizon) on traces
+LONGER than one tile -- the suffix-scan kernels of csrc/scan.cu behind ``compiler.OpenLeaf``.
+
+1. against the float64 oracle (values and gradients) with the scan path forced at sizes the dense oracle finishes;
+2. the scan path against the in-kernel path (one tile) on the same inputs;
+3. at T = 20000 (beyond any tile) against float64 suffix scans written with torch cumulative ops -- the closed forms of
+   classic.py:39-57 (min / max), smooth.py:47-65 (+-tau logsumexp(+-x / tau)) -- and through the properties the
+   domain offers (a constant trace, monotone suffixes, the last valid sample equals the operand).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense
+from pystl_b200 import create_semantics
+from pystl_b200.compiler import OpenLeaf
+from pystl_b200.formula import Always, And, Eventually, Interval, Not, Or, affine_predicate
+
+pytestmark = pytest.mark.gpu
+
+SEMS = [("classical", {}), ("smooth", {"temperature": 0.5}), ("smooth", {"temperature": 0.05}), ("agm", {}), ("dgmsr", {"eps": 1e-8, "p": 1}),
+        ("dgmsr", {"eps": 1e-8, "p": 2})]
+IDS = ["classical", "smooth0.5", "smooth0.05", "agm", "dgmsr1", "dgmsr2"]
+
+
+def preds():
+    x = affine_predicate("x", {0: 1.0}, 0.1)
+    y = affine_predicate("y", {1: -1.0, 0: 0.25}, 0.3)
+    return x, y
+
+
+def formulas():
+    x, y = preds()
+    return {
+        "G_open": Always(x, Interval(0, None)),
+        "F_open_a": Eventually(y, Interval(7, None)),
+        "mixed": And(Always(x, Interval(3, None)), Eventually(y, Interval(0, 10))),
+        "under_window": Eventually(Always(Or(x, Not(y)), Interval(2, None)), Interval(0, 5)),
+        "nested": Always(Eventually(x, Interval(0, None)), Interval(2, None)),
+        "over_nary": Eventually(And(x, Not(y)), Interval(5, None)),
+    }
+
+
+def signal(B, T, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.uniform(-0.5, 0.5, size=(B, 1, 2))
+    return (base + 0.4 * rng.standard_normal((B, T, 2))).astype(np.float32)
+
+
+def tol(sem):
+    # classical values are exact; the others accumulate a few hundred terms per output in fp32
+    return dict(rtol=1e-5, atol=1e-6) if sem == "classical" else dict(rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", list(formulas()))
+@pytest.mark.parametrize("sem,kw", SEMS, ids=IDS)
+def test_scan_path_against_the_oracle(sem, kw, name):
+    T = 300
+    phi = formulas()[name]
+    sig = signal(3, T, 11)
+    s = create_semantics(sem, backend="b200", **kw)
+    s.force_open_leaf = True
+    x = torch.tensor(sig, device="cuda", requires_grad=True)
+    cf = s._checked_compile(phi, x.detach())
+    assert any(isinstance(p, OpenLeaf) for p in cf.leaf_preds)
+    got = s.robustness_trace(phi, x)
+    x64 = torch.tensor(sig, dtype=torch.float64, requires_grad=True)
+    want = dense.robustness_trace(phi, x64, dense.make(sem, **kw))
+    ok = torch.isfinite(want)
+    assert torch.equal(torch.isfinite(got.detach().cpu()), ok)
+    assert torch.allclose(got.detach().cpu().double()[ok], want.detach()[ok], **tol(sem))
+
+    g = torch.tensor(np.random.default_rng(3).uniform(0.25, 1.0, size=tuple(want.shape)))
+    (torch.nan_to_num(got) * g.to("cuda", torch.float32)).sum().backward()
+    (torch.nan_to_num(want) * g).sum().backward()
+    # (dgmsr: the reference's formulation multiplies the window's entries, _dgmsr.py:96-102 -- over a few hundred samples
+    # the product underflows in float64 and autograd returns NaN for the whole trace; the kernels work in the log domain
+    # and are compared on the traces the oracle can differentiate)
+    fin = torch.isfinite(x64.grad).all(dim=(1, 2))
+    assert bool(fin.any()) and (sem == "dgmsr" or bool(fin.all()))
+    scale = float(x64.grad[fin].abs().max()) + 1e-12
+    assert bool(torch.isfinite(x.grad).all())
+    assert torch.allclose(x.grad.cpu().double()[fin], x64.grad[fin], rtol=5e-4, atol=2e-5 * scale)
+
+    mean, grad = s.mean_robustness_and_grad(phi, torch.tensor(sig, device="cuda"))
+    x2 = torch.tensor(sig, dtype=torch.float64, requires_grad=True)
+    w2 = dense.robustness_trace(phi, x2, dense.make(sem, **kw))
+    m2 = w2[torch.isfinite(w2)].mean()
+    m2.backward()
+    assert abs(float(mean) - float(m2.detach())) < 1e-4 * (1 + abs(float(m2.detach())))
+    fin = torch.isfinite(x2.grad).all(dim=(1, 2))
+    assert torch.allclose(grad.cpu().double()[fin], x2.grad[fin], rtol=5e-4, atol=2e-5 * (float(x2.grad[fin].abs().max()) + 1e-12))
+
+
+@pytest.mark.parametrize("sem,kw", SEMS, ids=IDS)
+def test_scan_path_equals_the_in_kernel_path(sem, kw):
+    T = 2048  # one tile for the value AND the gradient kernel of every semantics: both paths exist
+    sig = torch.tensor(signal(4, T, 5), device="cuda")
+    for name, phi in formulas().items():
+        a = create_semantics(sem, backend="b200", **kw)
+        b = create_semantics(sem, backend="b200", **kw)
+        b.force_open_leaf = True
+        xa = sig.clone().requires_grad_(True)
+        xb = sig.clone().requires_grad_(True)
+        ra, rb = a.robustness_trace(phi, xa), b.robustness_trace(phi, xb)
+        ok = torch.isfinite(ra)
+        assert torch.equal(ok, torch.isfinite(rb)), name
+        assert torch.allclose(ra[ok], rb[ok], **tol(sem)), (name, float((ra[ok] - rb[ok]).abs().max()))
+        torch.nan_to_num(ra).sum().backward()
+        torch.nan_to_num(rb).sum().backward()
+        scale = float(xa.grad.abs().max()) + 1e-12
+        assert torch.allclose(xa.grad, xb.grad, rtol=2e-3, atol=1e-4 * scale), (name, float((xa.grad - xb.grad).abs().max()), scale)
+
+
+def _suffix(y64, sem, kw, mode):
+    """float64 closed forms of the open-ended window of a value trace y[B, T] (a = 0)."""
+    r = torch.flip(y64, dims=(1,))
+    if sem == "classical":
+        c = torch.cummin(r, 1).values if mode == 0 else torch.cummax(r, 1).values
+    else:
+        tau = kw["temperature"]
+        c = -tau * torch.logcumsumexp(-r / tau, 1) if mode == 0 else tau * torch.logcumsumexp(r / tau, 1)
+    return torch.flip(c, dims=(1,))
+
+
+@pytest.mark.parametrize("sem,kw", [SEMS[0], SEMS[1], SEMS[2]], ids=IDS[:3])
+@pytest.mark.parametrize("a", [0, 37])
+def test_long_traces_against_closed_forms(sem, kw, a):
+    B, T = 5, 20000
+    x, _ = preds()
+    sig = signal(B, T, 9)
+    s = create_semantics(sem, backend="b200", **kw)
+    for mode, phi in ((0, Always(x, Interval(a, None))), (1, Eventually(x, Interval(a, None)))):
+        xs = torch.tensor(sig, device="cuda", requires_grad=True)
+        got = s.robustness_trace(phi, xs)
+        assert s.plan(phi, T, 2)["start_slack"] == a
+        x64 = torch.tensor(sig, dtype=torch.float64, requires_grad=True)
+        y64 = x64[..., 0] + 0.1
+        full = _suffix(y64, sem, kw, mode)  # value of the window starting at u
+        want = torch.full_like(full, float("nan"))
+        want[:, : T - a] = full[:, a:]
+        ok = torch.isfinite(want)
+        assert torch.equal(torch.isfinite(got.detach().cpu()), ok)
+        assert torch.allclose(got.detach().cpu().double()[ok], want.detach()[ok], rtol=1e-5, atol=2e-5)
+        g = torch.tensor(np.random.default_rng(1).uniform(0.25, 1.0, size=(B, T)))
+        (torch.nan_to_num(got) * g.to("cuda", torch.float32)).sum().backward()
+        (torch.nan_to_num(want) * g).sum().backward()
+        scale = float(x64.grad.abs().max())
+        assert torch.allclose(xs.grad.cpu().double(), x64.grad, rtol=1e-3, atol=1e-5 * scale)
+        # samples before t + a of the first output belong to no window
+        if a:
+            assert float(xs.grad[:, :a].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("sem,kw", SEMS, ids=IDS)
+def test_long_trace_properties(sem, kw):
+    B, T = 3, 16385  # one sample past the largest tile
+    x, y = preds()
+    s = create_semantics(sem, backend="b200", **kw)
+    sig = torch.tensor(signal(B, T, 21), device="cuda")
+    g = s.robustness_trace(Always(x, Interval(0, None)), sig)
+    f = s.robustness_trace(Eventually(x, Interval(0, None)), sig)
+    leaf = sig[..., 0] + 0.1
+    # the window [T-1, T-1] holds one sample: every semantics returns it (agm: the mean of one entry; dgmsr: up to
+    # sqrt(eps) = 1e-4, _dgmsr.py:83-102)
+    one = dict(rtol=1e-5, atol=1e-6) if sem != "dgmsr" else dict(rtol=1e-5, atol=2.5e-4)
+    assert torch.allclose(g[:, -1], leaf[:, -1], **one)
+    assert torch.allclose(f[:, -1], leaf[:, -1], **one)
+    assert bool((g <= f + one["atol"] + 1e-5).all())
+    if sem in ("classical", "smooth"):
+        # a longer window can only lower Always / raise Eventually
+        assert bool((g[:, :-1] <= g[:, 1:] + 1e-6).all()) and bool((f[:, :-1] >= f[:, 1:] - 1e-6).all())
+    # a constant positive trace: Always == Eventually == the constant for classical / agm / dgmsr
+    const = torch.full((2, T, 2), 0.7, device="cuda")
+    gc = s.robustness_trace(Always(x, Interval(0, None)), const)
+    if sem != "smooth":
+        assert torch.allclose(gc, torch.full_like(gc, 0.8), rtol=2e-4, atol=1e-5)
+    # mixed with bounded operators, one-pass mean + gradient agrees with autograd through the trace
+    phi = And(Always(x, Interval(3, None)), Eventually(y, Interval(0, 10)))
+    xs = sig.clone().requires_grad_(True)
+    r = s.robustness_trace(phi, xs)
+    assert int(torch.isnan(r).sum()) == B * 3 and bool(torch.isnan(r[:, -3:]).all())
+    m = r[torch.isfinite(r)].mean()
+    m.backward()
+    mean, grad = s.mean_robustness_and_grad(phi, sig)
+    assert abs(float(mean) - float(m)) < 1e-5 * (1 + abs(float(m)))
+    assert torch.allclose(grad, xs.grad, rtol=1e-4, atol=1e-6 * float(xs.grad.abs().max()) + 1e-12)
+
+
+def test_a_window_that_always_raises_is_nan_everywhere():
+    # an operand that is itself undefined near the horizon makes the open-ended window raise at every t (api.py:218-221)
+    x, _ = preds()
+    phi = Eventually(Always(x, Interval(1, 4)), Interval(5, None))
+    sig = torch.tensor(signal(2, 20000, 2), device="cuda")
+    for sem, kw in SEMS[:2]:
+        s = create_semantics(sem, backend="b200", **kw)
+        assert s.plan(phi, 20000, 2)["raises_always"] == 1
+        assert bool(torch.isnan(s.robustness_trace(phi, sig)).all())
+        want = dense.robustness_trace(phi, torch.tensor(signal(1, 40, 2), dtype=torch.float64), dense.make(sem, **kw))
+        assert bool(torch.isnan(want).all())
+
+
+def test_unsupported_cases_are_loud():
+    x, y = preds()
+    sig = torch.zeros(1, 20000, 2, device="cuda")
+    with pytest.raises(NotImplementedError):
+        create_semantics("cumulative", backend="b200").robustness_trace(Always(x, Interval(0, None)), sig)
+    with pytest.raises(NotImplementedError):
+        create_semantics("agm", backend="b200").robustness_trace(Always(x, Interval(0, None), weights=[1.0] * 20000), sig)

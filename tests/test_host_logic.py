@@ -115,7 +115,49 @@ def test_header_and_library_agree():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.pystl_b200_abi_version() == capi.ABI_VERSION
-    assert C.sizeof(capi.Node) == 48 and C.sizeof(capi.Pred) == 72
+    assert C.sizeof(capi.Node) == 48 and C.sizeof(capi.Pred) == 76  # ABI 2: + slack
+
+
+def test_open_ended_windows_beyond_one_tile_become_leaf_channels():
+    """An Always / Eventually without an end (api.py:49-54) keeps the whole trace in one tile; on longer traces the
+    node is lowered to a leaf channel the suffix-scan kernels fill (compiler.OpenLeaf), and the predicate's slack
+    carries the empty-window rule of api.py:218-221 into the plan."""
+    from pystl_b200.compiler import OpenLeaf, start_slack, NEVER
+
+    x = affine_predicate("x", {0: 1.0}, 0.0)
+    y = affine_predicate("y", {1: -1.0}, 0.5)
+    phi = And(Always(x, Interval(3, None)), Eventually(y, Interval(0, 10)))
+    for sem_name in ("classical", "smooth", "agm", "dgmsr"):
+        sem = create_semantics(sem_name, backend="b200")
+        inside = sem.compile(phi, 2)
+        assert inside.has_open and not inside.leaf_preds
+        assert not sem._needs_open_leaf(phi, inside, 2048) and sem._needs_open_leaf(phi, inside, 20000)
+        # (the gradient kernel keeps more planes: where IT stops fitting one tile, values go the scan path as well)
+        cf = sem.compile(phi, 2, open_leaf=True)
+        (leaf,) = cf.leaf_preds
+        assert isinstance(leaf, OpenLeaf) and leaf.child is x and (leaf.mode, leaf.start) == (0, 3)
+        assert cf.n_channels == 3 and not cf.has_open
+        slacks = sorted(cf.preds[i].slack for i in range(cf.struct.n_preds))
+        assert slacks == [0, 3]
+        short, long = sem.plan(phi, 2048, 2), sem.plan(phi, 20000, 2)
+        assert short["n_tiles"] == 1 and long["n_tiles"] > 1
+        assert short["start_slack"] == long["start_slack"] == 3 and long["lookahead"] == 10
+        # a window over the open-ended one: its whole extent must end before the operand does
+        over = Always(Always(x, Interval(3, None)), Interval(0, 5))
+        assert sem.plan(over, 2048, 2)["start_slack"] == sem.plan(over, 20000, 2)["start_slack"] == 8
+        # an operand that is undefined near the horizon: the open-ended window raises at every t
+        never = Eventually(Always(x, Interval(1, 4)), Interval(2, None))
+        assert start_slack(never) == NEVER
+        assert sem.plan(never, 2048, 2)["raises_always"] == sem.plan(never, 20000, 2)["raises_always"] == 1
+        assert sem.compile(never, 2, open_leaf=True).preds[0].slack == -1
+    cum = create_semantics("cumulative", backend="b200")
+    assert cum.plan(phi, 2048, 2)["n_tiles"] == 1
+    with pytest.raises(NotImplementedError):
+        cum.plan(phi, 20000, 2)
+    with pytest.raises(NotImplementedError):  # window weights are per position of the clipped window
+        create_semantics("agm", backend="b200").plan(Always(x, Interval(0, None), weights=[1.0] * 20000), 20000, 2)
+    with pytest.raises(NotImplementedError):  # an unbounded Until still needs one tile
+        create_semantics("classical", backend="b200").plan(Until(x, y, Interval(0, None)), 20000, 2)
 
 
 @pytest.mark.parametrize("cfg", sorted(BASELINE_SPECS))
@@ -142,9 +184,11 @@ def test_plan_validity_rules_follow_the_reference():
     # api.py:288-293: Until evaluates its children up to the horizon
     assert sem.plan(x.eventually((1, 2)).until(x, (0, 3)), 80, 1)["raises_always"] == 1
     assert sem.plan(x.eventually((0, 2)).until(x, (0, 3)), 80, 1)["raises_always"] == 0
-    with pytest.raises(NotImplementedError):  # open interval on a trace longer than any tile
-        sem.plan(x.always((0, None)), 100000, 1)
+    # an open interval keeps the trace in one tile; beyond that the window is a scanned leaf channel (next test)
+    assert sem.plan(x.always((0, None)), 100000, 1)["n_tiles"] > 1
     assert sem.plan(x.always((0, None)), 4000, 1)["n_tiles"] == 1
+    with pytest.raises(NotImplementedError):  # an unbounded Until on a trace longer than any tile
+        sem.plan(x.until(x, (0, None)), 100000, 1)
 
 
 def test_loud_failure_without_the_library(monkeypatch, tmp_path):
