@@ -38,7 +38,29 @@ struct ScanRed {  // agm, dgmsr: the reducers of the formula kernels
   static __device__ A ident() { return R::ident(); }
   static __device__ A lift(float y, int, const RP& rp) { return R::lift(Vec<1>{{y}}, rp, 1.f); }
   static __device__ A comb(A a, A b) { return R::comb(a, b); }
+  static __device__ A push(A l, A acc) { return R::comb(l, acc); }
   static __device__ float fin(A a, float n, const RP& rp) { return R::fin(a, n, rp).x[0]; }
+  static __device__ int arg(A) { return 0; }
+};
+template <int MODE>
+struct ScanRed<SEM_DGMSR, MODE> {  // the formula kernels' reducer; fin BRANCHES on the flag instead of evaluating both means
+  using R = Red<SEM_DGMSR, MODE>;  // (a long suffix almost always holds a non-positive entry: rcp + sqrt instead of seven MUFU ops)
+  using A = typename R::A;
+  static __device__ A ident() { return R::ident(); }
+  static __device__ A lift(float y, int, const RP& rp) { return R::lift(Vec<1>{{y}}, rp, 1.f); }
+  static __device__ A comb(A a, A b) { return R::comb(a, b); }
+  static __device__ A push(A l, A acc) { return R::comb(l, acc); }
+  static __device__ float fin(A a, float n, const RP& rp) {
+    float h;
+    if (a.x[1] == f_inf()) {  // _dgmsr.py:83-87
+      const float m = rp.eps_p + a.x[0] * fast_rcp(n);
+      h = rp.sqrt_eps - (PYSTL_P(rp) == 1 ? fast_sqrt(m) : fast_pow(m, rp.inv2p));
+    } else {
+      h = R::fin(a, n, rp).x[0];
+      return h;
+    }
+    return MODE == MODE_AND ? h : -h;
+  }
   static __device__ int arg(A) { return 0; }
 };
 template <int MODE>
@@ -50,6 +72,7 @@ struct ScanRed<SEM_CLASSIC, MODE> {  // (value, position): the earlier operand k
     const bool tb = MODE == MODE_AND ? (b.x[0] < a.x[0]) : (b.x[0] > a.x[0]);
     return tb ? b : a;
   }
+  static __device__ A push(A l, A acc) { return comb(l, acc); }
   static __device__ float fin(A a, float, const RP&) { return a.x[0]; }
   static __device__ int arg(A a) { return f2i(a.x[1]); }
 };
@@ -62,6 +85,12 @@ struct ScanRed<SEM_SMOOTH, MODE> {  // (m, s): sum of 2^e = s * 2^m, m the runni
     const float m = fmaxf(a.x[0], b.x[0]);
     if (m == -f_inf()) return A{{m, 0.f}};
     return A{{m, a.x[1] * fast_ex2(a.x[0] - m) + b.x[1] * fast_ex2(b.x[0] - m)}};
+  }
+  // one element in front of an accumulator: one MUFU instead of two
+  static __device__ A push(A l, A acc) {
+    const float d = l.x[0] - acc.x[0];
+    const float ex = fast_ex2(-fabsf(d));
+    return A{{fmaxf(l.x[0], acc.x[0]), d <= 0.f ? fmaf(l.x[1], ex, acc.x[1]) : fmaf(acc.x[1], ex, l.x[1])}};
   }
   static __device__ float fin(A a, float, const RP& rp) {
     const float l = (a.x[0] + fast_lg2(a.x[1])) * rp.invk;
@@ -84,48 +113,98 @@ __device__ A shfl_up_acc(A v, int d) {
   for (int w = 0; w < (int)(sizeof(A) / sizeof(float)); ++w) r.x[w] = __shfl_up_sync(0xffffffffu, v.x[w], d);
   return r;
 }
+template <class A>
+__device__ A shfl_acc(A v, int src) {
+  A r;
+#pragma unroll
+  for (int w = 0; w < (int)(sizeof(A) / sizeof(float)); ++w) r.x[w] = __shfl_sync(0xffffffffu, v.x[w], src);
+  return r;
+}
+
+// A warp walks its trace in CHUNKS of 256 samples: global loads and stores are coalesced rows of 32 consecutive samples,
+// staged through a per-warp shared-memory buffer so that every lane then owns 8 CONSECUTIVE samples (one pad word per 32
+// keeps both access patterns conflict-free).  The trace is read once and written once.
+constexpr int kChunk = 256;
+constexpr int kBuf = kChunk + kChunk / 32;
+__device__ __forceinline__ int pad(int e) { return e + (e >> 5); }
 
 template <int SEM, int MODE>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) open_window_fwd(const float* __restrict__ y, float* __restrict__ out,
                                                                        int* __restrict__ arg, long long B, int T, int a, RP rp) {
   using S = ScanRed<SEM, MODE>;
   using A = typename S::A;
-  const long long b = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  __shared__ float s_val[kWarpsPerBlock][kBuf];
+  __shared__ int s_arg[SEM == SEM_CLASSIC ? kWarpsPerBlock : 1][SEM == SEM_CLASSIC ? kBuf : 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * kWarpsPerBlock + warp;
   if (b >= B) return;
-  const int lane = threadIdx.x & 31;
   const float* yb = y + b * T;
   float* ob = out + b * T;
   int* ab = arg ? arg + b * T : nullptr;
-  const int seg = (T + 31) / 32;
-  const int lo = lane * seg < T ? lane * seg : T, hi = lo + seg < T ? lo + seg : T;
-  // pass 1: the segment's total
-  A tot = S::ident();
-  for (int k = hi - 1; k >= lo; --k) tot = S::comb(S::lift(yb[k], k, rp), tot);
-  // inclusive suffix scan over the lanes, then exclusive
-  A inc = tot;
+  float* buf = s_val[warp];
+  A carry = S::ident();  // everything after the current chunk
+  const int c_last = ((T - 1) / kChunk) * kChunk;
+  float nxt[8];  // the next chunk's rows, in flight while this one is reduced
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const A other = shfl_down_acc(inc, d);
-    if (lane + d < 32) inc = S::comb(inc, other);
+  for (int j = 0; j < 8; ++j) {
+    const int u = c_last + j * 32 + lane;
+    nxt[j] = u < T ? yb[u] : 0.f;
   }
-  A run = shfl_down_acc(inc, 1);
-  if (lane == 31) run = S::ident();
-  // pass 2: S[u] for the segment's u, stored at t = u - a; the last a outputs repeat S[T - 1]'s value
-  for (int u = hi - 1; u >= lo; --u) {
-    run = S::comb(S::lift(yb[u], u, rp), run);
-    const float v = S::fin(run, (float)(T - u), rp);
-    const int t = u - a;
-    if (t >= 0) {
-      ob[t] = v;
-      if (ab) ab[t] = S::arg(run);
+  for (int c0 = c_last; c0 >= 0; c0 -= kChunk) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) buf[pad(j * 32 + lane)] = nxt[j];
+    if (c0 > 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) nxt[j] = yb[c0 - kChunk + j * 32 + lane];
     }
-    if (u == T - 1) {  // t + a > T - 1: the reference raises (masked by the caller); keep a finite value of the right magnitude
-      for (int tt = (T - a > 0 ? T - a : 0); tt < T; ++tt) {
-        if (tt == t) continue;
-        ob[tt] = v;
-        if (ab) ab[tt] = -1;
+    __syncwarp();
+    const int u0 = c0 + lane * 8;
+    A l8[8];
+    A tot = S::ident();
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      l8[i] = S::lift(buf[pad(lane * 8 + i)], u0 + i, rp);
+      if (u0 + i < T) tot = S::push(l8[i], tot);
+    }
+    A inc = tot;  // suffix over the lanes: this lane's samples and every later lane's
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const A other = shfl_down_acc(inc, d);
+      if (lane + d < 32) inc = S::comb(inc, other);
+    }
+    A run = shfl_down_acc(inc, 1);
+    run = lane == 31 ? carry : S::comb(run, carry);
+    carry = S::comb(shfl_acc(inc, 0), carry);
+    float last = 0.f;  // the value of the window [T - 1, T - 1]
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      const int u = u0 + i;
+      if (u < T) {
+        run = S::push(l8[i], run);
+        const float v = S::fin(run, (float)(T - u), rp);
+        buf[pad(lane * 8 + i)] = v;
+        if constexpr (SEM == SEM_CLASSIC) s_arg[warp][pad(lane * 8 + i)] = S::arg(run);
+        if (u == T - 1) last = v;
       }
     }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = j * 32 + lane, u = c0 + e, t = u - a;
+      if (u < T && t >= 0) {
+        ob[t] = buf[pad(e)];
+        if constexpr (SEM == SEM_CLASSIC) ab[t] = s_arg[warp][pad(e)];
+      }
+    }
+    if (c0 + kChunk >= T && a > 0) {
+      // t + a > T - 1: the reference raises (masked by the caller's start_slack); a finite value of the right magnitude
+      const float v = __shfl_sync(0xffffffffu, last, ((T - 1 - c0) >> 3));
+      for (int tt = (T - a > 0 ? T - a : 0) + lane; tt < T; tt += 32) {
+        ob[tt] = v;
+        if constexpr (SEM == SEM_CLASSIC) ab[tt] = -1;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -141,6 +220,7 @@ struct ScanAdj {  // agm, dgmsr
     return g != 0.f ? AD::out_coeff(g, o, n, rp, lost) : ident();
   }
   static __device__ A comb(A a, A b) { return A{{a.x[0] + b.x[0], a.x[1] + b.x[1]}}; }
+  static __device__ A push(A acc, A l) { return comb(acc, l); }
   static __device__ float apply(A w, float y, const RP& rp) { return AD::in_factor(w, y, 1.f, rp); }
 };
 template <int MODE>
@@ -155,6 +235,12 @@ struct ScanAdj<SEM_SMOOTH, MODE> {  // d out_t / d y_k = 2^(k (out_t - y_k)) (AN
     if (m == -f_inf()) return A{{m, 0.f}};
     return A{{m, a.x[1] * fast_ex2(a.x[0] - m) + b.x[1] * fast_ex2(b.x[0] - m)}};
   }
+  static __device__ A push(A acc, A l) {  // one coefficient behind an accumulator: one MUFU
+    if (l.x[0] == -f_inf()) return acc;
+    const float d = l.x[0] - acc.x[0];
+    const float ex = fast_ex2(-fabsf(d));
+    return A{{fmaxf(l.x[0], acc.x[0]), d <= 0.f ? fmaf(l.x[1], ex, acc.x[1]) : fmaf(acc.x[1], ex, l.x[1])}};
+  }
   static __device__ float apply(A w, float y, const RP& rp) {
     if (w.x[0] == -f_inf()) return 0.f;
     return w.x[1] * fast_ex2(w.x[0] + (MODE == MODE_AND ? -y : y) * rp.k);
@@ -167,45 +253,125 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) open_window_bwd(const flo
                                                                        long long B, int T, int a, RP rp) {
   using S = ScanAdj<SEM, MODE>;
   using A = typename S::A;
-  const long long b = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  __shared__ float s_g[kWarpsPerBlock][kBuf], s_o[kWarpsPerBlock][kBuf], s_y[kWarpsPerBlock][kBuf];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * kWarpsPerBlock + warp;
   if (b >= B) return;
-  const int lane = threadIdx.x & 31;
   const float* yb = y + b * T;
   const float* ob = out + b * T;
   const float* gb = grad_out + b * T;
   float* dy = grad_y + b * T;
-  const int nvalid = T - a;  // outputs t < nvalid exist
-  const int seg = (T + 31) / 32;
-  const int lo = lane * seg < T ? lane * seg : T, hi = lo + seg < T ? lo + seg : T;
-  auto coeff = [&](int t) { return t < nvalid ? S::coeff(gb[t], ob[t], (float)(T - t - a), rp) : S::ident(); };
-  A tot = S::ident();
-  for (int t = lo; t < hi; ++t) tot = S::comb(tot, coeff(t));
-  A inc = tot;
+  float *bg = s_g[warp], *bo = s_o[warp], *by = s_y[warp];
+  const int nvalid = T - a;  // outputs t < nvalid exist; output t serves the samples k >= t + a
+  for (int k = lane; k < a && k < T; k += 32) dy[k] = 0.f;  // samples before the first window
+  A carry = S::ident();  // every output before the current chunk
+  for (int c0 = 0; c0 < nvalid; c0 += kChunk) {
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const A other = shfl_up_acc(inc, d);
-    if (lane >= d) inc = S::comb(other, inc);
-  }
-  A run = shfl_up_acc(inc, 1);
-  if (lane == 0) run = S::ident();
-  // P[t] for the segment's t serves grad_y[t + a]; samples k < a belong to no window
-  for (int t = lo; t < hi; ++t) {
-    run = S::comb(run, coeff(t));
-    const int k = t + a;
-    if (k < T) dy[k] = S::apply(run, yb[k], rp);
-    if (t < a) dy[t] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const int e = j * 32 + lane, t = c0 + e;
+      const bool live = t < nvalid;
+      bg[pad(e)] = live ? gb[t] : 0.f;
+      bo[pad(e)] = live ? ob[t] : 0.f;
+      by[pad(e)] = live ? yb[t + a] : 0.f;
+    }
+    __syncwarp();
+    const int t0 = c0 + lane * 8;
+    A k8[8];
+    A tot = S::ident();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 + i;
+      k8[i] = t < nvalid ? S::coeff(bg[pad(lane * 8 + i)], bo[pad(lane * 8 + i)], (float)(T - t - a), rp) : S::ident();
+      tot = S::push(tot, k8[i]);
+    }
+    A inc = tot;  // prefix over the lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const A other = shfl_up_acc(inc, d);
+      if (lane >= d) inc = S::comb(other, inc);
+    }
+    A run = shfl_up_acc(inc, 1);
+    run = lane == 0 ? carry : S::comb(carry, run);
+    carry = S::comb(carry, shfl_acc(inc, 31));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      run = S::push(run, k8[i]);
+      bg[pad(lane * 8 + i)] = S::apply(run, by[pad(lane * 8 + i)], rp);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = j * 32 + lane, t = c0 + e;
+      if (t < nvalid) dy[t + a] = bg[pad(e)];
+    }
+    __syncwarp();
   }
 }
-// classic: every valid output routes its cotangent to the recorded arg-min / arg-max
-__global__ void open_window_bwd_classic(const int* __restrict__ arg, const float* __restrict__ grad_out, float* __restrict__ grad_y,
-                                        long long B, int T, int a) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * T) return;
-  const int t = (int)(i % T);
-  if (t >= T - a) return;
-  const float g = grad_out[i];
-  const int k = arg[i];
-  if (g != 0.f && k >= 0) atomicAdd(&grad_y[(i / T) * T + k], g);
+// classic: every output routes its cotangent to the recorded arg-min / arg-max.  The arg of a suffix window is
+// non-decreasing in t, so the outputs that share a target are one RUN of consecutive t: a segmented prefix sum of the
+// cotangents, written once at the end of each run (no atomics; grad_y is zeroed first).
+struct Seg {
+  int f;    // a run starts inside
+  float v;  // sum since the last start (the whole range when none)
+};
+__device__ __forceinline__ Seg seg_comb(Seg a, Seg b) { return Seg{a.f | b.f, b.f ? b.v : a.v + b.v}; }
+
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) open_window_bwd_classic(const int* __restrict__ arg, const float* __restrict__ grad_out,
+                                                                               float* __restrict__ grad_y, long long B, int T, int a) {
+  __shared__ float s_g[kWarpsPerBlock][kBuf];
+  __shared__ int s_a[kWarpsPerBlock][kBuf + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * kWarpsPerBlock + warp;
+  if (b >= B) return;
+  const int* ab = arg + b * T;
+  const float* gb = grad_out + b * T;
+  float* dy = grad_y + b * T;
+  float* bg = s_g[warp];
+  int* ba = s_a[warp];
+  const int nvalid = T - a;
+  float carry = 0.f;  // the open run's sum over the chunks before this one
+  int prev = -1;      // arg of the sample before the chunk
+  for (int c0 = 0; c0 < nvalid; c0 += kChunk) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = j * 32 + lane, t = c0 + e;
+      bg[pad(e)] = t < nvalid ? gb[t] : 0.f;
+      ba[pad(e)] = t < nvalid ? ab[t] : -2;
+    }
+    const int after = c0 + kChunk < nvalid ? ab[c0 + kChunk] : -2;  // (uniform load)
+    __syncwarp();
+    int k[10];  // this lane's 8 targets and the neighbours on either side
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k[i + 1] = ba[pad(lane * 8 + i)];
+    k[0] = lane == 0 ? prev : ba[pad(lane * 8 - 1)];
+    k[9] = lane == 31 ? after : ba[pad(lane * 8 + 8)];
+    float g8[8];
+    Seg tot{0, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      g8[i] = bg[pad(lane * 8 + i)];
+      tot = seg_comb(tot, Seg{k[i + 1] != k[i], g8[i]});
+    }
+    Seg inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      Seg other{__shfl_up_sync(0xffffffffu, inc.f, d), __shfl_up_sync(0xffffffffu, inc.v, d)};
+      if (lane >= d) inc = seg_comb(other, inc);
+    }
+    Seg ex{__shfl_up_sync(0xffffffffu, inc.f, 1), __shfl_up_sync(0xffffffffu, inc.v, 1)};
+    if (lane == 0) ex = Seg{0, 0.f};
+    float run = ex.f ? ex.v : carry + ex.v;
+    const Seg whole{__shfl_sync(0xffffffffu, inc.f, 31), __shfl_sync(0xffffffffu, inc.v, 31)};
+    carry = whole.f ? whole.v : carry + whole.v;
+    prev = __shfl_sync(0xffffffffu, k[8], 31);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (k[i + 1] != k[i]) run = 0.f;
+      run += g8[i];
+      if (k[i + 1] >= 0 && k[i + 2] != k[i + 1]) dy[k[i + 1]] = run;  // the run ends here
+    }
+    __syncwarp();
+  }
 }
 
 thread_local char* g_err = nullptr;  // the caller's message buffer (pystl_b200.cu: pystl_b200_last_error)
@@ -310,8 +476,8 @@ int open_window_backward(int32_t semantics, int32_t mode, int32_t a, float tempe
     if (!arg) return scan_fail(PYSTL_E_INVALID, "classical needs the arg buffer");
     cudaError_t e = cudaMemsetAsync(grad_y, 0, (size_t)B * (size_t)T * sizeof(float), st);
     if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-    const long long n = (long long)B * T;
-    open_window_bwd_classic<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(arg, grad_out, grad_y, (long long)B, (int)T, (int)a);
+    open_window_bwd_classic<<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), 32 * kWarpsPerBlock, 0, st>>>(
+        arg, grad_out, grad_y, (long long)B, (int)T, (int)a);
   } else {
     const RP rp = make_rp(temperature, eps, p);
     const unsigned grid = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
