@@ -191,6 +191,18 @@ int pystl_b200_open_window_backward(int32_t semantics, int32_t mode, int32_t a, 
                                     const float* y, const float* out, const int32_t* arg, const float* grad_out,
                                     int64_t B, int64_t T, float* grad_y, void* stream);
 
+/* Classical Until without an interval end on traces longer than one tile (ABI 2): out[b, t] = W(t + a),
+ *   W(u) = max_{t' >= u} min( r[t'], min_{u <= t'' <= t'} l[t''] )            (classic.py:59-80 with Interval.end None)
+ * for the value traces l[B, T], r[B, T] of the two operands -- a suffix scan of clamp compositions.  The host wraps it as
+ * U[a, inf) = min( G[0, a] l, W(t + a) ) (the decomposition of pystl_b200/csrc/lower.cpp).  key[B, T] records where each
+ * value came from (2 * sample + 1 for an r, + 0 for an l); backward routes the cotangents there (grad_l, grad_r fully
+ * overwritten).  The other semantics' Until is O(T^2) per trace without an end and stays inside one tile
+ * (PYSTL_E_UNSUPPORTED here). */
+int pystl_b200_open_until_forward(int32_t semantics, int32_t a, const float* l, const float* r, int64_t B, int64_t T,
+                                  float* out, int32_t* key, void* stream);
+int pystl_b200_open_until_backward(int32_t semantics, int32_t a, const int32_t* key, const float* grad_out, int64_t B,
+                                   int64_t T, float* grad_l, float* grad_r, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,16 @@ class OpenLeaf:
     name: str = "open-ended window"
 
 
+@dataclass(frozen=True)
+class OpenUntilLeaf:
+    """``W(t + start)``: the classical Until of ``left, right`` without an end, computed outside the formula kernel."""
+
+    left: Any
+    right: Any
+    start: int
+    name: str = "open-ended until"
+
+
 def start_slack(node: Any) -> int:
     """Samples at the end of the trace where ``node`` raises (empty window); mirrors lower.cpp."""
     kind = type(node).__name__
@@ -309,10 +319,41 @@ def compile_formula(
             n.a, n.b = interval_of(node)
             n.w_off, n.w_len = add_weights(node.weights)
             has_open[0] |= n.b < 0
+        elif kind == "Until" and node.interval.end is None and open_leaf:
+            # U[a, inf) = min( G[0, a] left, W(t + a) ) with W the clamp-composition suffix scan (lower.cpp does the same in-tile)
+            a, _ = interval_of(node)
+            if semantics != "classical":
+                raise NotImplementedError(
+                    f"Until without an interval end on a trace longer than one tile: classical semantics only ({semantics}: O(T^2) per trace)"
+                )
+            leaf_index[key] = len(leaves)
+            leaves.append(OpenUntilLeaf(node.left, node.right, a))
+            pkey = (((n_channels + leaf_index[key], 1.0),), 0.0)
+            pred_index[pkey] = len(preds)
+            preds.append(pkey)
+            pred_slack[pred_index[pkey]] = a if max(start_slack(node.left), start_slack(node.right)) == 0 else -1
+            if a == 0:
+                n.kind = capi.NODE_PRED
+                n.pred = pred_index[pkey]
+            else:
+                w = capi.Node()
+                w.kind, w.pred, w.n_children, w.child_off = capi.NODE_PRED, pred_index[pkey], 0, len(children)
+                w.w_off, w.w_len, w.w2_off, w.w2_len, w.wp0, w.wp1 = -1, 0, -1, 0, 1.0, 1.0
+                nodes.append(w)
+                w_idx = len(nodes) - 1
+                left_idx = visit(node.left)
+                g = capi.Node()
+                g.kind, g.pred, g.n_children, g.child_off, g.a, g.b = capi.NODE_ALWAYS, -1, 1, len(children), 0, a
+                g.w_off, g.w_len, g.w2_off, g.w2_len, g.wp0, g.wp1 = -1, 0, -1, 0, 1.0, 1.0
+                children.append(left_idx)
+                nodes.append(g)
+                n.kind = capi.NODE_AND
+                kids = [w_idx, len(nodes) - 1]
         elif kind == "Until":
             n.kind = capi.NODE_UNTIL
             kids = [visit(node.left), visit(node.right)]
             n.a, n.b = interval_of(node)
+            has_open[0] |= n.b < 0
             n.w_off, n.w_len = add_weights(node.weights_left)
             n.w2_off, n.w2_len = add_weights(node.weights_right)
             wp = tuple(float(x) for x in node.weights_pair)
@@ -387,6 +428,14 @@ def leaf_values(cf: CompiledFormula, sig, sem=None):
     B, T, _ = sig.shape
     cols = []
     for pred in cf.leaf_preds:
+        if isinstance(pred, OpenUntilLeaf):
+            from . import ops
+
+            if sem is None:
+                raise RuntimeError("an open-ended until leaf needs the semantics object that compiled it")
+            yl, yr = sem.robustness_trace(pred.left, sig), sem.robustness_trace(pred.right, sig)
+            cols.append(ops.open_until(yl.contiguous(), yr.contiguous(), cf.struct.semantics, pred.start))
+            continue
         if isinstance(pred, OpenLeaf):
             from . import ops
 

@@ -404,7 +404,19 @@ int open_window_forward(int32_t semantics, int32_t mode, int32_t a, float temper
 int open_window_backward(int32_t semantics, int32_t mode, int32_t a, float temperature, float eps, int32_t p, const float* y,
                          const float* out, const int32_t* arg, const float* grad_out, int64_t B, int64_t T, float* grad_y,
                          void* stream, char* err, size_t err_cap);
+int open_until_forward(int32_t semantics, int32_t a, const float* l, const float* r, int64_t B, int64_t T, float* out, int32_t* key,
+                       void* stream, char* err, size_t err_cap);
+int open_until_backward(int32_t semantics, int32_t a, const int32_t* key, const float* grad_out, int64_t B, int64_t T, float* grad_l,
+                        float* grad_r, void* stream, char* err, size_t err_cap);
 }  // namespace pystl
+extern "C" int pystl_b200_open_until_forward(int32_t semantics, int32_t a, const float* l, const float* r, int64_t B, int64_t T,
+                                             float* out, int32_t* key, void* stream) {
+  return pystl::open_until_forward(semantics, a, l, r, B, T, out, key, stream, g_err, sizeof(g_err));
+}
+extern "C" int pystl_b200_open_until_backward(int32_t semantics, int32_t a, const int32_t* key, const float* grad_out, int64_t B,
+                                              int64_t T, float* grad_l, float* grad_r, void* stream) {
+  return pystl::open_until_backward(semantics, a, key, grad_out, B, T, grad_l, grad_r, stream, g_err, sizeof(g_err));
+}
 extern "C" int pystl_b200_open_window_forward(int32_t semantics, int32_t mode, int32_t a, float temperature, float eps, int32_t p,
                                               const float* y, int64_t B, int64_t T, float* out, int32_t* arg, void* stream) {
   return pystl::open_window_forward(semantics, mode, a, temperature, eps, p, y, B, T, out, arg, stream, g_err, sizeof(g_err));

@@ -208,6 +208,84 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) open_window_fwd(const flo
   }
 }
 
+// ---------------------------------------------------------------- classical Until without an end
+// W(u) = min(l_u, max(r_u, W(u + 1))), W(T) = -inf (classic.py:59-80 with Interval.end None): the composition of the clamps
+// f_u(w) = min(l_u, max(r_u, w)) is a clamp again (tile_eval.h: ClampOp, the operator of the in-kernel clamp scan), so the
+// unbounded Until is the same chunked suffix scan over (A, src A, B, src B) quadruples.  out[t] = W(t + a); the host adds
+// G[0, a] l around it (lower.cpp: U[a, inf) = min(G[0,a] l, W(t + a))).  key[t] = 2 * sample + (1 if the value is an r).
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) open_until_fwd_classic(const float* __restrict__ l, const float* __restrict__ r,
+                                                                              float* __restrict__ out, int* __restrict__ key, long long B,
+                                                                              int T, int a) {
+  using OP = ClampOp<SEM_CLASSIC_SRC>;
+  using A = OP::A;
+  __shared__ float s_l[kWarpsPerBlock][kBuf], s_r[kWarpsPerBlock][kBuf];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * kWarpsPerBlock + warp;
+  if (b >= B) return;
+  const float* lb = l + b * T;
+  const float* rb = r + b * T;
+  float* ob = out + b * T;
+  int* kb = key + b * T;
+  float *bl = s_l[warp], *br = s_r[warp];
+  A carry = OP::ident();
+  for (int c0 = ((T - 1) / kChunk) * kChunk; c0 >= 0; c0 -= kChunk) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = j * 32 + lane, u = c0 + e;
+      bl[pad(e)] = u < T ? lb[u] : 0.f;
+      br[pad(e)] = u < T ? rb[u] : 0.f;
+    }
+    __syncwarp();
+    const int u0 = c0 + lane * 8;
+    A x8[8];
+    A tot = OP::ident();
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      const int u = u0 + i;
+      x8[i] = u < T ? OP::make(Vec<2>{{bl[pad(lane * 8 + i)], i2f(2 * u)}}, Vec<2>{{br[pad(lane * 8 + i)], i2f(2 * u + 1)}}) : OP::ident();
+      tot = OP::comb(x8[i], tot);
+    }
+    A inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const A other = shfl_down_acc(inc, d);
+      if (lane + d < 32) inc = OP::comb(inc, other);
+    }
+    A run = shfl_down_acc(inc, 1);
+    run = lane == 31 ? carry : OP::comb(run, carry);
+    carry = OP::comb(shfl_acc(inc, 0), carry);
+    float last = 0.f;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      const int u = u0 + i;
+      if (u < T) {
+        run = OP::comb(x8[i], run);
+        const Vec<2> v = OP::value(run);
+        bl[pad(lane * 8 + i)] = v.x[0];
+        br[pad(lane * 8 + i)] = v.x[1];
+        if (u == T - 1) last = v.x[0];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = j * 32 + lane, u = c0 + e, t = u - a;
+      if (u < T && t >= 0) {
+        ob[t] = bl[pad(e)];
+        kb[t] = f2i(br[pad(e)]);
+      }
+    }
+    if (c0 + kChunk >= T && a > 0) {
+      const float v = __shfl_sync(0xffffffffu, last, ((T - 1 - c0) >> 3));
+      for (int tt = (T - a > 0 ? T - a : 0) + lane; tt < T; tt += 32) {
+        ob[tt] = v;
+        kb[tt] = -1;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------- backward
 // grad_y[k] = in_factor( sum_{t <= k - a, t valid} out_coeff(g_t, out_t, T - t - a), y_k ): a prefix scan of coefficients
 template <int SEM, int MODE>
@@ -316,16 +394,22 @@ struct Seg {
 };
 __device__ __forceinline__ Seg seg_comb(Seg a, Seg b) { return Seg{a.f | b.f, b.f ? b.v : a.v + b.v}; }
 
+template <bool TWO>  // TWO: the targets are keys 2 * sample + side of an Until (side 0: grad_y, 1: grad_r)
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) open_window_bwd_classic(const int* __restrict__ arg, const float* __restrict__ grad_out,
-                                                                               float* __restrict__ grad_y, long long B, int T, int a) {
+                                                                               float* __restrict__ grad_y, float* __restrict__ grad_r,
+                                                                               long long B, int T, int a) {
   __shared__ float s_g[kWarpsPerBlock][kBuf];
   __shared__ int s_a[kWarpsPerBlock][kBuf + 2];
+  // TWO: the runs of an Until are short (the source is often the sample itself), one 4-byte store per sample; targets inside
+  // [c0 + a, c0 + a + 256) are staged here and leave as coalesced rows (zeros are not stored: grad is zero-filled already)
+  __shared__ float s_t[TWO ? 2 : 1][TWO ? kWarpsPerBlock : 1][TWO ? kBuf : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = (long long)blockIdx.x * kWarpsPerBlock + warp;
   if (b >= B) return;
   const int* ab = arg + b * T;
   const float* gb = grad_out + b * T;
   float* dy = grad_y + b * T;
+  float* dr = TWO ? grad_r + b * T : nullptr;
   float* bg = s_g[warp];
   int* ba = s_a[warp];
   const int nvalid = T - a;
@@ -337,6 +421,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) open_window_bwd_classic(c
       const int e = j * 32 + lane, t = c0 + e;
       bg[pad(e)] = t < nvalid ? gb[t] : 0.f;
       ba[pad(e)] = t < nvalid ? ab[t] : -2;
+      if constexpr (TWO) s_t[0][warp][pad(e)] = s_t[1][warp][pad(e)] = 0.f;
     }
     const int after = c0 + kChunk < nvalid ? ab[c0 + kChunk] : -2;  // (uniform load)
     __syncwarp();
@@ -368,9 +453,27 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) open_window_bwd_classic(c
     for (int i = 0; i < 8; ++i) {
       if (k[i + 1] != k[i]) run = 0.f;
       run += g8[i];
-      if (k[i + 1] >= 0 && k[i + 2] != k[i + 1]) dy[k[i + 1]] = run;  // the run ends here
+      if (k[i + 1] >= 0 && k[i + 2] != k[i + 1]) {  // the run ends here
+        if constexpr (TWO) {
+          const int kk = k[i + 1] >> 1, side = k[i + 1] & 1, rel = kk - (c0 + a);
+          if (rel < kChunk) s_t[side][warp][pad(rel)] = run;  // (rel >= 0: a source is never before its output's t + a)
+          else (side ? dr : dy)[kk] = run;
+        } else {
+          dy[k[i + 1]] = run;
+        }
+      }
     }
     __syncwarp();
+    if constexpr (TWO) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = j * 32 + lane;
+        const float v0 = s_t[0][warp][pad(e)], v1 = s_t[1][warp][pad(e)];
+        if (v0 != 0.f) dy[c0 + a + e] = v0;
+        if (v1 != 0.f) dr[c0 + a + e] = v1;
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -476,8 +579,8 @@ int open_window_backward(int32_t semantics, int32_t mode, int32_t a, float tempe
     if (!arg) return scan_fail(PYSTL_E_INVALID, "classical needs the arg buffer");
     cudaError_t e = cudaMemsetAsync(grad_y, 0, (size_t)B * (size_t)T * sizeof(float), st);
     if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-    open_window_bwd_classic<<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), 32 * kWarpsPerBlock, 0, st>>>(
-        arg, grad_out, grad_y, (long long)B, (int)T, (int)a);
+    open_window_bwd_classic<false><<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), 32 * kWarpsPerBlock, 0, st>>>(
+        arg, grad_out, grad_y, nullptr, (long long)B, (int)T, (int)a);
   } else {
     const RP rp = make_rp(temperature, eps, p);
     const unsigned grid = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
@@ -494,6 +597,54 @@ int open_window_backward(int32_t semantics, int32_t mode, int32_t a, float tempe
   }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "open_window_bwd: %s", cudaGetErrorString(e));
+  return PYSTL_OK;
+}
+
+int open_until_forward(int32_t semantics, int32_t a, const float* l, const float* r, int64_t B, int64_t T, float* out, int32_t* key,
+                       void* stream, char* err, size_t err_cap) {
+  g_err = err;
+  g_err_cap = err_cap;
+  if (semantics != SEM_CLASSIC)
+    return scan_fail(PYSTL_E_UNSUPPORTED, "an Until without an interval end beyond one tile: classical semantics only (the others are O(T^2))");
+  if (a < 0) return scan_fail(PYSTL_E_INVALID, "Interval start must be >= 0.");
+  if (B < 0 || T < 0 || T >= (1ll << 30)) return scan_fail(PYSTL_E_INVALID, "bad shape");
+  if (B == 0 || T == 0) return PYSTL_OK;
+  if (!l || !r || !out || !key) return scan_fail(PYSTL_E_INVALID, "null buffer");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return scan_fail(PYSTL_E_CUDA, "no CUDA device: the b200 backend has no CPU path");
+  }
+  open_until_fwd_classic<<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
+      l, r, out, key, (long long)B, (int)T, (int)a);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "open_until_fwd: %s", cudaGetErrorString(e));
+  return PYSTL_OK;
+}
+
+int open_until_backward(int32_t semantics, int32_t a, const int32_t* key, const float* grad_out, int64_t B, int64_t T, float* grad_l,
+                        float* grad_r, void* stream, char* err, size_t err_cap) {
+  g_err = err;
+  g_err_cap = err_cap;
+  if (semantics != SEM_CLASSIC)
+    return scan_fail(PYSTL_E_UNSUPPORTED, "an Until without an interval end beyond one tile: classical semantics only (the others are O(T^2))");
+  if (a < 0) return scan_fail(PYSTL_E_INVALID, "Interval start must be >= 0.");
+  if (B < 0 || T < 0 || T >= (1ll << 30)) return scan_fail(PYSTL_E_INVALID, "bad shape");
+  if (B == 0 || T == 0) return PYSTL_OK;
+  if (!key || !grad_out || !grad_l || !grad_r) return scan_fail(PYSTL_E_INVALID, "null buffer");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return scan_fail(PYSTL_E_CUDA, "no CUDA device: the b200 backend has no CPU path");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(grad_l, 0, (size_t)B * (size_t)T * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(grad_r, 0, (size_t)B * (size_t)T * sizeof(float), st);
+  if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  open_window_bwd_classic<true><<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), 32 * kWarpsPerBlock, 0, st>>>(
+      key, grad_out, grad_l, grad_r, (long long)B, (int)T, (int)a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "open_until_bwd: %s", cudaGetErrorString(e));
   return PYSTL_OK;
 }
 

@@ -279,3 +279,79 @@ class OpenWindow(torch.autograd.Function):
 def open_window(y: torch.Tensor, semantics: int, mode: int, start: int, temperature: float, eps: float, p: int) -> torch.Tensor:
     """Differentiable ``G[start, inf)`` (mode 0) / ``F[start, inf)`` (mode 1) of the value trace ``y[B, T]``."""
     return OpenWindow.apply(y, int(semantics), int(mode), int(start), float(temperature), float(eps), int(p))[0]
+
+
+# ---- classical Until without an end beyond one tile: clamp-composition suffix scan (csrc/scan.cu) ------------------
+_lib.define("open_until_fwd(Tensor left, Tensor right, int semantics, int start) -> (Tensor, Tensor)")
+_lib.define("open_until_grad(Tensor key, Tensor grad_out, int semantics, int start) -> (Tensor, Tensor)")
+
+
+def _open_until_fwd_cuda(left, right, semantics, start):
+    _check_trace(left)
+    _check_trace(right)
+    if left.shape != right.shape:
+        raise ValueError("UNTIL traces must have the same shape")
+    left, right = left.contiguous(), right.contiguous()
+    B, T = left.shape
+    out = torch.empty_like(left)
+    key = torch.empty((B, T), dtype=torch.int32, device=left.device)
+    with torch.cuda.device(left.device):
+        rc = capi.lib().pystl_b200_open_until_forward(int(semantics), int(start), left.data_ptr(), right.data_ptr(), B, T,
+                                                      out.data_ptr(), key.data_ptr(), torch.cuda.current_stream(left.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return out, key
+
+
+def _open_until_grad_cuda(key, grad_out, semantics, start):
+    g = grad_out.to(dtype=torch.float32).contiguous()
+    _check_trace(g)
+    key = key.contiguous()
+    B, T = g.shape
+    gl, gr = torch.empty_like(g), torch.empty_like(g)
+    with torch.cuda.device(g.device):
+        rc = capi.lib().pystl_b200_open_until_backward(int(semantics), int(start), key.data_ptr(), g.data_ptr(), B, T,
+                                                       gl.data_ptr(), gr.data_ptr(), torch.cuda.current_stream(g.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return gl, gr
+
+
+_lib.impl("open_until_fwd", _open_until_fwd_cuda, "CUDA")
+_lib.impl("open_until_grad", _open_until_grad_cuda, "CUDA")
+open_until_fwd = torch.ops.pystl_b200.open_until_fwd
+open_until_grad = torch.ops.pystl_b200.open_until_grad
+
+
+@torch.library.register_fake("pystl_b200::open_until_fwd")
+def _(left, right, semantics, start):
+    return torch.empty_like(left), left.new_empty(tuple(left.shape), dtype=torch.int32)
+
+
+@torch.library.register_fake("pystl_b200::open_until_grad")
+def _(key, grad_out, semantics, start):
+    return torch.empty_like(grad_out), torch.empty_like(grad_out)
+
+
+class OpenUntil(torch.autograd.Function):
+    """``out[b, t] = W(t + start)``, the unbounded classical Until of two value traces; cotangents go to the recorded sources."""
+
+    @staticmethod
+    def forward(left, right, semantics, start):
+        return open_until_fwd(left, right, semantics, start)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        _, _, ctx.semantics, ctx.start = inputs
+        out, key = output
+        ctx.mark_non_differentiable(key)
+        ctx.save_for_backward(key)
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_key):
+        (key,) = ctx.saved_tensors
+        gl, gr = open_until_grad(key, grad_out, ctx.semantics, ctx.start)
+        return gl, gr, None, None
+
+
+def open_until(left: torch.Tensor, right: torch.Tensor, semantics: int, start: int) -> torch.Tensor:
+    """Differentiable unbounded Until of the value traces ``left, right [B, T]`` read at ``t + start`` (classical semantics)."""
+    return OpenUntil.apply(left, right, int(semantics), int(start))[0]

@@ -16,8 +16,8 @@ import torch
 
 from oracle import dense
 from pystl_b200 import create_semantics
-from pystl_b200.compiler import OpenLeaf
-from pystl_b200.formula import Always, And, Eventually, Interval, Not, Or, affine_predicate
+from pystl_b200.compiler import OpenLeaf, OpenUntilLeaf
+from pystl_b200.formula import Always, And, Eventually, Interval, Not, Or, Until, affine_predicate
 
 pytestmark = pytest.mark.gpu
 
@@ -190,6 +190,95 @@ def test_long_trace_properties(sem, kw):
     assert torch.allclose(grad, xs.grad, rtol=1e-4, atol=1e-6 * float(xs.grad.abs().max()) + 1e-12)
 
 
+# ---------------------------------------------------------------------------- classical Until without an end
+def preds32():
+    # coefficients that are float32 numbers: the classical kernels are bit-exact against float32(float64 reference)
+    return affine_predicate("x", {0: 1.0}, 0.125), affine_predicate("y", {1: -1.0, 0: 0.25}, 0.375)
+
+
+def until_formulas():
+    x, y = preds32()
+    return {
+        "U_open": Until(x, y, Interval(0, None)),
+        "U_open_a": Until(x, y, Interval(6, None)),
+        "U_nested_operands": Until(Or(x, Not(y)), Eventually(y, Interval(0, 3)), Interval(4, None)),
+        "U_mixed": And(Until(x, y, Interval(2, None)), Always(Not(y), Interval(1, None))),
+        "U_of_U": Until(x, Until(y, x, Interval(0, None)), Interval(1, None)),
+    }
+
+
+@pytest.mark.parametrize("name", list(until_formulas()))
+def test_open_until_against_the_oracle(name):
+    T = 300
+    phi = until_formulas()[name]
+    sig = signal(3, T, 17)
+    s = create_semantics("classical", backend="b200")
+    s.force_open_leaf = True
+    x = torch.tensor(sig, device="cuda", requires_grad=True)
+    cf = s._checked_compile(phi, x.detach())
+    assert any(isinstance(p, OpenUntilLeaf) for p in cf.leaf_preds)
+    got = s.robustness_trace(phi, x)
+    x64 = torch.tensor(sig, dtype=torch.float64, requires_grad=True)
+    want = dense.robustness_trace(phi, x64, dense.make("classical"))
+    ok = torch.isfinite(want)
+    assert torch.equal(torch.isfinite(got.detach().cpu()), ok)
+    assert torch.equal(got.detach().cpu()[ok], want.detach()[ok].to(torch.float32))  # classical: bit-exact
+    g = torch.tensor(np.random.default_rng(3).uniform(0.25, 1.0, size=tuple(want.shape)))
+    (torch.nan_to_num(got) * g.to("cuda", torch.float32)).sum().backward()
+    (torch.nan_to_num(want) * g).sum().backward()
+    assert torch.allclose(x.grad.cpu().double(), x64.grad, rtol=1e-5, atol=1e-5)
+    mean, grad = s.mean_robustness_and_grad(phi, torch.tensor(sig, device="cuda"))
+    x2 = torch.tensor(sig, dtype=torch.float64, requires_grad=True)
+    w2 = dense.robustness_trace(phi, x2, dense.make("classical"))
+    m2 = w2[torch.isfinite(w2)].mean()
+    m2.backward()
+    assert abs(float(mean) - float(m2.detach())) < 1e-5 * (1 + abs(float(m2.detach())))
+    assert torch.allclose(grad.cpu().double(), x2.grad, rtol=1e-5, atol=1e-7)
+
+
+def test_open_until_equals_the_in_kernel_path_and_scales():
+    sig = torch.tensor(signal(4, 2048, 5), device="cuda")
+    for name, phi in until_formulas().items():
+        a = create_semantics("classical", backend="b200")
+        b = create_semantics("classical", backend="b200")
+        b.force_open_leaf = True
+        xa, xb = sig.clone().requires_grad_(True), sig.clone().requires_grad_(True)
+        ra, rb = a.robustness_trace(phi, xa), b.robustness_trace(phi, xb)
+        ok = torch.isfinite(ra)
+        assert torch.equal(ok, torch.isfinite(rb)) and torch.equal(ra[ok], rb[ok]), name
+        torch.nan_to_num(ra).sum().backward()
+        torch.nan_to_num(rb).sum().backward()
+        assert torch.allclose(xa.grad, xb.grad, rtol=1e-5, atol=1e-4), (name, float((xa.grad - xb.grad).abs().max()))
+    # T = 20000: the recurrence W(u) = min(l_u, max(r_u, W(u + 1))) in float64, one step per sample
+    B, T, a0 = 3, 20000, 9
+    x, y = preds32()
+    phi = Until(x, y, Interval(a0, None))
+    sg = signal(B, T, 23)
+    s = create_semantics("classical", backend="b200")
+    xs = torch.tensor(sg, device="cuda", requires_grad=True)
+    got = s.robustness_trace(phi, xs)
+    assert s.plan(phi, T, 2)["start_slack"] == a0
+    x64 = torch.tensor(sg, dtype=torch.float64, requires_grad=True)
+    l = x64[..., 0] + 0.125
+    r = -x64[..., 1] + 0.25 * x64[..., 0] + 0.375
+    w = [None] * T
+    run = torch.full((B,), float("-inf"), dtype=torch.float64)
+    for u in range(T - 1, -1, -1):
+        run = torch.minimum(l[:, u], torch.maximum(r[:, u], run))
+        w[u] = run
+    W = torch.stack(w, 1)
+    gl = l.unfold(1, a0 + 1, 1).amin(-1)  # G[0, a] l
+    want = torch.full((B, T), float("nan"), dtype=torch.float64)
+    want[:, : T - a0] = torch.minimum(gl[:, : T - a0], W[:, a0:])
+    ok = torch.isfinite(want)
+    assert torch.equal(torch.isfinite(got.detach().cpu()), ok)
+    assert torch.equal(got.detach().cpu()[ok], want.detach()[ok].to(torch.float32))
+    gsel = torch.tensor(np.random.default_rng(2).uniform(0.25, 1.0, size=(B, T)))
+    (torch.nan_to_num(got) * gsel.to("cuda", torch.float32)).sum().backward()
+    (torch.nan_to_num(want) * gsel).sum().backward()
+    assert torch.allclose(xs.grad.cpu().double(), x64.grad, rtol=1e-4, atol=1e-3)
+
+
 def test_a_window_that_always_raises_is_nan_everywhere():
     # an operand that is itself undefined near the horizon makes the open-ended window raise at every t (api.py:218-221)
     x, _ = preds()
@@ -210,3 +299,5 @@ def test_unsupported_cases_are_loud():
         create_semantics("cumulative", backend="b200").robustness_trace(Always(x, Interval(0, None)), sig)
     with pytest.raises(NotImplementedError):
         create_semantics("agm", backend="b200").robustness_trace(Always(x, Interval(0, None), weights=[1.0] * 20000), sig)
+    with pytest.raises(NotImplementedError):  # the non-classical Until without an end is O(T^2) per trace: one tile only
+        create_semantics("smooth", backend="b200").robustness_trace(Until(x, y, Interval(0, None)), sig)

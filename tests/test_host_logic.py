@@ -156,8 +156,19 @@ def test_open_ended_windows_beyond_one_tile_become_leaf_channels():
         cum.plan(phi, 20000, 2)
     with pytest.raises(NotImplementedError):  # window weights are per position of the clipped window
         create_semantics("agm", backend="b200").plan(Always(x, Interval(0, None), weights=[1.0] * 20000), 20000, 2)
-    with pytest.raises(NotImplementedError):  # an unbounded Until still needs one tile
-        create_semantics("classical", backend="b200").plan(Until(x, y, Interval(0, None)), 20000, 2)
+    # Until without an end: classical only (a clamp-composition scan); U[a, inf) = min(G[0, a] left, W(t + a))
+    from pystl_b200.compiler import OpenUntilLeaf
+
+    cl = create_semantics("classical", backend="b200")
+    u = Until(x, y, Interval(4, None))
+    cfu = cl.compile(u, 2, open_leaf=True)
+    (leaf,) = cfu.leaf_preds
+    assert isinstance(leaf, OpenUntilLeaf) and leaf.left is x and leaf.right is y and leaf.start == 4
+    kinds = [cfu.nodes[i].kind for i in range(cfu.struct.n_nodes)]
+    assert kinds == [capi.NODE_PRED, capi.NODE_PRED, capi.NODE_ALWAYS, capi.NODE_AND]
+    assert cl.plan(u, 20000, 2)["start_slack"] == 4 and cl.plan(u, 2048, 2)["start_slack"] == 4
+    with pytest.raises(NotImplementedError):
+        create_semantics("agm", backend="b200").plan(u, 20000, 2)
 
 
 @pytest.mark.parametrize("cfg", sorted(BASELINE_SPECS))
@@ -187,8 +198,9 @@ def test_plan_validity_rules_follow_the_reference():
     # an open interval keeps the trace in one tile; beyond that the window is a scanned leaf channel (next test)
     assert sem.plan(x.always((0, None)), 100000, 1)["n_tiles"] > 1
     assert sem.plan(x.always((0, None)), 4000, 1)["n_tiles"] == 1
-    with pytest.raises(NotImplementedError):  # an unbounded Until on a trace longer than any tile
-        sem.plan(x.until(x, (0, None)), 100000, 1)
+    assert sem.plan(x.until(x, (0, None)), 100000, 1)["n_tiles"] > 1  # classical: a scanned leaf channel as well
+    with pytest.raises(NotImplementedError):  # a non-classical unbounded Until on a trace longer than any tile
+        create_semantics("smooth", backend="b200").plan(x.until(x, (0, None)), 100000, 1)
 
 
 def test_loud_failure_without_the_library(monkeypatch, tmp_path):

@@ -56,6 +56,25 @@ def main() -> None:
                              fwd_ms=round(f_ms, 4), fwd_gbs=round(fb / f_ms / 1e6, 1), bwd_ms=round(b_ms, 4), bwd_gbs=round(bb / b_ms / 1e6, 1),
                              finite=bool(torch.isfinite(gy).all())))
             print(json.dumps(rows[-1]), flush=True)
+    # classical Until without an end: reads l, r, writes out, key (16 B / sample); backward reads key, grad_out, zero-fills grad_l, grad_r
+    r2 = torch.randn(B, T, device="cuda") * 0.5
+    out, key = ops.open_until_fwd(y, r2, capi.SEM_CLASSIC, args.start)
+    for _ in range(2):
+        ops.open_until_fwd(y, r2, capi.SEM_CLASSIC, args.start)
+        ops.open_until_grad(key, g, capi.SEM_CLASSIC, args.start)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for _ in range(args.iters):
+        ops.open_until_fwd(y, r2, capi.SEM_CLASSIC, args.start)
+    ev[1].record()
+    for _ in range(args.iters):
+        ops.open_until_grad(key, g, capi.SEM_CLASSIC, args.start)
+    ev[2].record()
+    torch.cuda.synchronize()
+    f_ms, b_ms = ev[0].elapsed_time(ev[1]) / args.iters, ev[1].elapsed_time(ev[2]) / args.iters
+    print(json.dumps(dict(semantics="classical", mode="until", traces=B, horizon=T, fwd_ms=round(f_ms, 4),
+                          fwd_gbs=round(16 * B * T / f_ms / 1e6, 1), bwd_ms=round(b_ms, 4), bwd_gbs=round(16 * B * T / b_ms / 1e6, 1))), flush=True)
 
 
 if __name__ == "__main__":
