@@ -279,6 +279,63 @@ def test_open_until_equals_the_in_kernel_path_and_scales():
     assert torch.allclose(xs.grad.cpu().double(), x64.grad, rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("sem,kw", [SEMS[0], SEMS[2], SEMS[3], SEMS[4]], ids=["classical", "smooth0.05", "agm", "dgmsr1"])
+def test_chunk_boundaries_and_degenerate_shapes(sem, kw):
+    """The scan kernels walk 256-sample chunks, 8 samples per lane: every trace length around those boundaries, starts
+    up to and past the horizon (a >= T: the window is empty at every t, the reference raises, api.py:218-221).  Called
+    through the torch ops on raw value traces (no formula kernel, nothing to compile)."""
+    from pystl_b200 import capi, ops
+
+    sem_id = {"classical": capi.SEM_CLASSIC, "smooth": capi.SEM_SMOOTH, "agm": capi.SEM_AGM, "dgmsr": capi.SEM_DGMSR}[sem]
+    tau, eps, p = kw.get("temperature", 1.0), kw.get("eps", 1e-8), kw.get("p", 1)
+    v = affine_predicate("v", {0: 1.0}, 0.0)
+    w = affine_predicate("w", {1: 1.0}, 0.0)
+    rng = np.random.default_rng(77)
+    for T in (1, 2, 7, 8, 9, 31, 32, 33, 255, 256, 257, 511, 512, 513, 777):
+        sig = (0.5 * rng.standard_normal((2, T, 2))).astype(np.float32)
+        for a in sorted({0, 1, min(5, T - 1), T // 2, max(T - 2, 0), T - 1, T, T + 3}):
+            for mode, phi in ((0, Always(v, Interval(a, None))), (1, Eventually(v, Interval(a, None)))):
+                ys = torch.tensor(sig[..., 0], device="cuda", requires_grad=True)
+                got = ops.open_window(ys, sem_id, mode, a, tau, eps, p)
+                x64 = torch.tensor(sig, dtype=torch.float64, requires_grad=True)
+                want = dense.robustness_trace(phi, x64, dense.make(sem, **kw))
+                ok = torch.isfinite(want)
+                tag = (T, a, mode)
+                assert int(ok.sum()) == 2 * max(T - a, 0), tag
+                assert bool(torch.isfinite(got).all()), tag  # (positions the reference raises on hold a finite filler)
+                if not bool(ok.any()):
+                    continue
+                if sem == "classical":
+                    assert torch.equal(got.detach().cpu()[ok], want.detach()[ok].to(torch.float32)), tag
+                else:
+                    assert torch.allclose(got.detach().cpu().double()[ok], want.detach()[ok], **tol(sem)), tag
+                gsel = torch.tensor(rng.uniform(0.25, 1.0, size=(2, T)))
+                (got * torch.where(ok, gsel, 0.0).to("cuda", torch.float32)).sum().backward()
+                (torch.nan_to_num(want) * gsel).sum().backward()
+                fin = torch.isfinite(x64.grad).all(dim=(1, 2))  # (dgmsr: see test_scan_path_against_the_oracle)
+                assert bool(torch.isfinite(ys.grad).all()), tag
+                scale = float(x64.grad[fin].abs().max()) + 1e-12 if bool(fin.any()) else 1.0
+                assert torch.allclose(ys.grad.cpu().double()[fin], x64.grad[fin][..., 0], rtol=5e-4, atol=2e-5 * scale), tag
+            if sem != "classical":
+                continue
+            # Until: W(t + a); at a = 0 it is the reference's Until, at a > 0 the same trace read a samples later
+            l = torch.tensor(sig[..., 0], device="cuda", requires_grad=True)
+            r = torch.tensor(sig[..., 1], device="cuda", requires_grad=True)
+            w0 = ops.open_until(l, r, sem_id, 0)
+            x64 = torch.tensor(sig, dtype=torch.float64, requires_grad=True)
+            want = dense.robustness_trace(Until(v, w, Interval(0, None)), x64, dense.make("classical"))
+            assert torch.equal(w0.detach().cpu(), want.detach().to(torch.float32)), (T, "until")
+            gsel = torch.tensor(rng.uniform(0.25, 1.0, size=(2, T)))
+            (w0 * gsel.to("cuda", torch.float32)).sum().backward()
+            (want * gsel).sum().backward()
+            assert torch.allclose(torch.stack((l.grad, r.grad), -1).cpu().double(), x64.grad, rtol=1e-5, atol=1e-6), (T, "until grad")
+            wa = ops.open_until(l.detach(), r.detach(), sem_id, a)
+            if a < T:
+                assert torch.equal(wa[:, : T - a], w0.detach()[:, a:]), (T, a, "until shift")
+    # an empty batch is a no-op
+    assert tuple(ops.open_window(torch.zeros(0, 300, device="cuda"), sem_id, 0, 2, tau, eps, p).shape) == (0, 300)
+
+
 def test_a_window_that_always_raises_is_nan_everywhere():
     # an operand that is itself undefined near the horizon makes the open-ended window raise at every t (api.py:218-221)
     x, _ = preds()
