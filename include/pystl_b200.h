@@ -181,7 +181,8 @@ int pystl_b200_fused_source(const pystl_formula_t* formula, int64_t T, int32_t D
  * temporal_eventually (mode 1) of y[b, t+a .. T-1] -- Always / Eventually.evaluate with Interval.end None,
  * pystl/api.py:49-54,208-243 -> classic.py:39-57, smooth.py:47-65, agm.py:92-110, dgmsr.py:58-86 -- as one suffix
  * scan per trace (pystl_b200/csrc/scan.cu).  The host feeds `out` back to the formula kernels as a leaf channel
- * with pystl_pred_t.slack = a.  Outputs at t > T-1-a (empty window) hold a finite filler.
+ * with pystl_pred_t.slack = a.  Outputs at t > T-1-a (empty window) hold a finite filler for that kernel to read; mode + 2
+ * writes NaN there instead (the window is the whole formula: NaN is what eval_forward writes where the reference raises).
  *   arg   int32[B, T], classical only (may be NULL otherwise): the window's arg-min / arg-max for the gradient
  * Cumulative values are pairs and are not offered here (PYSTL_E_UNSUPPORTED), nor are window weights. */
 int pystl_b200_open_window_forward(int32_t semantics, int32_t mode, int32_t a, float temperature, float eps, int32_t p,
@@ -202,6 +203,16 @@ int pystl_b200_open_until_forward(int32_t semantics, int32_t a, const float* l, 
                                   float* out, int32_t* key, void* stream);
 int pystl_b200_open_until_backward(int32_t semantics, int32_t a, const int32_t* key, const float* grad_out, int64_t B,
                                    int64_t T, float* grad_l, float* grad_r, void* stream);
+
+/* The tensor a formula kernel reads when some predicates are leaf channels (host-computed columns: opaque predicates,
+ * pystl_b200/compiler.py: leaf_values; the open-ended windows above): for every row r = (trace, t)
+ *   out[r, :] = [ signal[r, channels[0 .. n_channels)] | cols[0][r] .. cols[n_cols - 1][r] ]       (one pass)
+ * and its adjoint: grad_signal[rows, D] fully overwritten (zeros for channels not read; may be NULL), grad_cols[j][rows]
+ * (entries may be NULL).  At most 32 read channels of a signal of at most 64, and 16 columns (PYSTL_E_UNSUPPORTED beyond). */
+int pystl_b200_assemble_channels(const float* signal, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels,
+                                 const float* const* cols, int32_t n_cols, float* out, void* stream);
+int pystl_b200_scatter_channels(const float* grad, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels,
+                                float* grad_signal, float* const* grad_cols, int32_t n_cols, void* stream);
 
 #ifdef __cplusplus
 }

@@ -196,12 +196,14 @@ class CompiledFormula:
     n_signal_channels: int = 0   # channels of the user's signal
     leaf_preds: Tuple[Any, ...] = ()  # non-affine predicates / OpenLeaf: leaf j is channel n_signal_channels + j
     has_open: bool = False  # an Always / Eventually without an end is evaluated inside the kernel (one tile)
+    signal_channels: Tuple[int, ...] = ()  # channels of the user's signal the kernels read, in kernel order (leaves follow)
+    root_leaf: Optional[int] = None  # the whole formula is leaf j (an open-ended window / until): no formula kernel runs
     probed_preds: Tuple[Any, ...] = ()  # (predicate, terms, bias) recognised as affine by probing only
 
     @property
     def n_channels(self) -> int:
         """Channels of the tensor the kernels read (signal + leaf channels)."""
-        return self.n_signal_channels + len(self.leaf_preds)
+        return len(self.signal_channels) + len(self.leaf_preds)
 
     def ptr(self):
         return C.byref(self.struct)
@@ -371,6 +373,22 @@ def compile_formula(
 
     visit(formula)
 
+    # With leaf channels the kernels read a tensor the host assembles anyway: signal channels no predicate reads are left out
+    # of it (an open-ended window over the whole formula needs none at all).
+    signal_channels = tuple(range(n_channels))
+    if leaves:
+        signal_channels = tuple(sorted({d for terms, _ in preds for d, _ in terms if d < n_channels}))
+        remap = {d: i for i, d in enumerate(signal_channels)}
+        remap.update({n_channels + j: len(signal_channels) + j for j in range(len(leaves))})
+        preds = [(tuple((remap[d], c) for d, c in terms), bias) for terms, bias in preds]
+    root = nodes[-1]
+    root_leaf = None
+    if leaves and root.kind == capi.NODE_PRED:
+        terms, bias = preds[root.pred]
+        j = terms[0][0] - len(signal_channels) if len(terms) == 1 else -1
+        if j >= 0 and terms[0][1] == 1.0 and bias == 0.0 and isinstance(leaves[j], (OpenLeaf, OpenUntilLeaf)):
+            root_leaf = j
+
     node_arr = (capi.Node * len(nodes))(*nodes)
     child_arr = (C.c_int32 * max(len(children), 1))(*children)
     weight_arr = (C.c_float * max(len(weights), 1))(*weights)
@@ -410,58 +428,61 @@ def compile_formula(
         leaf_preds=tuple(leaves),
         probed_preds=tuple(probed),
         has_open=has_open[0],
+        signal_channels=signal_channels,
+        root_leaf=root_leaf,
     )
 
 
-def leaf_values(cf: CompiledFormula, sig, sem=None):
-    """``sig[B, T, D]`` (torch, on the device) -> ``[B, T, D + L]`` with one channel per leaf predicate.
+def leaf_column(cf: CompiledFormula, pred: Any, sig, sem=None, nan_tail: bool = False):
+    """One leaf channel ``[B, T]`` of ``sig[B, T, D]`` (torch, on the device; differentiable).
 
-    An ``OpenLeaf`` channel is ``sem.robustness_trace(child, sig)`` through ``ops.open_window`` (differentiable).
-
-    ``fn(signal, t)`` is the reference's per-trace callable (api.py:24,133-143): it is mapped over
+    An ``OpenLeaf`` / ``OpenUntilLeaf`` channel is ``sem.robustness_trace`` of the operand(s) through ``ops.open_window`` /
+    ``ops.open_until``.  ``fn(signal, t)`` is the reference's per-trace callable (api.py:24,133-143): it is mapped over
     the batch with ``torch.func.vmap`` and over ``t`` either with a second vmap (callables that only
     index with ``t``) or with a Python loop (callables that compute with ``t``)."""
     import torch
 
+    B, T, _ = sig.shape
+    if isinstance(pred, (OpenLeaf, OpenUntilLeaf)):
+        from . import ops
+
+        if sem is None:
+            raise RuntimeError("an open-ended leaf needs the semantics object that compiled it")
+        if isinstance(pred, OpenUntilLeaf):
+            yl, yr = sem.robustness_trace(pred.left, sig), sem.robustness_trace(pred.right, sig)
+            return ops.open_until(yl.contiguous(), yr.contiguous(), cf.struct.semantics, pred.start)
+        y = sem.robustness_trace(pred.child, sig)  # [B, T]; nested open-ended windows recurse here
+        return ops.open_window(y.contiguous(), cf.struct.semantics, pred.mode, pred.start,
+                               cf.struct.temperature, cf.struct.eps, cf.struct.p, nan_tail=nan_tail)
+    fn = pred.fn
+    val = None
+    try:
+        t_idx = torch.arange(T, device=sig.device)
+        per_trace = torch.func.vmap(lambda s, t: torch.as_tensor(fn(s, t), dtype=s.dtype), in_dims=(None, 0))
+        val = torch.func.vmap(per_trace, in_dims=(0, None))(sig, t_idx)  # [B, T]
+    except Exception:
+        val = None
+    if val is None or tuple(val.shape) != (B, T):
+        try:
+            rows = [torch.func.vmap(lambda s, tt=tt: torch.as_tensor(fn(s, tt), dtype=s.dtype))(sig) for tt in range(T)]
+            val = torch.stack(rows, dim=1)
+        except Exception as exc:
+            raise NotImplementedError(
+                f"Predicate '{pred.name}': fn(signal, t) is neither affine nor traceable by torch on the device ({exc!r})"
+            ) from exc
+    if tuple(val.shape) != (B, T):
+        raise NotImplementedError(f"Predicate '{pred.name}': fn(signal, t) must return a scalar")
+    return val.to(sig.dtype)
+
+
+def leaf_values(cf: CompiledFormula, sig, sem=None):
+    """``sig[B, T, D]`` (torch, on the device) -> the tensor the kernels read: the signal channels the predicates use
+    (``cf.signal_channels``) followed by one channel per leaf predicate (``leaf_column``)."""
+    import torch
+
     if not cf.leaf_preds:
         return sig
-    B, T, _ = sig.shape
-    cols = []
-    for pred in cf.leaf_preds:
-        if isinstance(pred, OpenUntilLeaf):
-            from . import ops
+    from . import ops
 
-            if sem is None:
-                raise RuntimeError("an open-ended until leaf needs the semantics object that compiled it")
-            yl, yr = sem.robustness_trace(pred.left, sig), sem.robustness_trace(pred.right, sig)
-            cols.append(ops.open_until(yl.contiguous(), yr.contiguous(), cf.struct.semantics, pred.start))
-            continue
-        if isinstance(pred, OpenLeaf):
-            from . import ops
-
-            if sem is None:
-                raise RuntimeError("an open-ended window leaf needs the semantics object that compiled it")
-            y = sem.robustness_trace(pred.child, sig)  # [B, T]; nested open-ended windows recurse here
-            cols.append(ops.open_window(y.contiguous(), cf.struct.semantics, pred.mode, pred.start,
-                                        cf.struct.temperature, cf.struct.eps, cf.struct.p))
-            continue
-        fn = pred.fn
-        val = None
-        try:
-            t_idx = torch.arange(T, device=sig.device)
-            per_trace = torch.func.vmap(lambda s, t: torch.as_tensor(fn(s, t), dtype=s.dtype), in_dims=(None, 0))
-            val = torch.func.vmap(per_trace, in_dims=(0, None))(sig, t_idx)  # [B, T]
-        except Exception:
-            val = None
-        if val is None or tuple(val.shape) != (B, T):
-            try:
-                rows = [torch.func.vmap(lambda s, tt=tt: torch.as_tensor(fn(s, tt), dtype=s.dtype))(sig) for tt in range(T)]
-                val = torch.stack(rows, dim=1)
-            except Exception as exc:
-                raise NotImplementedError(
-                    f"Predicate '{pred.name}': fn(signal, t) is neither affine nor traceable by torch on the device ({exc!r})"
-                ) from exc
-        if tuple(val.shape) != (B, T):
-            raise NotImplementedError(f"Predicate '{pred.name}': fn(signal, t) must return a scalar")
-        cols.append(val.to(sig.dtype))
-    return torch.cat([sig, torch.stack(cols, dim=-1)], dim=-1).contiguous()
+    cols = [leaf_column(cf, pred, sig, sem) for pred in cf.leaf_preds]
+    return ops.assemble(sig, cf.signal_channels, cols)

@@ -408,7 +408,19 @@ int open_until_forward(int32_t semantics, int32_t a, const float* l, const float
                        void* stream, char* err, size_t err_cap);
 int open_until_backward(int32_t semantics, int32_t a, const int32_t* key, const float* grad_out, int64_t B, int64_t T, float* grad_l,
                         float* grad_r, void* stream, char* err, size_t err_cap);
+int assemble_channels(const float* signal, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels, const float* const* cols,
+                      int32_t n_cols, float* out, void* stream, char* err, size_t err_cap);
+int scatter_channels(const float* grad, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels, float* grad_signal,
+                     float* const* grad_cols, int32_t n_cols, void* stream, char* err, size_t err_cap);
 }  // namespace pystl
+extern "C" int pystl_b200_assemble_channels(const float* signal, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels,
+                                            const float* const* cols, int32_t n_cols, float* out, void* stream) {
+  return pystl::assemble_channels(signal, rows, D, channels, n_channels, cols, n_cols, out, stream, g_err, sizeof(g_err));
+}
+extern "C" int pystl_b200_scatter_channels(const float* grad, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels,
+                                           float* grad_signal, float* const* grad_cols, int32_t n_cols, void* stream) {
+  return pystl::scatter_channels(grad, rows, D, channels, n_channels, grad_signal, grad_cols, n_cols, stream, g_err, sizeof(g_err));
+}
 extern "C" int pystl_b200_open_until_forward(int32_t semantics, int32_t a, const float* l, const float* r, int64_t B, int64_t T,
                                              float* out, int32_t* key, void* stream) {
   return pystl::open_until_forward(semantics, a, l, r, B, T, out, key, stream, g_err, sizeof(g_err));

@@ -130,7 +130,8 @@ __device__ __forceinline__ int pad(int e) { return e + (e >> 5); }
 
 template <int SEM, int MODE>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) open_window_fwd(const float* __restrict__ y, float* __restrict__ out,
-                                                                       int* __restrict__ arg, long long B, int T, int a, RP rp) {
+                                                                       int* __restrict__ arg, long long B, int T, int a, RP rp,
+                                                                       int nan_tail) {
   using S = ScanRed<SEM, MODE>;
   using A = typename S::A;
   __shared__ float s_val[kWarpsPerBlock][kBuf];
@@ -197,8 +198,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) open_window_fwd(const flo
       }
     }
     if (c0 + kChunk >= T && a > 0) {
-      // t + a > T - 1: the reference raises (masked by the caller's start_slack); a finite value of the right magnitude
-      const float v = __shfl_sync(0xffffffffu, last, ((T - 1 - c0) >> 3));
+      // t + a > T - 1: the reference raises (masked by the caller's start_slack); a finite value of the right magnitude for a
+      // parent kernel to read, NaN (mode bit 1) when these values ARE the formula's robustness
+      const float v = nan_tail ? __int_as_float(0x7fc00000) : __shfl_sync(0xffffffffu, last, ((T - 1 - c0) >> 3));
       for (int tt = (T - a > 0 ? T - a : 0) + lane; tt < T; tt += 32) {
         ob[tt] = v;
         if constexpr (SEM == SEM_CLASSIC) ab[tt] = -1;
@@ -508,7 +510,7 @@ RP make_rp(float temperature, float eps, int p) {
 int check(int semantics, int mode, int a, long long B, long long T, float temperature, float eps, int p) {
   if (semantics != SEM_CLASSIC && semantics != SEM_SMOOTH && semantics != SEM_AGM && semantics != SEM_DGMSR)
     return scan_fail(PYSTL_E_UNSUPPORTED, "open-ended windows beyond one tile: classical, smooth, agm and dgmsr (cumulative values are pairs)");
-  if (mode != MODE_AND && mode != MODE_OR) return scan_fail(PYSTL_E_INVALID, "mode must be 0 (always) or 1 (eventually)");
+  if (mode < 0 || mode > 3) return scan_fail(PYSTL_E_INVALID, "mode must be 0 (always) or 1 (eventually), + 2 for a NaN tail");
   if (a < 0) return scan_fail(PYSTL_E_INVALID, "Interval start must be >= 0.");
   if (B < 0 || T < 0 || T >= (1ll << 31) - 65536) return scan_fail(PYSTL_E_INVALID, "bad shape");
   if (semantics == SEM_SMOOTH && !(temperature > 0.f)) return scan_fail(PYSTL_E_INVALID, "temperature must be > 0.");
@@ -554,7 +556,9 @@ int open_window_forward(int32_t semantics, int32_t mode, int32_t a, float temper
   cudaStream_t st = (cudaStream_t)stream;
   const RP rp = make_rp(temperature, eps, p);
   int* argp = semantics == SEM_CLASSIC ? arg : nullptr;
-  PYSTL_SCAN_DISPATCH(open_window_fwd, y, out, argp, (long long)B, (int)T, (int)a, rp);
+  const int nan_tail = (mode >> 1) & 1;
+  mode &= 1;
+  PYSTL_SCAN_DISPATCH(open_window_fwd, y, out, argp, (long long)B, (int)T, (int)a, rp, nan_tail);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "open_window_fwd: %s", cudaGetErrorString(e));
   return PYSTL_OK;
@@ -569,6 +573,7 @@ int open_window_backward(int32_t semantics, int32_t mode, int32_t a, float tempe
   if (rc) return rc;
   if (B == 0 || T == 0) return PYSTL_OK;
   if (!y || !out || !grad_out || !grad_y) return scan_fail(PYSTL_E_INVALID, "null buffer");
+  mode &= 1;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
     cudaGetLastError();
@@ -645,6 +650,123 @@ int open_until_backward(int32_t semantics, int32_t a, const int32_t* key, const 
       key, grad_out, grad_l, grad_r, (long long)B, (int)T, (int)a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "open_until_bwd: %s", cudaGetErrorString(e));
+  return PYSTL_OK;
+}
+
+// ---------------------------------------------------------------- the tensor a formula kernel reads next to leaf channels
+// out[r, :] = [ signal[r, ch[0..n)] | col_0[r] .. col_{L-1}[r] ] for every row r = (trace, t): one pass (a torch.cat of an
+// indexed signal and stacked columns is three), and the adjoint: grad_signal[r, :] = 0 except the read channels, one
+// gradient column per leaf.
+constexpr int kMaxAssembleCols = 16, kMaxAssembleCh = 32, kMaxAssembleD = 64;
+struct AssembleArgs {
+  const float* cols[kMaxAssembleCols];
+  float* gcols[kMaxAssembleCols];
+  int ch[kMaxAssembleCh];
+  signed char inv[kMaxAssembleD];  // channel d -> its position among the read channels, -1: not read
+  int n, L, D;
+};
+// A CTA of 256 threads owns 256 consecutive rows = 256 * W consecutive output floats: stores are fully coalesced, loads stay inside
+// the rows the CTA is writing, and the (row, column) split is 32-bit arithmetic on the tile-local index (compile-time W up to 8).
+template <int WT>
+__global__ void __launch_bounds__(256) assemble_rows(const float* __restrict__ signal, const __grid_constant__ AssembleArgs a,
+                                                     float* __restrict__ out, long long rows) {
+  const int W = WT ? WT : a.n + a.L;
+  for (long long r0 = (long long)blockIdx.x * 256; r0 < rows; r0 += (long long)gridDim.x * 256) {
+    const int nr = rows - r0 < 256 ? (int)(rows - r0) : 256;
+    const float* s = signal + r0 * a.D;
+    float* o = out + r0 * W;
+    for (int e = threadIdx.x; e < nr * W; e += 256) {
+      const int r = e / W, w = e - r * W;
+      o[e] = w < a.n ? s[r * a.D + a.ch[w]] : a.cols[w - a.n][r0 + r];
+    }
+  }
+}
+template <int DT>
+__global__ void __launch_bounds__(256) scatter_rows(const float* __restrict__ grad, const __grid_constant__ AssembleArgs a,
+                                                    float* __restrict__ grad_signal, long long rows) {
+  const int W = a.n + a.L, D = DT ? DT : a.D;
+  for (long long r0 = (long long)blockIdx.x * 256; r0 < rows; r0 += (long long)gridDim.x * 256) {
+    const int nr = rows - r0 < 256 ? (int)(rows - r0) : 256;
+    const float* g = grad + r0 * W;
+    if (grad_signal) {
+      float* s = grad_signal + r0 * D;
+      for (int e = threadIdx.x; e < nr * D; e += 256) {
+        const int r = e / D, i = a.inv[e - r * D];
+        s[e] = i >= 0 ? g[r * W + i] : 0.f;
+      }
+    }
+    if ((int)threadIdx.x < nr)
+      for (int jc = 0; jc < a.L; ++jc)
+        if (a.gcols[jc]) a.gcols[jc][r0 + threadIdx.x] = g[threadIdx.x * W + a.n + jc];
+  }
+}
+
+static int assemble_fill(AssembleArgs& a, int32_t D, const int32_t* channels, int32_t n_channels, int32_t n_cols) {
+  if (n_channels > kMaxAssembleCh || n_cols > kMaxAssembleCols || D > kMaxAssembleD)
+    return scan_fail(PYSTL_E_UNSUPPORTED, "at most %d read channels of %d and %d leaf columns", kMaxAssembleCh, kMaxAssembleD, kMaxAssembleCols);
+  a.n = n_channels, a.L = n_cols, a.D = D;
+  for (int d = 0; d < kMaxAssembleD; ++d) a.inv[d] = -1;
+  for (int i = 0; i < n_channels; ++i) {
+    if (channels[i] < 0 || channels[i] >= D) return scan_fail(PYSTL_E_INVALID, "channel %d of a %d-channel signal", channels[i], D);
+    if (a.inv[channels[i]] >= 0) return scan_fail(PYSTL_E_INVALID, "channel %d is listed twice", channels[i]);
+    a.ch[i] = channels[i];
+    a.inv[channels[i]] = (signed char)i;
+  }
+  return PYSTL_OK;
+}
+static unsigned assemble_grid(long long rows) {
+  const long long blocks = (rows + 255) / 256;
+  return (unsigned)(blocks < 148 * 64 ? (blocks < 1 ? 1 : blocks) : 148 * 64);  // tile-stride beyond that
+}
+
+int assemble_channels(const float* signal, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels, const float* const* cols,
+                      int32_t n_cols, float* out, void* stream, char* err, size_t err_cap) {
+  g_err = err;
+  g_err_cap = err_cap;
+  if (rows < 0 || D < 0 || n_channels < 0 || n_cols < 0 || n_channels + n_cols == 0) return scan_fail(PYSTL_E_INVALID, "bad shape");
+  if ((n_channels && (!signal || !channels)) || (n_cols && !cols) || (rows && !out)) return scan_fail(PYSTL_E_INVALID, "null buffer");
+  AssembleArgs a{};
+  const int rc = assemble_fill(a, D, channels, n_channels, n_cols);
+  if (rc) return rc;
+  if (rows == 0) return PYSTL_OK;
+  for (int j = 0; j < n_cols; ++j) {
+    if (!cols[j]) return scan_fail(PYSTL_E_INVALID, "null column");
+    a.cols[j] = cols[j];
+  }
+  const unsigned grid = assemble_grid(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (n_channels + n_cols) {
+#define PYSTL_ASM(WT) case WT: assemble_rows<WT><<<grid, 256, 0, st>>>(signal, a, out, (long long)rows); break;
+    PYSTL_ASM(1) PYSTL_ASM(2) PYSTL_ASM(3) PYSTL_ASM(4) PYSTL_ASM(5) PYSTL_ASM(6) PYSTL_ASM(7) PYSTL_ASM(8)
+#undef PYSTL_ASM
+    default: assemble_rows<0><<<grid, 256, 0, st>>>(signal, a, out, (long long)rows);
+  }
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "assemble_rows: %s", cudaGetErrorString(e));
+  return PYSTL_OK;
+}
+
+int scatter_channels(const float* grad, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels, float* grad_signal,
+                     float* const* grad_cols, int32_t n_cols, void* stream, char* err, size_t err_cap) {
+  g_err = err;
+  g_err_cap = err_cap;
+  if (rows < 0 || D < 0 || n_channels < 0 || n_cols < 0 || n_channels + n_cols == 0) return scan_fail(PYSTL_E_INVALID, "bad shape");
+  if ((rows && !grad) || (n_channels && !channels) || (n_cols && !grad_cols)) return scan_fail(PYSTL_E_INVALID, "null buffer");
+  AssembleArgs a{};
+  const int rc = assemble_fill(a, D, channels, n_channels, n_cols);
+  if (rc) return rc;
+  if (rows == 0) return PYSTL_OK;
+  for (int j = 0; j < n_cols; ++j) a.gcols[j] = grad_cols[j];
+  const unsigned grid = assemble_grid(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (D) {
+#define PYSTL_SCT(DT) case DT: scatter_rows<DT><<<grid, 256, 0, st>>>(grad, a, grad_signal, (long long)rows); break;
+    PYSTL_SCT(1) PYSTL_SCT(2) PYSTL_SCT(3) PYSTL_SCT(4) PYSTL_SCT(5) PYSTL_SCT(6) PYSTL_SCT(7) PYSTL_SCT(8)
+#undef PYSTL_SCT
+    default: scatter_rows<0><<<grid, 256, 0, st>>>(grad, a, grad_signal, (long long)rows);
+  }
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "scatter_rows: %s", cudaGetErrorString(e));
   return PYSTL_OK;
 }
 

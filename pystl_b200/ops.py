@@ -276,9 +276,11 @@ class OpenWindow(torch.autograd.Function):
         return (open_window_grad(y, out, arg, grad_out, *ctx.params),) + (None,) * 6
 
 
-def open_window(y: torch.Tensor, semantics: int, mode: int, start: int, temperature: float, eps: float, p: int) -> torch.Tensor:
-    """Differentiable ``G[start, inf)`` (mode 0) / ``F[start, inf)`` (mode 1) of the value trace ``y[B, T]``."""
-    return OpenWindow.apply(y, int(semantics), int(mode), int(start), float(temperature), float(eps), int(p))[0]
+def open_window(y: torch.Tensor, semantics: int, mode: int, start: int, temperature: float, eps: float, p: int,
+                nan_tail: bool = False) -> torch.Tensor:
+    """Differentiable ``G[start, inf)`` (mode 0) / ``F[start, inf)`` (mode 1) of the value trace ``y[B, T]``.
+    ``nan_tail``: the last ``start`` outputs (empty windows) are NaN instead of a finite filler."""
+    return OpenWindow.apply(y, int(semantics), int(mode) | (2 if nan_tail else 0), int(start), float(temperature), float(eps), int(p))[0]
 
 
 # ---- classical Until without an end beyond one tile: clamp-composition suffix scan (csrc/scan.cu) ------------------
@@ -355,3 +357,64 @@ class OpenUntil(torch.autograd.Function):
 def open_until(left: torch.Tensor, right: torch.Tensor, semantics: int, start: int) -> torch.Tensor:
     """Differentiable unbounded Until of the value traces ``left, right [B, T]`` read at ``t + start`` (classical semantics)."""
     return OpenUntil.apply(left, right, int(semantics), int(start))[0]
+
+
+# ---- the tensor the formula kernels read when some predicates are leaf channels -------------------------------------
+import ctypes as _C
+
+
+def _ptr_array(tensors):
+    return (_C.c_void_p * max(len(tensors), 1))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+class Assemble(torch.autograd.Function):
+    """``[signal[..., channels] | leaf columns]`` in one pass (``pystl_b200_assemble_channels``; a ``torch.cat`` of an
+    advanced-indexed signal and stacked columns is three, and its backward an accumulating ``index_put_``: 130 ms at
+    16384 x 16384 samples).  The adjoint (``pystl_b200_scatter_channels``) writes the signal's gradient and one column per leaf."""
+
+    @staticmethod
+    def forward(signal, channels, *cols):
+        _check(signal)
+        sig = signal.contiguous()
+        B, T, D = sig.shape
+        cols = [c.to(torch.float32).contiguous() for c in cols]
+        for c in cols:
+            if tuple(c.shape) != (B, T) or not c.is_cuda:
+                raise ValueError(f"leaf columns must be CUDA tensors of shape {(B, T)}")
+        out = sig.new_empty((B, T, len(channels) + len(cols)))
+        ch = (_C.c_int32 * max(len(channels), 1))(*channels)
+        with torch.cuda.device(sig.device):
+            rc = capi.lib().pystl_b200_assemble_channels(sig.data_ptr(), B * T, D, ch, len(channels), _ptr_array(cols), len(cols),
+                                                         out.data_ptr(), torch.cuda.current_stream(sig.device).cuda_stream)
+        capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+        return out
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        signal, channels = inputs[0], inputs[1]
+        ctx.channels = tuple(channels)
+        ctx.D = signal.shape[-1]
+        ctx.n_cols = len(inputs) - 2
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = grad.to(torch.float32).contiguous()
+        B, T, _ = g.shape
+        gs = g.new_empty((B, T, ctx.D)) if ctx.needs_input_grad[0] else None
+        gcols = [g.new_empty((B, T)) if ctx.needs_input_grad[2 + j] else None for j in range(ctx.n_cols)]
+        ch = (_C.c_int32 * max(len(ctx.channels), 1))(*ctx.channels)
+        with torch.cuda.device(g.device):
+            rc = capi.lib().pystl_b200_scatter_channels(g.data_ptr(), B * T, ctx.D, ch, len(ctx.channels),
+                                                        None if gs is None else gs.data_ptr(), _ptr_array(gcols), ctx.n_cols,
+                                                        torch.cuda.current_stream(g.device).cuda_stream)
+        capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+        return (gs, None) + tuple(gcols)
+
+
+def assemble(signal: torch.Tensor, channels, cols) -> torch.Tensor:
+    if not cols and tuple(channels) == tuple(range(signal.shape[-1])):
+        return signal
+    if len(channels) > 32 or len(cols) > 16 or signal.shape[-1] > 64:  # beyond the kernel's argument block: the same tensor by torch ops (device side too)
+        idx = torch.tensor([int(d) for d in channels], dtype=torch.long, device=signal.device)
+        return torch.cat([signal.index_select(-1, idx)] + [c.unsqueeze(-1) for c in cols], dim=-1).contiguous()
+    return Assemble.apply(signal, tuple(int(d) for d in channels), *cols)

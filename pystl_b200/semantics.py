@@ -34,7 +34,7 @@ from typing import Any, Dict, Optional, Sequence, Tuple
 import torch
 
 from . import capi
-from .compiler import CompiledFormula, compile_formula, leaf_values
+from .compiler import CompiledFormula, compile_formula, leaf_column, leaf_values
 from .formula import Predicate, affine_predicate
 
 
@@ -199,9 +199,12 @@ class _B200Semantics(_ReferenceSemantics):
 
         sig, squeeze, home = self._prepare(signal)  # (stays connected to `signal` in the autograd graph)
         cf = self._checked_compile(formula, sig)
-        if cf.leaf_preds:  # non-affine predicates: leaf channels computed by torch, inside the graph
-            sig = leaf_values(cf, sig, self)
-        out = ops.evaluate(sig, ops.handle_of(cf, self.out_channels))
+        if cf.root_leaf is not None:  # the formula IS one open-ended window / until: the scan kernels write its robustness
+            out = self._root_leaf_trace(cf, sig, nan_tail=True).unsqueeze(-1)
+        else:
+            if cf.leaf_preds:  # non-affine predicates: leaf channels computed by torch, inside the graph
+                sig = leaf_values(cf, sig, self)
+            out = ops.evaluate(sig, ops.handle_of(cf, self.out_channels))
         if home != out.device:
             out = out.to(home)
         if squeeze:
@@ -209,6 +212,17 @@ class _B200Semantics(_ReferenceSemantics):
         if self.out_channels == 2:
             return B200CumulativeRobustness(pos=out[..., 0], neg=out[..., 1])
         return out[..., 0]
+
+    def _root_leaf_trace(self, cf: CompiledFormula, sig: torch.Tensor, nan_tail: bool) -> torch.Tensor:
+        """``[B, T]`` robustness of a formula whose root is an open-ended window / until leaf (``cf.root_leaf``): the scan
+        kernels' output, no formula kernel and no assembled input tensor.  ``slack = -1``: the reference raises at every t."""
+        if cf.preds[0].slack < 0:
+            return torch.full(sig.shape[:2], float("nan"), dtype=torch.float32, device=sig.device) + 0.0 * sig[..., 0]
+        return leaf_column(cf, cf.leaf_preds[cf.root_leaf], sig, self, nan_tail=nan_tail)
+
+    def _root_leaf_valid(self, cf: CompiledFormula, T: int) -> int:
+        slack = cf.preds[0].slack
+        return 0 if slack < 0 else max(T - slack, 0)
 
     def mean_robustness(self, formula: Any, signal: Any, *, group=None) -> torch.Tensor:
         """Mean of the valid outputs (cumulative: of ``pos + neg``), reduced inside the kernel.
@@ -220,6 +234,13 @@ class _B200Semantics(_ReferenceSemantics):
         sig, _, _ = self._prepare(signal)
         cf = self._checked_compile(formula, sig)
         acc = torch.zeros(2, dtype=torch.float64, device=sig.device)
+        if cf.root_leaf is not None:
+            valid = self._root_leaf_valid(cf, sig.shape[1])
+            with torch.no_grad():
+                if valid > 0:
+                    acc[0] = self._root_leaf_trace(cf, sig, nan_tail=False)[:, :valid].sum(dim=1).sum(dtype=torch.float64)
+            acc[1] = float(sig.shape[0] * valid)
+            return all_reduce_mean(acc, group=group)
         plan = self.plan(formula, sig.shape[1], sig.shape[2], cf)
         with torch.no_grad():
             sig = leaf_values(cf, sig, self)
@@ -242,6 +263,26 @@ class _B200Semantics(_ReferenceSemantics):
         sig = sig.detach()
         B, T, D = sig.shape
         cf = self._checked_compile(formula, sig)
+        if cf.root_leaf is not None:  # the scan kernels and their adjoints are the whole evaluation
+            valid = self._root_leaf_valid(cf, T)
+            n_local = float(B * valid)
+            n_total = all_reduce_count(n_local, sig.device, group=group)
+            acc = torch.zeros(2, dtype=torch.float64, device=sig.device)
+            if valid > 0:
+                base = sig.detach().requires_grad_(True)
+                with torch.enable_grad():
+                    # (row sums in fp32, their sum in float64: summing with dtype=float64 materialises a float64 copy of the trace)
+                    total = self._root_leaf_trace(cf, base, nan_tail=False)[:, :valid].sum(dim=1).sum(dtype=torch.float64)
+                (grad,) = torch.autograd.grad(total, base, torch.tensor((1.0 / n_total) if n_total > 0 else 0.0, dtype=torch.float64,
+                                                                        device=sig.device))
+                acc[0] = total.detach()
+            else:
+                grad = torch.zeros_like(sig)
+            acc[1] = n_local
+            mean = all_reduce_mean(acc, group=group)
+            if home != grad.device:
+                grad = grad.to(home)
+            return mean, (grad[0] if squeeze else grad)
         plan = self.plan(formula, T, D, cf)
         valid = 0 if plan["raises_always"] else max(T - plan["start_slack"], 0)
         n_local = float(B * valid)

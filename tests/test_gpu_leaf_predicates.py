@@ -33,7 +33,7 @@ def test_values_and_gradients(sem, kw):
     phi = formula()
     s = create_semantics(sem, backend="b200", **kw)
     cf = s.compile(phi, 2)
-    assert len(cf.leaf_preds) == 2 and cf.n_channels == 4
+    assert len(cf.leaf_preds) == 2 and cf.signal_channels == (0,) and cf.n_channels == 3
 
     x = torch.tensor(sig, device="cuda", requires_grad=True)
     got = s.robustness_trace(phi, x)
@@ -68,3 +68,27 @@ def test_untraceable_predicate_is_loud():
     s = create_semantics("classical", backend="b200")
     with pytest.raises(NotImplementedError):
         s.robustness_trace(Always(bad, Interval(0, 3)), torch.zeros(2, 20, 2, device="cuda"))
+
+
+def test_assemble_kernel_matches_torch_cat():
+    """``ops.assemble`` (pystl_b200_assemble_channels / _scatter_channels): the tensor the kernels read next to leaf columns."""
+    from pystl_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for (B, T, D), ch, L in (((3, 70, 4), (2, 0), 2), ((2, 513, 2), (1,), 1), ((1, 33, 8), (), 3), ((4, 257, 3), (0, 1, 2), 1),
+                             ((2, 40, 40), tuple(range(0, 40)), 2), ((2, 40, 2), (0,), 17), ((2, 9, 70), (69, 3), 1), ((5, 1000, 5), (4, 1, 3), 4)):
+        sig = torch.randn(B, T, D, device="cuda", generator=g, requires_grad=True)
+        cols = [torch.randn(B, T, device="cuda", generator=g, requires_grad=True) for _ in range(L)]
+        out = ops.assemble(sig, ch, cols)
+        ref = torch.cat([sig.detach()[..., list(ch)]] + [c.detach()[..., None] for c in cols], -1)
+        assert torch.equal(out.detach(), ref)
+        w = torch.randn(out.shape, device="cuda", generator=g)
+        (out * w).sum().backward()
+        want = torch.zeros_like(sig)
+        for i, d in enumerate(ch):
+            want[..., d] = w[..., i]
+        assert torch.equal(sig.grad, want)
+        for j, c in enumerate(cols):
+            assert torch.equal(c.grad, w[..., len(ch) + j])
+    same = torch.randn(2, 5, 3, device="cuda")
+    assert ops.assemble(same, (0, 1, 2), []) is same

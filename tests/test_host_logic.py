@@ -136,13 +136,15 @@ def test_open_ended_windows_beyond_one_tile_become_leaf_channels():
         cf = sem.compile(phi, 2, open_leaf=True)
         (leaf,) = cf.leaf_preds
         assert isinstance(leaf, OpenLeaf) and leaf.child is x and (leaf.mode, leaf.start) == (0, 3)
-        assert cf.n_channels == 3 and not cf.has_open
+        assert cf.signal_channels == (1,) and cf.n_channels == 2 and not cf.has_open and cf.root_leaf is None
         slacks = sorted(cf.preds[i].slack for i in range(cf.struct.n_preds))
         assert slacks == [0, 3]
         short, long = sem.plan(phi, 2048, 2), sem.plan(phi, 20000, 2)
         assert short["n_tiles"] == 1 and long["n_tiles"] > 1
         assert short["start_slack"] == long["start_slack"] == 3 and long["lookahead"] == 10
         # a window over the open-ended one: its whole extent must end before the operand does
+        alone = sem.compile(Always(x, Interval(3, None)), 2, open_leaf=True)  # the whole formula is the scanned window
+        assert alone.root_leaf == 0 and alone.signal_channels == () and alone.n_channels == 1 and alone.preds[0].slack == 3
         over = Always(Always(x, Interval(3, None)), Interval(0, 5))
         assert sem.plan(over, 2048, 2)["start_slack"] == sem.plan(over, 20000, 2)["start_slack"] == 8
         # an operand that is undefined near the horizon: the open-ended window raises at every t
@@ -230,9 +232,12 @@ def test_non_affine_predicates_become_leaf_channels():
     lin = Predicate("lin", fn=lambda s, t: 0.5 - s[t, 1])
     phi = And(Always(sq, Interval(0, 3)), lin, Always(sq, Interval(1, 2)))
     cf = compile_formula(phi, "smooth", 2, temperature=1.0)
-    assert len(cf.leaf_preds) == 1 and cf.n_signal_channels == 2 and cf.n_channels == 3
+    # the kernels read [the signal channels an affine predicate uses] + [one channel per leaf]: channel 0 is only read by fn
+    assert len(cf.leaf_preds) == 1 and cf.n_signal_channels == 2 and cf.signal_channels == (1,) and cf.n_channels == 2
     terms = sorted(cf.pred_terms)
-    assert (((1, -1.0),), 0.5) in terms and (((2, 1.0),), 0.0) in terms
+    assert (((0, -1.0),), 0.5) in terms and (((1, 1.0),), 0.0) in terms
+    both = compile_formula(And(phi, Predicate("lin0", fn=lambda s, t: s[t, 0] + 1.0)), "smooth", 2, temperature=1.0)
+    assert both.signal_channels == (0, 1) and both.n_channels == 3
 
 
 # ---------------------------------------------------------------------------- probing is only a fast reject
@@ -257,7 +262,7 @@ def test_probe_rejects_what_it_can_and_real_signals_catch_the_rest():
     bad = verify_probed(cf, traces)
     assert bad == (id(p.fn),)
     cf2 = compile_formula(phi, "classical", 2, force_leaf=bad)
-    assert len(cf2.leaf_preds) == 1 and cf2.leaf_preds[0] is p and cf2.n_channels == 3
+    assert len(cf2.leaf_preds) == 1 and cf2.leaf_preds[0] is p and cf2.signal_channels == (1,) and cf2.n_channels == 2
     assert verify_probed(cf2, traces) == ()
     # metadata gives the structured form: never probed, never second-guessed
     assert compile_formula(gt(0, 0.5).always((0, 3)), "classical", 2).probed_preds == ()
