@@ -151,6 +151,31 @@ class _B200Semantics(_ReferenceSemantics):
             for k in [k for k in d if k[0] == id(formula)]:
                 d.pop(k, None)
 
+    def precompile(self, formula: Any, horizon: int, n_channels: int, *, backward: bool = True) -> int:
+        """Compile the fused kernels ``formula`` needs on traces of ``horizon`` samples into the on-disk cubin cache (no GPU
+        needed), following the host-side split at open-ended operators on long traces.  Returns the
+        number of kernels compiled or found; formulas that run on the interpreter tier count as 0."""
+        from .compiler import OpenLeaf, OpenUntilLeaf
+
+        cf = self.compile(formula, n_channels)
+        if self.force_open_leaf or (cf.has_open and self._needs_open_leaf(formula, cf, int(horizon))):
+            cf = self.compile(formula, n_channels, open_leaf=True)
+        done = 0
+        if cf.root_leaf is None:
+            for bwd in ((0, 1) if backward else (0,)):
+                rc = capi.lib().pystl_b200_fused_precompile(cf.ptr(), int(horizon), cf.n_channels, bwd)
+                if rc == capi.OK:
+                    done += 1
+                elif rc != capi.E_UNSUPPORTED:
+                    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+        for leaf in cf.leaf_preds:
+            if isinstance(leaf, OpenLeaf):
+                done += self.precompile(leaf.child, horizon, n_channels, backward=backward)
+            elif isinstance(leaf, OpenUntilLeaf):
+                done += self.precompile(leaf.left, horizon, n_channels, backward=backward)
+                done += self.precompile(leaf.right, horizon, n_channels, backward=backward)
+        return done
+
     def plan(self, formula: Any, horizon: int, n_channels: int, cf: Optional[CompiledFormula] = None) -> dict:
         """Tiling / validity report for ``formula`` on traces of ``horizon`` samples (host only)."""
         if cf is None:

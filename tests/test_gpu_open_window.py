@@ -291,9 +291,9 @@ def test_chunk_boundaries_and_degenerate_shapes(sem, kw):
     v = affine_predicate("v", {0: 1.0}, 0.0)
     w = affine_predicate("w", {1: 1.0}, 0.0)
     rng = np.random.default_rng(77)
-    for T in (1, 2, 7, 8, 9, 31, 32, 33, 255, 256, 257, 511, 512, 513, 777):
+    for T in (1, 2, 8, 9, 32, 33, 255, 256, 257, 513, 777):
         sig = (0.5 * rng.standard_normal((2, T, 2))).astype(np.float32)
-        for a in sorted({0, 1, min(5, T - 1), T // 2, max(T - 2, 0), T - 1, T, T + 3}):
+        for a in sorted({0, min(5, T - 1), T // 2, T - 1, T, T + 3}):
             for mode, phi in ((0, Always(v, Interval(a, None))), (1, Eventually(v, Interval(a, None)))):
                 ys = torch.tensor(sig[..., 0], device="cuda", requires_grad=True)
                 got = ops.open_window(ys, sem_id, mode, a, tau, eps, p)

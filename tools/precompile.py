@@ -21,7 +21,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 
+def _open(job):
+    """The open-ended corpus (tests/test_gpu_open_window.py): formulas the host splits at open-ended operators."""
+    _, which, name, sem, kw, T, force = job
+    import test_gpu_open_window as ow
+    from pystl_b200 import create_semantics
+
+    os.environ.pop("PYSTL_B200_FORCE_THREADS", None)
+    phi = (ow.formulas() if which == "window" else ow.until_formulas())[name]
+    s = create_semantics(sem, backend="b200", **kw)
+    s.force_open_leaf = force
+    try:
+        return (0 if s.precompile(phi, T, 2) else -2), ""
+    except NotImplementedError as exc:
+        return -2, str(exc)
+
+
 def _one(job):
+    if job[0] == "open":
+        return _open(job)
     spec, sem, kw, T, D, threads, backward = job
     from pystl_b200 import capi
     from pystl_b200.compiler import compile_formula
@@ -56,6 +74,16 @@ def jobs(with_tests: bool):
             out.append((c["spec"], c["sem"], c["kw"], c["T"], c["D"], c["threads"], False))
         for c in fused_cases.backward_cases() + fused_cases.cumulative_backward_cases() + fused_cases.smooth_until_backward_cases() + fused_cases.gm_backward_cases() + fused_cases.random_until_backward_cases() + fused_cases.nan_flow_backward_cases():
             out.append((c["spec"], c["sem"], c["kw"], c["T"], c["D"], c["threads"], True))
+        import test_gpu_open_window as ow
+
+        for sem, kw in ow.SEMS:
+            for name in ow.formulas():
+                out.append(("open", "window", name, sem, kw, 300, True))
+                out.append(("open", "window", name, sem, kw, 2048, True))
+                out.append(("open", "window", name, sem, kw, 2048, False))
+        for name in ow.until_formulas():
+            for T, force in ((300, True), (2048, True), (2048, False)):
+                out.append(("open", "until", name, "classical", {}, T, force))
     return out
 
 
@@ -73,7 +101,7 @@ def main(argv=None) -> int:
     bad = [(j, m) for j, (rc, m) in zip(todo, res) if rc not in (0, -2)]
     print(f"precompile: {ok} kernels cached, {unsup} on the interpreter tier, {len(bad)} failed, {time.time() - t0:.1f}s")
     for j, m in bad[:5]:
-        print("  FAILED", j[1], j[0], m[:300])
+        print("  FAILED", j[1], j[0] if j[0] != "open" else j[2:], m[:300])
     return 1 if bad else 0
 
 
