@@ -275,6 +275,15 @@ class OpenWindow(torch.autograd.Function):
         y, out, arg = ctx.saved_tensors
         return (open_window_grad(y, out, arg, grad_out, *ctx.params),) + (None,) * 6
 
+    generate_vmap_rule = False
+
+    @staticmethod
+    def vmap(info, in_dims, y, *params):  # traces are independent: a vmapped dimension folds into the batch
+        flat, n = _fold(y, in_dims[0])
+        out, arg = OpenWindow.apply(flat, *params)
+        arg = arg.reshape((n, -1) + tuple(arg.shape[1:])) if arg.numel() else arg.new_empty((n, 0))
+        return (out.reshape((n, -1) + tuple(out.shape[1:])), arg), (0, 0)
+
 
 def open_window(y: torch.Tensor, semantics: int, mode: int, start: int, temperature: float, eps: float, p: int,
                 nan_tail: bool = False) -> torch.Tensor:
@@ -353,6 +362,16 @@ class OpenUntil(torch.autograd.Function):
         gl, gr = open_until_grad(key, grad_out, ctx.semantics, ctx.start)
         return gl, gr, None, None
 
+    generate_vmap_rule = False
+
+    @staticmethod
+    def vmap(info, in_dims, left, right, semantics, start):
+        n = info.batch_size
+        lf = left.movedim(in_dims[0], 0) if in_dims[0] is not None else left.unsqueeze(0).expand((n,) + tuple(left.shape))
+        rt = right.movedim(in_dims[1], 0) if in_dims[1] is not None else right.unsqueeze(0).expand((n,) + tuple(right.shape))
+        out, key = OpenUntil.apply(lf.reshape((-1,) + tuple(lf.shape[2:])), rt.reshape((-1,) + tuple(rt.shape[2:])), semantics, start)
+        return (out.reshape((n, -1) + tuple(out.shape[1:])), key.reshape((n, -1) + tuple(key.shape[1:]))), (0, 0)
+
 
 def open_until(left: torch.Tensor, right: torch.Tensor, semantics: int, start: int) -> torch.Tensor:
     """Differentiable unbounded Until of the value traces ``left, right [B, T]`` read at ``t + start`` (classical semantics)."""
@@ -398,6 +417,14 @@ class Assemble(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
+        if torch._C._functorch.is_functorch_wrapped_tensor(grad):  # vmap(grad(...)): the same adjoint by (batchable) torch ops on the device
+            n = len(ctx.channels)
+            gs = None
+            if ctx.needs_input_grad[0]:
+                gs = grad.new_zeros(tuple(grad.shape[:-1]) + (ctx.D,))
+                if n:
+                    gs = gs.index_copy(-1, torch.tensor(ctx.channels, device=grad.device), grad[..., :n])
+            return (gs, None) + tuple(grad[..., n + j] for j in range(ctx.n_cols))
         g = grad.to(torch.float32).contiguous()
         B, T, _ = g.shape
         gs = g.new_empty((B, T, ctx.D)) if ctx.needs_input_grad[0] else None
@@ -410,6 +437,19 @@ class Assemble(torch.autograd.Function):
         capi.raise_for(rc, capi.lib().pystl_b200_last_error())
         return (gs, None) + tuple(gcols)
 
+    generate_vmap_rule = False
+
+    @staticmethod
+    def vmap(info, in_dims, signal, channels, *cols):
+        n = info.batch_size
+
+        def lead(x, d):
+            x = x.movedim(d, 0) if d is not None else x.unsqueeze(0).expand((n,) + tuple(x.shape))
+            return x.reshape((-1,) + tuple(x.shape[2:]))
+
+        out = Assemble.apply(lead(signal, in_dims[0]), channels, *[lead(c, d) for c, d in zip(cols, in_dims[2:])])
+        return out.reshape((n, -1) + tuple(out.shape[1:])), 0
+
 
 def assemble(signal: torch.Tensor, channels, cols) -> torch.Tensor:
     if not cols and tuple(channels) == tuple(range(signal.shape[-1])):
@@ -418,3 +458,25 @@ def assemble(signal: torch.Tensor, channels, cols) -> torch.Tensor:
         idx = torch.tensor([int(d) for d in channels], dtype=torch.long, device=signal.device)
         return torch.cat([signal.index_select(-1, idx)] + [c.unsqueeze(-1) for c in cols], dim=-1).contiguous()
     return Assemble.apply(signal, tuple(int(d) for d in channels), *cols)
+
+
+# ---- batching rules of the adjoint ops (vmap over a backward pass, e.g. vmap(grad(loss)))
+def _lead(x, d, n):
+    x = x.movedim(d, 0) if d is not None else x.unsqueeze(0).expand((n,) + tuple(x.shape))
+    return x.reshape((-1,) + tuple(x.shape[2:]))
+
+
+@torch.library.register_vmap("pystl_b200::open_window_grad")
+def _(info, in_dims, y, out, arg, grad_out, semantics, mode, start, temperature, eps, p):
+    n = info.batch_size
+    a = _lead(arg, in_dims[2], n) if arg.numel() else arg
+    g = open_window_grad(_lead(y, in_dims[0], n), _lead(out, in_dims[1], n), a, _lead(grad_out, in_dims[3], n),
+                         semantics, mode, start, temperature, eps, p)
+    return g.reshape((n, -1) + tuple(g.shape[1:])), 0
+
+
+@torch.library.register_vmap("pystl_b200::open_until_grad")
+def _(info, in_dims, key, grad_out, semantics, start):
+    n = info.batch_size
+    gl, gr = open_until_grad(_lead(key, in_dims[0], n), _lead(grad_out, in_dims[1], n), semantics, start)
+    return (gl.reshape((n, -1) + tuple(gl.shape[1:])), gr.reshape((n, -1) + tuple(gr.shape[1:]))), (0, 0)

@@ -336,6 +336,31 @@ def test_chunk_boundaries_and_degenerate_shapes(sem, kw):
     assert tuple(ops.open_window(torch.zeros(0, 300, device="cuda"), sem_id, 0, 2, tau, eps, p).shape) == (0, 300)
 
 
+def test_vmap_and_functional_grad_through_the_scan_route():
+    """``torch.func.vmap`` over traces and ``torch.func.grad`` compose with the open-ended route like with the formula
+    kernels (the precedent: jax.vmap over the reference's JAX backend, tests/test_jax_semantics.py:310-368)."""
+    x, y = preds32()
+    sig = torch.tensor(signal(5, 400, 31), device="cuda")
+    for sem, kw, phi in (("smooth", {"temperature": 0.5}, And(Always(x, Interval(3, None)), Eventually(y, Interval(0, 10)))),
+                         ("agm", {}, Eventually(Or(x, Not(y)), Interval(2, None))),
+                         ("classical", {}, And(Until(x, y, Interval(2, None)), Always(Not(y), Interval(1, None))))):
+        s = create_semantics(sem, backend="b200", **kw)
+        s.force_open_leaf = True
+        want = s.robustness_trace(phi, sig)
+        got = torch.func.vmap(lambda tr: s.robustness_trace(phi, tr))(sig)
+        assert torch.equal(torch.isfinite(got), torch.isfinite(want))
+        ok = torch.isfinite(want)
+        assert torch.equal(got[ok], want[ok]), sem
+
+        def loss(tr):
+            return torch.nan_to_num(s.robustness_trace(phi, tr)).sum()
+
+        xs = sig.clone().requires_grad_(True)
+        loss(xs).backward()
+        g_f = torch.func.vmap(torch.func.grad(loss))(sig)
+        assert torch.allclose(g_f, xs.grad, rtol=1e-6, atol=1e-7), sem
+
+
 def test_a_window_that_always_raises_is_nan_everywhere():
     # an operand that is itself undefined near the horizon makes the open-ended window raise at every t (api.py:218-221)
     x, _ = preds()
