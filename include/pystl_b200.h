@@ -94,6 +94,9 @@ typedef struct pystl_pred {
   int32_t slack; /* ABI 2.  0 for a predicate on the signal.  > 0: the channel holds values the host computed
                     (pystl_b200_open_window_forward) that do not exist at t > T-1-slack -- the reference raises
                     there (api.py:218-221) and the outputs that depend on them are NaN; -1: it raises for every t */
+  int32_t pair;  /* ABI 2, cumulative only.  1: the value is the PAIR (pos, neg) = (signal[t, channel[0]], signal[t, channel[1]])
+                    as it stands (n_terms = 2; coeff and bias unused) instead of (max(0, rho), min(0, rho)) of an affine rho
+                    (cumulative.py:24-30): how a host-computed cumulative value (an open-ended window) enters a formula */
 } pystl_pred_t;
 
 typedef struct pystl_formula {
@@ -184,7 +187,9 @@ int pystl_b200_fused_source(const pystl_formula_t* formula, int64_t T, int32_t D
  * with pystl_pred_t.slack = a.  Outputs at t > T-1-a (empty window) hold a finite filler for that kernel to read; mode + 2
  * writes NaN there instead (the window is the whole formula: NaN is what eval_forward writes where the reference raises).
  *   arg   int32[B, T], classical only (may be NULL otherwise): the window's arg-min / arg-max for the gradient
- * Cumulative values are pairs and are not offered here (PYSTL_E_UNSUPPORTED), nor are window weights. */
+ * PYSTL_SEM_CUMULATIVE works on ONE channel (pos or neg) of the pairs per call: Always is that channel's minimum
+ * (cumulative.py:35-46; needs arg), Eventually its SUM over the window (cumulative.py:62-73); the parent formula reads the two
+ * result channels through a pystl_pred_t with pair = 1.  Window weights are not offered here. */
 int pystl_b200_open_window_forward(int32_t semantics, int32_t mode, int32_t a, float temperature, float eps, int32_t p,
                                    const float* y, int64_t B, int64_t T, float* out, int32_t* arg, void* stream);
 /* grad_y[B, T] (fully overwritten) = d sum(grad_out * out) / d y over the outputs that exist (t <= T-1-a). */

@@ -45,6 +45,7 @@ class Pred(C.Structure):
         ("coeff", C.c_float * MAX_TERMS),
         ("bias", C.c_float),
         ("slack", C.c_int32),  # ABI 2: > 0 for a host-computed channel that ends before the horizon, -1 = never valid
+        ("pair", C.c_int32),   # ABI 2, cumulative: the value is (signal[t, channel[0]], signal[t, channel[1]]) as it stands
     ]
 
 

@@ -42,7 +42,7 @@ _SEM_IDS = {
 
 
 NEVER = 1 << 29  # start slack of a node the reference raises on at every t (lower.cpp: kNever)
-OPEN_LEAF_SEMANTICS = ("classical", "smooth", "agm", "dgmsr")  # cumulative values are pairs: not offered
+OPEN_LEAF_SEMANTICS = ("classical", "smooth", "agm", "dgmsr", "cumulative")
 
 
 @dataclass(frozen=True)
@@ -194,7 +194,8 @@ class CompiledFormula:
     channels_used: Tuple[int, ...]
     pred_terms: List[Tuple[Tuple[Tuple[int, float], ...], float]]
     n_signal_channels: int = 0   # channels of the user's signal
-    leaf_preds: Tuple[Any, ...] = ()  # non-affine predicates / OpenLeaf: leaf j is channel n_signal_channels + j
+    leaf_preds: Tuple[Any, ...] = ()  # non-affine predicates / OpenLeaf / OpenUntilLeaf, in column order
+    n_leaf_columns: int = 0  # one per leaf; two (pos, neg) for an open-ended window of the cumulative semantics
     has_open: bool = False  # an Always / Eventually without an end is evaluated inside the kernel (one tile)
     signal_channels: Tuple[int, ...] = ()  # channels of the user's signal the kernels read, in kernel order (leaves follow)
     root_leaf: Optional[int] = None  # the whole formula is leaf j (an open-ended window / until): no formula kernel runs
@@ -203,7 +204,7 @@ class CompiledFormula:
     @property
     def n_channels(self) -> int:
         """Channels of the tensor the kernels read (signal + leaf channels)."""
-        return len(self.signal_channels) + len(self.leaf_preds)
+        return len(self.signal_channels) + self.n_leaf_columns
 
     def ptr(self):
         return C.byref(self.struct)
@@ -222,6 +223,7 @@ def compile_formula(
 ) -> CompiledFormula:
     sem_id = _SEM_IDS[semantics]
     pred_slack: Dict[int, int] = {}
+    pred_pair: set = set()
     has_open = [False]
     nodes: List[capi.Node] = []
     children: List[int] = []
@@ -230,7 +232,16 @@ def compile_formula(
     pred_index: Dict[Any, int] = {}
     memo: Dict[int, int] = {}
     leaves: List[Any] = []
-    leaf_index: Dict[int, int] = {}
+    leaf_index: Dict[int, int] = {}  # id(fn) / id(node) -> first leaf COLUMN (a cumulative open-ended window has two: pos, neg)
+    leaf_first: List[int] = []       # first column of leaf j
+    n_cols = [0]
+
+    def add_leaf(key_: int, leaf: Any, width: int = 1) -> int:
+        leaf_index[key_] = n_cols[0]
+        leaf_first.append(n_cols[0])
+        leaves.append(leaf)
+        n_cols[0] += width
+        return leaf_index[key_]
     probed: List[Any] = []
     probed_seen: set = set()
 
@@ -262,7 +273,22 @@ def compile_formula(
         n.wp0 = n.wp1 = 1.0
         n.pred = -1
         kids: List[int] = []
-        if kind == "Predicate":
+        if kind == "Predicate" and "pair" in (getattr(node, "metadata", None) or {}):
+            # a cumulative value that already exists as two channels (pos, neg) of the signal: read as it stands
+            if semantics != "cumulative":
+                raise ValueError(f"Predicate '{node.name}': metadata['pair'] names a cumulative (pos, neg) value")
+            c0, c1 = (int(c) for c in node.metadata["pair"])
+            for d in (c0, c1):
+                if d < 0 or d >= n_channels:
+                    raise ValueError(f"Predicate '{node.name}' reads channel {d} of a {n_channels}-channel signal")
+            n.kind = capi.NODE_PRED
+            pkey = (((c0, 1.0), (c1, 1.0)), 0.0, "pair")
+            if pkey not in pred_index:
+                pred_index[pkey] = len(preds)
+                preds.append(pkey[:2])
+                pred_pair.add(pred_index[pkey])
+            n.pred = pred_index[pkey]
+        elif kind == "Predicate":
             n.kind = capi.NODE_PRED
             try:
                 if id(getattr(node, "fn", None)) in force_leaf:
@@ -276,13 +302,12 @@ def compile_formula(
                 # not affine: evaluated with torch on the device into leaf channel n_channels + j
                 fkey = id(node.fn)
                 if fkey not in leaf_index:
-                    leaf_index[fkey] = len(leaves)
-                    leaves.append(node)
+                    add_leaf(fkey, node)
                 terms, bias = ((n_channels + leaf_index[fkey], 1.0),), 0.0
             if len(terms) > capi.MAX_TERMS:
                 raise NotImplementedError(f"Predicate '{node.name}' has more than {capi.MAX_TERMS} terms")
             for d, _ in terms:
-                if d < 0 or d >= n_channels + len(leaves):
+                if d < 0 or d >= n_channels + n_cols[0]:
                     raise ValueError(f"Predicate '{node.name}' reads channel {d} of a {n_channels}-channel signal")
             pkey = (terms, bias)
             if pkey not in pred_index:
@@ -308,12 +333,17 @@ def compile_formula(
             if node.weights is not None:
                 raise NotImplementedError(f"{kind} without an interval end on a trace longer than one tile takes no weights")
             n.kind = capi.NODE_PRED
-            leaf_index[key] = len(leaves)
-            leaves.append(OpenLeaf(node.child, 0 if kind == "Always" else 1, a))
-            pkey = (((n_channels + leaf_index[key], 1.0),), 0.0)
-            pred_index[pkey] = len(preds)
+            if semantics == "cumulative":  # the window of a (pos, neg) trace is two columns, read back as a pair predicate
+                col = add_leaf(key, OpenLeaf(node.child, 0 if kind == "Always" else 1, a), width=2)
+                pkey = (((n_channels + col, 1.0), (n_channels + col + 1, 1.0)), 0.0)
+            else:
+                col = add_leaf(key, OpenLeaf(node.child, 0 if kind == "Always" else 1, a))
+                pkey = (((n_channels + col, 1.0),), 0.0)
+            pred_index[pkey + ("leaf",)] = len(preds)
             preds.append(pkey)
-            n.pred = pred_index[pkey]
+            n.pred = len(preds) - 1
+            if semantics == "cumulative":
+                pred_pair.add(n.pred)
             pred_slack[n.pred] = a if start_slack(node.child) == 0 else -1
         elif kind in ("Always", "Eventually"):
             n.kind = capi.NODE_ALWAYS if kind == "Always" else capi.NODE_EVENTUALLY
@@ -328,9 +358,8 @@ def compile_formula(
                 raise NotImplementedError(
                     f"Until without an interval end on a trace longer than one tile: classical semantics only ({semantics}: O(T^2) per trace)"
                 )
-            leaf_index[key] = len(leaves)
-            leaves.append(OpenUntilLeaf(node.left, node.right, a))
-            pkey = (((n_channels + leaf_index[key], 1.0),), 0.0)
+            col = add_leaf(key, OpenUntilLeaf(node.left, node.right, a))
+            pkey = (((n_channels + col, 1.0),), 0.0)
             pred_index[pkey] = len(preds)
             preds.append(pkey)
             pred_slack[pred_index[pkey]] = a if max(start_slack(node.left), start_slack(node.right)) == 0 else -1
@@ -379,15 +408,15 @@ def compile_formula(
     if leaves:
         signal_channels = tuple(sorted({d for terms, _ in preds for d, _ in terms if d < n_channels}))
         remap = {d: i for i, d in enumerate(signal_channels)}
-        remap.update({n_channels + j: len(signal_channels) + j for j in range(len(leaves))})
+        remap.update({n_channels + j: len(signal_channels) + j for j in range(n_cols[0])})
         preds = [(tuple((remap[d], c) for d, c in terms), bias) for terms, bias in preds]
     root = nodes[-1]
     root_leaf = None
-    if leaves and root.kind == capi.NODE_PRED:
+    if leaves and root.kind == capi.NODE_PRED and len(nodes) == 1:
         terms, bias = preds[root.pred]
-        j = terms[0][0] - len(signal_channels) if len(terms) == 1 else -1
-        if j >= 0 and terms[0][1] == 1.0 and bias == 0.0 and isinstance(leaves[j], (OpenLeaf, OpenUntilLeaf)):
-            root_leaf = j
+        col = terms[0][0] - len(signal_channels)
+        if col in leaf_first and isinstance(leaves[leaf_first.index(col)], (OpenLeaf, OpenUntilLeaf)):
+            root_leaf = leaf_first.index(col)
 
     node_arr = (capi.Node * len(nodes))(*nodes)
     child_arr = (C.c_int32 * max(len(children), 1))(*children)
@@ -402,6 +431,7 @@ def compile_formula(
             used.add(d)
         pred_arr[i].bias = bias
         pred_arr[i].slack = pred_slack.get(i, 0)
+        pred_arr[i].pair = 1 if i in pred_pair else 0
     st = capi.Formula()
     st.semantics = sem_id
     st.temperature = float(temperature)
@@ -426,6 +456,7 @@ def compile_formula(
         pred_terms=preds,
         n_signal_channels=int(n_channels),
         leaf_preds=tuple(leaves),
+        n_leaf_columns=n_cols[0],
         probed_preds=tuple(probed),
         has_open=has_open[0],
         signal_channels=signal_channels,
@@ -452,6 +483,9 @@ def leaf_column(cf: CompiledFormula, pred: Any, sig, sem=None, nan_tail: bool = 
             yl, yr = sem.robustness_trace(pred.left, sig), sem.robustness_trace(pred.right, sig)
             return ops.open_until(yl.contiguous(), yr.contiguous(), cf.struct.semantics, pred.start)
         y = sem.robustness_trace(pred.child, sig)  # [B, T]; nested open-ended windows recurse here
+        if cf.struct.semantics == capi.SEM_CUMULATIVE:  # each channel of the pairs on its own: minimum (Always) / sum (Eventually)
+            return tuple(ops.open_window(ch.contiguous(), cf.struct.semantics, pred.mode, pred.start, 1.0, 1e-8, 1, nan_tail=nan_tail)
+                         for ch in (y.pos, y.neg))
         return ops.open_window(y.contiguous(), cf.struct.semantics, pred.mode, pred.start,
                                cf.struct.temperature, cf.struct.eps, cf.struct.p, nan_tail=nan_tail)
     fn = pred.fn
@@ -484,5 +518,8 @@ def leaf_values(cf: CompiledFormula, sig, sem=None):
         return sig
     from . import ops
 
-    cols = [leaf_column(cf, pred, sig, sem) for pred in cf.leaf_preds]
+    cols = []
+    for pred in cf.leaf_preds:
+        c = leaf_column(cf, pred, sig, sem)
+        cols.extend(c if isinstance(c, tuple) else (c,))
     return ops.assemble(sig, cf.signal_channels, cols)

@@ -393,6 +393,13 @@ struct Gen {
         return std::string(b);
       };
       const bool f64 = P.sem == SEM_CLASSIC && pr.f64;
+      if (pr.pair) {
+        o.line("v%d[i] = V{{%s, %s}};  // a cumulative value computed by the host: (pos, neg) as they stand", (int)pr.dst, term(0).c_str(),
+               term(1).c_str());
+        o.indent--;
+        o.line("}");
+        continue;
+      }
       if (f64) {
         // same operations and order as the reference's float64 evaluation, one final rounding
         o.line("double a = 0.0;");
@@ -1217,7 +1224,9 @@ struct Gen {
           for (int k = 0; k < P.preds[q].n_terms; ++k)
             if (P.preds[q].ch[k] == d) {
               char b[96];
-              if (cum_bwd())
+              if (P.preds[q].pair)
+                snprintf(b, sizeof(b), "%sg%d[i].x[%d]", e.empty() ? "" : " + ", (int)P.preds[q].dst, k);
+              else if (cum_bwd())
                 snprintf(b, sizeof(b), "%sP.preds[%d].coeff[%d] * cum_pred_adj(v%d[i], g%d[i])", e.empty() ? "" : " + ", q, k, (int)P.preds[q].dst,
                          (int)P.preds[q].dst);
               else
@@ -1236,7 +1245,9 @@ struct Gen {
           for (int k = 0; k < P.preds[q].n_terms; ++k)
             if (P.preds[q].ch[k] == d) {
               char b[96];
-              if (cum_bwd())
+              if (P.preds[q].pair)
+                snprintf(b, sizeof(b), "%sg%d[i].x[%d]", e.empty() ? "" : " + ", (int)P.preds[q].dst, k);
+              else if (cum_bwd())
                 snprintf(b, sizeof(b), "%sP.preds[%d].coeff[%d] * cum_pred_adj(v%d[i], g%d[i])", e.empty() ? "" : " + ", q, k, (int)P.preds[q].dst,
                          (int)P.preds[q].dst);
               else

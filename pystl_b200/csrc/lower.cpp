@@ -86,11 +86,12 @@ struct Lowerer {
       p.coeff[k] = negate ? -src.coeff[k] : src.coeff[k];
     }
     p.bias = negate ? -src.bias : src.bias;
+    p.pair = src.pair ? 1 : 0;  // (never negated: resolve() keeps the NOT above a pair)
     // +0.0 / -0.0 biases are the same predicate
     if (p.bias == 0.f) p.bias = 0.f;
     for (int q = 0; q < P().n_preds; ++q) {
       const TPred& o = P().preds[q];
-      if (o.n_terms != p.n_terms || o.bias != p.bias) continue;  // (f64 is a function of these)
+      if (o.n_terms != p.n_terms || o.bias != p.bias || o.pair != p.pair) continue;  // (f64 is a function of these)
       bool same = true;
       for (int k = 0; k < p.n_terms && same; ++k) same = o.ch[k] == p.ch[k] && o.coeff[k] == p.coeff[k];
       if (same) return q;
@@ -182,7 +183,7 @@ struct Lowerer {
       v.is_pred = true;
     } else if (nd.kind == PYSTL_NODE_NOT) {
       const int ch = child(i, 0);
-      if (f->nodes[ch].kind == PYSTL_NODE_PRED) {  // fold the negation into the coefficients
+      if (f->nodes[ch].kind == PYSTL_NODE_PRED && !f->preds[f->nodes[ch].pred].pair) {  // fold the negation into the coefficients
         v.owner = find_or_add_pred(f->preds[f->nodes[ch].pred], true);
         v.is_pred = true;
       } else {
@@ -256,6 +257,11 @@ struct Lowerer {
           if (nd.pred < 0 || nd.pred >= f->n_preds) fail(PYSTL_E_INVALID, "node %d: predicate index out of range", i);
           const pystl_pred_t& pr = f->preds[nd.pred];
           if (pr.n_terms < 0 || pr.n_terms > kMaxTerms) fail(PYSTL_E_UNSUPPORTED, "predicate with more than %d terms", kMaxTerms);
+          if (pr.pair) {
+            if (sem != SEM_CUMULATIVE) fail(PYSTL_E_INVALID, "node %d: a pair predicate is a cumulative value", i);
+            if (pr.n_terms != 2) fail(PYSTL_E_INVALID, "node %d: a pair predicate names two channels (pos, neg)", i);
+            if (!ssa) fail(PYSTL_E_UNSUPPORTED, "pair predicates (host-computed cumulative values) need the fused tier (NVRTC)");
+          }
           // a channel of values the host computed (open-ended window beyond one tile) that end before the horizon
           slack[i] = pr.slack < 0 ? kNever : std::min(pr.slack, kNever);
           break;

@@ -63,7 +63,8 @@ enum TOp : int32_t {
 struct TPred {
   int16_t dst;  // plane slot
   int16_t n_terms;
-  int32_t f64;  // classic only: evaluate in float64 and round once (bit-exact against the float64 reference)
+  int16_t f64;  // classic only: evaluate in float64 and round once (bit-exact against the float64 reference)
+  int16_t pair; // cumulative only: the value is (signal[ch[0]], signal[ch[1]]) as it stands (a host-computed cumulative value)
   int16_t ch[kMaxTerms];
   float coeff[kMaxTerms];
   float bias;

@@ -43,6 +43,16 @@ struct ScanRed {  // agm, dgmsr: the reducers of the formula kernels
   static __device__ int arg(A) { return 0; }
 };
 template <int MODE>
+struct ScanRed<SEM_CUMULATIVE, MODE> {  // one channel (pos or neg) of a cumulative value: Eventually SUMS the window (cumulative.py:62-73)
+  using A = Vec<1>;                     // (Always is the minimum per channel, cumulative.py:35-46: the Classic kernels serve it)
+  static __device__ A ident() { return A{{0.f}}; }
+  static __device__ A lift(float y, int, const RP&) { return A{{y}}; }
+  static __device__ A comb(A a, A b) { return A{{a.x[0] + b.x[0]}}; }
+  static __device__ A push(A l, A acc) { return A{{l.x[0] + acc.x[0]}}; }
+  static __device__ float fin(A a, float, const RP&) { return a.x[0]; }
+  static __device__ int arg(A) { return 0; }
+};
+template <int MODE>
 struct ScanRed<SEM_DGMSR, MODE> {  // the formula kernels' reducer; fin BRANCHES on the flag instead of evaluating both means
   using R = Red<SEM_DGMSR, MODE>;  // (a long suffix almost always holds a non-positive entry: rcp + sqrt instead of seven MUFU ops)
   using A = typename R::A;
@@ -304,6 +314,15 @@ struct ScanAdj {  // agm, dgmsr
   static __device__ float apply(A w, float y, const RP& rp) { return AD::in_factor(w, y, 1.f, rp); }
 };
 template <int MODE>
+struct ScanAdj<SEM_CUMULATIVE, MODE> {  // d sum / d y_k = 1: the prefix sum of the cotangents
+  using A = Vec<1>;
+  static __device__ A ident() { return A{{0.f}}; }
+  static __device__ A coeff(float g, float, float, const RP&) { return A{{g}}; }
+  static __device__ A comb(A a, A b) { return A{{a.x[0] + b.x[0]}}; }
+  static __device__ A push(A acc, A l) { return A{{acc.x[0] + l.x[0]}}; }
+  static __device__ float apply(A w, float, const RP&) { return w.x[0]; }
+};
+template <int MODE>
 struct ScanAdj<SEM_SMOOTH, MODE> {  // d out_t / d y_k = 2^(k (out_t - y_k)) (AND), 2^(k (y_k - out_t)) (OR): <= 1, exact
   using A = Vec<2>;                 // (m, s): sum of g_t 2^(e_t) = s * 2^m, e_t = +- k out_t
   static __device__ A ident() { return A{{-f_inf(), 0.f}}; }
@@ -508,8 +527,8 @@ RP make_rp(float temperature, float eps, int p) {
 }
 
 int check(int semantics, int mode, int a, long long B, long long T, float temperature, float eps, int p) {
-  if (semantics != SEM_CLASSIC && semantics != SEM_SMOOTH && semantics != SEM_AGM && semantics != SEM_DGMSR)
-    return scan_fail(PYSTL_E_UNSUPPORTED, "open-ended windows beyond one tile: classical, smooth, agm and dgmsr (cumulative values are pairs)");
+  if (semantics != SEM_CLASSIC && semantics != SEM_SMOOTH && semantics != SEM_AGM && semantics != SEM_DGMSR && semantics != SEM_CUMULATIVE)
+    return scan_fail(PYSTL_E_INVALID, "unknown semantics %d", semantics);
   if (mode < 0 || mode > 3) return scan_fail(PYSTL_E_INVALID, "mode must be 0 (always) or 1 (eventually), + 2 for a NaN tail");
   if (a < 0) return scan_fail(PYSTL_E_INVALID, "Interval start must be >= 0.");
   if (B < 0 || T < 0 || T >= (1ll << 31) - 65536) return scan_fail(PYSTL_E_INVALID, "bad shape");
@@ -545,9 +564,10 @@ int open_window_forward(int32_t semantics, int32_t mode, int32_t a, float temper
   g_err_cap = err_cap;
   int rc = check(semantics, mode, a, B, T, temperature, eps, p);
   if (rc) return rc;
+  if (semantics == SEM_CUMULATIVE && (mode & 1) == 0) semantics = SEM_CLASSIC;  // Always: the minimum of the channel
   if (B == 0 || T == 0) return PYSTL_OK;
   if (!y || !out) return scan_fail(PYSTL_E_INVALID, "null buffer");
-  if (semantics == SEM_CLASSIC && !arg) return scan_fail(PYSTL_E_INVALID, "classical needs the arg buffer");
+  if (semantics == SEM_CLASSIC && !arg) return scan_fail(PYSTL_E_INVALID, "a minimum / maximum needs the arg buffer");
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
     cudaGetLastError();
@@ -558,7 +578,12 @@ int open_window_forward(int32_t semantics, int32_t mode, int32_t a, float temper
   int* argp = semantics == SEM_CLASSIC ? arg : nullptr;
   const int nan_tail = (mode >> 1) & 1;
   mode &= 1;
-  PYSTL_SCAN_DISPATCH(open_window_fwd, y, out, argp, (long long)B, (int)T, (int)a, rp, nan_tail);
+  if (semantics == SEM_CUMULATIVE) {  // (y is one channel of the pairs) Eventually: the window's sum
+    const unsigned grid = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    open_window_fwd<SEM_CUMULATIVE, MODE_OR><<<grid, 32 * kWarpsPerBlock, 0, st>>>(y, out, nullptr, (long long)B, (int)T, (int)a, rp, nan_tail);
+  } else {
+    PYSTL_SCAN_DISPATCH(open_window_fwd, y, out, argp, (long long)B, (int)T, (int)a, rp, nan_tail);
+  }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "open_window_fwd: %s", cudaGetErrorString(e));
   return PYSTL_OK;
@@ -574,6 +599,7 @@ int open_window_backward(int32_t semantics, int32_t mode, int32_t a, float tempe
   if (B == 0 || T == 0) return PYSTL_OK;
   if (!y || !out || !grad_out || !grad_y) return scan_fail(PYSTL_E_INVALID, "null buffer");
   mode &= 1;
+  if (semantics == SEM_CUMULATIVE && mode == 0) semantics = SEM_CLASSIC;  // Always: the minimum of the channel
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
     cudaGetLastError();
@@ -597,6 +623,8 @@ int open_window_backward(int32_t semantics, int32_t mode, int32_t a, float tempe
   } while (0)
     if (semantics == SEM_SMOOTH) PYSTL_BWD(SEM_SMOOTH);
     else if (semantics == SEM_AGM) PYSTL_BWD(SEM_AGM);
+    else if (semantics == SEM_CUMULATIVE)
+      open_window_bwd<SEM_CUMULATIVE, MODE_OR><<<grid, block, 0, st>>>(y, out, grad_out, grad_y, (long long)B, (int)T, (int)a, rp);
     else PYSTL_BWD(SEM_DGMSR);
 #undef PYSTL_BWD
   }

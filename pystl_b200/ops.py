@@ -208,12 +208,17 @@ def _check_trace(y: torch.Tensor) -> None:
         raise ValueError("the value trace must be float32 with shape (batch, time)")
 
 
+def _needs_arg(semantics: int, mode: int) -> bool:
+    """Minima / maxima record where they came from: classical, and Always on a channel of cumulative pairs."""
+    return semantics == capi.SEM_CLASSIC or (semantics == capi.SEM_CUMULATIVE and (mode & 1) == 0)
+
+
 def _open_window_fwd_cuda(y, semantics, mode, start, temperature, eps, p):
     _check_trace(y)
     y = y.contiguous()
     B, T = y.shape
     out = torch.empty_like(y)
-    arg = torch.empty((B, T) if semantics == capi.SEM_CLASSIC else (0,), dtype=torch.int32, device=y.device)
+    arg = torch.empty((B, T) if _needs_arg(semantics, mode) else (0,), dtype=torch.int32, device=y.device)
     with torch.cuda.device(y.device):
         rc = capi.lib().pystl_b200_open_window_forward(int(semantics), int(mode), int(start), float(temperature), float(eps), int(p),
                                                        y.data_ptr(), B, T, out.data_ptr(), arg.data_ptr() if arg.numel() else None,
@@ -247,7 +252,7 @@ open_window_grad = torch.ops.pystl_b200.open_window_grad
 
 @torch.library.register_fake("pystl_b200::open_window_fwd")
 def _(y, semantics, mode, start, temperature, eps, p):
-    return torch.empty_like(y), y.new_empty(tuple(y.shape) if semantics == capi.SEM_CLASSIC else (0,), dtype=torch.int32)
+    return torch.empty_like(y), y.new_empty(tuple(y.shape) if _needs_arg(semantics, mode) else (0,), dtype=torch.int32)
 
 
 @torch.library.register_fake("pystl_b200::open_window_grad")

@@ -225,7 +225,7 @@ class _B200Semantics(_ReferenceSemantics):
         sig, squeeze, home = self._prepare(signal)  # (stays connected to `signal` in the autograd graph)
         cf = self._checked_compile(formula, sig)
         if cf.root_leaf is not None:  # the formula IS one open-ended window / until: the scan kernels write its robustness
-            out = self._root_leaf_trace(cf, sig, nan_tail=True).unsqueeze(-1)
+            out = self._root_leaf_trace(cf, sig, nan_tail=True)
         else:
             if cf.leaf_preds:  # non-affine predicates: leaf channels computed by torch, inside the graph
                 sig = leaf_values(cf, sig, self)
@@ -239,11 +239,13 @@ class _B200Semantics(_ReferenceSemantics):
         return out[..., 0]
 
     def _root_leaf_trace(self, cf: CompiledFormula, sig: torch.Tensor, nan_tail: bool) -> torch.Tensor:
-        """``[B, T]`` robustness of a formula whose root is an open-ended window / until leaf (``cf.root_leaf``): the scan
+        """``[B, T, C]`` robustness of a formula whose root is an open-ended window / until leaf (``cf.root_leaf``): the scan
         kernels' output, no formula kernel and no assembled input tensor.  ``slack = -1``: the reference raises at every t."""
         if cf.preds[0].slack < 0:
-            return torch.full(sig.shape[:2], float("nan"), dtype=torch.float32, device=sig.device) + 0.0 * sig[..., 0]
-        return leaf_column(cf, cf.leaf_preds[cf.root_leaf], sig, self, nan_tail=nan_tail)
+            nan = torch.full(sig.shape[:2], float("nan"), dtype=torch.float32, device=sig.device) + 0.0 * sig[..., 0]
+            return torch.stack([nan] * self.out_channels, dim=-1)
+        col = leaf_column(cf, cf.leaf_preds[cf.root_leaf], sig, self, nan_tail=nan_tail)
+        return torch.stack(col, dim=-1) if isinstance(col, tuple) else col.unsqueeze(-1)  # [B, T, C]
 
     def _root_leaf_valid(self, cf: CompiledFormula, T: int) -> int:
         slack = cf.preds[0].slack
@@ -263,7 +265,7 @@ class _B200Semantics(_ReferenceSemantics):
             valid = self._root_leaf_valid(cf, sig.shape[1])
             with torch.no_grad():
                 if valid > 0:
-                    acc[0] = self._root_leaf_trace(cf, sig, nan_tail=False)[:, :valid].sum(dim=1).sum(dtype=torch.float64)
+                    acc[0] = self._root_leaf_trace(cf, sig, nan_tail=False)[:, :valid].sum(dim=(1, 2)).sum(dtype=torch.float64)
             acc[1] = float(sig.shape[0] * valid)
             return all_reduce_mean(acc, group=group)
         plan = self.plan(formula, sig.shape[1], sig.shape[2], cf)
@@ -297,7 +299,7 @@ class _B200Semantics(_ReferenceSemantics):
                 base = sig.detach().requires_grad_(True)
                 with torch.enable_grad():
                     # (row sums in fp32, their sum in float64: summing with dtype=float64 materialises a float64 copy of the trace)
-                    total = self._root_leaf_trace(cf, base, nan_tail=False)[:, :valid].sum(dim=1).sum(dtype=torch.float64)
+                    total = self._root_leaf_trace(cf, base, nan_tail=False)[:, :valid].sum(dim=(1, 2)).sum(dtype=torch.float64)
                 (grad,) = torch.autograd.grad(total, base, torch.tensor((1.0 / n_total) if n_total > 0 else 0.0, dtype=torch.float64,
                                                                         device=sig.device))
                 acc[0] = total.detach()

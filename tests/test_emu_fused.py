@@ -183,3 +183,34 @@ def test_classic_until_tie_routing_touches_active_leaves_only():
     from test_emu_backward import tie_routing_report
 
     tie_routing_report(lambda spec, sig, g: fused_emu_lib.eval_backward(from_spec(spec), "classical", sig, g))
+
+
+# ---------------------------------------------------------------------------- pair predicates (host-computed cumulative values)
+@pytest.mark.parametrize("threads", [0, 64])
+def test_cumulative_pair_predicates_read_the_channels_as_they_stand(threads):
+    """``pystl_pred_t.pair``: a cumulative value that already exists as two channels (pos, neg) -- how an open-ended window
+    computed by the scan kernels enters a formula.  Feeding (max(0, v), min(0, v)) of an affine v through pair predicates must
+    reproduce the formula over the affine predicates (cumulative.py:24-30), values and gradients (chain rule through the
+    max / min by hand)."""
+    from pystl_b200.formula import Always, And, Eventually, Interval, Not, Or, Predicate, Until, affine_predicate
+
+    rng = np.random.default_rng(4)
+    B, T = 3, 700
+    v = (0.6 * rng.standard_normal((B, T, 2))).astype(np.float32)
+    sig4 = np.stack([np.maximum(v[..., 0], 0), np.minimum(v[..., 0], 0), np.maximum(v[..., 1], 0), np.minimum(v[..., 1], 0)], -1)
+    x, y = affine_predicate("x", {0: 1.0}, 0.0), affine_predicate("y", {1: 1.0}, 0.0)
+    px, py = Predicate("px", metadata={"pair": (0, 1)}), Predicate("py", metadata={"pair": (2, 3)})
+
+    def build(a, b):
+        return Or(Always(And(a, Not(b)), Interval(0, 7)), Eventually(Until(a, b, Interval(0, 5)), Interval(2, 9)))
+
+    ref = fused_emu_lib.eval_forward(build(x, y), "cumulative", v, force_threads=threads)
+    got = fused_emu_lib.eval_forward(build(px, py), "cumulative", sig4.astype(np.float32), force_threads=threads)
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), ok) and np.array_equal(got[ok], ref[ok])
+    go = rng.uniform(0.25, 1.0, size=ref.shape).astype(np.float32)
+    g_ref = fused_emu_lib.eval_backward(build(x, y), "cumulative", v, go, force_threads=threads)
+    g = fused_emu_lib.eval_backward(build(px, py), "cumulative", sig4.astype(np.float32), go, force_threads=threads)
+    for d in (0, 1):
+        chained = g[..., 2 * d] * (v[..., d] > 0) + g[..., 2 * d + 1] * (v[..., d] < 0)
+        assert np.allclose(chained, g_ref[..., d], rtol=1e-6, atol=1e-6)  # (one ulp: the affine path contracts coeff * (g+ d+ + g- d-) differently)

@@ -32,6 +32,11 @@ def preds():
     return x, y
 
 
+def preds32():
+    # coefficients that are float32 numbers: the classical kernels are bit-exact against float32(float64 reference)
+    return affine_predicate("x", {0: 1.0}, 0.125), affine_predicate("y", {1: -1.0, 0: 0.25}, 0.375)
+
+
 def formulas():
     x, y = preds()
     return {
@@ -190,12 +195,78 @@ def test_long_trace_properties(sem, kw):
     assert torch.allclose(grad, xs.grad, rtol=1e-4, atol=1e-6 * float(xs.grad.abs().max()) + 1e-12)
 
 
+# ---------------------------------------------------------------------------- cumulative: (pos, neg) pairs
+def cumulative_formulas():
+    x, y = preds32()
+    return {
+        "G_open": Always(x, Interval(0, None)),
+        "F_open_a": Eventually(y, Interval(7, None)),
+        "mixed": And(Always(x, Interval(3, None)), Eventually(y, Interval(0, 10))),
+        "under_window": Eventually(Always(Or(x, Not(y)), Interval(2, None)), Interval(0, 5)),
+        "negated": Not(Eventually(And(x, y), Interval(1, None))),
+        "nested": Always(Eventually(x, Interval(0, None)), Interval(2, None)),
+        "over_until": Eventually(Until(x, y, Interval(0, 6)), Interval(5, None)),
+    }
+
+
+@pytest.mark.parametrize("name", list(cumulative_formulas()))
+def test_cumulative_scan_path_against_the_oracle(name):
+    """Cumulative values are (pos, neg) pairs (cumulative.py:13-18): Always is the minimum of each channel, Eventually its SUM
+    (cumulative.py:35-46, 62-73); the window's two columns come back into the formula through a pair predicate."""
+    T = 300
+    phi = cumulative_formulas()[name]
+    sig = signal(3, T, 13)
+    s = create_semantics("cumulative", backend="b200")
+    s.force_open_leaf = True
+    x = torch.tensor(sig, device="cuda", requires_grad=True)
+    cf = s._checked_compile(phi, x.detach())
+    assert any(isinstance(p, OpenLeaf) for p in cf.leaf_preds) and cf.n_leaf_columns == 2 * len(cf.leaf_preds)
+    r = s.robustness_trace(phi, x)
+    got = torch.stack((r.pos, r.neg), 0)
+    x64 = torch.tensor(sig, dtype=torch.float64, requires_grad=True)
+    want = dense.robustness_trace(phi, x64, dense.make("cumulative"))
+    ok = torch.isfinite(want)
+    assert torch.equal(torch.isfinite(got.detach().cpu()), ok)
+    assert torch.allclose(got.detach().cpu().double()[ok], want.detach()[ok], rtol=1e-5, atol=5e-6)
+    g = torch.tensor(np.random.default_rng(3).uniform(0.25, 1.0, size=tuple(want.shape)))
+    (torch.nan_to_num(got) * g.to("cuda", torch.float32)).sum().backward()
+    (torch.nan_to_num(want) * g).sum().backward()
+    scale = float(x64.grad.abs().max()) + 1e-12
+    assert torch.allclose(x.grad.cpu().double(), x64.grad, rtol=4e-5, atol=4e-5 * scale)
+    mean, grad = s.mean_robustness_and_grad(phi, torch.tensor(sig, device="cuda"))
+    x2 = torch.tensor(sig, dtype=torch.float64, requires_grad=True)
+    w2 = dense.robustness_trace(phi, x2, dense.make("cumulative")).sum(0)
+    m2 = w2[torch.isfinite(w2)].mean()
+    m2.backward()
+    assert abs(float(mean) - float(m2.detach())) < 1e-5 * (1 + abs(float(m2.detach())))
+    assert torch.allclose(grad.cpu().double(), x2.grad, rtol=4e-5, atol=4e-5 * (float(x2.grad.abs().max()) + 1e-12))
+    assert abs(float(s.mean_robustness(phi, torch.tensor(sig, device="cuda"))) - float(m2.detach())) < 1e-5 * (1 + abs(float(m2.detach())))
+
+
+def test_cumulative_long_traces_against_closed_forms():
+    B, T, a = 4, 20000, 11
+    x, _ = preds32()
+    sig = signal(B, T, 9)
+    s = create_semantics("cumulative", backend="b200")
+    x64 = torch.tensor(sig, dtype=torch.float64)
+    v = x64[..., 0] + 0.125
+    pos, neg = torch.clamp(v, min=0.0), torch.clamp(v, max=0.0)
+    for kind, phi in (("G", Always(x, Interval(a, None))), ("F", Eventually(x, Interval(a, None)))):
+        r = s.robustness_trace(phi, torch.tensor(sig, device="cuda"))
+        assert s.plan(phi, T, 2)["start_slack"] == a
+        for got, ch in ((r.pos, pos), (r.neg, neg)):
+            fl = torch.flip(ch, dims=(1,))
+            full = torch.flip(torch.cummin(fl, 1).values if kind == "G" else torch.cumsum(fl, 1), dims=(1,))
+            want = torch.full_like(full, float("nan"))
+            want[:, : T - a] = full[:, a:]
+            ok = torch.isfinite(want)
+            assert torch.equal(torch.isfinite(got.cpu()), ok)
+            assert torch.allclose(got.cpu().double()[ok], want[ok], rtol=1e-5, atol=5e-6), (kind, float((got.cpu().double()[ok] - want[ok]).abs().max()))
+    with pytest.raises(NotImplementedError):  # the cumulative Until without an end stays inside one tile
+        s.robustness_trace(Until(x, x, Interval(0, None)), torch.tensor(sig, device="cuda"))
+
+
 # ---------------------------------------------------------------------------- classical Until without an end
-def preds32():
-    # coefficients that are float32 numbers: the classical kernels are bit-exact against float32(float64 reference)
-    return affine_predicate("x", {0: 1.0}, 0.125), affine_predicate("y", {1: -1.0, 0: 0.25}, 0.375)
-
-
 def until_formulas():
     x, y = preds32()
     return {
@@ -377,8 +448,6 @@ def test_a_window_that_always_raises_is_nan_everywhere():
 def test_unsupported_cases_are_loud():
     x, y = preds()
     sig = torch.zeros(1, 20000, 2, device="cuda")
-    with pytest.raises(NotImplementedError):
-        create_semantics("cumulative", backend="b200").robustness_trace(Always(x, Interval(0, None)), sig)
     with pytest.raises(NotImplementedError):
         create_semantics("agm", backend="b200").robustness_trace(Always(x, Interval(0, None), weights=[1.0] * 20000), sig)
     with pytest.raises(NotImplementedError):  # the non-classical Until without an end is O(T^2) per trace: one tile only

@@ -115,7 +115,7 @@ def test_header_and_library_agree():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.pystl_b200_abi_version() == capi.ABI_VERSION
-    assert C.sizeof(capi.Node) == 48 and C.sizeof(capi.Pred) == 76  # ABI 2: + slack
+    assert C.sizeof(capi.Node) == 48 and C.sizeof(capi.Pred) == 80  # ABI 2: + slack, pair
 
 
 def test_open_ended_windows_beyond_one_tile_become_leaf_channels():
@@ -152,10 +152,17 @@ def test_open_ended_windows_beyond_one_tile_become_leaf_channels():
         assert start_slack(never) == NEVER
         assert sem.plan(never, 2048, 2)["raises_always"] == sem.plan(never, 20000, 2)["raises_always"] == 1
         assert sem.compile(never, 2, open_leaf=True).preds[0].slack == -1
+    # cumulative values are (pos, neg) pairs: the window is two leaf columns, read back by a PAIR predicate
     cum = create_semantics("cumulative", backend="b200")
-    assert cum.plan(phi, 2048, 2)["n_tiles"] == 1
-    with pytest.raises(NotImplementedError):
-        cum.plan(phi, 20000, 2)
+    assert cum.plan(phi, 20000, 2)["n_tiles"] > 1 and cum.plan(phi, 20000, 2)["start_slack"] == 3
+    ccf = cum.compile(phi, 2, open_leaf=True)
+    assert ccf.n_leaf_columns == 2 and ccf.signal_channels == (1,) and ccf.n_channels == 3
+    pairs = [(ccf.preds[i].pair, ccf.preds[i].n_terms, ccf.preds[i].slack) for i in range(ccf.struct.n_preds)]
+    assert sorted(pairs) == [(0, 1, 0), (1, 2, 3)]
+    with pytest.raises(NotImplementedError):  # the cumulative Until without an end stays inside one tile
+        cum.plan(Until(x, y, Interval(0, None)), 20000, 2)
+    with pytest.raises(ValueError):  # a pair is a cumulative value
+        create_semantics("smooth", backend="b200").compile(Predicate("p", metadata={"pair": (0, 1)}), 2)
     with pytest.raises(NotImplementedError):  # window weights are per position of the clipped window
         create_semantics("agm", backend="b200").plan(Always(x, Interval(0, None), weights=[1.0] * 20000), 20000, 2)
     # Until without an end: classical only (a clamp-composition scan); U[a, inf) = min(G[0, a] left, W(t + a))
