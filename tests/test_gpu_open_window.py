@@ -407,6 +407,95 @@ def test_chunk_boundaries_and_degenerate_shapes(sem, kw):
     assert tuple(ops.open_window(torch.zeros(0, 300, device="cuda"), sem_id, 0, 2, tau, eps, p).shape) == (0, 300)
 
 
+# ---------------------------------------------------------------------------- random formulas: both routes must agree
+def random_open_formula(seed: int, sem: str):
+    """A random tree of depth <= 3 over two affine predicates with at least one open-ended operator."""
+    rng = np.random.default_rng(1000 + seed)
+    x, y = preds32()
+
+    def interval(open_ok: bool):
+        a = int(rng.integers(0, 6))
+        if open_ok and rng.random() < 0.6:
+            return Interval(a, None), True
+        return Interval(a, a + int(rng.integers(0, 12))), False
+
+    def build(depth: int, slack_ok: bool):
+        """(formula, has an open-ended operator, start slack is zero)"""
+        r = rng.random()
+        if depth == 0 or r < 0.15:
+            return (x if rng.random() < 0.5 else y), False, True
+        if r < 0.3:
+            f, o, z = build(depth - 1, slack_ok)
+            return Not(f), o, z
+        if r < 0.55:
+            kids = [build(depth - 1, slack_ok) for _ in range(int(rng.integers(2, 4)))]
+            return (And if rng.random() < 0.5 else Or)(*[k[0] for k in kids]), any(k[1] for k in kids), all(k[2] for k in kids)
+        if r < 0.9 or sem != "classical":
+            f, o, z = build(depth - 1, True)
+            iv, is_open = interval(z)  # an operand with a start slack under an open-ended window raises everywhere: avoided
+            if not slack_ok and iv.start > 0:
+                iv = Interval(0, iv.end)
+            return (Always if rng.random() < 0.5 else Eventually)(f, iv), o or is_open, z and iv.start == 0
+        lf, lo, lz = build(depth - 1, False)
+        rf, ro, rz = build(depth - 1, False)
+        iv, is_open = interval(lz and rz)
+        if not slack_ok and iv.start > 0:
+            iv = Interval(0, iv.end)
+        return Until(lf, rf, iv), lo or ro or is_open, lz and rz and iv.start == 0
+
+    for _ in range(200):
+        f, has_open, _ = build(3, True)
+        if has_open:
+            return f
+    return Always(x, Interval(1, None))
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("sem,kw", [SEMS[0], SEMS[1], SEMS[3], SEMS[4], ("cumulative", {})], ids=["classical", "smooth0.5", "agm", "dgmsr1", "cumulative"])
+def test_random_formulas_scan_route_equals_in_kernel_route(sem, kw, seed):
+    """One tile holds T = 1000 for values and gradients of every semantics, so both routes exist: the open-ended operators
+    inside the formula kernel (interpreter tier) and behind leaf channels (scan kernels + a fused parent)."""
+    phi = random_open_formula(seed, sem)
+    sig = torch.tensor(signal(3, 1000, 40 + seed), device="cuda")
+    a = create_semantics(sem, backend="b200", **kw)
+    b = create_semantics(sem, backend="b200", **kw)
+    b.force_open_leaf = True
+    xa, xb = sig.clone().requires_grad_(True), sig.clone().requires_grad_(True)
+    rb = b.robustness_trace(phi, xb)
+    if sem == "cumulative":
+        # (its in-kernel gradient does not exist -- the interpreter tier has no cumulative adjoints -- so the automatic choice is
+        # the scan route already: values from the in-kernel forward, gradients from the oracle)
+        rb = torch.stack((rb.pos, rb.neg))
+        inside = a.compile(phi, 2)
+        assert inside.has_open and not inside.leaf_preds
+        ri = a._forward_raw(inside, sig, None).permute(2, 0, 1)
+        ok = torch.isfinite(ri)
+        assert torch.equal(ok, torch.isfinite(rb)) and torch.allclose(ri[ok], rb[ok], rtol=1e-5, atol=5e-6), repr(phi)
+        x64 = sig.detach().cpu().double().requires_grad_(True)
+        want = dense.robustness_trace(phi, x64, dense.make("cumulative"))
+        assert torch.allclose(rb.detach().cpu().double()[ok.cpu()], want.detach()[ok.cpu()], rtol=1e-5, atol=5e-6), repr(phi)
+        g = torch.rand(tuple(want.shape), dtype=torch.float64, generator=torch.Generator().manual_seed(seed)) + 0.25
+        (torch.nan_to_num(rb) * g.to("cuda", torch.float32)).sum().backward()
+        (torch.nan_to_num(want) * g).sum().backward()
+        scale = float(x64.grad.abs().max()) + 1e-12
+        assert torch.allclose(xb.grad.cpu().double(), x64.grad, rtol=4e-5, atol=4e-5 * scale), (repr(phi), scale)
+        return
+    ra = a.robustness_trace(phi, xa)
+    ok = torch.isfinite(ra)
+    assert torch.equal(ok, torch.isfinite(rb)), repr(phi)
+    if sem == "classical":
+        assert torch.equal(ra[ok], rb[ok]), repr(phi)
+    else:
+        assert torch.allclose(ra[ok], rb[ok], rtol=2e-4, atol=2e-5), (repr(phi), float((ra[ok] - rb[ok]).abs().max()))
+    if not bool(ok.any()):
+        return
+    g = torch.rand(ra.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(seed)) + 0.25
+    (torch.nan_to_num(ra) * g).sum().backward()
+    (torch.nan_to_num(rb) * g).sum().backward()
+    scale = float(xa.grad.abs().max()) + 1e-12
+    assert torch.allclose(xa.grad, xb.grad, rtol=2e-3, atol=2e-4 * scale), (repr(phi), float((xa.grad - xb.grad).abs().max()), scale)
+
+
 def test_vmap_and_functional_grad_through_the_scan_route():
     """``torch.func.vmap`` over traces and ``torch.func.grad`` compose with the open-ended route like with the formula
     kernels (the precedent: jax.vmap over the reference's JAX backend, tests/test_jax_semantics.py:310-368)."""

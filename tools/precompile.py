@@ -28,7 +28,10 @@ def _open(job):
     from pystl_b200 import create_semantics
 
     os.environ.pop("PYSTL_B200_FORCE_THREADS", None)
-    phi = (ow.formulas() if which == "window" else ow.until_formulas())[name]
+    if which == "random":
+        phi = ow.random_open_formula(name, sem)
+    else:
+        phi = {"window": ow.formulas, "until": ow.until_formulas, "cumulative": ow.cumulative_formulas}[which]()[name]
     s = create_semantics(sem, backend="b200", **kw)
     s.force_open_leaf = force
     try:
@@ -81,6 +84,13 @@ def jobs(with_tests: bool):
                 out.append(("open", "window", name, sem, kw, 300, True))
                 out.append(("open", "window", name, sem, kw, 2048, True))
                 out.append(("open", "window", name, sem, kw, 2048, False))
+            for seed in range(8):
+                if kw in ({}, {"temperature": 0.5}, {"eps": 1e-8, "p": 1}):
+                    out.append(("open", "random", seed, sem, kw, 1000, True))
+        for seed in range(8):
+            out.append(("open", "random", seed, "cumulative", {}, 1000, True))
+        for name in ow.cumulative_formulas():
+            out.append(("open", "cumulative", name, "cumulative", {}, 300, True))
         for name in ow.until_formulas():
             for T, force in ((300, True), (2048, True), (2048, False)):
                 out.append(("open", "until", name, "classical", {}, T, force))
