@@ -309,6 +309,61 @@ def cpu_port_throughput(cfg: str, budget_s: float, cores: int, pool=None, per: f
     }
 
 
+def open_ended_cases():
+    from pystl_b200.formula import Always, Eventually, Interval, Or, Until, affine_predicate
+
+    x = affine_predicate("x>0", {0: 1.0}, 0.0)
+    y = affine_predicate("y<0.5", {1: -1.0}, 0.5)
+    return (
+        ("classical", {}, "G[0,inf)(x>0)", Always(x, Interval(0, None))),
+        ("classical", {}, "(x>0) U[0,inf) (y<0.5)", Until(x, y, Interval(0, None))),
+        ("smooth", {"temperature": 1.0}, "G[0,inf)(x>0) | F[5,inf)(y<0.5)", Or(Always(x, Interval(0, None)), Eventually(y, Interval(5, None)))),
+    )
+
+
+OPEN_ENDED_SHAPE = (8192, 16384, 2)
+
+
+def open_ended_lines(dev) -> list:
+    """Open-ended operators on traces longer than one tile, through the public API: the operand's formula
+    kernel, the suffix-scan kernels of csrc/scan.cu and -- when the operator is not the root -- the parent formula kernel.  Not a
+    BASELINE configuration (those are all bounded); reported next to them because `Interval.end = None` is part of the path
+    (api.py:49-54).  CUDA-event time per call on torch's current stream, 3 calls after 2 warm-up calls."""
+    import pystl_b200
+
+    B, T, D = OPEN_ENDED_SHAPE
+    cases = open_ended_cases()
+    g = torch.Generator(device=dev).manual_seed(7)
+    sig = torch.randn(B, T, D, device=dev, generator=g) * 0.5
+    out = []
+    for sem_name, kw, text, phi in cases:
+        try:
+            sem = pystl_b200.create_semantics(sem_name, backend="b200", **kw)
+            for _ in range(2):
+                sem.robustness_trace(phi, sig)
+                sem.mean_robustness_and_grad(phi, sig)
+            torch.cuda.synchronize(dev)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            for _ in range(3):
+                sem.robustness_trace(phi, sig)
+            ev[1].record()
+            for _ in range(3):
+                mean, grad = sem.mean_robustness_and_grad(phi, sig)
+            ev[2].record()
+            torch.cuda.synchronize(dev)
+            f_ms, g_ms = ev[0].elapsed_time(ev[1]) / 3, ev[1].elapsed_time(ev[2]) / 3
+            out.append({"semantics": sem_name, "formula": text, "traces": B, "horizon": T, "channels": D,
+                        "values_ms": f_ms, "values_samples_per_s": B * T / (f_ms * 1e-3),
+                        "mean_and_grad_ms": g_ms, "mean_and_grad_samples_per_s": B * T / (g_ms * 1e-3), "mean_robustness": float(mean)})
+            del mean, grad
+        except Exception as exc:  # a secondary line never fails the bench
+            out.append({"semantics": sem_name, "formula": text, "error": f"{type(exc).__name__}: {exc}"[:200]})
+    del sig
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_vectorised_throughput(cfg: str, budget_s: float, with_bwd: bool) -> dict:
     """Second reported CPU figure (baseline 2): the all-t, batched float64
     restatement with torch CPU ops on every host thread (oracle/dense.py mirrors the reference's
@@ -752,6 +807,8 @@ def run_b200(args) -> None:
             except Exception as exc:
                 sharded["semantics"][key] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
+    open_ended = open_ended_lines(dev) if (world == 1 and not args.no_others) else None
+
     cpu = None
     cpu_vec = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -788,6 +845,7 @@ def run_b200(args) -> None:
             },
             "roofline": roofline,
             "cfg5_sharded": sharded,
+            "open_ended": open_ended,
             "cpu_baseline": cpu,
             "cpu_baseline_vectorised": cpu_vec,
             "e2e": e2e,

@@ -28,7 +28,12 @@ def _open(job):
     from pystl_b200 import create_semantics
 
     os.environ.pop("PYSTL_B200_FORCE_THREADS", None)
-    if which == "random":
+    if which == "bench":
+        import bench
+
+        sem, kw, _, phi = bench.open_ended_cases()[name]
+        T = bench.OPEN_ENDED_SHAPE[1]
+    elif which == "random":
         phi = ow.random_open_formula(name, sem)
     else:
         phi = {"window": ow.formulas, "until": ow.until_formulas, "cumulative": ow.cumulative_formulas}[which]()[name]
@@ -70,6 +75,8 @@ def jobs(with_tests: bool):
         out.append((BASELINE_SPECS[cfg[:4]], sem, kw, T, D, 0, False))
         if bwd:
             out.append((BASELINE_SPECS[cfg[:4]], sem, kw, T, D, 0, True))
+    for i in range(len(bench.open_ended_cases())):  # the open-ended lines of the bench
+        out.append(("open", "bench", i, "", {}, 0, False))
     if with_tests:
         import fused_cases
 
