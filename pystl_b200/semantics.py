@@ -300,8 +300,10 @@ class _B200Semantics(_ReferenceSemantics):
                 with torch.enable_grad():
                     # (row sums in fp32, their sum in float64: summing with dtype=float64 materialises a float64 copy of the trace)
                     total = self._root_leaf_trace(cf, base, nan_tail=False)[:, :valid].sum(dim=(1, 2)).sum(dtype=torch.float64)
-                (grad,) = torch.autograd.grad(total, base, torch.tensor((1.0 / n_total) if n_total > 0 else 0.0, dtype=torch.float64,
-                                                                        device=sig.device))
+                # (torch.full: a fill kernel; torch.tensor(scalar, device=...) is a pageable host-to-device copy that makes the host
+                # wait for everything queued before it)
+                (grad,) = torch.autograd.grad(total, base, torch.full((), (1.0 / n_total) if n_total > 0 else 0.0, dtype=torch.float64,
+                                                                      device=sig.device))
                 acc[0] = total.detach()
             else:
                 grad = torch.zeros_like(sig)
