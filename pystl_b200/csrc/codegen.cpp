@@ -124,6 +124,12 @@ struct Gen {
     // (dgmsr: p = 1 is baked into the kernel; unit weights_pair are a run-time condition, the per-output sweep stays as the other branch)
     return uniform && (P.sem == SEM_AGM || (P.sem == SEM_DGMSR && P.p == 1));
   }
+  // forward Smooth Until (unweighted, the shared-tail walk): lambda / rho exponentiated once per sample into two more planes
+  bool until_expl(const TInstr& in) const {
+    static const bool off = getenv("PYSTL_B200_UNTIL_EXP") && atoi(getenv("PYSTL_B200_UNTIL_EXP")) == 0;
+    return !off && !bwd && P.sem == SEM_SMOOTH && is_until(in) && in.a <= 64 && in.w_off < 0 && in.w2_off < 0;
+  }
+  int until_floats(const TInstr& in) const { return (2 * vw() + (until_expl(in) ? 2 : 0)) * 8 * nt; }
   bool cum_lockstep(const TInstr& in) const { return cum_bwd() && is_until(in) && in.a <= 64; }
   // cumulative backward: floats of dead forward scratch an instruction's adjoint borrows (scatter / hand-off planes)
   int cum_sp_floats(const TInstr& in) const {
@@ -240,7 +246,7 @@ struct Gen {
       if (is_until(in)) {
         if (bwd) continue;  // persistent (above): the adjoint re-reads the staged operands
         scr_off[i] = used[ins_level[i]];
-        used[ins_level[i]] += 2 * vw() * 8 * nt;  // UntilOp::FLOATS
+        used[ins_level[i]] += until_floats(in);  // UntilOp::FLOATS
         continue;
       }
       if (!is_window(in)) continue;
@@ -604,8 +610,8 @@ struct Gen {
     const TInstr& in = P.ins[i];
     const bool nl = in.negmask & 1, nr = in.negmask & 2;
     o.line("// until %d [%d, %d], phase 1: stage both operands", i, in.a, in.b);
-    o.line("using U%d = UntilOp<SEM, %d, %d, NT>;", i, in.a, in.b);
-    o.line("static_assert(U%d::FLOATS == %d, \"host / device scratch layout mismatch\");", i, 2 * vw() * 8 * nt);
+    o.line("using U%d = UntilOp<SEM, %d, %d, NT%s>;", i, in.a, in.b, until_expl(in) ? ", true" : "");
+    o.line("static_assert(U%d::FLOATS == %d, \"host / device scratch layout mismatch\");", i, bwd ? 2 * vw() * 8 * nt : until_floats(in));
     o.line("RP rp%d = rp;", i);
     if (P.sem == SEM_SMOOTH)
       o.line("rp%d.shift = fmaxf(-(%s), -(%s)) * rp.k;  // max exponent of -l, -r over the tile", i, lo_of(in.src[0], nl).c_str(),
@@ -614,7 +620,8 @@ struct Gen {
     o.indent++;
     o.line("V tl[8], tr[8];");
     o.line("_Pragma(\"unroll\") for (int i = 0; i < 8; ++i) { tl[i] = %s; tr[i] = %s; }", operand(in, 0, "i").c_str(), operand(in, 1, "i").c_str());
-    o.line("U%d::phase1(smem + %d, c.tid, tl, tr);", i, scr_off[i]);
+    if (until_expl(in)) o.line("U%d::phase1(smem + %d, c.tid, tl, tr, rp%d);", i, scr_off[i], i);
+    else o.line("U%d::phase1(smem + %d, c.tid, tl, tr);", i, scr_off[i]);
     o.indent--;
     o.line("}");
   }

@@ -158,7 +158,8 @@ static std::mutex g_prep_mu;
 static std::unordered_map<std::string, std::shared_ptr<Prepared>> g_prep;
 static const char* const kKnobs[] = {"PYSTL_B200_FORCE_THREADS", "PYSTL_B200_FUSED_MINB", "PYSTL_B200_FUSED_REGS", "PYSTL_B200_FUSED_REGS_BWD",
                                      "PYSTL_B200_PREFETCH",      "PYSTL_B200_MERGE",      "PYSTL_B200_NVRTC_FLAGS", "PYSTL_B200_TMA",
-                                     "PYSTL_B200_TMA_STORE",     "PYSTL_B200_CACHE",      "PYSTL_B200_RELIFT"};
+                                     "PYSTL_B200_TMA_STORE",     "PYSTL_B200_CACHE",      "PYSTL_B200_RELIFT",
+                                     "PYSTL_B200_UNTIL_EXP"};
 
 template <class X>
 static void key_put(std::string* k, const X* p, size_t n) {
