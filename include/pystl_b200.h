@@ -219,6 +219,29 @@ int pystl_b200_assemble_channels(const float* signal, int64_t rows, int32_t D, c
 int pystl_b200_scatter_channels(const float* grad, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels,
                                 float* grad_signal, float* const* grad_cols, int32_t n_cols, void* stream);
 
+/* CT-STL on value traces (CtstlSemantics, /root/reference/pystl/semantics/ctstl.py -- exported by the reference but not
+ * registered under create_semantics, semantics/__init__.py:47-74).  Everything else of CT-STL is the classical semantics.
+ *
+ * The cumulative-time operator C^tau_I (CtstlSemantics.temporal_cumulative, ctstl.py:107-127, with kth_largest :18-26 and
+ * tau_to_k :28-35): out[b, t] = k-th largest of y[b, t + a .. min(t + b_end, T - 1)] (window clipped as api.py:49-54; b_end < 0:
+ * no end), k = ceil(tau / delta) >= 1 computed by the caller; -inf where the clipped window holds fewer than k samples.
+ * arg[B, T] (may be NULL) records the sample the value came from (-1: none); among equal samples the one a stable ascending
+ * sort puts at position n - k (jax/semantics.py:378-386).  Windows of at most 49152 samples (PYSTL_E_UNSUPPORTED beyond).
+ * backward: grad_y[B, T] (fully overwritten) = d sum(grad_out * out) / d y. */
+int pystl_b200_ctstl_cumulative_forward(const float* y, int64_t B, int64_t T, int32_t a, int32_t b_end, int32_t k, float* out,
+                                        int32_t* arg, void* stream);
+int pystl_b200_ctstl_cumulative_backward(const int32_t* arg, const float* grad_out, int64_t B, int64_t T, int32_t a, int32_t b_end,
+                                         float* grad_y, void* stream);
+/* CT-STL Until (CtstlSemantics.temporal_until, ctstl.py:78-105): the left prefix of candidate i EXCLUDES t + i,
+ *   out[b, t] = max_{i = a .. min(b_end, T - 1 - t)} min( r[t + i], min_{k < i} l[t + k] )       (b_end < 0: no end)
+ * on the value traces l[B, T], r[B, T]; NaN where the window is empty (the reference raises ValueError, ctstl.py:96-97).
+ * key[B, T] (may be NULL): 2 * sample + 1 when the value is an r, 2 * sample when it is an l, -1 where there is none;
+ * backward routes the cotangents there (grad_l, grad_r fully overwritten). */
+int pystl_b200_ctstl_until_forward(const float* l, const float* r, int64_t B, int64_t T, int32_t a, int32_t b_end, float* out,
+                                   int32_t* key, void* stream);
+int pystl_b200_ctstl_until_backward(const int32_t* key, const float* grad_out, int64_t B, int64_t T, int32_t a, int32_t b_end,
+                                    float* grad_l, float* grad_r, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ from .semantics import (
     B200DgmsrSemantics,
     B200SmoothRobustSemantics,
 )
+from .ctstl import B200CtstlSemantics, CumulativeTime
 from .distributed import shard_bounds
 
 REGISTERED_IN_REFERENCE = install()
@@ -44,4 +45,5 @@ __all__ = [
     "create_semantics", "install", "BACKEND", "shard_bounds",
     "B200ClassicRobustSemantics", "B200SmoothRobustSemantics", "B200CumulativeSemantics",
     "B200CumulativeRobustness", "B200AgmRobustSemantics", "B200DgmsrSemantics",
+    "B200CtstlSemantics", "CumulativeTime",
 ]

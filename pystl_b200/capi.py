@@ -101,6 +101,10 @@ EXPORTS = (
     "pystl_b200_open_until_backward",
     "pystl_b200_assemble_channels",
     "pystl_b200_scatter_channels",
+    "pystl_b200_ctstl_cumulative_forward",
+    "pystl_b200_ctstl_cumulative_backward",
+    "pystl_b200_ctstl_until_forward",
+    "pystl_b200_ctstl_until_backward",
 )
 
 # PYSTL_B200_LIB points at an alternative build of the same library (A/B timing of kernel variants)
@@ -172,6 +176,18 @@ def declare(lib: C.CDLL, prefix: str = "pystl_b200") -> None:
         f = lib.pystl_b200_scatter_channels
         f.restype = C.c_int
         f.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]
+        f = lib.pystl_b200_ctstl_cumulative_forward
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        f = lib.pystl_b200_ctstl_cumulative_backward
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        f = lib.pystl_b200_ctstl_until_forward
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        f = lib.pystl_b200_ctstl_until_backward
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
 
 
 def lib() -> C.CDLL:

@@ -69,7 +69,7 @@ def start_slack(node: Any) -> int:
     """Samples at the end of the trace where ``node`` raises (empty window); mirrors lower.cpp."""
     kind = type(node).__name__
     if kind == "Predicate":
-        return 0
+        return pred_slack_of(node)
     if kind == "Not":
         return start_slack(node.child)
     if kind in ("And", "Or"):
@@ -83,6 +83,13 @@ def start_slack(node: Any) -> int:
     if kind == "Until" or b is None or cs >= NEVER:
         return NEVER
     return min(NEVER, cs + int(b))
+
+
+def pred_slack_of(pred: Any) -> int:
+    """``metadata["slack"] = s``: the predicate reads a value trace computed outside the kernel whose last ``s`` samples do
+    not exist (the reference raises there); ``-1``: it raises at every t.  Goes into ``pystl_pred_t.slack``."""
+    s = int((getattr(pred, "metadata", None) or {}).get("slack", 0))
+    return NEVER if s < 0 or s >= NEVER else s
 
 
 def wants_leaf(pred: Any) -> bool:
@@ -309,10 +316,13 @@ def compile_formula(
             for d, _ in terms:
                 if d < 0 or d >= n_channels + n_cols[0]:
                     raise ValueError(f"Predicate '{node.name}' reads channel {d} of a {n_channels}-channel signal")
-            pkey = (terms, bias)
+            sl = pred_slack_of(node)
+            pkey = (terms, bias) if sl == 0 else (terms, bias, sl)
             if pkey not in pred_index:
                 pred_index[pkey] = len(preds)
-                preds.append(pkey)
+                preds.append(pkey[:2])
+                if sl:
+                    pred_slack[pred_index[pkey]] = -1 if sl >= NEVER else sl
             n.pred = pred_index[pkey]
         elif kind == "Not":
             n.kind = capi.NODE_NOT

@@ -413,7 +413,32 @@ int assemble_channels(const float* signal, int64_t rows, int32_t D, const int32_
                       int32_t n_cols, float* out, void* stream, char* err, size_t err_cap);
 int scatter_channels(const float* grad, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels, float* grad_signal,
                      float* const* grad_cols, int32_t n_cols, void* stream, char* err, size_t err_cap);
+// CT-STL on value traces: select.cu
+int ctstl_cumulative_forward(const float* y, int64_t B, int64_t T, int32_t a, int32_t b_end, int32_t k, float* out, int32_t* arg,
+                             void* stream, char* err, size_t err_cap);
+int ctstl_cumulative_backward(const int32_t* arg, const float* grad_out, int64_t B, int64_t T, int32_t a, int32_t b_end, float* grad_y,
+                              void* stream, char* err, size_t err_cap);
+int ctstl_until_forward(const float* l, const float* r, int64_t B, int64_t T, int32_t a, int32_t b_end, float* out, int32_t* key,
+                        void* stream, char* err, size_t err_cap);
+int ctstl_until_backward(const int32_t* key, const float* grad_out, int64_t B, int64_t T, int32_t a, int32_t b_end, float* grad_l,
+                         float* grad_r, void* stream, char* err, size_t err_cap);
 }  // namespace pystl
+extern "C" int pystl_b200_ctstl_cumulative_forward(const float* y, int64_t B, int64_t T, int32_t a, int32_t b_end, int32_t k,
+                                                   float* out, int32_t* arg, void* stream) {
+  return pystl::ctstl_cumulative_forward(y, B, T, a, b_end, k, out, arg, stream, g_err, sizeof(g_err));
+}
+extern "C" int pystl_b200_ctstl_cumulative_backward(const int32_t* arg, const float* grad_out, int64_t B, int64_t T, int32_t a,
+                                                    int32_t b_end, float* grad_y, void* stream) {
+  return pystl::ctstl_cumulative_backward(arg, grad_out, B, T, a, b_end, grad_y, stream, g_err, sizeof(g_err));
+}
+extern "C" int pystl_b200_ctstl_until_forward(const float* l, const float* r, int64_t B, int64_t T, int32_t a, int32_t b_end,
+                                              float* out, int32_t* key, void* stream) {
+  return pystl::ctstl_until_forward(l, r, B, T, a, b_end, out, key, stream, g_err, sizeof(g_err));
+}
+extern "C" int pystl_b200_ctstl_until_backward(const int32_t* key, const float* grad_out, int64_t B, int64_t T, int32_t a,
+                                               int32_t b_end, float* grad_l, float* grad_r, void* stream) {
+  return pystl::ctstl_until_backward(key, grad_out, B, T, a, b_end, grad_l, grad_r, stream, g_err, sizeof(g_err));
+}
 extern "C" int pystl_b200_assemble_channels(const float* signal, int64_t rows, int32_t D, const int32_t* channels, int32_t n_channels,
                                             const float* const* cols, int32_t n_cols, float* out, void* stream) {
   return pystl::assemble_channels(signal, rows, D, channels, n_channels, cols, n_cols, out, stream, g_err, sizeof(g_err));

@@ -262,6 +262,9 @@ def _evaluate_recursive(node: Any, signal: Any, sem: Any, t: int) -> Any:
         vals = [_evaluate_recursive(node.child, signal, sem, tau) for tau in idx]
         op = sem.temporal_always if kind == "Always" else sem.temporal_eventually
         return op(vals, weights=node.weights)
+    if kind == "CumulativeTime":  # (pystl_b200.ctstl: the node of CtstlSemantics.temporal_cumulative, ctstl.py:107-127)
+        vals = [_evaluate_recursive(node.child, signal, sem, tau) for tau in window_indices(t, horizon, node.interval)]
+        return sem.temporal_cumulative(vals, tau=node.tau, delta=node.delta)
     if kind == "Until":
         if t >= horizon:
             raise IndexError(f"t={t} is out of bounds for horizon={horizon}.")

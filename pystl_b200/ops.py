@@ -21,7 +21,7 @@ PyTorch is plumbing here: the ops hand raw device pointers and the current strea
 from __future__ import annotations
 
 import itertools
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 
@@ -485,3 +485,179 @@ def _(info, in_dims, key, grad_out, semantics, start):
     n = info.batch_size
     gl, gr = open_until_grad(_lead(key, in_dims[0], n), _lead(grad_out, in_dims[1], n), semantics, start)
     return (gl.reshape((n, -1) + tuple(gl.shape[1:])), gr.reshape((n, -1) + tuple(gr.shape[1:]))), (0, 0)
+
+
+# ---- CT-STL on value traces: the cumulative-time operator and the Until with an exclusive prefix (csrc/select.cu) ---
+_lib.define("ctstl_cumulative_fwd(Tensor y, int start, int end, int k) -> (Tensor, Tensor)")
+_lib.define("ctstl_cumulative_grad(Tensor arg, Tensor grad_out, int start, int end) -> Tensor")
+_lib.define("ctstl_until_fwd(Tensor left, Tensor right, int start, int end) -> (Tensor, Tensor)")
+_lib.define("ctstl_until_grad(Tensor key, Tensor grad_out, int start, int end) -> (Tensor, Tensor)")
+
+
+def _ctstl_cumulative_fwd_cuda(y, start, end, k):
+    _check_trace(y)
+    y = y.contiguous()
+    B, T = y.shape
+    out = torch.empty_like(y)
+    arg = torch.empty((B, T), dtype=torch.int32, device=y.device)
+    with torch.cuda.device(y.device):
+        rc = capi.lib().pystl_b200_ctstl_cumulative_forward(y.data_ptr(), B, T, int(start), int(end), int(k), out.data_ptr(),
+                                                            arg.data_ptr(), torch.cuda.current_stream(y.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return out, arg
+
+
+def _ctstl_cumulative_grad_cuda(arg, grad_out, start, end):
+    g = grad_out.to(dtype=torch.float32).contiguous()
+    _check_trace(g)
+    arg = arg.contiguous()
+    B, T = g.shape
+    gy = torch.empty_like(g)
+    with torch.cuda.device(g.device):
+        rc = capi.lib().pystl_b200_ctstl_cumulative_backward(arg.data_ptr(), g.data_ptr(), B, T, int(start), int(end), gy.data_ptr(),
+                                                             torch.cuda.current_stream(g.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return gy
+
+
+def _ctstl_until_fwd_cuda(left, right, start, end):
+    _check_trace(left)
+    _check_trace(right)
+    if left.shape != right.shape:
+        raise ValueError("UNTIL traces must have the same shape")
+    left, right = left.contiguous(), right.contiguous()
+    B, T = left.shape
+    out = torch.empty_like(left)
+    key = torch.empty((B, T), dtype=torch.int32, device=left.device)
+    with torch.cuda.device(left.device):
+        rc = capi.lib().pystl_b200_ctstl_until_forward(left.data_ptr(), right.data_ptr(), B, T, int(start), int(end), out.data_ptr(),
+                                                       key.data_ptr(), torch.cuda.current_stream(left.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return out, key
+
+
+def _ctstl_until_grad_cuda(key, grad_out, start, end):
+    g = grad_out.to(dtype=torch.float32).contiguous()
+    _check_trace(g)
+    key = key.contiguous()
+    B, T = g.shape
+    gl, gr = torch.empty_like(g), torch.empty_like(g)
+    with torch.cuda.device(g.device):
+        rc = capi.lib().pystl_b200_ctstl_until_backward(key.data_ptr(), g.data_ptr(), B, T, int(start), int(end), gl.data_ptr(),
+                                                        gr.data_ptr(), torch.cuda.current_stream(g.device).cuda_stream)
+    capi.raise_for(rc, capi.lib().pystl_b200_last_error())
+    return gl, gr
+
+
+_lib.impl("ctstl_cumulative_fwd", _ctstl_cumulative_fwd_cuda, "CUDA")
+_lib.impl("ctstl_cumulative_grad", _ctstl_cumulative_grad_cuda, "CUDA")
+_lib.impl("ctstl_until_fwd", _ctstl_until_fwd_cuda, "CUDA")
+_lib.impl("ctstl_until_grad", _ctstl_until_grad_cuda, "CUDA")
+
+
+@torch.library.register_fake("pystl_b200::ctstl_cumulative_fwd")
+def _(y, start, end, k):
+    return torch.empty_like(y), y.new_empty(tuple(y.shape), dtype=torch.int32)
+
+
+@torch.library.register_fake("pystl_b200::ctstl_cumulative_grad")
+def _(arg, grad_out, start, end):
+    return torch.empty_like(grad_out)
+
+
+@torch.library.register_fake("pystl_b200::ctstl_until_fwd")
+def _(left, right, start, end):
+    return torch.empty_like(left), left.new_empty(tuple(left.shape), dtype=torch.int32)
+
+
+@torch.library.register_fake("pystl_b200::ctstl_until_grad")
+def _(key, grad_out, start, end):
+    return torch.empty_like(grad_out), torch.empty_like(grad_out)
+
+
+class CtstlCumulative(torch.autograd.Function):
+    """``out[b, t]`` = k-th largest of the window ``[t + start, min(t + end, T - 1)]`` of ``y[b]``; the cotangent of an output goes
+    to the sample it selected."""
+
+    @staticmethod
+    def forward(y, start, end, k):
+        return torch.ops.pystl_b200.ctstl_cumulative_fwd(y, start, end, k)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        _, ctx.start, ctx.end, _ = inputs
+        out, arg = output
+        ctx.mark_non_differentiable(arg)
+        ctx.save_for_backward(arg)
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_arg):
+        (arg,) = ctx.saved_tensors
+        return torch.ops.pystl_b200.ctstl_cumulative_grad(arg, grad_out, ctx.start, ctx.end), None, None, None
+
+    generate_vmap_rule = False
+
+    @staticmethod
+    def vmap(info, in_dims, y, start, end, k):
+        yy = y.movedim(in_dims[0], 0)
+        out, arg = CtstlCumulative.apply(yy.reshape((-1,) + tuple(yy.shape[2:])), start, end, k)
+        n = info.batch_size
+        return (out.reshape((n, -1) + tuple(out.shape[1:])), arg.reshape((n, -1) + tuple(arg.shape[1:]))), (0, 0)
+
+
+class CtstlUntil(torch.autograd.Function):
+    """CT-STL Until of two value traces (exclusive left prefix); cotangents go to the recorded sources."""
+
+    @staticmethod
+    def forward(left, right, start, end):
+        return torch.ops.pystl_b200.ctstl_until_fwd(left, right, start, end)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        _, _, ctx.start, ctx.end = inputs
+        out, key = output
+        ctx.mark_non_differentiable(key)
+        ctx.save_for_backward(key)
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_key):
+        (key,) = ctx.saved_tensors
+        gl, gr = torch.ops.pystl_b200.ctstl_until_grad(key, grad_out, ctx.start, ctx.end)
+        return gl, gr, None, None
+
+    generate_vmap_rule = False
+
+    @staticmethod
+    def vmap(info, in_dims, left, right, start, end):
+        n = info.batch_size
+        lf = left.movedim(in_dims[0], 0) if in_dims[0] is not None else left.unsqueeze(0).expand((n,) + tuple(left.shape))
+        rt = right.movedim(in_dims[1], 0) if in_dims[1] is not None else right.unsqueeze(0).expand((n,) + tuple(right.shape))
+        out, key = CtstlUntil.apply(lf.reshape((-1,) + tuple(lf.shape[2:])), rt.reshape((-1,) + tuple(rt.shape[2:])), start, end)
+        return (out.reshape((n, -1) + tuple(out.shape[1:])), key.reshape((n, -1) + tuple(key.shape[1:]))), (0, 0)
+
+
+@torch.library.register_vmap("pystl_b200::ctstl_cumulative_grad")
+def _(info, in_dims, arg, grad_out, start, end):
+    n = info.batch_size
+    a, g = _lead(arg, in_dims[0], n), _lead(grad_out, in_dims[1], n)
+    gy = torch.ops.pystl_b200.ctstl_cumulative_grad(a, g, start, end)
+    return gy.reshape((n, -1) + tuple(gy.shape[1:])), 0
+
+
+@torch.library.register_vmap("pystl_b200::ctstl_until_grad")
+def _(info, in_dims, key, grad_out, start, end):
+    n = info.batch_size
+    kk, g = _lead(key, in_dims[0], n), _lead(grad_out, in_dims[1], n)
+    gl, gr = torch.ops.pystl_b200.ctstl_until_grad(kk, g, start, end)
+    return (gl.reshape((n, -1) + tuple(gl.shape[1:])), gr.reshape((n, -1) + tuple(gr.shape[1:]))), (0, 0)
+
+
+def ctstl_cumulative(y: torch.Tensor, start: int, end: Optional[int], k: int) -> torch.Tensor:
+    """Differentiable ``C^tau_I`` of the value trace ``y [B, T]``: k-th largest of the clipped window at every t (-inf where the window
+    holds fewer than k samples); ``end=None``: no end."""
+    return CtstlCumulative.apply(y, int(start), -1 if end is None else int(end), int(k))[0]
+
+
+def ctstl_until(left: torch.Tensor, right: torch.Tensor, start: int, end: Optional[int]) -> torch.Tensor:
+    """Differentiable CT-STL Until of the value traces ``left, right [B, T]`` (NaN where the window is empty)."""
+    return CtstlUntil.apply(left, right, int(start), -1 if end is None else int(end))[0]
