@@ -708,6 +708,9 @@ PF_DEV void rcp2(float a, float b, float& ra, float& rb) {
 // EXPL (Smooth, forward kernels): two more planes hold lambda = 2^(-k l - shift), rho = 2^(-k r - shift), exponentiated ONCE per
 // sample by its owner; the walk -- which visits every position from about (UB + 8) / 8 threads -- then costs no exponential
 // (cfg5 Smooth forward: 32 -> 22 MUFU operations per sample on a kernel whose XU pipe was 74-83 % busy).
+#ifndef PYSTL_DGMSR_SELECT
+#define PYSTL_DGMSR_SELECT 1
+#endif
 template <int SEM, int UA, int UB, int NT, bool EXPL = false>
 struct UntilOp {
   static constexpr int VW = Tr<SEM>::VW;
@@ -1066,8 +1069,26 @@ struct UntilOp {
       take(i, se - fast_sqrt(fmaf(0.5f, fmaf(y, y, r2n), eps)));
     };
     // general candidate; zr: the value of an all-positive prefix paired with this r <= 0
+    // (the three cases are BRANCHES: behind a few positions almost every prefix holds some l <= 0 and a whole warp takes the
+    // two-square-root case -- with N(0, 1) signals the general case runs for about a third of the candidates of a warp;
+    // PYSTL_DGMSR_SELECT=1 evaluates every case and selects, which is what this walk did before)
     auto cand = [&](int i, float a0, float a1, float invk, float kf, float r, float r2n, float zr) {
       const bool flag = a1 == f_inf();
+#if PYSTL_DGMSR_SELECT == 0
+      if (flag) {
+        cand_flag(i, a0, invk, r2n);
+        return;
+      }
+      if (!(r > 0.f)) {
+        take(i, zr);
+        return;
+      }
+#elif PYSTL_DGMSR_SELECT == 2
+      if (__all_sync(__activemask(), flag)) {  // warp-uniform: no divergence, one vote per candidate
+        cand_flag(i, a0, invk, r2n);
+        return;
+      }
+#endif
       const float yf = se - fast_sqrt(fmaf(a0, invk, eps));
       const float zf = se - fast_sqrt(fmaf(0.5f, fmaf(yf, yf, r2n), eps));
       const float u = kf * lge;
@@ -1115,7 +1136,11 @@ struct UntilOp {
       float ik[11];  // 1 / cnt for cnt = 4 g + (k - i) + 1, k - i in [-7, 3]
 #pragma unroll
       for (int j = 0; j < 11; ++j) ik[j] = fast_rcp((float)(4 * g + j - 6));
+#if PYSTL_DGMSR_SELECT == 2
+      if (__all_sync(__activemask(), Ml == f_inf())) {
+#else
       if (Ml == f_inf()) {  // some l <= 0 in the shared tail already: every candidate of the group is flagged
+#endif
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int kq = 4 * g + k;

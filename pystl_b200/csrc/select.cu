@@ -10,8 +10,9 @@
 //
 // A selection is not a scan: there is no associative summary of a window from which the k-th largest of a shifted window
 // follows, so every output selects from its own window.  The kernel does that by BISECTION ON THE KEY: floats are mapped
-// to order-preserving 32-bit keys once, when the tile (outputs + window halo) is staged into shared memory with coalesced
-// loads, and the answer is built bit by bit from the top -- 32 counting passes `#(key >= candidate) >= k` over the window.
+// ordered by an order-preserving 32-bit key, the tile (outputs + window halo) is staged into shared memory with coalesced
+// loads, and the answer's key is built bit by bit from the top -- 32 counting passes `#(sample >= candidate) >= k` over the
+// window, the candidate key turned back into a float so that the compare is an FSET and the count an FADD (two pipes).
 // A thread owns 4 consecutive outputs whose windows overlap in all but 3 samples: every 128-bit shared-memory read feeds
 // 16 compare-and-count operations (no bank conflicts: consecutive threads read consecutive 16-byte groups).  The work is
 // 32 (W + 3) compares per output whatever k is; the samples are read from HBM once and the result written once.
@@ -53,51 +54,61 @@ __device__ __forceinline__ unsigned key_of(float v) {
 }
 __device__ __forceinline__ float val_of(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
-// one 128-bit group of keys against the four candidates: element e of the group sits at offset d0 + e from the thread's first
-// output; output q counts offsets q <= d <= q + W - 1 (EDGE: test it; interior groups satisfy it for every q)
+// one 128-bit group of samples against the four candidates: element e of the group sits at offset d0 + e from the thread's first
+// output; output q counts offsets q <= d <= q + W - 1 (EDGE: test it; interior groups satisfy it for every q).  The compare is
+// a float compare and the counter a float (exact up to 2^24): FSET on the ALU pipe + FADD on the FMA pipe, where an integer
+// compare-and-count is two ALU-pipe instructions -- the kernel is bound by that pipe.
 template <bool EDGE>
-__device__ __forceinline__ void count_group(const uint4 kv, int d0, int W, const unsigned (&thr)[4], int (&cnt)[4]) {
-  const unsigned ke[4] = {kv.x, kv.y, kv.z, kv.w};
+__device__ __forceinline__ void count_group(const float4 kv, int d0, int W, const float (&thr)[4], float (&cnt)[4]) {
+  const float ke[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       bool in = ke[e] >= thr[q];
       if (EDGE) in = in && (d0 + e >= q) && (d0 + e <= q + W - 1);
-      cnt[q] += in ? 1 : 0;
+      cnt[q] += in ? 1.f : 0.f;
     }
   }
 }
 
+// float whose order among floats is the key's order among keys; keys below key(-inf) (negative-NaN patterns) count everything,
+// like -inf; keys above key(+inf) are NaN and count nothing (no sample is above +inf: NaN samples are handled apart)
+__device__ __forceinline__ float thr_of(unsigned key) { return val_of(key < 0x007fffffu ? 0x007fffffu : key); }
+
 // grid: one CTA per (trace, tile of kSelOut outputs), linearised
 __global__ void __launch_bounds__(kSelThreads) kth_window_fwd(const float* __restrict__ y, float* __restrict__ out, int* __restrict__ arg,
                                                               int T, int a, int W, int k, int tiles_per_trace) {
-  extern __shared__ __align__(16) unsigned keys[];
+  extern __shared__ __align__(16) float vals[];
+  __shared__ int has_nan;
   const long long trace = blockIdx.x / tiles_per_trace;
   const int tb = (blockIdx.x - trace * tiles_per_trace) * kSelOut;  // first output of the tile
   const float* yt = y + trace * T;
-  // stage samples tb + a .. tb + a + kSelOut + W + 2 (keys; 0 past the horizon: below every candidate, never counted)
+  if (threadIdx.x == 0) has_nan = 0;
+  __syncthreads();
+  // stage samples tb + a .. tb + a + kSelOut + W + 2 (-0 read as +0; NaN past the horizon: no compare counts it)
   const int n_stage = (kSelOut + W + 3 + 3) & ~3;
   for (int i = threadIdx.x; i < n_stage; i += kSelThreads) {
     const long long s = (long long)tb + a + i;
-    unsigned kk = 0u;
+    float v = __int_as_float(0x7fc00000);
     if (s < T) {
-      const float v = yt[s];
-      kk = v != v ? 0xffffffffu : key_of(v);  // NaN (an operand the reference raises on): one key above everything
+      v = yt[s] + 0.f;  // (-0) + (+0) = +0
+      if (v != v) has_nan = 1;  // (an operand value the reference raises on)
     }
-    keys[i] = kk;
+    vals[i] = v;
   }
   __syncthreads();
   const int l0 = 4 * threadIdx.x;  // local index of the thread's first output = of the first sample of its first window
-  const uint4* k4 = reinterpret_cast<const uint4*>(keys) + threadIdx.x;
+  const float4* k4 = reinterpret_cast<const float4*>(vals) + threadIdx.x;
   const int g_last = (W + 2) >> 2;                 // last group that holds a sample of the 4 windows (offsets 0 .. W + 2)
   const int g_int = W >= 4 ? ((W - 4) >> 2) : 0;   // groups 1 .. g_int lie inside every one of the 4 windows
+  const float kf = (float)k;
   unsigned pre[4] = {0u, 0u, 0u, 0u};
   for (int bit = 31; bit >= 0; --bit) {
-    unsigned thr[4];
-    int cnt[4] = {0, 0, 0, 0};
+    float thr[4];
+    float cnt[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) thr[q] = pre[q] | (1u << bit);
+    for (int q = 0; q < 4; ++q) thr[q] = thr_of(pre[q] | (1u << bit));
     count_group<true>(k4[0], 0, W, thr, cnt);
     int g = 1;
 #pragma unroll 2
@@ -105,37 +116,38 @@ __global__ void __launch_bounds__(kSelThreads) kth_window_fwd(const float* __res
     for (; g <= g_last; ++g) count_group<true>(k4[g], 4 * g, W, thr, cnt);
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (cnt[q] >= k) pre[q] = thr[q];
+      if (cnt[q] >= kf) pre[q] |= 1u << bit;
   }
-  // a NaN inside the window (a value the reference raises on, api.py:218-221) makes the output NaN
-  int nans[4] = {0, 0, 0, 0};
-  {
-    const unsigned top[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-    for (int g = 0; g <= g_last; ++g) count_group<true>(k4[g], 4 * g, W, top, nans);
-  }
-  // occurrence number of the answer among its equals (stable ascending sort, position n - k): #(key >= answer) - k
+  float ans[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) ans[q] = val_of(pre[q]);
+  // occurrence number of the answer among its equals (stable ascending sort, position n - k): #(sample >= answer) - k
   int occ[4] = {0, 0, 0, 0};
   if (arg) {
-    int cge[4] = {0, 0, 0, 0};
-    for (int g = 0; g <= g_last; ++g) count_group<true>(k4[g], 4 * g, W, pre, cge);
+    float cge[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int g = 0; g <= g_last; ++g) count_group<true>(k4[g], 4 * g, W, ans, cge);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) occ[q] = cge[q] - k;
+    for (int q = 0; q < 4; ++q) occ[q] = (int)cge[q] - k;
   }
+  const bool any_nan = has_nan != 0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int t = tb + l0 + q;
     if (t >= T) break;
     long long last = (long long)t + a + W - 1;
     if (last > T - 1) last = T - 1;
-    const long long n = last - ((long long)t + a) + 1;
-    const bool has = n >= k;
-    out[trace * T + t] = nans[q] ? __int_as_float(0x7fc00000) : has ? val_of(pre[q]) : __int_as_float(0xff800000);
+    const int n = (int)(last - ((long long)t + a) + 1);
+    bool nan_in = false;
+    if (any_nan)  // rare: a NaN inside the window (a value the reference raises on, api.py:218-221) makes the output NaN
+      for (int d = 0; d < n; ++d) nan_in = nan_in || vals[l0 + q + d] != vals[l0 + q + d];
+    const bool has = n >= k && !nan_in;
+    out[trace * T + t] = nan_in ? __int_as_float(0x7fc00000) : has ? ans[q] : __int_as_float(0xff800000);
     if (arg) {
       int where = -1;
-      if (has && !nans[q]) {
+      if (has) {
         int seen = 0;
-        for (int d = 0; d < (int)n; ++d) {
-          if (keys[l0 + q + d] == pre[q]) {
+        for (int d = 0; d < n; ++d) {
+          if (vals[l0 + q + d] == ans[q]) {
             if (seen == occ[q]) {
               where = t + a + d;
               break;
