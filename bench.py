@@ -364,6 +364,53 @@ def open_ended_lines(dev) -> list:
     return out
 
 
+def ctstl_lines(dev) -> list:
+    """CT-STL's own operators on value traces through the public API (`B200CtstlSemantics`; not a BASELINE
+    configuration): the cumulative-time operator C^tau_[0,63] with k = 16 (a selection, bound by the compare rate: 32 (W + 3)
+    compares per output) and the Until with an exclusive prefix, values and gradients.  CUDA-event time per call, 3 calls after 2."""
+    import pystl_b200
+
+    B, T = 16384, 4096
+    g = torch.Generator(device=dev).manual_seed(11)
+    y = torch.randn(B, T, device=dev, generator=g).requires_grad_(True)
+    l = torch.randn(B, T, device=dev, generator=g).requires_grad_(True)
+    sem = pystl_b200.B200CtstlSemantics(delta=1.0)
+    cases = (("C^16_[0,63] y", 64, lambda: sem.cumulative_time_trace(y, (0, 63), tau=16.0)),
+             ("l U[0,24] y (exclusive prefix)", 0, lambda: sem.until_trace(l, y, (0, 24))))
+    out = []
+    for text, window, fn in cases:
+        try:
+            def both():
+                o = fn()
+                (gy,) = torch.autograd.grad(o.sum(), y)
+                return gy
+            for _ in range(2):
+                both()
+            torch.cuda.synchronize(dev)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            with torch.no_grad():
+                for _ in range(3):
+                    fn()
+            ev[1].record()
+            for _ in range(3):
+                both()
+            ev[2].record()
+            torch.cuda.synchronize(dev)
+            f_ms, g_ms = ev[0].elapsed_time(ev[1]) / 3, ev[1].elapsed_time(ev[2]) / 3
+            line = {"formula": text, "traces": B, "horizon": T, "values_ms": f_ms, "values_samples_per_s": B * T / (f_ms * 1e-3),
+                    "values_and_grad_ms": g_ms}
+            if window:
+                line["compares_per_s"] = 32.0 * (window + 3) * B * T / (f_ms * 1e-3)
+                line["bound"] = "issue rate of compare + count pairs (FSET + FADD): 148 SMs x 128 lanes x clock / 2"
+            out.append(line)
+        except Exception as exc:  # a secondary line never fails the bench
+            out.append({"formula": text, "error": f"{type(exc).__name__}: {exc}"[:200]})
+    del y, l
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_vectorised_throughput(cfg: str, budget_s: float, with_bwd: bool) -> dict:
     """Second reported CPU figure (baseline 2): the all-t, batched float64
     restatement with torch CPU ops on every host thread (oracle/dense.py mirrors the reference's
@@ -808,6 +855,7 @@ def run_b200(args) -> None:
                 sharded["semantics"][key] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     open_ended = open_ended_lines(dev) if (world == 1 and not args.no_others) else None
+    ctstl = ctstl_lines(dev) if (world == 1 and not args.no_others) else None
 
     cpu = None
     cpu_vec = None
@@ -846,6 +894,7 @@ def run_b200(args) -> None:
             "roofline": roofline,
             "cfg5_sharded": sharded,
             "open_ended": open_ended,
+            "ctstl": ctstl,
             "cpu_baseline": cpu,
             "cpu_baseline_vectorised": cpu_vec,
             "e2e": e2e,
