@@ -959,6 +959,10 @@ struct UntilOp {
     const int kmax = clip_kmax(c);
     float hneg[8], hlog[8], o0[8], o1[8];
     // one candidate of output i: prefix accumulator (pneg, plog), u = w0 / (sw cnt), right operand r (weighted by w1 / sw)
+    // The Or lift of a candidate z <= 0 is lg2(1 - z): the factors 1 - z >= 1 of up to FOUR candidates are multiplied and one
+    // logarithm taken of the product (|z| < 1e9 by the kernels' range assumption: the product stays below 1e36) -- 1.25 instead
+    // of 2 MUFU operations per candidate on a walk whose XU pipe was 75 % busy.  A positive candidate makes the product +inf.
+    float pr[8];
     auto cand = [&](int i, float pneg, float plog, float u, float rnegw, float rlogw, bool rpos) {
       const bool flag = plog == f_inf();  // some l <= 0: arithmetic prefix (agm.py:71)
       const float zA = fmaf(u, flag ? pneg : 0.f, rnegw);
@@ -966,7 +970,11 @@ struct UntilOp {
       const float z = (flag || !rpos) ? zA : zG;
       const bool pos = z > 0.f;  // agm.py:86
       o0[i] += pos ? z : 0.f;
-      o1[i] += pos ? f_inf() : fast_lg2(1.f - z);
+      pr[i] *= pos ? f_inf() : 1.f - z;
+    };
+    auto flush = [&](int i) {
+      o1[i] += fast_lg2(pr[i]);
+      pr[i] = 1.f;
     };
 
     {  // own chunk: triangular
@@ -986,12 +994,15 @@ struct UntilOp {
         float pn = 0.f, pl = 0.f;
         o0[i] = 0.f;
         o1[i] = 0.f;
+        pr[i] = 1.f;
 #pragma unroll
         for (int q = i; q < 8; ++q) {
           pn += ln[q];
           pl += ll[q];
           if (q - i >= UA && q - i <= UB && q <= kmax) cand(i, pn, pl, w0p * (1.f / (float)(q - i + 1)), rn[q], rl[q], ro[q] > 0.f);
+          if (q - i == 3) flush(i);  // at most four factors per product
         }
+        flush(i);
         hneg[i] = pn;
         hlog[i] = pl;
       }
@@ -1023,6 +1034,8 @@ struct UntilOp {
         for (int i = 0; i < 8; ++i)
           if (decltype(all)::value || (kq - i >= UA && kq - i <= UB)) cand(i, hneg[i] + Mn, hlog[i] + Ml, ik[k - i + 7], rn, rl, rpos);
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) flush(i);  // the group's (at most four) factors of every output
     };
 #pragma unroll
     for (int g = 2; g < KS / 4; ++g) group(g, BoolC<false>{});

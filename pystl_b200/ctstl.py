@@ -198,15 +198,48 @@ class B200CtstlSemantics(B200ClassicRobustSemantics):
             raise ValueError(f"temporal window is empty at t={t} for a horizon of {T} samples.")
         return out
 
+    def _mean_parts(self, formula: Any, sig: torch.Tensor):
+        """(sum of the outputs that exist, their number, the trace) -- all on the device, nothing synchronises."""
+        out = self._trace(formula, sig)
+        ok = ~torch.isnan(out)
+        total = torch.where(ok, out, torch.zeros_like(out)).sum(dim=1).sum(dtype=torch.float64)
+        return total, ok.sum().to(torch.float64), out
+
     def mean_robustness(self, formula: Any, signal: Any, *, group=None):
+        """Mean of the outputs the reference does not raise on (an output of -inf -- a ``C^tau_I`` window shorter than k -- makes
+        it -inf); with ``torch.distributed`` initialised over the whole sharded batch (one 16-byte all-reduce)."""
         if not _has_ct_node(formula):
             return super().mean_robustness(formula, signal, group=group)
-        raise NotImplementedError("the fused mean covers formulas without Until / CumulativeTime under CT-STL; take robustness_trace(...).mean()")
+        from .distributed import all_reduce_mean
+
+        sig, _, _ = self._prepare(signal)
+        with torch.no_grad():
+            total, count, _ = self._mean_parts(formula, sig)
+        return all_reduce_mean(torch.stack((total, count)), group=group)
 
     def mean_robustness_and_grad(self, formula: Any, signal: Any, *, group=None):
+        """``(mean robustness, d mean / d signal)``: the trace of ``robustness_trace`` and autograd through its kernels (the formula
+        is cut at its CT-STL nodes, so there is no single fused kernel); the count of valid outputs is reduced over ``group``
+        before the backward pass, the gradient itself needs no collective."""
         if not _has_ct_node(formula):
             return super().mean_robustness_and_grad(formula, signal, group=group)
-        raise NotImplementedError("the fused mean covers formulas without Until / CumulativeTime under CT-STL; use autograd on robustness_trace")
+        import torch.distributed as dist
+
+        from .distributed import all_reduce_mean
+
+        sig, squeeze, home = self._prepare(signal)
+        base = sig.detach().requires_grad_(True)
+        with torch.enable_grad():
+            total, count, _ = self._mean_parts(formula, base)
+        n_total = count.clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(n_total, op=dist.ReduceOp.SUM, group=group)
+        # (-inf outputs carry no gradient -- their selection index is -1 -- and make the mean -inf, which is what it is)
+        (grad,) = torch.autograd.grad(total, base, torch.where(n_total > 0, 1.0 / n_total, torch.zeros_like(n_total)))
+        mean = all_reduce_mean(torch.stack((total.detach(), count)), group=group)
+        if home != grad.device:
+            grad = grad.to(home)
+        return mean, (grad[0] if squeeze else grad)
 
     # ---- operator interface (lists of values at one t) ----------------------------------------------------------------
     def temporal_until(

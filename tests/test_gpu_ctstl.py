@@ -280,3 +280,27 @@ def test_operator_interface_lists():
     assert np.array_equal(sem.temporal_cumulative(bv, tau=1.5).cpu().numpy(), np.sort(y[:, :9], axis=1)[:, -3].astype(np.float32))
     assert np.array_equal(sem.boolean_and(bv).cpu().numpy(), y[:, :9].min(1).astype(np.float32))
     assert np.array_equal(sem.temporal_eventually(bv).cpu().numpy(), y[:, :9].max(1).astype(np.float32))
+
+
+def test_mean_robustness_and_grad_of_a_formula_with_ct_nodes():
+    x = affine_predicate("x", {0: 1.0}, 0.125)
+    y = affine_predicate("y", {1: -1.0, 0: 0.25}, 0.375)
+    phi = Or(Until(x, y, (1, 6)), CumulativeTime(And(x, Not(y)), (0, 5), tau=2.0))  # NaN at t = T - 1 (Until), no -inf (Or with the Until)
+    B, T = 5, 64
+    rng = np.random.default_rng(23)
+    sig = (rng.uniform(-0.5, 0.5, size=(B, 1, 2)) + 0.5 * rng.standard_normal((B, T, 2))).astype(np.float32)
+    sem = B200CtstlSemantics()
+    st = torch.tensor(sig, device=DEV)
+    mean, grad = sem.mean_robustness_and_grad(phi, st)
+    xr = st.clone().requires_grad_(True)
+    out = sem.robustness_trace(phi, xr)
+    ok = ~torch.isnan(out)
+    assert int(ok.sum()) == B * (T - 1)
+    ref = out[ok].double().mean()
+    (gref,) = torch.autograd.grad(ref, xr)
+    assert abs(float(mean) - float(ref)) <= 1e-6 * (1 + abs(float(ref)))
+    assert torch.allclose(grad, gref.float(), rtol=1e-5, atol=1e-7)
+    assert abs(float(sem.mean_robustness(phi, st)) - float(ref)) <= 1e-6 * (1 + abs(float(ref)))
+    # a window shorter than k at the end of every trace: the mean is -inf, the gradient stays finite
+    m2, g2 = sem.mean_robustness_and_grad(CumulativeTime(x, (0, 5), tau=3.0), st)
+    assert float(m2) == float("-inf") and bool(torch.isfinite(g2).all())
