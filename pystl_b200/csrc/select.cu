@@ -21,7 +21,16 @@
 // position n - k, i.e. occurrence number #(key >= answer) - k in window order -- what jnp.sort's gather does in the
 // reference's jax twin, jax/semantics.py:378-386).  Backward is a GATHER over the recorded indices: sample s collects from
 // the outputs t in [s - b_end, s - a] whose selection it was -- no atomics, deterministic.
+#if defined(PYSTL_SELECT_EMU)
+// Host build for the CPU test tier (tests/emu/select_emu.cpp): the kernels below are compiled with g++, every CUDA thread a fiber
+// of tests/emu/simt_host.h (barriers are cooperative yields).  Test infrastructure; the product is the CUDA build.
+#include "select_emu_shim.h"
+#else
 #include <cuda_runtime.h>
+#define SEL_KERNEL(NT) __global__ void __launch_bounds__(NT)
+#define SEL_DYN_SMEM(T, name) extern __shared__ __align__(16) T name[]
+#define SEL_SHARED(T, name) __shared__ T name
+#endif
 
 #include <cstdarg>
 #include <cstdio>
@@ -46,12 +55,8 @@ int sel_fail(int code, const char* fmt, ...) {
   return code;
 }
 
-// order-preserving key of a float: larger float <=> larger unsigned key, equal floats <=> equal keys (-0 is read as +0: a sort
-// does not tell them apart, and the routing among equal samples follows the sort)
-__device__ __forceinline__ unsigned key_of(float v) {
-  const unsigned u = __float_as_uint(v + 0.f);  // (-0) + (+0) = +0
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
+// The answer is found as an order-preserving 32-bit KEY (larger float <=> larger unsigned key: sign bit flipped for
+// non-negative floats, all bits for negative ones); val_of maps a key back to the float with that rank.
 __device__ __forceinline__ float val_of(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
 // one 128-bit group of samples against the four candidates: element e of the group sits at offset d0 + e from the thread's first
@@ -77,10 +82,10 @@ __device__ __forceinline__ void count_group(const float4 kv, int d0, int W, cons
 __device__ __forceinline__ float thr_of(unsigned key) { return val_of(key < 0x007fffffu ? 0x007fffffu : key); }
 
 // grid: one CTA per (trace, tile of kSelOut outputs), linearised
-__global__ void __launch_bounds__(kSelThreads) kth_window_fwd(const float* __restrict__ y, float* __restrict__ out, int* __restrict__ arg,
-                                                              int T, int a, int W, int k, int tiles_per_trace) {
-  extern __shared__ __align__(16) float vals[];
-  __shared__ int has_nan;
+SEL_KERNEL(kSelThreads) kth_window_fwd(const float* __restrict__ y, float* __restrict__ out, int* __restrict__ arg,
+                                       int T, int a, int W, int k, int tiles_per_trace) {
+  SEL_DYN_SMEM(float, vals);
+  SEL_SHARED(int, has_nan);
   const long long trace = blockIdx.x / tiles_per_trace;
   const int tb = (blockIdx.x - trace * tiles_per_trace) * kSelOut;  // first output of the tile
   const float* yt = y + trace * T;
@@ -162,8 +167,8 @@ __global__ void __launch_bounds__(kSelThreads) kth_window_fwd(const float* __res
 }
 
 // grad_y[b, s] = sum of grad_out[b, t] over the outputs t in [s - a - W + 1, s - a] that selected s
-__global__ void __launch_bounds__(256) kth_window_bwd(const int* __restrict__ arg, const float* __restrict__ grad_out,
-                                                      float* __restrict__ grad_y, long long B, int T, int a, int W) {
+SEL_KERNEL(256) kth_window_bwd(const int* __restrict__ arg, const float* __restrict__ grad_out,
+                               float* __restrict__ grad_y, long long B, int T, int a, int W) {
   const long long n = B * (long long)T;
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
     const long long trace = e / T;
@@ -181,8 +186,8 @@ __global__ void __launch_bounds__(256) kth_window_bwd(const int* __restrict__ ar
 
 // Until with the exclusive prefix: one thread per output walks its window (consecutive threads read consecutive samples).
 // key: 2 * sample + 1 when the value is an r, 2 * sample when it is an l, -1 where there is no value.
-__global__ void __launch_bounds__(256) ctstl_until_fwd(const float* __restrict__ l, const float* __restrict__ r, float* __restrict__ out,
-                                                       int* __restrict__ key, long long B, int T, int a, int b_end) {
+SEL_KERNEL(256) ctstl_until_fwd(const float* __restrict__ l, const float* __restrict__ r, float* __restrict__ out,
+                                int* __restrict__ key, long long B, int T, int a, int b_end) {
   const long long n = B * (long long)T;
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
     const long long trace = e / T;
@@ -221,9 +226,8 @@ __global__ void __launch_bounds__(256) ctstl_until_fwd(const float* __restrict__
 }
 
 // grad_l[s] collects from the outputs t in [s - b_end + 1, s] whose key is 2 s; grad_r[s] from t in [s - b_end, s - a], key 2 s + 1
-__global__ void __launch_bounds__(256) ctstl_until_bwd(const int* __restrict__ key, const float* __restrict__ grad_out,
-                                                       float* __restrict__ grad_l, float* __restrict__ grad_r, long long B, int T,
-                                                       int a, int b_end) {
+SEL_KERNEL(256) ctstl_until_bwd(const int* __restrict__ key, const float* __restrict__ grad_out,
+                                float* __restrict__ grad_l, float* __restrict__ grad_r, long long B, int T, int a, int b_end) {
   const long long n = B * (long long)T;
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
     const long long trace = e / T;
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(256) ctstl_until_bwd(const int* __restrict__ k
   }
 }
 
+#if !defined(PYSTL_SELECT_EMU)
 int check_shape(long long B, long long T) {
   if (B < 0 || T < 0 || T >= (1ll << 30)) return sel_fail(PYSTL_E_INVALID, "bad shape");
   return PYSTL_OK;
@@ -267,8 +272,10 @@ long long window_of(int a, int b_end, long long T) {
   return W;
 }
 
+#endif  // !PYSTL_SELECT_EMU
 }  // namespace
 
+#if !defined(PYSTL_SELECT_EMU)
 int ctstl_cumulative_forward(const float* y, int64_t B, int64_t T, int32_t a, int32_t b_end, int32_t k, float* out, int32_t* arg,
                              void* stream, char* err, size_t err_cap) {
   g_err = err;
@@ -351,5 +358,7 @@ int ctstl_until_backward(const int32_t* key, const float* grad_out, int64_t B, i
   if (e != cudaSuccess) return sel_fail(PYSTL_E_CUDA, "ctstl_until_bwd: %s", cudaGetErrorString(e));
   return PYSTL_OK;
 }
+
+#endif  // !PYSTL_SELECT_EMU
 
 }  // namespace pystl
