@@ -18,7 +18,10 @@ Besides the headline workload the line carries, driver-measured in the same run,
 ``other_kernels`` -- kernel time and roofline fraction of every BASELINE.json configuration
 (cfg1 .. cfg5, all five semantics for cfg5, forward and value-and-gradient) at its named size --
 and ``cfg5_sharded``: BASELINE config 5 as named, 2^20 traces x 2048 x 8 split over the N ranks
-(strong scaling) with the NCCL mean-robustness reduction.
+(strong scaling) with the NCCL mean-robustness reduction.  At N = 1 two more blocks time what is on the
+path but in no BASELINE configuration, through the public API: ``open_ended`` (operators without an
+interval end on traces longer than one tile, csrc/scan.cu) and ``ctstl`` (CT-STL's selection kernel
+and exclusive-prefix Until, csrc/select.cu).
 
 ``--impl reference`` times the CPU implementation of the same path on all host cores on a bounded
 sample of the same workload: for forward workloads the oracle port of the reference's
@@ -402,7 +405,7 @@ def ctstl_lines(dev) -> list:
                     "values_and_grad_ms": g_ms}
             if window:
                 line["compares_per_s"] = 32.0 * (window + 3) * B * T / (f_ms * 1e-3)
-                line["bound"] = "issue rate of compare + count pairs (FSET + FADD): 148 SMs x 128 lanes x clock / 2"
+                line["bound"] = "ALU pipe, one FSET per compare (= the issue rate of the FSET + FADD pairs): 148 SMs x 64 lanes x clock; ncu: ALU 85 %, issue 85 %"
             out.append(line)
         except Exception as exc:  # a secondary line never fails the bench
             out.append({"formula": text, "error": f"{type(exc).__name__}: {exc}"[:200]})
