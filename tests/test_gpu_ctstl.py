@@ -298,9 +298,43 @@ def test_mean_robustness_and_grad_of_a_formula_with_ct_nodes():
     assert int(ok.sum()) == B * (T - 1)
     ref = out[ok].double().mean()
     (gref,) = torch.autograd.grad(ref, xr)
+    ref = ref.detach()
     assert abs(float(mean) - float(ref)) <= 1e-6 * (1 + abs(float(ref)))
     assert torch.allclose(grad, gref.float(), rtol=1e-5, atol=1e-7)
     assert abs(float(sem.mean_robustness(phi, st)) - float(ref)) <= 1e-6 * (1 + abs(float(ref)))
     # a window shorter than k at the end of every trace: the mean is -inf, the gradient stays finite
     m2, g2 = sem.mean_robustness_and_grad(CumulativeTime(x, (0, 5), tau=3.0), st)
     assert float(m2) == float("-inf") and bool(torch.isfinite(g2).all())
+
+
+def test_vmap_and_functional_grad_through_the_ct_nodes():
+    """``torch.func.vmap`` over traces and ``vmap(grad)`` through the CT-STL ops (their batching rules, ops.py), like the formula kernels."""
+    x = affine_predicate("x", {0: 1.0}, 0.125)
+    y = affine_predicate("y", {1: -1.0, 0: 0.25}, 0.375)
+    phi = And(Until(x, y, (0, 7)), Not(CumulativeTime(Or(x, y), (1, 9), tau=3.0)), Eventually(CumulativeTime(y, (0, 4), tau=2.0), (0, 3)))
+    rng = np.random.default_rng(5)
+    sig = torch.tensor((rng.uniform(-0.5, 0.5, size=(6, 1, 2)) + 0.5 * rng.standard_normal((6, 80, 2))).astype(np.float32), device=DEV)
+    sem = B200CtstlSemantics()
+    want = sem.robustness_trace(phi, sig)
+    got = torch.func.vmap(lambda tr: sem.robustness_trace(phi, tr))(sig)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    ok = ~torch.isnan(want)
+    assert torch.equal(got[ok], want[ok])
+
+    def loss(tr):
+        out = sem.robustness_trace(phi, tr)
+        return torch.where(torch.isfinite(out), out, torch.zeros_like(out)).sum()
+
+    xs = sig.clone().requires_grad_(True)
+    loss(xs).backward()
+    g_f = torch.func.vmap(torch.func.grad(loss))(sig)
+    assert torch.allclose(g_f, xs.grad, rtol=1e-6, atol=1e-7)
+    # the value-trace ops directly, batched over a leading axis
+    yy = torch.randn(3, 4, 50, device=DEV)
+    ll = torch.randn(3, 4, 50, device=DEV)
+    f = lambda v: sem.cumulative_time_trace(v, (0, 5), tau=2.0)
+    assert torch.equal(torch.func.vmap(f)(yy), torch.stack([f(v) for v in yy]))
+    u = lambda a, b: sem.until_trace(a, b, (1, 6))
+    got_u, want_u = torch.func.vmap(u)(ll, yy), torch.stack([u(a, b) for a, b in zip(ll, yy)])
+    assert torch.equal(torch.isnan(got_u), torch.isnan(want_u)) and torch.equal(got_u[~torch.isnan(want_u)], want_u[~torch.isnan(want_u)])
+    assert torch.allclose(torch.func.vmap(u, in_dims=(None, 0))(ll[0], yy)[1], u(ll[0], yy[1]), rtol=0.0, atol=0.0, equal_nan=True)
