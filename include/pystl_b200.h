@@ -226,7 +226,9 @@ int pystl_b200_scatter_channels(const float* grad, int64_t rows, int32_t D, cons
  * tau_to_k :28-35): out[b, t] = k-th largest of y[b, t + a .. min(t + b_end, T - 1)] (window clipped as api.py:49-54; b_end < 0:
  * no end), k = ceil(tau / delta) >= 1 computed by the caller; -inf where the clipped window holds fewer than k samples.
  * arg[B, T] (may be NULL) records the sample the value came from (-1: none); among equal samples the one a stable ascending
- * sort puts at position n - k (jax/semantics.py:378-386).  Windows of at most 49152 samples (PYSTL_E_UNSUPPORTED beyond).
+ * sort puts at position n - k (jax/semantics.py:378-386; -0 and +0 are equal samples, a selected -0 is returned as +0).  A NaN
+ * inside a window (an operand value the reference raises on) makes that output NaN.  Windows of at most 49152 samples
+ * (PYSTL_E_UNSUPPORTED beyond).
  * backward: grad_y[B, T] (fully overwritten) = d sum(grad_out * out) / d y. */
 int pystl_b200_ctstl_cumulative_forward(const float* y, int64_t B, int64_t T, int32_t a, int32_t b_end, int32_t k, float* out,
                                         int32_t* arg, void* stream);
