@@ -75,6 +75,15 @@ bool is_wwin(const TInstr& in) { return in.op == T_WIN_WEIGHTED; }
 // instructions whose result needs one barrier (phase 1 | barrier | phase 2)
 bool is_staged(const TInstr& in) { return is_window(in) || is_scan(in) || is_until(in) || is_wwin(in); }
 
+// window formulas (no Until) under Smooth, value + gradient: latency bound, they gain from 27 instead of 24 resident warps
+constexpr int kWideSmoothThreads = 288;
+static bool wide_smooth_backward(const TileProgram& P) {
+  if (P.sem != SEM_SMOOTH) return false;
+  for (int i = 0; i < P.n_instr; ++i)
+    if (P.ins[i].op == T_UNTIL) return false;
+  return true;
+}
+
 struct Gen {
   const Lowered& lw;
   const TileProgram& P;
@@ -142,7 +151,14 @@ struct Gen {
 
   Gen(const Lowered& l, int D_, int nt_, int minb_, bool bwd_) : lw(l), P(l.prog), D(D_), nt(nt_), minb(minb_), bwd(bwd_) {}
   int kw() const { return P.sem == SEM_SMOOTH ? 1 : 2; }  // words of an adjoint coefficient
-  static bool relift() { const char* e = getenv("PYSTL_B200_RELIFT"); return e && atoi(e) != 0; }
+  // Smooth value-and-gradient kernels of window formulas on the wide tile (fused_geometry: 288 threads, 3 CTAs per SM at <= 75
+  // registers): the lifted operands are not kept in 8 registers per window for the adjoint, they are lifted again from the stash
+  // -- that is what lets 27 warps per SM run without spills (cfg2: 1.602 -> 1.555 ms).  PYSTL_B200_RELIFT = 0 / 1 overrides.
+  bool relift() const {
+    const char* e = getenv("PYSTL_B200_RELIFT");
+    if (e && *e) return atoi(e) != 0;
+    return bwd && nt == kWideSmoothThreads && wide_smooth_backward(P);
+  }
 
   int vw() const { return (P.sem == SEM_CUMULATIVE || src_bwd()) ? 2 : 1; }
   int aw() const { return src_bwd() ? 2 : ((P.sem == SEM_CLASSIC || P.sem == SEM_SMOOTH) ? 1 : 2); }
@@ -1474,6 +1490,9 @@ int fused_geometry(const Lowered& lw, int64_t B, int64_t T, int32_t D, int force
     double cost = (double)t.n_tiles * t.lext;
     if (nt > 256) cost *= 1.0 + 0.12 * (nt - 256) / 256.0;
     if (nt < 128) cost *= 1.05;
+    // (measured, cfg2 value + gradient: 3 tiles of 192 threads at 80 registers, 4 CTAs per SM: 1.602 ms; 2 tiles of 288 threads at
+    // <= 75 registers with the operands re-lifted, 3 CTAs per SM = 27 warps: 1.555 ms -- same padded work)
+    if (backward && nt == kWideSmoothThreads && t.n_tiles > 1 && wide_smooth_backward(P)) cost = (double)t.n_tiles * t.lext * 0.99;
     if (!have || cost < best * 0.995) {
       have = true;
       best = cost;

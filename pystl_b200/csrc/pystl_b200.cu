@@ -81,7 +81,7 @@ static int fused_minb(int nt, bool backward, const TileProgram& prog) {
   // B200 (profiles/README.md, sweep of CTA size x CTAs per SM on cfg2 / cfg3): smooth 80
   // (1.81 -> 1.77 ms), agm 72 (3.20 -> 2.86 ms), dgmsr 56 (4.05 -> 3.55 ms).
   int bwd_regs = 96;
-  if (sem == SEM_SMOOTH) bwd_regs = 80;
+  if (sem == SEM_SMOOTH) bwd_regs = (nt == 288 && !has_until) ? 72 : 80;  // (the wide tile of codegen.cpp: 3 CTAs of 9 warps, operands re-lifted)
   else if (sem == SEM_AGM) bwd_regs = 72;
   else if (sem == SEM_DGMSR) bwd_regs = 56;
   // the lockstep Until adjoints keep two sets of 8 running states and the hand-off numbers live: at 80 registers the
