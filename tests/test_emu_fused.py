@@ -23,6 +23,8 @@ def test_forward(case):
 
 
 # ---------------------------------------------------------------------------- backward
+import re  # noqa: E402
+
 import numpy as np  # noqa: E402
 
 from fused_cases import backward_cases  # noqa: E402
@@ -61,6 +63,23 @@ def test_smooth_extreme_dynamic_range_is_exact():
     g = rng.standard_normal((2, 300)).astype(np.float32).astype(np.float64)
     gb = fused_emu_lib.eval_backward(from_spec(spec), "smooth", sig, g, force_threads=64, **kw)
     check(gb.astype(np.float64), oracle_grad(spec, "smooth", kw, sig, g), "smooth", "cfg2/tau0.01", rtol, atol)
+
+
+@pytest.mark.parametrize("cfg, T, kw", [("cfg2", 4096, {}), ("cfg2", 2304, {"temperature": 0.05}), ("cfg3", 4096, {})],
+                         ids=["cfg2-T4096", "cfg2-T2304-tau0.05", "cfg3-T4096"])
+def test_smooth_wide_tile_default(cfg, T, kw):
+    """Smooth value + gradient of window formulas at BASELINE horizons with the geometry the product picks by itself: tiles of 288
+    threads whose lifted operands are lifted again from the stash for the adjoint (codegen.cpp: kWideSmoothThreads, Gen::relift)."""
+    spec = BASELINE_SPECS[cfg]
+    rng = np.random.default_rng(T)
+    sig = rng.standard_normal((2, T, 2)).astype(np.float32).astype(np.float64)
+    cf = fused_emu_lib.compile_formula(from_spec(spec), "smooth", 2, **kw)
+    src, _, _, _ = fused_emu_lib.prepare(cf, 2, T, 2, True, 0)
+    assert re.search(r"constexpr int NT = 288\b", src), "the wide tile is not the default at this shape any more: move the test"
+    g = rng.standard_normal((2, T)).astype(np.float32).astype(np.float64)
+    got = fused_emu_lib.eval_backward(from_spec(spec), "smooth", sig, g, **kw)
+    rtol, atol = grad_tol("smooth", kw)
+    check(got.astype(np.float64), oracle_grad(spec, "smooth", kw, sig, g), "smooth", f"{cfg}/T{T}/wide", rtol, atol)
 
 
 from fused_cases import cumulative_backward_cases  # noqa: E402
