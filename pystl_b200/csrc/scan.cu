@@ -17,7 +17,13 @@
 // with shuffles, and a second walk over the segment writes the outputs.  The trace is read twice and written once.
 // Smooth carries (max exponent, scaled sum) pairs, so no trace-wide shift is needed and the result is exact for any
 // temperature.  Classic records the arg-min / arg-max (first index on ties, like torch.min / max(dim)) for the gradient.
+#if defined(PYSTL_SCAN_EMU)
+// Host build for the CPU test tier (tests/emu/scan_emu.cpp): the kernels below are compiled with g++, every CUDA thread a fiber of
+// tests/emu/simt_host.h (warp collectives are cooperative yields).  Test infrastructure; the product is the CUDA build.
+#include "scan_emu_shim.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include <cstdarg>
 #include <cstdio>
@@ -498,6 +504,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) open_window_bwd_classic(c
   }
 }
 
+#if !defined(PYSTL_SCAN_EMU)
 thread_local char* g_err = nullptr;  // the caller's message buffer (pystl_b200.cu: pystl_b200_last_error)
 thread_local size_t g_err_cap = 0;
 int scan_fail(int code, const char* fmt, ...) {
@@ -508,6 +515,8 @@ int scan_fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+#endif  // !PYSTL_SCAN_EMU
 
 RP make_rp(float temperature, float eps, int p) {
   RP r{};
@@ -526,6 +535,7 @@ RP make_rp(float temperature, float eps, int p) {
   return r;
 }
 
+#if !defined(PYSTL_SCAN_EMU)
 int check(int semantics, int mode, int a, long long B, long long T, float temperature, float eps, int p) {
   if (semantics != SEM_CLASSIC && semantics != SEM_SMOOTH && semantics != SEM_AGM && semantics != SEM_DGMSR && semantics != SEM_CUMULATIVE)
     return scan_fail(PYSTL_E_INVALID, "unknown semantics %d", semantics);
@@ -536,9 +546,11 @@ int check(int semantics, int mode, int a, long long B, long long T, float temper
   if (semantics == SEM_DGMSR && (!(eps > 0.f) || p < 1)) return scan_fail(PYSTL_E_INVALID, "dgmsr needs eps > 0 and p >= 1");
   return PYSTL_OK;
 }
+#endif  // !PYSTL_SCAN_EMU
 
 }  // namespace
 
+#if !defined(PYSTL_SCAN_EMU)
 #define PYSTL_SCAN_DISPATCH(KERNEL, ...)                                               \
   do {                                                                                 \
     const unsigned grid = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);       \
@@ -797,5 +809,7 @@ int scatter_channels(const float* grad, int64_t rows, int32_t D, const int32_t* 
   if (e != cudaSuccess) return scan_fail(PYSTL_E_CUDA, "scatter_rows: %s", cudaGetErrorString(e));
   return PYSTL_OK;
 }
+
+#endif  // !PYSTL_SCAN_EMU
 
 }  // namespace pystl
