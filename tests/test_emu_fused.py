@@ -82,6 +82,25 @@ def test_smooth_wide_tile_default(cfg, T, kw):
     check(got.astype(np.float64), oracle_grad(spec, "smooth", kw, sig, g), "smooth", f"{cfg}/T{T}/wide", rtol, atol)
 
 
+@pytest.mark.parametrize("seed", [1, 3, 8, 20, 25, 34])
+def test_smooth_wide_tile_random_formulas(seed):
+    """Random nested window formulas (windows up to 150 samples, 1 - 3 channels, tau 1 / 0.25) at horizons where the product picks
+    the 288-thread tile by itself: halos on both sides of a tile, n-ary operators and negations with the re-lifted operands."""
+    rng = np.random.default_rng(9000 + seed)
+    D = int(rng.integers(1, 4))
+    spec = random_spec(rng, D, depth=3, max_b=int(rng.choice([24, 60, 150])), allow_open=False)
+    T = int(rng.choice([2100, 2304, 2500, 4096, 4608, 5000]))
+    kw = {"temperature": float(rng.choice([1.0, 0.25]))}
+    sig = mixed_signal(rng, 1, T, D)
+    cf = fused_emu_lib.compile_formula(from_spec(spec), "smooth", D, **kw)
+    src, _, _, _ = fused_emu_lib.prepare(cf, 1, T, D, True, 0)
+    assert not has_until(spec) and re.search(r"constexpr int NT = 288\b", src), "seed list out of date: pick seeds that land on the wide tile"
+    g = rng.uniform(0.25, 1.0, size=(1, T)).astype(np.float32).astype(np.float64)
+    got = fused_emu_lib.eval_backward(from_spec(spec), "smooth", sig, g, **kw)
+    rtol, atol = grad_tol("smooth", kw)
+    check(got.astype(np.float64), oracle_grad(spec, "smooth", kw, sig, g), "smooth", f"wide/seed{seed}/{spec}", rtol, atol)
+
+
 from fused_cases import cumulative_backward_cases  # noqa: E402
 
 CBWD = cumulative_backward_cases(light=True)
