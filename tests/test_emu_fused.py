@@ -28,7 +28,8 @@ import re  # noqa: E402
 import numpy as np  # noqa: E402
 
 from fused_cases import backward_cases  # noqa: E402
-from test_emu_backward import check, grad_tol, oracle_grad  # noqa: E402
+from parity_util import mixed_signal, random_spec  # noqa: E402
+from test_emu_backward import check, grad_tol, has_until, oracle_grad  # noqa: E402
 
 BWD = backward_cases(light=True)
 
@@ -189,8 +190,6 @@ def test_agm_dgmsr_until_and_weighted_backward(case):
 
 
 # ---------------------------------------------------------------------------- classic gradient (fused tier)
-from parity_util import mixed_signal, random_spec  # noqa: E402
-from test_emu_backward import has_until  # noqa: E402
 
 
 @pytest.mark.parametrize("seed", range(6))
