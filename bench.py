@@ -620,6 +620,9 @@ class Workload:
         line = {"workload": self.cfg, "kernel": name, "traces": self.B, "kernel_ms": ms_, "achieved": gbs, "frac": gbs / peak,
                 "algorithmic_bytes_per_sample": bytes_per_sample, "samples_per_s": self.B * self.T / (ms_ * 1e-3),
                 "traffic": traffic.get(f"{self.cfg}:{kind}<{self.sem_name}>")}
+        src = traffic.get("_source", {}).get(f"{self.cfg}:{kind}<{self.sem_name}>")
+        if src:
+            line["traffic_source"] = src  # which committed ncu capture the DRAM bytes come from
         floor = pipe_floor(self.cfg, kind, self.B, self.T, ms_, SM_MAX_MHZ)
         if floor:
             line["pipe_floor"] = floor  # the ceiling that binds this kernel; `frac` above stays the HBM fraction
