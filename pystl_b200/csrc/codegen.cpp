@@ -153,7 +153,7 @@ struct Gen {
   int kw() const { return P.sem == SEM_SMOOTH ? 1 : 2; }  // words of an adjoint coefficient
   // Smooth value-and-gradient kernels of window formulas on the wide tile (fused_geometry: 288 threads, 3 CTAs per SM at <= 75
   // registers): the lifted operands are not kept in 8 registers per window for the adjoint, they are lifted again from the stash
-  // -- that is what lets 27 warps per SM run without spills (cfg2: 1.602 -> 1.555 ms, as the default 1.560 ms).  PYSTL_B200_RELIFT = 0 / 1 overrides.
+  // -- that is what lets 27 warps per SM run at 72 registers with 16 bytes of stack (cfg2: 1.602 -> 1.555 ms, as the default 1.560 ms).  PYSTL_B200_RELIFT = 0 / 1 overrides.
   bool relift() const {
     const char* e = getenv("PYSTL_B200_RELIFT");
     if (e && *e) return atoi(e) != 0;
