@@ -697,6 +697,7 @@ int open_until_backward(int32_t semantics, int32_t a, const int32_t* key, const 
 // out[r, :] = [ signal[r, ch[0..n)] | col_0[r] .. col_{L-1}[r] ] for every row r = (trace, t): one pass (a torch.cat of an
 // indexed signal and stacked columns is three), and the adjoint: grad_signal[r, :] = 0 except the read channels, one
 // gradient column per leaf.
+#endif  // !PYSTL_SCAN_EMU
 constexpr int kMaxAssembleCols = 16, kMaxAssembleCh = 32, kMaxAssembleD = 64;
 struct AssembleArgs {
   const float* cols[kMaxAssembleCols];
@@ -741,6 +742,7 @@ __global__ void __launch_bounds__(256) scatter_rows(const float* __restrict__ gr
   }
 }
 
+#if !defined(PYSTL_SCAN_EMU)
 static int assemble_fill(AssembleArgs& a, int32_t D, const int32_t* channels, int32_t n_channels, int32_t n_cols) {
   if (n_channels > kMaxAssembleCh || n_cols > kMaxAssembleCols || D > kMaxAssembleD)
     return scan_fail(PYSTL_E_UNSUPPORTED, "at most %d read channels of %d and %d leaf columns", kMaxAssembleCh, kMaxAssembleD, kMaxAssembleCols);

@@ -76,3 +76,53 @@ extern "C" int pystl_scan_emu_until_backward(int a, const int* key, const float*
   run_grid(B, seg_body<true>, &S);
   return 0;
 }
+
+// ---- the tensor a formula kernel reads next to leaf channels (scan.cu: assemble_rows / scatter_rows), on a deliberately small grid
+namespace {
+struct AsmArgs { const float* signal; AssembleArgs a; float* out; long long rows; };
+template <int WT>
+void asm_body(void* p) { auto* A = static_cast<AsmArgs*>(p); assemble_rows<WT>(A->signal, A->a, A->out, A->rows); }
+struct SctArgs { const float* grad; AssembleArgs a; float* gs; long long rows; };
+template <int DT>
+void sct_body(void* p) { auto* A = static_cast<SctArgs*>(p); scatter_rows<DT>(A->grad, A->a, A->gs, A->rows); }
+void fill(AssembleArgs& a, int D, const int* channels, int n, int L) {  // (scan.cu: assemble_fill, minus the validation)
+  a.n = n, a.L = L, a.D = D;
+  for (int d = 0; d < kMaxAssembleD; ++d) a.inv[d] = -1;
+  for (int i = 0; i < n; ++i) a.ch[i] = channels[i], a.inv[channels[i]] = (signed char)i;
+}
+void run_rows(unsigned grid, void (*body)(void*), void* arg) {
+  scan_emu::grid_dim() = grid;
+  for (unsigned b = 0; b < grid; ++b) simt::run_cta((int)b, 0, 256, 16, body, arg);
+}
+}  // namespace
+
+extern "C" int pystl_scan_emu_assemble(const float* signal, long long rows, int D, const int* channels, int n, const float* const* cols,
+                                       int L, float* out, int templated) {
+  AsmArgs A{signal, AssembleArgs{}, out, rows};
+  fill(A.a, D, channels, n, L);
+  for (int j = 0; j < L; ++j) A.a.cols[j] = cols[j];
+  void (*body)(void*) = asm_body<0>;
+  if (templated) switch (n + L) {
+#define EMU_ASM(WT) case WT: body = asm_body<WT>; break;
+    EMU_ASM(1) EMU_ASM(2) EMU_ASM(3) EMU_ASM(4) EMU_ASM(5) EMU_ASM(6) EMU_ASM(7) EMU_ASM(8)
+#undef EMU_ASM
+    default: break;
+  }
+  run_rows(3, body, &A);
+  return 0;
+}
+extern "C" int pystl_scan_emu_scatter(const float* grad, long long rows, int D, const int* channels, int n, float* grad_signal,
+                                      float* const* gcols, int L, int templated) {
+  SctArgs A{grad, AssembleArgs{}, grad_signal, rows};
+  fill(A.a, D, channels, n, L);
+  for (int j = 0; j < L; ++j) A.a.gcols[j] = gcols[j];
+  void (*body)(void*) = sct_body<0>;
+  if (templated) switch (D) {
+#define EMU_SCT(DT) case DT: body = sct_body<DT>; break;
+    EMU_SCT(1) EMU_SCT(2) EMU_SCT(3) EMU_SCT(4) EMU_SCT(5) EMU_SCT(6) EMU_SCT(7) EMU_SCT(8)
+#undef EMU_SCT
+    default: break;
+  }
+  run_rows(3, body, &A);
+  return 0;
+}

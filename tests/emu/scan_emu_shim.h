@@ -9,11 +9,15 @@ struct ScanDim { unsigned x; };
 namespace scan_emu {
 inline ScanDim tidx() { return ScanDim{(unsigned)simt::tid()}; }
 inline ScanDim bidx() { return ScanDim{(unsigned)simt::bid_x()}; }
+inline unsigned& grid_dim() { static thread_local unsigned g = 1; return g; }
+inline ScanDim gdim() { return ScanDim{grid_dim()}; }
 inline float as_f(int v) { float f; memcpy(&f, &v, 4); return f; }
 inline int as_i(float f) { int v; memcpy(&v, &f, 4); return v; }
 }  // namespace scan_emu
 #define threadIdx (scan_emu::tidx())
 #define blockIdx (scan_emu::bidx())
+#define gridDim (scan_emu::gdim())
+#define __grid_constant__
 #define __global__
 #define __device__
 #define __forceinline__ inline

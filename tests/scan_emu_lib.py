@@ -88,3 +88,34 @@ def until_backward(a: int, key, g):
     gr = np.full((B, T), 123.0, dtype=np.float32)
     lib().pystl_scan_emu_until_backward(int(a), key.ctypes.data, g.ctypes.data, B, T, gl.ctypes.data, gr.ctypes.data)
     return gl, gr
+
+
+def _ptrs(arrays):
+    return (C.c_void_p * max(len(arrays), 1))(*[a.ctypes.data if a is not None else None for a in arrays])
+
+
+def assemble(signal, channels, cols, templated=True):
+    """out[r, :] = [signal[r, channels] | cols...] for rows r = (trace, t) -- pystl_b200_assemble_channels without the stream."""
+    signal = _f32(signal)
+    rows, D = signal.shape
+    cols = [_f32(c) for c in cols]
+    ch = np.ascontiguousarray(channels, dtype=np.int32)
+    out = np.full((rows, len(ch) + len(cols)), 123.0, dtype=np.float32)
+    h = lib()
+    h.pystl_scan_emu_assemble.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    h.pystl_scan_emu_assemble(signal.ctypes.data, rows, D, ch.ctypes.data, len(ch), _ptrs(cols), len(cols), out.ctypes.data, int(templated))
+    return out
+
+
+def scatter(grad, D, channels, n_cols, want_signal=True, skip_cols=(), templated=True):
+    """The adjoint: grad_signal[rows, D] (zeros in the channels nobody read) and one gradient column per leaf (None: not wanted)."""
+    grad = _f32(grad)
+    rows = grad.shape[0]
+    ch = np.ascontiguousarray(channels, dtype=np.int32)
+    gs = np.full((rows, D), 123.0, dtype=np.float32) if want_signal else None
+    gcols = [None if j in skip_cols else np.full(rows, 123.0, dtype=np.float32) for j in range(n_cols)]
+    h = lib()
+    h.pystl_scan_emu_scatter.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    h.pystl_scan_emu_scatter(grad.ctypes.data, rows, D, ch.ctypes.data, len(ch), None if gs is None else gs.ctypes.data, _ptrs(gcols), n_cols,
+                             int(templated))
+    return gs, gcols

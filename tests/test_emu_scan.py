@@ -137,3 +137,32 @@ def test_classical_until_without_an_end(B, T, a):
         want_sig = oracle_grad(("until", (0, None), X, Y), "classical", {}, sig, g[1:].astype(np.float64))
         if B > 1:
             check(np.stack([gl[1:], gr[1:]], -1).astype(np.float64), want_sig, "classical", f"scan/until/T{T}")
+
+
+@pytest.mark.parametrize("templated", [True, False])
+@pytest.mark.parametrize("rows,D,channels,L", [(1, 2, (0,), 1), (255, 4, (2, 0), 2), (1000, 3, (0, 1, 2), 1), (777, 8, (), 3), (2049, 5, (4, 1), 0),
+                                               (300, 9, (8, 0, 3), 7)])
+def test_assemble_and_scatter_rows(rows, D, channels, L, templated):
+    """The input of a parent formula kernel: the signal channels its predicates read next to one column per open-ended leaf, and the
+    adjoint (gradient columns back to the leaves, the read channels back into a zero-filled grad_signal); tile-stride loop on 3 CTAs."""
+    rng = np.random.default_rng(rows + D)
+    sig = rng.standard_normal((rows, D)).astype(np.float32)
+    cols = [rng.standard_normal(rows).astype(np.float32) for _ in range(L)]
+    out = emu.assemble(sig, channels, cols, templated)
+    want = np.concatenate([sig[:, list(channels)].reshape(rows, len(channels))] + [c[:, None] for c in cols], axis=1)
+    assert np.array_equal(out, want)
+    g = rng.standard_normal(out.shape).astype(np.float32)
+    skip = (1,) if L > 1 else ()
+    gs, gcols = emu.scatter(g, D, channels, L, want_signal=True, skip_cols=skip, templated=templated)
+    want_gs = np.zeros((rows, D), np.float32)
+    for i, d in enumerate(channels):
+        want_gs[:, d] = g[:, i]
+    assert np.array_equal(gs, want_gs)
+    for j in range(L):
+        if j in skip:
+            assert gcols[j] is None
+        else:
+            assert np.array_equal(gcols[j], g[:, len(channels) + j])
+    if L:  # no signal gradient wanted (the signal does not require grad)
+        _, only = emu.scatter(g, D, channels, L, want_signal=False, templated=templated)
+        assert all(np.array_equal(only[j], g[:, len(channels) + j]) for j in range(L))
