@@ -17,7 +17,8 @@ SRC = os.path.join(EMU, "scan_emu.cpp")
 DEPS = [SRC, os.path.join(EMU, "scan_emu_shim.h"), os.path.join(EMU, "simt_host.h"), os.path.join(ROOT, "include", "pystl_b200.h")] + [
     os.path.join(CSRC, f) for f in ("scan.cu", "tile_bwd.h", "tile_eval.h", "program.h")
 ]
-OUT = os.path.join(ROOT, "tests", "_emu", "libscan_emu.so")
+MUFU = os.environ.get("PYSTL_EMU_MUFU", "")  # perturb the transcendentals like the hardware approximations (tile_eval.h)
+OUT = os.path.join(ROOT, "tests", "_emu", f"libscan_emu{'_mufu' + MUFU if MUFU else ''}.so")
 SEM = {"classical": 0, "smooth": 1, "cumulative": 2, "agm": 3, "dgmsr": 4}  # include/pystl_b200.h: pystl_semantics_t
 _lib = None
 
@@ -28,7 +29,7 @@ def build(force: bool = False) -> str:
     if stale:
         tmp = f"{OUT}.{os.getpid()}.tmp"  # atomic publish: pytest-xdist workers may build concurrently
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-Wno-unused-function", "-I", EMU,
-                        "-I", CSRC, SRC, "-o", tmp], check=True)
+                        "-I", CSRC, SRC, "-o", tmp] + ([f"-DPYSTL_EMU_MUFU={int(MUFU)}"] if MUFU else []), check=True)
         os.replace(tmp, OUT)
     return OUT
 
